@@ -1,0 +1,13 @@
+"""ddiffpg_b200 -- B200-native (sm_100a) hot path of DDiffPG behind the reference's call surface.
+
+``DiffusionPolicy`` / ``DistributionalDoubleQ`` mirror ``ddiffpg/models``; ``update_target_action``,
+``optimizer_update`` and ``update_actor`` mirror ``ddiffpg/algo``.  Everything computes through
+``libddiffpg_b200.so`` (C ABI: ``include/ddiffpg_b200.h``); importing works without a GPU, calling does not.
+"""
+from .models import DiffusionPolicy, DistributionalDoubleQ, DiffusionNet, MLPNet  # noqa: F401
+from .algo import (FusedActorTrainer, HotPathMixin, optimizer_update, q_action_ascent_segments,  # noqa: F401
+                   soft_update, update_actor, update_target_action)
+
+__all__ = ["DiffusionPolicy", "DistributionalDoubleQ", "DiffusionNet", "MLPNet", "FusedActorTrainer",
+           "HotPathMixin", "optimizer_update", "q_action_ascent_segments", "soft_update", "update_actor",
+           "update_target_action"]

@@ -1,0 +1,193 @@
+"""Host-side mirror of the agent-level hot-path methods of ``ddiffpg/algo/ddiffpg.py`` and
+``ddiffpg/algo/ac_base.py`` (same names, argument meaning and return values).
+
+``update_target_action`` replaces ``AgentDDiffPG.update_target_action`` (ddiffpg.py:358-373);
+``optimizer_update`` is ``ActorCriticBase.optimizer_update`` (ac_base.py:83-92) verbatim in behaviour;
+``update_actor`` is ``AgentDDiffPG.update_actor`` (ddiffpg.py:353-356).  ``HotPathMixin`` bundles them so an
+agent class can inherit the accelerated versions without touching the rest of its code.
+"""
+from copy import deepcopy
+
+import torch
+from torch.nn.utils import clip_grad_norm_
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+from .models import _PackCache, pack_critics
+
+_ws_cache = {}
+
+
+def _workspace(name, nbytes, dev):
+    buf = _ws_cache.get((name, str(dev)))
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+        _ws_cache[(name, str(dev))] = buf
+    return buf
+
+
+def q_action_ascent_segments(critics, obs, action, seg_off, iters=20, lr=0.03, eps=1e-5, max_norm=1.0,
+                             betas=(0.9, 0.999), lim=1 - 1e-5, mean_counts=None, cache=None, return_norms=False):
+    """Run the reference's action-ascent loop for several mode segments in one launch sequence.
+
+    ``obs`` [B, O] / ``action`` [B, A] hold the rows of all modes, sorted by mode; ``seg_off`` (len
+    n_modes+1) delimits them; ``critics[m]`` is the critic of mode m.  ``action`` is updated IN PLACE like
+    the reference (ddiffpg.py:361-369).  Each segment is one reference call: its own 1/B_m in ``-Q.mean()``
+    (or ``mean_counts[m]`` when the segment is a shard of a larger batch) and its own clip norm.
+    Returns (mean|a| per segment [n_modes] tensor, optional pre-clip norms [n_modes, iters])."""
+    if max_norm is None:
+        max_norm = float("inf")
+    if not action.is_cuda or action.dtype != torch.float32 or not action.is_contiguous():
+        raise RuntimeError("action must be a contiguous fp32 CUDA tensor (it is updated in place)")
+    cache = cache if cache is not None else critics[0]._cache if len(critics) == 1 else _PackCache()
+    packed, shape, prec = pack_critics(list(critics), cache)
+    dev = packed.device
+    obs = obs.detach().to(device=dev, dtype=torch.float32).contiguous()
+    B = action.shape[0]
+    n_modes = len(critics)
+    seg_off = [int(v) for v in seg_off]
+    if len(seg_off) != n_modes + 1:
+        raise ValueError("seg_off must have n_modes + 1 entries")
+    counts = [seg_off[m + 1] - seg_off[m] for m in range(n_modes)] if mean_counts is None else list(mean_counts)
+    mean_abs = torch.zeros(n_modes, device=dev)
+    norms = torch.zeros(n_modes, iters, device=dev) if return_norms else None
+    if B:
+        with torch.cuda.device(dev):
+            ws_bytes = lib().ddp_q_ascent_workspace_bytes(shape, B, iters)
+            ws = _workspace("q_ascent", ws_bytes, dev)
+            check(lib().ddp_q_action_ascent(shape, ptr(packed), _lib.i64_array(seg_off), _lib.i64_array(counts),
+                                            ptr(obs), ptr(action), iters, lr, betas[0], betas[1], eps, max_norm,
+                                            lim, ptr(mean_abs), ptr(norms), B, prec, ptr(ws), ws_bytes,
+                                            stream_ptr()), "ddp_q_action_ascent")
+    return (mean_abs, norms) if return_norms else mean_abs
+
+
+def update_target_action(obs, action, critic, action_lr=0.03, update_times=20, max_grad_norm=1.0):
+    """``AgentDDiffPG.update_target_action(obs, action, critic)`` (ddiffpg.py:358-373).
+
+    ``action`` is clamped and updated in place; returns ``(mean |action| as a Python float, deep copy of the
+    new actions)`` like the reference.  The critic's ``requires_grad`` flags are left as the reference leaves
+    them (True on exit)."""
+    critic.requires_grad_(False)
+    mean_abs = q_action_ascent_segments([critic], obs, action, [0, action.shape[0]], iters=update_times,
+                                        lr=action_lr, eps=1e-5, max_norm=max_grad_norm)
+    update = deepcopy(action.detach())
+    critic.requires_grad_(True)
+    return mean_abs[0].item(), update
+
+
+def optimizer_update(optimizer, objective, max_grad_norm=1.0):
+    """``ActorCriticBase.optimizer_update`` (ac_base.py:83-92): zero_grad, backward, clip, step."""
+    optimizer.zero_grad(set_to_none=True)
+    objective.backward()
+    if max_grad_norm is not None:
+        grad_norm = clip_grad_norm_(parameters=optimizer.param_groups[0]["params"], max_norm=max_grad_norm)
+    else:
+        grad_norm = None
+    optimizer.step()
+    return grad_norm
+
+
+def update_actor(actor, actor_optimizer, obs, target_action, max_grad_norm=1.0, noise=None, timesteps=None):
+    """``AgentDDiffPG.update_actor`` (ddiffpg.py:353-356): returns (loss, pre-clip grad norm) as floats."""
+    actor_loss = actor.get_loss(obs, target_action, noise=noise, timesteps=timesteps)
+    grad_norm = optimizer_update(actor_optimizer, actor_loss, max_grad_norm)
+    return actor_loss.item(), grad_norm.item()
+
+
+@torch.no_grad()
+def soft_update(target_net, current_net, tau):
+    """``ddiffpg/utils/torch_util.py:9-12`` plus the cache invalidation ``.data`` writes cannot signal."""
+    for tar, cur in zip(target_net.parameters(), current_net.parameters()):
+        tar.data.copy_(cur.data * tau + tar.data * (1.0 - tau))
+    if hasattr(target_net, "mark_dirty"):
+        target_net.mark_dirty()
+
+
+class FusedActorTrainer:
+    """Whole ``update_actor`` on the device: loss + 12 gradients (one C-ABI call), optional data-parallel
+    gradient all-reduce, then clip + AdamW on a flat parameter vector (``ddp_clip_adamw_step``).
+
+    The module's parameters are re-pointed at slices of one flat fp32 buffer (state_dict keys, shapes and
+    values unchanged), so the flat gradient of ``ddp_actor_loss_fwd_bwd`` lines up with it and a single
+    NCCL all-reduce covers the whole model.  Hyper-parameters default to the reference's
+    ``torch.optim.AdamW(actor.parameters(), actor_lr)`` (ac_base.py:52) and ``max_grad_norm`` 1.0."""
+
+    def __init__(self, actor, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0,
+                 process_group=None):
+        self.actor = actor
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.max_grad_norm = float("inf") if max_grad_norm is None else max_grad_norm
+        self.group = process_group
+        params = actor._params()
+        dev = params[0].device
+        n = sum(p.numel() for p in params)
+        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        off = 0
+        for p in params:
+            self.flat[off:off + p.numel()].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_count = 0
+        self._norm = torch.zeros(1, device=dev)
+        self._scratch = torch.zeros(1, device=dev)
+        actor.mark_dirty()
+
+    def _check_flat(self):
+        off = 0
+        for p in self.actor._params():
+            if p.data_ptr() != self.flat.data_ptr() + 4 * off:
+                raise RuntimeError("actor parameters were re-allocated since FusedActorTrainer was built "
+                                   "(e.g. .to() or load into new storage); build a new trainer")
+            off += p.numel()
+
+    def step(self, state, action, noise=None, timesteps=None, global_batch=None):
+        """One training step; returns (loss, pre-clip grad norm) as 0-dim device tensors (no host sync).
+        ``global_batch``: rows over all data-parallel ranks (defaults to local rows x world size)."""
+        self._check_flat()
+        actor = self.actor
+        dev = self.flat.device
+        B = action.shape[0]
+        world = 1
+        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            world = torch.distributed.get_world_size(self.group)
+        if global_batch is None:
+            global_batch = B * world
+        if noise is None:
+            noise = torch.randn(action.shape, device=dev, dtype=torch.float32)
+        if timesteps is None:
+            timesteps = torch.randint(0, actor.diffusion_iter, (B,), device=dev)
+        loss, grads = actor._loss_and_grads(state, action, noise, timesteps,
+                                            inv_count=1.0 / (global_batch * actor.action_dim))
+        if world > 1:
+            # the one exchange step of the path: sum the flat gradient (and the loss) over NVLink
+            torch.distributed.all_reduce(grads, group=self.group)
+            torch.distributed.all_reduce(loss, group=self.group)
+        self.step_count += 1
+        with torch.cuda.device(dev):
+            check(lib().ddp_clip_adamw_step(ptr(self.flat), ptr(grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                            self.flat.numel(), self.step_count, self.lr, self.betas[0],
+                                            self.betas[1], self.eps, self.weight_decay, self.max_grad_norm,
+                                            ptr(self._norm), ptr(self._scratch), stream_ptr()),
+                  "ddp_clip_adamw_step")
+        actor.mark_dirty()
+        return loss, self._norm[0].clone()
+
+
+class HotPathMixin:
+    """Mix into an agent class (before ``ActorCriticBase``) to route its hot-path methods through the
+    kernels while keeping the reference's signatures; reads the same cfg keys
+    (cfg.diffusion.action_lr / update_times, cfg.algo.max_grad_norm)."""
+
+    def update_target_action(self, obs, action, critic):
+        return update_target_action(obs, action, critic, action_lr=self.cfg.diffusion.action_lr,
+                                    update_times=self.cfg.diffusion.update_times,
+                                    max_grad_norm=self.cfg.algo.max_grad_norm)
+
+    def optimizer_update(self, optimizer, objective):
+        return optimizer_update(optimizer, objective, self.cfg.algo.max_grad_norm)
+
+    def update_actor(self, obs, target_action):
+        return update_actor(self.actor, self.actor_optimizer, obs, target_action, self.cfg.algo.max_grad_norm)

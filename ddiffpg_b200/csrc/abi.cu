@@ -1,0 +1,190 @@
+// extern "C" entry points of libddiffpg_b200.so (declared in include/ddiffpg_b200.h).
+#include <string.h>
+#include "actor_layout.cuh"
+#include "q_layout.cuh"
+
+namespace ddp {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// implemented in the kernel translation units
+int pack_actor_fp32(const ActorLayout& L, const float* const p[12], float* out, cudaStream_t st);
+int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, cudaStream_t st);
+int actor_sample_fma(const ActorLayout& L, const float* pk, const float* state, const float* noise, float* out,
+                     long B, cudaStream_t st);
+int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state, const float* noise, float* out,
+                    long B, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t actor_sample_tc_workspace(const ActorLayout& L, long B);
+size_t actor_train_workspace(const ActorLayout& L, long B);
+int actor_train_fma(const ActorLayout& L, const float* pk, const float* const p[12], const float* state,
+                    const float* action, const float* noise, const int64_t* t, float inv_count, float* loss_out,
+                    float* grads, long B, void* ws, size_t ws_bytes, cudaStream_t st);
+int clip_adamw(float* p, float* g, float* m, float* v, size_t n, int step, float lr, float b1, float b2, float eps,
+               float wd, float max_norm, float* norm_out, float* scratch, cudaStream_t st);
+int pack_q_fp32(const QLayout& L, const float* const p[], float* out, cudaStream_t st);
+int q_forward_fma(const QLayout& L, const float* pk, const int64_t* seg_off, const float* obs, const float* act,
+                  float* qmin, float* p1, float* p2, float* dq_da, long B, cudaStream_t st);
+size_t q_ascent_workspace(const QLayout& L, long B, int iters);
+int q_ascent_fma(const QLayout& L, const float* pk, const int64_t* seg_off, const int64_t* seg_cnt, const float* obs,
+                 float* action, int iters, float lr, float b1, float b2, float eps, float max_norm, float lim,
+                 float* mean_abs, float* gnorm_out, long B, void* ws, size_t ws_bytes, cudaStream_t st);
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace ddp
+
+using namespace ddp;
+
+extern "C" {
+
+int ddp_abi_version(void) { return DDP_ABI_VERSION; }
+const char* ddp_last_error(void) { return g_err; }
+
+size_t ddp_actor_packed_bytes(const ddp_actor_shape* s, int precision) {
+    if (check_actor_shape(s) != DDP_OK) return 0;
+    return make_actor_layout(*s, precision).total_bytes;
+}
+
+int ddp_actor_pack(const ddp_actor_shape* s, const float* const params[12], void* packed, int precision,
+                   void* stream) {
+    int rc = check_actor_shape(s);
+    if (rc != DDP_OK) return rc;
+    if (!params || !packed) DDP_FAIL(DDP_ERR_ARG, "ddp_actor_pack: NULL argument");
+    for (int i = 0; i < 12; ++i)
+        if (!params[i]) DDP_FAIL(DDP_ERR_ARG, "ddp_actor_pack: params[%d] is NULL", i);
+    if (!aligned16(packed)) DDP_FAIL(DDP_ERR_ARG, "ddp_actor_pack: packed buffer must be 16-byte aligned");
+    if (precision != DDP_FP32 && precision != DDP_BF16) DDP_FAIL(DDP_ERR_ARG, "unknown precision %d", precision);
+    ActorLayout L = make_actor_layout(*s, precision);
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = pack_actor_fp32(L, params, (float*)packed, st);
+    if (rc != DDP_OK) return rc;
+    if (precision == DDP_BF16) return pack_actor_tc(L, params, packed, st);
+    return DDP_OK;
+}
+
+size_t ddp_actor_sample_workspace_bytes(const ddp_actor_shape* s, long B, int precision) {
+    if (check_actor_shape(s) != DDP_OK) return 0;
+    if (precision != DDP_BF16) return 0;
+    return actor_sample_tc_workspace(make_actor_layout(*s, precision), B);
+}
+
+int ddp_actor_sample(const ddp_actor_shape* s, const void* packed, const float* state, const float* noise,
+                     float* action_out, long B, int precision, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_actor_shape(s);
+    if (rc != DDP_OK) return rc;
+    if (B < 0) DDP_FAIL(DDP_ERR_SHAPE, "ddp_actor_sample: negative batch");
+    if (B == 0) return DDP_OK;
+    if (!packed || !state || !noise || !action_out) DDP_FAIL(DDP_ERR_ARG, "ddp_actor_sample: NULL argument");
+    ActorLayout L = make_actor_layout(*s, precision);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == DDP_FP32) return actor_sample_fma(L, (const float*)packed, state, noise, action_out, B, st);
+    if (precision == DDP_BF16) return actor_sample_tc(L, packed, state, noise, action_out, B, ws, ws_bytes, st);
+    DDP_FAIL(DDP_ERR_ARG, "unknown precision %d", precision);
+}
+
+size_t ddp_actor_grad_count(const ddp_actor_shape* s) {
+    if (check_actor_shape(s) != DDP_OK) return 0;
+    return actor_grad_offsets(*s).off[12];
+}
+
+size_t ddp_actor_train_workspace_bytes(const ddp_actor_shape* s, long B, int precision) {
+    if (check_actor_shape(s) != DDP_OK || B <= 0) return 0;
+    return actor_train_workspace(make_actor_layout(*s, precision), B);
+}
+
+int ddp_actor_loss_fwd_bwd(const ddp_actor_shape* s, const void* packed, const float* const params[12],
+                           const float* state, const float* action, const float* noise, const int64_t* t,
+                           float inv_count, float* loss_out, float* grads_flat, long B, int precision, void* ws,
+                           size_t ws_bytes, void* stream) {
+    int rc = check_actor_shape(s);
+    if (rc != DDP_OK) return rc;
+    if (B <= 0) DDP_FAIL(DDP_ERR_SHAPE, "ddp_actor_loss_fwd_bwd: batch must be positive");
+    if (!packed || !params || !state || !action || !noise || !t || !loss_out || !grads_flat || !ws)
+        DDP_FAIL(DDP_ERR_ARG, "ddp_actor_loss_fwd_bwd: NULL argument");
+    if (precision != DDP_FP32) DDP_FAIL(DDP_ERR_UNSUPPORTED, "training step: only DDP_FP32 is implemented");
+    ActorLayout L = make_actor_layout(*s, precision);
+    if (ws_bytes < actor_train_workspace(L, B)) DDP_FAIL(DDP_ERR_ARG, "ddp_actor_loss_fwd_bwd: workspace too small");
+    if (!aligned16(ws) || !aligned16(grads_flat)) DDP_FAIL(DDP_ERR_ARG, "workspace/grads must be 16-byte aligned");
+    return actor_train_fma(L, (const float*)packed, params, state, action, noise, t, inv_count, loss_out, grads_flat,
+                           B, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int ddp_clip_adamw_step(float* params_flat, float* grads_flat, float* exp_avg, float* exp_avg_sq, size_t n, int step,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,
+                        float* norm_out, float* scratch, void* stream) {
+    if (!params_flat || !grads_flat || !exp_avg || !exp_avg_sq || !norm_out || !scratch)
+        DDP_FAIL(DDP_ERR_ARG, "ddp_clip_adamw_step: NULL argument");
+    if (step < 1) DDP_FAIL(DDP_ERR_ARG, "ddp_clip_adamw_step: step is 1-based");
+    if (n == 0) return DDP_OK;
+    return clip_adamw(params_flat, grads_flat, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, weight_decay,
+                      max_norm, norm_out, scratch, (cudaStream_t)stream);
+}
+
+size_t ddp_q_packed_bytes(const ddp_q_shape* s, int precision) {
+    if (check_q_shape(s) != DDP_OK) return 0;
+    return make_q_layout(*s, precision).total_bytes;
+}
+
+int ddp_q_pack(const ddp_q_shape* s, const float* const params[], void* packed, int precision, void* stream) {
+    int rc = check_q_shape(s);
+    if (rc != DDP_OK) return rc;
+    if (!params || !packed) DDP_FAIL(DDP_ERR_ARG, "ddp_q_pack: NULL argument");
+    for (int i = 0; i < 16 * s->n_modes; ++i)
+        if (!params[i]) DDP_FAIL(DDP_ERR_ARG, "ddp_q_pack: params[%d] is NULL", i);
+    if (precision != DDP_FP32) DDP_FAIL(DDP_ERR_UNSUPPORTED, "critic: only DDP_FP32 is implemented");
+    return pack_q_fp32(make_q_layout(*s, precision), params, (float*)packed, (cudaStream_t)stream);
+}
+
+static int check_segments(const ddp_q_shape* s, const int64_t* seg_off, long B) {
+    if (!seg_off) DDP_FAIL(DDP_ERR_ARG, "seg_off is NULL");
+    if (seg_off[0] != 0 || seg_off[s->n_modes] != B) DDP_FAIL(DDP_ERR_SHAPE, "seg_off must start at 0 and end at B");
+    for (int m = 0; m < s->n_modes; ++m)
+        if (seg_off[m + 1] < seg_off[m]) DDP_FAIL(DDP_ERR_SHAPE, "seg_off must be non-decreasing");
+    return DDP_OK;
+}
+
+int ddp_q_forward(const ddp_q_shape* s, const void* packed, const int64_t* seg_off, const float* obs,
+                  const float* act, float* q_min_out, float* p1_out, float* p2_out, float* dq_da_out, long B,
+                  int precision, void* stream) {
+    int rc = check_q_shape(s);
+    if (rc != DDP_OK) return rc;
+    if (B < 0) DDP_FAIL(DDP_ERR_SHAPE, "ddp_q_forward: negative batch");
+    if (B == 0) return DDP_OK;
+    if (!packed || !obs || !act) DDP_FAIL(DDP_ERR_ARG, "ddp_q_forward: NULL argument");
+    if (precision != DDP_FP32) DDP_FAIL(DDP_ERR_UNSUPPORTED, "critic: only DDP_FP32 is implemented");
+    rc = check_segments(s, seg_off, B);
+    if (rc != DDP_OK) return rc;
+    return q_forward_fma(make_q_layout(*s, precision), (const float*)packed, seg_off, obs, act, q_min_out, p1_out,
+                         p2_out, dq_da_out, B, (cudaStream_t)stream);
+}
+
+size_t ddp_q_ascent_workspace_bytes(const ddp_q_shape* s, long B, int iters) {
+    if (check_q_shape(s) != DDP_OK || B <= 0 || iters <= 0) return 0;
+    return q_ascent_workspace(make_q_layout(*s, DDP_FP32), B, iters);
+}
+
+int ddp_q_action_ascent(const ddp_q_shape* s, const void* packed, const int64_t* seg_off,
+                        const int64_t* seg_mean_count, const float* obs, float* action_inout, int iters, float lr,
+                        float beta1, float beta2, float eps, float max_norm, float lim, float* mean_abs_out,
+                        float* gnorm_out, long B, int precision, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_q_shape(s);
+    if (rc != DDP_OK) return rc;
+    if (B <= 0 || iters <= 0) DDP_FAIL(DDP_ERR_SHAPE, "ddp_q_action_ascent: B and iters must be positive");
+    if (!packed || !obs || !action_inout || !mean_abs_out || !ws || !seg_mean_count)
+        DDP_FAIL(DDP_ERR_ARG, "ddp_q_action_ascent: NULL argument");
+    if (precision != DDP_FP32) DDP_FAIL(DDP_ERR_UNSUPPORTED, "critic: only DDP_FP32 is implemented");
+    rc = check_segments(s, seg_off, B);
+    if (rc != DDP_OK) return rc;
+    QLayout L = make_q_layout(*s, precision);
+    if (ws_bytes < q_ascent_workspace(L, B, iters)) DDP_FAIL(DDP_ERR_ARG, "ddp_q_action_ascent: workspace too small");
+    return q_ascent_fma(L, (const float*)packed, seg_off, seg_mean_count, obs, action_inout, iters, lr, beta1, beta2,
+                        eps, max_norm, lim, mean_abs_out, gnorm_out, B, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,416 @@
+// H2, fp32 warp-level FMA path: mode-segmented distributional double-Q forward, its analytic
+// gradient with respect to the action, and the Adam action-ascent loop.
+//
+// Reference semantics (paths relative to the reference repo):
+//   MLPNet / create_simple_mlp (ELU)                 ddiffpg/models/mlp.py:13-35
+//   DistributionalDoubleQ.get_q1_q2 / get_q_min      ddiffpg/models/mlp.py:143-151
+//   AgentDDiffPG.update_target_action                ddiffpg/algo/ddiffpg.py:358-373
+//   ActorCriticBase.optimizer_update (clip + step)   ddiffpg/algo/ac_base.py:83-92
+// One CTA owns a tile of rows of ONE mode segment; both nets' activations stay in shared memory
+// between the forward and the hand-written backward (the critic weights are frozen, :359, so only
+// dX products are needed).  The two cross-row couplings of the reference -- the 1/B of Q.mean() and
+// the global L2 clip norm -- are a per-segment scalar each, reduced with one atomic per CTA.
+#include <math.h>
+#include "q_layout.cuh"
+
+namespace ddp {
+
+struct SegTable {
+    long off[kMaxModes + 1];         // row offsets per mode
+    long tile0[kMaxModes + 1];       // first tile index per mode
+    float inv_cnt[kMaxModes];        // 1 / rows the reference's Q.mean() averages over
+    int n_modes;
+};
+
+struct QArgs {
+    const float* packed; size_t mode_stride;
+    QNetLayout net[2]; size_t z;
+    int O, A, atoms, h1, h2, h3, K1p, A4, atomsP;
+    int ks1, ks2, ks3, ks4, kb4, kb3, kb2, kb1;
+};
+
+static QArgs make_qargs(const QLayout& L, const float* pk, int NT) {
+    QArgs a;
+    a.packed = pk; a.mode_stride = L.mode_stride; a.net[0] = L.net[0]; a.net[1] = L.net[1]; a.z = L.z;
+    a.O = L.O; a.A = L.A; a.atoms = L.atoms; a.h1 = L.h1; a.h2 = L.h2; a.h3 = L.h3;
+    a.K1p = L.K1p; a.A4 = L.A4; a.atomsP = L.atomsP;
+    a.ks1 = pick_ksplit(L.h1, NT); a.ks2 = pick_ksplit(L.h2, NT); a.ks3 = pick_ksplit(L.h3, NT);
+    a.ks4 = pick_ksplit(L.atomsP, NT);
+    a.kb4 = pick_ksplit(L.h3, NT); a.kb3 = pick_ksplit(L.h2, NT); a.kb2 = pick_ksplit(L.h1, NT);
+    a.kb1 = pick_ksplit(L.A4, NT);
+    return a;
+}
+
+__global__ void q_support_kernel(float* __restrict__ z, int atoms, int atomsP, float v_min, float v_max) {
+    // torch.linspace (mlp.py:141): filled from both ends with step = (end-start)/(steps-1)
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= atomsP) return;
+    float step = (v_max - v_min) / (float)(atoms - 1);
+    float v = 0.f;
+    if (i < atoms) v = (i < atoms / 2) ? v_min + step * (float)i : v_max - step * (float)(atoms - i - 1);
+    z[i] = v;
+}
+
+// out[r][c] = src[r*ld + off + c] for c < cols, 0 for cols <= c < ldo
+__global__ void submatrix_pack_kernel(const float* __restrict__ src, int ld, int off, int rows, int cols, int ldo,
+                                      float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * ldo) return;
+    int r = i / ldo, c = i % ldo;
+    out[i] = c < cols ? src[(size_t)r * ld + off + c] : 0.f;
+}
+
+int pack_q_fp32(const QLayout& L, const float* const p[], float* out, cudaStream_t st) {
+    auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
+    const int in1 = L.O + L.A;
+    for (int m = 0; m < L.n_modes; ++m) {
+        float* base = out + (size_t)m * L.mode_stride;
+        for (int j = 0; j < 2; ++j) {
+            const float* const* q = p + 16 * m + 8 * j;       // W1,b1,W2,b2,W3,b3,W4,b4 of net j
+            const QNetLayout& n = L.net[j];
+            transpose_pack_kernel<<<blocks((size_t)L.K1p * L.h1), 256, 0, st>>>(q[0], in1, 0, in1, L.K1p, L.h1, L.h1, base + n.wt1);
+            transpose_pack_kernel<<<blocks((size_t)L.h1 * L.h2), 256, 0, st>>>(q[2], L.h1, 0, L.h1, L.h1, L.h2, L.h2, base + n.wt2);
+            transpose_pack_kernel<<<blocks((size_t)L.h2 * L.h3), 256, 0, st>>>(q[4], L.h2, 0, L.h2, L.h2, L.h3, L.h3, base + n.wt3);
+            transpose_pack_kernel<<<blocks((size_t)L.h3 * L.atomsP), 256, 0, st>>>(q[6], L.h3, 0, L.h3, L.h3, L.atoms, L.atomsP, base + n.wt4);
+            copy_pad_kernel<<<blocks(L.h1), 256, 0, st>>>(q[1], L.h1, L.h1, base + n.b1);
+            copy_pad_kernel<<<blocks(L.h2), 256, 0, st>>>(q[3], L.h2, L.h2, base + n.b2);
+            copy_pad_kernel<<<blocks(L.h3), 256, 0, st>>>(q[5], L.h3, L.h3, base + n.b3);
+            copy_pad_kernel<<<blocks(L.atomsP), 256, 0, st>>>(q[7], L.atoms, L.atomsP, base + n.b4);
+            // backward operands: dX = dY . W, streamed as [contraction = out features][in features]
+            copy_pad_kernel<<<blocks((size_t)L.atomsP * L.h3), 256, 0, st>>>(q[6], L.atoms * L.h3, L.atomsP * L.h3, base + n.w4b);
+            copy_pad_kernel<<<blocks((size_t)L.h3 * L.h2), 256, 0, st>>>(q[4], L.h3 * L.h2, L.h3 * L.h2, base + n.w3b);
+            copy_pad_kernel<<<blocks((size_t)L.h2 * L.h1), 256, 0, st>>>(q[2], L.h2 * L.h1, L.h2 * L.h1, base + n.w2b);
+            submatrix_pack_kernel<<<blocks((size_t)L.h1 * L.A4), 256, 0, st>>>(q[0], in1, L.O, L.h1, L.A, L.A4, base + n.w1a);
+        }
+        q_support_kernel<<<1, 64, 0, st>>>(base + L.z, L.atoms, L.atomsP, L.v_min, L.v_max);
+    }
+    DDP_LAUNCH_CHECK("critic pack kernels");
+    return DDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward (+ optional backward to the action) for one row tile.
+//   MODE 0: inference outputs (q_min, p1, p2, dq_da) -- get_q1_q2 / get_q_min and their autograd.
+//   MODE 1: one ascent iteration: g = -inv_cnt * d min(Q1,Q2)/da, plus sum g^2 into gsq[mode].
+template <int RT, int NT, int MODE>
+__global__ void __launch_bounds__(NT) q_tile_kernel(QArgs a, SegTable seg, const float* __restrict__ obs,
+                                                    const float* __restrict__ act, float* __restrict__ qmin_out,
+                                                    float* __restrict__ p1_out, float* __restrict__ p2_out,
+                                                    float* __restrict__ grad_out, float* __restrict__ gsq) {
+    extern __shared__ __align__(16) float smem[];
+    const int ld1 = a.h1 + 4, ld2 = a.h2 + 4, ld3 = a.h3 + 4, ldl = a.atomsP;
+    float* in1 = smem;                                  // [RT][K1p] = [obs | act | 0]
+    float* A1 = in1 + RT * a.K1p;                       // [2][RT][ld1]
+    float* A2 = A1 + 2 * RT * ld1;                      // [2][RT][ld2]
+    float* A3 = A2 + 2 * RT * ld2;                      // [2][RT][ld3]
+    float* LG = A3 + 2 * RT * ld3;                      // [2][RT][ldl] logits -> probs -> dlogits
+    float* QV = LG + 2 * RT * ldl;                      // [2][RT]
+    float* GA = QV + 2 * RT;                            // [2][RT][A4] per-net action gradients
+    __shared__ float red[NT / 32];
+
+    // locate the mode segment of this tile
+    int m = 0;
+    while (m + 1 < seg.n_modes && (long)blockIdx.x >= seg.tile0[m + 1]) ++m;
+    const long row0 = seg.off[m] + ((long)blockIdx.x - seg.tile0[m]) * RT;
+    const long row_end = seg.off[m + 1];
+    const float* base = a.packed + (size_t)m * a.mode_stride;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < RT * a.K1p; i += NT) {
+        int r = i / a.K1p, c = i % a.K1p;
+        long row = row0 + r;
+        float v = 0.f;
+        if (row < row_end) {
+            if (c < a.O) v = obs[row * a.O + c];
+            else if (c < a.O + a.A) v = act[row * a.A + (c - a.O)];
+        }
+        in1[i] = v;
+    }
+    __syncthreads();
+
+    for (int j = 0; j < 2; ++j) {
+        const QNetLayout& n = a.net[j];
+        float* a1 = A1 + j * RT * ld1; float* a2 = A2 + j * RT * ld2; float* a3 = A3 + j * RT * ld3;
+        float* lg = LG + j * RT * ldl;
+        const float* b1 = base + n.b1; const float* b2 = base + n.b2; const float* b3 = base + n.b3;
+        const float* b4 = base + n.b4;
+        tile_linear<RT, NT>(base + n.wt1, a.h1, a.K1p >> 2, a.h1, in1, a.K1p, a.ks1, [&](int r, int n0, float4 v) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + n0));
+            *reinterpret_cast<float4*>(a1 + r * ld1 + n0) =
+                make_float4(elu_f(v.x + bb.x), elu_f(v.y + bb.y), elu_f(v.z + bb.z), elu_f(v.w + bb.w));
+        });
+        __syncthreads();
+        tile_linear<RT, NT>(base + n.wt2, a.h2, a.h1 >> 2, a.h2, a1, ld1, a.ks2, [&](int r, int n0, float4 v) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + n0));
+            *reinterpret_cast<float4*>(a2 + r * ld2 + n0) =
+                make_float4(elu_f(v.x + bb.x), elu_f(v.y + bb.y), elu_f(v.z + bb.z), elu_f(v.w + bb.w));
+        });
+        __syncthreads();
+        tile_linear<RT, NT>(base + n.wt3, a.h3, a.h2 >> 2, a.h3, a2, ld2, a.ks3, [&](int r, int n0, float4 v) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(b3 + n0));
+            *reinterpret_cast<float4*>(a3 + r * ld3 + n0) =
+                make_float4(elu_f(v.x + bb.x), elu_f(v.y + bb.y), elu_f(v.z + bb.z), elu_f(v.w + bb.w));
+        });
+        __syncthreads();
+        tile_linear<RT, NT>(base + n.wt4, a.atomsP, a.h3 >> 2, a.atomsP, a3, ld3, a.ks4, [&](int r, int n0, float4 v) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(b4 + n0));
+            *reinterpret_cast<float4*>(lg + r * ldl + n0) = make_float4(v.x + bb.x, v.y + bb.y, v.z + bb.z, v.w + bb.w);
+        });
+        __syncthreads();
+    }
+
+    // softmax over atoms and expectation: one warp per (net, row)
+    const float* zs = base + a.z;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int pr = warp; pr < 2 * RT; pr += NT / 32) {
+        float* lg = LG + pr * ldl;                      // pr = j*RT + r, rows are contiguous
+        const int c0 = lane, c1 = lane + 32;
+        float l0 = c0 < a.atoms ? lg[c0] : -INFINITY, l1 = c1 < a.atoms ? lg[c1] : -INFINITY;
+        float mx = warp_max(fmaxf(l0, l1));
+        float e0 = c0 < a.atoms ? expf(l0 - mx) : 0.f, e1 = c1 < a.atoms ? expf(l1 - mx) : 0.f;
+        float sum = warp_sum(e0 + e1);
+        float p0 = e0 / sum, p1 = e1 / sum;
+        float q = warp_sum((c0 < a.atoms ? p0 * zs[c0] : 0.f) + (c1 < a.atoms ? p1 * zs[c1] : 0.f));
+        if (c0 < a.atomsP) lg[c0] = p0;
+        if (c1 < a.atomsP) lg[c1] = p1;
+        if (lane == 0) QV[pr] = q;
+    }
+    __syncthreads();
+
+    if (MODE == 0) {
+        for (int i = tid; i < RT; i += NT) {
+            long row = row0 + i;
+            if (row < row_end && qmin_out) qmin_out[row] = fminf(QV[i], QV[RT + i]);
+        }
+        for (int i = tid; i < 2 * RT * a.atoms; i += NT) {
+            int j = i / (RT * a.atoms), rem = i % (RT * a.atoms), r = rem / a.atoms, c = rem % a.atoms;
+            long row = row0 + r;
+            float* dst = j == 0 ? p1_out : p2_out;
+            if (row < row_end && dst) dst[row * a.atoms + c] = LG[(j * RT + r) * ldl + c];
+        }
+        if (!grad_out) return;                          // uniform: no barrier is skipped by a subset
+    }
+
+    // d min(Q1,Q2) / d logits: only the smaller net carries gradient (ties split, as torch.min does)
+    for (int i = tid; i < 2 * RT * ldl; i += NT) {
+        int j = i / (RT * ldl), rem = i % (RT * ldl), r = rem / ldl, c = rem % ldl;
+        float q1 = QV[r], q2 = QV[RT + r];
+        float w = (q1 == q2) ? 0.5f : ((j == 0) == (q1 < q2) ? 1.f : 0.f);
+        float qj = j == 0 ? q1 : q2;
+        float p = LG[i];
+        LG[i] = (c < a.atoms && row0 + r < row_end) ? w * p * (zs[c] - qj) : 0.f;
+    }
+    __syncthreads();
+
+    for (int j = 0; j < 2; ++j) {
+        const QNetLayout& n = a.net[j];
+        float* a1 = A1 + j * RT * ld1; float* a2 = A2 + j * RT * ld2; float* a3 = A3 + j * RT * ld3;
+        float* lg = LG + j * RT * ldl; float* ga = GA + j * RT * a.A4;
+        tile_linear<RT, NT>(base + n.w4b, a.h3, a.atomsP >> 2, a.h3, lg, ldl, a.kb4, [&](int r, int n0, float4 v) {
+            float4* p = reinterpret_cast<float4*>(a3 + r * ld3 + n0);
+            const float4 s = *p;
+            *p = make_float4(v.x * elu_grad_from_act(s.x), v.y * elu_grad_from_act(s.y),
+                             v.z * elu_grad_from_act(s.z), v.w * elu_grad_from_act(s.w));
+        });
+        __syncthreads();
+        tile_linear<RT, NT>(base + n.w3b, a.h2, a.h3 >> 2, a.h2, a3, ld3, a.kb3, [&](int r, int n0, float4 v) {
+            float4* p = reinterpret_cast<float4*>(a2 + r * ld2 + n0);
+            const float4 s = *p;
+            *p = make_float4(v.x * elu_grad_from_act(s.x), v.y * elu_grad_from_act(s.y),
+                             v.z * elu_grad_from_act(s.z), v.w * elu_grad_from_act(s.w));
+        });
+        __syncthreads();
+        tile_linear<RT, NT>(base + n.w2b, a.h1, a.h2 >> 2, a.h1, a2, ld2, a.kb2, [&](int r, int n0, float4 v) {
+            float4* p = reinterpret_cast<float4*>(a1 + r * ld1 + n0);
+            const float4 s = *p;
+            *p = make_float4(v.x * elu_grad_from_act(s.x), v.y * elu_grad_from_act(s.y),
+                             v.z * elu_grad_from_act(s.z), v.w * elu_grad_from_act(s.w));
+        });
+        __syncthreads();
+        tile_linear<RT, NT>(base + n.w1a, a.A4, a.h1 >> 2, a.A4, a1, ld1, a.kb1, [&](int r, int n0, float4 v) {
+            *reinterpret_cast<float4*>(ga + r * a.A4 + n0) = v;
+        });
+        __syncthreads();
+    }
+
+    float sq = 0.f;
+    const float scale = MODE == 1 ? -seg.inv_cnt[m] : 1.f;
+    for (int i = tid; i < RT * a.A; i += NT) {
+        int r = i / a.A, c = i % a.A;
+        long row = row0 + r;
+        if (row < row_end) {
+            float g = scale * (GA[r * a.A4 + c] + GA[(RT + r) * a.A4 + c]);
+            grad_out[row * a.A + c] = g;
+            sq = fmaf(g, g, sq);
+        }
+    }
+    if (MODE == 1) {
+        sq = warp_sum(sq);
+        if (lane == 0) red[warp] = sq;
+        __syncthreads();
+        if (tid == 0) {
+            float s = 0.f;
+            for (int w = 0; w < NT / 32; ++w) s += red[w];
+            atomicAdd(gsq + m, s);
+        }
+    }
+}
+
+// Adam on the action rows of each segment, with the segment's clip coefficient
+// (clip_grad_norm_ then torch.optim.Adam.step then clamp_, ac_base.py:86-91 / ddiffpg.py:369).
+__global__ void q_adam_kernel(SegTable seg, int A, float* __restrict__ act, const float* __restrict__ g,
+                              float* __restrict__ m1, float* __restrict__ m2, const float* __restrict__ gsq,
+                              float* __restrict__ gnorm_out, int iter, int iters, float step_size, float bc2_sqrt,
+                              float b1, float b2, float eps, float max_norm, float lim, long n_elems) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    int mode = 0;
+    if (i < n_elems) {
+        long row = i / A;
+        while (mode + 1 < seg.n_modes && row >= seg.off[mode + 1]) ++mode;
+        const float norm = sqrtf(gsq[mode]);
+        float coef = max_norm / (norm + 1e-6f);
+        coef = fminf(coef, 1.0f);
+        if (gnorm_out && i == seg.off[mode] * A) gnorm_out[mode * iters + iter] = norm;
+        const float gi = g[i] * coef;
+        const float ea = m1[i] * b1 + (1.f - b1) * gi;          // exp_avg.lerp_(grad, 1-beta1)
+        const float ev = m2[i] * b2 + (1.f - b2) * gi * gi;     // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+        m1[i] = ea; m2[i] = ev;
+        const float denom = sqrtf(ev) / bc2_sqrt + eps;
+        float v = act[i] - step_size * (ea / denom);
+        v = fminf(fmaxf(v, -lim), lim);
+        act[i] = v;
+    }
+}
+
+// sum |a| per mode segment (torch.abs(action).mean(), ddiffpg.py:373)
+__global__ void q_abs_sum_kernel(SegTable seg, int A, const float* __restrict__ act, long n_elems,
+                                 float* __restrict__ abs_sum) {
+    __shared__ float bins[kMaxModes];
+    if (threadIdx.x < kMaxModes) bins[threadIdx.x] = 0.f;
+    __syncthreads();
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long n_round = (n_elems + 31) / 32 * 32;           // whole warps iterate together
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        int mode = -1;
+        float v = 0.f;
+        if (i < n_elems) {
+            long row = i / A;
+            mode = 0;
+            while (mode + 1 < seg.n_modes && row >= seg.off[mode + 1]) ++mode;
+            v = fabsf(act[i]);
+        }
+        const int m0 = __shfl_sync(0xffffffffu, mode, 0);
+        if (__all_sync(0xffffffffu, mode == m0 || mode < 0) && m0 >= 0) {
+            v = warp_sum(v);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&bins[m0], v);
+        } else if (mode >= 0) {
+            atomicAdd(&bins[mode], v);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < seg.n_modes && bins[threadIdx.x] != 0.f) atomicAdd(abs_sum + threadIdx.x, bins[threadIdx.x]);
+}
+
+__global__ void q_clamp_kernel(float* __restrict__ act, long n, float lim) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) act[i] = fminf(fmaxf(act[i], -lim), lim);
+}
+
+__global__ void q_finish_kernel(SegTable seg, int A, const float* __restrict__ abs_sum, float* __restrict__ mean_abs) {
+    int m = threadIdx.x;
+    if (m < seg.n_modes) {
+        long n = (seg.off[m + 1] - seg.off[m]) * A;
+        mean_abs[m] = n > 0 ? abs_sum[m] / (float)n : 0.f;
+    }
+}
+
+static size_t q_tile_smem(const QLayout& L, int RT) {
+    size_t f = (size_t)RT * L.K1p + 2 * (size_t)RT * ((L.h1 + 4) + (L.h2 + 4) + (L.h3 + 4) + L.atomsP) + 2 * RT +
+               2 * (size_t)RT * L.A4;
+    return f * sizeof(float);
+}
+
+static long fill_segments(const QLayout& L, const int64_t* seg_off, const int64_t* seg_cnt, int RT, SegTable& st) {
+    st.n_modes = L.n_modes;
+    long tiles = 0;
+    for (int m = 0; m < L.n_modes; ++m) {
+        st.off[m] = seg_off[m];
+        st.tile0[m] = tiles;
+        long len = seg_off[m + 1] - seg_off[m];
+        tiles += (len + RT - 1) / RT;
+        long cnt = seg_cnt ? seg_cnt[m] : len;
+        st.inv_cnt[m] = cnt > 0 ? 1.0f / (float)cnt : 0.f;
+    }
+    st.off[L.n_modes] = seg_off[L.n_modes];
+    st.tile0[L.n_modes] = tiles;
+    return tiles;
+}
+
+template <int RT, int MODE>
+static int launch_q_tile(const QLayout& L, const float* pk, const SegTable& seg, long tiles, const float* obs,
+                         const float* act, float* qmin, float* p1, float* p2, float* grad, float* gsq,
+                         cudaStream_t st) {
+    constexpr int NT = 256;
+    size_t smem = q_tile_smem(L, RT);
+    if (smem > 227 * 1024) DDP_FAIL(DDP_ERR_SHAPE, "critic tile needs %zu B of shared memory", smem);
+    auto kern = q_tile_kernel<RT, NT, MODE>;
+    DDP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QArgs a = make_qargs(L, pk, NT);
+    kern<<<(unsigned)tiles, NT, smem, st>>>(a, seg, obs, act, qmin, p1, p2, grad, gsq);
+    DDP_LAUNCH_CHECK("q_tile_kernel");
+    return DDP_OK;
+}
+
+int q_forward_fma(const QLayout& L, const float* pk, const int64_t* seg_off, const float* obs, const float* act,
+                  float* qmin, float* p1, float* p2, float* dq_da, long B, cudaStream_t st) {
+    SegTable seg;
+    if (B <= 148 * 8) {
+        long tiles = fill_segments(L, seg_off, nullptr, 4, seg);
+        return launch_q_tile<4, 0>(L, pk, seg, tiles, obs, act, qmin, p1, p2, dq_da, nullptr, st);
+    }
+    long tiles = fill_segments(L, seg_off, nullptr, 16, seg);
+    return launch_q_tile<16, 0>(L, pk, seg, tiles, obs, act, qmin, p1, p2, dq_da, nullptr, st);
+}
+
+// workspace: g [B*A], exp_avg [B*A], exp_avg_sq [B*A], gsq [iters][kMaxModes], abs_sum [kMaxModes]
+size_t q_ascent_workspace(const QLayout& L, long B, int iters) {
+    size_t n = align_up((size_t)B * L.A, 64);
+    return (3 * n + (size_t)iters * kMaxModes + kMaxModes) * sizeof(float);
+}
+
+int q_ascent_fma(const QLayout& L, const float* pk, const int64_t* seg_off, const int64_t* seg_cnt, const float* obs,
+                 float* action, int iters, float lr, float b1, float b2, float eps, float max_norm, float lim,
+                 float* mean_abs, float* gnorm_out, long B, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const size_t n = align_up((size_t)B * L.A, 64);
+    float* g = (float*)ws;
+    float* m1 = g + n;
+    float* m2 = m1 + n;
+    float* gsq = m2 + n;
+    float* abs_sum = gsq + (size_t)iters * kMaxModes;
+    const long n_elems = B * L.A;
+    // fresh Adam state (a new torch.optim.Adam per call, ddiffpg.py:362) and zeroed reductions
+    DDP_CUDA_CHECK(cudaMemsetAsync(m1, 0, (2 * n + (size_t)iters * kMaxModes + kMaxModes) * sizeof(float), st));
+    const unsigned eb = (unsigned)((n_elems + 255) / 256);
+    q_clamp_kernel<<<eb, 256, 0, st>>>(action, n_elems, lim);                      // ddiffpg.py:361
+    SegTable seg;
+    const bool small = B <= 148 * 8;
+    const long tiles = fill_segments(L, seg_off, seg_cnt, small ? 4 : 16, seg);
+    for (int it = 0; it < iters; ++it) {
+        int rc = small ? launch_q_tile<4, 1>(L, pk, seg, tiles, obs, action, nullptr, nullptr, nullptr, g,
+                                            gsq + (size_t)it * kMaxModes, st)
+                       : launch_q_tile<16, 1>(L, pk, seg, tiles, obs, action, nullptr, nullptr, nullptr, g,
+                                             gsq + (size_t)it * kMaxModes, st);
+        if (rc != DDP_OK) return rc;
+        const int step = it + 1;
+        const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+        q_adam_kernel<<<eb, 256, 0, st>>>(seg, L.A, action, g, m1, m2, gsq + (size_t)it * kMaxModes, gnorm_out, it,
+                                          iters, (float)(lr / bc1), (float)sqrt(bc2), b1, b2, eps, max_norm, lim,
+                                          n_elems);
+    }
+    q_abs_sum_kernel<<<(unsigned)((n_elems + 2047) / 2048 < 592 ? (n_elems + 2047) / 2048 : 592), 256, 0, st>>>(seg, L.A, action, n_elems, abs_sum);
+    q_finish_kernel<<<1, kMaxModes, 0, st>>>(seg, L.A, abs_sum, mean_abs);
+    DDP_LAUNCH_CHECK("q ascent kernels");
+    return DDP_OK;
+}
+
+}  // namespace ddp

@@ -1,0 +1,132 @@
+/*
+ * ddiffpg_b200 -- C ABI of the B200-native DDiffPG hot path (sm_100a).
+ *
+ * The reference (sayantanauddy/ddiffpg) is pure Python/PyTorch and has no FFI; the seam it offers is
+ * the Python object protocol of two nn.Modules and one agent method.  Each
+ * entry point below names the reference interface it replaces (paths relative to the reference repo).
+ * The Python host layer (ddiffpg_b200/models.py, ddiffpg_b200/algo.py) binds these with ctypes and
+ * mirrors the reference call surface one to one; INTEGRATION.md shows the stub a maintainer adds.
+ *
+ * Conventions
+ *  - every data pointer is a DEVICE pointer on the current device, fp32 row-major contiguous unless
+ *    stated; `*_shape` structs and `params[]` pointer arrays are HOST memory;
+ *  - the caller owns all memory (inputs, outputs, packed weights, workspace); functions only enqueue
+ *    work on `stream` (a cudaStream_t passed as void*), never allocate and never synchronise;
+ *  - return 0 on success, a negative ddp_status otherwise; ddp_last_error() gives the thread-local
+ *    message of the last failure; no C++ types or exceptions cross the boundary;
+ *  - `precision`: DDP_FP32 = warp-level FMA path (parity <= 1e-4 relative against the reference),
+ *    DDP_BF16 = tcgen05/TMEM tensor-core path (bf16 operands, fp32 accumulate, parity <= 1e-2).
+ */
+#ifndef DDIFFPG_B200_H
+#define DDIFFPG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDP_ABI_VERSION 1
+
+enum ddp_status {
+    DDP_OK = 0,
+    DDP_ERR_SHAPE = -1,        /* unsupported or inconsistent shape                     */
+    DDP_ERR_ARG = -2,          /* null pointer, misaligned buffer, workspace too small  */
+    DDP_ERR_UNSUPPORTED = -3,  /* e.g. precision not available for this shape           */
+    DDP_ERR_CUDA = -4          /* a CUDA runtime call failed (message in last_error)    */
+};
+
+enum ddp_precision { DDP_FP32 = 0, DDP_BF16 = 1 };
+
+/* Diffusion actor: DiffusionPolicy(state_dim=S, action_dim=A, diffusion_iter=T) with
+ * DiffusionNet(dim=D) and trunk widths h1,h2,h3 (ddiffpg/models/diffusion_mlp.py:24-58,148-173).
+ * Reference values: S=34, A=8, T=5, D=256, h1=1024, h2=512, h3=256. */
+typedef struct { int S, A, T, D, h1, h2, h3; } ddp_actor_shape;
+
+/* DistributionalDoubleQ(state_dim=O, act_dim=A, v_min, v_max, num_atoms) with MLPNet hidden layers
+ * hid1,hid2,hid3 (ddiffpg/models/mlp.py:23-35,131-141); n_modes critics, one per behaviour mode
+ * (ddiffpg/utils/Q_scheduler.py:16-45).  Reference: O=29, A=8, atoms=51, v in [0,5], 512/256/128. */
+typedef struct { int O, A, atoms; float v_min, v_max; int n_modes; int hid1, hid2, hid3; } ddp_q_shape;
+
+int ddp_abi_version(void);
+const char* ddp_last_error(void);
+
+/* ----------------------------------------------------------------------------------------------
+ * Actor weights.  params[12] are the tensors of DiffusionPolicy.state_dict() in its own order
+ * (net.time_mlp.{1,3}.{weight,bias}, net.mlp.{0,2,4,6}.{weight,bias}).  Packing (a) transposes the
+ * trunk weights for coalesced streaming, (b) folds SinusoidalPosEmb + time_mlp + the 256 time
+ * columns of net.mlp.0 + its bias into a [T, h1] table (diffusion_mlp.py:14-21,38-43,68-70: these
+ * depend on t only), (c) evaluates the DDPMScheduler constants (diffusers, call sites
+ * diffusion_mlp.py:167-173,243-247,309-310) and (d) for DDP_BF16 adds bf16 tensor-core tiles.
+ * Re-pack whenever a parameter changes. */
+size_t ddp_actor_packed_bytes(const ddp_actor_shape* shape, int precision);
+int ddp_actor_pack(const ddp_actor_shape* shape, const float* const params[12], void* packed,
+                   int precision, void* stream);
+
+/* Replaces DiffusionPolicy.forward / get_actions(sample=True, add_noise=False)
+ * (ddiffpg/models/diffusion_mlp.py:184-185,219-251): the whole T-step reverse chain in one launch.
+ * state [B,S]; noise [T,B,A] with noise[0] = x_T (the draw at :222) and noise[j] = the Gaussian the
+ * scheduler adds at t = T-j (j >= 1); action_out [B,A] in [-1,1]. */
+size_t ddp_actor_sample_workspace_bytes(const ddp_actor_shape* shape, long B, int precision);
+int ddp_actor_sample(const ddp_actor_shape* shape, const void* packed, const float* state,
+                     const float* noise, float* action_out, long B, int precision,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* Replaces DiffusionPolicy.get_loss + the backward of optimizer_update
+ * (ddiffpg/models/diffusion_mlp.py:294-321, ddiffpg/algo/ac_base.py:83-85).
+ * state [B,S], action [B,A], noise [B,A], t [B] int64 in [0,T).  inv_count = 1/(B_global*A).
+ * loss_out[0]      += sum((eps_hat-noise)^2) * inv_count    (zero it first; partial sums add up)
+ * grads_flat[...]   = d loss / d params, flat in state_dict order (overwritten, not accumulated).
+ * params[12] are the live fp32 parameters (the backward streams them in their own layout). */
+size_t ddp_actor_grad_count(const ddp_actor_shape* shape);
+size_t ddp_actor_train_workspace_bytes(const ddp_actor_shape* shape, long B, int precision);
+int ddp_actor_loss_fwd_bwd(const ddp_actor_shape* shape, const void* packed,
+                           const float* const params[12], const float* state, const float* action,
+                           const float* noise, const int64_t* t, float inv_count, float* loss_out,
+                           float* grads_flat, long B, int precision, void* ws, size_t ws_bytes,
+                           void* stream);
+
+/* Tail of ActorCriticBase.optimizer_update (ddiffpg/algo/ac_base.py:86-91) for a flat parameter
+ * vector: g_norm = ||g||_2, g *= min(1, max_norm/(g_norm+1e-6)), AdamW step (torch.optim.AdamW
+ * semantics, decoupled weight decay, bias-corrected).  norm_out[0] receives the pre-clip norm.
+ * step is the 1-based step count after this update.  scratch: 1 float, zeroed by the call. */
+int ddp_clip_adamw_step(float* params_flat, float* grads_flat, float* exp_avg, float* exp_avg_sq,
+                        size_t n, int step, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, float max_norm, float* norm_out, float* scratch,
+                        void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Critics.  params[16*n_modes]: per mode the tensors of DistributionalDoubleQ.state_dict()
+ * (net_q1.net.{0,2,4,6}.{weight,bias}, net_q2.net....). */
+size_t ddp_q_packed_bytes(const ddp_q_shape* shape, int precision);
+int ddp_q_pack(const ddp_q_shape* shape, const float* const params[], void* packed, int precision,
+               void* stream);
+
+/* Replaces DistributionalDoubleQ.get_q1_q2 / get_q_min (ddiffpg/models/mlp.py:143-151).
+ * Rows are sorted by mode; seg_off[n_modes+1] (HOST) gives the row range of each mode's critic.
+ * q_min_out [B]; p1_out/p2_out [B,atoms] may be NULL; dq_da_out [B,A] (d q_min / d action, the
+ * autograd result of get_q_min w.r.t. action) may be NULL. */
+int ddp_q_forward(const ddp_q_shape* shape, const void* packed, const int64_t* seg_off,
+                  const float* obs, const float* act, float* q_min_out, float* p1_out, float* p2_out,
+                  float* dq_da_out, long B, int precision, void* stream);
+
+/* Replaces AgentDDiffPG.update_target_action (ddiffpg/algo/ddiffpg.py:358-373, identical copy
+ * ddiffpg/algo/dipo.py:246-261) including its optimizer_update tail (ac_base.py:83-92): pre-clamp,
+ * then `iters` x { g = grad_a(-mean_seg min(Q1,Q2)); global-L2 clip over the segment to max_norm;
+ * Adam(lr, betas, eps, fresh state); clamp(+-lim) }.  Each mode segment is one reference call: its
+ * mean uses seg_mean_count[m] rows (pass the segment length for reference semantics, or the global
+ * mode batch when sharded) and its own clip norm.  action_inout [B,A] is updated in place;
+ * mean_abs_out [n_modes] receives mean|a| per segment; gnorm_out [n_modes*iters] the pre-clip norms
+ * (may be NULL).  ws: ddp_q_ascent_workspace_bytes. */
+size_t ddp_q_ascent_workspace_bytes(const ddp_q_shape* shape, long B, int iters);
+int ddp_q_action_ascent(const ddp_q_shape* shape, const void* packed, const int64_t* seg_off,
+                        const int64_t* seg_mean_count, const float* obs, float* action_inout,
+                        int iters, float lr, float beta1, float beta2, float eps, float max_norm,
+                        float lim, float* mean_abs_out, float* gnorm_out, long B, int precision,
+                        void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDIFFPG_B200_H */

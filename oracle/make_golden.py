@@ -1,0 +1,176 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own modules (TEST INFRASTRUCTURE).
+
+Run in the build container only (needs /root/reference):  python -m oracle.make_golden
+
+Weights are NOT stored (1.49 M floats per actor): they are regenerated from a seed by
+``oracle.port.init_*_params`` and loaded into the reference modules with ``load_state_dict``; a
+checksum of every tensor is stored so a drift of the seeded generator would be caught.
+Noise is injected into the reference by (a) queueing the per-step draws inside the restated
+scheduler and (b) replacing ``torch.randn`` for the single initial draw of
+``DiffusionPolicy.get_actions`` (diffusion_mlp.py:222-223).
+"""
+import os
+from copy import deepcopy
+
+import numpy as np
+import torch
+
+from . import port, ref_loader
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def param_checksum(p, keys):
+    return np.array([[float(p[k].double().sum()), float(p[k].double().abs().sum())] for k in keys])
+
+
+class _PatchedRandn:
+    """Replace torch.randn / torch.randn_like for one call each with queued tensors."""
+
+    def __init__(self, queue):
+        self.queue = list(queue)
+
+    def __enter__(self):
+        self._randn, self._randn_like = torch.randn, torch.randn_like
+        torch.randn = lambda *a, **k: self.queue.pop(0).clone()
+        torch.randn_like = lambda *a, **k: self.queue.pop(0).clone()
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn, torch.randn_like = self._randn, self._randn_like
+
+
+def ref_actor(R, params, T):
+    pol = R.DiffusionPolicy(34, 8, T, device="cpu")
+    pol.load_state_dict(params)
+    return pol
+
+
+def ref_sample(R, pol, state, noise):
+    pol.noise_scheduler.noise_queue = [n for n in noise[1:]]
+    with _PatchedRandn([noise[0]]):
+        with torch.no_grad():
+            return pol(state)                  # DiffusionPolicy.forward -> get_actions(sample=True)
+
+
+def intree_ddpm_sample(R, pol, state, noise, T):
+    """The same chain through the reference's in-tree DDPM (baseline_models.py:59-185)."""
+    class Net(torch.nn.Module):
+        def forward(self, x, t, s):
+            return pol.net(x, t.float(), s)
+    dif = R.Diffusion(state_dim=34, action_dim=8, model=Net(), max_action=1.0,
+                      beta_schedule="cosine", n_timesteps=T)
+    # x_T via randn, then one randn_like per step; p_sample also draws at t == 0 (masked by 0).
+    with _PatchedRandn([n for n in noise] + [torch.zeros_like(noise[0])]):
+        with torch.no_grad():
+            return dif.sample(state)
+
+
+def ref_q_ascent(critic, obs, action, iters, lr, max_norm=1.0):
+    """update_target_action (ddiffpg.py:358-373) + optimizer_update (ac_base.py:83-92) around the
+    reference's real critic.  The agent module cannot be imported (gym), so its statements are
+    replayed here one for one."""
+    critic.requires_grad_(False)
+    lim = 1 - 1e-5
+    action.clamp_(-lim, lim)
+    opt = torch.optim.Adam([action], lr=lr, eps=1e-5)
+    norms = []
+    for _ in range(iters):
+        action.requires_grad_(True)
+        Q = critic.get_q_min(obs, action)
+        loss = -Q.mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        norms.append(float(torch.nn.utils.clip_grad_norm_(parameters=opt.param_groups[0]["params"],
+                                                          max_norm=max_norm)))
+        opt.step()
+        action.requires_grad_(False)
+        action.clamp_(-lim, lim)
+    upd = deepcopy(action.detach())
+    critic.requires_grad_(True)
+    return torch.abs(action).mean().item(), upd, np.array(norms)
+
+
+def main():
+    R = ref_loader.load_reference()
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+
+    # ---------------------------------------------------------------- H1 sampler
+    for name, T, B, wseed, scale in (("h1_T5_B16", 5, 16, 11, 1.0), ("h1_T5_B16_wide", 5, 16, 12, 2.5),
+                                     ("h1_T20_B8", 20, 8, 13, 1.0), ("h1_T100_B4", 100, 4, 14, 1.5)):
+        g = torch.Generator().manual_seed(1000 + T + B)
+        params = port.init_actor_params(wseed, scale=scale)
+        state = torch.randn(B, 34, generator=g)
+        noise = torch.randn(T, B, 8, generator=g)
+        pol = ref_actor(R, params, T)
+        act_ref = ref_sample(R, pol, state, noise)
+        act_port = port.actor_sample(params, state, noise, T)
+        act_tree = intree_ddpm_sample(R, pol, state, noise, T)
+        eps_ref = pol.net(noise[0], torch.ones(B) * (T - 1), state).detach()
+        d_port = (act_ref - act_port).abs().max().item()
+        d_tree = (act_ref - act_tree).abs().max().item()
+        print(f"{name}: |ref-port|={d_port:.3e} |ref-intree_ddpm|={d_tree:.3e} "
+              f"sat={(act_ref.abs() >= 1).float().mean().item():.2f}")
+        assert d_port < 1e-5 and d_tree < 5e-4, (d_port, d_tree)
+        np.savez(os.path.join(OUT, name + ".npz"), T=T, wseed=wseed, scale=scale,
+                 state=state.numpy(), noise=noise.numpy(), action=act_ref.numpy(),
+                 action_intree_ddpm=act_tree.numpy(), eps_first=eps_ref.numpy(),
+                 checksum=param_checksum(params, port.ACTOR_KEYS))
+
+    # ---------------------------------------------------------------- H3 loss + grads
+    for name, T, B, wseed, scale in (("h3_T5_B64", 5, 64, 21, 1.0), ("h3_T20_B32_wide", 20, 32, 22, 2.0)):
+        g = torch.Generator().manual_seed(2000 + T + B)
+        params = port.init_actor_params(wseed, scale=scale)
+        state = torch.randn(B, 34, generator=g)
+        action = torch.rand(B, 8, generator=g) * 2 - 1
+        noise = torch.randn(B, 8, generator=g)
+        ts = torch.randint(0, T, (B,), generator=g)
+        pol = ref_actor(R, params, T)
+        loss = pol.get_loss(state, action, noise=noise, timesteps=ts)
+        loss.backward()
+        grads = {k: v.grad.detach() for k, v in pol.named_parameters()}
+        gn = torch.sqrt(sum((v ** 2).sum() for v in grads.values()))
+        l_port, g_port = port.actor_loss_and_grads(params, state, action, noise, ts, T)
+        d = max((grads[k] - g_port[k]).abs().max().item() for k in port.ACTOR_KEYS)
+        print(f"{name}: loss={loss.item():.6f} |dloss|={abs(loss.item() - l_port.item()):.2e} "
+              f"max|dgrad|={d:.2e} gnorm={gn.item():.4f}")
+        assert abs(loss.item() - l_port.item()) < 1e-6 and d < 1e-6
+        save = dict(T=T, wseed=wseed, scale=scale, state=state.numpy(), action=action.numpy(),
+                    noise=noise.numpy(), timesteps=ts.numpy(), loss=loss.item(), grad_norm=gn.item(),
+                    checksum=param_checksum(params, port.ACTOR_KEYS))
+        for i, k in enumerate(port.ACTOR_KEYS):
+            gk = grads[k]
+            save[f"gnorm_{i}"] = float(gk.norm())
+            save[f"gsum_{i}"] = float(gk.double().sum())
+            # biases and the 8-row head in full; a fixed strided sample of the big matrices
+            save[f"gsample_{i}"] = (gk if gk.numel() <= 4096 else gk.flatten()[::997]).numpy()
+        np.savez(os.path.join(OUT, name + ".npz"), **save)
+
+    # ---------------------------------------------------------------- H2 double-Q + ascent
+    for name, B, wseed, scale, iters in (("h2_B32", 32, 31, 1.0, 20), ("h2_B8_wide_clip", 8, 32, 6.0, 20)):
+        g = torch.Generator().manual_seed(3000 + B)
+        params = port.init_critic_params(wseed, scale=scale)
+        obs = torch.randn(B, 29, generator=g)
+        act = torch.rand(B, 8, generator=g) * 2.2 - 1.1      # some rows start outside the clamp
+        critic = R.DistributionalDoubleQ(29, 8, v_min=0, v_max=5, num_atoms=51, device="cpu")
+        critic.load_state_dict(params)
+        with torch.no_grad():
+            p1, p2 = critic.get_q1_q2(obs, act)
+            qm = critic.get_q_min(obs, act)
+        a0 = act.clone().requires_grad_(True)
+        critic.get_q_min(obs, a0).sum().backward()
+        mean_abs, upd, norms = ref_q_ascent(critic, obs, act.clone(), iters, 0.03)
+        m2, u2, n2 = port.q_action_ascent(params, obs, act.clone(), iters=iters, return_trace=True)
+        d = (upd - u2).abs().max().item()
+        print(f"{name}: |ref-port| ascent={d:.2e} mean|a|={mean_abs:.5f} norms[0]={norms[0]:.4e} "
+              f"max norm={norms.max():.4e}")
+        assert d < 1e-6
+        np.savez(os.path.join(OUT, name + ".npz"), wseed=wseed, scale=scale, iters=iters,
+                 obs=obs.numpy(), action=act.numpy(), p1=p1.numpy(), p2=p2.numpy(), q_min=qm.numpy(),
+                 dq_da=a0.grad.numpy(), new_action=upd.numpy(), mean_abs=mean_abs, norms=norms,
+                 checksum=param_checksum(params, port.CRITIC_KEYS))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,216 @@
+"""Functional CPU restatement of the reference hot path (TEST INFRASTRUCTURE, "port" oracle).
+
+Every function cites the reference lines it follows (paths relative to the reference repo).
+Parameters are plain dicts keyed by the reference ``state_dict()`` names, so the same weights
+drive the reference modules (``oracle/make_golden.py``), this port and the CUDA kernels.
+Works in any float dtype (fp32 for parity, fp64 to calibrate tolerances).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from .ddpm import DDPMSchedulerRestated
+
+ACTOR_KEYS = (
+    "net.time_mlp.1.weight", "net.time_mlp.1.bias", "net.time_mlp.3.weight", "net.time_mlp.3.bias",
+    "net.mlp.0.weight", "net.mlp.0.bias", "net.mlp.2.weight", "net.mlp.2.bias",
+    "net.mlp.4.weight", "net.mlp.4.bias", "net.mlp.6.weight", "net.mlp.6.bias",
+)
+CRITIC_KEYS = tuple(f"net_q{j}.net.{i}.{w}" for j in (1, 2) for i in (0, 2, 4, 6)
+                    for w in ("weight", "bias"))
+
+
+# --------------------------------------------------------------------------- init helpers
+def _linear_init(gen, out_f, in_f, dtype=torch.float32):
+    """nn.Linear default init (kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(in), 1/sqrt(in)) for both)."""
+    bound = 1.0 / math.sqrt(in_f)
+    w = (torch.rand(out_f, in_f, generator=gen, dtype=torch.float64) * 2 - 1) * bound
+    b = (torch.rand(out_f, generator=gen, dtype=torch.float64) * 2 - 1) * bound
+    return w.to(dtype), b.to(dtype)
+
+
+def init_actor_params(seed, S=34, A=8, h=1024, D=256, scale=1.0):
+    """Random actor weights with the reference shapes (diffusion_mlp.py:38-58); h=1024 is the reference.
+
+    ``scale`` > 1 widens the weights so the chain leaves the small-output regime of a fresh init.
+    """
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(4 * D, D), (D, 4 * D), (h, D + S + A), (h // 2, h), (h // 4, h // 2), (A, h // 4)]
+    p = {}
+    for i, (o, k) in enumerate(shapes):
+        w, b = _linear_init(g, o, k)
+        p[ACTOR_KEYS[2 * i]] = w * scale
+        p[ACTOR_KEYS[2 * i + 1]] = b * scale
+    return p
+
+
+def init_critic_params(seed, O=29, A=8, atoms=51, hidden=(512, 256, 128), scale=1.0):
+    """Random double-Q weights with the reference shapes (mlp.py:23-35,131-138)."""
+    g = torch.Generator().manual_seed(seed)
+    dims = [O + A, *hidden, atoms]
+    p = {}
+    for j in (1, 2):
+        for li, (k, o) in enumerate(zip(dims[:-1], dims[1:])):
+            w, b = _linear_init(g, o, k)
+            p[f"net_q{j}.net.{2 * li}.weight"] = w * scale
+            p[f"net_q{j}.net.{2 * li}.bias"] = b * scale
+    return p
+
+
+def cast_params(p, dtype):
+    return {k: v.detach().to(dtype).clone() for k, v in p.items()}
+
+
+# --------------------------------------------------------------------------- H1 / H3 network
+def sinusoidal_pos_emb(t, dim=256):
+    """diffusion_mlp.py:14-21 -- [sin(t f_i) | cos(t f_i)], f_i = exp(-i ln(1e4)/(dim/2-1)).
+
+    The reference builds f in fp32 regardless of the dtype of ``t``; a float64 ``t`` promotes.
+    """
+    half = dim // 2
+    c = math.log(10000) / (half - 1)
+    f = torch.exp(torch.arange(half) * -c)
+    e = t[:, None] * f[None, :]
+    return torch.cat((e.sin(), e.cos()), dim=-1)
+
+
+def time_mlp(p, t, dim=256):
+    """diffusion_mlp.py:38-43 -- pos-emb -> Linear(D,4D) -> Mish -> Linear(4D,D)."""
+    e = sinusoidal_pos_emb(t, dim).to(p["net.time_mlp.1.weight"].dtype)
+    hdn = F.mish(F.linear(e, p["net.time_mlp.1.weight"], p["net.time_mlp.1.bias"]))
+    return F.linear(hdn, p["net.time_mlp.3.weight"], p["net.time_mlp.3.bias"])
+
+
+def actor_eps(p, x, t, cond):
+    """DiffusionNet.forward, diffusion_mlp.py:62-73 -- cat order is [temb, cond, x] (:70)."""
+    D = p["net.time_mlp.3.weight"].shape[0]
+    temb = time_mlp(p, t, D)
+    z = torch.cat([temb, cond, x], dim=-1)
+    z = F.mish(F.linear(z, p["net.mlp.0.weight"], p["net.mlp.0.bias"]))
+    z = F.mish(F.linear(z, p["net.mlp.2.weight"], p["net.mlp.2.bias"]))
+    z = F.mish(F.linear(z, p["net.mlp.4.weight"], p["net.mlp.4.bias"]))
+    return F.linear(z, p["net.mlp.6.weight"], p["net.mlp.6.bias"])
+
+
+@torch.no_grad()
+def actor_sample(p, state, noise, T, return_chain=False):
+    """DiffusionPolicy.get_actions(sample=True, add_noise=False), diffusion_mlp.py:219-251.
+
+    ``noise[0]`` replaces the initial ``torch.randn((B, A))`` (:222); ``noise[j]`` (j >= 1) replaces
+    the draw inside ``scheduler.step`` at t = T - j (t > 0 only).  ``noise`` has shape [T, B, A].
+    """
+    B = state.shape[0]
+    dtype = state.dtype
+    sched = DDPMSchedulerRestated(num_train_timesteps=T, noise_queue=[n for n in noise[1:]])
+    x = noise[0].clone()
+    sched.set_timesteps(T)
+    chain = [x.clone()]
+    for k in sched.timesteps:
+        tt = (torch.ones(B) * k).to(dtype)            # :229 (float timesteps in the sampler)
+        eps = actor_eps(p, x, tt, state)
+        x = sched.step(model_output=eps, timestep=k, sample=x).prev_sample.to(dtype)
+        chain.append(x.clone())
+    return (x, chain) if return_chain else x
+
+
+def actor_loss(p, state, action, noise, timesteps, T):
+    """DiffusionPolicy.get_loss, diffusion_mlp.py:294-321 (noise and timesteps injected)."""
+    sched = DDPMSchedulerRestated(num_train_timesteps=T)
+    noisy = sched.add_noise(action, noise, timesteps)
+    eps = actor_eps(p, noisy, timesteps, state)       # int64 timesteps feed the pos-emb (:313)
+    return F.mse_loss(eps, noise)
+
+
+def actor_loss_and_grads(p, state, action, noise, timesteps, T):
+    """loss + d loss / d params in ACTOR_KEYS order (what ``objective.backward()`` leaves in .grad,
+    ac_base.py:83-85), before clipping."""
+    q = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+    loss = actor_loss(q, state, action, noise, timesteps, T)
+    grads = torch.autograd.grad(loss, [q[k] for k in ACTOR_KEYS])
+    return loss.detach(), {k: g for k, g in zip(ACTOR_KEYS, grads)}
+
+
+def clip_coef(total_norm, max_norm=1.0):
+    """torch.nn.utils.clip_grad_norm_: coef = clamp(max_norm / (norm + 1e-6), max=1)."""
+    return torch.clamp(max_norm / (total_norm + 1e-6), max=1.0)
+
+
+def adamw_train_step(p, state, action, noise, timesteps, T, opt_state=None, lr=3e-4,
+                     betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_norm=1.0):
+    """update_actor, ddiffpg.py:353-356 = get_loss + optimizer_update (ac_base.py:83-92) with
+    AdamW(lr=actor_lr) (ac_base.py:52; torch defaults betas .9/.999, eps 1e-8, wd 1e-2).
+
+    Returns (loss, pre-clip grad norm, new params, new optimizer state)."""
+    loss, g = actor_loss_and_grads(p, state, action, noise, timesteps, T)
+    total = torch.sqrt(sum((g[k].double() ** 2).sum() for k in ACTOR_KEYS)).to(loss.dtype)
+    coef = clip_coef(total, max_norm)
+    if opt_state is None:
+        opt_state = {"step": 0, "m": {k: torch.zeros_like(p[k]) for k in ACTOR_KEYS},
+                     "v": {k: torch.zeros_like(p[k]) for k in ACTOR_KEYS}}
+    step = opt_state["step"] + 1
+    b1, b2 = betas
+    new_p, m_new, v_new = {}, {}, {}
+    for k in ACTOR_KEYS:
+        gk = g[k] * coef
+        w = p[k] * (1 - lr * weight_decay)
+        m = opt_state["m"][k] * b1 + (1 - b1) * gk
+        v = opt_state["v"][k] * b2 + (1 - b2) * gk * gk
+        denom = v.sqrt() / math.sqrt(1 - b2 ** step) + eps
+        new_p[k] = w - (lr / (1 - b1 ** step)) * m / denom
+        m_new[k], v_new[k] = m, v
+    return loss, total, new_p, {"step": step, "m": m_new, "v": v_new}
+
+
+# --------------------------------------------------------------------------- H2 critic
+def mlp_elu(p, prefix, x):
+    """MLPNet / create_simple_mlp, mlp.py:13-35 -- Linear/ELU x3 then Linear."""
+    for i in (0, 2, 4):
+        x = F.elu(F.linear(x, p[f"{prefix}.net.{i}.weight"], p[f"{prefix}.net.{i}.bias"]))
+    return F.linear(x, p[f"{prefix}.net.6.weight"], p[f"{prefix}.net.6.bias"])
+
+
+def z_atoms(v_min=0.0, v_max=5.0, atoms=51, dtype=torch.float32):
+    """mlp.py:141 -- linspace(v_min, v_max, num_atoms)."""
+    return torch.linspace(v_min, v_max, atoms).to(dtype)
+
+
+def q1_q2(p, obs, act):
+    """DistributionalDoubleQ.get_q1_q2, mlp.py:149-151."""
+    x = torch.cat((obs, act), dim=1)
+    return (torch.softmax(mlp_elu(p, "net_q1", x), dim=1),
+            torch.softmax(mlp_elu(p, "net_q2", x), dim=1))
+
+
+def q_min(p, obs, act, v_min=0.0, v_max=5.0):
+    """DistributionalDoubleQ.get_q_min, mlp.py:143-147."""
+    p1, p2 = q1_q2(p, obs, act)
+    z = z_atoms(v_min, v_max, p1.shape[1], p1.dtype)
+    return torch.min(torch.sum(p1 * z, dim=1), torch.sum(p2 * z, dim=1))
+
+
+def q_action_ascent(p, obs, action, iters=20, lr=0.03, eps=1e-5, max_norm=1.0,
+                    betas=(0.9, 0.999), v_min=0.0, v_max=5.0, return_trace=False):
+    """AgentDDiffPG.update_target_action, ddiffpg.py:358-373 (+ optimizer_update, ac_base.py:83-92).
+
+    Uses the real torch.optim.Adam and clip_grad_norm_ like the reference.  Returns
+    (mean |a|, new action[B, A]) and optionally the per-iteration pre-clip gradient norms.
+    """
+    pp = {k: v.detach() for k, v in p.items()}
+    action = action.detach().clone()
+    lim = 1 - 1e-5
+    action.clamp_(-lim, lim)
+    opt = torch.optim.Adam([action], lr=lr, eps=eps, betas=betas)
+    norms = []
+    for _ in range(iters):
+        action.requires_grad_(True)
+        loss = -q_min(pp, obs, action, v_min, v_max).mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        norms.append(torch.nn.utils.clip_grad_norm_([action], max_norm=max_norm).detach().clone())
+        opt.step()
+        action.requires_grad_(False)
+        action.clamp_(-lim, lim)
+    out = action.detach().clone()
+    res = (torch.abs(out).mean().item(), out)
+    return res + (torch.stack(norms),) if return_trace else res

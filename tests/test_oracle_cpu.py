@@ -1,0 +1,211 @@
+"""CPU tests: the oracle against the reference-generated golden vectors and known-answer constants,
+the C-ABI library (loads, exports every declared symbol, rejects bad arguments without a GPU) and the
+host-side mirror of the reference interface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ddpm, port
+from tests.util import actor_params_for, critic_params_for, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ schedule (SURVEY.md 8c constants)
+def test_schedule_known_answers_T5():
+    s = ddpm.DDPMSchedulerRestated(num_train_timesteps=5)
+    np.testing.assert_allclose(s.betas.numpy(), [0.10129408, 0.27954385, 0.47363535, 0.72405237, 0.99900001],
+                               rtol=2e-7)
+    np.testing.assert_allclose(s.alphas_cumprod.numpy(),
+                               [0.89870590, 0.64747816, 0.34080964, 0.09404562, 9.4044401e-05], rtol=3e-6)
+    c = ddpm.ddpm_step_constants(5).numpy()
+    table = {4: (0.99995297, 103.11776733, 0.30639073, 0.02865130, 0.95138508),
+             3: (0.95181632, 3.26084924, 0.46657300, 0.38222390, 0.72583389),
+             2: (0.81190538, 1.71294749, 0.57815701, 0.38798824, 0.50327992),
+             1: (0.59373552, 1.24276054, 0.75174886, 0.24389443, 0.28341579),
+             0: (0.31826735, 1.05485117, 1.0, 0.0, 0.0)}
+    for t, row in table.items():
+        np.testing.assert_allclose(c[t], row, rtol=5e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("T,b0,bl,al", [(20, 0.00799272, 0.999, 6.0595662e-06), (100, 0.00063128, 0.999, 2.4285407e-07)])
+def test_schedule_known_answers_long(T, b0, bl, al):
+    s = ddpm.DDPMSchedulerRestated(num_train_timesteps=T)
+    assert abs(s.betas[0].item() - b0) < 2e-8 * max(1, b0 / 1e-3)
+    assert abs(s.betas[-1].item() - bl) < 1e-7
+    assert abs(s.alphas_cumprod[-1].item() / al - 1) < 2e-5
+    s.set_timesteps(T)
+    assert s.timesteps.tolist() == list(range(T - 1, -1, -1))
+
+
+def test_posemb_known_answers():
+    e = port.sinusoidal_pos_emb(torch.tensor([1.0]), 256)[0]
+    np.testing.assert_allclose(e[:3].numpy(), [0.8415, 0.8016, 0.7611], atol=5e-5)
+    np.testing.assert_allclose(e[128:131].numpy(), [0.5403, 0.5978, 0.6487], atol=5e-5)
+
+
+def test_param_counts():
+    assert sum(v.numel() for v in port.init_actor_params(0).values()) == 1489928
+    assert sum(v.numel() for v in port.init_critic_params(0).values()) == 380518
+
+
+# ------------------------------------------------------------------ oracle port vs reference-made fixtures
+@pytest.mark.parametrize("name", ["h1_T5_B16", "h1_T5_B16_wide", "h1_T20_B8", "h1_T100_B4"])
+def test_port_sampler_matches_reference(name):
+    g = load_golden(name)
+    p = actor_params_for(g)
+    T = int(g["T"])
+    out = port.actor_sample(p, torch.from_numpy(g["state"]), torch.from_numpy(g["noise"]), T)
+    np.testing.assert_allclose(out.numpy(), g["action"], rtol=0, atol=2e-6)
+    # the restated diffusers scheduler against the reference's in-tree DDPM on the same chain
+    tol = {5: 5e-6, 20: 2e-5, 100: 1e-4}[T]
+    np.testing.assert_allclose(out.numpy(), g["action_intree_ddpm"], rtol=0, atol=tol)
+    eps = port.actor_eps(p, torch.from_numpy(g["noise"][0]), torch.ones(out.shape[0]) * (T - 1),
+                         torch.from_numpy(g["state"]))
+    np.testing.assert_allclose(eps.detach().numpy(), g["eps_first"], rtol=0, atol=2e-6)
+    assert np.abs(g["action"]).max() <= 1.0
+
+
+@pytest.mark.parametrize("name", ["h3_T5_B64", "h3_T20_B32_wide"])
+def test_port_loss_and_grads_match_reference(name):
+    g = load_golden(name)
+    p = actor_params_for(g)
+    loss, grads = port.actor_loss_and_grads(p, torch.from_numpy(g["state"]), torch.from_numpy(g["action"]),
+                                            torch.from_numpy(g["noise"]), torch.from_numpy(g["timesteps"]),
+                                            int(g["T"]))
+    assert abs(loss.item() - float(g["loss"])) < 1e-6
+    total = torch.sqrt(sum((v ** 2).sum() for v in grads.values())).item()
+    assert abs(total / float(g["grad_norm"]) - 1) < 1e-5
+    for i, k in enumerate(port.ACTOR_KEYS):
+        gk = grads[k]
+        samp = gk if gk.numel() <= 4096 else gk.flatten()[::997]
+        np.testing.assert_allclose(samp.numpy().reshape(-1), g[f"gsample_{i}"].reshape(-1), rtol=1e-4, atol=1e-7)
+        assert abs(gk.norm().item() - float(g[f"gnorm_{i}"])) <= 1e-5 * max(1.0, float(g[f"gnorm_{i}"]))
+
+
+@pytest.mark.parametrize("name", ["h2_B32", "h2_B8_wide_clip"])
+def test_port_q_ascent_matches_reference(name):
+    g = load_golden(name)
+    p = critic_params_for(g)
+    obs, act = torch.from_numpy(g["obs"]), torch.from_numpy(g["action"])
+    p1, p2 = port.q1_q2(p, obs, act)
+    np.testing.assert_allclose(p1.numpy(), g["p1"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(p2.numpy(), g["p2"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(port.q_min(p, obs, act).numpy(), g["q_min"], rtol=1e-6, atol=1e-6)
+    a = act.clone().requires_grad_(True)
+    port.q_min(p, obs, a).sum().backward()
+    np.testing.assert_allclose(a.grad.numpy(), g["dq_da"], rtol=1e-4, atol=1e-6)
+    mean_abs, new_a, norms = port.q_action_ascent(p, obs, act.clone(), iters=int(g["iters"]), return_trace=True)
+    np.testing.assert_allclose(new_a.numpy(), g["new_action"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(norms.numpy(), g["norms"], rtol=1e-5)
+    assert abs(mean_abs - float(g["mean_abs"])) < 1e-6
+    if name.endswith("clip"):
+        assert g["norms"].max() > 1.0, "fixture must exercise the active-clip branch"
+
+
+def test_port_adamw_step_matches_torch():
+    """oracle.port.adamw_train_step against torch.optim.AdamW + clip_grad_norm_ (ac_base.py:52,83-92)."""
+    g = load_golden("h3_T5_B64")
+    p = actor_params_for(g)
+    args = (torch.from_numpy(g["state"]), torch.from_numpy(g["action"]), torch.from_numpy(g["noise"]),
+            torch.from_numpy(g["timesteps"]), int(g["T"]))
+    q = {k: torch.nn.Parameter(v.clone()) for k, v in p.items()}
+    opt = torch.optim.AdamW([q[k] for k in port.ACTOR_KEYS], 3e-4)
+    st, cur = None, p
+    for _ in range(2):
+        loss = port.actor_loss(q, *args)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([q[k] for k in port.ACTOR_KEYS], 1.0)
+        opt.step()
+        _, _, cur, st = port.adamw_train_step(cur, *args, opt_state=st)
+    for k in port.ACTOR_KEYS:
+        np.testing.assert_allclose(cur[k].numpy(), q[k].detach().numpy(), rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------ C ABI without a GPU
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ddiffpg_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ddp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from ddiffpg_b200 import _lib
+    handle = ctypes.CDLL(built_lib)
+    names = declared_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in include/ddiffpg_b200.h but not exported"
+        assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype"
+    assert set(_lib.PROTOTYPES) == set(names)
+    assert _lib.lib().ddp_abi_version() == 1
+
+
+def test_abi_argument_errors_without_gpu(built_lib):
+    from ddiffpg_b200 import _lib
+    L = _lib.lib()
+    shape = _lib.ActorShape(34, 8, 5, 256, 1024, 512, 256)
+    n32 = L.ddp_actor_packed_bytes(shape, 0)
+    n16 = L.ddp_actor_packed_bytes(shape, 1)
+    assert n32 > 4 * (42 * 1024 + 1024 * 512 + 512 * 256 + 256 * 8) and n16 > n32
+    assert L.ddp_actor_grad_count(shape) == 1489928
+    bad = _lib.ActorShape(34, 8, 500, 256, 1024, 512, 256)          # T above the supported maximum
+    assert L.ddp_actor_packed_bytes(bad, 0) == 0
+    assert b"T" in L.ddp_last_error()
+    assert L.ddp_actor_sample(shape, None, None, None, None, 4, 0, None, 0, None) == -2
+    assert L.ddp_actor_sample(shape, None, None, None, None, 0, 0, None, 0, None) == 0      # empty batch
+    assert L.ddp_actor_sample(shape, None, None, None, None, -1, 0, None, 0, None) == -1
+    q = _lib.QShape(29, 8, 51, 0.0, 5.0, 3, 512, 256, 128)
+    assert L.ddp_q_packed_bytes(q, 0) > 3 * 4 * 380518
+    qbad = _lib.QShape(29, 8, 51, 5.0, 0.0, 1, 512, 256, 128)
+    assert L.ddp_q_packed_bytes(qbad, 0) == 0
+    assert L.ddp_q_forward(q, None, None, None, None, None, None, None, None, 0, 0, None) == 0
+
+
+# ------------------------------------------------------------------ host mirror of the reference surface
+def test_state_dict_keys_match_reference_names():
+    from ddiffpg_b200 import DiffusionPolicy, DistributionalDoubleQ
+    pol = DiffusionPolicy(34, 8, 5, device="cpu")
+    assert tuple(pol.state_dict().keys()) == port.ACTOR_KEYS
+    ref = port.init_actor_params(0)
+    assert all(pol.state_dict()[k].shape == ref[k].shape for k in port.ACTOR_KEYS)
+    cri = DistributionalDoubleQ([29], 8, v_min=0, v_max=5, num_atoms=51, device="cpu")
+    assert tuple(cri.state_dict().keys()) == port.CRITIC_KEYS
+    assert cri.z_atoms.shape == (51,) and cri.v_min == 0 and cri.v_max == 5
+    pol2 = DiffusionPolicy([29 + 5], 8, 5)       # Sequence state_dim like ac_base.py:29-31 passes
+    assert pol2.state_dim == 34
+
+
+def test_same_seed_gives_reference_init():
+    """Construction order equals the reference's, so torch.manual_seed(s) yields the reference's weights."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference not mounted")
+    from ddiffpg_b200 import DiffusionPolicy, DistributionalDoubleQ
+    R = ref_loader.load_reference()
+    torch.manual_seed(5); a = DiffusionPolicy(34, 8, 5, device="cpu")
+    torch.manual_seed(5); b = R.DiffusionPolicy(34, 8, 5, device="cpu")
+    for k, v in b.state_dict().items():
+        assert torch.equal(a.state_dict()[k], v), k
+    torch.manual_seed(6); c = DistributionalDoubleQ(29, 8, 0, 5, 51, device="cpu")
+    torch.manual_seed(6); d = R.DistributionalDoubleQ(29, 8, 0, 5, 51, device="cpu")
+    for k, v in d.state_dict().items():
+        assert torch.equal(c.state_dict()[k], v), k
+
+
+def test_unsupported_paths_fail_loudly():
+    from ddiffpg_b200 import DiffusionPolicy
+    pol = DiffusionPolicy(34, 8, 5, device="cpu")
+    with pytest.raises(NotImplementedError):
+        pol(torch.zeros(2, 34), sample=False)
+    with pytest.raises(NotImplementedError):
+        pol(torch.zeros(2, 34), add_noise=True)
+    with pytest.raises(NotImplementedError):
+        DiffusionPolicy(34, 8, 5, energy=True)
+    with pytest.raises(RuntimeError, match="CUDA only"):       # no CPU fallback
+        pol(torch.zeros(2, 34))

@@ -1,0 +1,56 @@
+"""Shared helpers for the parity tests (oracle = checker only)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import port
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def checksum(p, keys):
+    return np.array([[float(p[k].double().sum()), float(p[k].double().abs().sum())] for k in keys])
+
+
+def actor_params_for(g):
+    p = port.init_actor_params(int(g["wseed"]), scale=float(g["scale"]))
+    np.testing.assert_allclose(checksum(p, port.ACTOR_KEYS), g["checksum"], rtol=1e-12,
+                               err_msg="seeded weight generator drifted from the one that made the fixtures")
+    return p
+
+
+def critic_params_for(g):
+    p = port.init_critic_params(int(g["wseed"]), scale=float(g["scale"]))
+    np.testing.assert_allclose(checksum(p, port.CRITIC_KEYS), g["checksum"], rtol=1e-12)
+    return p
+
+
+def make_policy(params, T, precision="fp32", hidden=(1024, 512, 256), S=34, A=8):
+    from ddiffpg_b200 import DiffusionPolicy
+    pol = DiffusionPolicy(S, A, T, device="cuda", hidden=hidden, precision=precision)
+    pol.load_state_dict(params)
+    return pol.to("cuda")
+
+
+def make_critic(params, O=29, A=8, hidden=None):
+    from ddiffpg_b200 import DistributionalDoubleQ
+    c = DistributionalDoubleQ(O, A, v_min=0, v_max=5, num_atoms=51, device="cuda", hidden_layers=hidden)
+    c.load_state_dict(params)
+    return c.to("cuda")
+
+
+def assert_close(actual, expected, rtol, atol, what=""):
+    actual = torch.as_tensor(actual).detach().cpu().double()
+    expected = torch.as_tensor(expected).detach().cpu().double()
+    diff = (actual - expected).abs()
+    bound = atol + rtol * expected.abs()
+    bad = diff > bound
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} elements out of tolerance "
+                           f"(rtol={rtol}, atol={atol}); max abs diff {diff.max().item():.3e}, "
+                           f"worst ratio {(diff / bound).max().item():.2f}")
