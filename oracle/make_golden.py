@@ -161,7 +161,7 @@ def main():
         a0 = act.clone().requires_grad_(True)
         critic.get_q_min(obs, a0).sum().backward()
         mean_abs, upd, norms = ref_q_ascent(critic, obs, act.clone(), iters, 0.03)
-        m2, u2, n2 = port.q_action_ascent(params, obs, act.clone(), iters=iters, return_trace=True)
+        m2, u2, n2, gaps = port.q_action_ascent(params, obs, act.clone(), iters=iters, return_trace=True)
         d = (upd - u2).abs().max().item()
         print(f"{name}: |ref-port| ascent={d:.2e} mean|a|={mean_abs:.5f} norms[0]={norms[0]:.4e} "
               f"max norm={norms.max():.4e}")

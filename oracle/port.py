@@ -194,16 +194,24 @@ def q_action_ascent(p, obs, action, iters=20, lr=0.03, eps=1e-5, max_norm=1.0,
     """AgentDDiffPG.update_target_action, ddiffpg.py:358-373 (+ optimizer_update, ac_base.py:83-92).
 
     Uses the real torch.optim.Adam and clip_grad_norm_ like the reference.  Returns
-    (mean |a|, new action[B, A]) and optionally the per-iteration pre-clip gradient norms.
+    (mean |a|, new action[B, A]) and, with ``return_trace``, the per-iteration pre-clip gradient norms
+    and the per-iteration, per-row gap Q1-Q2 [iters, B].  The ascent climbs min(Q1, Q2), so rows drift
+    onto the ridge Q1 == Q2 where the arg-min (hence the gradient) flips on the last float bit; the
+    parity tests use the gap to treat such rows with the bound the non-smooth objective allows.
     """
     pp = {k: v.detach() for k, v in p.items()}
     action = action.detach().clone()
     lim = 1 - 1e-5
     action.clamp_(-lim, lim)
     opt = torch.optim.Adam([action], lr=lr, eps=eps, betas=betas)
-    norms = []
+    norms, gaps = [], []
     for _ in range(iters):
         action.requires_grad_(True)
+        if return_trace:
+            with torch.no_grad():
+                d1, d2 = q1_q2(pp, obs, action)
+                zz = z_atoms(v_min, v_max, d1.shape[1], d1.dtype)
+                gaps.append(((d1 * zz).sum(1) - (d2 * zz).sum(1)).clone())
         loss = -q_min(pp, obs, action, v_min, v_max).mean()
         opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -213,4 +221,4 @@ def q_action_ascent(p, obs, action, iters=20, lr=0.03, eps=1e-5, max_norm=1.0,
         action.clamp_(-lim, lim)
     out = action.detach().clone()
     res = (torch.abs(out).mean().item(), out)
-    return res + (torch.stack(norms),) if return_trace else res
+    return res + (torch.stack(norms), torch.stack(gaps)) if return_trace else res

@@ -99,7 +99,7 @@ def test_port_q_ascent_matches_reference(name):
     a = act.clone().requires_grad_(True)
     port.q_min(p, obs, a).sum().backward()
     np.testing.assert_allclose(a.grad.numpy(), g["dq_da"], rtol=1e-4, atol=1e-6)
-    mean_abs, new_a, norms = port.q_action_ascent(p, obs, act.clone(), iters=int(g["iters"]), return_trace=True)
+    mean_abs, new_a, norms, _ = port.q_action_ascent(p, obs, act.clone(), iters=int(g["iters"]), return_trace=True)
     np.testing.assert_allclose(new_a.numpy(), g["new_action"], rtol=0, atol=2e-6)
     np.testing.assert_allclose(norms.numpy(), g["norms"], rtol=1e-5)
     assert abs(mean_abs - float(g["mean_abs"])) < 1e-6

@@ -1,0 +1,275 @@
+"""GPU parity tests: the CUDA path, called through the C ABI via the host mirror, against the oracle and
+the reference-generated golden fixtures.  fp32 tolerance: rtol 1e-4 (north-star), atol 2e-5 (the fp32
+reference itself sits 1e-6..1e-5 from an fp64 run of the same chain, see tools/numerics_probe.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from tests.util import (actor_params_for, assert_ascent_close, assert_close, critic_params_for, load_golden,
+                        make_critic, make_policy)
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-4, 2e-5
+
+
+def _dev(x):
+    return torch.as_tensor(x).to("cuda")
+
+
+# ------------------------------------------------------------------------------------------ H1
+@pytest.mark.parametrize("name", ["h1_T5_B16", "h1_T20_B8", "h1_T100_B4"])
+def test_sampler_fp32_matches_reference_fixture(name):
+    g = load_golden(name)
+    pol = make_policy(actor_params_for(g), int(g["T"]))
+    out = pol.get_actions(_dev(g["state"]), noise=_dev(g["noise"]))
+    atol = ATOL if int(g["T"]) <= 20 else 1e-4          # T=100: 1/sqrt(abar_99) = 2029 amplifies fp32 noise
+    assert_close(out, g["action"], RTOL, atol, name)
+    assert out.abs().max().item() <= 1.0
+
+
+def test_sampler_fp32_chaotic_weights_within_fp64_noise_floor():
+    """Wide (x2.5) weights make the chain ill-conditioned; the bound is the fp32 reference's own distance
+    from an fp64 evaluation of the same chain."""
+    g = load_golden("h1_T5_B16_wide")
+    p = actor_params_for(g)
+    state, noise = torch.from_numpy(g["state"]), torch.from_numpy(g["noise"])
+    ref64 = port.actor_sample(port.cast_params(p, torch.float64), state.double(), noise.double(), 5)
+    floor = (torch.from_numpy(g["action"]).double() - ref64).abs().max().item()
+    out = make_policy(p, 5).get_actions(_dev(state), noise=_dev(noise)).cpu().double()
+    assert (out - ref64).abs().max().item() <= 20 * max(floor, 1e-5)
+
+
+@pytest.mark.parametrize("B", [1, 3, 20, 256, 700, 4096])
+def test_sampler_fp32_vs_oracle_batches(B):
+    T = 5
+    gen = torch.Generator().manual_seed(100 + B)
+    p = port.init_actor_params(41)
+    state = torch.randn(B, 34, generator=gen)
+    noise = torch.randn(T, B, 8, generator=gen)
+    ref = port.actor_sample(p, state, noise, T)
+    out = make_policy(p, T).get_actions(_dev(state), noise=_dev(noise))
+    assert_close(out, ref, RTOL, ATOL, f"B={B}")
+
+
+@pytest.mark.parametrize("h,T", [(256, 5), (512, 20), (256, 100)])
+def test_sampler_fp32_width_sweep(h, T):
+    B = 64
+    gen = torch.Generator().manual_seed(7 * h + T)
+    p = port.init_actor_params(43, h=h)
+    state = torch.randn(B, 34, generator=gen)
+    noise = torch.randn(T, B, 8, generator=gen)
+    ref = port.actor_sample(p, state, noise, T)
+    out = make_policy(p, T, hidden=(h, h // 2, h // 4)).get_actions(_dev(state), noise=_dev(noise))
+    assert_close(out, ref, RTOL, ATOL if T <= 20 else 1e-4, f"h={h} T={T}")
+
+
+def test_sampler_edge_cases():
+    p = port.init_actor_params(44)
+    pol = make_policy(p, 5)
+    assert pol(torch.zeros(0, 34, device="cuda")).shape == (0, 8)               # empty batch
+    with pytest.raises(ValueError):
+        pol(torch.zeros(4, 33, device="cuda"))                                   # wrong state width
+    with pytest.raises(ValueError):
+        pol.get_actions(torch.zeros(4, 34, device="cuda"), noise=torch.zeros(5, 3, 8, device="cuda"))
+    a = pol(torch.randn(33, 34, device="cuda"))                                  # device-drawn noise
+    assert a.shape == (33, 8) and torch.isfinite(a).all() and a.abs().max() <= 1.0
+    # rows are independent: a batch equals its two halves
+    gen = torch.Generator().manual_seed(3)
+    state, noise = torch.randn(50, 34, generator=gen).cuda(), torch.randn(5, 50, 8, generator=gen).cuda()
+    full = pol.get_actions(state, noise=noise)
+    lo = pol.get_actions(state[:23], noise=noise[:, :23].contiguous())
+    hi = pol.get_actions(state[23:], noise=noise[:, 23:].contiguous())
+    assert torch.equal(full, torch.cat([lo, hi]))
+
+
+def test_repack_follows_parameter_updates():
+    p = port.init_actor_params(45)
+    pol = make_policy(p, 5)
+    gen = torch.Generator().manual_seed(4)
+    state, noise = torch.randn(8, 34, generator=gen), torch.randn(5, 8, 8, generator=gen)
+    a0 = pol.get_actions(_dev(state), noise=_dev(noise))
+    with torch.no_grad():
+        for q in pol.parameters():
+            q.mul_(1.05)                                   # in-place update bumps _version -> repack
+    p2 = {k: v * 1.05 for k, v in p.items()}
+    a1 = pol.get_actions(_dev(state), noise=_dev(noise))
+    assert_close(a1, port.actor_sample(p2, state, noise, 5), RTOL, ATOL, "after in-place update")
+    assert not torch.equal(a0, a1)
+
+
+# ------------------------------------------------------------------------------------------ H2
+@pytest.mark.parametrize("name", ["h2_B32", "h2_B8_wide_clip"])
+def test_q_forward_and_ascent_match_reference_fixture(name):
+    from ddiffpg_b200 import update_target_action
+    g = load_golden(name)
+    cri = make_critic(critic_params_for(g))
+    obs, act = _dev(g["obs"]), _dev(g["action"])
+    cri.requires_grad_(False)
+    p1, p2 = cri.get_q1_q2(obs, act)
+    assert_close(p1, g["p1"], 1e-4, 1e-6, "p1")
+    assert_close(p2, g["p2"], 1e-4, 1e-6, "p2")
+    a = act.clone().requires_grad_(True)
+    q = cri.get_q_min(obs, a)
+    assert_close(q, g["q_min"], 1e-4, 1e-5, "q_min")
+    q.sum().backward()
+    assert_close(a.grad, g["dq_da"], 1e-3, 1e-5 * max(1.0, float(np.abs(g["dq_da"]).max())), "dq/da")
+    work = act.clone()
+    mean_abs, upd = update_target_action(obs, work, cri, action_lr=0.03, update_times=int(g["iters"]))
+    _, _, _, gaps = port.q_action_ascent(critic_params_for(g), torch.from_numpy(g["obs"]),
+                                         torch.from_numpy(g["action"]).clone(), iters=int(g["iters"]),
+                                         return_trace=True)
+    n_ridge = assert_ascent_close(upd, g["new_action"], gaps, int(g["iters"]), 0.03, "ascent result")
+    assert n_ridge <= 2
+    assert torch.equal(upd, work) and upd.data_ptr() != work.data_ptr()       # in place + deep copy
+    assert abs(mean_abs - float(g["mean_abs"])) < 1e-5 + 0.03 * 20 * n_ridge / upd.shape[0]
+    assert all(q.requires_grad for q in cri.parameters())                       # left as the reference leaves it
+
+
+def test_q_ascent_norm_trace_and_clip():
+    from ddiffpg_b200 import q_action_ascent_segments
+    g = load_golden("h2_B8_wide_clip")
+    cri = make_critic(critic_params_for(g))
+    work = _dev(g["action"]).clone()
+    _, norms = q_action_ascent_segments([cri], _dev(g["obs"]), work, [0, 8], iters=20, return_norms=True)
+    assert_close(norms[0], g["norms"], 2e-3, 1e-5, "pre-clip norms")
+    assert norms.max().item() > 1.0
+
+
+@pytest.mark.parametrize("B", [1, 5, 256, 1500])
+def test_q_ascent_vs_oracle_batches(B):
+    from ddiffpg_b200 import update_target_action
+    gen = torch.Generator().manual_seed(200 + B)
+    p = port.init_critic_params(51, scale=1.5)
+    obs = torch.randn(B, 29, generator=gen)
+    act = torch.rand(B, 8, generator=gen) * 2 - 1
+    m_ref, a_ref, _, gaps = port.q_action_ascent(p, obs, act.clone(), iters=20, return_trace=True)
+    work = _dev(act).clone()
+    m, upd = update_target_action(_dev(obs), work, make_critic(p))
+    n_ridge = assert_ascent_close(upd, a_ref, gaps, 20, 0.03, f"B={B}")
+    assert n_ridge <= max(1, B // 20)
+    assert abs(m - m_ref) < 1e-5 + 0.6 * n_ridge / B
+
+
+def test_q_ascent_mode_segments_equal_separate_calls():
+    """K+1 critics over rows sorted by mode == one reference call per mode (uneven, one empty segment)."""
+    from ddiffpg_b200 import q_action_ascent_segments
+    gen = torch.Generator().manual_seed(9)
+    sizes = [37, 0, 5, 130]
+    ps = [port.init_critic_params(60 + i, scale=1.0 + 0.5 * i) for i in range(len(sizes))]
+    B = sum(sizes)
+    obs = torch.randn(B, 29, generator=gen)
+    act = torch.rand(B, 8, generator=gen) * 2 - 1
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    refs, means, gaps = [], [], []
+    for i, n in enumerate(sizes):
+        if n == 0:
+            means.append(0.0)
+            continue
+        m, a, _, gp = port.q_action_ascent(ps[i], obs[off[i]:off[i + 1]], act[off[i]:off[i + 1]].clone(), iters=20,
+                                           return_trace=True)
+        refs.append(a)
+        means.append(m)
+        gaps.append(gp)
+    work = _dev(act).clone()
+    mean_abs = q_action_ascent_segments([make_critic(p) for p in ps], _dev(obs), work, off.tolist(), iters=20)
+    n_ridge = assert_ascent_close(work, torch.cat(refs), torch.cat(gaps, dim=1), 20, 0.03, "segmented ascent")
+    assert n_ridge <= 4
+    assert_close(mean_abs, means, 1e-4, 1e-5 + 0.6 * n_ridge / 5, "mean|a| per mode")
+
+
+# ------------------------------------------------------------------------------------------ H3
+def _flat(grads):
+    return torch.cat([grads[k].reshape(-1) for k in port.ACTOR_KEYS])
+
+
+@pytest.mark.parametrize("name", ["h3_T5_B64", "h3_T20_B32_wide"])
+def test_train_loss_and_grads_match_reference_fixture(name):
+    g = load_golden(name)
+    p = actor_params_for(g)
+    pol = make_policy(p, int(g["T"]))
+    loss = pol.get_loss(_dev(g["state"]), _dev(g["action"]), noise=_dev(g["noise"]),
+                        timesteps=_dev(g["timesteps"]))
+    assert loss.dim() == 0 and abs(loss.item() - float(g["loss"])) < 1e-5 * max(1.0, float(g["loss"]))
+    loss.backward()
+    params = dict(pol.named_parameters())
+    total = torch.sqrt(sum((q.grad ** 2).sum() for q in params.values())).item()
+    assert abs(total / float(g["grad_norm"]) - 1) < 1e-4
+    for i, k in enumerate(port.ACTOR_KEYS):
+        gk = params[k].grad
+        samp = gk if gk.numel() <= 4096 else gk.flatten()[::997]
+        scale = float(g[f"gnorm_{i}"]) / np.sqrt(gk.numel())            # rms of this tensor's gradient
+        assert_close(samp.reshape(-1), g[f"gsample_{i}"].reshape(-1), 1e-3, 1e-3 * scale + 1e-9, k)
+        assert abs(gk.norm().item() - float(g[f"gnorm_{i}"])) <= 1e-4 * float(g[f"gnorm_{i}"]) + 1e-9
+
+
+@pytest.mark.parametrize("B,T", [(1, 5), (37, 5), (700, 5), (2000, 20)])
+def test_train_grads_vs_oracle(B, T):
+    gen = torch.Generator().manual_seed(300 + B)
+    p = port.init_actor_params(71)
+    state = torch.randn(B, 34, generator=gen)
+    action = torch.rand(B, 8, generator=gen) * 2 - 1
+    noise = torch.randn(B, 8, generator=gen)
+    ts = torch.randint(0, T, (B,), generator=gen)
+    l_ref, g_ref = port.actor_loss_and_grads(p, state, action, noise, ts, T)
+    pol = make_policy(p, T)
+    loss = pol.get_loss(_dev(state), _dev(action), noise=_dev(noise), timesteps=_dev(ts))
+    loss.backward()
+    assert abs(loss.item() - l_ref.item()) < 1e-5 * max(1.0, l_ref.item())
+    got = torch.cat([q.grad.reshape(-1) for _, q in pol.named_parameters()]).cpu()
+    ref = _flat(g_ref)
+    rel = (got - ref).norm() / ref.norm()
+    assert rel < 1e-4, f"relative L2 error of the flat gradient {rel:.3e}"
+    for k, q in pol.named_parameters():
+        r = g_ref[k]
+        assert (q.grad.cpu() - r).abs().max() <= 1e-3 * r.abs().max() + 1e-8, k
+
+
+def _assert_params_after_adam(pol, ref_params, steps, lr):
+    """Adam normalises every element's step to ~lr, so an element whose gradient is rounding noise
+    (|g| ~ 1e-9) can legitimately land anywhere within steps*lr; everything else must agree closely."""
+    for k, q in pol.named_parameters():
+        d = (q.detach().cpu().double() - ref_params[k].double()).abs()
+        assert d.max().item() <= steps * lr * 0.1, f"{k}: max deviation {d.max().item():.3e}"
+        assert (d > 2e-6 + 1e-4 * ref_params[k].abs().double()).double().mean().item() < 1e-3, k
+        assert d.mean().item() < 2e-7, f"{k}: mean deviation {d.mean().item():.3e}"
+
+
+def test_update_actor_matches_reference_optimizer_step():
+    """get_loss + the reference's optimizer_update (AdamW, clip 1.0) for two steps == the oracle."""
+    from ddiffpg_b200 import update_actor
+    g = load_golden("h3_T5_B64")
+    p = actor_params_for(g)
+    args = (torch.from_numpy(g["state"]), torch.from_numpy(g["action"]), torch.from_numpy(g["noise"]),
+            torch.from_numpy(g["timesteps"]))
+    pol = make_policy(p, 5)
+    opt = torch.optim.AdamW(pol.parameters(), 3e-4)
+    st, cur = None, p
+    for _ in range(2):
+        loss, gnorm = update_actor(pol, opt, _dev(args[0]), _dev(args[1]), noise=_dev(args[2]), timesteps=_dev(args[3]))
+        l_ref, n_ref, cur, st = port.adamw_train_step(cur, *args, 5, opt_state=st)
+        assert abs(loss - l_ref.item()) < 1e-5 and abs(gnorm / n_ref.item() - 1) < 1e-4
+    _assert_params_after_adam(pol, cur, steps=2, lr=3e-4)
+
+
+def test_fused_trainer_matches_oracle_steps():
+    from ddiffpg_b200 import FusedActorTrainer
+    g = load_golden("h3_T20_B32_wide")
+    p = actor_params_for(g)
+    args = (torch.from_numpy(g["state"]), torch.from_numpy(g["action"]), torch.from_numpy(g["noise"]),
+            torch.from_numpy(g["timesteps"]))
+    pol = make_policy(p, 20)
+    tr = FusedActorTrainer(pol)
+    assert tuple(pol.state_dict().keys()) == port.ACTOR_KEYS
+    st, cur = None, p
+    for _ in range(3):
+        loss, gnorm = tr.step(_dev(args[0]), _dev(args[1]), noise=_dev(args[2]), timesteps=_dev(args[3]))
+        l_ref, n_ref, cur, st = port.adamw_train_step(cur, *args, 20, opt_state=st)
+        assert abs(loss.item() - l_ref.item()) < 1e-5 * max(1, l_ref.item())
+        assert abs(gnorm.item() / n_ref.item() - 1) < 1e-4
+    _assert_params_after_adam(pol, cur, steps=3, lr=3e-4)
+    # the sampler sees the updated weights
+    gen = torch.Generator().manual_seed(1)
+    s, n = torch.randn(6, 34, generator=gen), torch.randn(20, 6, 8, generator=gen)
+    assert_close(pol.get_actions(_dev(s), noise=_dev(n)), port.actor_sample(cur, s, n, 20), 1e-3, 1e-3, "post-train")

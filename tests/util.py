@@ -54,3 +54,25 @@ def assert_close(actual, expected, rtol, atol, what=""):
     assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} elements out of tolerance "
                            f"(rtol={rtol}, atol={atol}); max abs diff {diff.max().item():.3e}, "
                            f"worst ratio {(diff / bound).max().item():.2f}")
+
+
+def assert_ascent_close(actual, expected, gaps, iters, lr, what="", rtol=1e-4, atol=5e-5, ridge=2e-4):
+    """Compare Q-ascent results row by row.
+
+    The ascent maximises min(Q1, Q2); rows are attracted to the ridge Q1 == Q2, where the arg-min -- and
+    with it the whole action gradient -- flips on the last float bit (the fp32 reference itself is
+    discontinuous there).  Rows whose reference gap |Q1-Q2| ever drops below ``ridge`` are therefore only
+    required to stay within the distance Adam can open after the first possible flip (lr per iteration);
+    every other row must match to (rtol, atol)."""
+    actual = torch.as_tensor(actual).detach().cpu().double()
+    expected = torch.as_tensor(expected).detach().cpu().double()
+    gaps = torch.as_tensor(gaps).detach().cpu().abs()                    # [iters, B]
+    near = gaps < ridge
+    on_ridge = near.any(0)
+    assert_close(actual[~on_ridge], expected[~on_ridge], rtol, atol, what + " (smooth rows)")
+    if on_ridge.any():
+        first = torch.where(near, torch.arange(iters)[:, None], iters).min(0).values[on_ridge]
+        bound = (iters - first).double()[:, None] * lr * 1.05 + atol
+        diff = (actual[on_ridge] - expected[on_ridge]).abs()
+        assert (diff <= bound).all(), f"{what}: ridge rows moved further than Adam allows ({diff.max():.3e})"
+    return int(on_ridge.sum())
