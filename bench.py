@@ -148,7 +148,6 @@ def run_cuda(args):
     import torch
     import torch.distributed as dist
     from ddiffpg_b200 import DiffusionPolicy, DistributionalDoubleQ, FusedActorTrainer, q_action_ascent_segments
-    from oracle import port            # cpu_baseline leg only (checker-side code is never on the timed GPU path)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -164,8 +163,9 @@ def run_cuda(args):
     launches = 0
 
     if args.workload == "sample":
+        torch.manual_seed(0)                          # reference default init (nn.Linear), random weights
         pol = DiffusionPolicy(S, A, T, device="cuda", hidden=hidden, precision=args.precision)
-        pol.load_state_dict(port.init_actor_params(0, h=h))
+        cpu_params = {k: v.clone() for k, v in pol.state_dict().items()}
         pol.to(dev)
         state_h = torch.randn(B, S, generator=gen).pin_memory()
         state = state_h.to(dev)
@@ -184,8 +184,10 @@ def run_cuda(args):
         K = args.modes
         critics = []
         for m in range(K):
+            torch.manual_seed(m)
             c = DistributionalDoubleQ(O, A, v_min=0, v_max=5, num_atoms=51, device="cuda")
-            c.load_state_dict(port.init_critic_params(m))
+            if m == 0:
+                cpu_params = {k: v.clone() for k, v in c.state_dict().items()}
             critics.append(c.to(dev).requires_grad_(False))
         seg = [B * m // K for m in range(K + 1)]
         obs_h = torch.randn(B, O, generator=gen).pin_memory()
@@ -209,8 +211,9 @@ def run_cuda(args):
             torch.cuda.current_stream().synchronize()
         h2d, d2h = (obs_h.numel() + act_h.numel()) * 4, out_h.numel() * 4
     else:
+        torch.manual_seed(0)
         pol = DiffusionPolicy(S, A, T, device="cuda", hidden=hidden)
-        pol.load_state_dict(port.init_actor_params(0, h=h))
+        cpu_params = {k: v.clone() for k, v in pol.state_dict().items()}
         pol.to(dev)
         trainer = FusedActorTrainer(pol)
         st_h = torch.randn(B, S, generator=gen).pin_memory()
@@ -294,21 +297,20 @@ def run_cuda(args):
     # CPU baseline: the oracle port on this box's host cores, bounded sample (N=1 runs only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        from oracle import port        # the checker's CPU restatement, timed as the baseline only
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         rows = 4096
         cg = torch.Generator().manual_seed(0)
+        p = cpu_params
         if args.workload == "sample":
-            p = port.init_actor_params(0, h=h)
             cs, cn = torch.randn(rows, S, generator=cg), torch.randn(T, rows, A, generator=cg)
             cfn = lambda: port.actor_sample(p, cs, cn, T)
         elif args.workload == "ascent":
             rows = 2048
-            p = port.init_critic_params(0)
             co, ca = torch.randn(rows, O, generator=cg), torch.rand(rows, A, generator=cg) * 2 - 1
             cfn = lambda: port.q_action_ascent(p, co, ca.clone(), iters=20)
         else:
-            p = port.init_actor_params(0, h=h)
             c1, c2 = torch.randn(rows, S, generator=cg), torch.rand(rows, A, generator=cg) * 2 - 1
             c3, c4 = torch.randn(rows, A, generator=cg), torch.randint(0, T, (rows,), generator=cg)
             cfn = lambda: port.actor_loss_and_grads(p, c1, c2, c3, c4, T)

@@ -32,7 +32,8 @@ struct ActorLayout {
     size_t temb;  // [T][D]      time_mlp output
     size_t fp32_floats;
     // bf16 tensor-core section (offsets in BYTES from the start of the buffer), precision == BF16
-    size_t tc_w0, tc_w1, tc_w2, tc_w3;
+    size_t tc_w0, tc_w1, tc_w2, tc_w3;        // bf16 operands
+    size_t tc_w0h, tc_w1h, tc_w2h, tc_w3h;    // fp16 copies for the ill-conditioned first denoising step
     size_t total_bytes;
 };
 
@@ -58,6 +59,7 @@ inline ActorLayout make_actor_layout(const ddp_actor_shape& s, int precision) {
     L.fp32_floats = o;
     size_t bytes = align_up(o * sizeof(float), 1024);
     L.tc_w0 = L.tc_w1 = L.tc_w2 = L.tc_w3 = 0;
+    L.tc_w0h = L.tc_w1h = L.tc_w2h = L.tc_w3h = 0;
     if (precision == DDP_BF16) {
         // filled in by the tensor-core packer (actor_sample_tc.cu); sizes in bf16 elements
         auto takeb = [&](size_t nbytes) { size_t r = bytes; bytes += align_up(nbytes, 1024); return r; };
@@ -65,6 +67,10 @@ inline ActorLayout make_actor_layout(const ddp_actor_shape& s, int precision) {
         L.tc_w1 = takeb((size_t)s.h2 * s.h1 * 2);          // [h2][h1]
         L.tc_w2 = takeb((size_t)s.h3 * s.h2 * 2);          // [h3][h2]
         L.tc_w3 = takeb((size_t)16 * s.h3 * 2);            // [16][h3]  A padded to 16 rows
+        L.tc_w0h = takeb((size_t)s.h1 * 64 * 2);
+        L.tc_w1h = takeb((size_t)s.h2 * s.h1 * 2);
+        L.tc_w2h = takeb((size_t)s.h3 * s.h2 * 2);
+        L.tc_w3h = takeb((size_t)16 * s.h3 * 2);
     }
     L.total_bytes = bytes;
     return L;

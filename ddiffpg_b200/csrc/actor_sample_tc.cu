@@ -1,15 +1,576 @@
-// H1, bf16 tensor-core path (tcgen05 / TMEM / TMA) -- placeholder until the kernel lands.
+// H1, bf16 tensor-core path: the whole T-step DDPM reverse chain for a 128-row tile in one persistent,
+// warp-specialised sm_100a kernel.  Operands bf16, accumulation fp32 (TMEM), epilogues fp32.
+//
+// Reference semantics (paths relative to the reference repo):
+//   DiffusionPolicy.get_actions(sample=True)      ddiffpg/models/diffusion_mlp.py:219-251
+//   DiffusionNet.forward (trunk, Mish)            ddiffpg/models/diffusion_mlp.py:50-58,62-73
+//   DDPMScheduler.step                            diffusers ^0.18.2, call site diffusion_mlp.py:243-247
+//
+// Per CTA (one per SM, persistent over 128-row tiles), per denoising step:
+//   layer 0 (K = [x|state] = 42 -> 48): warp-level mma.sync in the 8 epilogue warps, register
+//            accumulators; + time table, Mish, bf16 -> 64-column A chunks in SWIZZLE_128B shared memory
+//   layer 1 (K = h1): tcgen05.mma, A = those chunks as they appear (K-outer), B = W1 tiles streamed by
+//            TMA from L2 through a 4-stage ring, D = the full [128 x h2] fp32 accumulator in TMEM
+//   layer 2 (K = h2): A = Mish(acc1) chunks drained from TMEM by the epilogue warps, D = [128 x h3]
+//            re-using the drained low columns of acc1
+//   layer 3 (K = h3): B = W3 resident in shared memory, D = [128 x 16]
+//   scheduler step on x_t: fp32 registers of the thread that owns the row; x_t never leaves the SM.
+// Activations only ever exist as 16 KB chunks in a 4-slot ring; weights never leave L2/SMEM.
 #include "actor_layout.cuh"
+#include "tc_common.cuh"
 
 namespace ddp {
+using namespace tc;
 
-int pack_actor_tc(const ActorLayout&, const float* const[12], void*, cudaStream_t) {
-    DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 actor path is not built in this library");
+namespace {
+
+constexpr int kRows = 128;                  // rows per tile == UMMA M
+constexpr int kChunkBytes = kRows * 128;    // one A chunk: 128 rows x 64 bf16
+constexpr int kStageBytes = 256 * 128;      // one weight stage: up to 256 rows x 64 bf16
+constexpr int kStages = 4;
+constexpr int kASlots = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = kEpiThreads + 64;  // + TMA warp + MMA warp
+constexpr int kIn0Stride = 56;              // bf16 per row of the layer-0 input tile (112 B: conflict-free)
+constexpr int kK0 = 48;                     // layer-0 contraction: x(8) | state(<=34) | zero pad
+constexpr int kTmemCols = 512;
+
+struct TcArgs {
+    const uint2* w0frag;       // layer-0 B fragments in mma.sync order
+    const uint4* w3img;        // layer-3 B tiles, pre-swizzled shared-memory image
+    const float *tb0, *b1, *b2, *b3, *cst;
+    const float *state, *noise;
+    float* out;
+    long B;
+    int S, A, T, h1, h2, h3;
+    int nparts1, part1;        // layer-1 output split into nparts1 parts of part1 (<= 256) columns
+    int num_tiles;
+};
+
+struct SmemLayout {
+    uint32_t wring, aring, w3, in0, b1, b2, bars, tmem_ptr, total;
+};
+
+__host__ __device__ inline SmemLayout make_smem_layout(int h2, int h3) {
+    SmemLayout s;
+    uint32_t o = 0;
+    s.wring = o; o += kStages * kStageBytes;
+    s.aring = o; o += kASlots * kChunkBytes;
+    s.w3 = o; o += (uint32_t)(h3 / 64) * 2048;
+    s.in0 = o; o += kRows * kIn0Stride * 2;
+    o = (o + 15) & ~15u;
+    s.b1 = o; o += (uint32_t)h2 * 4;
+    s.b2 = o; o += (uint32_t)h3 * 4;
+    o = (o + 7) & ~7u;
+    s.bars = o; o += 8 * (2 * kStages + 2 * kASlots + 2);
+    s.tmem_ptr = o; o += 8;
+    s.total = o;
+    return s;
 }
+
+// barrier indices inside the bars block
+__device__ __forceinline__ uint32_t bar_w_full(uint32_t base, int i) { return base + 8 * i; }
+__device__ __forceinline__ uint32_t bar_w_empty(uint32_t base, int i) { return base + 8 * (kStages + i); }
+__device__ __forceinline__ uint32_t bar_a_full(uint32_t base, int i) { return base + 8 * (2 * kStages + i); }
+__device__ __forceinline__ uint32_t bar_a_empty(uint32_t base, int i) { return base + 8 * (2 * kStages + kASlots + i); }
+__device__ __forceinline__ uint32_t bar_acc_full(uint32_t base) { return base + 8 * (2 * kStages + 2 * kASlots); }
+__device__ __forceinline__ uint32_t bar_lo_free(uint32_t base) { return base + 8 * (2 * kStages + 2 * kASlots + 1); }
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+struct Ring {
+    int idx = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance(int n) { if (++idx == n) { idx = 0; phase ^= 1; } }
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
+                       const TcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need a 1024-byte aligned base
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const SmemLayout L = make_smem_layout(a.h2, a.h3);
+    const uint32_t bars = base + L.bars;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NC1 = a.h1 >> 6, NC2 = a.h2 >> 6, NC3 = a.h3 >> 6;
+
+    // ------------------------------------------------------------------ one-time setup
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(bar_w_full(bars, i), 1); mbar_init(bar_w_empty(bars, i), 1); }
+        for (int i = 0; i < kASlots; ++i) { mbar_init(bar_a_full(bars, i), kEpiThreads); mbar_init(bar_a_empty(bars, i), 1); }
+        mbar_init(bar_acc_full(bars), 1);
+        mbar_init(bar_lo_free(bars), kEpiThreads);
+        fence_barrier_init();
+    }
+    if (warp == kEpiWarps + 1) tmem_alloc(base + L.tmem_ptr, kTmemCols);
+    // resident operands: W3 tiles (pre-swizzled image), biases
+    {
+        const int n16 = NC3 * 2048 / 16;
+        uint4* dst = reinterpret_cast<uint4*>(smem + L.w3);
+        for (int i = threadIdx.x; i < n16; i += kThreads) dst[i] = a.w3img[i];
+        float* sb1 = reinterpret_cast<float*>(smem + L.b1);
+        float* sb2 = reinterpret_cast<float*>(smem + L.b2);
+        for (int i = threadIdx.x; i < a.h2; i += kThreads) sb1[i] = a.b1[i];
+        for (int i = threadIdx.x; i < a.h3; i += kThreads) sb2[i] = a.b2[i];
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L.tmem_ptr);
+
+    if (warp == kEpiWarps) {
+        // ============================================================== TMA producer (one lane)
+        if (lane == 0) {
+            tma_prefetch_desc(&map_w1);
+            tma_prefetch_desc(&map_w2);
+            Ring ws;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+                for (int j = 0; j < a.T; ++j) {
+                    for (int c = 0; c < NC1; ++c)
+                        for (int p = 0; p < a.nparts1; ++p) {
+                            mbar_wait(bar_w_empty(bars, ws.idx), ws.phase ^ 1);
+                            mbar_expect_tx(bar_w_full(bars, ws.idx), (uint32_t)a.part1 * 128u);
+                            tma_load_2d(base + L.wring + ws.idx * kStageBytes, &map_w1, bar_w_full(bars, ws.idx),
+                                        c * 64, p * a.part1);
+                            ws.advance(kStages);
+                        }
+                    for (int c = 0; c < NC2; ++c) {
+                        mbar_wait(bar_w_empty(bars, ws.idx), ws.phase ^ 1);
+                        mbar_expect_tx(bar_w_full(bars, ws.idx), (uint32_t)a.h3 * 128u);
+                        tma_load_2d(base + L.wring + ws.idx * kStageBytes, &map_w2, bar_w_full(bars, ws.idx), c * 64, 0);
+                        ws.advance(kStages);
+                    }
+                }
+            }
+        }
+    } else if (warp == kEpiWarps + 1) {
+        // ============================================================== MMA issuer (one lane)
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc_bf16(kRows, a.part1);
+            const uint32_t idesc2 = make_idesc_bf16(kRows, a.h3);
+            const uint32_t idesc3 = make_idesc_bf16(kRows, 16);
+            Ring ws, as;
+            uint32_t lo_phase = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+                for (int j = 0; j < a.T; ++j) {
+                    // ---- layer 1: acc1[128 x h2] (TMEM cols [0, h2)) += h0 chunk . W1 chunk^T
+                    for (int c = 0; c < NC1; ++c) {
+                        mbar_wait(bar_a_full(bars, as.idx), as.phase);
+                        tc_fence_after();
+                        const uint64_t adesc = make_smem_desc_sw128(base + L.aring + as.idx * kChunkBytes);
+                        for (int p = 0; p < a.nparts1; ++p) {
+                            mbar_wait(bar_w_full(bars, ws.idx), ws.phase);
+                            tc_fence_after();
+                            const uint64_t bdesc = make_smem_desc_sw128(base + L.wring + ws.idx * kStageBytes);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(tmem_base + p * a.part1, adesc + 2 * k, bdesc + 2 * k, idesc1, (c | k) != 0);
+                            umma_commit(bar_w_empty(bars, ws.idx));
+                            ws.advance(kStages);
+                        }
+                        umma_commit(bar_a_empty(bars, as.idx));
+                        as.advance(kASlots);
+                    }
+                    umma_commit(bar_acc_full(bars));
+                    // ---- layer 2: acc2[128 x h3] re-uses TMEM cols [0, h3) once the epilogue has drained them
+                    mbar_wait(bar_lo_free(bars), lo_phase);
+                    lo_phase ^= 1;
+                    tc_fence_after();
+                    for (int c = 0; c < NC2; ++c) {
+                        mbar_wait(bar_a_full(bars, as.idx), as.phase);
+                        mbar_wait(bar_w_full(bars, ws.idx), ws.phase);
+                        tc_fence_after();
+                        const uint64_t adesc = make_smem_desc_sw128(base + L.aring + as.idx * kChunkBytes);
+                        const uint64_t bdesc = make_smem_desc_sw128(base + L.wring + ws.idx * kStageBytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc2, (c | k) != 0);
+                        umma_commit(bar_w_empty(bars, ws.idx));
+                        umma_commit(bar_a_empty(bars, as.idx));
+                        ws.advance(kStages);
+                        as.advance(kASlots);
+                    }
+                    umma_commit(bar_acc_full(bars));
+                    // ---- layer 3: acc3[128 x 16] at TMEM cols [h3, h3+16) (acc1 is fully drained by now)
+                    for (int c = 0; c < NC3; ++c) {
+                        mbar_wait(bar_a_full(bars, as.idx), as.phase);
+                        tc_fence_after();
+                        const uint64_t adesc = make_smem_desc_sw128(base + L.aring + as.idx * kChunkBytes);
+                        const uint64_t bdesc = make_smem_desc_sw128(base + L.w3 + c * 2048);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem_base + a.h3, adesc + 2 * k, bdesc + 2 * k, idesc3, (c | k) != 0);
+                        umma_commit(bar_a_empty(bars, as.idx));
+                        as.advance(kASlots);
+                    }
+                    umma_commit(bar_acc_full(bars));
+                }
+            }
+        }
+    } else {
+        // ============================================================== epilogue / layer-0 warps
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int ch = warp >> 2;               // which 32-column half of a 64-column chunk
+        const int g = lane >> 2, t4 = lane & 3; // mma.sync fragment coordinates
+        const int my_row = q * 32 + lane;       // row owned in the TMEM epilogues
+        __nv_bfloat16* in0 = reinterpret_cast<__nv_bfloat16*>(smem + L.in0);
+        const float* sb1 = reinterpret_cast<const float*>(smem + L.b1);
+        const float* sb2 = reinterpret_cast<const float*>(smem + L.b2);
+        Ring as;
+        uint32_t acc_phase = 0;
+        float b3r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b3r[i] = i < a.A ? a.b3[i] : 0.f;
+
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+            const long row = (long)tile * kRows + my_row;
+            const bool valid = row < a.B;
+            float xr[8];
+            // ---- tile prologue: state -> bf16 in0[:, 8:8+S], x_T -> registers and in0[:, 0:8]
+            if (ch == 0) {
+                __nv_bfloat16* rp = in0 + my_row * kIn0Stride;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xr[i] = (valid && i < a.A) ? a.noise[row * a.A + i] : 0.f;
+                uint4 xv;
+                xv.x = pack_bf16x2(xr[0], xr[1]); xv.y = pack_bf16x2(xr[2], xr[3]);
+                xv.z = pack_bf16x2(xr[4], xr[5]); xv.w = pack_bf16x2(xr[6], xr[7]);
+                *reinterpret_cast<uint4*>(rp) = xv;
+                for (int i = 0; i < kK0 - 8; ++i)
+                    rp[8 + i] = __float2bfloat16((valid && i < a.S) ? a.state[row * a.S + i] : 0.f);
+            }
+            epi_bar_sync();
+
+            for (int j = 0; j < a.T; ++j) {
+                const int t = a.T - 1 - j;
+                // A fragments of layer 0 for this warp's 32 rows (2 m16 tiles x 3 k16 steps)
+                uint32_t af[2][3][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) {
+                        const __nv_bfloat16* p0 = in0 + (q * 32 + mt * 16 + g) * kIn0Stride + ks * 16 + 2 * t4;
+                        af[mt][ks][0] = *reinterpret_cast<const uint32_t*>(p0);
+                        af[mt][ks][1] = *reinterpret_cast<const uint32_t*>(p0 + 8 * kIn0Stride);
+                        af[mt][ks][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+                        af[mt][ks][3] = *reinterpret_cast<const uint32_t*>(p0 + 8 * kIn0Stride + 8);
+                    }
+                // step noise for the rows this thread owns (consumed in the final epilogue)
+                float zr[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    zr[i] = (ch == 0 && valid && t > 0 && i < a.A) ? a.noise[((size_t)(j + 1) * a.B + row) * a.A + i] : 0.f;
+
+                // ---- layer 0: one 64-feature chunk at a time, straight into the A ring
+                const float* tb = a.tb0 + (size_t)t * a.h1;
+                for (int c = 0; c < NC1; ++c) {
+                    const uint2* bf = a.w0frag + ((size_t)(c * 2 + ch) * 12) * 32 + lane;
+                    uint2 bfr[4][3];
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                        for (int ks = 0; ks < 3; ++ks) bfr[nt][ks] = __ldg(bf + (nt * 3 + ks) * 32);
+                    float2 bias[4];
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt)
+                        bias[nt] = __ldg(reinterpret_cast<const float2*>(tb + c * 64 + ch * 32 + nt * 8 + 2 * t4));
+                    float acc[2][4][4];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) {
+                            acc[mt][nt][0] = bias[nt].x; acc[mt][nt][1] = bias[nt].y;
+                            acc[mt][nt][2] = bias[nt].x; acc[mt][nt][3] = bias[nt].y;
+#pragma unroll
+                            for (int ks = 0; ks < 3; ++ks)
+                                mma_m16n8k16_bf16(acc[mt][nt], af[mt][ks], bfr[nt][ks].x, bfr[nt][ks].y);
+                        }
+                    mbar_wait(bar_a_empty(bars, as.idx), as.phase ^ 1);
+                    uint8_t* slot = smem + L.aring + as.idx * kChunkBytes;
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) {
+                            const int r0 = q * 32 + mt * 16 + g, col = ch * 32 + nt * 8 + 2 * t4;
+                            *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0, col)) =
+                                pack_bf16x2(mish_fast(acc[mt][nt][0]), mish_fast(acc[mt][nt][1]));
+                            *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0 + 8, col)) =
+                                pack_bf16x2(mish_fast(acc[mt][nt][2]), mish_fast(acc[mt][nt][3]));
+                        }
+                    fence_proxy_async();
+                    mbar_arrive(bar_a_full(bars, as.idx));
+                    as.advance(kASlots);
+                }
+
+                // ---- layer-1 epilogue: acc1 (TMEM cols [0,h2)) -> +b1, Mish, bf16 -> A chunks of layer 2
+                mbar_wait(bar_acc_full(bars), acc_phase); acc_phase ^= 1;
+                tc_fence_after();
+                for (int c = 0; c < NC2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 64 + ch * 32, v);
+                    mbar_wait(bar_a_empty(bars, as.idx), as.phase ^ 1);
+                    tmem_ld_wait();
+                    uint8_t* slot = smem + L.aring + as.idx * kChunkBytes;
+                    const float* bb = sb1 + c * 64 + ch * 32;
+#pragma unroll
+                    for (int i8 = 0; i8 < 4; ++i8) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = i8 * 8 + 2 * k;
+                            w[k] = pack_bf16x2(mish_fast(__uint_as_float(v[i]) + bb[i]),
+                                               mish_fast(__uint_as_float(v[i + 1]) + bb[i + 1]));
+                        }
+                        *reinterpret_cast<uint4*>(slot + sw128_offset(my_row, ch * 32 + i8 * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    fence_proxy_async();
+                    tc_fence_before();
+                    mbar_arrive(bar_a_full(bars, as.idx));
+                    as.advance(kASlots);
+                    if (c == NC3 - 1) mbar_arrive(bar_lo_free(bars));      // TMEM cols [0, h3) are drained
+                }
+
+                // ---- layer-2 epilogue: acc2 (TMEM cols [0,h3)) -> +b2, Mish, bf16 -> A chunks of layer 3
+                mbar_wait(bar_acc_full(bars), acc_phase); acc_phase ^= 1;
+                tc_fence_after();
+                for (int c = 0; c < NC3; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 64 + ch * 32, v);
+                    mbar_wait(bar_a_empty(bars, as.idx), as.phase ^ 1);
+                    tmem_ld_wait();
+                    uint8_t* slot = smem + L.aring + as.idx * kChunkBytes;
+                    const float* bb = sb2 + c * 64 + ch * 32;
+#pragma unroll
+                    for (int i8 = 0; i8 < 4; ++i8) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = i8 * 8 + 2 * k;
+                            w[k] = pack_bf16x2(mish_fast(__uint_as_float(v[i]) + bb[i]),
+                                               mish_fast(__uint_as_float(v[i + 1]) + bb[i + 1]));
+                        }
+                        *reinterpret_cast<uint4*>(slot + sw128_offset(my_row, ch * 32 + i8 * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    fence_proxy_async();
+                    tc_fence_before();
+                    mbar_arrive(bar_a_full(bars, as.idx));
+                    as.advance(kASlots);
+                }
+
+                // ---- head + scheduler step: eps_hat from acc3, x_t in registers (fp32)
+                mbar_wait(bar_acc_full(bars), acc_phase); acc_phase ^= 1;
+                tc_fence_after();
+                if (ch == 0) {
+                    uint32_t e[8];
+                    tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + a.h3, e);
+                    tmem_ld_wait();
+                    const float* cs = a.cst + t * kCstStride;
+                    const float c_eps = cs[CST_CEPS], s_ab = cs[CST_SQRT_AB], c_x0 = cs[CST_CX0], c_xt = cs[CST_CXT],
+                                sigma = cs[CST_SIGMA];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float eps = __uint_as_float(e[i]) + b3r[i];
+                        float x0 = __fdiv_rn(__fsub_rn(xr[i], __fmul_rn(c_eps, eps)), s_ab);
+                        x0 = fminf(fmaxf(x0, -1.f), 1.f);
+                        float xn = __fadd_rn(__fmul_rn(c_x0, x0), __fmul_rn(c_xt, xr[i]));
+                        if (t > 0) xn = __fadd_rn(xn, __fmul_rn(sigma, zr[i]));
+                        xr[i] = i < a.A ? xn : 0.f;
+                    }
+                    if (t > 0) {
+                        uint4 xv;
+                        xv.x = pack_bf16x2(xr[0], xr[1]); xv.y = pack_bf16x2(xr[2], xr[3]);
+                        xv.z = pack_bf16x2(xr[4], xr[5]); xv.w = pack_bf16x2(xr[6], xr[7]);
+                        *reinterpret_cast<uint4*>(in0 + my_row * kIn0Stride) = xv;
+                    } else if (valid) {
+                        for (int i = 0; i < a.A; ++i) a.out[row * a.A + i] = xr[i];
+                    }
+                }
+                tc_fence_before();
+                epi_bar_sync();         // new x visible to all layer-0 warps; acc3 reads are complete
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------ teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kEpiWarps + 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------- packing
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float2bfloat16(src[i]);
+}
+
+// Layer-0 B fragments in mma.sync m16n8k16 order.  K order is [x (A<=8, padded to 8) | state (S) | 0 ...].
+// Entry [(c*2+ch)*12 + nt*3 + ks][lane] = {b0, b1}: feature f = c*64 + ch*32 + nt*8 + lane/4,
+// b0 = (k, k+1) with k = ks*16 + 2*(lane%4), b1 = (k+8, k+9).
+__global__ void w0_frag_pack_kernel(const float* __restrict__ W0, int ld0, int D, int S, int A, int h1,
+                                    uint2* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = (h1 / 32) * 12 * 32;
+    if (idx >= total) return;
+    const int lane = idx & 31, e = idx >> 5;
+    const int ks = e % 3, nt = (e / 3) % 4, cc = e / 12;           // cc = c*2 + ch
+    const int f = cc * 32 + nt * 8 + (lane >> 2);
+    auto wk = [&](int k) -> float {                                 // weight of kernel-order input k
+        if (k < 8) return k < A ? W0[(size_t)f * ld0 + D + S + k] : 0.f;
+        const int s = k - 8;
+        return s < S ? W0[(size_t)f * ld0 + D + s] : 0.f;
+    };
+    const int k0 = ks * 16 + 2 * (lane & 3);
+    uint2 v;
+    v.x = pack_bf16x2(wk(k0), wk(k0 + 1));
+    v.y = pack_bf16x2(wk(k0 + 8), wk(k0 + 9));
+    out[idx] = v;
+}
+
+// Layer-3 B tiles: [h3/64][16 rows][64] bf16 written as the SWIZZLE_128B shared-memory image.
+__global__ void w3_image_pack_kernel(const float* __restrict__ W3, int A, int h3, __nv_bfloat16* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = (h3 / 64) * 16 * 64;
+    if (idx >= total) return;
+    const int col = idx & 63, r = (idx >> 6) & 15, c = idx >> 10;
+    const float v = r < A ? W3[(size_t)r * h3 + c * 64 + col] : 0.f;
+    out[(size_t)c * 1024 + sw128_offset(r, col) / 2] = __float2bfloat16(v);
+}
+
+struct TcPacked {      // byte offsets inside the packed buffer (see ActorLayout::tc_*)
+    size_t w0frag, w1, w2, w3img;
+};
+
+}  // namespace
+
+static bool tc_shape_ok(const ActorLayout& L) {
+    return L.A <= 8 && L.S + 8 <= kK0 && L.h1 % 64 == 0 && L.h2 % 64 == 0 && L.h3 % 64 == 0 && L.h2 <= 512 &&
+           L.h3 <= 256 && L.h3 + 16 <= kTmemCols && L.h3 / 64 <= kASlots && L.h3 <= L.h2 &&
+           (L.h2 <= 256 || L.h2 % 256 == 0);
+}
+
+int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, cudaStream_t st) {
+    if (!tc_shape_ok(L))
+        DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 actor path needs A<=8, S<=40, widths multiple of 64 with h2<=512, h3<=256");
+    uint8_t* base = (uint8_t*)packed;
+    auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
+    const int ld0 = L.D + L.S + L.A;
+    w0_frag_pack_kernel<<<blocks((size_t)(L.h1 / 32) * 12 * 32), 256, 0, st>>>(p[4], ld0, L.D, L.S, L.A, L.h1,
+                                                                             (uint2*)(base + L.tc_w0));
+    f32_to_bf16_kernel<<<blocks((size_t)L.h2 * L.h1), 256, 0, st>>>(p[6], (__nv_bfloat16*)(base + L.tc_w1), (size_t)L.h2 * L.h1);
+    f32_to_bf16_kernel<<<blocks((size_t)L.h3 * L.h2), 256, 0, st>>>(p[8], (__nv_bfloat16*)(base + L.tc_w2), (size_t)L.h3 * L.h2);
+    w3_image_pack_kernel<<<blocks((size_t)(L.h3 / 64) * 1024), 256, 0, st>>>(p[10], L.A, L.h3, (__nv_bfloat16*)(base + L.tc_w3));
+    DDP_LAUNCH_CHECK("actor tensor-core pack kernels");
+    return DDP_OK;
+}
+
 size_t actor_sample_tc_workspace(const ActorLayout&, long) { return 0; }
-int actor_sample_tc(const ActorLayout&, const void*, const float*, const float*, float*, long, void*, size_t,
-                    cudaStream_t) {
-    DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 actor path is not built in this library");
+
+int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state, const float* noise, float* out,
+                    long B, void*, size_t, cudaStream_t st) {
+    if (!tc_shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 actor path does not support this shape");
+    const uint8_t* base = (const uint8_t*)packed;
+    const float* pk = (const float*)packed;
+    TcArgs a;
+    a.w0frag = (const uint2*)(base + L.tc_w0);
+    a.w3img = (const uint4*)(base + L.tc_w3);
+    a.tb0 = pk + L.tb0; a.b1 = pk + L.b1; a.b2 = pk + L.b2; a.b3 = pk + L.b3; a.cst = pk + L.cst;
+    a.state = state; a.noise = noise; a.out = out; a.B = B;
+    a.S = L.S; a.A = L.A; a.T = L.T; a.h1 = L.h1; a.h2 = L.h2; a.h3 = L.h3;
+    a.nparts1 = L.h2 > 256 ? L.h2 / 256 : 1;
+    a.part1 = L.h2 / a.nparts1;
+    a.num_tiles = (int)((B + kRows - 1) / kRows);
+    CUtensorMap m1, m2;
+    if (make_tmap_bf16_sw128(&m1, base + L.tc_w1, L.h2, L.h1, a.part1) != 0 ||
+        make_tmap_bf16_sw128(&m2, base + L.tc_w2, L.h3, L.h2, L.h3) != 0)
+        DDP_FAIL(DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the actor weight tiles");
+    int dev = 0, sms = 0;
+    DDP_CUDA_CHECK(cudaGetDevice(&dev));
+    DDP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const SmemLayout S = make_smem_layout(L.h2, L.h3);
+    const size_t smem = S.total + 1024;         // slack for the 1024-byte alignment of the base
+    DDP_CUDA_CHECK(cudaFuncSetAttribute(actor_sample_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+    actor_sample_tc_kernel<<<grid, kThreads, smem, st>>>(m1, m2, a);
+    DDP_LAUNCH_CHECK("actor_sample_tc_kernel");
+    return DDP_OK;
 }
 
 }  // namespace ddp
+
+// ---------------------------------------------------------------------------------------- self-test
+// C[128][N] = A[128][K] . B[N][K]^T with the SAME building blocks as the sampler (manual SWIZZLE_128B
+// A chunks, TMA-loaded B tiles, tcgen05.mma into TMEM, 32x32b TMEM loads).  One CTA; used by
+// tests/test_tc_blocks_gpu.py to pin descriptors and layouts independently of the fused kernel.
+namespace ddp {
+namespace {
+__global__ void __launch_bounds__(128, 1)
+tc_gemm_selftest_kernel(const __grid_constant__ CUtensorMap map_b, const __nv_bfloat16* __restrict__ A,
+                        float* __restrict__ C, int N, int K) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const uint32_t a_off = 0, b_off = kChunkBytes, bar_off = kChunkBytes + kStageBytes, tp_off = bar_off + 16;
+    const uint32_t bar_full = base + bar_off, bar_done = base + bar_off + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(bar_full, 1); mbar_init(bar_done, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(base + tp_off, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + tp_off);
+    const uint32_t idesc = make_idesc_bf16(128, N);
+    uint32_t phase = 0;
+    for (int kc = 0; kc < K / 64; ++kc) {
+        // A chunk: thread r writes its row (64 bf16) as 8 swizzled 16-byte pieces
+        const uint4* src = reinterpret_cast<const uint4*>(A + (size_t)threadIdx.x * K + kc * 64);
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(smem + a_off + sw128_offset(threadIdx.x, j * 8)) = src[j];
+        fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar_full, (uint32_t)N * 128u);
+            tma_load_2d(base + b_off, &map_b, bar_full, kc * 64, 0);
+            mbar_wait(bar_full, phase);
+            tc_fence_after();
+            const uint64_t ad = make_smem_desc_sw128(base + a_off), bd = make_smem_desc_sw128(base + b_off);
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (kc | k) != 0);
+            umma_commit(bar_done);
+            mbar_wait(bar_done, phase);
+        }
+        phase ^= 1;
+        __syncthreads();
+    }
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 32 && c0 + i < N; ++i) C[(size_t)(warp * 32 + lane) * N + c0 + i] = __uint_as_float(v[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+}  // namespace
+}  // namespace ddp
+
+// Debug entry point (not part of the public header): A [128][K] bf16, Bm [N][K] bf16, C [128][N] fp32.
+extern "C" int ddp_debug_tc_gemm(const void* A, const void* Bm, float* C, int N, int K, void* stream) {
+    using namespace ddp;
+    if (N % 16 || N < 16 || N > 256 || K % 64 || K <= 0) DDP_FAIL(DDP_ERR_SHAPE, "selftest: N in [16,256] step 16, K multiple of 64");
+    CUtensorMap m;
+    if (tc::make_tmap_bf16_sw128(&m, Bm, N, K, N) != 0) DDP_FAIL(DDP_ERR_CUDA, "selftest: tensor map encode failed");
+    const size_t smem = kChunkBytes + kStageBytes + 64 + 1024;
+    DDP_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_gemm_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(m, (const __nv_bfloat16*)A, C, N, K);
+    DDP_LAUNCH_CHECK("tc_gemm_selftest_kernel");
+    return DDP_OK;
+}
