@@ -343,13 +343,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="sample", choices=["sample", "ascent", "train"])
-    ap.add_argument("--precision", default=os.environ.get("DDP_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16"],
+                    help="default: bf16 tensor path for the sampler, fp32 for ascent/train")
     ap.add_argument("--batch", type=int, default=65536, help="rows per GPU")
     ap.add_argument("--T", type=int, default=5)
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--modes", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.precision is None:
+        args.precision = os.environ.get("DDP_BENCH_PRECISION", "bf16" if args.workload == "sample" else "fp32")
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -16,6 +16,7 @@
 //   layer 3 (K = h3): B = W3 resident in shared memory, D = [128 x 16]
 //   scheduler step on x_t: fp32 registers of the thread that owns the row; x_t never leaves the SM.
 // Activations only ever exist as 16 KB chunks in a 4-slot ring; weights never leave L2/SMEM.
+#include <stdlib.h>
 #include "actor_layout.cuh"
 #include "tc_common.cuh"
 
@@ -37,8 +38,11 @@ constexpr int kK0 = 48;                     // layer-0 contraction: x(8) | state
 constexpr int kTmemCols = 512;
 
 struct TcArgs {
-    const uint2* w0frag;       // layer-0 B fragments in mma.sync order
-    const uint4* w3img;        // layer-3 B tiles, pre-swizzled shared-memory image
+    const uint2* w0frag;       // layer-0 B fragments in mma.sync order (bf16)
+    const uint2* w0frag_h;     // same, fp16 (first denoising step)
+    const uint4* w3img;        // layer-3 B tiles, pre-swizzled shared-memory image (bf16)
+    const uint4* w3img_h;      // same, fp16
+    int first_f16;             // 1: step t = T-1 runs with fp16 operands (numerics)
     const float *tb0, *b1, *b2, *b3, *cst;
     const float *state, *noise;
     float* out;
@@ -57,7 +61,7 @@ __host__ __device__ inline SmemLayout make_smem_layout(int h2, int h3) {
     uint32_t o = 0;
     s.wring = o; o += kStages * kStageBytes;
     s.aring = o; o += kASlots * kChunkBytes;
-    s.w3 = o; o += (uint32_t)(h3 / 64) * 2048;
+    s.w3 = o; o += (uint32_t)(h3 / 64) * 2048 * 2;      // bf16 image then fp16 image
     s.in0 = o; o += kRows * kIn0Stride * 2;
     o = (o + 15) & ~15u;
     s.b1 = o; o += (uint32_t)h2 * 4;
@@ -85,8 +89,171 @@ struct Ring {
     __device__ __forceinline__ void advance(int n) { if (++idx == n) { idx = 0; phase ^= 1; } }
 };
 
+// Per-thread state of an epilogue / layer-0 warp.
+struct EpiCtx {
+    uint8_t* smem;
+    SmemLayout L;
+    uint32_t bars, tmem_base, acc_phase;
+    int q, ch, g, t4, lane, my_row;     // TMEM lane quarter, 32-column half, mma.sync coords, owned row
+    int NC1, NC2, NC3;
+    Ring as;
+    long row;
+    bool valid;
+    float xr[8];                        // x_t of the owned row (ch == 0 threads), fp32
+    float b3r[8];
+};
+
+// [x (8) | state (S) | 0 ...] of the owned row into the layer-0 input tile, in the operand format F16/bf16
+template <bool F16>
+__device__ __forceinline__ void write_in0_row(const TcArgs& a, const EpiCtx& e, bool with_state) {
+    uint16_t* rp = reinterpret_cast<uint16_t*>(e.smem + e.L.in0) + e.my_row * kIn0Stride;
+    uint4 xv;
+    xv.x = pack2<F16>(e.xr[0], e.xr[1]); xv.y = pack2<F16>(e.xr[2], e.xr[3]);
+    xv.z = pack2<F16>(e.xr[4], e.xr[5]); xv.w = pack2<F16>(e.xr[6], e.xr[7]);
+    *reinterpret_cast<uint4*>(rp) = xv;
+    if (with_state)
+        for (int i = 0; i < kK0 - 8; ++i)
+            rp[8 + i] = cvt16<F16>((e.valid && i < a.S) ? a.state[e.row * a.S + i] : 0.f);
+}
+
+// TMEM accumulator columns [col0, col0+64) of this warp's rows -> +bias, Mish, 16-bit -> one A chunk
+template <bool F16>
+__device__ __forceinline__ void drain_chunk(EpiCtx& e, int tmem_col, const float* bb) {
+    uint32_t v[32];
+    tmem_ld32(e.tmem_base + ((uint32_t)(e.q * 32) << 16) + tmem_col + e.ch * 32, v);
+    mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
+    tmem_ld_wait();
+    uint8_t* slot = e.smem + e.L.aring + e.as.idx * kChunkBytes;
+#pragma unroll
+    for (int i8 = 0; i8 < 4; ++i8) {
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = i8 * 8 + 2 * k;
+            w[k] = pack2<F16>(mish_fast(__uint_as_float(v[i]) + bb[i]), mish_fast(__uint_as_float(v[i + 1]) + bb[i + 1]));
+        }
+        *reinterpret_cast<uint4*>(slot + sw128_offset(e.my_row, e.ch * 32 + i8 * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    mbar_arrive(bar_a_full(e.bars, e.as.idx));
+    e.as.advance(kASlots);
+}
+
+// One denoising step of the epilogue warps (operand format of THIS step = F16 ? fp16 : bf16).
+template <bool F16>
+__device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
+    const int t = a.T - 1 - j;
+    const uint16_t* in0 = reinterpret_cast<const uint16_t*>(e.smem + e.L.in0);
+    // A fragments of layer 0 for this warp's 32 rows (2 m16 tiles x 3 k16 steps)
+    uint32_t af[2][3][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+            const uint16_t* p0 = in0 + (e.q * 32 + mt * 16 + e.g) * kIn0Stride + ks * 16 + 2 * e.t4;
+            af[mt][ks][0] = *reinterpret_cast<const uint32_t*>(p0);
+            af[mt][ks][1] = *reinterpret_cast<const uint32_t*>(p0 + 8 * kIn0Stride);
+            af[mt][ks][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+            af[mt][ks][3] = *reinterpret_cast<const uint32_t*>(p0 + 8 * kIn0Stride + 8);
+        }
+    // step noise for the row this thread owns (consumed in the final epilogue)
+    float zr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        zr[i] = (e.ch == 0 && e.valid && t > 0 && i < a.A) ? a.noise[((size_t)(j + 1) * a.B + e.row) * a.A + i] : 0.f;
+
+    // ---- layer 0: one 64-feature chunk at a time, straight into the A ring
+    const float* tb = a.tb0 + (size_t)t * a.h1;
+    const uint2* wf = F16 ? a.w0frag_h : a.w0frag;
+    for (int c = 0; c < e.NC1; ++c) {
+        const uint2* bf = wf + ((size_t)(c * 2 + e.ch) * 12) * 32 + e.lane;
+        uint2 bfr[4][3];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) bfr[nt][ks] = __ldg(bf + (nt * 3 + ks) * 32);
+        float2 bias[4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+            bias[nt] = __ldg(reinterpret_cast<const float2*>(tb + c * 64 + e.ch * 32 + nt * 8 + 2 * e.t4));
+        float acc[2][4][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                acc[mt][nt][0] = bias[nt].x; acc[mt][nt][1] = bias[nt].y;
+                acc[mt][nt][2] = bias[nt].x; acc[mt][nt][3] = bias[nt].y;
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks)
+                    mma_m16n8k16<F16>(acc[mt][nt], af[mt][ks], bfr[nt][ks].x, bfr[nt][ks].y);
+            }
+        mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
+        uint8_t* slot = e.smem + e.L.aring + e.as.idx * kChunkBytes;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int r0 = e.q * 32 + mt * 16 + e.g, col = e.ch * 32 + nt * 8 + 2 * e.t4;
+                *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0, col)) =
+                    pack2<F16>(mish_fast(acc[mt][nt][0]), mish_fast(acc[mt][nt][1]));
+                *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0 + 8, col)) =
+                    pack2<F16>(mish_fast(acc[mt][nt][2]), mish_fast(acc[mt][nt][3]));
+            }
+        fence_proxy_async();
+        mbar_arrive(bar_a_full(e.bars, e.as.idx));
+        e.as.advance(kASlots);
+    }
+
+    // ---- layer-1 epilogue: acc1 (TMEM cols [0,h2)) -> +b1, Mish -> A chunks of layer 2
+    const float* sb1 = reinterpret_cast<const float*>(e.smem + e.L.b1);
+    const float* sb2 = reinterpret_cast<const float*>(e.smem + e.L.b2);
+    mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
+    tc_fence_after();
+    for (int c = 0; c < e.NC2; ++c) {
+        drain_chunk<F16>(e, c * 64, sb1 + c * 64 + e.ch * 32);
+        if (c == e.NC3 - 1) mbar_arrive(bar_lo_free(e.bars));      // TMEM cols [0, h3) are drained
+    }
+    // ---- layer-2 epilogue: acc2 (TMEM cols [0,h3)) -> +b2, Mish -> A chunks of layer 3
+    mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
+    tc_fence_after();
+    for (int c = 0; c < e.NC3; ++c) drain_chunk<F16>(e, c * 64, sb2 + c * 64 + e.ch * 32);
+
+    // ---- head + scheduler step: eps_hat from acc3, x_t in registers (fp32)
+    mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
+    tc_fence_after();
+    if (e.ch == 0) {
+        uint32_t ev[8];
+        tmem_ld8(e.tmem_base + ((uint32_t)(e.q * 32) << 16) + a.h3, ev);
+        tmem_ld_wait();
+        const float* cs = a.cst + t * kCstStride;
+        const float c_eps = cs[CST_CEPS], s_ab = cs[CST_SQRT_AB], c_x0 = cs[CST_CX0], c_xt = cs[CST_CXT],
+                    sigma = cs[CST_SIGMA];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float eps = __uint_as_float(ev[i]) + e.b3r[i];
+            float x0 = __fdiv_rn(__fsub_rn(e.xr[i], __fmul_rn(c_eps, eps)), s_ab);
+            x0 = fminf(fmaxf(x0, -1.f), 1.f);
+            float xn = __fadd_rn(__fmul_rn(c_x0, x0), __fmul_rn(c_xt, e.xr[i]));
+            if (t > 0) xn = __fadd_rn(xn, __fmul_rn(sigma, zr[i]));
+            e.xr[i] = i < a.A ? xn : 0.f;
+        }
+        if (t > 0) {
+            // the next step runs in bf16; after an fp16 step the state columns are re-written as bf16 too
+            write_in0_row<false>(a, e, F16);
+        } else if (e.valid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < a.A) a.out[e.row * a.A + i] = e.xr[i];
+        }
+    }
+    tc_fence_before();
+    epi_bar_sync();         // new x visible to all layer-0 warps; acc3 reads are complete
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
+                       const __grid_constant__ CUtensorMap map_w1h, const __grid_constant__ CUtensorMap map_w2h,
                        const TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // SWIZZLE_128B tiles need a 1024-byte aligned base
@@ -111,7 +278,7 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
     {
         const int n16 = NC3 * 2048 / 16;
         uint4* dst = reinterpret_cast<uint4*>(smem + L.w3);
-        for (int i = threadIdx.x; i < n16; i += kThreads) dst[i] = a.w3img[i];
+        for (int i = threadIdx.x; i < n16; i += kThreads) { dst[i] = a.w3img[i]; dst[n16 + i] = a.w3img_h[i]; }
         float* sb1 = reinterpret_cast<float*>(smem + L.b1);
         float* sb2 = reinterpret_cast<float*>(smem + L.b2);
         for (int i = threadIdx.x; i < a.h2; i += kThreads) sb1[i] = a.b1[i];
@@ -128,21 +295,26 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
         if (lane == 0) {
             tma_prefetch_desc(&map_w1);
             tma_prefetch_desc(&map_w2);
+            tma_prefetch_desc(&map_w1h);
+            tma_prefetch_desc(&map_w2h);
             Ring ws;
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
                 for (int j = 0; j < a.T; ++j) {
+                    const bool f16 = a.first_f16 && j == 0;
+                    const CUtensorMap* m1 = f16 ? &map_w1h : &map_w1;
+                    const CUtensorMap* m2 = f16 ? &map_w2h : &map_w2;
                     for (int c = 0; c < NC1; ++c)
                         for (int p = 0; p < a.nparts1; ++p) {
                             mbar_wait(bar_w_empty(bars, ws.idx), ws.phase ^ 1);
                             mbar_expect_tx(bar_w_full(bars, ws.idx), (uint32_t)a.part1 * 128u);
-                            tma_load_2d(base + L.wring + ws.idx * kStageBytes, &map_w1, bar_w_full(bars, ws.idx),
+                            tma_load_2d(base + L.wring + ws.idx * kStageBytes, m1, bar_w_full(bars, ws.idx),
                                         c * 64, p * a.part1);
                             ws.advance(kStages);
                         }
                     for (int c = 0; c < NC2; ++c) {
                         mbar_wait(bar_w_empty(bars, ws.idx), ws.phase ^ 1);
                         mbar_expect_tx(bar_w_full(bars, ws.idx), (uint32_t)a.h3 * 128u);
-                        tma_load_2d(base + L.wring + ws.idx * kStageBytes, &map_w2, bar_w_full(bars, ws.idx), c * 64, 0);
+                        tma_load_2d(base + L.wring + ws.idx * kStageBytes, m2, bar_w_full(bars, ws.idx), c * 64, 0);
                         ws.advance(kStages);
                     }
                 }
@@ -151,13 +323,15 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
     } else if (warp == kEpiWarps + 1) {
         // ============================================================== MMA issuer (one lane)
         if (lane == 0) {
-            const uint32_t idesc1 = make_idesc_bf16(kRows, a.part1);
-            const uint32_t idesc2 = make_idesc_bf16(kRows, a.h3);
-            const uint32_t idesc3 = make_idesc_bf16(kRows, 16);
             Ring ws, as;
             uint32_t lo_phase = 0;
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
                 for (int j = 0; j < a.T; ++j) {
+                    const bool f16 = a.first_f16 && j == 0;
+                    const uint32_t idesc1 = make_idesc_16(kRows, a.part1, f16);
+                    const uint32_t idesc2 = make_idesc_16(kRows, a.h3, f16);
+                    const uint32_t idesc3 = make_idesc_16(kRows, 16, f16);
+                    const uint32_t w3base = base + L.w3 + (f16 ? NC3 * 2048 : 0);
                     // ---- layer 1: acc1[128 x h2] (TMEM cols [0, h2)) += h0 chunk . W1 chunk^T
                     for (int c = 0; c < NC1; ++c) {
                         mbar_wait(bar_a_full(bars, as.idx), as.phase);
@@ -201,7 +375,7 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
                         mbar_wait(bar_a_full(bars, as.idx), as.phase);
                         tc_fence_after();
                         const uint64_t adesc = make_smem_desc_sw128(base + L.aring + as.idx * kChunkBytes);
-                        const uint64_t bdesc = make_smem_desc_sw128(base + L.w3 + c * 2048);
+                        const uint64_t bdesc = make_smem_desc_sw128(w3base + c * 2048);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_bf16(tmem_base + a.h3, adesc + 2 * k, bdesc + 2 * k, idesc3, (c | k) != 0);
@@ -214,183 +388,27 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
         }
     } else {
         // ============================================================== epilogue / layer-0 warps
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int ch = warp >> 2;               // which 32-column half of a 64-column chunk
-        const int g = lane >> 2, t4 = lane & 3; // mma.sync fragment coordinates
-        const int my_row = q * 32 + lane;       // row owned in the TMEM epilogues
-        __nv_bfloat16* in0 = reinterpret_cast<__nv_bfloat16*>(smem + L.in0);
-        const float* sb1 = reinterpret_cast<const float*>(smem + L.b1);
-        const float* sb2 = reinterpret_cast<const float*>(smem + L.b2);
-        Ring as;
-        uint32_t acc_phase = 0;
-        float b3r[8];
+        EpiCtx e;
+        e.smem = smem; e.L = L; e.bars = bars; e.tmem_base = tmem_base;
+        e.q = warp & 3; e.ch = warp >> 2; e.g = lane >> 2; e.t4 = lane & 3; e.lane = lane;
+        e.my_row = e.q * 32 + lane;
+        e.NC1 = NC1; e.NC2 = NC2; e.NC3 = NC3;
+        e.acc_phase = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b3r[i] = i < a.A ? a.b3[i] : 0.f;
+        for (int i = 0; i < 8; ++i) e.b3r[i] = i < a.A ? a.b3[i] : 0.f;
 
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-            const long row = (long)tile * kRows + my_row;
-            const bool valid = row < a.B;
-            float xr[8];
-            // ---- tile prologue: state -> bf16 in0[:, 8:8+S], x_T -> registers and in0[:, 0:8]
-            if (ch == 0) {
-                __nv_bfloat16* rp = in0 + my_row * kIn0Stride;
+            e.row = (long)tile * kRows + e.my_row;
+            e.valid = e.row < a.B;
+            // ---- tile prologue: x_T -> registers; [x | state | 0] -> in0 in the first step's operand format
+            if (e.ch == 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) xr[i] = (valid && i < a.A) ? a.noise[row * a.A + i] : 0.f;
-                uint4 xv;
-                xv.x = pack_bf16x2(xr[0], xr[1]); xv.y = pack_bf16x2(xr[2], xr[3]);
-                xv.z = pack_bf16x2(xr[4], xr[5]); xv.w = pack_bf16x2(xr[6], xr[7]);
-                *reinterpret_cast<uint4*>(rp) = xv;
-                for (int i = 0; i < kK0 - 8; ++i)
-                    rp[8 + i] = __float2bfloat16((valid && i < a.S) ? a.state[row * a.S + i] : 0.f);
+                for (int i = 0; i < 8; ++i) e.xr[i] = (e.valid && i < a.A) ? a.noise[e.row * a.A + i] : 0.f;
+                if (a.first_f16) write_in0_row<true>(a, e, true); else write_in0_row<false>(a, e, true);
             }
             epi_bar_sync();
-
             for (int j = 0; j < a.T; ++j) {
-                const int t = a.T - 1 - j;
-                // A fragments of layer 0 for this warp's 32 rows (2 m16 tiles x 3 k16 steps)
-                uint32_t af[2][3][4];
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                    for (int ks = 0; ks < 3; ++ks) {
-                        const __nv_bfloat16* p0 = in0 + (q * 32 + mt * 16 + g) * kIn0Stride + ks * 16 + 2 * t4;
-                        af[mt][ks][0] = *reinterpret_cast<const uint32_t*>(p0);
-                        af[mt][ks][1] = *reinterpret_cast<const uint32_t*>(p0 + 8 * kIn0Stride);
-                        af[mt][ks][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
-                        af[mt][ks][3] = *reinterpret_cast<const uint32_t*>(p0 + 8 * kIn0Stride + 8);
-                    }
-                // step noise for the rows this thread owns (consumed in the final epilogue)
-                float zr[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    zr[i] = (ch == 0 && valid && t > 0 && i < a.A) ? a.noise[((size_t)(j + 1) * a.B + row) * a.A + i] : 0.f;
-
-                // ---- layer 0: one 64-feature chunk at a time, straight into the A ring
-                const float* tb = a.tb0 + (size_t)t * a.h1;
-                for (int c = 0; c < NC1; ++c) {
-                    const uint2* bf = a.w0frag + ((size_t)(c * 2 + ch) * 12) * 32 + lane;
-                    uint2 bfr[4][3];
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                        for (int ks = 0; ks < 3; ++ks) bfr[nt][ks] = __ldg(bf + (nt * 3 + ks) * 32);
-                    float2 bias[4];
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt)
-                        bias[nt] = __ldg(reinterpret_cast<const float2*>(tb + c * 64 + ch * 32 + nt * 8 + 2 * t4));
-                    float acc[2][4][4];
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                        for (int nt = 0; nt < 4; ++nt) {
-                            acc[mt][nt][0] = bias[nt].x; acc[mt][nt][1] = bias[nt].y;
-                            acc[mt][nt][2] = bias[nt].x; acc[mt][nt][3] = bias[nt].y;
-#pragma unroll
-                            for (int ks = 0; ks < 3; ++ks)
-                                mma_m16n8k16_bf16(acc[mt][nt], af[mt][ks], bfr[nt][ks].x, bfr[nt][ks].y);
-                        }
-                    mbar_wait(bar_a_empty(bars, as.idx), as.phase ^ 1);
-                    uint8_t* slot = smem + L.aring + as.idx * kChunkBytes;
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                        for (int nt = 0; nt < 4; ++nt) {
-                            const int r0 = q * 32 + mt * 16 + g, col = ch * 32 + nt * 8 + 2 * t4;
-                            *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0, col)) =
-                                pack_bf16x2(mish_fast(acc[mt][nt][0]), mish_fast(acc[mt][nt][1]));
-                            *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0 + 8, col)) =
-                                pack_bf16x2(mish_fast(acc[mt][nt][2]), mish_fast(acc[mt][nt][3]));
-                        }
-                    fence_proxy_async();
-                    mbar_arrive(bar_a_full(bars, as.idx));
-                    as.advance(kASlots);
-                }
-
-                // ---- layer-1 epilogue: acc1 (TMEM cols [0,h2)) -> +b1, Mish, bf16 -> A chunks of layer 2
-                mbar_wait(bar_acc_full(bars), acc_phase); acc_phase ^= 1;
-                tc_fence_after();
-                for (int c = 0; c < NC2; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 64 + ch * 32, v);
-                    mbar_wait(bar_a_empty(bars, as.idx), as.phase ^ 1);
-                    tmem_ld_wait();
-                    uint8_t* slot = smem + L.aring + as.idx * kChunkBytes;
-                    const float* bb = sb1 + c * 64 + ch * 32;
-#pragma unroll
-                    for (int i8 = 0; i8 < 4; ++i8) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int i = i8 * 8 + 2 * k;
-                            w[k] = pack_bf16x2(mish_fast(__uint_as_float(v[i]) + bb[i]),
-                                               mish_fast(__uint_as_float(v[i + 1]) + bb[i + 1]));
-                        }
-                        *reinterpret_cast<uint4*>(slot + sw128_offset(my_row, ch * 32 + i8 * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                    fence_proxy_async();
-                    tc_fence_before();
-                    mbar_arrive(bar_a_full(bars, as.idx));
-                    as.advance(kASlots);
-                    if (c == NC3 - 1) mbar_arrive(bar_lo_free(bars));      // TMEM cols [0, h3) are drained
-                }
-
-                // ---- layer-2 epilogue: acc2 (TMEM cols [0,h3)) -> +b2, Mish, bf16 -> A chunks of layer 3
-                mbar_wait(bar_acc_full(bars), acc_phase); acc_phase ^= 1;
-                tc_fence_after();
-                for (int c = 0; c < NC3; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 64 + ch * 32, v);
-                    mbar_wait(bar_a_empty(bars, as.idx), as.phase ^ 1);
-                    tmem_ld_wait();
-                    uint8_t* slot = smem + L.aring + as.idx * kChunkBytes;
-                    const float* bb = sb2 + c * 64 + ch * 32;
-#pragma unroll
-                    for (int i8 = 0; i8 < 4; ++i8) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int i = i8 * 8 + 2 * k;
-                            w[k] = pack_bf16x2(mish_fast(__uint_as_float(v[i]) + bb[i]),
-                                               mish_fast(__uint_as_float(v[i + 1]) + bb[i + 1]));
-                        }
-                        *reinterpret_cast<uint4*>(slot + sw128_offset(my_row, ch * 32 + i8 * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                    fence_proxy_async();
-                    tc_fence_before();
-                    mbar_arrive(bar_a_full(bars, as.idx));
-                    as.advance(kASlots);
-                }
-
-                // ---- head + scheduler step: eps_hat from acc3, x_t in registers (fp32)
-                mbar_wait(bar_acc_full(bars), acc_phase); acc_phase ^= 1;
-                tc_fence_after();
-                if (ch == 0) {
-                    uint32_t e[8];
-                    tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + a.h3, e);
-                    tmem_ld_wait();
-                    const float* cs = a.cst + t * kCstStride;
-                    const float c_eps = cs[CST_CEPS], s_ab = cs[CST_SQRT_AB], c_x0 = cs[CST_CX0], c_xt = cs[CST_CXT],
-                                sigma = cs[CST_SIGMA];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float eps = __uint_as_float(e[i]) + b3r[i];
-                        float x0 = __fdiv_rn(__fsub_rn(xr[i], __fmul_rn(c_eps, eps)), s_ab);
-                        x0 = fminf(fmaxf(x0, -1.f), 1.f);
-                        float xn = __fadd_rn(__fmul_rn(c_x0, x0), __fmul_rn(c_xt, xr[i]));
-                        if (t > 0) xn = __fadd_rn(xn, __fmul_rn(sigma, zr[i]));
-                        xr[i] = i < a.A ? xn : 0.f;
-                    }
-                    if (t > 0) {
-                        uint4 xv;
-                        xv.x = pack_bf16x2(xr[0], xr[1]); xv.y = pack_bf16x2(xr[2], xr[3]);
-                        xv.z = pack_bf16x2(xr[4], xr[5]); xv.w = pack_bf16x2(xr[6], xr[7]);
-                        *reinterpret_cast<uint4*>(in0 + my_row * kIn0Stride) = xv;
-                    } else if (valid) {
-                        for (int i = 0; i < a.A; ++i) a.out[row * a.A + i] = xr[i];
-                    }
-                }
-                tc_fence_before();
-                epi_bar_sync();         // new x visible to all layer-0 warps; acc3 reads are complete
+                if (a.first_f16 && j == 0) epi_step<true>(a, e, j); else epi_step<false>(a, e, j);
             }
         }
     }
@@ -405,14 +423,16 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
 }
 
 // ---------------------------------------------------------------------------------------- packing
-__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+template <bool F16>
+__global__ void f32_to_16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = __float2bfloat16(src[i]);
+    if (i < n) dst[i] = cvt16<F16>(src[i]);
 }
 
 // Layer-0 B fragments in mma.sync m16n8k16 order.  K order is [x (A<=8, padded to 8) | state (S) | 0 ...].
 // Entry [(c*2+ch)*12 + nt*3 + ks][lane] = {b0, b1}: feature f = c*64 + ch*32 + nt*8 + lane/4,
 // b0 = (k, k+1) with k = ks*16 + 2*(lane%4), b1 = (k+8, k+9).
+template <bool F16>
 __global__ void w0_frag_pack_kernel(const float* __restrict__ W0, int ld0, int D, int S, int A, int h1,
                                     uint2* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -428,19 +448,20 @@ __global__ void w0_frag_pack_kernel(const float* __restrict__ W0, int ld0, int D
     };
     const int k0 = ks * 16 + 2 * (lane & 3);
     uint2 v;
-    v.x = pack_bf16x2(wk(k0), wk(k0 + 1));
-    v.y = pack_bf16x2(wk(k0 + 8), wk(k0 + 9));
+    v.x = pack2<F16>(wk(k0), wk(k0 + 1));
+    v.y = pack2<F16>(wk(k0 + 8), wk(k0 + 9));
     out[idx] = v;
 }
 
 // Layer-3 B tiles: [h3/64][16 rows][64] bf16 written as the SWIZZLE_128B shared-memory image.
-__global__ void w3_image_pack_kernel(const float* __restrict__ W3, int A, int h3, __nv_bfloat16* __restrict__ out) {
+template <bool F16>
+__global__ void w3_image_pack_kernel(const float* __restrict__ W3, int A, int h3, uint16_t* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = (h3 / 64) * 16 * 64;
     if (idx >= total) return;
     const int col = idx & 63, r = (idx >> 6) & 15, c = idx >> 10;
     const float v = r < A ? W3[(size_t)r * h3 + c * 64 + col] : 0.f;
-    out[(size_t)c * 1024 + sw128_offset(r, col) / 2] = __float2bfloat16(v);
+    out[(size_t)c * 1024 + sw128_offset(r, col) / 2] = cvt16<F16>(v);
 }
 
 struct TcPacked {      // byte offsets inside the packed buffer (see ActorLayout::tc_*)
@@ -461,11 +482,16 @@ int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, 
     uint8_t* base = (uint8_t*)packed;
     auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
     const int ld0 = L.D + L.S + L.A;
-    w0_frag_pack_kernel<<<blocks((size_t)(L.h1 / 32) * 12 * 32), 256, 0, st>>>(p[4], ld0, L.D, L.S, L.A, L.h1,
-                                                                             (uint2*)(base + L.tc_w0));
-    f32_to_bf16_kernel<<<blocks((size_t)L.h2 * L.h1), 256, 0, st>>>(p[6], (__nv_bfloat16*)(base + L.tc_w1), (size_t)L.h2 * L.h1);
-    f32_to_bf16_kernel<<<blocks((size_t)L.h3 * L.h2), 256, 0, st>>>(p[8], (__nv_bfloat16*)(base + L.tc_w2), (size_t)L.h3 * L.h2);
-    w3_image_pack_kernel<<<blocks((size_t)(L.h3 / 64) * 1024), 256, 0, st>>>(p[10], L.A, L.h3, (__nv_bfloat16*)(base + L.tc_w3));
+    const size_t n0 = (size_t)(L.h1 / 32) * 12 * 32, n1 = (size_t)L.h2 * L.h1, n2 = (size_t)L.h3 * L.h2,
+                 n3 = (size_t)(L.h3 / 64) * 1024;
+    w0_frag_pack_kernel<false><<<blocks(n0), 256, 0, st>>>(p[4], ld0, L.D, L.S, L.A, L.h1, (uint2*)(base + L.tc_w0));
+    w0_frag_pack_kernel<true><<<blocks(n0), 256, 0, st>>>(p[4], ld0, L.D, L.S, L.A, L.h1, (uint2*)(base + L.tc_w0h));
+    f32_to_16_kernel<false><<<blocks(n1), 256, 0, st>>>(p[6], (uint16_t*)(base + L.tc_w1), n1);
+    f32_to_16_kernel<true><<<blocks(n1), 256, 0, st>>>(p[6], (uint16_t*)(base + L.tc_w1h), n1);
+    f32_to_16_kernel<false><<<blocks(n2), 256, 0, st>>>(p[8], (uint16_t*)(base + L.tc_w2), n2);
+    f32_to_16_kernel<true><<<blocks(n2), 256, 0, st>>>(p[8], (uint16_t*)(base + L.tc_w2h), n2);
+    w3_image_pack_kernel<false><<<blocks(n3), 256, 0, st>>>(p[10], L.A, L.h3, (uint16_t*)(base + L.tc_w3));
+    w3_image_pack_kernel<true><<<blocks(n3), 256, 0, st>>>(p[10], L.A, L.h3, (uint16_t*)(base + L.tc_w3h));
     DDP_LAUNCH_CHECK("actor tensor-core pack kernels");
     return DDP_OK;
 }
@@ -479,16 +505,25 @@ int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state
     const float* pk = (const float*)packed;
     TcArgs a;
     a.w0frag = (const uint2*)(base + L.tc_w0);
+    a.w0frag_h = (const uint2*)(base + L.tc_w0h);
     a.w3img = (const uint4*)(base + L.tc_w3);
+    a.w3img_h = (const uint4*)(base + L.tc_w3h);
+    // The first reverse step divides by sqrt(abar_{T-1}) (1e2..2e3): bf16 operand rounding of eps_hat would
+    // surface as ~1e-2 action errors, so that one step uses fp16 operands (same tensor rate, 3 more mantissa
+    // bits).  DDP_TC_PURE_BF16=1 keeps every step in bf16 (for measurements).
+    static const bool pure_bf16 = getenv("DDP_TC_PURE_BF16") && atoi(getenv("DDP_TC_PURE_BF16")) != 0;
+    a.first_f16 = pure_bf16 ? 0 : 1;
     a.tb0 = pk + L.tb0; a.b1 = pk + L.b1; a.b2 = pk + L.b2; a.b3 = pk + L.b3; a.cst = pk + L.cst;
     a.state = state; a.noise = noise; a.out = out; a.B = B;
     a.S = L.S; a.A = L.A; a.T = L.T; a.h1 = L.h1; a.h2 = L.h2; a.h3 = L.h3;
     a.nparts1 = L.h2 > 256 ? L.h2 / 256 : 1;
     a.part1 = L.h2 / a.nparts1;
     a.num_tiles = (int)((B + kRows - 1) / kRows);
-    CUtensorMap m1, m2;
+    CUtensorMap m1, m2, m1h, m2h;
     if (make_tmap_bf16_sw128(&m1, base + L.tc_w1, L.h2, L.h1, a.part1) != 0 ||
-        make_tmap_bf16_sw128(&m2, base + L.tc_w2, L.h3, L.h2, L.h3) != 0)
+        make_tmap_bf16_sw128(&m2, base + L.tc_w2, L.h3, L.h2, L.h3) != 0 ||
+        make_tmap_bf16_sw128(&m1h, base + L.tc_w1h, L.h2, L.h1, a.part1, true) != 0 ||
+        make_tmap_bf16_sw128(&m2h, base + L.tc_w2h, L.h3, L.h2, L.h3, true) != 0)
         DDP_FAIL(DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the actor weight tiles");
     int dev = 0, sms = 0;
     DDP_CUDA_CHECK(cudaGetDevice(&dev));
@@ -497,7 +532,7 @@ int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state
     const size_t smem = S.total + 1024;         // slack for the 1024-byte alignment of the base
     DDP_CUDA_CHECK(cudaFuncSetAttribute(actor_sample_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    actor_sample_tc_kernel<<<grid, kThreads, smem, st>>>(m1, m2, a);
+    actor_sample_tc_kernel<<<grid, kThreads, smem, st>>>(m1, m2, m1h, m2h, a);
     DDP_LAUNCH_CHECK("actor_sample_tc_kernel");
     return DDP_OK;
 }
