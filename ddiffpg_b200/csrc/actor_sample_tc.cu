@@ -33,6 +33,8 @@ constexpr int kASlots = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kEpiThreads + 64;  // + TMA warp + MMA warp
+constexpr int kRegsEpilogue = 224;          // setmaxnreg budgets (per thread) after the role split
+constexpr int kRegsProducer = 64;
 constexpr int kIn0Stride = 56;              // bf16 per row of the layer-0 input tile (112 B: conflict-free)
 constexpr int kK0 = 48;                     // layer-0 contraction: x(8) | state(<=34) | zero pad
 constexpr int kTmemCols = 512;
@@ -100,7 +102,6 @@ struct EpiCtx {
     long row;
     bool valid;
     float xr[8];                        // x_t of the owned row (ch == 0 threads), fp32
-    float b3r[8];
 };
 
 // [x (8) | state (S) | 0 ...] of the owned row into the layer-0 input tile, in the operand format F16/bf16
@@ -116,28 +117,47 @@ __device__ __forceinline__ void write_in0_row(const TcArgs& a, const EpiCtx& e, 
             rp[8 + i] = cvt16<F16>((e.valid && i < a.S) ? a.state[e.row * a.S + i] : 0.f);
 }
 
-// TMEM accumulator columns [col0, col0+64) of this warp's rows -> +bias, Mish, 16-bit -> one A chunk
+// 16 accumulator columns (already in registers) of this thread's row -> +bias, Mish, 16-bit -> two
+// 16-byte pieces of the A chunk slot (columns col0 .. col0+15 of the 64-column chunk)
 template <bool F16>
-__device__ __forceinline__ void drain_chunk(EpiCtx& e, int tmem_col, const float* bb) {
-    uint32_t v[32];
-    tmem_ld32(e.tmem_base + ((uint32_t)(e.q * 32) << 16) + tmem_col + e.ch * 32, v);
-    mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
-    tmem_ld_wait();
-    uint8_t* slot = e.smem + e.L.aring + e.as.idx * kChunkBytes;
+__device__ __forceinline__ void emit_half(const EpiCtx& e, uint8_t* slot, const uint32_t (&v)[16], const float* bb, int col0) {
 #pragma unroll
-    for (int i8 = 0; i8 < 4; ++i8) {
-        uint32_t w[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = i8 * 8 + 2 * k;
-            w[k] = pack2<F16>(mish_fast(__uint_as_float(v[i]) + bb[i]), mish_fast(__uint_as_float(v[i + 1]) + bb[i + 1]));
-        }
-        *reinterpret_cast<uint4*>(slot + sw128_offset(e.my_row, e.ch * 32 + i8 * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int i8 = 0; i8 < 2; ++i8) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bb + i8 * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bb + i8 * 8 + 4);
+        uint4 w;
+        w.x = pack2<F16>(mish_fast(__uint_as_float(v[i8 * 8 + 0]) + b0.x), mish_fast(__uint_as_float(v[i8 * 8 + 1]) + b0.y));
+        w.y = pack2<F16>(mish_fast(__uint_as_float(v[i8 * 8 + 2]) + b0.z), mish_fast(__uint_as_float(v[i8 * 8 + 3]) + b0.w));
+        w.z = pack2<F16>(mish_fast(__uint_as_float(v[i8 * 8 + 4]) + b1.x), mish_fast(__uint_as_float(v[i8 * 8 + 5]) + b1.y));
+        w.w = pack2<F16>(mish_fast(__uint_as_float(v[i8 * 8 + 6]) + b1.z), mish_fast(__uint_as_float(v[i8 * 8 + 7]) + b1.w));
+        *reinterpret_cast<uint4*>(slot + sw128_offset(e.my_row, col0 + i8 * 8)) = w;
     }
-    fence_proxy_async();
-    tc_fence_before();
-    mbar_arrive(bar_a_full(e.bars, e.as.idx));
-    e.as.advance(kASlots);
+}
+
+// Drain `nchunks` 64-column chunks of the accumulator at TMEM column 0 into the A ring.  This warp owns 32
+// columns of each chunk, moved as two 16-column TMEM loads: while one half goes through Mish the next load is
+// in flight (two 16-register buffers).  After chunk `signal_after` the thread arrives on lo_free (-1: never).
+template <bool F16>
+__device__ __forceinline__ void drain_acc(EpiCtx& e, int nchunks, const float* bias, int signal_after) {
+    const uint32_t tbase = e.tmem_base + ((uint32_t)(e.q * 32) << 16) + e.ch * 32;
+    uint32_t va[16], vb[16];
+    tmem_ld16(tbase, va);
+    for (int c = 0; c < nchunks; ++c) {
+        const float* bb = bias + c * 64 + e.ch * 32;
+        tmem_ld_wait();
+        tmem_ld16(tbase + c * 64 + 16, vb);
+        mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
+        uint8_t* slot = e.smem + e.L.aring + e.as.idx * kChunkBytes;
+        emit_half<F16>(e, slot, va, bb, e.ch * 32);
+        tmem_ld_wait();
+        if (c + 1 < nchunks) tmem_ld16(tbase + (c + 1) * 64, va);
+        emit_half<F16>(e, slot, vb, bb + 16, e.ch * 32 + 16);
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_a_full(e.bars, e.as.idx));
+        e.as.advance(kASlots);
+        if (c == signal_after) mbar_arrive(bar_lo_free(e.bars));
+    }
 }
 
 // One denoising step of the epilogue warps (operand format of THIS step = F16 ? fp16 : bf16).
@@ -157,26 +177,23 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
             af[mt][ks][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
             af[mt][ks][3] = *reinterpret_cast<const uint32_t*>(p0 + 8 * kIn0Stride + 8);
         }
-    // step noise for the row this thread owns (consumed in the final epilogue)
-    float zr[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        zr[i] = (e.ch == 0 && e.valid && t > 0 && i < a.A) ? a.noise[((size_t)(j + 1) * a.B + e.row) * a.A + i] : 0.f;
-
     // ---- layer 0: one 64-feature chunk at a time, straight into the A ring
     const float* tb = a.tb0 + (size_t)t * a.h1;
     const uint2* wf = F16 ? a.w0frag_h : a.w0frag;
-    for (int c = 0; c < e.NC1; ++c) {
+    uint2 bfr[4][3];
+    float2 bias[4];
+    auto load_frags = [&](int c, uint2 (&f)[4][3], float2 (&b)[4]) {
         const uint2* bf = wf + ((size_t)(c * 2 + e.ch) * 12) * 32 + e.lane;
-        uint2 bfr[4][3];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-            for (int ks = 0; ks < 3; ++ks) bfr[nt][ks] = __ldg(bf + (nt * 3 + ks) * 32);
-        float2 bias[4];
+            for (int ks = 0; ks < 3; ++ks) f[nt][ks] = __ldg(bf + (nt * 3 + ks) * 32);
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
-            bias[nt] = __ldg(reinterpret_cast<const float2*>(tb + c * 64 + e.ch * 32 + nt * 8 + 2 * e.t4));
+            b[nt] = __ldg(reinterpret_cast<const float2*>(tb + c * 64 + e.ch * 32 + nt * 8 + 2 * e.t4));
+    };
+    load_frags(0, bfr, bias);
+    for (int c = 0; c < e.NC1; ++c) {
         float acc[2][4][4];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
@@ -188,6 +205,9 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
                 for (int ks = 0; ks < 3; ++ks)
                     mma_m16n8k16<F16>(acc[mt][nt], af[mt][ks], bfr[nt][ks].x, bfr[nt][ks].y);
             }
+        // the fragment registers are dead after the HMMAs: refill them for the next chunk now, so the
+        // loads are in flight during the Mish / store phase
+        if (c + 1 < e.NC1) load_frags(c + 1, bfr, bias);
         mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
         uint8_t* slot = e.smem + e.L.aring + e.as.idx * kChunkBytes;
 #pragma unroll
@@ -210,14 +230,18 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
     const float* sb2 = reinterpret_cast<const float*>(e.smem + e.L.b2);
     mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
     tc_fence_after();
-    for (int c = 0; c < e.NC2; ++c) {
-        drain_chunk<F16>(e, c * 64, sb1 + c * 64 + e.ch * 32);
-        if (c == e.NC3 - 1) mbar_arrive(bar_lo_free(e.bars));      // TMEM cols [0, h3) are drained
+    drain_acc<F16>(e, e.NC2, sb1, e.NC3 - 1);          // lo_free: TMEM cols [0, h3) are drained
+    // step noise and head bias for the row this thread owns: issued here, consumed in the final epilogue
+    float zr[8], b3r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        zr[i] = (e.ch == 0 && e.valid && t > 0 && i < a.A) ? __ldg(a.noise + ((size_t)(j + 1) * a.B + e.row) * a.A + i) : 0.f;
+        b3r[i] = i < a.A ? __ldg(a.b3 + i) : 0.f;
     }
     // ---- layer-2 epilogue: acc2 (TMEM cols [0,h3)) -> +b2, Mish -> A chunks of layer 3
     mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
     tc_fence_after();
-    for (int c = 0; c < e.NC3; ++c) drain_chunk<F16>(e, c * 64, sb2 + c * 64 + e.ch * 32);
+    drain_acc<F16>(e, e.NC3, sb2, -1);
 
     // ---- head + scheduler step: eps_hat from acc3, x_t in registers (fp32)
     mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
@@ -231,7 +255,7 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
                     sigma = cs[CST_SIGMA];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float eps = __uint_as_float(ev[i]) + e.b3r[i];
+            const float eps = __uint_as_float(ev[i]) + b3r[i];
             float x0 = __fdiv_rn(__fsub_rn(e.xr[i], __fmul_rn(c_eps, eps)), s_ab);
             x0 = fminf(fmaxf(x0, -1.f), 1.f);
             float xn = __fadd_rn(__fmul_rn(c_x0, x0), __fmul_rn(c_xt, e.xr[i]));
@@ -386,7 +410,7 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
                 }
             }
         }
-    } else {
+    } else if (warp < kEpiWarps) {
         // ============================================================== epilogue / layer-0 warps
         EpiCtx e;
         e.smem = smem; e.L = L; e.bars = bars; e.tmem_base = tmem_base;
@@ -394,9 +418,6 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
         e.my_row = e.q * 32 + lane;
         e.NC1 = NC1; e.NC2 = NC2; e.NC3 = NC3;
         e.acc_phase = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) e.b3r[i] = i < a.A ? a.b3[i] : 0.f;
-
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
             e.row = (long)tile * kRows + e.my_row;
             e.valid = e.row < a.B;

@@ -26,19 +26,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+    // the last operand is the suspend-time hint: the warp sleeps in hardware instead of spinning
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     return ok != 0;
 }
 // Bounded spin: a protocol bug must surface as a trap (reported by the next CUDA call), not as a hang
 // of the GPU box.  ~2^28 polls is seconds; a healthy wait is microseconds.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 28)) { asm volatile("trap;"); }
+        if (++spins > (1u << 24)) { asm volatile("trap;"); }
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -114,6 +116,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -168,11 +178,17 @@ __device__ __forceinline__ void mma_m16n8k16(float (&c)[4], const uint32_t (&a)[
     if (F16) mma_m16n8k16_f16(c, a, b0, b1); else mma_m16n8k16_bf16(c, a, b0, b1);
 }
 
-// Mish with fast intrinsics (ex2.approx + rcp.approx): relative error ~1e-6, far below bf16's 2^-9
+// Mish for the 16-bit epilogues: 7 FP32 + 2 MUFU instructions.  With e = exp(x), s = e + 1:
+// tanh(softplus(x)) = (s^2 - 1)/(s^2 + 1) = 1 - 2/(s^2 + 1), so mish(x) = x - 2x / (s^2 + 1).
+// ex2.approx / rcp.approx are ~2^-22 relative, far below the 2^-9 (bf16) / 2^-11 (fp16) of the output;
+// the exponent is capped at x = 20 (mish(x) = x to fp32 there, s^2 stays finite).
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mish_fast(float x) {
-    const float e = __expf(fminf(x, 20.f));
-    const float n = e * (e + 2.f);
-    return x * __fdividef(n, n + 2.f);
+    const float t = fminf(x * 1.4426950408889634f, 28.853900817779268f);
+    const float s = ex2_approx(t) + 1.f;
+    const float r = rcp_approx(fmaf(s, s, 1.f));
+    return fmaf(-2.f * x, r, x);
 }
 
 // ------------------------------------------------------------------------------------ host: tensor maps
