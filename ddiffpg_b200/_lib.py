@@ -7,7 +7,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_long, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libddiffpg_b200.so")
+LIB_PATH = os.environ.get("DDP_LIB_PATH") or os.path.join(HERE, "libddiffpg_b200.so")   # override: A/B builds
 
 DDP_FP32, DDP_BF16 = 0, 1
 PRECISIONS = {"fp32": DDP_FP32, "bf16": DDP_BF16}

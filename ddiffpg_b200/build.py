@@ -33,6 +33,20 @@ def nvcc_path():
     return "nvcc"
 
 
+def build_variant(out, defines):
+    """Experimental A/B build: same sources with extra -D flags into another .so (see DDP_LIB_PATH)."""
+    objdir = os.path.join(HERE, "build", "variant_" + os.path.basename(out))
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        subprocess.run([nvcc_path(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj],
+                       check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        objs.append(obj)
+    subprocess.run([nvcc_path(), "-shared", "-cudart", "static", "-o", out, *objs], check=True)
+    return out
+
+
 def build(force=False, verbose=True):
     """Compile every .cu under csrc/ into one shared library.  Skips when sources are unchanged."""
     dig = _digest()

@@ -30,7 +30,12 @@ constexpr int kChunkBytes = kRows * 128;    // one A chunk: 128 rows x 64 bf16
 constexpr int kStageBytes = 256 * 128;      // one weight stage: up to 256 rows x 64 bf16
 constexpr int kStages = 4;
 constexpr int kASlots = 4;
-constexpr int kEpiWarps = 8;
+#ifndef DDP_TC_EPI_WARPS
+#define DDP_TC_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = DDP_TC_EPI_WARPS;  // 8 or 16 (2 or 4 per SM sub-partition)
+constexpr int kColsPerWarp = 64 / (kEpiWarps / 4);   // columns of a 64-column chunk owned by one warp (32 or 16)
+constexpr int kNT = kColsPerWarp / 8;        // mma.sync n8 tiles per warp in layer 0
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kEpiThreads + 64;  // + TMA warp + MMA warp
 constexpr int kRegsEpilogue = 224;          // setmaxnreg budgets (per thread) after the role split
@@ -96,7 +101,7 @@ struct EpiCtx {
     uint8_t* smem;
     SmemLayout L;
     uint32_t bars, tmem_base, acc_phase;
-    int q, ch, g, t4, lane, my_row;     // TMEM lane quarter, 32-column half, mma.sync coords, owned row
+    int q, ch, g, t4, lane, my_row;     // TMEM lane quarter, column group of the chunk, mma.sync coords, owned row
     int NC1, NC2, NC3;
     Ring as;
     long row;
@@ -134,29 +139,49 @@ __device__ __forceinline__ void emit_half(const EpiCtx& e, uint8_t* slot, const 
     }
 }
 
-// Drain `nchunks` 64-column chunks of the accumulator at TMEM column 0 into the A ring.  This warp owns 32
-// columns of each chunk, moved as two 16-column TMEM loads: while one half goes through Mish the next load is
-// in flight (two 16-register buffers).  After chunk `signal_after` the thread arrives on lo_free (-1: never).
+// Drain `nchunks` 64-column chunks of the accumulator at TMEM column 0 into the A ring.  This warp owns
+// kColsPerWarp columns of each chunk, moved as 16-column TMEM loads: while one piece goes through Mish the
+// next load is in flight (two 16-register buffers).  After chunk `signal_after` the thread arrives on
+// lo_free (-1: never).
 template <bool F16>
 __device__ __forceinline__ void drain_acc(EpiCtx& e, int nchunks, const float* bias, int signal_after) {
-    const uint32_t tbase = e.tmem_base + ((uint32_t)(e.q * 32) << 16) + e.ch * 32;
+    const uint32_t tbase = e.tmem_base + ((uint32_t)(e.q * 32) << 16) + e.ch * kColsPerWarp;
     uint32_t va[16], vb[16];
     tmem_ld16(tbase, va);
     for (int c = 0; c < nchunks; ++c) {
-        const float* bb = bias + c * 64 + e.ch * 32;
-        tmem_ld_wait();
-        tmem_ld16(tbase + c * 64 + 16, vb);
-        mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
-        uint8_t* slot = e.smem + e.L.aring + e.as.idx * kChunkBytes;
-        emit_half<F16>(e, slot, va, bb, e.ch * 32);
-        tmem_ld_wait();
-        if (c + 1 < nchunks) tmem_ld16(tbase + (c + 1) * 64, va);
-        emit_half<F16>(e, slot, vb, bb + 16, e.ch * 32 + 16);
+        const float* bb = bias + c * 64 + e.ch * kColsPerWarp;
+        if (kColsPerWarp == 32) {
+            tmem_ld_wait();
+            tmem_ld16(tbase + c * 64 + 16, vb);
+            mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
+            uint8_t* slot = e.smem + e.L.aring + e.as.idx * kChunkBytes;
+            emit_half<F16>(e, slot, va, bb, e.ch * 32);
+            tmem_ld_wait();
+            if (c + 1 < nchunks) tmem_ld16(tbase + (c + 1) * 64, va);
+            emit_half<F16>(e, slot, vb, bb + 16, e.ch * 32 + 16);
+        } else {
+            // 16 columns per warp: alternate the two buffers chunk by chunk
+            tmem_ld_wait();
+            mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
+            uint8_t* slot = e.smem + e.L.aring + e.as.idx * kChunkBytes;
+            if ((c & 1) == 0) {
+                if (c + 1 < nchunks) tmem_ld16(tbase + (c + 1) * 64, vb);
+                emit_half<F16>(e, slot, va, bb, e.ch * 16);
+            } else {
+                if (c + 1 < nchunks) tmem_ld16(tbase + (c + 1) * 64, va);
+                emit_half<F16>(e, slot, vb, bb, e.ch * 16);
+            }
+        }
+        // every lane publishes its own writes to the async proxy, then one lane arrives for the warp
+        // (32 lanes arriving on one mbarrier word serialise in the shared-memory pipe)
         fence_proxy_async();
         tc_fence_before();
-        mbar_arrive(bar_a_full(e.bars, e.as.idx));
+        __syncwarp();
+        if (e.lane == 0) {
+            mbar_arrive(bar_a_full(e.bars, e.as.idx));
+            if (c == signal_after) mbar_arrive(bar_lo_free(e.bars));
+        }
         e.as.advance(kASlots);
-        if (c == signal_after) mbar_arrive(bar_lo_free(e.bars));
     }
 }
 
@@ -164,47 +189,47 @@ __device__ __forceinline__ void drain_acc(EpiCtx& e, int nchunks, const float* b
 template <bool F16>
 __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
     const int t = a.T - 1 - j;
-    const uint16_t* in0 = reinterpret_cast<const uint16_t*>(e.smem + e.L.in0);
-    // A fragments of layer 0 for this warp's 32 rows (2 m16 tiles x 3 k16 steps)
-    uint32_t af[2][3][4];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int ks = 0; ks < 3; ++ks) {
-            const uint16_t* p0 = in0 + (e.q * 32 + mt * 16 + e.g) * kIn0Stride + ks * 16 + 2 * e.t4;
-            af[mt][ks][0] = *reinterpret_cast<const uint32_t*>(p0);
-            af[mt][ks][1] = *reinterpret_cast<const uint32_t*>(p0 + 8 * kIn0Stride);
-            af[mt][ks][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
-            af[mt][ks][3] = *reinterpret_cast<const uint32_t*>(p0 + 8 * kIn0Stride + 8);
-        }
+    // layer-0 A fragments are re-read from the input tile with ldmatrix for every chunk (6 per chunk) instead
+    // of living in 24 registers for the whole step
+    const uint32_t in0_lane = smem_u32(e.smem + e.L.in0) +
+        (uint32_t)(((e.q * 32 + (e.lane & 7) + ((e.lane >> 3) & 1) * 8) * kIn0Stride + (e.lane >> 4) * 8) * 2);
+
     // ---- layer 0: one 64-feature chunk at a time, straight into the A ring
     const float* tb = a.tb0 + (size_t)t * a.h1;
     const uint2* wf = F16 ? a.w0frag_h : a.w0frag;
-    uint2 bfr[4][3];
-    float2 bias[4];
-    auto load_frags = [&](int c, uint2 (&f)[4][3], float2 (&b)[4]) {
-        const uint2* bf = wf + ((size_t)(c * 2 + e.ch) * 12) * 32 + e.lane;
+    uint2 bfr[kNT][3];
+    float2 bias[kNT];
+    // packed fragment order: [chunk][32-feature half][n8 tile 0..3][k16 step][lane]; this warp's first
+    // feature inside the chunk is ch * kColsPerWarp
+    auto load_frags = [&](int c, uint2 (&f)[kNT][3], float2 (&b)[kNT]) {
+        const int n8 = e.ch * kNT;                              // first n8 tile (0..7) of this warp in the chunk
+        const uint2* bf = wf + ((size_t)(c * 8 + n8) * 3) * 32 + e.lane;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < kNT; ++nt)
 #pragma unroll
             for (int ks = 0; ks < 3; ++ks) f[nt][ks] = __ldg(bf + (nt * 3 + ks) * 32);
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-            b[nt] = __ldg(reinterpret_cast<const float2*>(tb + c * 64 + e.ch * 32 + nt * 8 + 2 * e.t4));
+        for (int nt = 0; nt < kNT; ++nt)
+            b[nt] = __ldg(reinterpret_cast<const float2*>(tb + c * 64 + e.ch * kColsPerWarp + nt * 8 + 2 * e.t4));
     };
     load_frags(0, bfr, bias);
     for (int c = 0; c < e.NC1; ++c) {
-        float acc[2][4][4];
+        float acc[2][kNT][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
+            for (int nt = 0; nt < kNT; ++nt) {
                 acc[mt][nt][0] = bias[nt].x; acc[mt][nt][1] = bias[nt].y;
                 acc[mt][nt][2] = bias[nt].x; acc[mt][nt][3] = bias[nt].y;
-#pragma unroll
-                for (int ks = 0; ks < 3; ++ks)
-                    mma_m16n8k16<F16>(acc[mt][nt], af[mt][ks], bfr[nt][ks].x, bfr[nt][ks].y);
             }
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) {
+                uint32_t af[4];
+                ldmatrix_x4(af, in0_lane + (uint32_t)((mt * 16 * kIn0Stride + ks * 16) * 2));
+#pragma unroll
+                for (int nt = 0; nt < kNT; ++nt) mma_m16n8k16<F16>(acc[mt][nt], af, bfr[nt][ks].x, bfr[nt][ks].y);
+            }
+        }
         // the fragment registers are dead after the HMMAs: refill them for the next chunk now, so the
         // loads are in flight during the Mish / store phase
         if (c + 1 < e.NC1) load_frags(c + 1, bfr, bias);
@@ -213,15 +238,16 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const int r0 = e.q * 32 + mt * 16 + e.g, col = e.ch * 32 + nt * 8 + 2 * e.t4;
+            for (int nt = 0; nt < kNT; ++nt) {
+                const int r0 = e.q * 32 + mt * 16 + e.g, col = e.ch * kColsPerWarp + nt * 8 + 2 * e.t4;
                 *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0, col)) =
                     pack2<F16>(mish_fast(acc[mt][nt][0]), mish_fast(acc[mt][nt][1]));
                 *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0 + 8, col)) =
                     pack2<F16>(mish_fast(acc[mt][nt][2]), mish_fast(acc[mt][nt][3]));
             }
         fence_proxy_async();
-        mbar_arrive(bar_a_full(e.bars, e.as.idx));
+        __syncwarp();
+        if (e.lane == 0) mbar_arrive(bar_a_full(e.bars, e.as.idx));
         e.as.advance(kASlots);
     }
 
@@ -292,9 +318,9 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
     // ------------------------------------------------------------------ one-time setup
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(bar_w_full(bars, i), 1); mbar_init(bar_w_empty(bars, i), 1); }
-        for (int i = 0; i < kASlots; ++i) { mbar_init(bar_a_full(bars, i), kEpiThreads); mbar_init(bar_a_empty(bars, i), 1); }
+        for (int i = 0; i < kASlots; ++i) { mbar_init(bar_a_full(bars, i), kEpiWarps); mbar_init(bar_a_empty(bars, i), 1); }
         mbar_init(bar_acc_full(bars), 1);
-        mbar_init(bar_lo_free(bars), kEpiThreads);
+        mbar_init(bar_lo_free(bars), kEpiWarps);
         fence_barrier_init();
     }
     if (warp == kEpiWarps + 1) tmem_alloc(base + L.tmem_ptr, kTmemCols);

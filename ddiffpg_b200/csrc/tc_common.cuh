@@ -159,6 +159,13 @@ template <bool F16> __device__ __forceinline__ uint16_t cvt16(float v) {
     return *reinterpret_cast<uint16_t*>(&b);
 }
 
+// one m16k16 A fragment (four 8x8 b16 matrices) from shared memory; lane l supplies the address of row
+// (l & 7) + 8 * ((l >> 3) & 1), k offset 8 * (l >> 4)
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t smem_addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr));
+}
+
 // legacy warp-level tensor-core MMA for the K=48 first layer (register accumulators, no TMEM needed)
 __device__ __forceinline__ void mma_m16n8k16_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
