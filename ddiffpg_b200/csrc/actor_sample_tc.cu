@@ -57,28 +57,23 @@ struct TcArgs {
     int S, A, T, h1, h2, h3;
     int nparts1, part1;        // layer-1 output split into nparts1 parts of part1 (<= 256) columns
     int num_tiles;
+    long long* dbg;            // optional per-phase cycle counters of CTA 0 (development aid), else NULL
 };
 
-struct SmemLayout {
-    uint32_t wring, aring, w3, in0, b1, b2, bars, tmem_ptr, total;
+// Shared-memory map (bytes from the 1024-aligned base); sized for the largest supported shape
+// (h2 <= 512, h3 <= 256) so that every offset is a compile-time constant.
+struct SM {
+    static constexpr uint32_t wring = 0;                                   // kStages x 32 KB weight stages
+    static constexpr uint32_t aring = wring + kStages * kStageBytes;       // kASlots x 16 KB A chunks
+    static constexpr uint32_t w3 = aring + kASlots * kChunkBytes;          // W3 tiles: bf16 image, fp16 image
+    static constexpr uint32_t w3_f16 = w3 + 4 * 2048;
+    static constexpr uint32_t in0 = w3 + 2 * 4 * 2048;                     // layer-0 input tile [128][56] 16-bit
+    static constexpr uint32_t b1 = in0 + kRows * kIn0Stride * 2;           // fp32 biases
+    static constexpr uint32_t b2 = b1 + 512 * 4;
+    static constexpr uint32_t bars = b2 + 256 * 4;
+    static constexpr uint32_t tmem_ptr = bars + 8 * (2 * kStages + 2 * kASlots + 2);
+    static constexpr uint32_t total = tmem_ptr + 8;
 };
-
-__host__ __device__ inline SmemLayout make_smem_layout(int h2, int h3) {
-    SmemLayout s;
-    uint32_t o = 0;
-    s.wring = o; o += kStages * kStageBytes;
-    s.aring = o; o += kASlots * kChunkBytes;
-    s.w3 = o; o += (uint32_t)(h3 / 64) * 2048 * 2;      // bf16 image then fp16 image
-    s.in0 = o; o += kRows * kIn0Stride * 2;
-    o = (o + 15) & ~15u;
-    s.b1 = o; o += (uint32_t)h2 * 4;
-    s.b2 = o; o += (uint32_t)h3 * 4;
-    o = (o + 7) & ~7u;
-    s.bars = o; o += 8 * (2 * kStages + 2 * kASlots + 2);
-    s.tmem_ptr = o; o += 8;
-    s.total = o;
-    return s;
-}
 
 // barrier indices inside the bars block
 __device__ __forceinline__ uint32_t bar_w_full(uint32_t base, int i) { return base + 8 * i; }
@@ -99,7 +94,6 @@ struct Ring {
 // Per-thread state of an epilogue / layer-0 warp.
 struct EpiCtx {
     uint8_t* smem;
-    SmemLayout L;
     uint32_t bars, tmem_base, acc_phase;
     int q, ch, g, t4, lane, my_row;     // TMEM lane quarter, column group of the chunk, mma.sync coords, owned row
     int NC1, NC2, NC3;
@@ -112,7 +106,7 @@ struct EpiCtx {
 // [x (8) | state (S) | 0 ...] of the owned row into the layer-0 input tile, in the operand format F16/bf16
 template <bool F16>
 __device__ __forceinline__ void write_in0_row(const TcArgs& a, const EpiCtx& e, bool with_state) {
-    uint16_t* rp = reinterpret_cast<uint16_t*>(e.smem + e.L.in0) + e.my_row * kIn0Stride;
+    uint16_t* rp = reinterpret_cast<uint16_t*>(e.smem + SM::in0) + e.my_row * kIn0Stride;
     uint4 xv;
     xv.x = pack2<F16>(e.xr[0], e.xr[1]); xv.y = pack2<F16>(e.xr[2], e.xr[3]);
     xv.z = pack2<F16>(e.xr[4], e.xr[5]); xv.w = pack2<F16>(e.xr[6], e.xr[7]);
@@ -126,15 +120,24 @@ __device__ __forceinline__ void write_in0_row(const TcArgs& a, const EpiCtx& e, 
 // 16-byte pieces of the A chunk slot (columns col0 .. col0+15 of the 64-column chunk)
 template <bool F16>
 __device__ __forceinline__ void emit_half(const EpiCtx& e, uint8_t* slot, const uint32_t (&v)[16], const float* bb, int col0) {
+    float x[16];
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {
+        const float4 b = *reinterpret_cast<const float4*>(bb + i4 * 4);
+        x[i4 * 4 + 0] = __uint_as_float(v[i4 * 4 + 0]) + b.x; x[i4 * 4 + 1] = __uint_as_float(v[i4 * 4 + 1]) + b.y;
+        x[i4 * 4 + 2] = __uint_as_float(v[i4 * 4 + 2]) + b.z; x[i4 * 4 + 3] = __uint_as_float(v[i4 * 4 + 3]) + b.w;
+    }
+#if DDP_TC_EPI_WARPS >= 16
+    mish_fast_n<8>(reinterpret_cast<float(&)[8]>(x[0]));
+    mish_fast_n<8>(reinterpret_cast<float(&)[8]>(x[8]));
+#else
+    mish_fast_n<16>(x);
+#endif
 #pragma unroll
     for (int i8 = 0; i8 < 2; ++i8) {
-        const float4 b0 = *reinterpret_cast<const float4*>(bb + i8 * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(bb + i8 * 8 + 4);
         uint4 w;
-        w.x = pack2<F16>(mish_fast(__uint_as_float(v[i8 * 8 + 0]) + b0.x), mish_fast(__uint_as_float(v[i8 * 8 + 1]) + b0.y));
-        w.y = pack2<F16>(mish_fast(__uint_as_float(v[i8 * 8 + 2]) + b0.z), mish_fast(__uint_as_float(v[i8 * 8 + 3]) + b0.w));
-        w.z = pack2<F16>(mish_fast(__uint_as_float(v[i8 * 8 + 4]) + b1.x), mish_fast(__uint_as_float(v[i8 * 8 + 5]) + b1.y));
-        w.w = pack2<F16>(mish_fast(__uint_as_float(v[i8 * 8 + 6]) + b1.z), mish_fast(__uint_as_float(v[i8 * 8 + 7]) + b1.w));
+        w.x = pack2<F16>(x[i8 * 8 + 0], x[i8 * 8 + 1]); w.y = pack2<F16>(x[i8 * 8 + 2], x[i8 * 8 + 3]);
+        w.z = pack2<F16>(x[i8 * 8 + 4], x[i8 * 8 + 5]); w.w = pack2<F16>(x[i8 * 8 + 6], x[i8 * 8 + 7]);
         *reinterpret_cast<uint4*>(slot + sw128_offset(e.my_row, col0 + i8 * 8)) = w;
     }
 }
@@ -154,7 +157,7 @@ __device__ __forceinline__ void drain_acc(EpiCtx& e, int nchunks, const float* b
             tmem_ld_wait();
             tmem_ld16(tbase + c * 64 + 16, vb);
             mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
-            uint8_t* slot = e.smem + e.L.aring + e.as.idx * kChunkBytes;
+            uint8_t* slot = e.smem + SM::aring + e.as.idx * kChunkBytes;
             emit_half<F16>(e, slot, va, bb, e.ch * 32);
             tmem_ld_wait();
             if (c + 1 < nchunks) tmem_ld16(tbase + (c + 1) * 64, va);
@@ -163,7 +166,7 @@ __device__ __forceinline__ void drain_acc(EpiCtx& e, int nchunks, const float* b
             // 16 columns per warp: alternate the two buffers chunk by chunk
             tmem_ld_wait();
             mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
-            uint8_t* slot = e.smem + e.L.aring + e.as.idx * kChunkBytes;
+            uint8_t* slot = e.smem + SM::aring + e.as.idx * kChunkBytes;
             if ((c & 1) == 0) {
                 if (c + 1 < nchunks) tmem_ld16(tbase + (c + 1) * 64, vb);
                 emit_half<F16>(e, slot, va, bb, e.ch * 16);
@@ -189,9 +192,12 @@ __device__ __forceinline__ void drain_acc(EpiCtx& e, int nchunks, const float* b
 template <bool F16>
 __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
     const int t = a.T - 1 - j;
+    const bool prof = a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long tk0 = prof ? clock64() : 0, tk1;
+#define DDP_TICK(slot) do { if (prof) { tk1 = clock64(); a.dbg[slot] += tk1 - tk0; tk0 = tk1; } } while (0)
     // layer-0 A fragments are re-read from the input tile with ldmatrix for every chunk (6 per chunk) instead
     // of living in 24 registers for the whole step
-    const uint32_t in0_lane = smem_u32(e.smem + e.L.in0) +
+    const uint32_t in0_lane = smem_u32(e.smem + SM::in0) +
         (uint32_t)(((e.q * 32 + (e.lane & 7) + ((e.lane >> 3) & 1) * 8) * kIn0Stride + (e.lane >> 4) * 8) * 2);
 
     // ---- layer 0: one 64-feature chunk at a time, straight into the A ring
@@ -227,52 +233,65 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
                 uint32_t af[4];
                 ldmatrix_x4(af, in0_lane + (uint32_t)((mt * 16 * kIn0Stride + ks * 16) * 2));
 #pragma unroll
+#ifndef DDP_EXP_NO_HMMA
                 for (int nt = 0; nt < kNT; ++nt) mma_m16n8k16<F16>(acc[mt][nt], af, bfr[nt][ks].x, bfr[nt][ks].y);
+#else
+                for (int nt = 0; nt < kNT; ++nt) { acc[mt][nt][0] += __uint_as_float(af[0] ^ bfr[nt][ks].x) * 1e-30f; acc[mt][nt][3] += __uint_as_float(af[3] ^ bfr[nt][ks].y) * 1e-30f; }
+#endif
             }
         }
         // the fragment registers are dead after the HMMAs: refill them for the next chunk now, so the
         // loads are in flight during the Mish / store phase
         if (c + 1 < e.NC1) load_frags(c + 1, bfr, bias);
         mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
-        uint8_t* slot = e.smem + e.L.aring + e.as.idx * kChunkBytes;
+        uint8_t* slot = e.smem + SM::aring + e.as.idx * kChunkBytes;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt) {
+#ifndef DDP_EXP_NO_L0_MISH
+            mish_fast_n<kNT * 4>(reinterpret_cast<float(&)[kNT * 4]>(acc[mt]));
+#endif
 #pragma unroll
             for (int nt = 0; nt < kNT; ++nt) {
                 const int r0 = e.q * 32 + mt * 16 + e.g, col = e.ch * kColsPerWarp + nt * 8 + 2 * e.t4;
-                *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0, col)) =
-                    pack2<F16>(mish_fast(acc[mt][nt][0]), mish_fast(acc[mt][nt][1]));
-                *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0 + 8, col)) =
-                    pack2<F16>(mish_fast(acc[mt][nt][2]), mish_fast(acc[mt][nt][3]));
+                *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0, col)) = pack2<F16>(acc[mt][nt][0], acc[mt][nt][1]);
+                *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0 + 8, col)) = pack2<F16>(acc[mt][nt][2], acc[mt][nt][3]);
             }
+        }
         fence_proxy_async();
         __syncwarp();
         if (e.lane == 0) mbar_arrive(bar_a_full(e.bars, e.as.idx));
         e.as.advance(kASlots);
     }
 
+    DDP_TICK(0);       // layer 0 + Mish, 16 chunks
     // ---- layer-1 epilogue: acc1 (TMEM cols [0,h2)) -> +b1, Mish -> A chunks of layer 2
-    const float* sb1 = reinterpret_cast<const float*>(e.smem + e.L.b1);
-    const float* sb2 = reinterpret_cast<const float*>(e.smem + e.L.b2);
+    const float* sb1 = reinterpret_cast<const float*>(e.smem + SM::b1);
+    const float* sb2 = reinterpret_cast<const float*>(e.smem + SM::b2);
     mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
     tc_fence_after();
+    DDP_TICK(1);       // wait for the last layer-1 MMA
     drain_acc<F16>(e, e.NC2, sb1, e.NC3 - 1);          // lo_free: TMEM cols [0, h3) are drained
-    // step noise and head bias for the row this thread owns: issued here, consumed in the final epilogue
-    float zr[8], b3r[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        zr[i] = (e.ch == 0 && e.valid && t > 0 && i < a.A) ? __ldg(a.noise + ((size_t)(j + 1) * a.B + e.row) * a.A + i) : 0.f;
-        b3r[i] = i < a.A ? __ldg(a.b3 + i) : 0.f;
-    }
+    DDP_TICK(2);       // drain acc1
     // ---- layer-2 epilogue: acc2 (TMEM cols [0,h3)) -> +b2, Mish -> A chunks of layer 3
     mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
     tc_fence_after();
+    DDP_TICK(3);       // wait for the last layer-2 MMA
     drain_acc<F16>(e, e.NC3, sb2, -1);
+    DDP_TICK(4);       // drain acc2
 
     // ---- head + scheduler step: eps_hat from acc3, x_t in registers (fp32)
     mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
     tc_fence_after();
+    DDP_TICK(5);       // wait for layer 3
     if (e.ch == 0) {
+        // step noise and head bias of the owned row (loaded here: keeping them live across the drains costs
+        // 16 registers for ~500 cycles of exposed latency per step)
+        float zr[8], b3r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            zr[i] = (e.valid && t > 0 && i < a.A) ? __ldg(a.noise + ((size_t)(j + 1) * a.B + e.row) * a.A + i) : 0.f;
+            b3r[i] = i < a.A ? __ldg(a.b3 + i) : 0.f;
+        }
         uint32_t ev[8];
         tmem_ld8(e.tmem_base + ((uint32_t)(e.q * 32) << 16) + a.h3, ev);
         tmem_ld_wait();
@@ -299,6 +318,8 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
     }
     tc_fence_before();
     epi_bar_sync();         // new x visible to all layer-0 warps; acc3 reads are complete
+    DDP_TICK(6);       // head + scheduler step + barrier
+#undef DDP_TICK
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -310,8 +331,7 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw);
-    const SmemLayout L = make_smem_layout(a.h2, a.h3);
-    const uint32_t bars = base + L.bars;
+    const uint32_t bars = base + SM::bars;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NC1 = a.h1 >> 6, NC2 = a.h2 >> 6, NC3 = a.h3 >> 6;
 
@@ -323,14 +343,14 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
         mbar_init(bar_lo_free(bars), kEpiWarps);
         fence_barrier_init();
     }
-    if (warp == kEpiWarps + 1) tmem_alloc(base + L.tmem_ptr, kTmemCols);
+    if (warp == kEpiWarps + 1) tmem_alloc(base + SM::tmem_ptr, kTmemCols);
     // resident operands: W3 tiles (pre-swizzled image), biases
     {
         const int n16 = NC3 * 2048 / 16;
-        uint4* dst = reinterpret_cast<uint4*>(smem + L.w3);
-        for (int i = threadIdx.x; i < n16; i += kThreads) { dst[i] = a.w3img[i]; dst[n16 + i] = a.w3img_h[i]; }
-        float* sb1 = reinterpret_cast<float*>(smem + L.b1);
-        float* sb2 = reinterpret_cast<float*>(smem + L.b2);
+        uint4* dst = reinterpret_cast<uint4*>(smem + SM::w3);
+        for (int i = threadIdx.x; i < n16; i += kThreads) { dst[i] = a.w3img[i]; dst[(SM::w3_f16 - SM::w3) / 16 + i] = a.w3img_h[i]; }
+        float* sb1 = reinterpret_cast<float*>(smem + SM::b1);
+        float* sb2 = reinterpret_cast<float*>(smem + SM::b2);
         for (int i = threadIdx.x; i < a.h2; i += kThreads) sb1[i] = a.b1[i];
         for (int i = threadIdx.x; i < a.h3; i += kThreads) sb2[i] = a.b2[i];
         fence_proxy_async();
@@ -338,7 +358,7 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L.tmem_ptr);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + SM::tmem_ptr);
 
     if (warp == kEpiWarps) {
         // ============================================================== TMA producer (one lane)
@@ -357,14 +377,14 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
                         for (int p = 0; p < a.nparts1; ++p) {
                             mbar_wait(bar_w_empty(bars, ws.idx), ws.phase ^ 1);
                             mbar_expect_tx(bar_w_full(bars, ws.idx), (uint32_t)a.part1 * 128u);
-                            tma_load_2d(base + L.wring + ws.idx * kStageBytes, m1, bar_w_full(bars, ws.idx),
+                            tma_load_2d(base + SM::wring + ws.idx * kStageBytes, m1, bar_w_full(bars, ws.idx),
                                         c * 64, p * a.part1);
                             ws.advance(kStages);
                         }
                     for (int c = 0; c < NC2; ++c) {
                         mbar_wait(bar_w_empty(bars, ws.idx), ws.phase ^ 1);
                         mbar_expect_tx(bar_w_full(bars, ws.idx), (uint32_t)a.h3 * 128u);
-                        tma_load_2d(base + L.wring + ws.idx * kStageBytes, m2, bar_w_full(bars, ws.idx), c * 64, 0);
+                        tma_load_2d(base + SM::wring + ws.idx * kStageBytes, m2, bar_w_full(bars, ws.idx), c * 64, 0);
                         ws.advance(kStages);
                     }
                 }
@@ -381,16 +401,16 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
                     const uint32_t idesc1 = make_idesc_16(kRows, a.part1, f16);
                     const uint32_t idesc2 = make_idesc_16(kRows, a.h3, f16);
                     const uint32_t idesc3 = make_idesc_16(kRows, 16, f16);
-                    const uint32_t w3base = base + L.w3 + (f16 ? NC3 * 2048 : 0);
+                    const uint32_t w3base = base + (f16 ? SM::w3_f16 : SM::w3);
                     // ---- layer 1: acc1[128 x h2] (TMEM cols [0, h2)) += h0 chunk . W1 chunk^T
                     for (int c = 0; c < NC1; ++c) {
                         mbar_wait(bar_a_full(bars, as.idx), as.phase);
                         tc_fence_after();
-                        const uint64_t adesc = make_smem_desc_sw128(base + L.aring + as.idx * kChunkBytes);
+                        const uint64_t adesc = make_smem_desc_sw128(base + SM::aring + as.idx * kChunkBytes);
                         for (int p = 0; p < a.nparts1; ++p) {
                             mbar_wait(bar_w_full(bars, ws.idx), ws.phase);
                             tc_fence_after();
-                            const uint64_t bdesc = make_smem_desc_sw128(base + L.wring + ws.idx * kStageBytes);
+                            const uint64_t bdesc = make_smem_desc_sw128(base + SM::wring + ws.idx * kStageBytes);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 umma_bf16(tmem_base + p * a.part1, adesc + 2 * k, bdesc + 2 * k, idesc1, (c | k) != 0);
@@ -409,8 +429,8 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
                         mbar_wait(bar_a_full(bars, as.idx), as.phase);
                         mbar_wait(bar_w_full(bars, ws.idx), ws.phase);
                         tc_fence_after();
-                        const uint64_t adesc = make_smem_desc_sw128(base + L.aring + as.idx * kChunkBytes);
-                        const uint64_t bdesc = make_smem_desc_sw128(base + L.wring + ws.idx * kStageBytes);
+                        const uint64_t adesc = make_smem_desc_sw128(base + SM::aring + as.idx * kChunkBytes);
+                        const uint64_t bdesc = make_smem_desc_sw128(base + SM::wring + ws.idx * kStageBytes);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc2, (c | k) != 0);
@@ -424,7 +444,7 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
                     for (int c = 0; c < NC3; ++c) {
                         mbar_wait(bar_a_full(bars, as.idx), as.phase);
                         tc_fence_after();
-                        const uint64_t adesc = make_smem_desc_sw128(base + L.aring + as.idx * kChunkBytes);
+                        const uint64_t adesc = make_smem_desc_sw128(base + SM::aring + as.idx * kChunkBytes);
                         const uint64_t bdesc = make_smem_desc_sw128(w3base + c * 2048);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
@@ -439,7 +459,7 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
     } else if (warp < kEpiWarps) {
         // ============================================================== epilogue / layer-0 warps
         EpiCtx e;
-        e.smem = smem; e.L = L; e.bars = bars; e.tmem_base = tmem_base;
+        e.smem = smem; e.bars = bars; e.tmem_base = tmem_base;
         e.q = warp & 3; e.ch = warp >> 2; e.g = lane >> 2; e.t4 = lane & 3; e.lane = lane;
         e.my_row = e.q * 32 + lane;
         e.NC1 = NC1; e.NC2 = NC2; e.NC3 = NC3;
@@ -517,6 +537,8 @@ struct TcPacked {      // byte offsets inside the packed buffer (see ActorLayout
 
 }  // namespace
 
+static long long* g_tc_dbg = nullptr;   // set by ddp_debug_tc_timing (development aid)
+
 static bool tc_shape_ok(const ActorLayout& L) {
     return L.A <= 8 && L.S + 8 <= kK0 && L.h1 % 64 == 0 && L.h2 % 64 == 0 && L.h3 % 64 == 0 && L.h2 <= 512 &&
            L.h3 <= 256 && L.h3 + 16 <= kTmemCols && L.h3 / 64 <= kASlots && L.h3 <= L.h2 &&
@@ -566,6 +588,7 @@ int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state
     a.nparts1 = L.h2 > 256 ? L.h2 / 256 : 1;
     a.part1 = L.h2 / a.nparts1;
     a.num_tiles = (int)((B + kRows - 1) / kRows);
+    a.dbg = g_tc_dbg;
     CUtensorMap m1, m2, m1h, m2h;
     if (make_tmap_bf16_sw128(&m1, base + L.tc_w1, L.h2, L.h1, a.part1) != 0 ||
         make_tmap_bf16_sw128(&m2, base + L.tc_w2, L.h3, L.h2, L.h3) != 0 ||
@@ -575,8 +598,7 @@ int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state
     int dev = 0, sms = 0;
     DDP_CUDA_CHECK(cudaGetDevice(&dev));
     DDP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const SmemLayout S = make_smem_layout(L.h2, L.h3);
-    const size_t smem = S.total + 1024;         // slack for the 1024-byte alignment of the base
+    const size_t smem = SM::total + 1024;         // slack for the 1024-byte alignment of the base
     DDP_CUDA_CHECK(cudaFuncSetAttribute(actor_sample_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
     actor_sample_tc_kernel<<<grid, kThreads, smem, st>>>(m1, m2, m1h, m2h, a);
@@ -656,3 +678,7 @@ extern "C" int ddp_debug_tc_gemm(const void* A, const void* Bm, float* C, int N,
     DDP_LAUNCH_CHECK("tc_gemm_selftest_kernel");
     return DDP_OK;
 }
+
+// Debug entry point (not part of the public header): device buffer of >= 8 int64 that CTA 0 of the next
+// sampler launches accumulates per-phase cycle counts into (NULL switches it off).
+extern "C" void ddp_debug_tc_timing(long long* dev_buf) { ddp::g_tc_dbg = dev_buf; }

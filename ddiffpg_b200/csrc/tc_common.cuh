@@ -197,6 +197,18 @@ __device__ __forceinline__ float mish_fast(float x) {
     const float r = rcp_approx(fmaf(s, s, 1.f));
     return fmaf(-2.f * x, r, x);
 }
+// N independent Mish evaluations in explicit stages (all ex2, then all rcp): with only two epilogue warps
+// per SM sub-partition the MUFU latency has to be covered by instruction-level parallelism inside the warp.
+template <int N>
+__device__ __forceinline__ void mish_fast_n(float (&x)[N]) {
+    float s[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) s[i] = ex2_approx(fminf(x[i] * 1.4426950408889634f, 28.853900817779268f));
+#pragma unroll
+    for (int i = 0; i < N; ++i) { const float u = s[i] + 1.f; s[i] = rcp_approx(fmaf(u, u, 1.f)); }
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = fmaf(-2.f * x[i], s[i], x[i]);
+}
 
 // ------------------------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
