@@ -12,6 +12,7 @@ import torch
 from torch.nn.utils import clip_grad_norm_
 
 from . import _lib
+from . import dist as ddist
 from ._lib import check, lib, ptr, stream_ptr
 from .models import _PackCache, pack_critics
 
@@ -161,10 +162,8 @@ class FusedActorTrainer:
             timesteps = torch.randint(0, actor.diffusion_iter, (B,), device=dev)
         loss, grads = actor._loss_and_grads(state, action, noise, timesteps,
                                             inv_count=1.0 / (global_batch * actor.action_dim))
-        if world > 1:
-            # the one exchange step of the path: sum the flat gradient (and the loss) over NVLink
-            torch.distributed.all_reduce(grads, group=self.group)
-            torch.distributed.all_reduce(loss, group=self.group)
+        # the one exchange step of the path: sum the flat gradient (and the loss) over NVLink
+        ddist.allreduce_sum_(grads, loss, group=self.group)
         self.step_count += 1
         with torch.cuda.device(dev):
             check(lib().ddp_clip_adamw_step(ptr(self.flat), ptr(grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),

@@ -30,6 +30,9 @@ constexpr int kChunkBytes = kRows * 128;    // one A chunk: 128 rows x 64 bf16
 constexpr int kStageBytes = 256 * 128;      // one weight stage: up to 256 rows x 64 bf16
 constexpr int kStages = 4;
 constexpr int kASlots = 4;
+#ifndef DDP_TC_HALF_EX2
+#define DDP_TC_HALF_EX2 0   // 1: packed-fp16 ex2 in the bf16 steps (one MUFU op per two elements)
+#endif
 #ifndef DDP_TC_EPI_WARPS
 #define DDP_TC_EPI_WARPS 8
 #endif
@@ -131,7 +134,7 @@ __device__ __forceinline__ void emit_half(const EpiCtx& e, uint8_t* slot, const 
     mish_fast_n<8>(reinterpret_cast<float(&)[8]>(x[0]));
     mish_fast_n<8>(reinterpret_cast<float(&)[8]>(x[8]));
 #else
-    mish_fast_n<16>(x);
+    mish_fast_n<16, !F16 && DDP_TC_HALF_EX2>(x);
 #endif
 #pragma unroll
     for (int i8 = 0; i8 < 2; ++i8) {
@@ -248,7 +251,7 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
 #ifndef DDP_EXP_NO_L0_MISH
-            mish_fast_n<kNT * 4>(reinterpret_cast<float(&)[kNT * 4]>(acc[mt]));
+            mish_fast_n<kNT * 4, !F16 && DDP_TC_HALF_EX2>(reinterpret_cast<float(&)[kNT * 4]>(acc[mt]));
 #endif
 #pragma unroll
             for (int nt = 0; nt < kNT; ++nt) {

@@ -199,11 +199,28 @@ __device__ __forceinline__ float mish_fast(float x) {
 }
 // N independent Mish evaluations in explicit stages (all ex2, then all rcp): with only two epilogue warps
 // per SM sub-partition the MUFU latency has to be covered by instruction-level parallelism inside the warp.
-template <int N>
+// ex2 of two values with ONE MUFU op (packed fp16 in, packed fp16 out; ~2^-11 relative).  The MUFU pipe
+// (16 lanes/SM) is the tightest resource of the Mish epilogues; this halves the exp half of its load.
+// Arguments must be <= 15.9 so that 2^t stays finite in fp16.
+__device__ __forceinline__ void ex2_pair_f16(float t0, float t1, float& e0, float& e1) {
+    __half2 h = __floats2half2_rn(t0, t1);
+    uint32_t u = *reinterpret_cast<uint32_t*>(&h), v;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(v) : "r"(u));
+    const float2 f = __half22float2(*reinterpret_cast<__half2*>(&v));
+    e0 = f.x; e1 = f.y;
+}
+template <int N, bool HALF_EX2 = false>
 __device__ __forceinline__ void mish_fast_n(float (&x)[N]) {
     float s[N];
+    if (HALF_EX2) {
+        // cap at x = 11: mish(x) == x to 1e-9 there, and exp(x) still fits fp16
 #pragma unroll
-    for (int i = 0; i < N; ++i) s[i] = ex2_approx(fminf(x[i] * 1.4426950408889634f, 28.853900817779268f));
+        for (int i = 0; i < N; i += 2)
+            ex2_pair_f16(fminf(x[i] * 1.4426950408889634f, 15.87f), fminf(x[i + 1] * 1.4426950408889634f, 15.87f), s[i], s[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) s[i] = ex2_approx(fminf(x[i] * 1.4426950408889634f, 28.853900817779268f));
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) { const float u = s[i] + 1.f; s[i] = rcp_approx(fmaf(u, u, 1.f)); }
 #pragma unroll

@@ -1,0 +1,64 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: row sharding, mode-segment sharding and the
+H3 exchange step (sum all-reduce of gradients computed with the GLOBAL 1/(B*A) equals the full-batch gradient).
+The per-shard gradients come from the oracle port, standing in for the CUDA kernel (same contract:
+loss partial sums and gradients scaled by inv_count)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ddiffpg_b200 import dist as ddist
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 256, 65536, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [ddist.shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_segments():
+    seg = [0, 37, 37, 42, 172]
+    got = [ddist.shard_segments(seg, 2, r) for r in range(2)]
+    for m in range(4):
+        (lo0, hi0), (lo1, hi1) = got[0][0][m], got[1][0][m]
+        assert lo0 == seg[m] and hi0 == lo1 and hi1 == seg[m + 1]
+    assert got[0][2] == [37, 0, 5, 130] and got[0][1][-1] + got[1][1][-1] == 172
+
+
+def _worker(rank, world, port_no, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import port
+    torch.set_num_threads(2)
+    T, B, h = 5, 50, 256
+    gen = torch.Generator().manual_seed(5)
+    p = port.init_actor_params(3, h=h)
+    state, action = torch.randn(B, 34, generator=gen), torch.rand(B, 8, generator=gen) * 2 - 1
+    noise, ts = torch.randn(B, 8, generator=gen), torch.randint(0, T, (B,), generator=gen)
+    lo, hi = ddist.shard_bounds(B, world, rank)
+    inv = ddist.global_inv_count(hi - lo, 8)
+    assert abs(inv - 1.0 / (B * 8)) < 1e-15
+    # per-shard loss/grads with the global normaliser == (local mean) * local_rows / B
+    l_loc, g_loc = port.actor_loss_and_grads(p, state[lo:hi], action[lo:hi], noise[lo:hi], ts[lo:hi], T)
+    scale = (hi - lo) / B
+    flat = torch.cat([g_loc[k].reshape(-1) for k in port.ACTOR_KEYS]) * scale
+    loss = (l_loc * scale).reshape(1).clone()
+    ddist.allreduce_sum_(flat, loss)
+    l_ref, g_ref = port.actor_loss_and_grads(p, state, action, noise, ts, T)
+    ref = torch.cat([g_ref[k].reshape(-1) for k in port.ACTOR_KEYS])
+    ok = bool(torch.allclose(flat, ref, rtol=1e-4, atol=1e-7) and abs(loss.item() - l_ref.item()) < 1e-6)
+    open(os.path.join(tmp, f"ok{rank}"), "w").write(str(ok))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_equals_full_batch_gloo(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, 29641, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"ok{r}").read() == "True"
