@@ -1,0 +1,451 @@
+// tcgen05 GEMM kernels for the tensor-core paths of H2 (Q-ascent) and H3 (denoiser training step).
+//
+//  row GEMM   C[M x N] = epi(A[M x K] . W[N x K]^T)     one nn.Linear (forward) or dX = dY . W (backward) over
+//             a 128-row tile, with the activation / derivative / masking fused into the TMEM epilogue
+//             (reference layers: ddiffpg/models/diffusion_mlp.py:50-58, ddiffpg/models/mlp.py:13-35)
+//  dW GEMM    dW[n][k] += sum_r dZ[r][n] * X[r][k]      the weight gradient autograd produces for
+//             objective.backward() (ddiffpg/algo/ac_base.py:85); both operands are read MN-major straight from
+//             the row-major activations, rows split over CTAs, fp32 atomics into the flat gradient
+#include "tc_gemm.cuh"
+#include "tc_common.cuh"
+
+namespace ddp {
+namespace tcg {
+using namespace tc;
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kStageA = 128 * 128;          // 128 rows x 64 bf16
+constexpr int kStageW = 256 * 128;          // up to 256 rows x 64 bf16
+constexpr int kStageBytes = kStageA + kStageW;
+constexpr int kThreads = 192;               // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr uint32_t kOffBars = kStages * kStageBytes;
+constexpr uint32_t kSmemBytes = kOffBars + 8 * (2 * kStages + 4) + 16 + 1024;
+
+struct WMaps { CUtensorMap m[kMaxGroups]; };
+
+struct RowKernelArgs {
+    RowGemm g;
+    long tile0[kMaxGroups + 1];    // first m-tile of each group
+    int n_tiles_n, BN;
+    long total_tiles;
+};
+
+// 16-bit (bf16) row-major matrix [rows][cols valid] with leading dimension ld; box = [box_rows][64 columns],
+// 128-byte swizzle, out-of-bounds elements read as zero
+int make_tmap(CUtensorMap* map, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return -1;
+        fn = (PFN_encodeTiled)p;
+    }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+__device__ __forceinline__ void store_bf16x16(__nv_bfloat16* p, const float (&v)[16]) {
+    uint4 a, b;
+    a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]); a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
+    b.x = pack_bf16x2(v[8], v[9]); b.y = pack_bf16x2(v[10], v[11]); b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
+    reinterpret_cast<uint4*>(p)[0] = a;
+    reinterpret_cast<uint4*>(p)[1] = b;
+}
+__device__ __forceinline__ void load_bf16x16(const __nv_bfloat16* p, float (&v)[16]) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ row GEMM
+__global__ void __launch_bounds__(kThreads, 1)
+row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ WMaps maps_w, const RowKernelArgs k) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const uint32_t bars = base + kOffBars;
+    auto bar_full = [&](int i) { return bars + 8 * i; };
+    auto bar_empty = [&](int i) { return bars + 8 * (kStages + i); };
+    auto bar_acc_full = [&](int i) { return bars + 8 * (2 * kStages + i); };
+    auto bar_acc_empty = [&](int i) { return bars + 8 * (2 * kStages + 2 + i); };
+    const uint32_t tmem_slot = bars + 8 * (2 * kStages + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const RowGemm& g = k.g;
+    const int kchunks = (g.K + 63) >> 6;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full(i), 1); mbar_init(bar_acc_empty(i), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
+
+    // tile -> (group, first row, row limit, first column)
+    auto decode = [&](long tile, int& grp, long& row0, long& row_end, int& n0) {
+        const long mt = tile / k.n_tiles_n;
+        n0 = (int)(tile % k.n_tiles_n) * k.BN;
+        grp = 0;
+        while (grp + 1 < g.groups.n_groups && mt >= k.tile0[grp + 1]) ++grp;
+        row0 = g.groups.off[grp] + (mt - k.tile0[grp]) * 128;
+        row_end = g.groups.off[grp + 1];
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&map_a);
+            int st = 0; uint32_t ph = 0;
+            for (long tile = blockIdx.x; tile < k.total_tiles; tile += gridDim.x) {
+                int grp, n0; long row0, row_end;
+                decode(tile, grp, row0, row_end, n0);
+                for (int c = 0; c < kchunks; ++c) {
+                    mbar_wait(bar_empty(st), ph ^ 1);
+                    mbar_expect_tx(bar_full(st), (uint32_t)(kStageA + k.BN * 128));
+                    tma_load_2d(base + st * kStageBytes, &map_a, bar_full(st), c * 64, (int)row0);
+                    tma_load_2d(base + st * kStageBytes + kStageA, &maps_w.m[grp], bar_full(st), c * 64, n0);
+                    if (++st == kStages) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_16(128, k.BN, false);
+            int st = 0; uint32_t ph = 0, it = 0;
+            for (long tile = blockIdx.x; tile < k.total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(bar_acc_empty(buf), ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int c = 0; c < kchunks; ++c) {
+                    mbar_wait(bar_full(st), ph);
+                    tc_fence_after();
+                    const uint64_t ad = make_smem_desc_sw128(base + st * kStageBytes);
+                    const uint64_t bd = make_smem_desc_sw128(base + st * kStageBytes + kStageA);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) umma_bf16(tmem_base + buf * 256, ad + 2 * q, bd + 2 * q, idesc, (c | q) != 0);
+                    umma_commit(bar_empty(st));
+                    if (++st == kStages) { st = 0; ph ^= 1; }
+                }
+                umma_commit(bar_acc_full(buf));
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: thread = one row of the tile
+        const int q = warp & 3;
+        uint32_t it = 0;
+        for (long tile = blockIdx.x; tile < k.total_tiles; tile += gridDim.x, ++it) {
+            int grp, n0; long row0, row_end;
+            decode(tile, grp, row0, row_end, n0);
+            const int buf = it & 1;
+            const long row = row0 + q * 32 + lane;
+            const bool valid = row < row_end;
+            const float* bias = g.bias ? g.bias + (size_t)grp * g.bias_stride : nullptr;
+            const float* trow = nullptr;
+            if (g.tbl && valid) {
+                long t = g.trow[row];
+                t = t < 0 ? 0 : (t >= g.tbl_rows ? g.tbl_rows - 1 : t);
+                trow = g.tbl + t * g.tbl_ld;
+            }
+            mbar_wait(bar_acc_full(buf), (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
+            const int pieces = k.BN >> 4;
+            auto process = [&](const uint32_t (&cur)[16], int p) {
+                const int c0 = n0 + p * 16;
+                if (!valid || c0 >= g.N) return;
+                float z[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) z[i] = __uint_as_float(cur[i]);
+                if (bias) {
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + i4);
+                        z[4 * i4] += b.x; z[4 * i4 + 1] += b.y; z[4 * i4 + 2] += b.z; z[4 * i4 + 3] += b.w;
+                    }
+                }
+                if (trow) {
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(trow + c0) + i4);
+                        z[4 * i4] += b.x; z[4 * i4 + 1] += b.y; z[4 * i4 + 2] += b.z; z[4 * i4 + 3] += b.w;
+                    }
+                }
+                if (g.epi == EPI_MISH_FWD) {
+                    float d[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        // s = e^z + 1, p = s^2 + 1: tanh(softplus) = 1 - 2/p, sigmoid = 1 - 1/s; one rcp for both
+                        const float s = ex2_approx(fminf(z[i] * 1.4426950408889634f, 28.853900817779268f)) + 1.f;
+                        const float pp = fmaf(s, s, 1.f);
+                        const float qq = rcp_approx(s * pp);
+                        const float r = qq * s, inv_s = qq * pp;
+                        const float w = fmaf(-2.f, r, 1.f);
+                        d[i] = fmaf(z[i] * (1.f - inv_s), 4.f * r * (1.f - r), w);
+                        z[i] *= w;
+                    }
+                    store_bf16x16(g.out_a + row * g.out_ld + c0, z);
+                    store_bf16x16(g.out_d + row * g.out_ld + c0, d);
+                } else if (g.epi == EPI_ELU_FWD) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) z[i] = z[i] > 0.f ? z[i] : ex2_approx(z[i] * 1.4426950408889634f) - 1.f;
+                    store_bf16x16(g.out_a + row * g.out_ld + c0, z);
+                } else if (g.epi == EPI_LINEAR_F32) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < g.n_valid) g.out_f[row * g.outf_ld + c0 + i] = z[i];
+                } else {
+                    float a[16];
+                    load_bf16x16(g.aux + row * g.aux_ld + c0, a);
+                    if (g.epi == EPI_MUL_D) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) z[i] *= a[i];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) z[i] *= a[i] > 0.f ? 1.f : a[i] + 1.f;
+                    }
+                    store_bf16x16(g.out_a + row * g.out_ld + c0, z);
+                }
+            };
+            uint32_t va[16], vb[16];
+            tmem_ld16(tb, va);
+            for (int p = 0; p < pieces; p += 2) {
+                tmem_ld_wait();
+                if (p + 1 < pieces) tmem_ld16(tb + (p + 1) * 16, vb);
+                process(va, p);
+                if (p + 1 < pieces) {
+                    tmem_ld_wait();
+                    if (p + 2 < pieces) tmem_ld16(tb + (p + 2) * 16, va);
+                    process(vb, p + 1);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty(buf));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------ dW GEMM
+struct DwKernelArgs {
+    DwGemm g;
+    int BN;                 // X columns per tile (64..256, multiple of 64)
+    int tiles_n, tiles_k;   // output tiles along dZ columns (128 each) and X columns (BN each)
+    long rows_per_split;
+};
+
+// MN-major SWIZZLE_128B operand: 64-element (128 B) rows per reduction index, 64-element blocks along M/N
+// `lbo` bytes apart, 8-row groups 1024 B apart (cute: ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)))
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+dw_gemm_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_x, const DwKernelArgs k) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const uint32_t bars = base + kOffBars;
+    auto bar_full = [&](int i) { return bars + 8 * i; };
+    auto bar_empty = [&](int i) { return bars + 8 * (kStages + i); };
+    const uint32_t bar_done = bars + 8 * (2 * kStages);
+    const uint32_t tmem_slot = bars + 8 * (2 * kStages + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const DwGemm& g = k.g;
+
+    const int tile = blockIdx.x % (k.tiles_n * k.tiles_k), split = blockIdx.x / (k.tiles_n * k.tiles_k);
+    const int n0 = (tile % k.tiles_n) * 128, k0 = (tile / k.tiles_n) * k.BN;
+    const long r_begin = (long)split * k.rows_per_split;
+    const long r_end = r_begin + k.rows_per_split < g.R ? r_begin + k.rows_per_split : g.R;
+    const int chunks = r_end > r_begin ? (int)((r_end - r_begin + 63) >> 6) : 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
+        mbar_init(bar_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
+    const int xboxes = k.BN >> 6;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&map_z);
+            tma_prefetch_desc(&map_x);
+            int st = 0; uint32_t ph = 0;
+            for (int c = 0; c < chunks; ++c) {
+                mbar_wait(bar_empty(st), ph ^ 1);
+                mbar_expect_tx(bar_full(st), (uint32_t)((2 + xboxes) * 8192));
+                const int r = (int)(r_begin + (long)c * 64);
+                // rows past r_end inside the last chunk belong to the next split: they are read here too, so
+                // splits are kept multiples of 64 rows on the host (only the global tail is zero-filled)
+                tma_load_2d(base + st * kStageBytes, &map_z, bar_full(st), n0, r);
+                tma_load_2d(base + st * kStageBytes + 8192, &map_z, bar_full(st), n0 + 64, r);
+                for (int b = 0; b < xboxes; ++b)
+                    tma_load_2d(base + st * kStageBytes + kStageA + b * 8192, &map_x, bar_full(st), k0 + b * 64, r);
+                if (++st == kStages) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // both operands MN-major: bits 15 / 16 of the instruction descriptor
+            const uint32_t idesc = make_idesc_16(128, k.BN, false) | (1u << 15) | (1u << 16);
+            int st = 0; uint32_t ph = 0;
+            for (int c = 0; c < chunks; ++c) {
+                mbar_wait(bar_full(st), ph);
+                tc_fence_after();
+                const uint32_t a0 = base + st * kStageBytes, b0 = a0 + kStageA;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)       // 16 reduction rows per instruction = 2 KB
+                    umma_bf16(tmem_base, make_smem_desc_mn_sw128(a0 + q * 2048, 8192),
+                              make_smem_desc_mn_sw128(b0 + q * 2048, 8192), idesc, (c | q) != 0);
+                umma_commit(bar_empty(st));
+                if (++st == kStages) { st = 0; ph ^= 1; }
+            }
+            umma_commit(bar_done);
+        }
+    } else if (chunks > 0) {
+        const int q = warp & 3;
+        const int n = n0 + q * 32 + lane;
+        mbar_wait(bar_done, 0);
+        tc_fence_after();
+        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int p = 0; p < (k.BN >> 4); ++p) {
+            uint32_t v[16];
+            tmem_ld16(tb + p * 16, v);
+            tmem_ld_wait();
+            if (n >= g.N) continue;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int kk = k0 + p * 16 + i;
+                if (kk >= g.K) break;
+                const int col = g.colmap ? g.colmap[kk] : kk;
+                if (col >= 0) atomicAdd(g.C + (size_t)n * g.ldc + col, __uint_as_float(v[i]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+}  // namespace
+
+int launch_row_gemm(const RowGemm& g, cudaStream_t st) {
+    if (g.M <= 0) return DDP_OK;
+    if (g.N <= 0 || g.K <= 0 || g.lda % 8 || g.ldw % 8) DDP_FAIL(DDP_ERR_SHAPE, "row gemm: bad shape (N=%d K=%d lda=%d ldw=%d)", g.N, g.K, g.lda, g.ldw);
+    if (g.groups.n_groups < 1 || g.groups.n_groups > kMaxGroups) DDP_FAIL(DDP_ERR_SHAPE, "row gemm: bad group count");
+    RowKernelArgs k;
+    k.g = g;
+    const int n16 = (g.N + 15) / 16 * 16;
+    k.BN = n16 < 256 ? n16 : 256;
+    k.n_tiles_n = (g.N + k.BN - 1) / k.BN;
+    long tiles = 0;
+    for (int i = 0; i < g.groups.n_groups; ++i) {
+        k.tile0[i] = tiles;
+        tiles += (g.groups.off[i + 1] - g.groups.off[i] + 127) / 128;
+    }
+    k.tile0[g.groups.n_groups] = tiles;
+    k.total_tiles = tiles * k.n_tiles_n;
+    if (k.total_tiles == 0) return DDP_OK;
+    CUtensorMap ma;
+    WMaps mw;
+    if (make_tmap(&ma, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, 128) != 0)
+        DDP_FAIL(DDP_ERR_CUDA, "row gemm: tensor map (A) failed");
+    for (int i = 0; i < g.groups.n_groups; ++i)
+        if (make_tmap(&mw.m[i], g.W + (size_t)i * g.w_stride, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, (uint32_t)k.BN) != 0)
+            DDP_FAIL(DDP_ERR_CUDA, "row gemm: tensor map (W) failed");
+    for (int i = g.groups.n_groups; i < kMaxGroups; ++i) mw.m[i] = mw.m[0];
+    int dev = 0, sms = 0;
+    DDP_CUDA_CHECK(cudaGetDevice(&dev));
+    DDP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DDP_CUDA_CHECK(cudaFuncSetAttribute(row_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    const long grid = k.total_tiles < sms ? k.total_tiles : sms;
+    row_gemm_kernel<<<(unsigned)grid, kThreads, kSmemBytes, st>>>(ma, mw, k);
+    DDP_LAUNCH_CHECK("row_gemm_kernel");
+    return DDP_OK;
+}
+
+int launch_dw_gemm(const DwGemm& g, cudaStream_t st) {
+    if (g.R <= 0) return DDP_OK;
+    if (g.N <= 0 || g.K <= 0 || g.ldz % 8 || g.ldx % 8) DDP_FAIL(DDP_ERR_SHAPE, "dW gemm: bad shape");
+    DwKernelArgs k;
+    k.g = g;
+    const int k64 = (g.K + 63) / 64 * 64;
+    k.BN = k64 < 256 ? k64 : 256;
+    k.tiles_n = (g.N + 127) / 128;
+    k.tiles_k = (g.K + k.BN - 1) / k.BN;
+    const long tiles = (long)k.tiles_n * k.tiles_k;
+    const long chunks = (g.R + 63) / 64;
+    long splits = (2 * 148 + tiles - 1) / tiles;          // about two waves of CTAs
+    if (splits > chunks) splits = chunks;
+    if (splits < 1) splits = 1;
+    const long cps = (chunks + splits - 1) / splits;
+    k.rows_per_split = cps * 64;
+    splits = (chunks + cps - 1) / cps;
+    CUtensorMap mz, mx;
+    if (make_tmap(&mz, g.dZ, (uint64_t)g.R, (uint64_t)g.N, (uint64_t)g.ldz, 64) != 0 ||
+        make_tmap(&mx, g.X, (uint64_t)g.R, (uint64_t)g.K, (uint64_t)g.ldx, 64) != 0)
+        DDP_FAIL(DDP_ERR_CUDA, "dW gemm: tensor map failed");
+    DDP_CUDA_CHECK(cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    dw_gemm_kernel<<<(unsigned)(tiles * splits), kThreads, kSmemBytes, st>>>(mz, mx, k);
+    DDP_LAUNCH_CHECK("dw_gemm_kernel");
+    return DDP_OK;
+}
+
+}  // namespace tcg
+}  // namespace ddp
+
+// Debug entry points (not part of the public header) used by tests/test_tc_gemm_gpu.py
+extern "C" int ddp_debug_row_gemm(const void* A, int lda, const void* W, int ldw, long M, int N, int K, int epi,
+                                  const float* bias, const void* aux, void* out_a, void* out_d, float* out_f,
+                                  int n_groups, const long* group_off, size_t w_stride, size_t bias_stride,
+                                  const float* tbl, const int64_t* trow, int tbl_ld, int tbl_rows, void* stream) {
+    using namespace ddp::tcg;
+    RowGemm g{};
+    g.A = (const __nv_bfloat16*)A; g.lda = lda; g.W = (const __nv_bfloat16*)W; g.ldw = ldw; g.w_stride = w_stride;
+    g.M = M; g.N = N; g.K = K; g.epi = epi; g.bias = bias; g.bias_stride = bias_stride;
+    g.tbl = tbl; g.trow = trow; g.tbl_ld = tbl_ld; g.tbl_rows = tbl_rows;
+    g.aux = (const __nv_bfloat16*)aux; g.aux_ld = N;
+    g.out_a = (__nv_bfloat16*)out_a; g.out_d = (__nv_bfloat16*)out_d; g.out_ld = N;
+    g.out_f = out_f; g.outf_ld = N; g.n_valid = N;
+    g.groups.n_groups = n_groups;
+    for (int i = 0; i <= n_groups; ++i) g.groups.off[i] = group_off[i];
+    return launch_row_gemm(g, (cudaStream_t)stream);
+}
+
+extern "C" int ddp_debug_dw_gemm(const void* dZ, int ldz, int N, const void* X, int ldx, int K, long R, float* C, int ldc,
+                                 const int* colmap, void* stream) {
+    using namespace ddp::tcg;
+    DwGemm g{};
+    g.dZ = (const __nv_bfloat16*)dZ; g.ldz = ldz; g.N = N; g.X = (const __nv_bfloat16*)X; g.ldx = ldx; g.K = K;
+    g.R = R; g.C = C; g.ldc = ldc; g.colmap = colmap;
+    return launch_dw_gemm(g, (cudaStream_t)stream);
+}
