@@ -215,7 +215,7 @@ def run_cuda(args):
         pol = DiffusionPolicy(S, A, T, device="cuda", hidden=hidden)
         cpu_params = {k: v.clone() for k, v in pol.state_dict().items()}
         pol.to(dev)
-        trainer = FusedActorTrainer(pol)
+        trainer = FusedActorTrainer(pol, precision=args.precision)
         st_h = torch.randn(B, S, generator=gen).pin_memory()
         ac_h = (torch.rand(B, A, generator=gen) * 2 - 1).pin_memory()
         st, ac = st_h.to(dev), ac_h.to(dev)

@@ -115,8 +115,9 @@ class FusedActorTrainer:
     ``torch.optim.AdamW(actor.parameters(), actor_lr)`` (ac_base.py:52) and ``max_grad_norm`` 1.0."""
 
     def __init__(self, actor, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0,
-                 process_group=None):
+                 process_group=None, precision=None):
         self.actor = actor
+        self.precision = precision          # None: actor.train_precision ("fp32" | "bf16")
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.max_grad_norm = float("inf") if max_grad_norm is None else max_grad_norm
         self.group = process_group
@@ -161,7 +162,8 @@ class FusedActorTrainer:
         if timesteps is None:
             timesteps = torch.randint(0, actor.diffusion_iter, (B,), device=dev)
         loss, grads = actor._loss_and_grads(state, action, noise, timesteps,
-                                            inv_count=1.0 / (global_batch * actor.action_dim))
+                                            inv_count=1.0 / (global_batch * actor.action_dim),
+                                            precision=self.precision)
         # the one exchange step of the path: sum the flat gradient (and the loss) over NVLink
         ddist.allreduce_sum_(grads, loss, group=self.group)
         self.step_count += 1

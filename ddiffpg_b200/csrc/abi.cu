@@ -25,6 +25,11 @@ size_t actor_train_workspace(const ActorLayout& L, long B);
 int actor_train_fma(const ActorLayout& L, const float* pk, const float* const p[12], const float* state,
                     const float* action, const float* noise, const int64_t* t, float inv_count, float* loss_out,
                     float* grads, long B, void* ws, size_t ws_bytes, cudaStream_t st);
+int pack_actor_train_tc(const ActorLayout& L, const float* const p[12], void* packed, cudaStream_t st);
+size_t actor_train_tc_workspace(const ActorLayout& L, long B);
+int actor_train_tc(const ActorLayout& L, const void* packed, const float* const p[12], const float* state,
+                   const float* action, const float* noise, const int64_t* t, float inv_count, float* loss_out,
+                   float* grads, long B, void* ws, size_t ws_bytes, cudaStream_t st);
 int clip_adamw(float* p, float* g, float* m, float* v, size_t n, int step, float lr, float b1, float b2, float eps,
                float wd, float max_norm, float* norm_out, float* scratch, cudaStream_t st);
 int pack_q_fp32(const QLayout& L, const float* const p[], float* out, cudaStream_t st);
@@ -64,7 +69,11 @@ int ddp_actor_pack(const ddp_actor_shape* s, const float* const params[12], void
     cudaStream_t st = (cudaStream_t)stream;
     rc = pack_actor_fp32(L, params, (float*)packed, st);
     if (rc != DDP_OK) return rc;
-    if (precision == DDP_BF16) return pack_actor_tc(L, params, packed, st);
+    if (precision == DDP_BF16) {
+        rc = pack_actor_tc(L, params, packed, st);
+        if (rc != DDP_OK) return rc;
+        return pack_actor_train_tc(L, params, packed, st);
+    }
     return DDP_OK;
 }
 
@@ -95,6 +104,7 @@ size_t ddp_actor_grad_count(const ddp_actor_shape* s) {
 
 size_t ddp_actor_train_workspace_bytes(const ddp_actor_shape* s, long B, int precision) {
     if (check_actor_shape(s) != DDP_OK || B <= 0) return 0;
+    if (precision == DDP_BF16) return actor_train_tc_workspace(make_actor_layout(*s, precision), B);
     return actor_train_workspace(make_actor_layout(*s, precision), B);
 }
 
@@ -107,10 +117,13 @@ int ddp_actor_loss_fwd_bwd(const ddp_actor_shape* s, const void* packed, const f
     if (B <= 0) DDP_FAIL(DDP_ERR_SHAPE, "ddp_actor_loss_fwd_bwd: batch must be positive");
     if (!packed || !params || !state || !action || !noise || !t || !loss_out || !grads_flat || !ws)
         DDP_FAIL(DDP_ERR_ARG, "ddp_actor_loss_fwd_bwd: NULL argument");
-    if (precision != DDP_FP32) DDP_FAIL(DDP_ERR_UNSUPPORTED, "training step: only DDP_FP32 is implemented");
+    if (precision != DDP_FP32 && precision != DDP_BF16) DDP_FAIL(DDP_ERR_ARG, "unknown precision %d", precision);
     ActorLayout L = make_actor_layout(*s, precision);
-    if (ws_bytes < actor_train_workspace(L, B)) DDP_FAIL(DDP_ERR_ARG, "ddp_actor_loss_fwd_bwd: workspace too small");
     if (!aligned16(ws) || !aligned16(grads_flat)) DDP_FAIL(DDP_ERR_ARG, "workspace/grads must be 16-byte aligned");
+    if (precision == DDP_BF16)
+        return actor_train_tc(L, packed, params, state, action, noise, t, inv_count, loss_out, grads_flat, B, ws,
+                              ws_bytes, (cudaStream_t)stream);
+    if (ws_bytes < actor_train_workspace(L, B)) DDP_FAIL(DDP_ERR_ARG, "ddp_actor_loss_fwd_bwd: workspace too small");
     return actor_train_fma(L, (const float*)packed, params, state, action, noise, t, inv_count, loss_out, grads_flat,
                            B, ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -34,6 +34,8 @@ struct ActorLayout {
     // bf16 tensor-core section (offsets in BYTES from the start of the buffer), precision == BF16
     size_t tc_w0, tc_w1, tc_w2, tc_w3;        // bf16 operands
     size_t tc_w0h, tc_w1h, tc_w2h, tc_w3h;    // fp16 copies for the ill-conditioned first denoising step
+    // training tensor path (H3): plain K-major bf16 operands of the row GEMMs and their transposes
+    size_t tr_w0, tr_w3, tr_w3t, tr_w2t, tr_w1t, tr_colmap;
     size_t total_bytes;
 };
 
@@ -60,6 +62,7 @@ inline ActorLayout make_actor_layout(const ddp_actor_shape& s, int precision) {
     size_t bytes = align_up(o * sizeof(float), 1024);
     L.tc_w0 = L.tc_w1 = L.tc_w2 = L.tc_w3 = 0;
     L.tc_w0h = L.tc_w1h = L.tc_w2h = L.tc_w3h = 0;
+    L.tr_w0 = L.tr_w3 = L.tr_w3t = L.tr_w2t = L.tr_w1t = L.tr_colmap = 0;
     if (precision == DDP_BF16) {
         // filled in by the tensor-core packer (actor_sample_tc.cu); sizes in bf16 elements
         auto takeb = [&](size_t nbytes) { size_t r = bytes; bytes += align_up(nbytes, 1024); return r; };
@@ -71,6 +74,12 @@ inline ActorLayout make_actor_layout(const ddp_actor_shape& s, int precision) {
         L.tc_w1h = takeb((size_t)s.h2 * s.h1 * 2);
         L.tc_w2h = takeb((size_t)s.h3 * s.h2 * 2);
         L.tc_w3h = takeb((size_t)16 * s.h3 * 2);
+        L.tr_w0 = takeb((size_t)s.h1 * 64 * 2);            // [h1][64]   K order [x | state | 0]
+        L.tr_w3 = takeb((size_t)16 * s.h3 * 2);            // [16][h3]   rows >= A are zero
+        L.tr_w3t = takeb((size_t)s.h3 * 64 * 2);           // [h3][64]   W3^T, columns >= A are zero
+        L.tr_w2t = takeb((size_t)s.h2 * s.h3 * 2);         // [h2][h3]   W2^T
+        L.tr_w1t = takeb((size_t)s.h1 * s.h2 * 2);         // [h1][h2]   W1^T
+        L.tr_colmap = takeb(64 * 4);                       // xin column -> net.mlp.0.weight column
     }
     L.total_bytes = bytes;
     return L;

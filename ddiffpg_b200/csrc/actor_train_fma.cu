@@ -319,6 +319,21 @@ __global__ void rows_linear_t_kernel(const float* __restrict__ g, int ldg, int N
     y[(size_t)t * M + i] = acc;
 }
 
+// Backward of the time branch on its T distinct rows, given G[t] = sum of dZ0 rows with timestep t:
+// gradients of the 256 time columns of net.mlp.0 (+ its bias) and of both time_mlp layers.
+void time_branch_backward(const ActorLayout& L, const float* pk, const float* const p[12], const float* G,
+                          float* dtemb, float* dhmid, float* g, cudaStream_t st) {
+    ddp_actor_shape shp{L.S, L.A, L.T, L.D, L.h1, L.h2, L.h3};
+    const ActorGradOffsets go = actor_grad_offsets(shp);
+    const int D = L.D, ld0 = D + L.S + L.A;
+    launch_dw(G, L.h1, L.h1, pk + L.temb, D, D, g + go.off[4], ld0, g + go.off[5], L.T, st);
+    dim3 gt((D + 127) / 128, L.T), gm((4 * D + 127) / 128, L.T);
+    rows_linear_t_kernel<<<gt, 128, 0, st>>>(G, L.h1, L.h1, p[4], ld0, D, nullptr, dtemb);               // dtemb = G . W0[:, :D]
+    launch_dw(dtemb, D, D, pk + L.hmid, 4 * D, 4 * D, g + go.off[2], 4 * D, g + go.off[3], L.T, st);
+    rows_linear_t_kernel<<<gm, 128, 0, st>>>(dtemb, D, D, p[2], 4 * D, 4 * D, pk + L.zmid, dhmid);        // dZmid
+    launch_dw(dhmid, 4 * D, 4 * D, pk + L.pe, D, D, g + go.off[0], D, g + go.off[1], L.T, st);
+}
+
 template <int RT>
 static int launch_train(const ActorLayout& L, const TrainArgs& a, const TrainWs& w, const float* state,
                         const float* action, const float* noise, const int64_t* t, float inv_count, float* loss_out,
@@ -367,13 +382,7 @@ int actor_train_fma(const ActorLayout& L, const float* pk, const float* const p[
     launch_dw(w.d2, L.h3, L.h3, w.act1, L.h2, L.h2, g + go.off[8], L.h2, g + go.off[9], B, st);
     launch_dw(w.d1, L.h2, L.h2, w.act0, L.h1, L.h1, g + go.off[6], L.h1, g + go.off[7], B, st);
     launch_dw(w.d0, L.h1, L.h1, w.xin, L.K0p, L.S + L.A, g + go.off[4] + D, ld0, nullptr, B, st);
-    // time branch on T rows: G[t] = sum of dZ0 rows with timestep t
-    launch_dw(w.G, L.h1, L.h1, pk + L.temb, D, D, g + go.off[4], ld0, g + go.off[5], L.T, st);
-    dim3 gt((D + 127) / 128, L.T), gm((4 * D + 127) / 128, L.T);
-    rows_linear_t_kernel<<<gt, 128, 0, st>>>(w.G, L.h1, L.h1, p[4], ld0, D, nullptr, w.dtemb);          // dtemb = G . W0[:, :D]
-    launch_dw(w.dtemb, D, D, pk + L.hmid, 4 * D, 4 * D, g + go.off[2], 4 * D, g + go.off[3], L.T, st);
-    rows_linear_t_kernel<<<gm, 128, 0, st>>>(w.dtemb, D, D, p[2], 4 * D, 4 * D, pk + L.zmid, w.dhmid);   // dZmid
-    launch_dw(w.dhmid, 4 * D, 4 * D, pk + L.pe, D, D, g + go.off[0], D, g + go.off[1], L.T, st);
+    time_branch_backward(L, pk, p, w.G, w.dtemb, w.dhmid, g, st);
     DDP_LAUNCH_CHECK("train dW kernels");
     return DDP_OK;
 }

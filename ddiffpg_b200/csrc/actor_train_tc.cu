@@ -1,0 +1,232 @@
+// H3, bf16 tensor-core path: denoiser eps-loss forward + backward assembled from the tcgen05 row GEMM (one per
+// Linear, activation / derivative fused in the TMEM epilogue) and the MN-major dW GEMM (csrc/tc_gemm.cu).
+//
+// Reference semantics (paths relative to the reference repo):
+//   DiffusionPolicy.get_loss (add_noise, net, mse_loss)     ddiffpg/models/diffusion_mlp.py:294-321
+//   objective.backward() of optimizer_update                 ddiffpg/algo/ac_base.py:83-85
+// Operands bf16, accumulation fp32; loss, d loss/d eps and every gradient accumulate in fp32.  The time branch
+// uses the packed fp32 [T, h1] table in the forward (added per row in the epilogue of layer 0) and, in the
+// backward, G[t] = sum of dZ0 rows with timestep t obtained as dZ0^T . onehot(t) by the same dW GEMM, followed
+// by the fp32 T-row products shared with the fp32 path.
+#include "actor_layout.cuh"
+#include "tc_gemm.cuh"
+
+namespace ddp {
+
+void time_branch_backward(const ActorLayout& L, const float* pk, const float* const p[12], const float* G,
+                          float* dtemb, float* dhmid, float* g, cudaStream_t st);
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+struct TrainTcWs {
+    bf16 *xin, *onehot, *a0, *d0, *a1, *d1, *a2, *d2, *deps;
+    float *eps, *GT, *G, *dtemb, *dhmid;
+    size_t total;
+};
+
+TrainTcWs carve(const ActorLayout& L, long B, uint8_t* base) {
+    TrainTcWs w{};
+    size_t o = 0;
+    auto take = [&](size_t bytes) { uint8_t* r = base ? base + o : nullptr; o += (bytes + 255) / 256 * 256; return r; };
+    const int Tp = (L.T + 7) / 8 * 8;
+    w.xin = (bf16*)take((size_t)B * 64 * 2);
+    w.onehot = (bf16*)take((size_t)B * Tp * 2);
+    w.a0 = (bf16*)take((size_t)B * L.h1 * 2); w.d0 = (bf16*)take((size_t)B * L.h1 * 2);
+    w.a1 = (bf16*)take((size_t)B * L.h2 * 2); w.d1 = (bf16*)take((size_t)B * L.h2 * 2);
+    w.a2 = (bf16*)take((size_t)B * L.h3 * 2); w.d2 = (bf16*)take((size_t)B * L.h3 * 2);
+    w.deps = (bf16*)take((size_t)B * 64 * 2);
+    w.eps = (float*)take((size_t)B * 16 * 4);
+    w.GT = (float*)take((size_t)L.h1 * Tp * 4);
+    w.G = (float*)take((size_t)L.T * L.h1 * 4);
+    w.dtemb = (float*)take((size_t)L.T * L.D * 4);
+    w.dhmid = (float*)take((size_t)L.T * 4 * L.D * 4);
+    w.total = o;
+    return w;
+}
+
+// xin[r] = [noisy action (A, padded to 8) | state (S) | 0 ...] (64 columns), onehot[r][t_r] = 1
+__global__ void train_tc_prep_kernel(const float* __restrict__ state, const float* __restrict__ action,
+                                     const float* __restrict__ noise, const int64_t* __restrict__ ts,
+                                     const float* __restrict__ cst, int S, int A, int T, int Tp, long B,
+                                     bf16* __restrict__ xin, bf16* __restrict__ onehot) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long row = idx >> 6;
+    const int c = (int)(idx & 63);
+    if (row >= B) return;
+    int t = (int)ts[row];
+    t = t < 0 ? 0 : (t >= T ? T - 1 : t);
+    float v = 0.f;
+    if (c < 8) {
+        if (c < A) {
+            const float* cs = cst + t * kCstStride;       // scheduler.add_noise (diffusion_mlp.py:309-310)
+            v = __fadd_rn(__fmul_rn(cs[CST_ADD_A], action[row * A + c]), __fmul_rn(cs[CST_ADD_B], noise[row * A + c]));
+        }
+    } else if (c - 8 < S) {
+        v = state[row * S + c - 8];
+    }
+    xin[row * 64 + c] = __float2bfloat16(v);
+    if (c < Tp) onehot[row * Tp + c] = __float2bfloat16(c == t ? 1.f : 0.f);
+}
+
+// eps_hat [B][16] fp32 -> loss partial sum (mse_loss, :320) and d loss / d eps_hat as zero-padded bf16 [B][64]
+__global__ void train_tc_loss_kernel(const float* __restrict__ eps, const float* __restrict__ noise, int A, long B,
+                                     float inv_count, float* __restrict__ loss_out, bf16* __restrict__ deps) {
+    __shared__ float red[8];
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long row = idx >> 6;
+    const int c = (int)(idx & 63);
+    float sq = 0.f;
+    if (row < B) {
+        float d = 0.f;
+        if (c < A) {
+            const float diff = eps[row * 16 + c] - noise[row * A + c];
+            sq = diff * diff;
+            d = 2.f * diff * inv_count;
+        }
+        deps[row * 64 + c] = __float2bfloat16(d);
+    }
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        if (s != 0.f) atomicAdd(loss_out, s * inv_count);
+    }
+}
+
+// db[n] += sum_r dZ[r][n]  (bias gradients), bf16 input, fp32 atomics; one block handles 64 rows x N columns
+__global__ void colsum_bf16_kernel(const bf16* __restrict__ dz, int ld, int N, long R, float* __restrict__ db) {
+    const long r0 = (long)blockIdx.x * 256;
+    for (int c = threadIdx.x; c < N; c += blockDim.x) {
+        float s = 0.f;
+        const long r1 = r0 + 256 < R ? r0 + 256 : R;
+        for (long r = r0; r < r1; ++r) s += __bfloat162float(dz[r * ld + c]);
+        atomicAdd(db + c, s);
+    }
+}
+
+__global__ void transpose_small_kernel(const float* __restrict__ src, int rows, int cols, int ld, float* __restrict__ dst) {
+    // dst[c][r] = src[r][c]  (src: [rows][ld], dst: [cols][rows])
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols) return;
+    const int r = idx / cols, c = idx % cols;
+    dst[(size_t)c * rows + r] = src[(size_t)r * ld + c];
+}
+
+// plain bf16 operands for the training GEMMs
+__global__ void pack_train_tc_kernel(const float* __restrict__ W0, const float* __restrict__ W1,
+                                     const float* __restrict__ W2, const float* __restrict__ W3, int D, int S, int A,
+                                     int h1, int h2, int h3, bf16* __restrict__ w0, bf16* __restrict__ w3,
+                                     bf16* __restrict__ w3t, bf16* __restrict__ w2t, bf16* __restrict__ w1t,
+                                     int* __restrict__ colmap) {
+    const size_t n0 = (size_t)h1 * 64, n3 = (size_t)16 * h3, n3t = (size_t)h3 * 64, n2t = (size_t)h2 * h3,
+                 n1t = (size_t)h1 * h2;
+    const int ld0 = D + S + A;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n3 + n3t + n2t + n1t + 64;
+         i += (size_t)gridDim.x * blockDim.x) {
+        size_t j = i;
+        if (j < n0) {                                   // w0[f][k]: k < 8 -> x column k, 8 <= k < 8+S -> state
+            const int f = (int)(j / 64), k = (int)(j % 64);
+            float v = 0.f;
+            if (k < 8) { if (k < A) v = W0[(size_t)f * ld0 + D + S + k]; }
+            else if (k - 8 < S) v = W0[(size_t)f * ld0 + D + k - 8];
+            w0[j] = __float2bfloat16(v);
+            continue;
+        }
+        j -= n0;
+        if (j < n3) { const int r = (int)(j / h3), c = (int)(j % h3); w3[j] = __float2bfloat16(r < A ? W3[(size_t)r * h3 + c] : 0.f); continue; }
+        j -= n3;
+        if (j < n3t) { const int r = (int)(j / 64), c = (int)(j % 64); w3t[j] = __float2bfloat16(c < A ? W3[(size_t)c * h3 + r] : 0.f); continue; }
+        j -= n3t;
+        if (j < n2t) { const int r = (int)(j / h3), c = (int)(j % h3); w2t[j] = __float2bfloat16(W2[(size_t)c * h2 + r]); continue; }
+        j -= n2t;
+        if (j < n1t) { const int r = (int)(j / h2), c = (int)(j % h2); w1t[j] = __float2bfloat16(W1[(size_t)c * h1 + r]); continue; }
+        j -= n1t;
+        const int k = (int)j;
+        colmap[k] = k < 8 ? (k < A ? D + S + k : -1) : (k - 8 < S ? D + k - 8 : -1);
+    }
+}
+
+bool shape_ok(const ActorLayout& L) { return L.A <= 8 && L.S + 8 <= 64 && L.h1 % 64 == 0 && L.h2 % 64 == 0 && L.h3 % 64 == 0; }
+
+}  // namespace
+
+int pack_actor_train_tc(const ActorLayout& L, const float* const p[12], void* packed, cudaStream_t st) {
+    if (!shape_ok(L)) return DDP_OK;        // the sampler-only shapes simply have no training tensor path
+    uint8_t* b = (uint8_t*)packed;
+    pack_train_tc_kernel<<<592, 256, 0, st>>>(p[4], p[6], p[8], p[10], L.D, L.S, L.A, L.h1, L.h2, L.h3,
+                                               (bf16*)(b + L.tr_w0), (bf16*)(b + L.tr_w3), (bf16*)(b + L.tr_w3t),
+                                               (bf16*)(b + L.tr_w2t), (bf16*)(b + L.tr_w1t), (int*)(b + L.tr_colmap));
+    DDP_LAUNCH_CHECK("pack_train_tc_kernel");
+    return DDP_OK;
+}
+
+size_t actor_train_tc_workspace(const ActorLayout& L, long B) { return carve(L, B, nullptr).total; }
+
+int actor_train_tc(const ActorLayout& L, const void* packed, const float* const p[12], const float* state,
+                   const float* action, const float* noise, const int64_t* t, float inv_count, float* loss_out,
+                   float* grads, long B, void* ws, size_t ws_bytes, cudaStream_t st) {
+    using namespace tcg;
+    if (!shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 training path needs A<=8, S<=56, widths multiple of 64");
+    if (ws_bytes < carve(L, B, nullptr).total) DDP_FAIL(DDP_ERR_ARG, "training workspace too small");
+    const uint8_t* pb = (const uint8_t*)packed;
+    const float* pk = (const float*)packed;
+    TrainTcWs w = carve(L, B, (uint8_t*)ws);
+    ddp_actor_shape shp{L.S, L.A, L.T, L.D, L.h1, L.h2, L.h3};
+    const ActorGradOffsets go = actor_grad_offsets(shp);
+    const int Tp = (L.T + 7) / 8 * 8, D = L.D, ld0 = D + L.S + L.A;
+    DDP_CUDA_CHECK(cudaMemsetAsync(grads, 0, go.off[12] * sizeof(float), st));
+    DDP_CUDA_CHECK(cudaMemsetAsync(w.GT, 0, (size_t)L.h1 * Tp * sizeof(float), st));
+    const unsigned eb = (unsigned)((B * 64 + 255) / 256);
+    train_tc_prep_kernel<<<eb, 256, 0, st>>>(state, action, noise, t, pk + L.cst, L.S, L.A, L.T, Tp, B, w.xin, w.onehot);
+
+    auto row = [&](const bf16* A, int lda, const bf16* W, int ldw, int N, int K, int epi, const float* bias,
+                   const bf16* aux, bf16* out_a, bf16* out_d, float* out_f, int outf_ld, int n_valid) {
+        RowGemm g{};
+        g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.M = B; g.N = N; g.K = K; g.epi = epi; g.bias = bias;
+        g.aux = aux; g.aux_ld = N; g.out_a = out_a; g.out_d = out_d; g.out_ld = N;
+        g.out_f = out_f; g.outf_ld = outf_ld; g.n_valid = n_valid;
+        g.groups.n_groups = 1; g.groups.off[0] = 0; g.groups.off[1] = B;
+        return g;
+    };
+    int rc;
+    // ---- forward
+    {
+        RowGemm g = row(w.xin, 64, (const bf16*)(pb + L.tr_w0), 64, L.h1, 64, EPI_MISH_FWD, nullptr, nullptr, w.a0, w.d0, nullptr, 0, 0);
+        g.tbl = pk + L.tb0; g.trow = t; g.tbl_ld = L.h1; g.tbl_rows = L.T;      // time table (includes b0), per row
+        if ((rc = launch_row_gemm(g, st)) != DDP_OK) return rc;
+    }
+    if ((rc = launch_row_gemm(row(w.a0, L.h1, (const bf16*)(pb + L.tc_w1), L.h1, L.h2, L.h1, EPI_MISH_FWD, pk + L.b1, nullptr, w.a1, w.d1, nullptr, 0, 0), st)) != DDP_OK) return rc;
+    if ((rc = launch_row_gemm(row(w.a1, L.h2, (const bf16*)(pb + L.tc_w2), L.h2, L.h3, L.h2, EPI_MISH_FWD, pk + L.b2, nullptr, w.a2, w.d2, nullptr, 0, 0), st)) != DDP_OK) return rc;
+    if ((rc = launch_row_gemm(row(w.a2, L.h3, (const bf16*)(pb + L.tr_w3), L.h3, 16, L.h3, EPI_LINEAR_F32, pk + L.b3, nullptr, nullptr, nullptr, w.eps, 16, L.A), st)) != DDP_OK) return rc;
+    train_tc_loss_kernel<<<eb, 256, 0, st>>>(w.eps, noise, L.A, B, inv_count, loss_out, w.deps);
+    // ---- backward: dZ chain (dZ_l overwrites the stored derivative d_l in place)
+    if ((rc = launch_row_gemm(row(w.deps, 64, (const bf16*)(pb + L.tr_w3t), 64, L.h3, 64, EPI_MUL_D, nullptr, w.d2, w.d2, nullptr, nullptr, 0, 0), st)) != DDP_OK) return rc;
+    if ((rc = launch_row_gemm(row(w.d2, L.h3, (const bf16*)(pb + L.tr_w2t), L.h3, L.h2, L.h3, EPI_MUL_D, nullptr, w.d1, w.d1, nullptr, nullptr, 0, 0), st)) != DDP_OK) return rc;
+    if ((rc = launch_row_gemm(row(w.d1, L.h2, (const bf16*)(pb + L.tr_w1t), L.h2, L.h1, L.h2, EPI_MUL_D, nullptr, w.d0, w.d0, nullptr, nullptr, 0, 0), st)) != DDP_OK) return rc;
+    // ---- weight gradients
+    auto dw = [&](const bf16* dz, int ldz, int N, const bf16* X, int ldx, int K, float* C, int ldc, const int* colmap) {
+        DwGemm g{};
+        g.dZ = dz; g.ldz = ldz; g.N = N; g.X = X; g.ldx = ldx; g.K = K; g.R = B; g.C = C; g.ldc = ldc; g.colmap = colmap;
+        return launch_dw_gemm(g, st);
+    };
+    if ((rc = dw(w.deps, 64, L.A, w.a2, L.h3, L.h3, grads + go.off[10], L.h3, nullptr)) != DDP_OK) return rc;
+    if ((rc = dw(w.d2, L.h3, L.h3, w.a1, L.h2, L.h2, grads + go.off[8], L.h2, nullptr)) != DDP_OK) return rc;
+    if ((rc = dw(w.d1, L.h2, L.h2, w.a0, L.h1, L.h1, grads + go.off[6], L.h1, nullptr)) != DDP_OK) return rc;
+    if ((rc = dw(w.d0, L.h1, L.h1, w.xin, 64, 64, grads + go.off[4], ld0, (const int*)(pb + L.tr_colmap))) != DDP_OK) return rc;
+    if ((rc = dw(w.d0, L.h1, L.h1, w.onehot, Tp, L.T, w.GT, Tp, nullptr)) != DDP_OK) return rc;       // G^T[n][t]
+    const unsigned rb = (unsigned)((B + 255) / 256);
+    colsum_bf16_kernel<<<rb, 256, 0, st>>>(w.deps, 64, L.A, B, grads + go.off[11]);
+    colsum_bf16_kernel<<<rb, 256, 0, st>>>(w.d2, L.h3, L.h3, B, grads + go.off[9]);
+    colsum_bf16_kernel<<<rb, 256, 0, st>>>(w.d1, L.h2, L.h2, B, grads + go.off[7]);
+    // ---- time branch (fp32, T rows): b0's gradient comes out of it as the column sums of G
+    transpose_small_kernel<<<(L.h1 * L.T + 255) / 256, 256, 0, st>>>(w.GT, L.h1, L.T, Tp, w.G);
+    time_branch_backward(L, pk, p, w.G, w.dtemb, w.dhmid, grads, st);
+    DDP_LAUNCH_CHECK("actor_train_tc kernels");
+    return DDP_OK;
+}
+
+}  // namespace ddp

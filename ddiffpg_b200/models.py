@@ -111,6 +111,7 @@ class DiffusionPolicy(nn.Module):
         self.num_mode = num_mode
         self.hidden = tuple(hidden)
         self.precision = precision
+        self.train_precision = "fp32"       # "bf16": tcgen05 GEMM path for get_loss / FusedActorTrainer
         self.net = DiffusionNet(transition_dim=state_dim + action_dim + num_mode, cond_dim=state_dim + num_mode,
                                 hidden=self.hidden)
         # noise-related attributes kept for interface parity (diffusion_mlp.py:176-182)
@@ -200,8 +201,8 @@ class DiffusionPolicy(nn.Module):
                                          ws_bytes, stream_ptr()), "ddp_actor_sample")
         return out
 
-    def _loss_and_grads(self, state, action, noise, timesteps, inv_count=None):
-        packed, shape, prec = self._packed("fp32")
+    def _loss_and_grads(self, state, action, noise, timesteps, inv_count=None, precision=None):
+        packed, shape, prec = self._packed(precision or self.train_precision)
         dev = packed.device
         B = action.shape[0]
         state = state.detach().to(device=dev, dtype=torch.float32).contiguous()

@@ -93,3 +93,48 @@ def test_sampler_bf16_large_batch_properties():
     assert torch.equal(part, out[sl])                                           # rows independent of tiling
     ref = port.actor_sample(p, state[sl], noise[:, sl], T)
     assert (part.cpu() - ref).abs().max().item() <= BF16_ATOL
+
+
+# ------------------------------------------------------------------------------------------ H3 tensor path
+@pytest.mark.parametrize("B,T", [(64, 5), (700, 5), (4096, 5), (1000, 20)])
+def test_train_bf16_grads_vs_oracle(B, T):
+    """tcgen05 GEMM path of the training step: loss and all 12 gradients against the fp32 oracle at the bf16
+    bound (relative L2 error of the flat gradient <= 2e-2, of every weight matrix <= 3e-2)."""
+    gen = torch.Generator().manual_seed(900 + B)
+    p = port.init_actor_params(84)
+    state = torch.randn(B, 34, generator=gen)
+    action = torch.rand(B, 8, generator=gen) * 2 - 1
+    noise = torch.randn(B, 8, generator=gen)
+    ts = torch.randint(0, T, (B,), generator=gen)
+    l_ref, g_ref = port.actor_loss_and_grads(p, state, action, noise, ts, T)
+    pol = make_policy(p, T)
+    pol.train_precision = "bf16"
+    loss = pol.get_loss(_dev(state), _dev(action), noise=_dev(noise), timesteps=_dev(ts))
+    loss.backward()
+    assert abs(loss.item() - l_ref.item()) <= 2e-3 * l_ref.item()
+    got = torch.cat([q.grad.reshape(-1) for _, q in pol.named_parameters()]).cpu()
+    ref = torch.cat([g_ref[k].reshape(-1) for k in port.ACTOR_KEYS])
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel <= 2e-2, f"flat gradient relative L2 error {rel:.3e}"
+    for k, q in pol.named_parameters():
+        r = g_ref[k]
+        e = ((q.grad.cpu() - r).norm() / r.norm().clamp_min(1e-12)).item()
+        assert e <= 3e-2, f"{k}: relative L2 error {e:.3e}"
+
+
+def test_fused_trainer_bf16_tracks_fp32():
+    """Three fused training steps on the tensor path stay close to the fp32 oracle trajectory."""
+    from ddiffpg_b200 import FusedActorTrainer
+    B, T = 2048, 5
+    gen = torch.Generator().manual_seed(77)
+    p = port.init_actor_params(85)
+    args = (torch.randn(B, 34, generator=gen), torch.rand(B, 8, generator=gen) * 2 - 1,
+            torch.randn(B, 8, generator=gen), torch.randint(0, T, (B,), generator=gen))
+    pol = make_policy(p, T)
+    tr = FusedActorTrainer(pol, precision="bf16")
+    st, cur = None, p
+    for _ in range(3):
+        loss, gnorm = tr.step(_dev(args[0]), _dev(args[1]), noise=_dev(args[2]), timesteps=_dev(args[3]))
+        l_ref, n_ref, cur, st = port.adamw_train_step(cur, *args, T, opt_state=st)
+        assert abs(loss.item() - l_ref.item()) <= 3e-3 * l_ref.item()
+        assert abs(gnorm.item() / n_ref.item() - 1) <= 2e-2
