@@ -200,13 +200,13 @@ def run_cuda(args):
 
         def step():
             work.copy_(act0)
-            q_action_ascent_segments(critics, obs, work, seg, iters=20, cache=cache)
+            q_action_ascent_segments(critics, obs, work, seg, iters=20, cache=cache, precision=args.precision)
         launches_per_step = 2 + 20 * 2 + 2
 
         def e2e_step():
             o = obs_h.to(dev, non_blocking=True)
             w = act_h.to(dev, non_blocking=True)
-            q_action_ascent_segments(critics, o, w, seg, iters=20, cache=cache)
+            q_action_ascent_segments(critics, o, w, seg, iters=20, cache=cache, precision=args.precision)
             out_h.copy_(w, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         h2d, d2h = (obs_h.numel() + act_h.numel()) * 4, out_h.numel() * 4

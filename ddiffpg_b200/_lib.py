@@ -40,8 +40,9 @@ PROTOTYPES = {
                                     c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "ddp_q_packed_bytes": (c_size_t, [POINTER(QShape), c_int]),
     "ddp_q_pack": (c_int, [POINTER(QShape), POINTER(c_void_p), c_void_p, c_int, c_void_p]),
+    "ddp_q_forward_workspace_bytes": (c_size_t, [POINTER(QShape), c_long, c_int]),
     "ddp_q_forward": (c_int, [POINTER(QShape), c_void_p, POINTER(c_int64), c_void_p, c_void_p, c_void_p, c_void_p,
-                              c_void_p, c_void_p, c_long, c_int, c_void_p]),
+                              c_void_p, c_void_p, c_long, c_int, c_void_p, c_size_t, c_void_p]),
     "ddp_q_ascent_workspace_bytes": (c_size_t, [POINTER(QShape), c_long, c_int]),
     "ddp_q_action_ascent": (c_int, [POINTER(QShape), c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p,
                                     c_void_p, c_int, c_float, c_float, c_float, c_float, c_float, c_float, c_void_p,

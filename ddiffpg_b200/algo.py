@@ -28,7 +28,8 @@ def _workspace(name, nbytes, dev):
 
 
 def q_action_ascent_segments(critics, obs, action, seg_off, iters=20, lr=0.03, eps=1e-5, max_norm=1.0,
-                             betas=(0.9, 0.999), lim=1 - 1e-5, mean_counts=None, cache=None, return_norms=False):
+                             betas=(0.9, 0.999), lim=1 - 1e-5, mean_counts=None, cache=None, return_norms=False,
+                             precision=None):
     """Run the reference's action-ascent loop for several mode segments in one launch sequence.
 
     ``obs`` [B, O] / ``action`` [B, A] hold the rows of all modes, sorted by mode; ``seg_off`` (len
@@ -41,7 +42,7 @@ def q_action_ascent_segments(critics, obs, action, seg_off, iters=20, lr=0.03, e
     if not action.is_cuda or action.dtype != torch.float32 or not action.is_contiguous():
         raise RuntimeError("action must be a contiguous fp32 CUDA tensor (it is updated in place)")
     cache = cache if cache is not None else critics[0]._cache if len(critics) == 1 else _PackCache()
-    packed, shape, prec = pack_critics(list(critics), cache)
+    packed, shape, prec = pack_critics(list(critics), cache, precision)
     dev = packed.device
     obs = obs.detach().to(device=dev, dtype=torch.float32).contiguous()
     B = action.shape[0]

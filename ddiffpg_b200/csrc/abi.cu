@@ -40,6 +40,14 @@ int q_ascent_fma(const QLayout& L, const float* pk, const int64_t* seg_off, cons
                  float* action, int iters, float lr, float b1, float b2, float eps, float max_norm, float lim,
                  float* mean_abs, float* gnorm_out, long B, void* ws, size_t ws_bytes, cudaStream_t st);
 
+int pack_q_tc(const QLayout& L, const float* const p[], void* packed, cudaStream_t st);
+size_t q_tc_workspace(const QLayout& L, long B, int iters);
+int q_forward_tc(const QLayout& L, const void* packed, const int64_t* seg_off, const float* obs, const float* act,
+                 float* qmin, float* p1, float* p2, float* dq_da, long B, void* ws, size_t ws_bytes, cudaStream_t st);
+int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, const int64_t* seg_cnt, const float* obs,
+                float* action, int iters, float lr, float b1, float b2, float eps, float max_norm, float lim,
+                float* mean_abs, float* gnorm_out, long B, void* ws, size_t ws_bytes, cudaStream_t st);
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace ddp
@@ -150,8 +158,11 @@ int ddp_q_pack(const ddp_q_shape* s, const float* const params[], void* packed, 
     if (!params || !packed) DDP_FAIL(DDP_ERR_ARG, "ddp_q_pack: NULL argument");
     for (int i = 0; i < 16 * s->n_modes; ++i)
         if (!params[i]) DDP_FAIL(DDP_ERR_ARG, "ddp_q_pack: params[%d] is NULL", i);
-    if (precision != DDP_FP32) DDP_FAIL(DDP_ERR_UNSUPPORTED, "critic: only DDP_FP32 is implemented");
-    return pack_q_fp32(make_q_layout(*s, precision), params, (float*)packed, (cudaStream_t)stream);
+    if (precision != DDP_FP32 && precision != DDP_BF16) DDP_FAIL(DDP_ERR_ARG, "unknown precision %d", precision);
+    QLayout L = make_q_layout(*s, precision);
+    rc = pack_q_fp32(L, params, (float*)packed, (cudaStream_t)stream);
+    if (rc != DDP_OK || precision == DDP_FP32) return rc;
+    return pack_q_tc(L, params, packed, (cudaStream_t)stream);
 }
 
 static int check_segments(const ddp_q_shape* s, const int64_t* seg_off, long B) {
@@ -162,24 +173,34 @@ static int check_segments(const ddp_q_shape* s, const int64_t* seg_off, long B) 
     return DDP_OK;
 }
 
+size_t ddp_q_forward_workspace_bytes(const ddp_q_shape* s, long B, int precision) {
+    if (check_q_shape(s) != DDP_OK || B <= 0 || precision != DDP_BF16) return 0;
+    return q_tc_workspace(make_q_layout(*s, precision), B, 0);
+}
+
 int ddp_q_forward(const ddp_q_shape* s, const void* packed, const int64_t* seg_off, const float* obs,
                   const float* act, float* q_min_out, float* p1_out, float* p2_out, float* dq_da_out, long B,
-                  int precision, void* stream) {
+                  int precision, void* ws, size_t ws_bytes, void* stream) {
     int rc = check_q_shape(s);
     if (rc != DDP_OK) return rc;
     if (B < 0) DDP_FAIL(DDP_ERR_SHAPE, "ddp_q_forward: negative batch");
     if (B == 0) return DDP_OK;
     if (!packed || !obs || !act) DDP_FAIL(DDP_ERR_ARG, "ddp_q_forward: NULL argument");
-    if (precision != DDP_FP32) DDP_FAIL(DDP_ERR_UNSUPPORTED, "critic: only DDP_FP32 is implemented");
+    if (precision != DDP_FP32 && precision != DDP_BF16) DDP_FAIL(DDP_ERR_ARG, "unknown precision %d", precision);
     rc = check_segments(s, seg_off, B);
     if (rc != DDP_OK) return rc;
+    if (precision == DDP_BF16)
+        return q_forward_tc(make_q_layout(*s, precision), packed, seg_off, obs, act, q_min_out, p1_out, p2_out,
+                            dq_da_out, B, ws, ws_bytes, (cudaStream_t)stream);
     return q_forward_fma(make_q_layout(*s, precision), (const float*)packed, seg_off, obs, act, q_min_out, p1_out,
                          p2_out, dq_da_out, B, (cudaStream_t)stream);
 }
 
 size_t ddp_q_ascent_workspace_bytes(const ddp_q_shape* s, long B, int iters) {
     if (check_q_shape(s) != DDP_OK || B <= 0 || iters <= 0) return 0;
-    return q_ascent_workspace(make_q_layout(*s, DDP_FP32), B, iters);
+    const size_t a = q_ascent_workspace(make_q_layout(*s, DDP_FP32), B, iters);
+    const size_t b = q_tc_workspace(make_q_layout(*s, DDP_BF16), B, iters);
+    return a > b ? a : b;
 }
 
 int ddp_q_action_ascent(const ddp_q_shape* s, const void* packed, const int64_t* seg_off,
@@ -191,10 +212,13 @@ int ddp_q_action_ascent(const ddp_q_shape* s, const void* packed, const int64_t*
     if (B <= 0 || iters <= 0) DDP_FAIL(DDP_ERR_SHAPE, "ddp_q_action_ascent: B and iters must be positive");
     if (!packed || !obs || !action_inout || !mean_abs_out || !ws || !seg_mean_count)
         DDP_FAIL(DDP_ERR_ARG, "ddp_q_action_ascent: NULL argument");
-    if (precision != DDP_FP32) DDP_FAIL(DDP_ERR_UNSUPPORTED, "critic: only DDP_FP32 is implemented");
+    if (precision != DDP_FP32 && precision != DDP_BF16) DDP_FAIL(DDP_ERR_ARG, "unknown precision %d", precision);
     rc = check_segments(s, seg_off, B);
     if (rc != DDP_OK) return rc;
     QLayout L = make_q_layout(*s, precision);
+    if (precision == DDP_BF16)
+        return q_ascent_tc(L, packed, seg_off, seg_mean_count, obs, action_inout, iters, lr, beta1, beta2, eps, max_norm,
+                           lim, mean_abs_out, gnorm_out, B, ws, ws_bytes, (cudaStream_t)stream);
     if (ws_bytes < q_ascent_workspace(L, B, iters)) DDP_FAIL(DDP_ERR_ARG, "ddp_q_action_ascent: workspace too small");
     return q_ascent_fma(L, (const float*)packed, seg_off, seg_mean_count, obs, action_inout, iters, lr, beta1, beta2,
                         eps, max_norm, lim, mean_abs_out, gnorm_out, B, ws, ws_bytes, (cudaStream_t)stream);

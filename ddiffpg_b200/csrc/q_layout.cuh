@@ -21,10 +21,14 @@ struct QLayout {
     QNetLayout net[2];           // offsets in floats inside one mode's block
     size_t z;                    // [atomsP] support atoms (shared by both nets)
     size_t mode_stride;          // floats per mode
+    // bf16 tensor-core section (precision == DDP_BF16): byte offsets; each array holds n_modes matrices back to
+    // back so that the grouped row GEMM can stride over the modes.  Index [net][layer].
+    size_t tc_fwd[2][4], tc_bwd[2][4];
+    size_t tc_fwd_elems[4], tc_bwd_elems[4];   // elements per mode of each matrix
     size_t total_bytes;
 };
 
-inline QLayout make_q_layout(const ddp_q_shape& s, int /*precision*/) {
+inline QLayout make_q_layout(const ddp_q_shape& s, int precision) {
     QLayout L{};
     L.O = s.O; L.A = s.A; L.atoms = s.atoms; L.n_modes = s.n_modes; L.h1 = s.hid1; L.h2 = s.hid2; L.h3 = s.hid3;
     L.v_min = s.v_min; L.v_max = s.v_max;
@@ -41,7 +45,19 @@ inline QLayout make_q_layout(const ddp_q_shape& s, int /*precision*/) {
     }
     L.z = take(L.atomsP);
     L.mode_stride = o;
-    L.total_bytes = o * sizeof(float) * (size_t)s.n_modes;
+    size_t bytes = align_up(o * sizeof(float) * (size_t)s.n_modes, 1024);
+    if (precision == DDP_BF16) {
+        // forward: W1 [h1][64] (K = [obs|act|0]), W2 [h2][h1], W3 [h3][h2], W4 [64][h3] (rows >= atoms zero)
+        // backward (dX = dY.W): W4^T [h3][64], W3^T [h2][h3], W2^T [h1][h2], W1[:, O:O+A]^T [16][h1]
+        const size_t fe[4] = {(size_t)L.h1 * 64, (size_t)L.h2 * L.h1, (size_t)L.h3 * L.h2, (size_t)64 * L.h3};
+        const size_t be[4] = {(size_t)L.h3 * 64, (size_t)L.h2 * L.h3, (size_t)L.h1 * L.h2, (size_t)16 * L.h1};
+        for (int i = 0; i < 4; ++i) { L.tc_fwd_elems[i] = fe[i]; L.tc_bwd_elems[i] = be[i]; }
+        for (int j = 0; j < 2; ++j) {
+            for (int i = 0; i < 4; ++i) { L.tc_fwd[j][i] = bytes; bytes += align_up(fe[i] * 2 * s.n_modes, 1024); }
+            for (int i = 0; i < 4; ++i) { L.tc_bwd[j][i] = bytes; bytes += align_up(be[i] * 2 * s.n_modes, 1024); }
+        }
+    }
+    L.total_bytes = bytes;
     return L;
 }
 

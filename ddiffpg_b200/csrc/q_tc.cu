@@ -1,0 +1,323 @@
+// H2, bf16 tensor-core path: mode-segmented double-Q forward, its gradient w.r.t. the action and the Adam
+// action-ascent loop, assembled from the grouped tcgen05 row GEMM (csrc/tc_gemm.cu; one group per mode, so all
+// K+1 critics run in the same launches).
+//
+// Reference semantics (paths relative to the reference repo):
+//   MLPNet (ELU) / DistributionalDoubleQ.get_q1_q2 / get_q_min     ddiffpg/models/mlp.py:13-35,143-151
+//   AgentDDiffPG.update_target_action + optimizer_update           ddiffpg/algo/ddiffpg.py:358-373, ac_base.py:83-92
+// Operands bf16, accumulation fp32; softmax / expectation / arg-min selection, the clip norm and Adam are fp32.
+// Per ascent iteration: 2 nets x 4 forward GEMMs, one softmax/selection kernel, 2 nets x 4 backward GEMMs (ELU
+// derivative fused in the epilogue, from the stored activation), one gradient/norm kernel, one Adam kernel.
+#include <math.h>
+#include "q_layout.cuh"
+#include "tc_gemm.cuh"
+
+namespace ddp {
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+struct QSeg {
+    long off[kMaxModes + 1];
+    float inv_cnt[kMaxModes];
+    int n_modes;
+};
+
+struct QTcWs {
+    bf16 *xin, *a1[2], *a2[2], *a3[2], *dl[2];
+    float *logits[2], *ga[2], *g, *m1, *m2, *gsq, *abs_sum;
+    size_t total, adam_bytes;
+};
+
+QTcWs carve(const QLayout& L, long B, int iters, uint8_t* base) {
+    QTcWs w{};
+    size_t o = 0;
+    auto take = [&](size_t bytes) { uint8_t* r = base ? base + o : nullptr; o += (bytes + 255) / 256 * 256; return r; };
+    w.xin = (bf16*)take((size_t)B * 64 * 2);
+    for (int j = 0; j < 2; ++j) {
+        w.a1[j] = (bf16*)take((size_t)B * L.h1 * 2);
+        w.a2[j] = (bf16*)take((size_t)B * L.h2 * 2);
+        w.a3[j] = (bf16*)take((size_t)B * L.h3 * 2);
+        w.dl[j] = (bf16*)take((size_t)B * 64 * 2);
+        w.logits[j] = (float*)take((size_t)B * 64 * 4);
+        w.ga[j] = (float*)take((size_t)B * 16 * 4);
+    }
+    w.g = (float*)take((size_t)B * L.A * 4);
+    const size_t adam0 = o;
+    w.m1 = (float*)take((size_t)B * L.A * 4);
+    w.m2 = (float*)take((size_t)B * L.A * 4);
+    w.gsq = (float*)take((size_t)(iters > 0 ? iters : 1) * kMaxModes * 4);
+    w.abs_sum = (float*)take(kMaxModes * 4);
+    w.adam_bytes = o - adam0;
+    w.total = o;
+    return w;
+}
+
+// xin[r] = [obs (O) | action (A) | 0 ...] as bf16, 64 columns; `clamp_lim` > 0 also clamps the fp32 action in
+// place first (the pre-loop clamp of update_target_action, ddiffpg.py:361)
+__global__ void q_tc_prep_kernel(const float* __restrict__ obs, float* __restrict__ act, int O, int A, long B,
+                                 float clamp_lim, bf16* __restrict__ xin) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long row = idx >> 6;
+    const int c = (int)(idx & 63);
+    if (row >= B) return;
+    float v = 0.f;
+    if (c < O) v = obs[row * O + c];
+    else if (c < O + A) {
+        v = act[row * A + c - O];
+        if (clamp_lim > 0.f) { v = fminf(fmaxf(v, -clamp_lim), clamp_lim); act[row * A + c - O] = v; }
+    }
+    xin[row * 64 + c] = __float2bfloat16(v);
+}
+
+// One warp per row: softmax over atoms of both nets, expectations, min / selection, d min(Q1,Q2) / d logits.
+__global__ void q_tc_softmax_kernel(const float* __restrict__ lg1, const float* __restrict__ lg2,
+                                    const float* __restrict__ z, int atoms, long B, float* __restrict__ qmin_out,
+                                    float* __restrict__ p1_out, float* __restrict__ p2_out, bf16* __restrict__ dl1,
+                                    bf16* __restrict__ dl2) {
+    const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= B) return;
+    const int c0 = lane, c1 = lane + 32;
+    const float z0 = c0 < atoms ? z[c0] : 0.f, z1 = c1 < atoms ? z[c1] : 0.f;
+    float p[2][2], q[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float* lg = (j == 0 ? lg1 : lg2) + row * 64;
+        const float l0 = c0 < atoms ? lg[c0] : -INFINITY, l1 = c1 < atoms ? lg[c1] : -INFINITY;
+        const float mx = warp_max(fmaxf(l0, l1));
+        const float e0 = c0 < atoms ? expf(l0 - mx) : 0.f, e1 = c1 < atoms ? expf(l1 - mx) : 0.f;
+        const float sum = warp_sum(e0 + e1);
+        p[j][0] = e0 / sum; p[j][1] = e1 / sum;
+        q[j] = warp_sum(p[j][0] * z0 + p[j][1] * z1);
+    }
+    if (lane == 0 && qmin_out) qmin_out[row] = fminf(q[0], q[1]);
+    if (p1_out) { if (c0 < atoms) p1_out[row * atoms + c0] = p[0][0]; if (c1 < atoms) p1_out[row * atoms + c1] = p[0][1]; }
+    if (p2_out) { if (c0 < atoms) p2_out[row * atoms + c0] = p[1][0]; if (c1 < atoms) p2_out[row * atoms + c1] = p[1][1]; }
+    if (dl1) {
+        // only the smaller net carries gradient; exact ties split evenly (torch.min backward)
+        const float w1 = q[0] == q[1] ? 0.5f : (q[0] < q[1] ? 1.f : 0.f), w2 = 1.f - w1;
+        dl1[row * 64 + c0] = __float2bfloat16(w1 * p[0][0] * (z0 - q[0]));
+        dl1[row * 64 + c1] = __float2bfloat16(w1 * p[0][1] * (z1 - q[0]));
+        dl2[row * 64 + c0] = __float2bfloat16(w2 * p[1][0] * (z0 - q[1]));
+        dl2[row * 64 + c1] = __float2bfloat16(w2 * p[1][1] * (z1 - q[1]));
+    }
+}
+
+// g = scale * (ga1 + ga2) per action element (+ per-mode sum of squares for the clip norm)
+__global__ void q_tc_grad_kernel(QSeg seg, const float* __restrict__ ga1, const float* __restrict__ ga2, int A,
+                                 long n_elems, int ascent, float* __restrict__ g, float* __restrict__ gsq) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float bins[kMaxModes];
+    if (threadIdx.x < kMaxModes) bins[threadIdx.x] = 0.f;
+    __syncthreads();
+    if (i < n_elems) {
+        const long row = i / A;
+        const int c = (int)(i % A);
+        int mode = 0;
+        while (mode + 1 < seg.n_modes && row >= seg.off[mode + 1]) ++mode;
+        const float scale = ascent ? -seg.inv_cnt[mode] : 1.f;
+        const float v = scale * (ga1[row * 16 + c] + ga2[row * 16 + c]);
+        g[i] = v;
+        if (ascent) atomicAdd(&bins[mode], v * v);
+    }
+    __syncthreads();
+    if (ascent && threadIdx.x < seg.n_modes && bins[threadIdx.x] != 0.f) atomicAdd(gsq + threadIdx.x, bins[threadIdx.x]);
+}
+
+// clip_grad_norm_ + torch.optim.Adam.step + clamp_ (ac_base.py:86-91, ddiffpg.py:369); also refreshes the bf16
+// action columns of the GEMM input
+__global__ void q_tc_adam_kernel(QSeg seg, int O, int A, float* __restrict__ act, const float* __restrict__ g,
+                                 float* __restrict__ m1, float* __restrict__ m2, const float* __restrict__ gsq,
+                                 float* __restrict__ gnorm_out, int iter, int iters, float step_size, float bc2_sqrt,
+                                 float b1, float b2, float eps, float max_norm, float lim, long n_elems,
+                                 bf16* __restrict__ xin) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_elems) return;
+    const long row = i / A;
+    const int c = (int)(i % A);
+    int mode = 0;
+    while (mode + 1 < seg.n_modes && row >= seg.off[mode + 1]) ++mode;
+    const float norm = sqrtf(gsq[mode]);
+    const float coef = fminf(max_norm / (norm + 1e-6f), 1.0f);
+    if (gnorm_out && i == seg.off[mode] * A) gnorm_out[mode * iters + iter] = norm;
+    const float gi = g[i] * coef;
+    const float ea = m1[i] * b1 + (1.f - b1) * gi;
+    const float ev = m2[i] * b2 + (1.f - b2) * gi * gi;
+    m1[i] = ea; m2[i] = ev;
+    float v = act[i] - step_size * (ea / (sqrtf(ev) / bc2_sqrt + eps));
+    v = fminf(fmaxf(v, -lim), lim);
+    act[i] = v;
+    xin[row * 64 + O + c] = __float2bfloat16(v);
+}
+
+__global__ void q_tc_abs_kernel(QSeg seg, int A, const float* __restrict__ act, long n_elems, float* __restrict__ abs_sum) {
+    __shared__ float bins[kMaxModes];
+    if (threadIdx.x < kMaxModes) bins[threadIdx.x] = 0.f;
+    __syncthreads();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += (long)gridDim.x * blockDim.x) {
+        const long row = i / A;
+        int mode = 0;
+        while (mode + 1 < seg.n_modes && row >= seg.off[mode + 1]) ++mode;
+        atomicAdd(&bins[mode], fabsf(act[i]));
+    }
+    __syncthreads();
+    if (threadIdx.x < seg.n_modes && bins[threadIdx.x] != 0.f) atomicAdd(abs_sum + threadIdx.x, bins[threadIdx.x]);
+}
+
+__global__ void q_tc_finish_kernel(QSeg seg, int A, const float* __restrict__ abs_sum, float* __restrict__ mean_abs) {
+    const int m = threadIdx.x;
+    if (m < seg.n_modes) {
+        const long n = (seg.off[m + 1] - seg.off[m]) * A;
+        mean_abs[m] = n > 0 ? abs_sum[m] / (float)n : 0.f;
+    }
+}
+
+// bf16 operands, all modes back to back per (net, layer)
+__global__ void q_tc_pack_kernel(const float* __restrict__ W1, const float* __restrict__ W2, const float* __restrict__ W3,
+                                 const float* __restrict__ W4, int O, int A, int atoms, int h1, int h2, int h3,
+                                 bf16* f1, bf16* f2, bf16* f3, bf16* f4, bf16* b4, bf16* b3, bf16* b2, bf16* b1) {
+    const int in1 = O + A;
+    const size_t n1 = (size_t)h1 * 64, n2 = (size_t)h2 * h1, n3 = (size_t)h3 * h2, n4 = (size_t)64 * h3,
+                 m4 = (size_t)h3 * 64, m3 = (size_t)h2 * h3, m2 = (size_t)h1 * h2, m1 = (size_t)16 * h1;
+    const size_t total = n1 + n2 + n3 + n4 + m4 + m3 + m2 + m1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t j = i;
+        if (j < n1) { const int r = (int)(j / 64), c = (int)(j % 64); f1[j] = __float2bfloat16(c < in1 ? W1[(size_t)r * in1 + c] : 0.f); continue; }
+        j -= n1;
+        if (j < n2) { f2[j] = __float2bfloat16(W2[j]); continue; }
+        j -= n2;
+        if (j < n3) { f3[j] = __float2bfloat16(W3[j]); continue; }
+        j -= n3;
+        if (j < n4) { const int r = (int)(j / h3); f4[j] = __float2bfloat16(r < atoms ? W4[j] : 0.f); continue; }
+        j -= n4;
+        if (j < m4) { const int r = (int)(j / 64), c = (int)(j % 64); b4[j] = __float2bfloat16(c < atoms ? W4[(size_t)c * h3 + r] : 0.f); continue; }
+        j -= m4;
+        if (j < m3) { const int r = (int)(j / h3), c = (int)(j % h3); b3[j] = __float2bfloat16(W3[(size_t)c * h2 + r]); continue; }
+        j -= m3;
+        if (j < m2) { const int r = (int)(j / h2), c = (int)(j % h2); b2[j] = __float2bfloat16(W2[(size_t)c * h1 + r]); continue; }
+        j -= m2;
+        { const int r = (int)(j / h1), c = (int)(j % h1); b1[j] = __float2bfloat16(r < A ? W1[(size_t)c * in1 + O + r] : 0.f); }
+    }
+}
+
+bool shape_ok(const QLayout& L) {
+    return L.O + L.A <= 64 && L.A <= 16 && L.atoms <= 64 && L.h1 % 64 == 0 && L.h2 % 64 == 0 && L.h3 % 64 == 0;
+}
+
+QSeg make_seg(const QLayout& L, const int64_t* seg_off, const int64_t* seg_cnt) {
+    QSeg s{};
+    s.n_modes = L.n_modes;
+    for (int m = 0; m <= L.n_modes; ++m) s.off[m] = seg_off[m];
+    for (int m = 0; m < L.n_modes; ++m) {
+        const long cnt = seg_cnt ? seg_cnt[m] : seg_off[m + 1] - seg_off[m];
+        s.inv_cnt[m] = cnt > 0 ? 1.0f / (float)cnt : 0.f;
+    }
+    return s;
+}
+
+// forward of both nets (+ optional backward to the action) for all rows; results in w.logits / w.ga
+int q_tc_pass(const QLayout& L, const uint8_t* pb, const QTcWs& w, const QSeg& seg, long B, bool backward,
+              float* qmin, float* p1, float* p2, cudaStream_t st) {
+    using namespace tcg;
+    const float* pk = (const float*)pb;
+    auto gemm = [&](const bf16* A, int lda, size_t w_off, size_t w_elems, int ldw, int N, int K, int epi,
+                    const float* bias, const bf16* aux, bf16* out_a, float* out_f, int outf_ld, int n_valid) {
+        RowGemm g{};
+        g.A = A; g.lda = lda; g.W = (const bf16*)(pb + w_off); g.ldw = ldw; g.w_stride = w_elems;
+        g.M = B; g.N = N; g.K = K; g.epi = epi; g.bias = bias; g.bias_stride = L.mode_stride;
+        g.aux = aux; g.aux_ld = N; g.out_a = out_a; g.out_ld = N; g.out_f = out_f; g.outf_ld = outf_ld; g.n_valid = n_valid;
+        g.groups.n_groups = seg.n_modes;
+        for (int m = 0; m <= seg.n_modes; ++m) g.groups.off[m] = seg.off[m];
+        return launch_row_gemm(g, st);
+    };
+    int rc;
+    for (int j = 0; j < 2; ++j) {
+        const QNetLayout& n = L.net[j];
+        if ((rc = gemm(w.xin, 64, L.tc_fwd[j][0], L.tc_fwd_elems[0], 64, L.h1, 64, EPI_ELU_FWD, pk + n.b1, nullptr, w.a1[j], nullptr, 0, 0)) != DDP_OK) return rc;
+        if ((rc = gemm(w.a1[j], L.h1, L.tc_fwd[j][1], L.tc_fwd_elems[1], L.h1, L.h2, L.h1, EPI_ELU_FWD, pk + n.b2, nullptr, w.a2[j], nullptr, 0, 0)) != DDP_OK) return rc;
+        if ((rc = gemm(w.a2[j], L.h2, L.tc_fwd[j][2], L.tc_fwd_elems[2], L.h2, L.h3, L.h2, EPI_ELU_FWD, pk + n.b3, nullptr, w.a3[j], nullptr, 0, 0)) != DDP_OK) return rc;
+        if ((rc = gemm(w.a3[j], L.h3, L.tc_fwd[j][3], L.tc_fwd_elems[3], L.h3, 64, L.h3, EPI_LINEAR_F32, pk + n.b4, nullptr, nullptr, w.logits[j], 64, L.atoms)) != DDP_OK) return rc;
+    }
+    const unsigned wb = (unsigned)((B * 32 + 255) / 256);
+    q_tc_softmax_kernel<<<wb, 256, 0, st>>>(w.logits[0], w.logits[1], pk + L.z, L.atoms, B, qmin, p1, p2,
+                                            backward ? w.dl[0] : nullptr, backward ? w.dl[1] : nullptr);
+    if (!backward) return DDP_OK;
+    for (int j = 0; j < 2; ++j) {
+        // dZ overwrites the stored activation in place (same thread reads the activation, writes the gradient)
+        if ((rc = gemm(w.dl[j], 64, L.tc_bwd[j][0], L.tc_bwd_elems[0], 64, L.h3, 64, EPI_MUL_ELU_D, nullptr, w.a3[j], w.a3[j], nullptr, 0, 0)) != DDP_OK) return rc;
+        if ((rc = gemm(w.a3[j], L.h3, L.tc_bwd[j][1], L.tc_bwd_elems[1], L.h3, L.h2, L.h3, EPI_MUL_ELU_D, nullptr, w.a2[j], w.a2[j], nullptr, 0, 0)) != DDP_OK) return rc;
+        if ((rc = gemm(w.a2[j], L.h2, L.tc_bwd[j][2], L.tc_bwd_elems[2], L.h2, L.h1, L.h2, EPI_MUL_ELU_D, nullptr, w.a1[j], w.a1[j], nullptr, 0, 0)) != DDP_OK) return rc;
+        if ((rc = gemm(w.a1[j], L.h1, L.tc_bwd[j][3], L.tc_bwd_elems[3], L.h1, 16, L.h1, EPI_LINEAR_F32, nullptr, nullptr, nullptr, w.ga[j], 16, L.A)) != DDP_OK) return rc;
+    }
+    return DDP_OK;
+}
+
+}  // namespace
+
+int pack_q_tc(const QLayout& L, const float* const p[], void* packed, cudaStream_t st) {
+    if (!shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 critic path needs O+A<=64, A<=16, atoms<=64, widths multiple of 64");
+    uint8_t* b = (uint8_t*)packed;
+    for (int m = 0; m < L.n_modes; ++m)
+        for (int j = 0; j < 2; ++j) {
+            const float* const* q = p + 16 * m + 8 * j;
+            bf16* f[4]; bf16* r[4];
+            for (int i = 0; i < 4; ++i) {
+                f[i] = (bf16*)(b + L.tc_fwd[j][i]) + (size_t)m * L.tc_fwd_elems[i];
+                r[i] = (bf16*)(b + L.tc_bwd[j][i]) + (size_t)m * L.tc_bwd_elems[i];
+            }
+            q_tc_pack_kernel<<<296, 256, 0, st>>>(q[0], q[2], q[4], q[6], L.O, L.A, L.atoms, L.h1, L.h2, L.h3, f[0], f[1],
+                                                  f[2], f[3], r[0], r[1], r[2], r[3]);
+        }
+    DDP_LAUNCH_CHECK("q_tc_pack_kernel");
+    return DDP_OK;
+}
+
+size_t q_tc_workspace(const QLayout& L, long B, int iters) { return carve(L, B, iters, nullptr).total; }
+
+int q_forward_tc(const QLayout& L, const void* packed, const int64_t* seg_off, const float* obs, const float* act,
+                 float* qmin, float* p1, float* p2, float* dq_da, long B, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 critic path does not support this shape");
+    if (!ws || ws_bytes < carve(L, B, 0, nullptr).total) DDP_FAIL(DDP_ERR_ARG, "critic tensor path: workspace too small");
+    QTcWs w = carve(L, B, 0, (uint8_t*)ws);
+    QSeg seg = make_seg(L, seg_off, nullptr);
+    const unsigned eb = (unsigned)((B * 64 + 255) / 256);
+    q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, const_cast<float*>(act), L.O, L.A, B, 0.f, w.xin);
+    int rc = q_tc_pass(L, (const uint8_t*)packed, w, seg, B, dq_da != nullptr, qmin, p1, p2, st);
+    if (rc != DDP_OK) return rc;
+    if (dq_da) {
+        const long n = B * L.A;
+        q_tc_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(seg, w.ga[0], w.ga[1], L.A, n, 0, dq_da, nullptr);
+    }
+    DDP_LAUNCH_CHECK("q_forward_tc kernels");
+    return DDP_OK;
+}
+
+int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, const int64_t* seg_cnt, const float* obs,
+                float* action, int iters, float lr, float b1, float b2, float eps, float max_norm, float lim,
+                float* mean_abs, float* gnorm_out, long B, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 critic path does not support this shape");
+    if (ws_bytes < carve(L, B, iters, nullptr).total) DDP_FAIL(DDP_ERR_ARG, "critic tensor path: workspace too small");
+    QTcWs w = carve(L, B, iters, (uint8_t*)ws);
+    QSeg seg = make_seg(L, seg_off, seg_cnt);
+    const long n = B * L.A;
+    const unsigned eb = (unsigned)((B * 64 + 255) / 256), nb = (unsigned)((n + 255) / 256);
+    DDP_CUDA_CHECK(cudaMemsetAsync(w.m1, 0, w.adam_bytes, st));          // fresh Adam state, zeroed reductions
+    q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, action, L.O, L.A, B, lim, w.xin);
+    for (int it = 0; it < iters; ++it) {
+        int rc = q_tc_pass(L, (const uint8_t*)packed, w, seg, B, true, nullptr, nullptr, nullptr, st);
+        if (rc != DDP_OK) return rc;
+        float* gsq = w.gsq + (size_t)it * kMaxModes;
+        q_tc_grad_kernel<<<nb, 256, 0, st>>>(seg, w.ga[0], w.ga[1], L.A, n, 1, w.g, gsq);
+        const int step = it + 1;
+        const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+        q_tc_adam_kernel<<<nb, 256, 0, st>>>(seg, L.O, L.A, action, w.g, w.m1, w.m2, gsq, gnorm_out, it, iters,
+                                             (float)(lr / bc1), (float)sqrt(bc2), b1, b2, eps, max_norm, lim, n, w.xin);
+    }
+    q_tc_abs_kernel<<<nb < 592 ? nb : 592, 256, 0, st>>>(seg, L.A, action, n, w.abs_sum);
+    q_tc_finish_kernel<<<1, kMaxModes, 0, st>>>(seg, L.A, w.abs_sum, mean_abs);
+    DDP_LAUNCH_CHECK("q_ascent_tc kernels");
+    return DDP_OK;
+}
+
+}  // namespace ddp

@@ -264,9 +264,10 @@ class MLPNet(nn.Module):
         return self.net(x)
 
 
-def pack_critics(critics, cache, precision="fp32"):
+def pack_critics(critics, cache, precision=None):
     """Pack one or more DistributionalDoubleQ modules (one per behaviour mode) into one buffer."""
     first = critics[0]
+    precision = precision or getattr(first, "precision", "fp32")
     params = [p for c in critics for _, p in c.named_parameters()]
     dev = params[0].device
     if dev.type != "cuda":
@@ -310,8 +311,10 @@ class _QMinFn(torch.autograd.Function):
 class DistributionalDoubleQ(nn.Module):
     """Drop-in for ``ddiffpg.models.mlp.DistributionalDoubleQ`` (:131-155)."""
 
-    def __init__(self, state_dim, act_dim, v_min=-10, v_max=10, num_atoms=51, device="cuda", hidden_layers=None):
+    def __init__(self, state_dim, act_dim, v_min=-10, v_max=10, num_atoms=51, device="cuda", hidden_layers=None,
+                 precision="fp32"):
         super().__init__()
+        self.precision = precision      # "fp32" FMA path | "bf16" tcgen05 GEMM path (large batches)
         if isinstance(state_dim, Sequence):
             state_dim = state_dim[0]
         self.device = device
@@ -342,8 +345,11 @@ class DistributionalDoubleQ(nn.Module):
         dq = torch.empty(B, self.act_dim, device=dev) if want_grad else None
         if B:
             with torch.cuda.device(dev):
+                ws_bytes = lib().ddp_q_forward_workspace_bytes(shape, B, prec)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
                 check(lib().ddp_q_forward(shape, ptr(packed), _lib.i64_array([0, B]), ptr(obs), ptr(action), ptr(q),
-                                          ptr(p1), ptr(p2), ptr(dq), B, prec, stream_ptr()), "ddp_q_forward")
+                                          ptr(p1), ptr(p2), ptr(dq), B, prec, ptr(ws), ws_bytes, stream_ptr()),
+                      "ddp_q_forward")
         return q, p1, p2, dq
 
     def _params_need_grad(self):

@@ -106,10 +106,12 @@ int ddp_q_pack(const ddp_q_shape* shape, const float* const params[], void* pack
 /* Replaces DistributionalDoubleQ.get_q1_q2 / get_q_min (ddiffpg/models/mlp.py:143-151).
  * Rows are sorted by mode; seg_off[n_modes+1] (HOST) gives the row range of each mode's critic.
  * q_min_out [B]; p1_out/p2_out [B,atoms] may be NULL; dq_da_out [B,A] (d q_min / d action, the
- * autograd result of get_q_min w.r.t. action) may be NULL. */
+ * autograd result of get_q_min w.r.t. action) may be NULL.  ws: ddp_q_forward_workspace_bytes (0 for
+ * DDP_FP32, then ws may be NULL). */
+size_t ddp_q_forward_workspace_bytes(const ddp_q_shape* shape, long B, int precision);
 int ddp_q_forward(const ddp_q_shape* shape, const void* packed, const int64_t* seg_off,
                   const float* obs, const float* act, float* q_min_out, float* p1_out, float* p2_out,
-                  float* dq_da_out, long B, int precision, void* stream);
+                  float* dq_da_out, long B, int precision, void* ws, size_t ws_bytes, void* stream);
 
 /* Replaces AgentDDiffPG.update_target_action (ddiffpg/algo/ddiffpg.py:358-373, identical copy
  * ddiffpg/algo/dipo.py:246-261) including its optimizer_update tail (ac_base.py:83-92): pre-clamp,
@@ -119,7 +121,7 @@ int ddp_q_forward(const ddp_q_shape* shape, const void* packed, const int64_t* s
  * mode batch when sharded) and its own clip norm.  action_inout [B,A] is updated in place;
  * mean_abs_out [n_modes] receives mean|a| per segment; gnorm_out [n_modes*iters] the pre-clip norms
  * (may be NULL).  ws: ddp_q_ascent_workspace_bytes. */
-size_t ddp_q_ascent_workspace_bytes(const ddp_q_shape* shape, long B, int iters);
+size_t ddp_q_ascent_workspace_bytes(const ddp_q_shape* shape, long B, int iters);   /* covers both precisions */
 int ddp_q_action_ascent(const ddp_q_shape* shape, const void* packed, const int64_t* seg_off,
                         const int64_t* seg_mean_count, const float* obs, float* action_inout,
                         int iters, float lr, float beta1, float beta2, float eps, float max_norm,

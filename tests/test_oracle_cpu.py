@@ -164,7 +164,7 @@ def test_abi_argument_errors_without_gpu(built_lib):
     assert L.ddp_q_packed_bytes(q, 0) > 3 * 4 * 380518
     qbad = _lib.QShape(29, 8, 51, 5.0, 0.0, 1, 512, 256, 128)
     assert L.ddp_q_packed_bytes(qbad, 0) == 0
-    assert L.ddp_q_forward(q, None, None, None, None, None, None, None, None, 0, 0, None) == 0
+    assert L.ddp_q_forward(q, None, None, None, None, None, None, None, None, 0, 0, None, 0, None) == 0
 
 
 # ------------------------------------------------------------------ host mirror of the reference surface
