@@ -303,20 +303,30 @@ static void launch_dw(const float* dz, int ldz, int N, const float* x, int ldx, 
     dw_gemm_kernel<<<grid, 256, 0, st>>>(dz, ldz, N, x, ldx, K, C, ldc, dbias, R, rps);
 }
 
-// y[t][i] = sum_n g[t*ldg + n] * W[n*ldw + i]  (i < M, n < N); optional multiply by mish'(zmul[t][i])
+// y[t][i] = sum_n g[t*ldg + n] * W[n*ldw + i]  (i < M, n < N); optional multiply by mish'(zmul[t][i]).
+// Block = 32 output columns x 8 warps that split n; W is read coalesced along i.
 __global__ void rows_linear_t_kernel(const float* __restrict__ g, int ldg, int N, const float* __restrict__ W,
                                      int ldw, int M, const float* __restrict__ zmul, float* __restrict__ y) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
-    if (i >= M) return;
+    __shared__ float part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane, t = blockIdx.y;
     const float* gr = g + (size_t)t * ldg;
     float acc = 0.f;
-    for (int n = 0; n < N; ++n) acc = fmaf(gr[n], W[(size_t)n * ldw + i], acc);
-    if (zmul) {
-        float yv, dv;
-        mish_fd(zmul[(size_t)t * M + i], yv, dv);
-        acc *= dv;
+    if (i < M)
+        for (int n = warp; n < N; n += 8) acc = fmaf(gr[n], W[(size_t)n * ldw + i], acc);
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && i < M) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += part[w][lane];
+        if (zmul) {
+            float yv, dv;
+            mish_fd(zmul[(size_t)t * M + i], yv, dv);
+            s *= dv;
+        }
+        y[(size_t)t * M + i] = s;
     }
-    y[(size_t)t * M + i] = acc;
 }
 
 // Backward of the time branch on its T distinct rows, given G[t] = sum of dZ0 rows with timestep t:
@@ -327,10 +337,10 @@ void time_branch_backward(const ActorLayout& L, const float* pk, const float* co
     const ActorGradOffsets go = actor_grad_offsets(shp);
     const int D = L.D, ld0 = D + L.S + L.A;
     launch_dw(G, L.h1, L.h1, pk + L.temb, D, D, g + go.off[4], ld0, g + go.off[5], L.T, st);
-    dim3 gt((D + 127) / 128, L.T), gm((4 * D + 127) / 128, L.T);
-    rows_linear_t_kernel<<<gt, 128, 0, st>>>(G, L.h1, L.h1, p[4], ld0, D, nullptr, dtemb);               // dtemb = G . W0[:, :D]
+    dim3 gt((D + 31) / 32, L.T), gm((4 * D + 31) / 32, L.T);
+    rows_linear_t_kernel<<<gt, 256, 0, st>>>(G, L.h1, L.h1, p[4], ld0, D, nullptr, dtemb);               // dtemb = G . W0[:, :D]
     launch_dw(dtemb, D, D, pk + L.hmid, 4 * D, 4 * D, g + go.off[2], 4 * D, g + go.off[3], L.T, st);
-    rows_linear_t_kernel<<<gm, 128, 0, st>>>(dtemb, D, D, p[2], 4 * D, 4 * D, pk + L.zmid, dhmid);        // dZmid
+    rows_linear_t_kernel<<<gm, 256, 0, st>>>(dtemb, D, D, p[2], 4 * D, 4 * D, pk + L.zmid, dhmid);        // dZmid
     launch_dw(dhmid, 4 * D, 4 * D, pk + L.pe, D, D, g + go.off[0], D, g + go.off[1], L.T, st);
 }
 

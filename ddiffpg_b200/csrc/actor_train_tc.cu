@@ -97,14 +97,36 @@ __global__ void train_tc_loss_kernel(const float* __restrict__ eps, const float*
     }
 }
 
-// db[n] += sum_r dZ[r][n]  (bias gradients), bf16 input, fp32 atomics; one block handles 64 rows x N columns
+// db[n] += sum_r dZ[r][n]  (bias gradients), bf16 input, fp32 atomics.  A block covers 256 rows; each thread owns
+// 8 consecutive columns (one 16-byte load per row) of one row strip, strips are reduced through shared memory.
 __global__ void colsum_bf16_kernel(const bf16* __restrict__ dz, int ld, int N, long R, float* __restrict__ db) {
-    const long r0 = (long)blockIdx.x * 256;
-    for (int c = threadIdx.x; c < N; c += blockDim.x) {
-        float s = 0.f;
-        const long r1 = r0 + 256 < R ? r0 + 256 : R;
-        for (long r = r0; r < r1; ++r) s += __bfloat162float(dz[r * ld + c]);
-        atomicAdd(db + c, s);
+    __shared__ float part[256][9];
+    const int groups = (N + 7) >> 3;                       // 8-column groups
+    const int strips = 256 / groups > 0 ? 256 / groups : 1;  // row strips handled concurrently by the block
+    const int grp = threadIdx.x % groups, strip = threadIdx.x / groups;
+    const long r0 = (long)blockIdx.x * 256, r1 = r0 + 256 < R ? r0 + 256 : R;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (strip < strips && groups <= 256) {
+        for (long r = r0 + strip; r < r1; r += strips) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(dz + r * ld + grp * 8));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                s[2 * i] += __uint_as_float(w[i] << 16);
+                s[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[threadIdx.x][i] = s[i];
+    __syncthreads();
+    if (threadIdx.x < groups) {
+        for (int i = 0; i < 8; ++i) {
+            float t = 0.f;
+            for (int st = 0; st < strips; ++st) t += part[st * groups + threadIdx.x][i];
+            const int c = threadIdx.x * 8 + i;
+            if (c < N && t != 0.f) atomicAdd(db + c, t);
+        }
     }
 }
 

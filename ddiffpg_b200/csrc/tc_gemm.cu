@@ -19,7 +19,8 @@ constexpr int kStages = 4;
 constexpr int kStageA = 128 * 128;          // 128 rows x 64 bf16
 constexpr int kStageW = 256 * 128;          // up to 256 rows x 64 bf16
 constexpr int kStageBytes = kStageA + kStageW;
-constexpr int kThreads = 192;               // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kThreads = 320;               // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (row GEMM)
+constexpr int kDwThreads = 192;             // dW GEMM: warps 2-5 epilogue
 constexpr uint32_t kOffBars = kStages * kStageBytes;
 constexpr uint32_t kSmemBytes = kOffBars + 8 * (2 * kStages + 4) + 16 + 1024;
 
@@ -88,7 +89,7 @@ row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full(i), 1); mbar_init(bar_acc_empty(i), 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full(i), 1); mbar_init(bar_acc_empty(i), 8); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -221,15 +222,18 @@ row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     store_bf16x16(g.out_a + row * g.out_ld + c0, z);
                 }
             };
+            // the two warps of a lane quarter split the 16-column pieces of the tile
+            const int half = (warp - 2) >> 2;
+            const int p_begin = half == 0 ? 0 : (pieces + 1) / 2, p_end = half == 0 ? (pieces + 1) / 2 : pieces;
             uint32_t va[16], vb[16];
-            tmem_ld16(tb, va);
-            for (int p = 0; p < pieces; p += 2) {
+            if (p_begin < p_end) tmem_ld16(tb + p_begin * 16, va);
+            for (int p = p_begin; p < p_end; p += 2) {
                 tmem_ld_wait();
-                if (p + 1 < pieces) tmem_ld16(tb + (p + 1) * 16, vb);
+                if (p + 1 < p_end) tmem_ld16(tb + (p + 1) * 16, vb);
                 process(va, p);
-                if (p + 1 < pieces) {
+                if (p + 1 < p_end) {
                     tmem_ld_wait();
-                    if (p + 2 < pieces) tmem_ld16(tb + (p + 2) * 16, va);
+                    if (p + 2 < p_end) tmem_ld16(tb + (p + 2) * 16, va);
                     process(vb, p + 1);
                 }
             }
@@ -263,7 +267,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, 
     return d;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kDwThreads, 1)
 dw_gemm_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_x, const DwKernelArgs k) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -415,7 +419,7 @@ int launch_dw_gemm(const DwGemm& g, cudaStream_t st) {
         make_tmap(&mx, g.X, (uint64_t)g.R, (uint64_t)g.K, (uint64_t)g.ldx, 64) != 0)
         DDP_FAIL(DDP_ERR_CUDA, "dW gemm: tensor map failed");
     DDP_CUDA_CHECK(cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    dw_gemm_kernel<<<(unsigned)(tiles * splits), kThreads, kSmemBytes, st>>>(mz, mx, k);
+    dw_gemm_kernel<<<(unsigned)(tiles * splits), kDwThreads, kSmemBytes, st>>>(mz, mx, k);
     DDP_LAUNCH_CHECK("dw_gemm_kernel");
     return DDP_OK;
 }
