@@ -201,6 +201,54 @@ class DiffusionPolicy(nn.Module):
                                          ws_bytes, stream_ptr()), "ddp_actor_sample")
         return out
 
+    def get_actions_host(self, state_host, out_host=None, chunks=4, precision=None):
+        """``actor(obs)`` for a batch that lives in (pinned) HOST memory, the situation of the reference's env
+        wrappers (wrappers/d4rl_wrapper.py:21-45 copy observations up and actions down around every call).
+        The batch is cut into ``chunks`` row ranges; the H2D copy of range i+1 and the D2H copy of range i-1
+        overlap the sampler launch of range i on two side streams, so PCIe time hides behind the kernel.
+        Returns ``out_host`` ([B, A] fp32, pinned; valid once the call returns)."""
+        precision = precision or self.precision
+        B, A, T = state_host.shape[0], self.action_dim, self.diffusion_iter
+        packed, shape, prec = self._packed(precision)
+        dev = packed.device
+        if out_host is None:
+            out_host = torch.empty((B, A), dtype=torch.float32).pin_memory()
+        if B == 0:
+            return out_host
+        chunks = max(1, min(chunks, (B + 127) // 128))
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream()
+            if "h2d" not in self._ws:
+                self._ws["h2d"], self._ws["d2h"] = torch.cuda.Stream(), torch.cuda.Stream()
+            h2d, d2h = self._ws["h2d"], self._ws["d2h"]
+            h2d.wait_stream(main)
+            rows = ((B + chunks - 1) // chunks + 127) // 128 * 128
+            st_dev = torch.empty((B, state_host.shape[1]), device=dev, dtype=torch.float32)
+            out_dev = torch.empty((B, A), device=dev, dtype=torch.float32)
+            done = []
+            for lo in range(0, B, rows):
+                hi = min(B, lo + rows)
+                with torch.cuda.stream(h2d):
+                    st_dev[lo:hi].copy_(state_host[lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(h2d)
+                main.wait_event(ev)
+                n = hi - lo
+                noise = torch.randn((T, n, A), device=dev, dtype=torch.float32)
+                ws_bytes = lib().ddp_actor_sample_workspace_bytes(shape, n, prec)
+                ws = self._workspace("sample", ws_bytes, dev) if ws_bytes else None
+                check(lib().ddp_actor_sample(shape, ptr(packed), ptr(st_dev[lo:hi]), ptr(noise), ptr(out_dev[lo:hi]), n,
+                                             prec, ptr(ws), ws_bytes, stream_ptr()), "ddp_actor_sample")
+                ev2 = torch.cuda.Event()
+                ev2.record(main)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(ev2)
+                    out_host[lo:hi].copy_(out_dev[lo:hi], non_blocking=True)
+                done.append(noise)          # keep the buffers alive until the streams have drained
+            main.wait_stream(d2h)
+            d2h.synchronize()
+        return out_host
+
     def _loss_and_grads(self, state, action, noise, timesteps, inv_count=None, precision=None):
         packed, shape, prec = self._packed(precision or self.train_precision)
         dev = packed.device
