@@ -343,7 +343,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="sample", choices=["sample", "ascent", "train"])
     ap.add_argument("--precision", default=None, choices=["fp32", "bf16"],
-                    help="default: bf16 tensor path for the sampler, fp32 for ascent/train")
+                    help="default: bf16 tensor-core paths (fp32 = warp-FMA parity paths)")
     ap.add_argument("--batch", type=int, default=65536, help="rows per GPU")
     ap.add_argument("--T", type=int, default=5)
     ap.add_argument("--width", type=int, default=1024)
@@ -351,7 +351,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.precision is None:
-        args.precision = os.environ.get("DDP_BENCH_PRECISION", "bf16" if args.workload == "sample" else "fp32")
+        args.precision = os.environ.get("DDP_BENCH_PRECISION", "bf16")
     if args.impl == "reference":
         run_reference(args)
     else:

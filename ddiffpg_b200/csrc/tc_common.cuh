@@ -58,6 +58,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
         ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(x), "r"(y) : "memory");
 }
 
+// 2-D tile store (shared -> global), bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------ TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {     // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");

@@ -190,13 +190,13 @@ row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     float d[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        // s = e^z + 1, p = s^2 + 1: tanh(softplus) = 1 - 2/p, sigmoid = 1 - 1/s; one rcp for both
-                        const float s = ex2_approx(fminf(z[i] * 1.4426950408889634f, 28.853900817779268f)) + 1.f;
-                        const float pp = fmaf(s, s, 1.f);
-                        const float qq = rcp_approx(s * pp);
-                        const float r = qq * s, inv_s = qq * pp;
-                        const float w = fmaf(-2.f, r, 1.f);
-                        d[i] = fmaf(z[i] * (1.f - inv_s), 4.f * r * (1.f - r), w);
+                        // e = exp(z), s = e + 1, p = s^2 + 1, R = 1/p:  tanh(softplus(z)) = w = 1 - 2R  and
+                        // mish'(z) = w + z * sigmoid(z) * (1 - w^2) = w + 4 z s e R^2   (sigmoid = e/s, 1 - w^2 = 4 s^2 R^2)
+                        const float e = ex2_approx(fminf(z[i] * 1.4426950408889634f, 28.853900817779268f));
+                        const float s = e + 1.f;
+                        const float R = rcp_approx(fmaf(s, s, 1.f));
+                        const float w = fmaf(-2.f, R, 1.f);
+                        d[i] = fmaf(4.f * z[i], (s * e) * R * R, w);
                         z[i] *= w;
                     }
                     store_bf16x16(g.out_a + row * g.out_ld + c0, z);
