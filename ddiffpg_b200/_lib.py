@@ -31,6 +31,8 @@ PROTOTYPES = {
     "ddp_actor_sample_workspace_bytes": (c_size_t, [POINTER(ActorShape), c_long, c_int]),
     "ddp_actor_sample": (c_int, [POINTER(ActorShape), c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int,
                                  c_void_p, c_size_t, c_void_p]),
+    "ddp_actor_sample_noisy": (c_int, [POINTER(ActorShape), c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                                       c_float, c_void_p, c_long, c_int, c_void_p, c_size_t, c_void_p]),
     "ddp_actor_grad_count": (c_size_t, [POINTER(ActorShape)]),
     "ddp_actor_train_workspace_bytes": (c_size_t, [POINTER(ActorShape), c_long, c_int]),
     "ddp_actor_loss_fwd_bwd": (c_int, [POINTER(ActorShape), c_void_p, POINTER(c_void_p), c_void_p, c_void_p,

@@ -78,6 +78,29 @@ def update_target_action(obs, action, critic, action_lr=0.03, update_times=20, m
     return mean_abs[0].item(), update
 
 
+def get_actions(actor, obs, sample=True, noise_type="mixed", std_min=0.05, std_max=0.8, std=None, noise=None,
+                expl_noise=None):
+    """``AgentDDiffPG.get_actions`` (ddiffpg.py:82-100) after the optional obs normalisation: ``actor(obs)``
+    followed by ``add_mixed_normal_noise`` (type 'mixed') or ``add_normal_noise`` (type 'fixed', ``std``) with
+    ``out_bounds=[-1, 1]`` -- one fused launch."""
+    if not sample:
+        return actor.get_actions(obs, noise=noise)
+    if noise_type == "mixed":
+        return actor.get_actions(obs, noise=noise, expl_std=(std_min, std_max), expl_noise=expl_noise)
+    if noise_type == "fixed":
+        return actor.get_actions(obs, noise=noise, expl_std=(std, std), expl_noise=expl_noise)
+    raise NotImplementedError(noise_type)
+
+
+def get_tgt_policy_actions(actor_target, obs, sample=True, tgt_pol_std=0.8, tgt_pol_noise_bound=0.2, noise=None,
+                           expl_noise=None):
+    """``AgentDDiffPG.get_tgt_policy_actions`` (ddiffpg.py:102-110): target actor + clipped Gaussian smoothing."""
+    if not sample:
+        return actor_target.get_actions(obs, noise=noise)
+    return actor_target.get_actions(obs, noise=noise, expl_std=(tgt_pol_std, tgt_pol_std), expl_noise=expl_noise,
+                                    noise_bound=tgt_pol_noise_bound)
+
+
 def optimizer_update(optimizer, objective, max_grad_norm=1.0):
     """``ActorCriticBase.optimizer_update`` (ac_base.py:83-92): zero_grad, backward, clip, step."""
     optimizer.zero_grad(set_to_none=True)
@@ -182,6 +205,18 @@ class HotPathMixin:
     """Mix into an agent class (before ``ActorCriticBase``) to route its hot-path methods through the
     kernels while keeping the reference's signatures; reads the same cfg keys
     (cfg.diffusion.action_lr / update_times, cfg.algo.max_grad_norm)."""
+
+    def get_actions(self, obs, sample=True):
+        if self.cfg.algo.obs_norm:
+            obs = self.obs_rms.normalize(obs)
+        n = self.cfg.algo.noise
+        return get_actions(self.actor, obs, sample=sample, noise_type=n.type, std_min=n.get("std_min", 0.0),
+                           std_max=n.get("std_max", 0.0), std=self.get_noise_std() if n.type == "fixed" else None)
+
+    def get_tgt_policy_actions(self, obs, sample=True):
+        n = self.cfg.algo.noise
+        return get_tgt_policy_actions(self.actor_target, obs, sample=sample, tgt_pol_std=n.tgt_pol_std,
+                                      tgt_pol_noise_bound=n.tgt_pol_noise_bound)
 
     def update_target_action(self, obs, action, critic):
         return update_target_action(obs, action, critic, action_lr=self.cfg.diffusion.action_lr,

@@ -17,9 +17,9 @@ void set_error(const char* fmt, ...) {
 int pack_actor_fp32(const ActorLayout& L, const float* const p[12], float* out, cudaStream_t st);
 int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, cudaStream_t st);
 int actor_sample_fma(const ActorLayout& L, const float* pk, const float* state, const float* noise, float* out,
-                     long B, cudaStream_t st);
+                     long B, const ExplNoise& expl, cudaStream_t st);
 int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state, const float* noise, float* out,
-                    long B, void* ws, size_t ws_bytes, cudaStream_t st);
+                    long B, const ExplNoise& expl, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t actor_sample_tc_workspace(const ActorLayout& L, long B);
 size_t actor_train_workspace(const ActorLayout& L, long B);
 int actor_train_fma(const ActorLayout& L, const float* pk, const float* const p[12], const float* state,
@@ -91,18 +91,27 @@ size_t ddp_actor_sample_workspace_bytes(const ddp_actor_shape* s, long B, int pr
     return actor_sample_tc_workspace(make_actor_layout(*s, precision), B);
 }
 
-int ddp_actor_sample(const ddp_actor_shape* s, const void* packed, const float* state, const float* noise,
-                     float* action_out, long B, int precision, void* ws, size_t ws_bytes, void* stream) {
+int ddp_actor_sample_noisy(const ddp_actor_shape* s, const void* packed, const float* state, const float* noise,
+                           const float* expl_noise, float std_min, float std_max, float noise_bound,
+                           float* action_out, long B, int precision, void* ws, size_t ws_bytes, void* stream) {
     int rc = check_actor_shape(s);
     if (rc != DDP_OK) return rc;
     if (B < 0) DDP_FAIL(DDP_ERR_SHAPE, "ddp_actor_sample: negative batch");
     if (B == 0) return DDP_OK;
     if (!packed || !state || !noise || !action_out) DDP_FAIL(DDP_ERR_ARG, "ddp_actor_sample: NULL argument");
+    if (expl_noise && (std_min < 0.f || std_max < 0.f)) DDP_FAIL(DDP_ERR_ARG, "ddp_actor_sample_noisy: negative std");
     ActorLayout L = make_actor_layout(*s, precision);
     cudaStream_t st = (cudaStream_t)stream;
-    if (precision == DDP_FP32) return actor_sample_fma(L, (const float*)packed, state, noise, action_out, B, st);
-    if (precision == DDP_BF16) return actor_sample_tc(L, packed, state, noise, action_out, B, ws, ws_bytes, st);
+    ExplNoise e{expl_noise, std_min, std_max, noise_bound};
+    if (precision == DDP_FP32) return actor_sample_fma(L, (const float*)packed, state, noise, action_out, B, e, st);
+    if (precision == DDP_BF16) return actor_sample_tc(L, packed, state, noise, action_out, B, e, ws, ws_bytes, st);
     DDP_FAIL(DDP_ERR_ARG, "unknown precision %d", precision);
+}
+
+int ddp_actor_sample(const ddp_actor_shape* s, const void* packed, const float* state, const float* noise,
+                     float* action_out, long B, int precision, void* ws, size_t ws_bytes, void* stream) {
+    return ddp_actor_sample_noisy(s, packed, state, noise, nullptr, 0.f, 0.f, 0.f, action_out, B, precision, ws,
+                                  ws_bytes, stream);
 }
 
 size_t ddp_actor_grad_count(const ddp_actor_shape* s) {

@@ -97,6 +97,24 @@ inline int check_actor_shape(const ddp_actor_shape* s) {
     return DDP_OK;
 }
 
+// Exploration / target-policy noise applied to the sampled action (reference: ddiffpg/utils/noise.py:19-41 as
+// called by AgentDDiffPG.get_actions / get_tgt_policy_actions, ddiffpg/algo/ddiffpg.py:88-109):
+//   out = clamp(a + clamp(std_r * z, -bound, +bound), -1, 1),  std_r = linspace(std_min, std_max, B)[r]
+// z [B, A] is pre-drawn standard normal noise (NULL switches the epilogue off); bound <= 0 means no noise clamp.
+struct ExplNoise {
+    const float* z;
+    float std_min, std_max, bound;
+};
+__device__ __forceinline__ float apply_expl_noise(const ExplNoise& e, float a, long row, long B, int A, int c) {
+    if (!e.z) return a;
+    // torch.linspace fills from both ends with step = (end - start) / (steps - 1)
+    const float step = B > 1 ? (e.std_max - e.std_min) / (float)(B - 1) : 0.f;
+    const float sd = row < B / 2 ? e.std_min + step * (float)row : e.std_max - step * (float)(B - 1 - row);
+    float nz = sd * e.z[row * A + c];
+    if (e.bound > 0.f) nz = fminf(fmaxf(nz, -e.bound), e.bound);
+    return fminf(fmaxf(a + nz, -1.f), 1.f);
+}
+
 // offsets (in floats) of each parameter inside the flat gradient vector, state_dict order
 struct ActorGradOffsets { size_t off[13]; };
 inline ActorGradOffsets actor_grad_offsets(const ddp_actor_shape& s) {

@@ -16,6 +16,7 @@ struct SampleFmaArgs {
     const float* b1; const float* b2; const float* b3; const float* tb0; const float* cst;
     int S, A, T, h1, h2, h3, K0p, A4;
     int ks0, ks1, ks2, ks3;
+    ExplNoise expl;
 };
 
 template <int RT, int NT>
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(NT) actor_sample_fma_kernel(SampleFmaArgs a, c
     for (int i = tid; i < RT * a.A; i += NT) {
         int r = i / a.A, c = i % a.A;
         long row = row0 + r;
-        if (row < B) out[row * a.A + c] = in0[r * a.K0p + a.S + c];
+        if (row < B) out[row * a.A + c] = apply_expl_noise(a.expl, in0[r * a.K0p + a.S + c], row, B, a.A, c);
     }
 }
 
@@ -113,8 +114,9 @@ static int launch_sample_fma(const SampleFmaArgs& a, const float* state, const f
 }
 
 int actor_sample_fma(const ActorLayout& L, const float* pk, const float* state, const float* noise, float* out,
-                     long B, cudaStream_t st) {
+                     long B, const ExplNoise& expl, cudaStream_t st) {
     SampleFmaArgs a;
+    a.expl = expl;
     a.wt0 = pk + L.wt0; a.wt1 = pk + L.wt1; a.wt2 = pk + L.wt2; a.wt3 = pk + L.wt3;
     a.b1 = pk + L.b1; a.b2 = pk + L.b2; a.b3 = pk + L.b3; a.tb0 = pk + L.tb0; a.cst = pk + L.cst;
     a.S = L.S; a.A = L.A; a.T = L.T; a.h1 = L.h1; a.h2 = L.h2; a.h3 = L.h3; a.K0p = L.K0p; a.A4 = L.A4;

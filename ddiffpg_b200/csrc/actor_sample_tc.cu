@@ -60,6 +60,7 @@ struct TcArgs {
     int S, A, T, h1, h2, h3;
     int nparts1, part1;        // layer-1 output split into nparts1 parts of part1 (<= 256) columns
     int num_tiles;
+    ExplNoise expl;            // optional exploration / target-policy noise epilogue
     long long* dbg;            // optional per-phase cycle counters of CTA 0 (development aid), else NULL
 };
 
@@ -316,7 +317,7 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
         } else if (e.valid) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                if (i < a.A) a.out[e.row * a.A + i] = e.xr[i];
+                if (i < a.A) a.out[e.row * a.A + i] = apply_expl_noise(a.expl, e.xr[i], e.row, a.B, a.A, i);
         }
     }
     tc_fence_before();
@@ -571,7 +572,7 @@ int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, 
 size_t actor_sample_tc_workspace(const ActorLayout&, long) { return 0; }
 
 int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state, const float* noise, float* out,
-                    long B, void*, size_t, cudaStream_t st) {
+                    long B, const ExplNoise& expl, void*, size_t, cudaStream_t st) {
     if (!tc_shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 actor path does not support this shape");
     const uint8_t* base = (const uint8_t*)packed;
     const float* pk = (const float*)packed;
@@ -592,6 +593,7 @@ int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state
     a.part1 = L.h2 / a.nparts1;
     a.num_tiles = (int)((B + kRows - 1) / kRows);
     a.dbg = g_tc_dbg;
+    a.expl = expl;
     CUtensorMap m1, m2, m1h, m2h;
     if (make_tmap_bf16_sw128(&m1, base + L.tc_w1, L.h2, L.h1, a.part1) != 0 ||
         make_tmap_bf16_sw128(&m2, base + L.tc_w2, L.h3, L.h2, L.h3) != 0 ||

@@ -168,9 +168,15 @@ class DiffusionPolicy(nn.Module):
     def forward(self, x, sample=True, add_noise=False):
         return self.get_actions(x, sample=sample, add_noise=add_noise)
 
-    def get_actions(self, state, sample=True, add_noise=False, noise=None, precision=None):
+    def get_actions(self, state, sample=True, add_noise=False, noise=None, precision=None, expl_std=None,
+                    expl_noise=None, noise_bound=0.0):
         """diffusion_mlp.py:219-251.  ``noise`` ([T, B, A]; [0] = x_T, [j] = step noise at t = T-j) may be
-        injected for reproducibility; otherwise it is drawn on the device."""
+        injected for reproducibility; otherwise it is drawn on the device.
+
+        ``expl_std=(std_min, std_max)`` fuses the noise the agent adds right after the call
+        (``add_mixed_normal_noise`` / ``add_normal_noise``, utils/noise.py:19-41) into the sampler epilogue:
+        ``clamp(a + clamp(linspace(std_min, std_max, B)[r] * z, +-noise_bound), -1, 1)`` with ``z`` =
+        ``expl_noise`` ([B, A] standard normal; drawn on the device when omitted)."""
         if not sample:
             raise NotImplementedError("sample=False (autograd through the chain) is unused by the DDiffPG agent "
                                       "and not provided by the fused sampler")
@@ -194,11 +200,22 @@ class DiffusionPolicy(nn.Module):
         out = torch.empty((B, A), device=dev, dtype=torch.float32)
         if B == 0:
             return out
+        std_min = std_max = 0.0
+        if expl_std is not None:
+            std_min, std_max = (expl_std, expl_std) if isinstance(expl_std, (int, float)) else expl_std
+            if expl_noise is None:
+                expl_noise = torch.randn((B, A), device=dev, dtype=torch.float32)
+            elif tuple(expl_noise.shape) != (B, A):
+                raise ValueError(f"expl_noise must be [B={B}, A={A}], got {tuple(expl_noise.shape)}")
+            expl_noise = expl_noise.to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            expl_noise = None
         with torch.cuda.device(dev):
             ws_bytes = lib().ddp_actor_sample_workspace_bytes(shape, B, prec)
             ws = self._workspace("sample", ws_bytes, dev) if ws_bytes else None
-            check(lib().ddp_actor_sample(shape, ptr(packed), ptr(state), ptr(noise), ptr(out), B, prec, ptr(ws),
-                                         ws_bytes, stream_ptr()), "ddp_actor_sample")
+            check(lib().ddp_actor_sample_noisy(shape, ptr(packed), ptr(state), ptr(noise), ptr(expl_noise),
+                                               float(std_min), float(std_max), float(noise_bound or 0.0), ptr(out),
+                                               B, prec, ptr(ws), ws_bytes, stream_ptr()), "ddp_actor_sample_noisy")
         return out
 
     def get_actions_host(self, state_host, out_host=None, chunks=4, precision=None):

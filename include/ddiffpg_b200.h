@@ -73,6 +73,17 @@ int ddp_actor_sample(const ddp_actor_shape* shape, const void* packed, const flo
                      const float* noise, float* action_out, long B, int precision,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* ddp_actor_sample fused with the noise its callers add right after it: AgentDDiffPG.get_actions
+ * (add_mixed_normal_noise / add_normal_noise, ddiffpg/algo/ddiffpg.py:88-99) and get_tgt_policy_actions
+ * (:102-109), i.e. ddiffpg/utils/noise.py:19-41:
+ *   out = clamp(a + clamp(std_r * z, -noise_bound, +noise_bound), -1, 1), std_r = linspace(std_min, std_max, B)[r]
+ * expl_noise [B,A] is pre-drawn standard normal noise (NULL = plain ddp_actor_sample); std_min == std_max is
+ * the 'fixed' type; noise_bound <= 0 disables the inner clamp. */
+int ddp_actor_sample_noisy(const ddp_actor_shape* shape, const void* packed, const float* state,
+                           const float* noise, const float* expl_noise, float std_min, float std_max,
+                           float noise_bound, float* action_out, long B, int precision,
+                           void* ws, size_t ws_bytes, void* stream);
+
 /* Replaces DiffusionPolicy.get_loss + the backward of optimizer_update
  * (ddiffpg/models/diffusion_mlp.py:294-321, ddiffpg/algo/ac_base.py:83-85).
  * state [B,S], action [B,A], noise [B,A], t [B] int64 in [0,T).  inv_count = 1/(B_global*A).

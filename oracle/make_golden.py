@@ -172,5 +172,34 @@ def main():
                  checksum=param_checksum(params, port.CRITIC_KEYS))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--noise-only" not in __import__("sys").argv:
     main()
+    noise_fixture()
+
+
+def noise_fixture():
+    """N3: the reference's own add_mixed_normal_noise / add_normal_noise (ddiffpg/utils/noise.py) with the
+    Gaussian draw replaced by std * z."""
+    import sys
+    sys.path.insert(0, ref_loader.REF_ROOT)
+    from ddiffpg.utils import noise as ref_noise
+    g = torch.Generator().manual_seed(4000)
+    a = torch.rand(37, 8, generator=g) * 2 - 1
+    z = torch.randn(37, 8, generator=g)
+    real_normal = torch.normal
+    torch.normal = lambda mean, std: mean + std * z
+    try:
+        mixed = ref_noise.add_mixed_normal_noise(a, std_max=0.8, std_min=0.05, out_bounds=[-1.0, 1.0])
+        fixed = ref_noise.add_normal_noise(a, std=0.3, out_bounds=[-1.0, 1.0])
+        tgt = ref_noise.add_normal_noise(a, std=0.8, noise_bounds=[-0.2, 0.2], out_bounds=[-1.0, 1.0])
+    finally:
+        torch.normal = real_normal
+    assert torch.equal(mixed, port.add_noise_to_actions(a, z, 0.05, 0.8))
+    assert torch.equal(tgt, port.add_noise_to_actions(a, z, 0.8, 0.8, noise_bounds=(-0.2, 0.2)))
+    np.savez(os.path.join(OUT, "n3_noise.npz"), a=a.numpy(), z=z.numpy(), mixed=mixed.numpy(), fixed=fixed.numpy(),
+             tgt=tgt.numpy())
+    print("n3_noise: port == reference")
+
+
+if __name__ == "__main__" and "--noise-only" in __import__("sys").argv:
+    noise_fixture()

@@ -131,6 +131,21 @@ def actor_loss_and_grads(p, state, action, noise, timesteps, T):
     return loss.detach(), {k: g for k, g in zip(ACTOR_KEYS, grads)}
 
 
+def add_noise_to_actions(actions, z, std_min, std_max, noise_bounds=None, out_bounds=(-1.0, 1.0)):
+    """utils/noise.py:19-41 with the Gaussian draw replaced by std * z (z standard normal, injected):
+    add_mixed_normal_noise (std = linspace(std_min, std_max, B) per row) and, for std_min == std_max,
+    add_normal_noise; optional noise clamp (get_tgt_policy_actions, ddiffpg.py:104-109) and output clamp."""
+    B = actions.shape[0]
+    std_seq = torch.linspace(std_min, std_max, B).to(actions.dtype).unsqueeze(-1).expand(actions.shape)
+    noise = std_seq * z
+    if noise_bounds is not None:
+        noise = noise.clamp(noise_bounds[0], noise_bounds[1])
+    out = actions + noise
+    if out_bounds is not None:
+        out = out.clamp(out_bounds[0], out_bounds[1])
+    return out
+
+
 def clip_coef(total_norm, max_norm=1.0):
     """torch.nn.utils.clip_grad_norm_: coef = clamp(max_norm / (norm + 1e-6), max=1)."""
     return torch.clamp(max_norm / (total_norm + 1e-6), max=1.0)

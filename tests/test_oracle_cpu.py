@@ -209,3 +209,12 @@ def test_unsupported_paths_fail_loudly():
         DiffusionPolicy(34, 8, 5, energy=True)
     with pytest.raises(RuntimeError, match="CUDA only"):       # no CPU fallback
         pol(torch.zeros(2, 34))
+
+
+def test_port_action_noise_matches_reference_fixture():
+    """N3: add_mixed_normal_noise / add_normal_noise (utils/noise.py:19-41) with injected standard normals."""
+    g = load_golden("n3_noise")
+    a, z = torch.from_numpy(g["a"]), torch.from_numpy(g["z"])
+    np.testing.assert_array_equal(port.add_noise_to_actions(a, z, 0.05, 0.8).numpy(), g["mixed"])
+    np.testing.assert_array_equal(port.add_noise_to_actions(a, z, 0.3, 0.3).numpy(), g["fixed"])
+    np.testing.assert_array_equal(port.add_noise_to_actions(a, z, 0.8, 0.8, noise_bounds=(-0.2, 0.2)).numpy(), g["tgt"])
