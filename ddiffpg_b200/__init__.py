@@ -5,9 +5,10 @@
 ``libddiffpg_b200.so`` (C ABI: ``include/ddiffpg_b200.h``); importing works without a GPU, calling does not.
 """
 from .models import DiffusionPolicy, DistributionalDoubleQ, DiffusionNet, MLPNet  # noqa: F401
-from .algo import (FusedActorTrainer, HotPathMixin, get_actions, get_tgt_policy_actions,  # noqa: F401
+from .algo import (FusedActorTrainer, HotPathMixin, critic_loss_and_grads, get_actions,  # noqa: F401
+                   get_tgt_policy_actions, update_critic,
                    optimizer_update, q_action_ascent_segments, soft_update, update_actor, update_target_action)
 
 __all__ = ["DiffusionPolicy", "DistributionalDoubleQ", "DiffusionNet", "MLPNet", "FusedActorTrainer",
-           "HotPathMixin", "get_actions", "get_tgt_policy_actions", "optimizer_update", "q_action_ascent_segments", "soft_update", "update_actor",
+           "HotPathMixin", "critic_loss_and_grads", "update_critic", "get_actions", "get_tgt_policy_actions", "optimizer_update", "q_action_ascent_segments", "soft_update", "update_actor",
            "update_target_action"]

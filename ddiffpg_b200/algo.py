@@ -120,6 +120,57 @@ def update_actor(actor, actor_optimizer, obs, target_action, max_grad_norm=1.0, 
     return actor_loss.item(), grad_norm.item()
 
 
+def critic_loss_and_grads(critic, critic_target, obs, action, next_obs, next_actions, reward, done, gamma_n):
+    """Loss and flat gradient (state_dict order) of the reference's critic objective (ddiffpg.py:325-349) for one
+    critic: target = min of the two C51-projected target heads, loss = BCE(Q1, target) + BCE(Q2, target)."""
+    def fp32_cache(c):      # the update runs on the fp32 path; keep its pack apart from a bf16 inference pack
+        if getattr(c, "precision", "fp32") == "fp32":
+            return c._cache
+        if not hasattr(c, "_cache_fp32"):
+            c._cache_fp32 = _PackCache()
+        return c._cache_fp32
+    packed, shape, prec = pack_critics([critic], fp32_cache(critic), "fp32")
+    packed_t, _, _ = pack_critics([critic_target], fp32_cache(critic_target), "fp32")
+    dev = packed.device
+    f = lambda x: x.detach().to(device=dev, dtype=torch.float32).contiguous()
+    obs, action, next_obs, next_actions = f(obs), f(action), f(next_obs), f(next_actions)
+    reward, done = f(reward).reshape(-1), f(done).reshape(-1)
+    B = obs.shape[0]
+    if reward.numel() != B or done.numel() != B:
+        raise ValueError("reward and done must have one entry per row")
+    n = lib().ddp_q_grad_count(shape)
+    grads = torch.empty(n, device=dev, dtype=torch.float32)
+    loss = torch.zeros((), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        ws_bytes = lib().ddp_q_critic_train_workspace_bytes(shape, B, prec)
+        ws = _workspace("q_train", ws_bytes, dev)
+        check(lib().ddp_q_critic_loss_fwd_bwd(shape, ptr(packed), ptr(packed_t), ptr(obs), ptr(action), ptr(next_obs),
+                                              ptr(next_actions), ptr(reward), ptr(done), float(gamma_n), ptr(loss),
+                                              ptr(grads), B, prec, ptr(ws), ws_bytes, stream_ptr()),
+              "ddp_q_critic_loss_fwd_bwd")
+    return loss, grads
+
+
+def update_critic(critic, critic_target, critic_optimizer, obs, action, reward, next_obs, next_actions, done,
+                  gamma_n=0.99, max_grad_norm=1.0):
+    """``AgentDDiffPG.update_critic`` (ddiffpg.py:322-351) with ``next_actions`` already sampled
+    (``get_tgt_policy_actions``): fused target/loss/backward, then the reference's own clip + optimizer step on
+    the ``.grad`` fields.  Returns ``(critic, loss float, pre-clip grad norm float)``."""
+    loss, grads = critic_loss_and_grads(critic, critic_target, obs, action, next_obs, next_actions, reward, done,
+                                        gamma_n)
+    critic_optimizer.zero_grad(set_to_none=True)
+    off = 0
+    for p in critic.parameters():
+        p.grad = grads[off:off + p.numel()].view(p.shape)
+        off += p.numel()
+    if max_grad_norm is not None:
+        grad_norm = clip_grad_norm_(parameters=critic_optimizer.param_groups[0]["params"], max_norm=max_grad_norm)
+    else:
+        grad_norm = None
+    critic_optimizer.step()
+    return critic, loss.item(), (grad_norm.item() if grad_norm is not None else None)
+
+
 @torch.no_grad()
 def soft_update(target_net, current_net, tau):
     """``ddiffpg/utils/torch_util.py:9-12`` plus the cache invalidation ``.data`` writes cannot signal."""
@@ -217,6 +268,13 @@ class HotPathMixin:
         n = self.cfg.algo.noise
         return get_tgt_policy_actions(self.actor_target, obs, sample=sample, tgt_pol_std=n.tgt_pol_std,
                                       tgt_pol_noise_bound=n.tgt_pol_noise_bound)
+
+    def update_critic(self, critic, critic_target, critic_optimizer, obs, action, reward, next_obs,
+                      embedded_next_obs, done):
+        next_actions = self.get_tgt_policy_actions(embedded_next_obs)
+        return update_critic(critic, critic_target, critic_optimizer, obs, action, reward, next_obs, next_actions,
+                             done, gamma_n=self.cfg.algo.gamma ** self.cfg.algo.nstep,
+                             max_grad_norm=self.cfg.algo.max_grad_norm)
 
     def update_target_action(self, obs, action, critic):
         return update_target_action(obs, action, critic, action_lr=self.cfg.diffusion.action_lr,

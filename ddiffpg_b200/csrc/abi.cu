@@ -48,6 +48,12 @@ int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, co
                 float* action, int iters, float lr, float b1, float b2, float eps, float max_norm, float lim,
                 float* mean_abs, float* gnorm_out, long B, void* ws, size_t ws_bytes, cudaStream_t st);
 
+size_t q_critic_train_workspace(const QLayout& L, long B);
+size_t q_grad_count(const QLayout& L);
+int q_critic_train_fma(const QLayout& L, const float* pk, const float* pk_target, const float* obs, const float* act,
+                       const float* next_obs, const float* next_act, const float* reward, const float* done, float gamma,
+                       float* loss_out, float* grads, long B, void* ws, size_t ws_bytes, cudaStream_t st);
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace ddp
@@ -231,6 +237,34 @@ int ddp_q_action_ascent(const ddp_q_shape* s, const void* packed, const int64_t*
     if (ws_bytes < q_ascent_workspace(L, B, iters)) DDP_FAIL(DDP_ERR_ARG, "ddp_q_action_ascent: workspace too small");
     return q_ascent_fma(L, (const float*)packed, seg_off, seg_mean_count, obs, action_inout, iters, lr, beta1, beta2,
                         eps, max_norm, lim, mean_abs_out, gnorm_out, B, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+size_t ddp_q_grad_count(const ddp_q_shape* s) {
+    if (check_q_shape(s) != DDP_OK) return 0;
+    return q_grad_count(make_q_layout(*s, DDP_FP32));
+}
+
+size_t ddp_q_critic_train_workspace_bytes(const ddp_q_shape* s, long B, int precision) {
+    if (check_q_shape(s) != DDP_OK || B <= 0 || precision != DDP_FP32) return 0;
+    return q_critic_train_workspace(make_q_layout(*s, precision), B);
+}
+
+int ddp_q_critic_loss_fwd_bwd(const ddp_q_shape* s, const void* packed, const void* packed_target, const float* obs,
+                              const float* action, const float* next_obs, const float* next_action,
+                              const float* reward, const float* done, float gamma_n, float* loss_out,
+                              float* grads_flat, long B, int precision, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_q_shape(s);
+    if (rc != DDP_OK) return rc;
+    if (s->n_modes != 1) DDP_FAIL(DDP_ERR_SHAPE, "ddp_q_critic_loss_fwd_bwd: one critic per call (n_modes must be 1)");
+    if (B <= 0) DDP_FAIL(DDP_ERR_SHAPE, "ddp_q_critic_loss_fwd_bwd: batch must be positive");
+    if (!packed || !packed_target || !obs || !action || !next_obs || !next_action || !reward || !done || !loss_out ||
+        !grads_flat || !ws)
+        DDP_FAIL(DDP_ERR_ARG, "ddp_q_critic_loss_fwd_bwd: NULL argument");
+    if (precision != DDP_FP32) DDP_FAIL(DDP_ERR_UNSUPPORTED, "critic update: only DDP_FP32 is implemented");
+    if (!aligned16(ws) || !aligned16(grads_flat)) DDP_FAIL(DDP_ERR_ARG, "workspace/grads must be 16-byte aligned");
+    return q_critic_train_fma(make_q_layout(*s, precision), (const float*)packed, (const float*)packed_target, obs,
+                              action, next_obs, next_action, reward, done, gamma_n, loss_out, grads_flat, B, ws,
+                              ws_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

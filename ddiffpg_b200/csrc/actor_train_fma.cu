@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(256) dw_gemm_kernel(const float* __restrict__ 
     }
 }
 
-static void launch_dw(const float* dz, int ldz, int N, const float* x, int ldx, int K, float* C, int ldc,
+void launch_dw(const float* dz, int ldz, int N, const float* x, int ldx, int K, float* C, int ldc,
                       float* dbias, long R, cudaStream_t st) {
     dim3 grid((N + 63) / 64, (K + 63) / 64, 1);
     // enough row splits for ~4 waves of 148 SMs, at least 64 rows per split

@@ -29,6 +29,17 @@ struct QArgs {
     int ks1, ks2, ks3, ks4, kb4, kb3, kb2, kb1;
 };
 
+// Global buffers of the critic training step (MODE 2): everything the weight-gradient GEMMs need.
+struct QTrainBufs {
+    float *xin;                     // [B][K1p]  [obs | act | 0]
+    float *a1[2], *a2[2], *a3[2];   // activations, then overwritten by dZ1, dZ2, dZ3 AFTER the copies below
+    float *z1[2], *z2[2], *z3[2];   // dZ1, dZ2, dZ3
+    float *dl[2];                   // [B][atomsP] d loss / d logits
+    const float* target;            // [B][atoms]   projected target distribution
+    float inv_count;                // 1 / (B * atoms): mean of binary_cross_entropy
+    float* loss_out;
+};
+
 static QArgs make_qargs(const QLayout& L, const float* pk, int NT) {
     QArgs a;
     a.packed = pk; a.mode_stride = L.mode_stride; a.net[0] = L.net[0]; a.net[1] = L.net[1]; a.z = L.z;
@@ -92,11 +103,15 @@ int pack_q_fp32(const QLayout& L, const float* const p[], float* out, cudaStream
 // Forward (+ optional backward to the action) for one row tile.
 //   MODE 0: inference outputs (q_min, p1, p2, dq_da) -- get_q1_q2 / get_q_min and their autograd.
 //   MODE 1: one ascent iteration: g = -inv_cnt * d min(Q1,Q2)/da, plus sum g^2 into gsq[mode].
+//   MODE 2: critic training step (AgentDDiffPG.update_critic, ddiffpg.py:348-349): BCE(current_Q1, target) +
+//           BCE(current_Q2, target), softmax backward, dZ chain; activations and dZ go to global memory for the
+//           weight-gradient GEMMs.
 template <int RT, int NT, int MODE>
 __global__ void __launch_bounds__(NT) q_tile_kernel(QArgs a, SegTable seg, const float* __restrict__ obs,
                                                     const float* __restrict__ act, float* __restrict__ qmin_out,
                                                     float* __restrict__ p1_out, float* __restrict__ p2_out,
-                                                    float* __restrict__ grad_out, float* __restrict__ gsq) {
+                                                    float* __restrict__ grad_out, float* __restrict__ gsq,
+                                                    QTrainBufs tr) {
     extern __shared__ __align__(16) float smem[];
     const int ld1 = a.h1 + 4, ld2 = a.h2 + 4, ld3 = a.h3 + 4, ldl = a.atomsP;
     float* in1 = smem;                                  // [RT][K1p] = [obs | act | 0]
@@ -159,10 +174,69 @@ __global__ void __launch_bounds__(NT) q_tile_kernel(QArgs a, SegTable seg, const
         __syncthreads();
     }
 
-    // softmax over atoms and expectation: one warp per (net, row)
     const float* zs = base + a.z;
     const int warp = tid >> 5, lane = tid & 31;
-    for (int pr = warp; pr < 2 * RT; pr += NT / 32) {
+    // shared [RT][ld] tile -> global [B][ldg] rows of this tile
+    auto store_tile = [&](const float* sbuf, int lds, float* gbuf, int ldg, int ncols) {
+        for (int i = tid; i < RT * ncols; i += NT) {
+            const int r = i / ncols, c = i % ncols;
+            const long row = row0 + r;
+            if (row < row_end) gbuf[row * ldg + c] = sbuf[r * lds + c];
+        }
+    };
+    if (MODE == 2) {
+        store_tile(in1, a.K1p, tr.xin, a.K1p, a.K1p);
+        for (int j = 0; j < 2; ++j) {
+            store_tile(A1 + j * RT * ld1, ld1, tr.a1[j], a.h1, a.h1);
+            store_tile(A2 + j * RT * ld2, ld2, tr.a2[j], a.h2, a.h2);
+            store_tile(A3 + j * RT * ld3, ld3, tr.a3[j], a.h3, a.h3);
+        }
+        // softmax, BCE against the projected target, and d loss / d logits: one warp per (net, row)
+        float lsum = 0.f;
+        for (int pr = warp; pr < 2 * RT; pr += NT / 32) {
+            float* lg = LG + pr * ldl;
+            const int j = pr / RT, r = pr % RT;
+            const long row = row0 + r;
+            const bool ok = row < row_end;
+            const int c0 = lane, c1 = lane + 32;
+            const bool v0 = c0 < a.atoms, v1 = c1 < a.atoms;
+            const float l0 = v0 ? lg[c0] : -INFINITY, l1 = v1 ? lg[c1] : -INFINITY;
+            const float mx = warp_max(fmaxf(l0, l1));
+            const float e0 = v0 ? expf(l0 - mx) : 0.f, e1 = v1 ? expf(l1 - mx) : 0.f;
+            const float sum = warp_sum(e0 + e1);
+            const float p0 = e0 / sum, p1 = e1 / sum;
+            const float t0 = (ok && v0) ? tr.target[row * a.atoms + c0] : 0.f, t1 = (ok && v1) ? tr.target[row * a.atoms + c1] : 0.f;
+            // F.binary_cross_entropy: logs clamped at -100; backward (p - t) / max((1 - p) p, 1e-12)
+            float g0 = 0.f, g1 = 0.f;
+            if (ok && v0) {
+                lsum -= t0 * fmaxf(logf(p0), -100.f) + (1.f - t0) * fmaxf(log1pf(-p0), -100.f);
+                g0 = tr.inv_count * (p0 - t0) / fmaxf((1.f - p0) * p0, 1e-12f);
+            }
+            if (ok && v1) {
+                lsum -= t1 * fmaxf(logf(p1), -100.f) + (1.f - t1) * fmaxf(log1pf(-p1), -100.f);
+                g1 = tr.inv_count * (p1 - t1) / fmaxf((1.f - p1) * p1, 1e-12f);
+            }
+            const float dot = warp_sum(p0 * g0 + p1 * g1);
+            const float d0 = p0 * (g0 - dot), d1 = p1 * (g1 - dot);
+            if (c0 < a.atomsP) lg[c0] = d0;
+            if (c1 < a.atomsP) lg[c1] = v1 ? d1 : 0.f;
+            if (ok) {
+                if (c0 < a.atomsP) tr.dl[j][row * a.atomsP + c0] = d0;
+                if (c1 < a.atomsP) tr.dl[j][row * a.atomsP + c1] = v1 ? d1 : 0.f;
+            }
+        }
+        lsum = warp_sum(lsum);
+        if (lane == 0) red[warp] = lsum;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int w = 0; w < NT / 32; ++w) t += red[w];
+            atomicAdd(tr.loss_out, t * tr.inv_count);
+        }
+        __syncthreads();
+    }
+    // softmax over atoms and expectation: one warp per (net, row)
+    for (int pr = warp; MODE != 2 && pr < 2 * RT; pr += NT / 32) {
         float* lg = LG + pr * ldl;                      // pr = j*RT + r, rows are contiguous
         const int c0 = lane, c1 = lane + 32;
         float l0 = c0 < a.atoms ? lg[c0] : -INFINITY, l1 = c1 < a.atoms ? lg[c1] : -INFINITY;
@@ -192,7 +266,7 @@ __global__ void __launch_bounds__(NT) q_tile_kernel(QArgs a, SegTable seg, const
     }
 
     // d min(Q1,Q2) / d logits: only the smaller net carries gradient (ties split, as torch.min does)
-    for (int i = tid; i < 2 * RT * ldl; i += NT) {
+    for (int i = tid; MODE != 2 && i < 2 * RT * ldl; i += NT) {
         int j = i / (RT * ldl), rem = i % (RT * ldl), r = rem / ldl, c = rem % ldl;
         float q1 = QV[r], q2 = QV[RT + r];
         float w = (q1 == q2) ? 0.5f : ((j == 0) == (q1 < q2) ? 1.f : 0.f);
@@ -227,11 +301,18 @@ __global__ void __launch_bounds__(NT) q_tile_kernel(QArgs a, SegTable seg, const
                              v.z * elu_grad_from_act(s.z), v.w * elu_grad_from_act(s.w));
         });
         __syncthreads();
+        if (MODE == 2) {
+            store_tile(a3, ld3, tr.z3[j], a.h3, a.h3);
+            store_tile(a2, ld2, tr.z2[j], a.h2, a.h2);
+            store_tile(a1, ld1, tr.z1[j], a.h1, a.h1);
+            continue;
+        }
         tile_linear<RT, NT>(base + n.w1a, a.A4, a.h1 >> 2, a.A4, a1, ld1, a.kb1, [&](int r, int n0, float4 v) {
             *reinterpret_cast<float4*>(ga + r * a.A4 + n0) = v;
         });
         __syncthreads();
     }
+    if (MODE == 2) return;
 
     float sq = 0.f;
     const float scale = MODE == 1 ? -seg.inv_cnt[m] : 1.f;
@@ -349,14 +430,14 @@ static long fill_segments(const QLayout& L, const int64_t* seg_off, const int64_
 template <int RT, int MODE>
 static int launch_q_tile(const QLayout& L, const float* pk, const SegTable& seg, long tiles, const float* obs,
                          const float* act, float* qmin, float* p1, float* p2, float* grad, float* gsq,
-                         cudaStream_t st) {
+                         cudaStream_t st, const QTrainBufs* tr = nullptr) {
     constexpr int NT = 256;
     size_t smem = q_tile_smem(L, RT);
     if (smem > 227 * 1024) DDP_FAIL(DDP_ERR_SHAPE, "critic tile needs %zu B of shared memory", smem);
     auto kern = q_tile_kernel<RT, NT, MODE>;
     DDP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QArgs a = make_qargs(L, pk, NT);
-    kern<<<(unsigned)tiles, NT, smem, st>>>(a, seg, obs, act, qmin, p1, p2, grad, gsq);
+    kern<<<(unsigned)tiles, NT, smem, st>>>(a, seg, obs, act, qmin, p1, p2, grad, gsq, tr ? *tr : QTrainBufs{});
     DDP_LAUNCH_CHECK("q_tile_kernel");
     return DDP_OK;
 }
@@ -410,6 +491,110 @@ int q_ascent_fma(const QLayout& L, const float* pk, const int64_t* seg_off, cons
     q_abs_sum_kernel<<<(unsigned)((n_elems + 2047) / 2048 < 592 ? (n_elems + 2047) / 2048 : 592), 256, 0, st>>>(seg, L.A, action, n_elems, abs_sum);
     q_finish_kernel<<<1, kMaxModes, 0, st>>>(seg, L.A, abs_sum, mean_abs);
     DDP_LAUNCH_CHECK("q ascent kernels");
+    return DDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// N1: critic update (AgentDDiffPG.update_critic, ddiffpg/algo/ddiffpg.py:322-351), fp32 path.
+void launch_dw(const float* dz, int ldz, int N, const float* x, int ldx, int K, float* C, int ldc, float* dbias, long R,
+               cudaStream_t st);      // fp32 dW = dZ^T . X with bias column sums (actor_train_fma.cu)
+
+// Categorical projection of r + (1 - done) * gamma * z onto the support (ddiffpg/utils/distl_util.py:4-20) for
+// both target heads, then their element-wise minimum (ddiffpg.py:346).  One warp per row.
+__global__ void c51_projection_min_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                                          const float* __restrict__ reward, const float* __restrict__ done,
+                                          float gamma, float v_min, float v_max, int atoms, const float* __restrict__ z,
+                                          long B, float* __restrict__ target) {
+    __shared__ float bins[8][2][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + warp;
+    bins[warp][0][lane] = 0.f; bins[warp][0][lane + 32] = 0.f;
+    bins[warp][1][lane] = 0.f; bins[warp][1][lane + 32] = 0.f;
+    __syncwarp();
+    if (row < B) {
+        const float delta_z = (float)(((double)v_max - (double)v_min) / (double)(atoms - 1));
+        const float r = reward[row], nd = __fmul_rn(__fsub_rn(1.f, done[row]), gamma);
+        for (int j = lane; j < atoms; j += 32) {
+            float tz = __fadd_rn(r, __fmul_rn(nd, z[j]));
+            tz = fminf(fmaxf(tz, v_min), v_max);
+            const float b = __fdiv_rn(__fsub_rn(tz, v_min), delta_z);
+            int lo = (int)floorf(b), up = (int)ceilf(b);
+            if (up > 0 && lo == up) lo -= 1;
+            if (lo < atoms - 1 && lo == up) up += 1;
+            const float wl = __fsub_rn((float)up, b), wu = __fsub_rn(b, (float)lo);
+            const float a1 = p1[row * atoms + j], a2 = p2[row * atoms + j];
+            atomicAdd(&bins[warp][0][lo], a1 * wl); atomicAdd(&bins[warp][0][up], a1 * wu);
+            atomicAdd(&bins[warp][1][lo], a2 * wl); atomicAdd(&bins[warp][1][up], a2 * wu);
+        }
+        __syncwarp();
+        for (int j = lane; j < atoms; j += 32) target[row * atoms + j] = fminf(bins[warp][0][j], bins[warp][1][j]);
+    }
+}
+
+struct QTrainWs {
+    float *p1t, *p2t, *target;
+    QTrainBufs b;
+    size_t total;
+};
+
+static QTrainWs carve_q_train(const QLayout& L, long B, float* base) {
+    QTrainWs w{};
+    size_t o = 0;
+    auto take = [&](size_t n) { float* r = base ? base + o : nullptr; o += (n + 63) / 64 * 64; return r; };
+    w.p1t = take((size_t)B * L.atoms); w.p2t = take((size_t)B * L.atoms); w.target = take((size_t)B * L.atoms);
+    w.b.xin = take((size_t)B * L.K1p);
+    for (int j = 0; j < 2; ++j) {
+        w.b.a1[j] = take((size_t)B * L.h1); w.b.a2[j] = take((size_t)B * L.h2); w.b.a3[j] = take((size_t)B * L.h3);
+        w.b.z1[j] = take((size_t)B * L.h1); w.b.z2[j] = take((size_t)B * L.h2); w.b.z3[j] = take((size_t)B * L.h3);
+        w.b.dl[j] = take((size_t)B * L.atomsP);
+    }
+    w.total = o * sizeof(float);
+    return w;
+}
+
+size_t q_critic_train_workspace(const QLayout& L, long B) { return carve_q_train(L, B, nullptr).total; }
+
+size_t q_grad_count(const QLayout& L) {
+    const size_t in1 = L.O + L.A;
+    return 2 * ((size_t)L.h1 * in1 + L.h1 + (size_t)L.h2 * L.h1 + L.h2 + (size_t)L.h3 * L.h2 + L.h3 + (size_t)L.atoms * L.h3 + L.atoms);
+}
+
+// pk / pk_target: packed critic and target critic (single mode).  grads: flat, state_dict order.
+int q_critic_train_fma(const QLayout& L, const float* pk, const float* pk_target, const float* obs, const float* act,
+                       const float* next_obs, const float* next_act, const float* reward, const float* done, float gamma,
+                       float* loss_out, float* grads, long B, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (ws_bytes < carve_q_train(L, B, nullptr).total) DDP_FAIL(DDP_ERR_ARG, "critic training: workspace too small");
+    QTrainWs w = carve_q_train(L, B, (float*)ws);
+    const int64_t seg_off[2] = {0, B};
+    // target distribution: critic_target.get_q1_q2(next_obs, next_actions) -> projection x2 -> min
+    int rc = q_forward_fma(L, pk_target, seg_off, next_obs, next_act, nullptr, w.p1t, w.p2t, nullptr, B, st);
+    if (rc != DDP_OK) return rc;
+    c51_projection_min_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(w.p1t, w.p2t, reward, done, gamma, L.v_min, L.v_max,
+                                                                        L.atoms, pk_target + L.z, B, w.target);
+    DDP_CUDA_CHECK(cudaMemsetAsync(grads, 0, q_grad_count(L) * sizeof(float), st));
+    w.b.target = w.target;
+    w.b.inv_count = 1.0f / ((float)B * (float)L.atoms);
+    w.b.loss_out = loss_out;
+    SegTable seg;
+    const bool small = B <= 148 * 8;
+    const long tiles = fill_segments(L, seg_off, nullptr, small ? 4 : 16, seg);
+    rc = small ? launch_q_tile<4, 2>(L, pk, seg, tiles, obs, act, nullptr, nullptr, nullptr, nullptr, nullptr, st, &w.b)
+               : launch_q_tile<16, 2>(L, pk, seg, tiles, obs, act, nullptr, nullptr, nullptr, nullptr, nullptr, st, &w.b);
+    if (rc != DDP_OK) return rc;
+    // weight gradients, flat in state_dict order: per net W1,b1,W2,b2,W3,b3,W4,b4
+    const int in1 = L.O + L.A;
+    float* g = grads;
+    for (int j = 0; j < 2; ++j) {
+        launch_dw(w.b.z1[j], L.h1, L.h1, w.b.xin, L.K1p, in1, g, in1, g + (size_t)L.h1 * in1, B, st);
+        g += (size_t)L.h1 * in1 + L.h1;
+        launch_dw(w.b.z2[j], L.h2, L.h2, w.b.a1[j], L.h1, L.h1, g, L.h1, g + (size_t)L.h2 * L.h1, B, st);
+        g += (size_t)L.h2 * L.h1 + L.h2;
+        launch_dw(w.b.z3[j], L.h3, L.h3, w.b.a2[j], L.h2, L.h2, g, L.h2, g + (size_t)L.h3 * L.h2, B, st);
+        g += (size_t)L.h3 * L.h2 + L.h3;
+        launch_dw(w.b.dl[j], L.atomsP, L.atoms, w.b.a3[j], L.h3, L.h3, g, L.h3, g + (size_t)L.atoms * L.h3, B, st);
+        g += (size_t)L.atoms * L.h3 + L.atoms;
+    }
+    DDP_LAUNCH_CHECK("critic training kernels");
     return DDP_OK;
 }
 

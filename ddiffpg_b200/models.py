@@ -394,6 +394,8 @@ class DistributionalDoubleQ(nn.Module):
 
     def mark_dirty(self):
         self._cache.dirty = True
+        if hasattr(self, "_cache_fp32"):
+            self._cache_fp32.dirty = True
 
     def _forward_raw(self, obs, action, want_probs, want_grad):
         packed, shape, prec = pack_critics([self], self._cache)

@@ -139,6 +139,23 @@ int ddp_q_action_ascent(const ddp_q_shape* shape, const void* packed, const int6
                         float lim, float* mean_abs_out, float* gnorm_out, long B, int precision,
                         void* ws, size_t ws_bytes, void* stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * Critic update.  Replaces the loss/backward half of AgentDDiffPG.update_critic
+ * (ddiffpg/algo/ddiffpg.py:322-351) for ONE critic (shape->n_modes must be 1):
+ *   target  = min(projection(Q1_tgt), projection(Q2_tgt))   critic_target.get_q1_q2(next_obs, next_action) and the
+ *             C51 projection of reward + (1-done)*gamma_n*z (ddiffpg/utils/distl_util.py:4-20), no gradient;
+ *   loss    = BCE(current_Q1, target) + BCE(current_Q2, target)   (F.binary_cross_entropy, mean over B*atoms);
+ *   grads   = d loss / d params of `packed`, flat in DistributionalDoubleQ.state_dict() order (overwritten).
+ * reward, done: [B] fp32.  loss_out[0] += loss (zero it first).  The optimizer step (clip_grad_norm_ + AdamW,
+ * ac_base.py:86-91) stays with the caller: ddp_clip_adamw_step on a flat vector, or torch's own. */
+size_t ddp_q_grad_count(const ddp_q_shape* shape);
+size_t ddp_q_critic_train_workspace_bytes(const ddp_q_shape* shape, long B, int precision);
+int ddp_q_critic_loss_fwd_bwd(const ddp_q_shape* shape, const void* packed, const void* packed_target,
+                              const float* obs, const float* action, const float* next_obs,
+                              const float* next_action, const float* reward, const float* done, float gamma_n,
+                              float* loss_out, float* grads_flat, long B, int precision, void* ws, size_t ws_bytes,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

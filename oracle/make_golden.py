@@ -172,9 +172,10 @@ def main():
                  checksum=param_checksum(params, port.CRITIC_KEYS))
 
 
-if __name__ == "__main__" and "--noise-only" not in __import__("sys").argv:
+if __name__ == "__main__" and not {"--noise-only", "--critic-only"} & set(__import__("sys").argv):
     main()
     noise_fixture()
+    critic_fixture()
 
 
 def noise_fixture():
@@ -203,3 +204,52 @@ def noise_fixture():
 
 if __name__ == "__main__" and "--noise-only" in __import__("sys").argv:
     noise_fixture()
+
+
+def critic_fixture():
+    """N1: the reference's own C51 projection (ddiffpg/utils/distl_util.py) and critic loss
+    (ddiffpg/algo/ddiffpg.py:322-349) around its real DistributionalDoubleQ modules."""
+    import sys
+    import torch.nn.functional as F
+    sys.path.insert(0, ref_loader.REF_ROOT)
+    from ddiffpg.utils.distl_util import projection
+    R = ref_loader.load_reference()
+    g = torch.Generator().manual_seed(5000)
+    B, gamma = 48, 0.99
+    params = port.init_critic_params(41, scale=1.5)
+    params_t = port.init_critic_params(42, scale=1.5)
+    obs, nobs = torch.randn(B, 29, generator=g), torch.randn(B, 29, generator=g)
+    act, nact = torch.rand(B, 8, generator=g) * 2 - 1, torch.rand(B, 8, generator=g) * 2 - 1
+    reward = torch.rand(B, 1, generator=g) * 2.0
+    reward[:4] = 0.0                                       # integer-b cases: l == u fix-ups
+    reward[4:8] = 4.5                                      # upper atoms clamp at v_max
+    done = (torch.rand(B, 1, generator=g) < 0.3).float()
+    critic = R.DistributionalDoubleQ(29, 8, v_min=0, v_max=5, num_atoms=51, device="cpu"); critic.load_state_dict(params)
+    target = R.DistributionalDoubleQ(29, 8, v_min=0, v_max=5, num_atoms=51, device="cpu"); target.load_state_dict(params_t)
+    with torch.no_grad():
+        t1, t2 = target.get_q1_q2(nobs, nact)
+        pr1 = projection(next_dist=t1, reward=reward, done=done, gamma=gamma, v_min=0, v_max=5, num_atoms=51,
+                         support=critic.z_atoms, device="cpu")
+        pr2 = projection(next_dist=t2, reward=reward, done=done, gamma=gamma, v_min=0, v_max=5, num_atoms=51,
+                         support=critic.z_atoms, device="cpu")
+        tq = torch.min(pr1, pr2)
+    c1, c2 = critic.get_q1_q2(obs, act)
+    loss = F.binary_cross_entropy(c1, tq) + F.binary_cross_entropy(c2, tq)
+    loss.backward()
+    grads = {k: v.grad.detach() for k, v in critic.named_parameters()}
+    tq_port = port.critic_target_dist(params_t, nobs, nact, reward, done, gamma)
+    l_port, g_port = port.critic_loss_and_grads(params, tq_port, obs, act)
+    d = max((grads[k] - g_port[k]).abs().max().item() for k in port.CRITIC_KEYS)
+    print(f"n1_critic: |proj diff|={(tq - tq_port).abs().max().item():.2e} |dloss|={abs(loss.item() - l_port.item()):.2e} max|dgrad|={d:.2e}")
+    assert (tq - tq_port).abs().max().item() < 1e-7 and d < 1e-7
+    save = dict(gamma=gamma, obs=obs.numpy(), act=act.numpy(), nobs=nobs.numpy(), nact=nact.numpy(), reward=reward.numpy(),
+                done=done.numpy(), proj1=pr1.numpy(), target_q=tq.numpy(), loss=loss.item(),
+                checksum=param_checksum(params, port.CRITIC_KEYS), checksum_t=param_checksum(params_t, port.CRITIC_KEYS))
+    for i, k in enumerate(port.CRITIC_KEYS):
+        save[f"g_{i}"] = grads[k].numpy() if grads[k].numel() <= 8192 else grads[k].flatten()[::97].numpy()
+        save[f"gnorm_{i}"] = float(grads[k].norm())
+    np.savez(os.path.join(OUT, "n1_critic.npz"), **save)
+
+
+if __name__ == "__main__" and "--critic-only" in __import__("sys").argv:
+    critic_fixture()

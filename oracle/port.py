@@ -204,6 +204,44 @@ def q_min(p, obs, act, v_min=0.0, v_max=5.0):
     return torch.min(torch.sum(p1 * z, dim=1), torch.sum(p2 * z, dim=1))
 
 
+def c51_projection(next_dist, reward, done, gamma, v_min=0.0, v_max=5.0, num_atoms=51):
+    """utils/distl_util.py:4-20 -- categorical (C51) projection of r + (1-done) gamma z onto the support."""
+    support = z_atoms(v_min, v_max, num_atoms, next_dist.dtype)
+    delta_z = (v_max - v_min) / (num_atoms - 1)
+    B = reward.shape[0]
+    target_z = (reward + (1 - done) * gamma * support).clamp(min=v_min, max=v_max)
+    b = (target_z - v_min) / delta_z
+    lo = b.floor().long()
+    up = b.ceil().long()
+    lo[torch.logical_and(up > 0, lo == up)] -= 1
+    up[torch.logical_and(lo < (num_atoms - 1), lo == up)] += 1
+    proj = torch.zeros_like(next_dist)
+    offset = (torch.arange(B) * num_atoms).unsqueeze(1).expand(B, num_atoms)
+    proj.view(-1).index_add_(0, (lo + offset).view(-1), (next_dist * (up.to(b.dtype) - b)).view(-1))
+    proj.view(-1).index_add_(0, (up + offset).view(-1), (next_dist * (b - lo.to(b.dtype))).view(-1))
+    return proj
+
+
+def critic_target_dist(p_target, next_obs, next_action, reward, done, gamma, v_min=0.0, v_max=5.0):
+    """AgentDDiffPG.update_critic, ddiffpg.py:325-346 (no_grad block): min of the two projected target heads.
+    reward / done are [B, 1] like the replay buffer hands them over."""
+    with torch.no_grad():
+        t1, t2 = q1_q2(p_target, next_obs, next_action)
+        n = t1.shape[1]
+        return torch.min(c51_projection(t1, reward, done, gamma, v_min, v_max, n),
+                         c51_projection(t2, reward, done, gamma, v_min, v_max, n))
+
+
+def critic_loss_and_grads(p, target_q, obs, action):
+    """ddiffpg.py:348-349: BCE(current_Q1, target_Q) + BCE(current_Q2, target_Q) and its gradients in
+    CRITIC_KEYS order (what objective.backward() leaves in .grad, before clipping)."""
+    q = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+    c1, c2 = q1_q2(q, obs, action)
+    loss = F.binary_cross_entropy(c1, target_q) + F.binary_cross_entropy(c2, target_q)
+    grads = torch.autograd.grad(loss, [q[k] for k in CRITIC_KEYS])
+    return loss.detach(), {k: g for k, g in zip(CRITIC_KEYS, grads)}
+
+
 def q_action_ascent(p, obs, action, iters=20, lr=0.03, eps=1e-5, max_norm=1.0,
                     betas=(0.9, 0.999), v_min=0.0, v_max=5.0, return_trace=False):
     """AgentDDiffPG.update_target_action, ddiffpg.py:358-373 (+ optimizer_update, ac_base.py:83-92).

@@ -218,3 +218,45 @@ def test_port_action_noise_matches_reference_fixture():
     np.testing.assert_array_equal(port.add_noise_to_actions(a, z, 0.05, 0.8).numpy(), g["mixed"])
     np.testing.assert_array_equal(port.add_noise_to_actions(a, z, 0.3, 0.3).numpy(), g["fixed"])
     np.testing.assert_array_equal(port.add_noise_to_actions(a, z, 0.8, 0.8, noise_bounds=(-0.2, 0.2)).numpy(), g["tgt"])
+
+
+def _critic_fixture_params(g):
+    p, pt = port.init_critic_params(41, scale=1.5), port.init_critic_params(42, scale=1.5)
+    from tests.util import checksum
+    np.testing.assert_allclose(checksum(p, port.CRITIC_KEYS), g["checksum"], rtol=1e-12)
+    np.testing.assert_allclose(checksum(pt, port.CRITIC_KEYS), g["checksum_t"], rtol=1e-12)
+    return p, pt
+
+
+def test_port_critic_update_matches_reference_fixture():
+    """N1: C51 projection (utils/distl_util.py:4-20) + BCE critic loss and its gradients (ddiffpg.py:325-349)."""
+    g = load_golden("n1_critic")
+    p, pt = _critic_fixture_params(g)
+    t = lambda k: torch.from_numpy(g[k])
+    tq = port.critic_target_dist(pt, t("nobs"), t("nact"), t("reward"), t("done"), float(g["gamma"]))
+    np.testing.assert_allclose(tq.numpy(), g["target_q"], rtol=0, atol=1e-7)
+    # every projected row is a distribution; the element-wise min of two may lose mass but never gains any
+    np.testing.assert_allclose(g["proj1"].sum(1), 1.0, atol=1e-5)
+    assert (tq.sum(1) <= 1.0 + 1e-5).all()
+    loss, grads = port.critic_loss_and_grads(p, tq, t("obs"), t("act"))
+    assert abs(loss.item() - float(g["loss"])) < 1e-6
+    for i, k in enumerate(port.CRITIC_KEYS):
+        ref = g[f"g_{i}"]
+        got = grads[k] if grads[k].numel() <= 8192 else grads[k].flatten()[::97]
+        np.testing.assert_allclose(got.numpy().reshape(ref.shape), ref, rtol=1e-5, atol=1e-7, err_msg=k)
+        assert abs(float(grads[k].norm()) - float(g[f"gnorm_{i}"])) <= 1e-5 * max(1.0, float(g[f"gnorm_{i}"]))
+
+
+def test_c51_projection_edge_cases():
+    """done rows collapse onto the reward atom; integer positions put all mass on one atom; out-of-range targets
+    clamp to the end atoms."""
+    atoms = 51
+    nd = torch.full((4, atoms), 1.0 / atoms)
+    reward = torch.tensor([[1.0], [7.0], [-3.0], [0.25]])
+    done = torch.tensor([[1.0], [1.0], [1.0], [1.0]])
+    pr = port.c51_projection(nd, reward, done, 0.99)
+    assert abs(pr[0, 10].item() - 1.0) < 1e-5                  # 1.0 / 0.1 = atom 10 exactly
+    assert abs(pr[1, 50].item() - 1.0) < 1e-5                  # clamped to v_max
+    assert abs(pr[2, 0].item() - 1.0) < 1e-5                   # clamped to v_min
+    assert abs(pr[3, 2].item() - 0.5) < 1e-4 and abs(pr[3, 3].item() - 0.5) < 1e-4
+    np.testing.assert_allclose(pr.sum(1).numpy(), 1.0, atol=1e-5)

@@ -304,3 +304,95 @@ def test_noise_epilogue_matches_reference_fixture():
     g = load_golden("n3_noise")
     a, z = torch.from_numpy(g["a"]), torch.from_numpy(g["z"])
     assert torch.equal(port.add_noise_to_actions(a, z, 0.05, 0.8), torch.from_numpy(g["mixed"]))
+
+
+# ------------------------------------------------------------------------------------------ N1
+def _critic_pair(g=None, seeds=(41, 42), scale=1.5):
+    p, pt = port.init_critic_params(seeds[0], scale=scale), port.init_critic_params(seeds[1], scale=scale)
+    if g is not None:
+        from tests.util import checksum
+        np.testing.assert_allclose(checksum(p, port.CRITIC_KEYS), g["checksum"], rtol=1e-12)
+        np.testing.assert_allclose(checksum(pt, port.CRITIC_KEYS), g["checksum_t"], rtol=1e-12)
+    return p, pt
+
+
+def _flat_to_named(flat, params):
+    out, off = {}, 0
+    for k in port.CRITIC_KEYS:
+        n = params[k].numel()
+        out[k] = flat[off:off + n].view(params[k].shape).cpu()
+        off += n
+    assert off == flat.numel()
+    return out
+
+
+def _rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-12)).item()
+
+
+def test_critic_update_matches_reference_fixture():
+    """Loss and all 16 gradients of update_critic (ddiffpg.py:322-349) against the reference's autograd."""
+    from ddiffpg_b200 import critic_loss_and_grads
+    g = load_golden("n1_critic")
+    p, pt = _critic_pair(g)
+    critic, target = make_critic(p), make_critic(pt)
+    loss, flat = critic_loss_and_grads(critic, target, _dev(g["obs"]), _dev(g["act"]), _dev(g["nobs"]),
+                                       _dev(g["nact"]), _dev(g["reward"]), _dev(g["done"]), float(g["gamma"]))
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * max(1.0, abs(float(g["loss"])))
+    named = _flat_to_named(flat, p)
+    for i, k in enumerate(port.CRITIC_KEYS):
+        ref = torch.from_numpy(g[f"g_{i}"])
+        got = named[k] if named[k].numel() <= 8192 else named[k].flatten()[::97]
+        assert _rel_l2(got.reshape(ref.shape), ref) <= 1e-4, k
+        assert abs(float(named[k].norm()) - float(g[f"gnorm_{i}"])) <= 1e-4 * float(g[f"gnorm_{i}"]) + 1e-8, k
+
+
+@pytest.mark.parametrize("B", [1, 7, 512, 3000])
+def test_critic_update_vs_oracle_batches(B):
+    from ddiffpg_b200 import critic_loss_and_grads
+    p, pt = _critic_pair(seeds=(51, 52), scale=1.2)
+    gen = torch.Generator().manual_seed(600 + B)
+    obs, nobs = torch.randn(B, 29, generator=gen), torch.randn(B, 29, generator=gen)
+    act, nact = torch.rand(B, 8, generator=gen) * 2 - 1, torch.rand(B, 8, generator=gen) * 2 - 1
+    reward = torch.rand(B, 1, generator=gen) * 3.0
+    reward[::5] = 0.0
+    done = (torch.rand(B, 1, generator=gen) < 0.25).float()
+    tq = port.critic_target_dist(pt, nobs, nact, reward, done, 0.97)
+    # rows whose clamped mass rounds to 1 + 1ulp make F.binary_cross_entropy raise (in the reference too): drop them
+    keep = tq.max(1).values <= 1.0
+    obs, nobs, act, nact, reward, done, tq = (x[keep] for x in (obs, nobs, act, nact, reward, done, tq))
+    assert keep.float().mean() > 0.9
+    l_ref, g_ref = port.critic_loss_and_grads(p, tq, obs, act)
+    loss, flat = critic_loss_and_grads(make_critic(p), make_critic(pt), _dev(obs), _dev(act), _dev(nobs), _dev(nact),
+                                       _dev(reward), _dev(done), 0.97)
+    assert abs(loss.item() - l_ref.item()) <= 1e-5 * max(1.0, abs(l_ref.item()))
+    named = _flat_to_named(flat, p)
+    for k in port.CRITIC_KEYS:
+        assert _rel_l2(named[k], g_ref[k]) <= 1e-4, (k, _rel_l2(named[k], g_ref[k]))
+
+
+def test_update_critic_matches_reference_optimizer_step():
+    """Whole update_critic: loss -> backward -> clip_grad_norm_ -> AdamW, against torch on the port's gradients."""
+    from ddiffpg_b200 import update_critic
+    p, pt = _critic_pair(seeds=(61, 62), scale=1.0)
+    gen = torch.Generator().manual_seed(77)
+    B = 256
+    obs, nobs = torch.randn(B, 29, generator=gen), torch.randn(B, 29, generator=gen)
+    act, nact = torch.rand(B, 8, generator=gen) * 2 - 1, torch.rand(B, 8, generator=gen) * 2 - 1
+    reward, done = torch.rand(B, 1, generator=gen), (torch.rand(B, 1, generator=gen) < 0.2).float()
+    critic, target = make_critic(p), make_critic(pt)
+    opt = torch.optim.AdamW(critic.parameters(), lr=5e-4)
+    ref = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    ropt = torch.optim.AdamW([ref[k] for k in port.CRITIC_KEYS], lr=5e-4)
+    for _ in range(3):
+        _, loss, gnorm = update_critic(critic, target, opt, _dev(obs), _dev(act), _dev(reward), _dev(nobs), _dev(nact),
+                                       _dev(done), gamma_n=0.99 ** 3, max_grad_norm=1.0)
+        tq = port.critic_target_dist(pt, nobs, nact, reward, done, 0.99 ** 3).clamp_max(1.0)
+        l_ref, g_ref = port.critic_loss_and_grads({k: v.detach() for k, v in ref.items()}, tq, obs, act)
+        for k in port.CRITIC_KEYS:
+            ref[k].grad = g_ref[k].clone()
+        n_ref = torch.nn.utils.clip_grad_norm_([ref[k] for k in port.CRITIC_KEYS], 1.0)
+        ropt.step()
+        assert abs(loss - l_ref.item()) <= 2e-5 * max(1.0, abs(l_ref.item()))
+        assert abs(gnorm - n_ref.item()) <= 1e-4 * n_ref.item()
+    _assert_params_after_adam(critic, {k: v.detach() for k, v in ref.items()}, steps=3, lr=5e-4)
