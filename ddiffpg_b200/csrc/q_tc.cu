@@ -9,13 +9,28 @@
 // Per ascent iteration: 2 nets x 4 forward GEMMs, one softmax/selection kernel, 2 nets x 4 backward GEMMs (ELU
 // derivative fused in the epilogue, from the stored activation), one gradient/norm kernel, one Adam kernel.
 #include <math.h>
+#include <stdlib.h>
 #include "q_layout.cuh"
 #include "tc_gemm.cuh"
 
 namespace ddp {
+
+// fused per-tile forward/backward chain (csrc/q_chain_tc.cu)
+bool q_chain_shape_ok(const QLayout& L);
+size_t q_chain_workspace(const QLayout& L);
+int q_chain_pass(const QLayout& L, const void* packed, const int64_t* seg_off, const float* scale, const float* obs,
+                 const float* act, float* g_out, float* gsq, float* qmin, float* p1, float* p2, long B, void* scratch,
+                 size_t scratch_bytes, cudaStream_t st);
+
 namespace {
 
 using bf16 = __nv_bfloat16;
+
+// DDP_Q_NO_CHAIN=1 selects the layer-by-layer GEMM path even where the fused kernel applies (A/B measurements)
+bool use_chain(const QLayout& L) {
+    static const bool off = getenv("DDP_Q_NO_CHAIN") && atoi(getenv("DDP_Q_NO_CHAIN")) != 0;
+    return !off && q_chain_shape_ok(L);
+}
 
 struct QSeg {
     long off[kMaxModes + 1];
@@ -26,6 +41,7 @@ struct QSeg {
 struct QTcWs {
     bf16 *xin, *a1[2], *a2[2], *a3[2], *dl[2];
     float *logits[2], *ga[2], *g, *m1, *m2, *gsq, *abs_sum;
+    void* chain_scratch;
     size_t total, adam_bytes;
 };
 
@@ -33,8 +49,10 @@ QTcWs carve(const QLayout& L, long B, int iters, uint8_t* base) {
     QTcWs w{};
     size_t o = 0;
     auto take = [&](size_t bytes) { uint8_t* r = base ? base + o : nullptr; o += (bytes + 255) / 256 * 256; return r; };
-    w.xin = (bf16*)take((size_t)B * 64 * 2);
-    for (int j = 0; j < 2; ++j) {
+    const bool chain = use_chain(L);
+    if (chain) w.chain_scratch = take(q_chain_workspace(L));
+    if (!chain) w.xin = (bf16*)take((size_t)B * 64 * 2);
+    for (int j = 0; j < 2 && !chain; ++j) {
         w.a1[j] = (bf16*)take((size_t)B * L.h1 * 2);
         w.a2[j] = (bf16*)take((size_t)B * L.h2 * 2);
         w.a3[j] = (bf16*)take((size_t)B * L.h3 * 2);
@@ -67,7 +85,7 @@ __global__ void q_tc_prep_kernel(const float* __restrict__ obs, float* __restric
         v = act[row * A + c - O];
         if (clamp_lim > 0.f) { v = fminf(fmaxf(v, -clamp_lim), clamp_lim); act[row * A + c - O] = v; }
     }
-    xin[row * 64 + c] = __float2bfloat16(v);
+    if (xin) xin[row * 64 + c] = __float2bfloat16(v);
 }
 
 // One warp per row: softmax over atoms of both nets, expectations, min / selection, d min(Q1,Q2) / d logits.
@@ -148,7 +166,7 @@ __global__ void q_tc_adam_kernel(QSeg seg, int O, int A, float* __restrict__ act
     float v = act[i] - step_size * (ea / (sqrtf(ev) / bc2_sqrt + eps));
     v = fminf(fmaxf(v, -lim), lim);
     act[i] = v;
-    xin[row * 64 + O + c] = __float2bfloat16(v);
+    if (xin) xin[row * 64 + O + c] = __float2bfloat16(v);
 }
 
 __global__ void q_tc_abs_kernel(QSeg seg, int A, const float* __restrict__ act, long n_elems, float* __restrict__ abs_sum) {
@@ -280,6 +298,9 @@ int q_forward_tc(const QLayout& L, const void* packed, const int64_t* seg_off, c
     if (!shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 critic path does not support this shape");
     if (!ws || ws_bytes < carve(L, B, 0, nullptr).total) DDP_FAIL(DDP_ERR_ARG, "critic tensor path: workspace too small");
     QTcWs w = carve(L, B, 0, (uint8_t*)ws);
+    if (use_chain(L))
+        return q_chain_pass(L, packed, seg_off, nullptr, obs, act, dq_da, nullptr, qmin, p1, p2, B, w.chain_scratch,
+                            q_chain_workspace(L), st);
     QSeg seg = make_seg(L, seg_off, nullptr);
     const unsigned eb = (unsigned)((B * 64 + 255) / 256);
     q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, const_cast<float*>(act), L.O, L.A, B, 0.f, w.xin);
@@ -304,11 +325,20 @@ int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, co
     const unsigned eb = (unsigned)((B * 64 + 255) / 256), nb = (unsigned)((n + 255) / 256);
     DDP_CUDA_CHECK(cudaMemsetAsync(w.m1, 0, w.adam_bytes, st));          // fresh Adam state, zeroed reductions
     q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, action, L.O, L.A, B, lim, w.xin);
+    const bool chain = use_chain(L);
+    float neg_inv[kMaxModes];
+    for (int m = 0; m < L.n_modes; ++m) neg_inv[m] = -seg.inv_cnt[m];
     for (int it = 0; it < iters; ++it) {
-        int rc = q_tc_pass(L, (const uint8_t*)packed, w, seg, B, true, nullptr, nullptr, nullptr, st);
-        if (rc != DDP_OK) return rc;
         float* gsq = w.gsq + (size_t)it * kMaxModes;
-        q_tc_grad_kernel<<<nb, 256, 0, st>>>(seg, w.ga[0], w.ga[1], L.A, n, 1, w.g, gsq);
+        if (chain) {
+            int rc = q_chain_pass(L, packed, seg_off, neg_inv, obs, action, w.g, gsq, nullptr, nullptr, nullptr, B,
+                                  w.chain_scratch, q_chain_workspace(L), st);
+            if (rc != DDP_OK) return rc;
+        } else {
+            int rc = q_tc_pass(L, (const uint8_t*)packed, w, seg, B, true, nullptr, nullptr, nullptr, st);
+            if (rc != DDP_OK) return rc;
+            q_tc_grad_kernel<<<nb, 256, 0, st>>>(seg, w.ga[0], w.ga[1], L.A, n, 1, w.g, gsq);
+        }
         const int step = it + 1;
         const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
         q_tc_adam_kernel<<<nb, 256, 0, st>>>(seg, L.O, L.A, action, w.g, w.m1, w.m2, gsq, gnorm_out, it, iters,

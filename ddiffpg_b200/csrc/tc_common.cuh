@@ -219,20 +219,46 @@ __device__ __forceinline__ void ex2_pair_f16(float t0, float t1, float& e0, floa
     const float2 f = __half22float2(*reinterpret_cast<__half2*>(&v));
     e0 = f.x; e1 = f.y;
 }
-template <int N, bool HALF_EX2 = false>
+// RCPG = 2 or 4: one MUFU.RCP serves RCPG elements -- 1/a and 1/b from r = rcp(a*b) as r*b and r*a (extra FMULs run
+// on the wide FMA pipe, the 16-lane MUFU pipe is what the Mish epilogues saturate).  The exponent cap at x = 11
+// keeps the product of four (e^x+1)^2+1 terms below 2^128; mish(x) == x to fp32 precision beyond it.
+#ifndef DDP_MISH_RCPG
+#define DDP_MISH_RCPG 2
+#endif
+template <int N, bool HALF_EX2 = false, int RCPG = DDP_MISH_RCPG>
 __device__ __forceinline__ void mish_fast_n(float (&x)[N]) {
     float s[N];
+    constexpr float kCap = (HALF_EX2 || RCPG > 1) ? 15.87f : 28.853900817779268f;
     if (HALF_EX2) {
-        // cap at x = 11: mish(x) == x to 1e-9 there, and exp(x) still fits fp16
 #pragma unroll
         for (int i = 0; i < N; i += 2)
-            ex2_pair_f16(fminf(x[i] * 1.4426950408889634f, 15.87f), fminf(x[i + 1] * 1.4426950408889634f, 15.87f), s[i], s[i + 1]);
+            ex2_pair_f16(fminf(x[i] * 1.4426950408889634f, kCap), fminf(x[i + 1] * 1.4426950408889634f, kCap), s[i], s[i + 1]);
     } else {
 #pragma unroll
-        for (int i = 0; i < N; ++i) s[i] = ex2_approx(fminf(x[i] * 1.4426950408889634f, 28.853900817779268f));
+        for (int i = 0; i < N; ++i) s[i] = ex2_approx(fminf(x[i] * 1.4426950408889634f, kCap));
     }
 #pragma unroll
-    for (int i = 0; i < N; ++i) { const float u = s[i] + 1.f; s[i] = rcp_approx(fmaf(u, u, 1.f)); }
+    for (int i = 0; i < N; ++i) { const float u = s[i] + 1.f; s[i] = fmaf(u, u, 1.f); }
+    if (RCPG == 4) {
+#pragma unroll
+        for (int i = 0; i < N; i += 4) {
+            const float p01 = s[i] * s[i + 1], p23 = s[i + 2] * s[i + 3];
+            const float r = rcp_approx(p01 * p23);
+            const float r01 = r * p23, r23 = r * p01;
+            const float r0 = r01 * s[i + 1], r1 = r01 * s[i], r2 = r23 * s[i + 3], r3 = r23 * s[i + 2];
+            s[i] = r0; s[i + 1] = r1; s[i + 2] = r2; s[i + 3] = r3;
+        }
+    } else if (RCPG == 2) {
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            const float r = rcp_approx(s[i] * s[i + 1]);
+            const float r0 = r * s[i + 1], r1 = r * s[i];
+            s[i] = r0; s[i + 1] = r1;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) s[i] = rcp_approx(s[i]);
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = fmaf(-2.f * x[i], s[i], x[i]);
 }
