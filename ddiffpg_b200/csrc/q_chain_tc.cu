@@ -22,6 +22,7 @@
 // Weight tiles stream from L2 through a 3-stage TMA ring; all K+1 critics live in the same tensor maps (row
 // offset = mode * N), a tile never straddles a mode segment.
 #include <stdlib.h>
+#include <type_traits>
 #include "q_layout.cuh"
 #include "tc_common.cuh"
 
@@ -49,14 +50,12 @@ constexpr int kTmemCols = 512;
 constexpr int kBiasPerNet = 512 + 256 + 256 + 64;     // b1 | b2 | b3 | b4 slots (floats)
 constexpr float kLog2e = 1.4426950408889634f;
 
-struct alignas(64) QcMaps { CUtensorMap fwd[2][4]; CUtensorMap bwd[2][4]; };
+struct alignas(64) QcMaps { CUtensorMap fwd[2][4]; CUtensorMap bwd[2][4]; CUtensorMap xin; };
 
 struct QcArgs {
     const float* pk;                 // fp32 section of the packed critics (biases)
     size_t mode_stride;
     size_t b_off[2][4];
-    const float* obs;
-    const float* act;
     float* g_out;                    // [B, A]  scale * d qmin / d action           (NULL: no backward)
     float* gsq;                      // [n_modes] += sum g^2 over the segment       (may be NULL)
     float* qmin;                     // [B]                                          (may be NULL)
@@ -91,6 +90,8 @@ __device__ __forceinline__ uint32_t qb_acc_full(uint32_t b, int i) { return b + 
 __device__ __forceinline__ uint32_t qb_lo_free(uint32_t b) { return b + 8 * (2 * kStages + 2 * kASlots + 2); }
 __device__ __forceinline__ uint32_t qb_dl_full(uint32_t b) { return b + 8 * (2 * kStages + 2 * kASlots + 3); }
 __device__ __forceinline__ uint32_t qb_a0_full(uint32_t b) { return b + 8 * (2 * kStages + 2 * kASlots + 4); }
+__device__ __forceinline__ uint32_t qb_a0_free(uint32_t b) { return b + 8 * (2 * kStages + 2 * kASlots + 5); }
+__device__ __forceinline__ uint32_t qb_acc_free(uint32_t b) { return b + 8 * (2 * kStages + 2 * kASlots + 6); }
 
 __device__ __forceinline__ void q_epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
@@ -293,7 +294,9 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
         mbar_init(qb_acc_full(bars, 1), 1);
         mbar_init(qb_lo_free(bars), kEpiWarps);
         mbar_init(qb_dl_full(bars), 4);
-        mbar_init(qb_a0_full(bars), kEpiWarps);
+        mbar_init(qb_a0_full(bars), 1);
+        mbar_init(qb_a0_free(bars), 1);
+        mbar_init(qb_acc_free(bars), kEpiWarps);
         fence_barrier_init();
     }
     if (warp == kEpiWarps + 1) tmem_alloc(base + SMQ::tmem_ptr, kTmemCols);
@@ -314,6 +317,17 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                 tma_load_2d(base + SMQ::wring + ws.idx * kStageBytes, m, qb_w_full(bars, ws.idx), x, y);
                 ws.advance(kStages);
             };
+            tma_prefetch_desc(&maps.xin);
+            // the [obs | act | 0] rows of a tile: one 16 KB box into the dedicated buffer, fetched one tile ahead
+            uint32_t a0_free_phase = 0;
+            auto load_input = [&](int tile, bool first) {
+                if (!first) { mbar_wait(qb_a0_free(bars), a0_free_phase); a0_free_phase ^= 1; }
+                const int m = q_mode_of(a, tile);
+                const long row0 = a.seg_off[m] + (long)(tile - a.tile_off[m]) * kRows;
+                mbar_expect_tx(qb_a0_full(bars), kChunkBytes);
+                tma_load_2d(base + SMQ::a0, &maps.xin, qb_a0_full(bars), 0, (int)row0);
+            };
+            load_input(blockIdx.x, true);
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
                 const int m = q_mode_of(a, tile);
                 for (int j = 0; j < 2; ++j) {
@@ -322,6 +336,8 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                     for (int c = 0; c < NC2; ++c) load(&maps.fwd[j][2], c * 64, m * a.h3, a.h3);
                     for (int c = 0; c < NC3; ++c) load(&maps.fwd[j][3], c * 64, m * 64, 64);
                 }
+                // both first layers of this tile have been issued long ago: their input buffer can take the next tile
+                if (tile + (int)gridDim.x < a.num_tiles) load_input(tile + (int)gridDim.x, false);
                 if (!backward) continue;
                 for (int j = 0; j < 2; ++j) {
                     load(&maps.bwd[j][0], 0, m * a.h3, a.h3);
@@ -340,7 +356,7 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
         // ============================================================== MMA issuer (one lane)
         if (lane == 0) {
             QRing ws, as;
-            uint32_t lo_phase = 0, dl_phase = 0, a0_phase = 0, acc_cnt = 0;
+            uint32_t lo_phase = 0, dl_phase = 0, a0_phase = 0, free_phase = 0, acc_cnt = 0;
             const uint32_t id_p1 = make_idesc_bf16(kRows, a.part1), id_h2 = make_idesc_bf16(kRows, a.h2),
                            id_h3 = make_idesc_bf16(kRows, a.h3), id_64 = make_idesc_bf16(kRows, 64),
                            id_16 = make_idesc_bf16(kRows, 16);
@@ -373,13 +389,16 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
             };
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
                 for (int j = 0; j < 2; ++j) {
-                    // j == 0: the tile's input chunk is built; j == 1: the logits of net 0 have left the accumulator
-                    mbar_wait(qb_a0_full(bars), a0_phase);
-                    a0_phase ^= 1;
+                    // the epilogue warps have read everything they need from the accumulator columns (j == 0: the
+                    // previous tile's action gradient; j == 1: the logits of net 0)
+                    mbar_wait(qb_acc_free(bars), free_phase);
+                    free_phase ^= 1;
+                    if (j == 0) { mbar_wait(qb_a0_full(bars), a0_phase); a0_phase ^= 1; }
                     tc_fence_after();
                     {   // F1: the tile's input chunk against the column parts of W1
                         const uint64_t ad = make_smem_desc_sw128(base + SMQ::a0);
                         for (int p = 0; p < a.nparts1; ++p) mma_w(p * a.part1, ad, id_p1, true);
+                        if (j == 1) umma_commit(qb_a0_free(bars));
                         acc_done();
                     }
                     lo_wait();                      // columns [0, h2) of the F1 accumulator are drained
@@ -432,6 +451,7 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
         long long tk0 = prof ? clock64() : 0, tk1;
 #define QC_TICK(slot) do { if (prof) { tk1 = clock64(); a.dbg[slot] += tk1 - tk0; tk0 = tk1; } } while (0)
         int cur_mode = -1;
+        if (lane == 0) mbar_arrive(qb_acc_free(bars));          // nothing to drain before the first tile
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
             const int m = q_mode_of(a, tile);
             const long row = a.seg_off[m] + (long)(tile - a.tile_off[m]) * kRows + e.my_row;
@@ -448,41 +468,6 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                 }
                 q_epi_bar_sync();
                 cur_mode = m;
-            }
-            {   // input chunk [obs | act | 0] of the tile (both nets read it): zero, then scatter the contiguous
-                // obs / act row blocks with coalesced loads.  The previous tile's F1 MMAs are complete (their
-                // accumulators were drained), so the buffer is free.
-                uint8_t* a0 = smem + SMQ::a0;
-                const long row0 = a.seg_off[m] + (long)(tile - a.tile_off[m]) * kRows;
-                const long left = a.seg_off[m + 1] - row0;
-                const int nv = left < kRows ? (int)left : kRows;
-                for (int i = threadIdx.x; i < kChunkBytes / 16; i += kEpiThreads) reinterpret_cast<uint4*>(a0)[i] = make_uint4(0, 0, 0, 0);
-                q_epi_bar_sync();
-                // batches of 8 independent loads per thread: one L2 latency per batch instead of one per element
-                auto scatter = [&](const float* src, int ncol, int col0) {
-                    const int total = nv * ncol;
-                    for (int b0 = 0; b0 < total; b0 += kEpiThreads * 8) {
-                        float v[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int i = b0 + u * kEpiThreads + (int)threadIdx.x;
-                            v[u] = i < total ? __ldg(src + i) : 0.f;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int i = b0 + u * kEpiThreads + (int)threadIdx.x;
-                            if (i < total) {
-                                const int r = i / ncol, c = i - r * ncol;
-                                *reinterpret_cast<__nv_bfloat16*>(a0 + sw128_offset(r, col0 + c)) = __float2bfloat16(v[u]);
-                            }
-                        }
-                    }
-                };
-                scatter(a.obs + row0 * a.O, a.O, 0);
-                scatter(a.act + row0 * a.A, a.A, a.O);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(qb_a0_full(bars));
             }
             float qv[2] = {0.f, 0.f};
             for (int j = 0; j < 2; ++j) {
@@ -522,7 +507,7 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                     // the accumulator columns are free again: the MMA warp may start the next net's first layer
                     tc_fence_before();
                     __syncwarp();
-                    if (j == 0 && lane == 0) mbar_arrive(qb_a0_full(bars));
+                    if ((j == 0 || !backward) && lane == 0) mbar_arrive(qb_acc_free(bars));
                     float mx4[4] = {l[0], l[1], l[2], l[3]};
 #pragma unroll
                     for (int i = 4; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], l[i]);
@@ -559,7 +544,7 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                     tc_fence_before();
                 } else {
                     ++e.acc_cnt;                   // the logits stage is read by the ch == 0 warps only
-                    if (j == 0 && lane == 0) mbar_arrive(qb_a0_full(bars));
+                    if ((j == 0 || !backward) && lane == 0) mbar_arrive(qb_acc_free(bars));
                 }
                 QC_TICK(5);
             }
@@ -613,8 +598,11 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) da[i] += __uint_as_float(v[i]);
                     tc_fence_before();
+                    __syncwarp();
+                    if (j == 1 && lane == 0) mbar_arrive(qb_acc_free(bars));     // the next tile may overwrite the columns
                 } else {
                     ++e.acc_cnt;
+                    if (j == 1 && lane == 0) mbar_arrive(qb_acc_free(bars));
                 }
                 QC_TICK(9);
             }
@@ -671,10 +659,10 @@ size_t q_chain_workspace(const QLayout& L) {
     return (size_t)160 * 2 * ((L.h1 + L.h2 + L.h3) / 16) * kRows * 16 * 2;
 }
 
-// One pass over all rows.  g_out != NULL: backward to the action, g_out = scale[m] * d qmin / d action and
+// One pass over all rows; xin = [B][64] bf16 rows [obs | action | 0].  g_out != NULL: backward to the action, g_out = scale[m] * d qmin / d action and
 // gsq[m] += sum over the segment of g^2 (gsq may be NULL).  qmin / p1 / p2 optional.
-int q_chain_pass(const QLayout& L, const void* packed, const int64_t* seg_off, const float* scale, const float* obs,
-                 const float* act, float* g_out, float* gsq, float* qmin, float* p1, float* p2, long B, void* scratch,
+int q_chain_pass(const QLayout& L, const void* packed, const int64_t* seg_off, const float* scale, const void* xin,
+                 float* g_out, float* gsq, float* qmin, float* p1, float* p2, long B, void* scratch,
                  size_t scratch_bytes, cudaStream_t st) {
     if (!q_chain_shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "fused critic kernel does not support this shape");
     if (!scratch || scratch_bytes < q_chain_workspace(L)) DDP_FAIL(DDP_ERR_ARG, "fused critic kernel: scratch too small");
@@ -685,7 +673,7 @@ int q_chain_pass(const QLayout& L, const void* packed, const int64_t* seg_off, c
     for (int j = 0; j < 2; ++j) {
         a.b_off[j][0] = L.net[j].b1; a.b_off[j][1] = L.net[j].b2; a.b_off[j][2] = L.net[j].b3; a.b_off[j][3] = L.net[j].b4;
     }
-    a.obs = obs; a.act = act; a.g_out = g_out; a.gsq = gsq; a.qmin = qmin; a.p_out[0] = p1; a.p_out[1] = p2;
+    a.g_out = g_out; a.gsq = gsq; a.qmin = qmin; a.p_out[0] = p1; a.p_out[1] = p2;
     a.dscr = (uint16_t*)scratch;
     a.n_modes = L.n_modes;
     for (int m = 0; m <= L.n_modes; ++m) a.seg_off[m] = seg_off[m];
@@ -711,6 +699,7 @@ int q_chain_pass(const QLayout& L, const void* packed, const int64_t* seg_off, c
         bad |= make_tmap_bf16_sw128(&maps.bwd[j][2], pb + L.tc_bwd[j][2], M * L.h1, L.h2, a.part1);
         bad |= make_tmap_bf16_sw128(&maps.bwd[j][3], pb + L.tc_bwd[j][3], M * 16, L.h1, 16);
     }
+    bad |= make_tmap_bf16_sw128(&maps.xin, xin, (uint64_t)B, 64, kRows);        // rows past B read as zeros
     if (bad) DDP_FAIL(DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the critic weight tiles");
     int dev = 0, sms = 0;
     DDP_CUDA_CHECK(cudaGetDevice(&dev));

@@ -18,8 +18,8 @@ namespace ddp {
 // fused per-tile forward/backward chain (csrc/q_chain_tc.cu)
 bool q_chain_shape_ok(const QLayout& L);
 size_t q_chain_workspace(const QLayout& L);
-int q_chain_pass(const QLayout& L, const void* packed, const int64_t* seg_off, const float* scale, const float* obs,
-                 const float* act, float* g_out, float* gsq, float* qmin, float* p1, float* p2, long B, void* scratch,
+int q_chain_pass(const QLayout& L, const void* packed, const int64_t* seg_off, const float* scale, const void* xin,
+                 float* g_out, float* gsq, float* qmin, float* p1, float* p2, long B, void* scratch,
                  size_t scratch_bytes, cudaStream_t st);
 
 namespace {
@@ -51,7 +51,7 @@ QTcWs carve(const QLayout& L, long B, int iters, uint8_t* base) {
     auto take = [&](size_t bytes) { uint8_t* r = base ? base + o : nullptr; o += (bytes + 255) / 256 * 256; return r; };
     const bool chain = use_chain(L);
     if (chain) w.chain_scratch = take(q_chain_workspace(L));
-    if (!chain) w.xin = (bf16*)take((size_t)B * 64 * 2);
+    w.xin = (bf16*)take((size_t)B * 64 * 2);
     for (int j = 0; j < 2 && !chain; ++j) {
         w.a1[j] = (bf16*)take((size_t)B * L.h1 * 2);
         w.a2[j] = (bf16*)take((size_t)B * L.h2 * 2);
@@ -298,12 +298,12 @@ int q_forward_tc(const QLayout& L, const void* packed, const int64_t* seg_off, c
     if (!shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 critic path does not support this shape");
     if (!ws || ws_bytes < carve(L, B, 0, nullptr).total) DDP_FAIL(DDP_ERR_ARG, "critic tensor path: workspace too small");
     QTcWs w = carve(L, B, 0, (uint8_t*)ws);
-    if (use_chain(L))
-        return q_chain_pass(L, packed, seg_off, nullptr, obs, act, dq_da, nullptr, qmin, p1, p2, B, w.chain_scratch,
-                            q_chain_workspace(L), st);
     QSeg seg = make_seg(L, seg_off, nullptr);
     const unsigned eb = (unsigned)((B * 64 + 255) / 256);
     q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, const_cast<float*>(act), L.O, L.A, B, 0.f, w.xin);
+    if (use_chain(L))
+        return q_chain_pass(L, packed, seg_off, nullptr, w.xin, dq_da, nullptr, qmin, p1, p2, B, w.chain_scratch,
+                            q_chain_workspace(L), st);
     int rc = q_tc_pass(L, (const uint8_t*)packed, w, seg, B, dq_da != nullptr, qmin, p1, p2, st);
     if (rc != DDP_OK) return rc;
     if (dq_da) {
@@ -331,7 +331,7 @@ int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, co
     for (int it = 0; it < iters; ++it) {
         float* gsq = w.gsq + (size_t)it * kMaxModes;
         if (chain) {
-            int rc = q_chain_pass(L, packed, seg_off, neg_inv, obs, action, w.g, gsq, nullptr, nullptr, nullptr, B,
+            int rc = q_chain_pass(L, packed, seg_off, neg_inv, w.xin, w.g, gsq, nullptr, nullptr, nullptr, B,
                                   w.chain_scratch, q_chain_workspace(L), st);
             if (rc != DDP_OK) return rc;
         } else {
