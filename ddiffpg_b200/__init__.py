@@ -8,7 +8,8 @@ from .models import DiffusionPolicy, DistributionalDoubleQ, DiffusionNet, MLPNet
 from .algo import (FusedActorTrainer, HotPathMixin, critic_loss_and_grads, get_actions,  # noqa: F401
                    get_tgt_policy_actions, update_critic,
                    optimizer_update, q_action_ascent_segments, soft_update, update_actor, update_target_action)
+from .intrinsic import IntrinsicM, RNDModel, RunningMeanStd  # noqa: F401
 
-__all__ = ["DiffusionPolicy", "DistributionalDoubleQ", "DiffusionNet", "MLPNet", "FusedActorTrainer",
+__all__ = ["IntrinsicM", "RNDModel", "RunningMeanStd", "DiffusionPolicy", "DistributionalDoubleQ", "DiffusionNet", "MLPNet", "FusedActorTrainer",
            "HotPathMixin", "critic_loss_and_grads", "update_critic", "get_actions", "get_tgt_policy_actions", "optimizer_update", "q_action_ascent_segments", "soft_update", "update_actor",
            "update_target_action"]

@@ -22,6 +22,10 @@ class QShape(Structure):
                 ("n_modes", c_int), ("hid1", c_int), ("hid2", c_int), ("hid3", c_int)]
 
 
+class RndShape(Structure):
+    _fields_ = [("D", c_int), ("F", c_int), ("hid1", c_int), ("hid2", c_int), ("hid3", c_int)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/ddiffpg_b200.h
 PROTOTYPES = {
     "ddp_abi_version": (c_int, []),
@@ -54,6 +58,13 @@ PROTOTYPES = {
     "ddp_q_critic_loss_fwd_bwd": (c_int, [POINTER(QShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_long, c_int, c_void_p,
                                           c_size_t, c_void_p]),
+    "ddp_rnd_packed_bytes": (c_size_t, [POINTER(RndShape)]),
+    "ddp_rnd_pack": (c_int, [POINTER(RndShape), POINTER(c_void_p), c_void_p, c_void_p]),
+    "ddp_rnd_novelty": (c_int, [POINTER(RndShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p]),
+    "ddp_rnd_grad_count": (c_size_t, [POINTER(RndShape)]),
+    "ddp_rnd_train_workspace_bytes": (c_size_t, [POINTER(RndShape), c_long]),
+    "ddp_rnd_loss_fwd_bwd": (c_int, [POINTER(RndShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long,
+                                     c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

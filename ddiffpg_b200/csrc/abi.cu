@@ -54,6 +54,13 @@ int q_critic_train_fma(const QLayout& L, const float* pk, const float* pk_target
                        const float* next_obs, const float* next_act, const float* reward, const float* done, float gamma,
                        float* loss_out, float* grads, long B, void* ws, size_t ws_bytes, cudaStream_t st);
 
+size_t rnd_grad_count(const QLayout& L);
+size_t rnd_train_workspace(const QLayout& L, long B);
+int rnd_novelty_fma(const QLayout& L, const float* pk, const float* x, float* novelty, float* pred, float* target,
+                    long B, cudaStream_t st);
+int rnd_train_fma(const QLayout& L, const float* pk, const float* x, float* loss_out, float* grads, float* novelty,
+                  long B, void* ws, size_t ws_bytes, cudaStream_t st);
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace ddp
@@ -265,6 +272,69 @@ int ddp_q_critic_loss_fwd_bwd(const ddp_q_shape* s, const void* packed, const vo
     return q_critic_train_fma(make_q_layout(*s, precision), (const float*)packed, (const float*)packed_target, obs,
                               action, next_obs, next_action, reward, done, gamma_n, loss_out, grads_flat, B, ws,
                               ws_bytes, (cudaStream_t)stream);
+}
+
+// RNDModel as a two-net pack: O = D, no action columns, atoms = F, net 0 = predictor, net 1 = target
+static int rnd_layout(const ddp_rnd_shape* s, QLayout* L) {
+    if (!s) DDP_FAIL(DDP_ERR_ARG, "RND shape is NULL");
+    if (s->D <= 0 || s->D > 512 || s->F < 4 || s->F > 256 || s->F % 4)
+        DDP_FAIL(DDP_ERR_SHAPE, "RND shape: need 0<D<=512 and F a multiple of 4 in [4,256] (got D=%d F=%d)", s->D, s->F);
+    if (s->hid1 <= 0 || s->hid2 <= 0 || s->hid3 <= 0 || s->hid1 % 4 || s->hid2 % 4 || s->hid3 % 4 || s->hid1 > 1024 ||
+        s->hid2 > 1024 || s->hid3 > 1024)
+        DDP_FAIL(DDP_ERR_SHAPE, "RND shape: hidden widths must be multiples of 4 in (0,1024]");
+    ddp_q_shape q{};
+    q.O = s->D; q.A = 0; q.atoms = s->F; q.v_min = 0.f; q.v_max = 1.f; q.n_modes = 1;
+    q.hid1 = s->hid1; q.hid2 = s->hid2; q.hid3 = s->hid3;
+    *L = make_q_layout(q, DDP_FP32);
+    return DDP_OK;
+}
+
+size_t ddp_rnd_packed_bytes(const ddp_rnd_shape* s) {
+    QLayout L;
+    return rnd_layout(s, &L) == DDP_OK ? L.total_bytes : 0;
+}
+
+int ddp_rnd_pack(const ddp_rnd_shape* s, const float* const params[16], void* packed, void* stream) {
+    QLayout L;
+    int rc = rnd_layout(s, &L);
+    if (rc != DDP_OK) return rc;
+    if (!params || !packed) DDP_FAIL(DDP_ERR_ARG, "ddp_rnd_pack: NULL argument");
+    for (int i = 0; i < 16; ++i)
+        if (!params[i]) DDP_FAIL(DDP_ERR_ARG, "ddp_rnd_pack: params[%d] is NULL", i);
+    return pack_q_fp32(L, params, (float*)packed, (cudaStream_t)stream);
+}
+
+int ddp_rnd_novelty(const ddp_rnd_shape* s, const void* packed, const float* x, float* novelty_out, float* pred_out,
+                    float* target_out, long B, void* stream) {
+    QLayout L;
+    int rc = rnd_layout(s, &L);
+    if (rc != DDP_OK) return rc;
+    if (B <= 0) DDP_FAIL(DDP_ERR_SHAPE, "ddp_rnd_novelty: batch must be positive");
+    if (!packed || !x) DDP_FAIL(DDP_ERR_ARG, "ddp_rnd_novelty: NULL argument");
+    return rnd_novelty_fma(L, (const float*)packed, x, novelty_out, pred_out, target_out, B, (cudaStream_t)stream);
+}
+
+size_t ddp_rnd_grad_count(const ddp_rnd_shape* s) {
+    QLayout L;
+    return rnd_layout(s, &L) == DDP_OK ? rnd_grad_count(L) : 0;
+}
+
+size_t ddp_rnd_train_workspace_bytes(const ddp_rnd_shape* s, long B) {
+    QLayout L;
+    if (rnd_layout(s, &L) != DDP_OK || B <= 0) return 0;
+    return rnd_train_workspace(L, B);
+}
+
+int ddp_rnd_loss_fwd_bwd(const ddp_rnd_shape* s, const void* packed, const float* x, float* loss_out, float* grads_flat,
+                         float* novelty_out, long B, void* ws, size_t ws_bytes, void* stream) {
+    QLayout L;
+    int rc = rnd_layout(s, &L);
+    if (rc != DDP_OK) return rc;
+    if (B <= 0) DDP_FAIL(DDP_ERR_SHAPE, "ddp_rnd_loss_fwd_bwd: batch must be positive");
+    if (!packed || !x || !loss_out || !grads_flat || !ws) DDP_FAIL(DDP_ERR_ARG, "ddp_rnd_loss_fwd_bwd: NULL argument");
+    if (!aligned16(ws) || !aligned16(grads_flat)) DDP_FAIL(DDP_ERR_ARG, "workspace/grads must be 16-byte aligned");
+    return rnd_train_fma(L, (const float*)packed, x, loss_out, grads_flat, novelty_out, B, ws, ws_bytes,
+                         (cudaStream_t)stream);
 }
 
 }  // extern "C"

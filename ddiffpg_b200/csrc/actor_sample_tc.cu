@@ -36,6 +36,10 @@ constexpr int kASlots = 4;
 #ifndef DDP_TC_EPI_WARPS
 #define DDP_TC_EPI_WARPS 8
 #endif
+#ifndef DDP_TC_PAIR_PUBLISH
+#define DDP_TC_PAIR_PUBLISH 0   // 1: two chunks per proxy fence (measured slower here: it delays the layer-1 MMAs)
+#endif
+constexpr bool kPairPublish = DDP_TC_PAIR_PUBLISH != 0;
 constexpr int kEpiWarps = DDP_TC_EPI_WARPS;  // 8 or 16 (2 or 4 per SM sub-partition)
 constexpr int kColsPerWarp = 64 / (kEpiWarps / 4);   // columns of a 64-column chunk owned by one warp (32 or 16)
 constexpr int kNT = kColsPerWarp / 8;        // mma.sync n8 tiles per warp in layer 0
@@ -154,6 +158,7 @@ template <bool F16>
 __device__ __forceinline__ void drain_acc(EpiCtx& e, int nchunks, const float* bias, int signal_after) {
     const uint32_t tbase = e.tmem_base + ((uint32_t)(e.q * 32) << 16) + e.ch * kColsPerWarp;
     uint32_t va[16], vb[16];
+    int pending = -1;                  // ring slot written but not yet published
     tmem_ld16(tbase, va);
     for (int c = 0; c < nchunks; ++c) {
         const float* bb = bias + c * 64 + e.ch * kColsPerWarp;
@@ -180,13 +185,21 @@ __device__ __forceinline__ void drain_acc(EpiCtx& e, int nchunks, const float* b
             }
         }
         // every lane publishes its own writes to the async proxy, then one lane arrives for the warp
-        // (32 lanes arriving on one mbarrier word serialise in the shared-memory pipe)
-        fence_proxy_async();
-        tc_fence_before();
-        __syncwarp();
-        if (e.lane == 0) {
-            mbar_arrive(bar_a_full(e.bars, e.as.idx));
-            if (c == signal_after) mbar_arrive(bar_lo_free(e.bars));
+        // (32 lanes arriving on one mbarrier word serialise in the shared-memory pipe).  Two chunks share one
+        // publication: the proxy fence is the expensive part of handing a chunk over.
+        const bool flush = !kPairPublish || (c & 1) || c + 1 == nchunks;
+        if (flush) {
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (e.lane == 0) {
+                if (pending >= 0) mbar_arrive(bar_a_full(e.bars, pending));
+                mbar_arrive(bar_a_full(e.bars, e.as.idx));
+                if (c == signal_after || (pending >= 0 && c - 1 == signal_after)) mbar_arrive(bar_lo_free(e.bars));
+            }
+            pending = -1;
+        } else {
+            pending = e.as.idx;
         }
         e.as.advance(kASlots);
     }
@@ -223,6 +236,7 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
             b[nt] = __ldg(reinterpret_cast<const float2*>(tb + c * 64 + e.ch * kColsPerWarp + nt * 8 + 2 * e.t4));
     };
     load_frags(0, bfr, bias);
+    int pending0 = -1;
     for (int c = 0; c < e.NC1; ++c) {
         float acc[2][kNT][4];
 #pragma unroll
@@ -261,9 +275,17 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
                 *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0 + 8, col)) = pack2<F16>(acc[mt][nt][2], acc[mt][nt][3]);
             }
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (e.lane == 0) mbar_arrive(bar_a_full(e.bars, e.as.idx));
+        if (!kPairPublish || (c & 1) || c + 1 == e.NC1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (e.lane == 0) {
+                if (pending0 >= 0) mbar_arrive(bar_a_full(e.bars, pending0));
+                mbar_arrive(bar_a_full(e.bars, e.as.idx));
+            }
+            pending0 = -1;
+        } else {
+            pending0 = e.as.idx;
+        }
         e.as.advance(kASlots);
     }
 

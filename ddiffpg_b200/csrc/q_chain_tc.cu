@@ -42,6 +42,10 @@ constexpr int kASlots = 4;
 #ifndef DDP_QC_EPI_WARPS
 #define DDP_QC_EPI_WARPS 8
 #endif
+#ifndef DDP_QC_PAIR_PUBLISH
+#define DDP_QC_PAIR_PUBLISH 0   // 1: two chunks per proxy fence (measured slower: the hand-off latency matters more)
+#endif
+constexpr bool kPairPublish = DDP_QC_PAIR_PUBLISH != 0;
 constexpr int kEpiWarps = DDP_QC_EPI_WARPS;      // 8 or 16: 2 or 4 warps per SM sub-partition
 constexpr int kColsPerWarp = 64 / (kEpiWarps / 4);  // columns of a chunk owned by one warp (32 or 16)
 constexpr int kEpiThreads = kEpiWarps * 32;
@@ -206,9 +210,9 @@ __device__ __forceinline__ void q_drain(QEpi& e, int col, int nchunks, const flo
 #define QC_FINE(slot) do { } while (0)
 #define QC_FINE_COUNT() do { } while (0)
 #endif
-    for (int c0 = 0; c0 < nchunks; c0 += 2) {
+    for (int c0 = 0; c0 < nchunks; c0 += kPairPublish ? 2 : 1) {
         // two chunks per publication: the generic->async proxy fence is the expensive part of handing a chunk over
-        const int n2 = nchunks - c0 < 2 ? nchunks - c0 : 2;
+        const int n2 = (!kPairPublish || nchunks - c0 < 2) ? 1 : 2;
         QRing rs = e.as;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {

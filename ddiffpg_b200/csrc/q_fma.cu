@@ -91,7 +91,8 @@ int pack_q_fp32(const QLayout& L, const float* const p[], float* out, cudaStream
             copy_pad_kernel<<<blocks((size_t)L.atomsP * L.h3), 256, 0, st>>>(q[6], L.atoms * L.h3, L.atomsP * L.h3, base + n.w4b);
             copy_pad_kernel<<<blocks((size_t)L.h3 * L.h2), 256, 0, st>>>(q[4], L.h3 * L.h2, L.h3 * L.h2, base + n.w3b);
             copy_pad_kernel<<<blocks((size_t)L.h2 * L.h1), 256, 0, st>>>(q[2], L.h2 * L.h1, L.h2 * L.h1, base + n.w2b);
-            submatrix_pack_kernel<<<blocks((size_t)L.h1 * L.A4), 256, 0, st>>>(q[0], in1, L.O, L.h1, L.A, L.A4, base + n.w1a);
+            if (L.A4 > 0)
+                submatrix_pack_kernel<<<blocks((size_t)L.h1 * L.A4), 256, 0, st>>>(q[0], in1, L.O, L.h1, L.A, L.A4, base + n.w1a);
         }
         q_support_kernel<<<1, 64, 0, st>>>(base + L.z, L.atoms, L.atomsP, L.v_min, L.v_max);
     }
@@ -106,6 +107,10 @@ int pack_q_fp32(const QLayout& L, const float* const p[], float* out, cudaStream
 //   MODE 2: critic training step (AgentDDiffPG.update_critic, ddiffpg.py:348-349): BCE(current_Q1, target) +
 //           BCE(current_Q2, target), softmax backward, dZ chain; activations and dZ go to global memory for the
 //           weight-gradient GEMMs.
+//   MODE 3: RNDModel (mlp.py:233-267): net 0 = predictor, net 1 = target, `atoms` = feature width.  Novelty
+//           ||pred - target||_2 per row (IntrinsicM.get_novelty, utils/intrinsic.py:62-65) into qmin_out; with
+//           tr.loss_out set also the predictor update of IntrinsicM.update (:67-75): mse loss, d loss / d pred and
+//           the predictor's dZ chain (the target net has no gradient).
 template <int RT, int NT, int MODE>
 __global__ void __launch_bounds__(NT) q_tile_kernel(QArgs a, SegTable seg, const float* __restrict__ obs,
                                                     const float* __restrict__ act, float* __restrict__ qmin_out,
@@ -235,8 +240,51 @@ __global__ void __launch_bounds__(NT) q_tile_kernel(QArgs a, SegTable seg, const
         }
         __syncthreads();
     }
+    if (MODE == 3) {
+        const bool train = tr.loss_out != nullptr;
+        if (train) {
+            store_tile(in1, a.K1p, tr.xin, a.K1p, a.K1p);
+            store_tile(A1, ld1, tr.a1[0], a.h1, a.h1);
+            store_tile(A2, ld2, tr.a2[0], a.h2, a.h2);
+            store_tile(A3, ld3, tr.a3[0], a.h3, a.h3);
+        }
+        if (p1_out) store_tile(LG, ldl, p1_out, a.atoms, a.atoms);                 // predictor features
+        if (p2_out) store_tile(LG + RT * ldl, ldl, p2_out, a.atoms, a.atoms);      // target features
+        __syncthreads();
+        float lsum = 0.f;
+        for (int r = warp; r < RT; r += NT / 32) {            // one warp per row
+            float* lp = LG + r * ldl;
+            const float* lt = LG + (RT + r) * ldl;
+            const long row = row0 + r;
+            const bool ok = row < row_end;
+            float ss = 0.f;
+            for (int c = lane; c < a.atomsP; c += 32) {
+                const float d = c < a.atoms ? lp[c] - lt[c] : 0.f;
+                ss = fmaf(d, d, ss);
+                if (train) {
+                    const float g = 2.f * tr.inv_count * d;   // d mean((pred - target)^2) / d pred
+                    lp[c] = g;
+                    if (ok) tr.dl[0][row * a.atomsP + c] = g;
+                }
+            }
+            ss = warp_sum(ss);
+            if (ok) {
+                if (lane == 0 && qmin_out) qmin_out[row] = sqrtf(ss);
+                lsum += ss;
+            }
+        }
+        if (!train) return;
+        if (lane == 0) red[warp] = lsum;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int w = 0; w < NT / 32; ++w) t += red[w];
+            atomicAdd(tr.loss_out, t * tr.inv_count);
+        }
+        __syncthreads();
+    }
     // softmax over atoms and expectation: one warp per (net, row)
-    for (int pr = warp; MODE != 2 && pr < 2 * RT; pr += NT / 32) {
+    for (int pr = warp; MODE < 2 && pr < 2 * RT; pr += NT / 32) {
         float* lg = LG + pr * ldl;                      // pr = j*RT + r, rows are contiguous
         const int c0 = lane, c1 = lane + 32;
         float l0 = c0 < a.atoms ? lg[c0] : -INFINITY, l1 = c1 < a.atoms ? lg[c1] : -INFINITY;
@@ -266,7 +314,7 @@ __global__ void __launch_bounds__(NT) q_tile_kernel(QArgs a, SegTable seg, const
     }
 
     // d min(Q1,Q2) / d logits: only the smaller net carries gradient (ties split, as torch.min does)
-    for (int i = tid; MODE != 2 && i < 2 * RT * ldl; i += NT) {
+    for (int i = tid; MODE < 2 && i < 2 * RT * ldl; i += NT) {
         int j = i / (RT * ldl), rem = i % (RT * ldl), r = rem / ldl, c = rem % ldl;
         float q1 = QV[r], q2 = QV[RT + r];
         float w = (q1 == q2) ? 0.5f : ((j == 0) == (q1 < q2) ? 1.f : 0.f);
@@ -276,7 +324,7 @@ __global__ void __launch_bounds__(NT) q_tile_kernel(QArgs a, SegTable seg, const
     }
     __syncthreads();
 
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < (MODE == 3 ? 1 : 2); ++j) {
         const QNetLayout& n = a.net[j];
         float* a1 = A1 + j * RT * ld1; float* a2 = A2 + j * RT * ld2; float* a3 = A3 + j * RT * ld3;
         float* lg = LG + j * RT * ldl; float* ga = GA + j * RT * a.A4;
@@ -301,7 +349,7 @@ __global__ void __launch_bounds__(NT) q_tile_kernel(QArgs a, SegTable seg, const
                              v.z * elu_grad_from_act(s.z), v.w * elu_grad_from_act(s.w));
         });
         __syncthreads();
-        if (MODE == 2) {
+        if (MODE >= 2) {
             store_tile(a3, ld3, tr.z3[j], a.h3, a.h3);
             store_tile(a2, ld2, tr.z2[j], a.h2, a.h2);
             store_tile(a1, ld1, tr.z1[j], a.h1, a.h1);
@@ -312,7 +360,7 @@ __global__ void __launch_bounds__(NT) q_tile_kernel(QArgs a, SegTable seg, const
         });
         __syncthreads();
     }
-    if (MODE == 2) return;
+    if (MODE >= 2) return;
 
     float sq = 0.f;
     const float scale = MODE == 1 ? -seg.inv_cnt[m] : 1.f;
@@ -595,6 +643,52 @@ int q_critic_train_fma(const QLayout& L, const float* pk, const float* pk_target
         g += (size_t)L.atoms * L.h3 + L.atoms;
     }
     DDP_LAUNCH_CHECK("critic training kernels");
+    return DDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RND / NovelD.  L describes RNDModel as a two-net pack: O = input width, A = 0,
+// atoms = feature width, net 0 = predictor, net 1 = target.
+size_t rnd_grad_count(const QLayout& L) { return q_grad_count(L) / 2; }
+size_t rnd_train_workspace(const QLayout& L, long B) { return carve_q_train(L, B, nullptr).total; }
+
+int rnd_novelty_fma(const QLayout& L, const float* pk, const float* x, float* novelty, float* pred, float* target,
+                    long B, cudaStream_t st) {
+    const int64_t seg_off[2] = {0, B};
+    SegTable seg;
+    const bool small = B <= 148 * 8;
+    const long tiles = fill_segments(L, seg_off, nullptr, small ? 4 : 16, seg);
+    return small ? launch_q_tile<4, 3>(L, pk, seg, tiles, x, nullptr, novelty, pred, target, nullptr, nullptr, st)
+                 : launch_q_tile<16, 3>(L, pk, seg, tiles, x, nullptr, novelty, pred, target, nullptr, nullptr, st);
+}
+
+// loss_out[0] += mse(pred, target); grads = d loss / d predictor params (W1,b1,...,W4,b4), overwritten;
+// novelty (optional) as in rnd_novelty_fma
+int rnd_train_fma(const QLayout& L, const float* pk, const float* x, float* loss_out, float* grads, float* novelty,
+                  long B, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (ws_bytes < carve_q_train(L, B, nullptr).total) DDP_FAIL(DDP_ERR_ARG, "RND update: workspace too small");
+    QTrainWs w = carve_q_train(L, B, (float*)ws);
+    const int64_t seg_off[2] = {0, B};
+    DDP_CUDA_CHECK(cudaMemsetAsync(grads, 0, rnd_grad_count(L) * sizeof(float), st));
+    w.b.target = nullptr;
+    w.b.inv_count = 1.0f / ((float)B * (float)L.atoms);
+    w.b.loss_out = loss_out;
+    SegTable seg;
+    const bool small = B <= 148 * 8;
+    const long tiles = fill_segments(L, seg_off, nullptr, small ? 4 : 16, seg);
+    int rc = small ? launch_q_tile<4, 3>(L, pk, seg, tiles, x, nullptr, novelty, nullptr, nullptr, nullptr, nullptr, st, &w.b)
+                   : launch_q_tile<16, 3>(L, pk, seg, tiles, x, nullptr, novelty, nullptr, nullptr, nullptr, nullptr, st, &w.b);
+    if (rc != DDP_OK) return rc;
+    const int in1 = L.O + L.A;
+    float* g = grads;
+    launch_dw(w.b.z1[0], L.h1, L.h1, w.b.xin, L.K1p, in1, g, in1, g + (size_t)L.h1 * in1, B, st);
+    g += (size_t)L.h1 * in1 + L.h1;
+    launch_dw(w.b.z2[0], L.h2, L.h2, w.b.a1[0], L.h1, L.h1, g, L.h1, g + (size_t)L.h2 * L.h1, B, st);
+    g += (size_t)L.h2 * L.h1 + L.h2;
+    launch_dw(w.b.z3[0], L.h3, L.h3, w.b.a2[0], L.h2, L.h2, g, L.h2, g + (size_t)L.h3 * L.h2, B, st);
+    g += (size_t)L.h3 * L.h2 + L.h3;
+    launch_dw(w.b.dl[0], L.atomsP, L.atoms, w.b.a3[0], L.h3, L.h3, g, L.h3, g + (size_t)L.atoms * L.h3, B, st);
+    DDP_LAUNCH_CHECK("RND update kernels");
     return DDP_OK;
 }
 

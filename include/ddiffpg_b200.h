@@ -156,6 +156,29 @@ int ddp_q_critic_loss_fwd_bwd(const ddp_q_shape* shape, const void* packed, cons
                               float* loss_out, float* grads_flat, long B, int precision, void* ws, size_t ws_bytes,
                               void* stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * RND / NovelD intrinsic reward.  RNDModel(state_dim=D) (ddiffpg/models/mlp.py:233-267):
+ * predictor and target, each Linear(D,hid1)-ELU-Linear(hid1,hid2)-ELU-Linear(hid2,hid3)-ELU-Linear(hid3,F).
+ * Reference: D = 69 (29 + 2*2*10 positional encoding), 512/256/128, F = 128.  params[16] = RNDModel.state_dict()
+ * order (predictor.{0,2,4,6}.{weight,bias}, target....). */
+typedef struct { int D, F, hid1, hid2, hid3; } ddp_rnd_shape;
+size_t ddp_rnd_packed_bytes(const ddp_rnd_shape* shape);
+int ddp_rnd_pack(const ddp_rnd_shape* shape, const float* const params[16], void* packed, void* stream);
+
+/* Replaces RNDModel.forward and IntrinsicM.get_novelty (ddiffpg/models/mlp.py:262-266, ddiffpg/utils/intrinsic.py:62-65):
+ * novelty_out[r] = ||predictor(x_r) - target(x_r)||_2; pred_out / target_out [B,F] receive the two feature vectors.
+ * Any of the three outputs may be NULL.  x [B,D] is the (already position-encoded) observation. */
+int ddp_rnd_novelty(const ddp_rnd_shape* shape, const void* packed, const float* x, float* novelty_out, float* pred_out,
+                    float* target_out, long B, void* stream);
+
+/* Replaces the loss/backward half of IntrinsicM.update (ddiffpg/utils/intrinsic.py:67-75):
+ * loss_out[0] += mse_loss(predictor(x), target(x)) (zero it first); grads_flat = d loss / d predictor parameters,
+ * flat in state_dict order (the target net is frozen), overwritten.  novelty_out may be NULL. */
+size_t ddp_rnd_grad_count(const ddp_rnd_shape* shape);
+size_t ddp_rnd_train_workspace_bytes(const ddp_rnd_shape* shape, long B);
+int ddp_rnd_loss_fwd_bwd(const ddp_rnd_shape* shape, const void* packed, const float* x, float* loss_out,
+                         float* grads_flat, float* novelty_out, long B, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

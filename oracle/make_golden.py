@@ -172,12 +172,6 @@ def main():
                  checksum=param_checksum(params, port.CRITIC_KEYS))
 
 
-if __name__ == "__main__" and not {"--noise-only", "--critic-only"} & set(__import__("sys").argv):
-    main()
-    noise_fixture()
-    critic_fixture()
-
-
 def noise_fixture():
     """N3: the reference's own add_mixed_normal_noise / add_normal_noise (ddiffpg/utils/noise.py) with the
     Gaussian draw replaced by std * z."""
@@ -200,10 +194,6 @@ def noise_fixture():
     np.savez(os.path.join(OUT, "n3_noise.npz"), a=a.numpy(), z=z.numpy(), mixed=mixed.numpy(), fixed=fixed.numpy(),
              tgt=tgt.numpy())
     print("n3_noise: port == reference")
-
-
-if __name__ == "__main__" and "--noise-only" in __import__("sys").argv:
-    noise_fixture()
 
 
 def critic_fixture():
@@ -251,5 +241,58 @@ def critic_fixture():
     np.savez(os.path.join(OUT, "n1_critic.npz"), **save)
 
 
-if __name__ == "__main__" and "--critic-only" in __import__("sys").argv:
-    critic_fixture()
+def rnd_fixture():
+    """N4: the reference's own RNDModel (ddiffpg/models/mlp.py:233-267) inside its own IntrinsicM
+    (ddiffpg/utils/intrinsic.py), NovelD reward with and without running normalisation, one predictor update."""
+    import sys
+    R = ref_loader.load_reference()
+    sys.modules["ddiffpg.models.mlp"] = sys.modules["_ref_mlp"]          # intrinsic.py imports RNDModel from there
+    sys.path.insert(0, ref_loader.REF_ROOT)
+    from ddiffpg.utils.intrinsic import IntrinsicM
+    g = torch.Generator().manual_seed(6000)
+    B = 40
+    params = port.init_rnd_params(71)
+    obs, nobs = torch.randn(B, 29, generator=g), torch.randn(B, 29, generator=g)
+    obs[:, :2] *= 4.0; nobs[:, :2] *= 4.0                                # ant positions span several metres
+    im = IntrinsicM((29,), type="noveld", env_name="antmaze-v1", normalize=True, pos_enc=True, L=10, warm_up=0, device="cpu")
+    im.rnd_model.load_state_dict(params)
+    enc = im.encode_obs(obs)
+    nov = im.get_novelty(enc)
+    r0 = im.compute_reward(obs, nobs)                                    # update_step == 0: no normalisation
+    im.update_step = 1
+    r1 = im.compute_reward(obs, nobs)                                    # running statistics updated, normalised
+    rms = torch.stack([im.rnd_rms.mean.reshape(()), im.rnd_rms.var.reshape(())])
+    x = torch.cat([obs, nobs])
+    pf, tf = im.rnd_model(im.encode_obs(x))
+    loss = torch.nn.functional.mse_loss(pf, tf.detach())
+    loss.backward()
+    keys = [k for k in port.RND_KEYS if k.startswith("predictor")]
+    grads = {k: dict(im.rnd_model.named_parameters())[k].grad.detach() for k in keys}
+    # the port against the real thing
+    encp = port.encode_obs_antmaze(obs)
+    novp = port.rnd_novelty(params, encp)
+    lp, gp = port.rnd_loss_and_grads(params, port.encode_obs_antmaze(x))
+    d = max((grads[k] - gp[k]).abs().max().item() for k in keys)
+    r0p = port.noveld_reward(novp, port.rnd_novelty(params, port.encode_obs_antmaze(nobs)))
+    print(f"n4_rnd: |enc diff|={(enc - encp).abs().max().item():.2e} |nov diff|={(nov - novp).abs().max().item():.2e} "
+          f"|r0 diff|={(r0 - r0p).abs().max().item():.2e} |dloss|={abs(loss.item() - lp.item()):.2e} max|dgrad|={d:.2e}")
+    assert (enc - encp).abs().max().item() < 1e-6 and (nov - novp).abs().max().item() < 1e-5 and d < 1e-7
+    save = dict(obs=obs.numpy(), nobs=nobs.numpy(), enc=enc.numpy(), novelty=nov.numpy(), r0=r0.numpy(), r1=r1.numpy(),
+                rms=rms.numpy(), loss=loss.item(), checksum=param_checksum(params, port.RND_KEYS))
+    for i, k in enumerate(keys):
+        save[f"g_{i}"] = grads[k].numpy() if grads[k].numel() <= 8192 else grads[k].flatten()[::97].numpy()
+        save[f"gnorm_{i}"] = float(grads[k].norm())
+    np.savez(os.path.join(OUT, "n4_rnd.npz"), **save)
+
+
+if __name__ == "__main__":
+    argv = set(__import__("sys").argv[1:])
+    only = {"--noise-only": noise_fixture, "--critic-only": critic_fixture, "--rnd-only": rnd_fixture}
+    if argv & set(only):
+        for flag in sorted(argv & set(only)):
+            only[flag]()
+    else:
+        main()
+        noise_fixture()
+        critic_fixture()
+        rnd_fixture()

@@ -275,3 +275,63 @@ def q_action_ascent(p, obs, action, iters=20, lr=0.03, eps=1e-5, max_norm=1.0,
     out = action.detach().clone()
     res = (torch.abs(out).mean().item(), out)
     return res + (torch.stack(norms), torch.stack(gaps)) if return_trace else res
+
+
+# ------------------------------------------------------------------------------------------ N4: RND / NovelD
+RND_KEYS = tuple(f"{net}.{i}.{w}" for net in ("predictor", "target") for i in (0, 2, 4, 6) for w in ("weight", "bias"))
+
+
+def init_rnd_params(seed, D=69, hidden=(512, 256, 128), feat=128, scale=1.0):
+    """Seeded RNDModel state_dict (ddiffpg/models/mlp.py:233-260 shapes; values from a plain generator)."""
+    g = torch.Generator().manual_seed(seed)
+    dims = (D,) + tuple(hidden) + (feat,)
+    p = {}
+    for net in ("predictor", "target"):
+        for li, i in enumerate((0, 2, 4, 6)):
+            fan_in = dims[li]
+            p[f"{net}.{i}.weight"] = (torch.rand(dims[li + 1], fan_in, generator=g) * 2 - 1) * scale * (3.0 / fan_in) ** 0.5
+            p[f"{net}.{i}.bias"] = (torch.rand(dims[li + 1], generator=g) * 2 - 1) * 0.1
+    return p
+
+
+def _rnd_net(p, net, x):
+    h = x
+    for i in (0, 2, 4):
+        h = F.elu(F.linear(h, p[f"{net}.{i}.weight"], p[f"{net}.{i}.bias"]))
+    return F.linear(h, p[f"{net}.6.weight"], p[f"{net}.6.bias"])
+
+
+def rnd_forward(p, x):
+    """RNDModel.forward (mlp.py:262-266): (predict_feature, target_feature)."""
+    return _rnd_net(p, "predictor", x), _rnd_net(p, "target", x)
+
+
+def rnd_novelty(p, x):
+    """IntrinsicM.get_novelty (utils/intrinsic.py:62-65)."""
+    pf, tf = rnd_forward(p, x)
+    return torch.norm(pf - tf, dim=1, p=2)
+
+
+def rnd_loss_and_grads(p, x):
+    """IntrinsicM.update up to the backward (utils/intrinsic.py:67-72): mse loss and predictor gradients."""
+    q = {k: (v.clone().requires_grad_(True) if k.startswith("predictor") else v) for k, v in p.items()}
+    pf, tf = rnd_forward(q, x)
+    loss = F.mse_loss(pf, tf.detach())
+    keys = [k for k in RND_KEYS if k.startswith("predictor")]
+    grads = torch.autograd.grad(loss, [q[k] for k in keys])
+    return loss.detach(), dict(zip(keys, grads))
+
+
+def encode_obs_antmaze(obs, L=10):
+    """IntrinsicM.encode_obs for antmaze (utils/intrinsic.py:85-88,122-171): NeRF encoding of the 2-d position."""
+    x = obs[:, :2]
+    outs = [x]
+    for k in range(L):
+        f = 2.0 ** k
+        outs += [torch.sin(x * f), torch.cos(x * f)]
+    return torch.cat(outs + [obs[:, 2:]], dim=1)
+
+
+def noveld_reward(nov_obs, nov_next):
+    """IntrinsicM.compute_reward, type 'noveld', before normalisation kicks in (utils/intrinsic.py:45-59)."""
+    return 0.01 * torch.clamp(nov_next - 0.5 * nov_obs, min=0).unsqueeze(1)

@@ -260,3 +260,26 @@ def test_c51_projection_edge_cases():
     assert abs(pr[2, 0].item() - 1.0) < 1e-5                   # clamped to v_min
     assert abs(pr[3, 2].item() - 0.5) < 1e-4 and abs(pr[3, 3].item() - 0.5) < 1e-4
     np.testing.assert_allclose(pr.sum(1).numpy(), 1.0, atol=1e-5)
+
+
+def test_port_rnd_matches_reference_fixture():
+    """N4: RNDModel / IntrinsicM (models/mlp.py:233-267, utils/intrinsic.py) -- encoding, novelty, NovelD reward,
+    mse loss and predictor gradients."""
+    from tests.util import checksum
+    g = load_golden("n4_rnd")
+    p = port.init_rnd_params(71)
+    np.testing.assert_allclose(checksum(p, port.RND_KEYS), g["checksum"], rtol=1e-12)
+    obs, nobs = torch.from_numpy(g["obs"]), torch.from_numpy(g["nobs"])
+    enc = port.encode_obs_antmaze(obs)
+    np.testing.assert_array_equal(enc.numpy(), g["enc"])
+    assert enc.shape[1] == 69
+    nov = port.rnd_novelty(p, enc)
+    np.testing.assert_allclose(nov.numpy(), g["novelty"], rtol=1e-6)
+    r0 = port.noveld_reward(nov, port.rnd_novelty(p, port.encode_obs_antmaze(nobs)))
+    np.testing.assert_allclose(r0.numpy(), g["r0"], rtol=1e-6, atol=1e-9)
+    loss, grads = port.rnd_loss_and_grads(p, port.encode_obs_antmaze(torch.cat([obs, nobs])))
+    assert abs(loss.item() - float(g["loss"])) <= 1e-6 * float(g["loss"])
+    for i, k in enumerate(k for k in port.RND_KEYS if k.startswith("predictor")):
+        ref = g[f"g_{i}"]
+        got = grads[k] if grads[k].numel() <= 8192 else grads[k].flatten()[::97]
+        np.testing.assert_allclose(got.numpy().reshape(ref.shape), ref, rtol=1e-5, atol=1e-9, err_msg=k)

@@ -396,3 +396,85 @@ def test_update_critic_matches_reference_optimizer_step():
         assert abs(loss - l_ref.item()) <= 2e-5 * max(1.0, abs(l_ref.item()))
         assert abs(gnorm - n_ref.item()) <= 1e-4 * n_ref.item()
     _assert_params_after_adam(critic, {k: v.detach() for k, v in ref.items()}, steps=3, lr=5e-4)
+
+
+# ------------------------------------------------------------------------------------------ N4
+def _make_rnd(p):
+    from ddiffpg_b200 import RNDModel
+    m = RNDModel(69)
+    m.load_state_dict(p)
+    return m.to("cuda")
+
+
+def test_rnd_matches_reference_fixture():
+    """IntrinsicM.compute_reward / update (utils/intrinsic.py:33-75) against the reference's own outputs."""
+    from ddiffpg_b200 import IntrinsicM
+    g = load_golden("n4_rnd")
+    p = port.init_rnd_params(71)
+    im = IntrinsicM((29,), type="noveld", env_name="antmaze-v1", normalize=True, pos_enc=True, L=10, warm_up=0, device="cuda")
+    im.rnd_model.load_state_dict(p)
+    obs, nobs = _dev(g["obs"]), _dev(g["nobs"])
+    enc = im.encode_obs(obs)
+    assert_close(enc, g["enc"], 1e-5, 1e-5, "positional encoding")
+    assert_close(im.get_novelty(enc), g["novelty"], RTOL, ATOL, "novelty")
+    assert_close(im.compute_reward(obs, nobs), g["r0"], RTOL, 1e-7, "noveld reward (raw)")
+    im.update_step = 1
+    assert_close(im.compute_reward(obs, nobs), g["r1"], 2e-4, 1e-6, "noveld reward (normalised)")
+    assert_close(torch.stack([im.rnd_rms.mean.reshape(()), im.rnd_rms.var.reshape(())]), g["rms"], 1e-4, 1e-6, "running stats")
+    x = im.encode_obs(torch.cat([obs, nobs]))
+    loss, flat = im.rnd_model.loss_and_grads(x)
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    off = 0
+    for i, (k, q) in enumerate(im.rnd_model.predictor.named_parameters()):
+        got = flat[off:off + q.numel()].view(q.shape).cpu()
+        off += q.numel()
+        ref = torch.from_numpy(g[f"g_{i}"])
+        sub = got if got.numel() <= 8192 else got.flatten()[::97]
+        assert _rel_l2(sub.reshape(ref.shape), ref) <= 1e-4, k
+        assert abs(float(got.norm()) - float(g[f"gnorm_{i}"])) <= 1e-4 * float(g[f"gnorm_{i}"]) + 1e-9, k
+    assert off == flat.numel()
+    pf, tf = im.rnd_model(x)
+    rp, rt = port.rnd_forward(p, x.cpu())
+    assert_close(pf, rp, RTOL, ATOL, "predictor features")
+    assert_close(tf, rt, RTOL, ATOL, "target features")
+
+
+@pytest.mark.parametrize("B", [1, 9, 600, 5000])
+def test_rnd_update_vs_oracle_batches(B):
+    p = port.init_rnd_params(72, scale=1.3)
+    gen = torch.Generator().manual_seed(900 + B)
+    x = torch.randn(B, 69, generator=gen)
+    m = _make_rnd(p)
+    assert_close(m.novelty(_dev(x)), port.rnd_novelty(p, x), RTOL, ATOL, "novelty")
+    loss, flat = m.loss_and_grads(_dev(x))
+    l_ref, g_ref = port.rnd_loss_and_grads(p, x)
+    assert abs(loss.item() - l_ref.item()) <= 1e-5 * l_ref.item()
+    off = 0
+    for k in (k for k in port.RND_KEYS if k.startswith("predictor")):
+        n = p[k].numel()
+        assert _rel_l2(flat[off:off + n].view(p[k].shape).cpu(), g_ref[k]) <= 1e-4, k
+        off += n
+
+
+def test_intrinsic_update_matches_torch_adamw():
+    """IntrinsicM.update: loss, clip_grad_norm_(1.0) and AdamW(1e-4) on the predictor; the target stays frozen."""
+    from ddiffpg_b200 import IntrinsicM
+    p = port.init_rnd_params(73)
+    im = IntrinsicM((29,), type="rnd", env_name="antmaze-v1", device="cuda")
+    im.rnd_model.load_state_dict(p)
+    gen = torch.Generator().manual_seed(5)
+    obs = torch.randn(300, 29, generator=gen)
+    ref = {k: v.clone().requires_grad_(k.startswith("predictor")) for k, v in p.items()}
+    keys = [k for k in port.RND_KEYS if k.startswith("predictor")]
+    ropt = torch.optim.AdamW([ref[k] for k in keys], 1e-4)
+    for _ in range(3):
+        loss, gnorm = im.update(_dev(obs))
+        l_ref, g_ref = port.rnd_loss_and_grads({k: v.detach() for k, v in ref.items()}, port.encode_obs_antmaze(obs))
+        for k in keys:
+            ref[k].grad = g_ref[k].clone()
+        n_ref = torch.nn.utils.clip_grad_norm_([ref[k] for k in keys], 1.0)
+        ropt.step()
+        assert abs(loss - l_ref.item()) <= 2e-5 * l_ref.item()
+        assert abs(gnorm - n_ref.item()) <= 1e-4 * n_ref.item()
+    assert im.update_step == 3
+    _assert_params_after_adam(im.rnd_model, {k: v.detach() for k, v in ref.items()}, steps=3, lr=1e-4)
