@@ -22,6 +22,10 @@ class QShape(Structure):
                 ("n_modes", c_int), ("hid1", c_int), ("hid2", c_int), ("hid3", c_int)]
 
 
+class BatchShape(Structure):
+    _fields_ = [("O", c_int), ("A", c_int), ("E", c_int), ("n_groups", c_int)]
+
+
 class RndShape(Structure):
     _fields_ = [("D", c_int), ("F", c_int), ("hid1", c_int), ("hid2", c_int), ("hid3", c_int)]
 
@@ -65,6 +69,9 @@ PROTOTYPES = {
     "ddp_rnd_train_workspace_bytes": (c_size_t, [POINTER(RndShape), c_long]),
     "ddp_rnd_loss_fwd_bwd": (c_int, [POINTER(RndShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long,
                                      c_void_p, c_size_t, c_void_p]),
+    "ddp_replay_gather": (c_int, [POINTER(BatchShape)] + [c_void_p] * 6 + [c_long] + [c_void_p] * 13 + [c_long, c_void_p]),
+    "ddp_replay_scatter_target": (c_int, [POINTER(BatchShape), c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_long,
+                                          c_void_p]),
 }
 
 _lib = None

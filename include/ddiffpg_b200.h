@@ -179,6 +179,30 @@ size_t ddp_rnd_train_workspace_bytes(const ddp_rnd_shape* shape, long B);
 int ddp_rnd_loss_fwd_bwd(const ddp_rnd_shape* shape, const void* packed, const float* x, float* loss_out,
                          float* grads_flat, float* novelty_out, long B, void* ws, size_t ws_bytes, void* stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * Batch assembly / scatter-back around the hot path, all mode groups in one launch.
+ * Replay storage as in DiffusionReplayBuffer (ddiffpg/replay/simple_replay.py:98-200): buf_obs / buf_next_obs [N,O],
+ * buf_action [N,A], buf_target_action [n_groups,N,A], buf_reward [N], buf_done [N] (bool bytes).
+ * Output row r reads replay row indices[r] for mode group[r] (NULL = group 0):
+ *   the six gathers of sample_batch (:150-163; done as float), plus add_embedding (ddiffpg/utils/torch_util.py:17-43)
+ *   applied to state and next state: [obs | embeddings[group[r]]] with the embedding zeroed where zero_state[r] /
+ *   zero_next[r] is non-zero (the reference draws those rows with np.random.choice; the caller passes the draw).
+ * Every output pointer may be NULL (that output is skipped); embeddings == NULL writes zero embeddings.
+ * Rows whose index is outside [0,N) produce zeros. */
+typedef struct { int O, A, E, n_groups; } ddp_batch_shape;
+int ddp_replay_gather(const ddp_batch_shape* shape, const float* buf_obs, const float* buf_action,
+                      const float* buf_target_action, const float* buf_reward, const float* buf_next_obs,
+                      const uint8_t* buf_done, long N, const int64_t* indices, const int32_t* group,
+                      const float* embeddings, const uint8_t* zero_state, const uint8_t* zero_next, float* obs_out,
+                      float* action_out, float* target_action_out, float* reward_out, float* next_obs_out,
+                      float* done_out, float* state_emb_out, float* next_state_emb_out, long n, void* stream);
+
+/* Replaces DiffusionReplayBuffer.update_target_action (simple_replay.py:198-200) for all groups at once:
+ * buf_target_action[group[r], indices[r], :] = new_action[r, :].  Duplicate (group, index) pairs keep one of the
+ * candidates, as torch's indexed assignment does. */
+int ddp_replay_scatter_target(const ddp_batch_shape* shape, float* buf_target_action, long N, const float* new_action,
+                              const int64_t* indices, const int32_t* group, long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -285,9 +285,60 @@ def rnd_fixture():
     np.savez(os.path.join(OUT, "n4_rnd.npz"), **save)
 
 
+def replay_fixture():
+    """N2: the reference's own DiffusionReplayBuffer.sample_batch / update_target_action
+    (ddiffpg/replay/simple_replay.py:98-200) and add_embedding (ddiffpg/utils/torch_util.py:17-43), with their
+    random draws recorded (torch.randint replaced by a recorded draw, np.random seeded)."""
+    import sys
+    sys.path.insert(0, ref_loader.REF_ROOT)
+    from ddiffpg.replay.simple_replay import DiffusionReplayBuffer
+    from ddiffpg.utils.torch_util import add_embedding
+    g = torch.Generator().manual_seed(7000)
+    buf = DiffusionReplayBuffer(10000, 29, 8, device="cpu")
+    lens = [17, 30, 9, 22, 40]
+    for tid, n in enumerate(lens):
+        tr = (torch.randn(n, 29, generator=g), torch.rand(n, 8, generator=g) * 2 - 1, torch.rand(n, 8, generator=g) * 2 - 1,
+              torch.rand(n, generator=g), torch.randn(n, 29, generator=g), torch.rand(n, generator=g) < 0.2)
+        buf.add_to_buffer(tr, tid)
+    buf.update_target_action_dim([-1, 0])                        # three target-action slots (explore + 2 modes)
+    buf.buf_target_action[1] += 0.25; buf.buf_target_action[2] -= 0.25
+    store = dict(obs=buf.buf_obs.clone(), action=buf.buf_action.clone(), target_action=buf.buf_target_action.clone(),
+                 reward=buf.buf_reward.clone(), next_obs=buf.buf_next_obs.clone(), done=buf.buf_done.clone(), id=buf.buf_id.clone())
+    groups = [[0, 1, 2, 3, 4], [0, 3], [1, 4]]
+    draws = [torch.randint(sum(lens[t] for t in grp), (sz,), generator=g) for grp, sz in zip(groups, (14, 12, 12))]
+    save = {f"store_{k}": v.numpy() for k, v in store.items()}
+    real_randint = torch.randint
+    for gi, (grp, draw) in enumerate(zip(groups, draws)):
+        torch.randint = lambda *a, **k: draw                     # replay the recorded draw inside the reference
+        try:
+            data, idx = buf.sample_batch(draw.shape[0], grp, gi, device="cpu")
+        finally:
+            torch.randint = real_randint
+        port_data = port.replay_gather(store, idx, gi)
+        assert all(torch.equal(a, b) for a, b in zip(data, port_data))
+        save[f"draw_{gi}"] = draw.numpy(); save[f"idx_{gi}"] = idx.numpy()
+        for name, t in zip(("obs", "action", "target", "reward", "next_obs", "done"), data):
+            save[f"g{gi}_{name}"] = t.numpy()
+    emb = torch.randn(5, generator=g)
+    np.random.seed(11)
+    state = save["g1_obs"]
+    es = add_embedding(torch.from_numpy(state), emb)             # p = 0.5: np.random.choice(12, 6, replace=False)
+    np.random.seed(11)
+    zero_idx = np.random.choice(state.shape[0], size=int(state.shape[0] * 0.5), replace=False)
+    assert torch.equal(es, port.add_embedding_port(torch.from_numpy(state), emb, zero_idx))
+    e0 = add_embedding(torch.from_numpy(save["g0_obs"]), emb, p=0)
+    new_action = torch.rand(12, 8, generator=g) * 2 - 1
+    buf.update_target_action(new_action, torch.from_numpy(save["idx_2"]), 2)
+    save.update(emb=emb.numpy(), zero_idx=zero_idx, emb_state=es.numpy(), emb_state_p0=e0.numpy(), new_action=new_action.numpy(),
+                target_after=buf.buf_target_action.numpy())
+    np.savez(os.path.join(OUT, "n2_replay.npz"), **save)
+    print("n2_replay: port == reference")
+
+
 if __name__ == "__main__":
     argv = set(__import__("sys").argv[1:])
-    only = {"--noise-only": noise_fixture, "--critic-only": critic_fixture, "--rnd-only": rnd_fixture}
+    only = {"--noise-only": noise_fixture, "--critic-only": critic_fixture, "--rnd-only": rnd_fixture,
+            "--replay-only": replay_fixture}
     if argv & set(only):
         for flag in sorted(argv & set(only)):
             only[flag]()
@@ -296,3 +347,4 @@ if __name__ == "__main__":
         noise_fixture()
         critic_fixture()
         rnd_fixture()
+        replay_fixture()

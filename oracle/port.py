@@ -335,3 +335,24 @@ def encode_obs_antmaze(obs, L=10):
 def noveld_reward(nov_obs, nov_next):
     """IntrinsicM.compute_reward, type 'noveld', before normalisation kicks in (utils/intrinsic.py:45-59)."""
     return 0.01 * torch.clamp(nov_next - 0.5 * nov_obs, min=0).unsqueeze(1)
+
+
+# ------------------------------------------------------------------------------------------ N2: batch assembly
+def replay_gather(bufs, indices, target_idx):
+    """DiffusionReplayBuffer.sample_batch after the index draw (replay/simple_replay.py:155-162).
+    bufs: dict obs, action, target_action [K,N,A], reward [N,1], next_obs, done (bool [N,1])."""
+    return (bufs["obs"][indices], bufs["action"][indices], bufs["target_action"][target_idx, indices],
+            bufs["reward"][indices], bufs["next_obs"][indices], bufs["done"][indices].float())
+
+
+def add_embedding_port(state, embedding, zero_indices):
+    """add_embedding (utils/torch_util.py:17-43) with the np.random.choice draw passed in."""
+    new_embedding = embedding.unsqueeze(0).repeat(state.shape[0], 1)
+    if len(zero_indices):
+        new_embedding[torch.as_tensor(zero_indices).long()] = 0.0
+    return torch.cat([state, new_embedding], dim=1)
+
+
+def replay_scatter(bufs, new_action, indices, i):
+    """DiffusionReplayBuffer.update_target_action (replay/simple_replay.py:198-200), in place."""
+    bufs["target_action"][i, indices] = new_action

@@ -283,3 +283,19 @@ def test_port_rnd_matches_reference_fixture():
         ref = g[f"g_{i}"]
         got = grads[k] if grads[k].numel() <= 8192 else grads[k].flatten()[::97]
         np.testing.assert_allclose(got.numpy().reshape(ref.shape), ref, rtol=1e-5, atol=1e-9, err_msg=k)
+
+
+def test_port_replay_matches_reference_fixture():
+    """N2: DiffusionReplayBuffer.sample_batch / update_target_action and add_embedding with recorded draws."""
+    g = load_golden("n2_replay")
+    store = {k[6:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("store_")}
+    for gi in range(3):
+        idx = torch.from_numpy(g[f"idx_{gi}"])
+        data = port.replay_gather(store, idx, gi)
+        for name, t in zip(("obs", "action", "target", "reward", "next_obs", "done"), data):
+            np.testing.assert_array_equal(t.numpy(), g[f"g{gi}_{name}"], err_msg=f"group {gi} {name}")
+    emb = torch.from_numpy(g["emb"])
+    np.testing.assert_array_equal(port.add_embedding_port(torch.from_numpy(g["g1_obs"]), emb, g["zero_idx"]).numpy(), g["emb_state"])
+    np.testing.assert_array_equal(port.add_embedding_port(torch.from_numpy(g["g0_obs"]), emb, []).numpy(), g["emb_state_p0"])
+    port.replay_scatter(store, torch.from_numpy(g["new_action"]), torch.from_numpy(g["idx_2"]), 2)
+    np.testing.assert_array_equal(store["target_action"].numpy(), g["target_after"])

@@ -478,3 +478,81 @@ def test_intrinsic_update_matches_torch_adamw():
         assert abs(gnorm - n_ref.item()) <= 1e-4 * n_ref.item()
     assert im.update_step == 3
     _assert_params_after_adam(im.rnd_model, {k: v.detach() for k, v in ref.items()}, steps=3, lr=1e-4)
+
+
+# ------------------------------------------------------------------------------------------ N2
+def _replay_from_fixture(g):
+    from ddiffpg_b200 import DiffusionReplayBuffer
+    buf = DiffusionReplayBuffer(10000, 29, 8, device="cuda")
+    buf.buf_obs, buf.buf_action = _dev(g["store_obs"]), _dev(g["store_action"])
+    buf.buf_target_action, buf.buf_reward = _dev(g["store_target_action"]), _dev(g["store_reward"])
+    buf.buf_next_obs, buf.buf_done, buf.buf_id = _dev(g["store_next_obs"]), _dev(g["store_done"]), _dev(g["store_id"])
+    buf.cur_capacity = buf.buf_obs.shape[0]
+    return buf
+
+
+def test_replay_sample_and_scatter_match_reference_fixture():
+    """Byte-exact: the gathers move fp32 values, nothing is computed."""
+    from ddiffpg_b200 import add_embedding
+    g = load_golden("n2_replay")
+    buf = _replay_from_fixture(g)
+    groups = [[0, 1, 2, 3, 4], [0, 3], [1, 4]]
+    names = ("obs", "action", "target", "reward", "next_obs", "done")
+    for gi, grp in enumerate(groups):
+        data, idx = buf.sample_batch(len(g[f"draw_{gi}"]), grp, gi, indices=_dev(g[f"draw_{gi}"]))
+        assert torch.equal(idx.cpu(), torch.from_numpy(g[f"idx_{gi}"]))
+        for name, t in zip(names, data):
+            assert torch.equal(t.cpu(), torch.from_numpy(g[f"g{gi}_{name}"])), (gi, name)
+        assert buf.get_buffer_size(grp) == sum(1 for t in g["store_id"].ravel() if int(t) in grp)
+    emb = _dev(g["emb"])
+    assert torch.equal(add_embedding(_dev(g["g1_obs"]), emb, zero_indices=g["zero_idx"]).cpu(), torch.from_numpy(g["emb_state"]))
+    assert torch.equal(add_embedding(_dev(g["g0_obs"]), emb, p=0).cpu(), torch.from_numpy(g["emb_state_p0"]))
+    # fused form: all groups, embedded states included, one launch
+    embs = torch.stack([emb, emb * 2, emb * 3])
+    o, seg_off, idx, grp_ids, se, ne = buf.sample_groups([g[f"idx_{gi}"] for gi in range(3)], embeddings=embs,
+                                                         zero_state=g["zero_idx"] + 14)
+    assert seg_off == [0, 14, 26, 38]
+    for gi in range(3):
+        for name in names:
+            assert torch.equal(o[name][seg_off[gi]:seg_off[gi + 1]].cpu(), torch.from_numpy(g[f"g{gi}_{name}"])), (gi, name)
+    ref_se = torch.from_numpy(g["emb_state"]).clone()
+    ref_se[:, 29:] *= 2                                        # group 1 uses 2 * emb
+    assert torch.equal(se[14:26].cpu(), ref_se)
+    assert torch.equal(ne[26:, :29].cpu(), torch.from_numpy(g["g2_next_obs"])) and torch.equal(ne[26:, 29:].cpu(), (emb * 3).cpu().expand(12, 5))
+    # scatter-back: rows drawn once must match exactly, duplicated rows keep one of their candidates
+    buf.update_target_action(_dev(g["new_action"]), _dev(g["idx_2"]), 2)
+    after, ref = buf.buf_target_action.cpu(), torch.from_numpy(g["target_after"])
+    idx2 = torch.from_numpy(g["idx_2"])
+    uniq, counts = torch.unique(idx2, return_counts=True)
+    once = uniq[counts == 1]
+    assert torch.equal(after[:2], ref[:2])
+    keep = torch.ones(after.shape[1], dtype=torch.bool); keep[uniq[counts > 1]] = False
+    assert torch.equal(after[2][keep], ref[2][keep]) and len(once) > 0
+    for d in uniq[counts > 1]:
+        cands = torch.from_numpy(g["new_action"])[idx2 == d]
+        assert any(torch.equal(after[2, d], c) for c in cands)
+
+
+def test_replay_gather_large_roundtrip():
+    """Full-size property: gather(scatter(x)) == x for a permutation, 1M-row buffer, 3 groups."""
+    from ddiffpg_b200 import DiffusionReplayBuffer
+    N, n = 1 << 20, 1 << 18
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    buf = DiffusionReplayBuffer(N, 29, 8, device="cuda")
+    buf.buf_obs = torch.randn(N, 29, device="cuda", generator=gen)
+    buf.buf_next_obs = torch.randn(N, 29, device="cuda", generator=gen)
+    buf.buf_action = torch.rand(N, 8, device="cuda", generator=gen)
+    buf.buf_target_action = torch.zeros(3, N, 8, device="cuda")
+    buf.buf_reward = torch.rand(N, 1, device="cuda", generator=gen)
+    buf.buf_done = torch.rand(N, 1, device="cuda", generator=gen) < 0.1
+    buf.buf_id = torch.zeros(N, 1, device="cuda")
+    perm = torch.randperm(N, device="cuda", generator=gen)[:n]
+    grp = (torch.arange(n, device="cuda") % 3).to(torch.int32).sort().values.contiguous()
+    new = torch.rand(n, 8, device="cuda", generator=gen)
+    buf.scatter_groups(new, perm, grp)
+    sizes = [int((grp == k).sum()) for k in range(3)]
+    parts = torch.split(perm, sizes)
+    o, seg_off, idx, gids, _, _ = buf.sample_groups(parts)
+    assert torch.equal(o["target"], new) and torch.equal(gids, grp) and seg_off[-1] == n
+    assert torch.equal(o["obs"], buf.buf_obs[perm]) and torch.equal(o["done"], buf.buf_done[perm].float())
+    assert torch.equal(o["reward"], buf.buf_reward[perm]) and torch.equal(o["next_obs"], buf.buf_next_obs[perm])
