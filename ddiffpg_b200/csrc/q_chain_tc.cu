@@ -21,6 +21,7 @@
 //   Ba  dz1 chunks . W1[:, O:O+A] -> [128 x 16] cols [0, 16)
 // Weight tiles stream from L2 through a 3-stage TMA ring; all K+1 critics live in the same tensor maps (row
 // offset = mode * N), a tile never straddles a mode segment.
+#include <math.h>
 #include <stdlib.h>
 #include <type_traits>
 #include "q_layout.cuh"
@@ -28,6 +29,16 @@
 
 namespace ddp {
 using namespace tc;
+
+// Adam action ascent carried inside the fused kernel (one cooperative launch for all iterations)
+struct QChainAscent {
+    int iters;
+    float* act;                      // [B, A], updated in place
+    float *m1, *m2;                  // zeroed Adam moments [B, A]
+    float* gnorm_out;                // [n_modes, iters] or NULL
+    unsigned int* grid_bar;          // zeroed
+    float lr, beta1, beta2, eps, max_norm, lim;
+};
 
 namespace {
 
@@ -53,6 +64,7 @@ constexpr int kThreads = kEpiThreads + 64;
 constexpr int kTmemCols = 512;
 constexpr int kBiasPerNet = 512 + 256 + 256 + 64;     // b1 | b2 | b3 | b4 slots (floats)
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kMaxIters = 32;               // iterations one cooperative launch can carry
 
 struct alignas(64) QcMaps { CUtensorMap fwd[2][4]; CUtensorMap bwd[2][4]; CUtensorMap xin; };
 
@@ -71,6 +83,17 @@ struct QcArgs {
     int n_modes, num_tiles;
     int O, A, atoms, h1, h2, h3, part1, nparts1;
     float v_min, dz;
+    // multi-iteration ascent in one cooperative launch (iters > 1 or adam != 0): Adam / clip / clamp of
+    // update_target_action applied by the CTA that owns the rows, after a grid-wide barrier on the clip norm
+    int iters;                       // passes over the rows (1 = plain pass, the caller applies Adam)
+    int fused_adam;
+    float* act;                      // [B, A] fp32 actions, updated in place
+    __nv_bfloat16* xin;              // [B, 64] bf16 rows [obs | act | 0]: action columns refreshed
+    float *m1, *m2;                  // Adam moments [B, A]
+    float* gnorm_out;                // [n_modes, iters] pre-clip norms (may be NULL)
+    unsigned int* grid_bar;          // zeroed counter for the grid barrier
+    float step_size[kMaxIters], bc2_sqrt[kMaxIters];
+    float beta1, beta2, eps, max_norm, lim;
     long long* dbg;
 };
 
@@ -96,6 +119,7 @@ __device__ __forceinline__ uint32_t qb_dl_full(uint32_t b) { return b + 8 * (2 *
 __device__ __forceinline__ uint32_t qb_a0_full(uint32_t b) { return b + 8 * (2 * kStages + 2 * kASlots + 4); }
 __device__ __forceinline__ uint32_t qb_a0_free(uint32_t b) { return b + 8 * (2 * kStages + 2 * kASlots + 5); }
 __device__ __forceinline__ uint32_t qb_acc_free(uint32_t b) { return b + 8 * (2 * kStages + 2 * kASlots + 6); }
+__device__ __forceinline__ uint32_t qb_adam_done(uint32_t b) { return b + 8 * (2 * kStages + 2 * kASlots + 7); }
 
 __device__ __forceinline__ void q_epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
@@ -301,6 +325,7 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
         mbar_init(qb_a0_full(bars), 1);
         mbar_init(qb_a0_free(bars), 1);
         mbar_init(qb_acc_free(bars), kEpiWarps);
+        mbar_init(qb_adam_done(bars), kEpiWarps);
         fence_barrier_init();
     }
     if (warp == kEpiWarps + 1) tmem_alloc(base + SMQ::tmem_ptr, kTmemCols);
@@ -331,7 +356,14 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                 mbar_expect_tx(qb_a0_full(bars), kChunkBytes);
                 tma_load_2d(base + SMQ::a0, &maps.xin, qb_a0_full(bars), 0, (int)row0);
             };
-            load_input(blockIdx.x, true);
+            uint32_t adam_phase = 0;
+            for (int it = 0; it < a.iters; ++it) {
+            if (it > 0) {
+                // the owning CTA has rewritten the action columns of its rows (generic proxy, fenced) for this pass
+                mbar_wait(qb_adam_done(bars), adam_phase);
+                adam_phase ^= 1;
+            }
+            load_input(blockIdx.x, it == 0);
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
                 const int m = q_mode_of(a, tile);
                 for (int j = 0; j < 2; ++j) {
@@ -354,6 +386,7 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                             if (q_gated(a, p)) load(&maps.bwd[j][2], c * 64, m * a.h1 + p * a.part1, a.part1);
                     for (int c = 0; c < NC1; ++c) load(&maps.bwd[j][3], c * 64, m * 16, 16);
                 }
+            }
             }
         }
     } else if (warp == kEpiWarps + 1) {
@@ -391,6 +424,7 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                 }
                 acc_done();
             };
+            for (int it = 0; it < a.iters; ++it)
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
                 for (int j = 0; j < 2; ++j) {
                     // the epilogue warps have read everything they need from the accumulator columns (j == 0: the
@@ -456,6 +490,9 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
 #define QC_TICK(slot) do { if (prof) { tk1 = clock64(); a.dbg[slot] += tk1 - tk0; tk0 = tk1; } } while (0)
         int cur_mode = -1;
         if (lane == 0) mbar_arrive(qb_acc_free(bars));          // nothing to drain before the first tile
+        for (int it = 0; it < a.iters; ++it) {
+        const long long iter_t0 = clock64();
+        float* gsq_it = a.gsq ? a.gsq + (size_t)it * kMaxModes : nullptr;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
             const int m = q_mode_of(a, tile);
             const long row = a.seg_off[m] + (long)(tile - a.tile_off[m]) * kRows + e.my_row;
@@ -618,12 +655,57 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                     for (int i = 0; i < 16; ++i)
                         if (i < a.A) { const float g = sc * da[i]; a.g_out[row * a.A + i] = g; ss += g * g; }
                 }
-                if (a.gsq) {
+                if (gsq_it) {
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                    if (lane == 0 && ss != 0.f) atomicAdd(a.gsq + m, ss);
+                    if (lane == 0 && ss != 0.f) atomicAdd(gsq_it + m, ss);
                 }
             }
+        }
+        if (a.fused_adam) {
+            // ---- grid-wide barrier: every CTA has added its rows to the clip norms of this iteration
+            q_epi_bar_sync();
+            if (a.dbg && threadIdx.x == 0) a.dbg[32 + blockIdx.x] += clock64() - iter_t0;   // work of this pass, before the wait
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(a.grid_bar, 1u);
+                const unsigned target = (unsigned)(it + 1) * gridDim.x;
+                unsigned seen, spins = 0;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.grid_bar) : "memory");
+                    if (seen < target) { __nanosleep(64); if (++spins > (1u << 26)) asm volatile("trap;"); }
+                } while (seen < target);
+            }
+            q_epi_bar_sync();
+            // ---- clip_grad_norm_ + Adam + clamp_ on the rows this CTA owns (ac_base.py:86-91, ddiffpg.py:362-369)
+            const float step_size = a.step_size[it], bc2_sqrt = a.bc2_sqrt[it];
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+                const int m = q_mode_of(a, tile);
+                const long row0 = a.seg_off[m] + (long)(tile - a.tile_off[m]) * kRows;
+                const long left = a.seg_off[m + 1] - row0;
+                const int nv = left < kRows ? (int)left : kRows;
+                const float norm = sqrtf(__ldcg(gsq_it + m));
+                const float coef = fminf(a.max_norm / (norm + 1e-6f), 1.0f);
+                for (int i = threadIdx.x; i < nv * a.A; i += kEpiThreads) {
+                    const long idx = row0 * a.A + i;
+                    const float gi = __ldcg(a.g_out + idx) * coef;
+                    const float ea = a.m1[idx] * a.beta1 + (1.f - a.beta1) * gi;
+                    const float ev = a.m2[idx] * a.beta2 + (1.f - a.beta2) * gi * gi;
+                    a.m1[idx] = ea; a.m2[idx] = ev;
+                    float v = a.act[idx] - step_size * (ea / (sqrtf(ev) / bc2_sqrt + a.eps));
+                    v = fminf(fmaxf(v, -a.lim), a.lim);
+                    a.act[idx] = v;
+                    const int r = i / a.A, c = i - r * a.A;
+                    a.xin[(row0 + r) * 64 + a.O + c] = __float2bfloat16(v);
+                }
+            }
+            if (blockIdx.x == 0 && a.gnorm_out && (int)threadIdx.x < a.n_modes)
+                a.gnorm_out[threadIdx.x * a.iters + it] = sqrtf(__ldcg(gsq_it + threadIdx.x));
+            // the refreshed rows are read back through TMA (async proxy) by this CTA's producer lane
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(qb_adam_done(bars));
+        }
         }
 #undef QC_TICK
     }
@@ -667,7 +749,7 @@ size_t q_chain_workspace(const QLayout& L) {
 // gsq[m] += sum over the segment of g^2 (gsq may be NULL).  qmin / p1 / p2 optional.
 int q_chain_pass(const QLayout& L, const void* packed, const int64_t* seg_off, const float* scale, const void* xin,
                  float* g_out, float* gsq, float* qmin, float* p1, float* p2, long B, void* scratch,
-                 size_t scratch_bytes, cudaStream_t st) {
+                 size_t scratch_bytes, cudaStream_t st, const QChainAscent* asc) {
     if (!q_chain_shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "fused critic kernel does not support this shape");
     if (!scratch || scratch_bytes < q_chain_workspace(L)) DDP_FAIL(DDP_ERR_ARG, "fused critic kernel: scratch too small");
     const uint8_t* pb = (const uint8_t*)packed;
@@ -689,6 +771,19 @@ int q_chain_pass(const QLayout& L, const void* packed, const int64_t* seg_off, c
     a.v_min = L.v_min;
     a.dz = (L.v_max - L.v_min) / (float)(L.atoms - 1);
     a.dbg = g_qc_dbg;
+    a.iters = 1;
+    if (asc) {
+        if (asc->iters < 1 || asc->iters > kMaxIters) DDP_FAIL(DDP_ERR_ARG, "fused ascent carries 1..%d iterations per launch", kMaxIters);
+        a.iters = asc->iters; a.fused_adam = 1;
+        a.act = asc->act; a.xin = (__nv_bfloat16*)const_cast<void*>(xin); a.m1 = asc->m1; a.m2 = asc->m2;
+        a.gnorm_out = asc->gnorm_out; a.grid_bar = asc->grid_bar;
+        a.beta1 = asc->beta1; a.beta2 = asc->beta2; a.eps = asc->eps; a.max_norm = asc->max_norm; a.lim = asc->lim;
+        for (int it = 0; it < asc->iters; ++it) {
+            const double bc1 = 1.0 - pow((double)asc->beta1, it + 1), bc2 = 1.0 - pow((double)asc->beta2, it + 1);
+            a.step_size[it] = (float)(asc->lr / bc1);
+            a.bc2_sqrt[it] = (float)sqrt(bc2);
+        }
+    }
     if (a.num_tiles == 0) return DDP_OK;
     QcMaps maps;
     const uint64_t M = (uint64_t)L.n_modes;
@@ -714,6 +809,13 @@ int q_chain_pass(const QLayout& L, const void* packed, const int64_t* seg_off, c
     int grid = a.num_tiles < sms ? a.num_tiles : sms;
     static const int grid_cap = getenv("DDP_QC_GRID") ? atoi(getenv("DDP_QC_GRID")) : 0;      // experiments only
     if (grid_cap > 0 && grid_cap < grid) grid = grid_cap;
+    if (asc) {
+        // the grid barrier needs every CTA resident at once: cooperative launch, one CTA per SM
+        void* kargs[2] = {(void*)&maps, (void*)&a};
+        cudaError_t err = cudaLaunchCooperativeKernel((const void*)q_chain_tc_kernel, dim3(grid), dim3(kThreads), kargs, smem, st);
+        if (err != cudaSuccess) DDP_FAIL(DDP_ERR_CUDA, "cooperative launch of q_chain_tc_kernel failed: %s", cudaGetErrorString(err));
+        return DDP_OK;
+    }
     q_chain_tc_kernel<<<grid, kThreads, smem, st>>>(maps, a);
     DDP_LAUNCH_CHECK("q_chain_tc_kernel");
     return DDP_OK;

@@ -18,9 +18,17 @@ namespace ddp {
 // fused per-tile forward/backward chain (csrc/q_chain_tc.cu)
 bool q_chain_shape_ok(const QLayout& L);
 size_t q_chain_workspace(const QLayout& L);
+struct QChainAscent {
+    int iters;
+    float* act;
+    float *m1, *m2;
+    float* gnorm_out;
+    unsigned int* grid_bar;
+    float lr, beta1, beta2, eps, max_norm, lim;
+};
 int q_chain_pass(const QLayout& L, const void* packed, const int64_t* seg_off, const float* scale, const void* xin,
                  float* g_out, float* gsq, float* qmin, float* p1, float* p2, long B, void* scratch,
-                 size_t scratch_bytes, cudaStream_t st);
+                 size_t scratch_bytes, cudaStream_t st, const QChainAscent* asc);
 
 namespace {
 
@@ -41,6 +49,7 @@ struct QSeg {
 struct QTcWs {
     bf16 *xin, *a1[2], *a2[2], *a3[2], *dl[2];
     float *logits[2], *ga[2], *g, *m1, *m2, *gsq, *abs_sum;
+    unsigned int* grid_bar;
     void* chain_scratch;
     size_t total, adam_bytes;
 };
@@ -66,6 +75,7 @@ QTcWs carve(const QLayout& L, long B, int iters, uint8_t* base) {
     w.m2 = (float*)take((size_t)B * L.A * 4);
     w.gsq = (float*)take((size_t)(iters > 0 ? iters : 1) * kMaxModes * 4);
     w.abs_sum = (float*)take(kMaxModes * 4);
+    w.grid_bar = (unsigned int*)take(256);
     w.adam_bytes = o - adam0;
     w.total = o;
     return w;
@@ -303,7 +313,7 @@ int q_forward_tc(const QLayout& L, const void* packed, const int64_t* seg_off, c
     q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, const_cast<float*>(act), L.O, L.A, B, 0.f, w.xin);
     if (use_chain(L))
         return q_chain_pass(L, packed, seg_off, nullptr, w.xin, dq_da, nullptr, qmin, p1, p2, B, w.chain_scratch,
-                            q_chain_workspace(L), st);
+                            q_chain_workspace(L), st, nullptr);
     int rc = q_tc_pass(L, (const uint8_t*)packed, w, seg, B, dq_da != nullptr, qmin, p1, p2, st);
     if (rc != DDP_OK) return rc;
     if (dq_da) {
@@ -328,11 +338,22 @@ int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, co
     const bool chain = use_chain(L);
     float neg_inv[kMaxModes];
     for (int m = 0; m < L.n_modes; ++m) neg_inv[m] = -seg.inv_cnt[m];
+    // DDP_Q_FUSED_ADAM=1: all iterations in ONE cooperative launch (grid barrier on the clip norm, Adam applied by the
+    // CTA that owns the rows).  Measured equal to one launch per iteration + the Adam kernel (4.41 vs 4.33 ms: the
+    // stream already hides the launches, a pass is 344 k cycles of tile work either way), so it stays opt-in.
+    static const bool fused = getenv("DDP_Q_FUSED_ADAM") && atoi(getenv("DDP_Q_FUSED_ADAM")) != 0;
+    if (chain && fused && iters >= 1 && iters <= 32) {
+        QChainAscent asc{iters, action, w.m1, w.m2, gnorm_out, w.grid_bar, lr, b1, b2, eps, max_norm, lim};
+        int rc = q_chain_pass(L, packed, seg_off, neg_inv, w.xin, w.g, w.gsq, nullptr, nullptr, nullptr, B,
+                              w.chain_scratch, q_chain_workspace(L), st, &asc);
+        if (rc != DDP_OK) return rc;
+        iters = 0;                      // nothing left for the per-iteration loop below
+    }
     for (int it = 0; it < iters; ++it) {
         float* gsq = w.gsq + (size_t)it * kMaxModes;
         if (chain) {
             int rc = q_chain_pass(L, packed, seg_off, neg_inv, w.xin, w.g, gsq, nullptr, nullptr, nullptr, B,
-                                  w.chain_scratch, q_chain_workspace(L), st);
+                                  w.chain_scratch, q_chain_workspace(L), st, nullptr);
             if (rc != DDP_OK) return rc;
         } else {
             int rc = q_tc_pass(L, (const uint8_t*)packed, w, seg, B, true, nullptr, nullptr, nullptr, st);

@@ -17,7 +17,7 @@ torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 ev[0].record(); run(); ev[1].record(); torch.cuda.synchronize()
 print(f"ascent B={B}: {ev[0].elapsed_time(ev[1]):.3f} ms for {iters} iterations")
-buf = torch.zeros(32, dtype=torch.int64, device='cuda')
+buf = torch.zeros(256, dtype=torch.int64, device='cuda')
 L.ddp_debug_qc_timing(buf.data_ptr())
 run(); torch.cuda.synchronize()
 L.ddp_debug_qc_timing(None)
@@ -32,3 +32,11 @@ for off, nm in ((16, "forward drains"), (24, "backward drains")):
     v = buf[off:off + 7].tolist(); n = max(v[6], 1)
     print(f"{nm}: {n} chunks, {sum(v[:6])/n:.0f} clk per chunk")
     for k in range(6): print(f"    {fn[k]:28s} {v[k]/n:7.0f} clk")
+per = buf[32:32 + 148].tolist()
+if any(per):
+    import statistics
+    a4 = [v for i, v in enumerate(per) if v and i < tiles - 3 * grid]; a3 = [v for i, v in enumerate(per) if v and i >= tiles - 3 * grid]
+    print(f"per-CTA work cycles per pass (x{iters} passes, before the barrier wait): 4-tile CTAs n={len(a4)} min {min(a4)/iters/1e3:.0f}k med {statistics.median(a4)/iters/1e3:.0f}k max {max(a4)/iters/1e3:.0f}k;"
+          f" 3-tile CTAs n={len(a3)} min {min(a3)/iters/1e3:.0f}k med {statistics.median(a3)/iters/1e3:.0f}k max {max(a3)/iters/1e3:.0f}k")
+    worst = sorted(range(148), key=lambda i: -per[i])[:8]
+    print("slowest CTAs:", [(i, round(per[i] / iters / 1e3)) for i in worst])
