@@ -36,8 +36,8 @@ using bf16 = __nv_bfloat16;
 
 // DDP_Q_NO_CHAIN=1 selects the layer-by-layer GEMM path even where the fused kernel applies (A/B measurements)
 bool use_chain(const QLayout& L) {
-    static const bool off = getenv("DDP_Q_NO_CHAIN") && atoi(getenv("DDP_Q_NO_CHAIN")) != 0;
-    return !off && q_chain_shape_ok(L);
+    const char* e = getenv("DDP_Q_NO_CHAIN");          // read per call: tests flip it
+    return !(e && atoi(e) != 0) && q_chain_shape_ok(L);
 }
 
 struct QSeg {
@@ -341,7 +341,7 @@ int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, co
     // DDP_Q_FUSED_ADAM=1: all iterations in ONE cooperative launch (grid barrier on the clip norm, Adam applied by the
     // CTA that owns the rows).  Measured equal to one launch per iteration + the Adam kernel (4.41 vs 4.33 ms: the
     // stream already hides the launches, a pass is 344 k cycles of tile work either way), so it stays opt-in.
-    static const bool fused = getenv("DDP_Q_FUSED_ADAM") && atoi(getenv("DDP_Q_FUSED_ADAM")) != 0;
+    const bool fused = getenv("DDP_Q_FUSED_ADAM") && atoi(getenv("DDP_Q_FUSED_ADAM")) != 0;
     if (chain && fused && iters >= 1 && iters <= 32) {
         QChainAscent asc{iters, action, w.m1, w.m2, gnorm_out, w.grid_bar, lr, b1, b2, eps, max_norm, lim};
         int rc = q_chain_pass(L, packed, seg_off, neg_inv, w.xin, w.g, w.gsq, nullptr, nullptr, nullptr, B,
