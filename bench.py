@@ -264,9 +264,14 @@ def run_cuda(args):
     ms = timed(step, args.steps)
     # nvidia-smi polls every 100 ms and K steps can be shorter than one poll: keep the identical loop (flush + step)
     # running, untimed, until the sampler has seen >= 0.6 s of this load pattern, then stop it
-    t_end = time.time() + max(0.0, 0.6 - ms * 1e-3)
-    while time.time() < t_end:
-        timed(step, 4)
+    # (same step count on every rank: the training step contains a collective)
+    ms_all = ms
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_all = tmax.item()
+    per_step = max(ms_all / args.steps, 0.05) + 0.15          # + the untimed L2 flush
+    timed(step, min(2000, max(0, int((600.0 - ms_all) / per_step))))
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
