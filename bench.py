@@ -24,6 +24,25 @@ S, A, O = 34, 8, 29
 L2_FLUSH_BYTES = 256 << 20
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries print to fd 1 (NCCL's version banner, torchrun notices) goes to stderr; the JSON line is
+    written to the original stdout by emit(), so stdout carries exactly one line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def algorithmic_flops(workload, T, h):
     """minimal FLOPs after removing batch- and loop-invariant terms."""
     if workload == "sample":
@@ -127,7 +146,7 @@ def run_reference(args):
                              "sample": f"{sample_rows} rows per step x {args.steps} steps, torch CPU fp32, "
                                        f"{cores} threads (oracle port of the reference modules)"},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def metric_name(workload):
@@ -347,7 +366,7 @@ def run_cuda(args):
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -367,6 +386,7 @@ def main():
     ap.add_argument("--modes", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    quiet_stdout()
     if args.precision is None:
         args.precision = os.environ.get("DDP_BENCH_PRECISION", "bf16")
     if args.impl == "reference":
