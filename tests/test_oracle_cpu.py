@@ -299,3 +299,23 @@ def test_port_replay_matches_reference_fixture():
     np.testing.assert_array_equal(port.add_embedding_port(torch.from_numpy(g["g0_obs"]), emb, []).numpy(), g["emb_state_p0"])
     port.replay_scatter(store, torch.from_numpy(g["new_action"]), torch.from_numpy(g["idx_2"]), 2)
     np.testing.assert_array_equal(store["target_action"].numpy(), g["target_after"])
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py contract on the CPU-only arm: exactly one line on stdout, valid JSON, the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["vs_baseline"] is None and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
