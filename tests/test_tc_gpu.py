@@ -313,3 +313,74 @@ def test_q_chain_full_size_row_permutation():
     cri.precision = "bf16"
     q0, q1 = cri.get_q_min(obs, act).mean().item(), cri.get_q_min(obs, a1).mean().item()
     assert q1 > q0
+
+
+# ------------------------------------------------------------------------------------------ 1M-row shapes (BASELINE configs[2], [3])
+def test_million_row_train_gradient_is_mean_of_halves():
+    """configs[3] size (1 M rows): loss and gradient are means over rows, so the full batch must equal the average
+    of its two halves (linearity of the backward in the batch) -- holds for any size, checked at the largest."""
+    B, T = 1 << 20, 5
+    gen = torch.Generator(device="cuda").manual_seed(23)
+    pol = make_policy(port.init_actor_params(140), T)
+    state = torch.randn(B, 34, device="cuda", generator=gen)
+    action = torch.rand(B, 8, device="cuda", generator=gen) * 2 - 1
+    noise = torch.randn(B, 8, device="cuda", generator=gen)
+    ts = torch.randint(0, T, (B,), device="cuda", generator=gen)
+    full_l, full_g = pol._loss_and_grads(state, action, noise, ts, precision="bf16")
+    full_l, full_g = full_l.clone(), full_g.clone()
+    h = B // 2
+    l0, g0 = pol._loss_and_grads(state[:h], action[:h], noise[:h], ts[:h], precision="bf16")
+    l0, g0 = l0.clone(), g0.clone()
+    l1, g1 = pol._loss_and_grads(state[h:], action[h:], noise[h:], ts[h:], precision="bf16")
+    assert torch.isfinite(full_g).all()
+    assert abs(full_l.item() - 0.5 * (l0.item() + l1.item())) <= 1e-4 * abs(full_l.item())
+    rel = ((full_g - 0.5 * (g0 + g1)).norm() / full_g.norm()).item()
+    assert rel <= 1e-3, rel                        # fp32 atomics in a different order, bf16 operands identical
+
+
+def test_million_state_ascent_rows_are_independent_given_the_norm():
+    """configs[2] size (1 M states, 8 mode segments of uneven length): finite, inside the clamp, and the objective
+    of every mode rises; a 4 096-row slice run alone with the same 1/B factor and an inactive clip reproduces its
+    rows (rows only couple through the mean factor and the clip norm)."""
+    from tests.util import make_critic
+    from ddiffpg_b200 import q_action_ascent_segments
+    B = 1 << 20
+    gen = torch.Generator(device="cuda").manual_seed(29)
+    sizes = [200000, 100001, 150000, 99999, 131072, 50000, 17504, 300000]
+    assert sum(sizes) == B
+    off = [0]
+    for s in sizes:
+        off.append(off[-1] + s)
+    critics = [make_critic(port.init_critic_params(150 + i, scale=2.0)) for i in range(len(sizes))]
+    obs = torch.randn(B, 29, device="cuda", generator=gen)
+    act = torch.rand(B, 8, device="cuda", generator=gen) * 2 - 1
+    work = act.clone()
+    # max_norm = inf: the clip coefficient is exactly 1 for every segment
+    q_action_ascent_segments(critics, obs, work, off, iters=20, precision="bf16", max_norm=None)
+    assert torch.isfinite(work).all() and work.abs().max().item() <= 1 - 1e-5 + 1e-7
+    for i, c in enumerate(critics):
+        c.requires_grad_(False)
+        c.precision = "bf16"
+        sl = slice(off[i], off[i] + 4096)
+        assert c.get_q_min(obs[sl], work[sl]).mean().item() > c.get_q_min(obs[sl], act[sl]).mean().item(), i
+    sl = slice(off[3] + 1000, off[3] + 1000 + 4096)
+    part = act[sl].clone()
+    q_action_ascent_segments([critics[3]], obs[sl].contiguous(), part, [0, 4096], iters=20, precision="bf16", max_norm=None,
+                             mean_counts=[sizes[3]])
+    d = (part - work[sl]).abs().max(1).values
+    assert (d <= 1e-3).float().mean().item() >= 0.995        # tile position changes nothing; ridge rows may flip
+
+
+def test_million_row_sampler_equals_chunked_calls():
+    """1 M rows through the fused sampler in one call == four 262 144-row calls (rows never interact)."""
+    B, T = 1 << 20, 5
+    gen = torch.Generator(device="cuda").manual_seed(31)
+    pol = make_policy(port.init_actor_params(141), T, precision="bf16")
+    state = torch.randn(B, 34, device="cuda", generator=gen)
+    noise = torch.randn(T, B, 8, device="cuda", generator=gen)
+    out = pol.get_actions(state, noise=noise)
+    assert torch.isfinite(out).all() and out.abs().max().item() <= 1.0
+    q = B // 4
+    for i in range(4):
+        sl = slice(i * q, (i + 1) * q)
+        assert torch.equal(out[sl], pol.get_actions(state[sl].contiguous(), noise=noise[:, sl].contiguous()))
