@@ -233,7 +233,7 @@ def run_cuda(args):
         pol = DiffusionPolicy(S, A, T, device="cuda", hidden=hidden)
         cpu_params = {k: v.clone() for k, v in pol.state_dict().items()}
         pol.to(dev)
-        trainer = FusedActorTrainer(pol, precision=args.precision)
+        trainer = FusedActorTrainer(pol, precision=args.precision, graph=not args.no_graph)
         st_h = torch.randn(B, S, generator=gen).pin_memory()
         ac_h = (torch.rand(B, A, generator=gen) * 2 - 1).pin_memory()
         st, ac = st_h.to(dev), ac_h.to(dev)
@@ -385,6 +385,7 @@ def main():
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--modes", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="train workload: eager launches instead of the CUDA graph")
     args = ap.parse_args()
     quiet_stdout()
     if args.precision is None:

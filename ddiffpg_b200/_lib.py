@@ -36,6 +36,7 @@ PROTOTYPES = {
     "ddp_last_error": (c_char_p, []),
     "ddp_actor_packed_bytes": (c_size_t, [POINTER(ActorShape), c_int]),
     "ddp_actor_pack": (c_int, [POINTER(ActorShape), POINTER(c_void_p), c_void_p, c_int, c_void_p]),
+    "ddp_actor_pack_parts": (c_int, [POINTER(ActorShape), POINTER(c_void_p), c_void_p, c_int, c_int, c_void_p]),
     "ddp_actor_sample_workspace_bytes": (c_size_t, [POINTER(ActorShape), c_long, c_int]),
     "ddp_actor_sample": (c_int, [POINTER(ActorShape), c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int,
                                  c_void_p, c_size_t, c_void_p]),
@@ -48,6 +49,8 @@ PROTOTYPES = {
                                        c_size_t, c_void_p]),
     "ddp_clip_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_float, c_float,
                                     c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "ddp_clip_adamw_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_float, c_float,
+                                        c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "ddp_q_packed_bytes": (c_size_t, [POINTER(QShape), c_int]),
     "ddp_q_pack": (c_int, [POINTER(QShape), POINTER(c_void_p), c_void_p, c_int, c_void_p]),
     "ddp_q_forward_workspace_bytes": (c_size_t, [POINTER(QShape), c_long, c_int]),

@@ -190,8 +190,12 @@ class FusedActorTrainer:
     ``torch.optim.AdamW(actor.parameters(), actor_lr)`` (ac_base.py:52) and ``max_grad_norm`` 1.0."""
 
     def __init__(self, actor, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0,
-                 process_group=None, precision=None):
+                 process_group=None, precision=None, graph=False):
         self.actor = actor
+        # graph=True: the whole step (re-pack, forward/backward, all-reduce, clip + AdamW: ~50 launches) is captured
+        # once per batch shape into a CUDA graph and replayed; the Adam step count lives on the device
+        self.use_graph = graph
+        self._graphs = {}
         self.precision = precision          # None: actor.train_precision ("fp32" | "bf16")
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.max_grad_norm = float("inf") if max_grad_norm is None else max_grad_norm
@@ -209,7 +213,8 @@ class FusedActorTrainer:
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = 0
         self._norm = torch.zeros(1, device=dev)
-        self._scratch = torch.zeros(1, device=dev)
+        self._scratch = torch.zeros(4, device=dev)
+        self._step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         actor.mark_dirty()
 
     def _check_flat(self):
@@ -236,6 +241,14 @@ class FusedActorTrainer:
             noise = torch.randn(action.shape, device=dev, dtype=torch.float32)
         if timesteps is None:
             timesteps = torch.randint(0, actor.diffusion_iter, (B,), device=dev)
+        if self.use_graph:
+            return self._step_graph(state, action, noise, timesteps, global_batch)
+        loss, norm = self._step_body(state, action, noise, timesteps, global_batch)
+        return loss, norm.clone()
+
+    def _step_body(self, state, action, noise, timesteps, global_batch):
+        actor = self.actor
+        dev = self.flat.device
         loss, grads = actor._loss_and_grads(state, action, noise, timesteps,
                                             inv_count=1.0 / (global_batch * actor.action_dim),
                                             precision=self.precision)
@@ -243,13 +256,40 @@ class FusedActorTrainer:
         ddist.allreduce_sum_(grads, loss, group=self.group)
         self.step_count += 1
         with torch.cuda.device(dev):
-            check(lib().ddp_clip_adamw_step(ptr(self.flat), ptr(grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                                            self.flat.numel(), self.step_count, self.lr, self.betas[0],
-                                            self.betas[1], self.eps, self.weight_decay, self.max_grad_norm,
-                                            ptr(self._norm), ptr(self._scratch), stream_ptr()),
-                  "ddp_clip_adamw_step")
+            check(lib().ddp_clip_adamw_step_dev(ptr(self.flat), ptr(grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                                self.flat.numel(), ptr(self._step_dev), self.lr, self.betas[0],
+                                                self.betas[1], self.eps, self.weight_decay, self.max_grad_norm,
+                                                ptr(self._norm), ptr(self._scratch), stream_ptr()),
+                  "ddp_clip_adamw_step_dev")
         actor.mark_dirty()
-        return loss, self._norm[0].clone()
+        return loss, self._norm[0]
+
+    def _step_graph(self, state, action, noise, timesteps, global_batch):
+        dev = self.flat.device
+        key = (tuple(state.shape), tuple(action.shape), int(global_batch), self.precision or self.actor.train_precision)
+        ent = self._graphs.get(key)
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32)
+        if ent is None:
+            # first step of this shape runs eagerly (sizes the workspaces and the weight pack); the static inputs
+            # the graph will read are created here
+            ent = {"state": f32(state).clone(), "action": f32(action).clone(), "noise": f32(noise).clone(),
+                   "ts": timesteps.detach().to(device=dev, dtype=torch.int64).clone(), "graph": None}
+            self._graphs[key] = ent
+            loss, norm = self._step_body(ent["state"], ent["action"], ent["noise"], ent["ts"], global_batch)
+            return loss.clone(), norm.clone()
+        ent["state"].copy_(state); ent["action"].copy_(action); ent["noise"].copy_(noise); ent["ts"].copy_(timesteps)
+        if ent["graph"] is None:
+            self.actor.mark_dirty()                  # the capture must contain the weight re-pack
+            g = torch.cuda.CUDAGraph()
+            count = self.step_count
+            with torch.cuda.graph(g):
+                ent["loss"], ent["norm"] = self._step_body(ent["state"], ent["action"], ent["noise"], ent["ts"], global_batch)
+            self.step_count = count                  # capturing records, it does not execute
+            ent["graph"] = g
+        ent["graph"].replay()
+        self.step_count += 1
+        self.actor.mark_dirty()
+        return ent["loss"].clone(), ent["norm"].clone()
 
 
 class HotPathMixin:

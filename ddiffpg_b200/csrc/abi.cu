@@ -14,8 +14,8 @@ void set_error(const char* fmt, ...) {
 }
 
 // implemented in the kernel translation units
-int pack_actor_fp32(const ActorLayout& L, const float* const p[12], float* out, cudaStream_t st);
-int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, cudaStream_t st);
+int pack_actor_fp32(const ActorLayout& L, const float* const p[12], float* out, bool fma_operands, cudaStream_t st);
+int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, bool sampler, cudaStream_t st);
 int actor_sample_fma(const ActorLayout& L, const float* pk, const float* state, const float* noise, float* out,
                      long B, const ExplNoise& expl, cudaStream_t st);
 int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state, const float* noise, float* out,
@@ -32,6 +32,8 @@ int actor_train_tc(const ActorLayout& L, const void* packed, const float* const 
                    float* grads, long B, void* ws, size_t ws_bytes, cudaStream_t st);
 int clip_adamw(float* p, float* g, float* m, float* v, size_t n, int step, float lr, float b1, float b2, float eps,
                float wd, float max_norm, float* norm_out, float* scratch, cudaStream_t st);
+int clip_adamw_dev(float* p, float* g, float* m, float* v, size_t n, int* step_dev, float lr, float b1, float b2,
+                   float eps, float wd, float max_norm, float* norm_out, float* scratch, cudaStream_t st);
 int pack_q_fp32(const QLayout& L, const float* const p[], float* out, cudaStream_t st);
 int q_forward_fma(const QLayout& L, const float* pk, const int64_t* seg_off, const float* obs, const float* act,
                   float* qmin, float* p1, float* p2, float* dq_da, long B, cudaStream_t st);
@@ -77,8 +79,8 @@ size_t ddp_actor_packed_bytes(const ddp_actor_shape* s, int precision) {
     return make_actor_layout(*s, precision).total_bytes;
 }
 
-int ddp_actor_pack(const ddp_actor_shape* s, const float* const params[12], void* packed, int precision,
-                   void* stream) {
+int ddp_actor_pack_parts(const ddp_actor_shape* s, const float* const params[12], void* packed, int precision,
+                         int parts, void* stream) {
     int rc = check_actor_shape(s);
     if (rc != DDP_OK) return rc;
     if (!params || !packed) DDP_FAIL(DDP_ERR_ARG, "ddp_actor_pack: NULL argument");
@@ -86,16 +88,24 @@ int ddp_actor_pack(const ddp_actor_shape* s, const float* const params[12], void
         if (!params[i]) DDP_FAIL(DDP_ERR_ARG, "ddp_actor_pack: params[%d] is NULL", i);
     if (!aligned16(packed)) DDP_FAIL(DDP_ERR_ARG, "ddp_actor_pack: packed buffer must be 16-byte aligned");
     if (precision != DDP_FP32 && precision != DDP_BF16) DDP_FAIL(DDP_ERR_ARG, "unknown precision %d", precision);
+    if (!(parts & (DDP_PACK_SAMPLE | DDP_PACK_TRAIN))) DDP_FAIL(DDP_ERR_ARG, "ddp_actor_pack_parts: empty part mask %d", parts);
     ActorLayout L = make_actor_layout(*s, precision);
     cudaStream_t st = (cudaStream_t)stream;
-    rc = pack_actor_fp32(L, params, (float*)packed, st);
+    // biases, scheduler constants and the time table serve every consumer; the transposed fp32 weights only the
+    // warp-FMA kernels
+    rc = pack_actor_fp32(L, params, (float*)packed, precision == DDP_FP32, st);
     if (rc != DDP_OK) return rc;
     if (precision == DDP_BF16) {
-        rc = pack_actor_tc(L, params, packed, st);
+        rc = pack_actor_tc(L, params, packed, (parts & DDP_PACK_SAMPLE) != 0, st);
         if (rc != DDP_OK) return rc;
-        return pack_actor_train_tc(L, params, packed, st);
+        if (parts & DDP_PACK_TRAIN) return pack_actor_train_tc(L, params, packed, st);
     }
     return DDP_OK;
+}
+
+int ddp_actor_pack(const ddp_actor_shape* s, const float* const params[12], void* packed, int precision,
+                   void* stream) {
+    return ddp_actor_pack_parts(s, params, packed, precision, DDP_PACK_SAMPLE | DDP_PACK_TRAIN, stream);
 }
 
 size_t ddp_actor_sample_workspace_bytes(const ddp_actor_shape* s, long B, int precision) {
@@ -167,6 +177,16 @@ int ddp_clip_adamw_step(float* params_flat, float* grads_flat, float* exp_avg, f
     if (n == 0) return DDP_OK;
     return clip_adamw(params_flat, grads_flat, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, weight_decay,
                       max_norm, norm_out, scratch, (cudaStream_t)stream);
+}
+
+int ddp_clip_adamw_step_dev(float* params_flat, float* grads_flat, float* exp_avg, float* exp_avg_sq, size_t n,
+                            int* step_counter, float lr, float beta1, float beta2, float eps, float weight_decay,
+                            float max_norm, float* norm_out, float* scratch, void* stream) {
+    if (!params_flat || !grads_flat || !exp_avg || !exp_avg_sq || !norm_out || !scratch || !step_counter)
+        DDP_FAIL(DDP_ERR_ARG, "ddp_clip_adamw_step_dev: NULL argument");
+    if (n == 0) return DDP_OK;
+    return clip_adamw_dev(params_flat, grads_flat, exp_avg, exp_avg_sq, n, step_counter, lr, beta1, beta2, eps,
+                          weight_decay, max_norm, norm_out, scratch, (cudaStream_t)stream);
 }
 
 size_t ddp_q_packed_bytes(const ddp_q_shape* s, int precision) {

@@ -90,18 +90,21 @@ __global__ void rows_linear_kernel(const float* __restrict__ W, int ldw, int kof
     }
 }
 
-int pack_actor_fp32(const ActorLayout& L, const float* const p[12], float* out, cudaStream_t st) {
+int pack_actor_fp32(const ActorLayout& L, const float* const p[12], float* out, bool fma_operands, cudaStream_t st) {
     const int D = L.D, S = L.S, A = L.A, T = L.T;
     const int ld0 = D + S + A;
     auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
-    transpose_pack_kernel<<<blocks((size_t)L.K0p * L.h1), 256, 0, st>>>(p[4], ld0, D, S + A, L.K0p, L.h1, L.h1, out + L.wt0);
-    transpose_pack_kernel<<<blocks((size_t)L.h1 * L.h2), 256, 0, st>>>(p[6], L.h1, 0, L.h1, L.h1, L.h2, L.h2, out + L.wt1);
-    transpose_pack_kernel<<<blocks((size_t)L.h2 * L.h3), 256, 0, st>>>(p[8], L.h2, 0, L.h2, L.h2, L.h3, L.h3, out + L.wt2);
-    transpose_pack_kernel<<<blocks((size_t)L.h3 * L.A4), 256, 0, st>>>(p[10], L.h3, 0, L.h3, L.h3, A, L.A4, out + L.wt3);
+    if (fma_operands) {
+        // transposed fp32 weights: streamed by the warp-FMA kernels only (the tensor paths read their own 16-bit copies)
+        transpose_pack_kernel<<<blocks((size_t)L.K0p * L.h1), 256, 0, st>>>(p[4], ld0, D, S + A, L.K0p, L.h1, L.h1, out + L.wt0);
+        transpose_pack_kernel<<<blocks((size_t)L.h1 * L.h2), 256, 0, st>>>(p[6], L.h1, 0, L.h1, L.h1, L.h2, L.h2, out + L.wt1);
+        transpose_pack_kernel<<<blocks((size_t)L.h2 * L.h3), 256, 0, st>>>(p[8], L.h2, 0, L.h2, L.h2, L.h3, L.h3, out + L.wt2);
+        transpose_pack_kernel<<<blocks((size_t)L.h3 * L.A4), 256, 0, st>>>(p[10], L.h3, 0, L.h3, L.h3, A, L.A4, out + L.wt3);
+        copy_pad_kernel<<<blocks((size_t)L.A4 * L.h3), 256, 0, st>>>(p[10], A * L.h3, L.A4 * L.h3, out + L.w3b);
+    }
     copy_pad_kernel<<<blocks(L.h2), 256, 0, st>>>(p[7], L.h2, L.h2, out + L.b1);
     copy_pad_kernel<<<blocks(L.h3), 256, 0, st>>>(p[9], L.h3, L.h3, out + L.b2);
     copy_pad_kernel<<<blocks(L.A4), 256, 0, st>>>(p[11], A, L.A4, out + L.b3);
-    copy_pad_kernel<<<blocks((size_t)L.A4 * L.h3), 256, 0, st>>>(p[10], A * L.h3, L.A4 * L.h3, out + L.w3b);
     ScheduleTable tab;
     fill_schedule(T, tab);
     schedule_store_kernel<<<blocks((size_t)T * kCstStride), 256, 0, st>>>(tab, T, out + L.cst);

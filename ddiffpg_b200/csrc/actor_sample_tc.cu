@@ -571,7 +571,7 @@ static bool tc_shape_ok(const ActorLayout& L) {
            (L.h2 <= 256 || L.h2 % 256 == 0);
 }
 
-int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, cudaStream_t st) {
+int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, bool sampler, cudaStream_t st) {
     if (!tc_shape_ok(L))
         DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 actor path needs A<=8, S<=40, widths multiple of 64 with h2<=512, h3<=256");
     uint8_t* base = (uint8_t*)packed;
@@ -579,14 +579,17 @@ int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, 
     const int ld0 = L.D + L.S + L.A;
     const size_t n0 = (size_t)(L.h1 / 32) * 12 * 32, n1 = (size_t)L.h2 * L.h1, n2 = (size_t)L.h3 * L.h2,
                  n3 = (size_t)(L.h3 / 64) * 1024;
-    w0_frag_pack_kernel<false><<<blocks(n0), 256, 0, st>>>(p[4], ld0, L.D, L.S, L.A, L.h1, (uint2*)(base + L.tc_w0));
-    w0_frag_pack_kernel<true><<<blocks(n0), 256, 0, st>>>(p[4], ld0, L.D, L.S, L.A, L.h1, (uint2*)(base + L.tc_w0h));
+    // bf16 W1 / W2: read by the sampler and by the training GEMMs; everything else is the sampler's own
     f32_to_16_kernel<false><<<blocks(n1), 256, 0, st>>>(p[6], (uint16_t*)(base + L.tc_w1), n1);
-    f32_to_16_kernel<true><<<blocks(n1), 256, 0, st>>>(p[6], (uint16_t*)(base + L.tc_w1h), n1);
     f32_to_16_kernel<false><<<blocks(n2), 256, 0, st>>>(p[8], (uint16_t*)(base + L.tc_w2), n2);
-    f32_to_16_kernel<true><<<blocks(n2), 256, 0, st>>>(p[8], (uint16_t*)(base + L.tc_w2h), n2);
-    w3_image_pack_kernel<false><<<blocks(n3), 256, 0, st>>>(p[10], L.A, L.h3, (uint16_t*)(base + L.tc_w3));
-    w3_image_pack_kernel<true><<<blocks(n3), 256, 0, st>>>(p[10], L.A, L.h3, (uint16_t*)(base + L.tc_w3h));
+    if (sampler) {
+        w0_frag_pack_kernel<false><<<blocks(n0), 256, 0, st>>>(p[4], ld0, L.D, L.S, L.A, L.h1, (uint2*)(base + L.tc_w0));
+        w0_frag_pack_kernel<true><<<blocks(n0), 256, 0, st>>>(p[4], ld0, L.D, L.S, L.A, L.h1, (uint2*)(base + L.tc_w0h));
+        f32_to_16_kernel<true><<<blocks(n1), 256, 0, st>>>(p[6], (uint16_t*)(base + L.tc_w1h), n1);
+        f32_to_16_kernel<true><<<blocks(n2), 256, 0, st>>>(p[8], (uint16_t*)(base + L.tc_w2h), n2);
+        w3_image_pack_kernel<false><<<blocks(n3), 256, 0, st>>>(p[10], L.A, L.h3, (uint16_t*)(base + L.tc_w3));
+        w3_image_pack_kernel<true><<<blocks(n3), 256, 0, st>>>(p[10], L.A, L.h3, (uint16_t*)(base + L.tc_w3h));
+    }
     DDP_LAUNCH_CHECK("actor tensor-core pack kernels");
     return DDP_OK;
 }

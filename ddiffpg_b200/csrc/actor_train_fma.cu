@@ -418,7 +418,8 @@ __global__ void sumsq_kernel(const float* __restrict__ g, size_t n, float* __res
 __global__ void clip_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                   float* __restrict__ v, size_t n, const float* __restrict__ sumsq, float decay,
                                   float step_size, float bc2_sqrt, float b1, float b2, float eps, float max_norm,
-                                  float* __restrict__ norm_out) {
+                                  float* __restrict__ norm_out, const float* __restrict__ dev_scalars) {
+    if (dev_scalars) { step_size = dev_scalars[0]; bc2_sqrt = dev_scalars[1]; }     // step count kept on the device
     const float norm = sqrtf(*sumsq);
     const float coef = fminf(max_norm / (norm + 1e-6f), 1.0f);
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -440,8 +441,30 @@ int clip_adamw(float* p, float* g, float* m, float* v, size_t n, int step, float
     sumsq_kernel<<<gb < 592 ? gb : 592, 256, 0, st>>>(g, n, scratch);
     const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
     clip_adamw_kernel<<<gb, 256, 0, st>>>(p, g, m, v, n, scratch, (float)(1.0 - (double)lr * wd), (float)(lr / bc1),
-                                         (float)sqrt(bc2), b1, b2, eps, max_norm, norm_out);
+                                         (float)sqrt(bc2), b1, b2, eps, max_norm, norm_out, nullptr);
     DDP_LAUNCH_CHECK("clip_adamw kernels");
+    return DDP_OK;
+}
+
+// The same step with the step count on the device (incremented by the call), so that the launch sequence carries
+// no per-step host value and can be captured once into a CUDA graph.  scratch: 3 floats.
+__global__ void adam_scalars_kernel(int* __restrict__ step_dev, float lr, float b1, float b2, float* __restrict__ out) {
+    const int step = *step_dev + 1;
+    *step_dev = step;
+    const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+    out[0] = (float)((double)lr / bc1);
+    out[1] = (float)sqrt(bc2);
+}
+
+int clip_adamw_dev(float* p, float* g, float* m, float* v, size_t n, int* step_dev, float lr, float b1, float b2,
+                   float eps, float wd, float max_norm, float* norm_out, float* scratch, cudaStream_t st) {
+    DDP_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(float), st));
+    unsigned gb = (unsigned)((n + 255) / 256);
+    sumsq_kernel<<<gb < 592 ? gb : 592, 256, 0, st>>>(g, n, scratch);
+    adam_scalars_kernel<<<1, 1, 0, st>>>(step_dev, lr, b1, b2, scratch + 1);
+    clip_adamw_kernel<<<gb, 256, 0, st>>>(p, g, m, v, n, scratch, (float)(1.0 - (double)lr * wd), 0.f, 1.f, b1, b2, eps,
+                                         max_norm, norm_out, scratch + 1);
+    DDP_LAUNCH_CHECK("clip_adamw (device step) kernels");
     return DDP_OK;
 }
 

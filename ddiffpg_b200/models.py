@@ -133,7 +133,8 @@ class DiffusionPolicy(nn.Module):
         for c in self._cache.values():
             c.dirty = True
 
-    def _packed(self, precision):
+    def _packed(self, precision, need=3):
+        """Packed weights for ``precision``; ``need`` = 1 sampler, 2 training, 3 both (parts packed lazily)."""
         prec = _lib.PRECISIONS[precision]
         params = self._params()
         dev = params[0].device
@@ -146,14 +147,20 @@ class DiffusionPolicy(nn.Module):
         cache = self._cache.setdefault(precision, _PackCache())
         shape = self._shape()
         if cache.stale(params, (precision, self.diffusion_iter, str(dev))):
+            cache.parts = 0
+        missing = need & ~getattr(cache, "parts", 0)
+        if missing:
             nbytes = lib().ddp_actor_packed_bytes(shape, prec)
             if nbytes == 0:
                 check(-1, "ddp_actor_packed_bytes")
             if cache.buf is None or cache.buf.numel() != nbytes or cache.buf.device != dev:
                 cache.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                missing = need
+                cache.parts = 0
             with torch.cuda.device(dev):
-                check(lib().ddp_actor_pack(shape, ptr_array([p.detach() for p in params]), ptr(cache.buf), prec,
-                                           stream_ptr()), "ddp_actor_pack")
+                check(lib().ddp_actor_pack_parts(shape, ptr_array([p.detach() for p in params]), ptr(cache.buf), prec,
+                                                 missing, stream_ptr()), "ddp_actor_pack_parts")
+            cache.parts = getattr(cache, "parts", 0) | missing
             cache.dirty = False
         return cache.buf, shape, prec
 
@@ -188,7 +195,7 @@ class DiffusionPolicy(nn.Module):
         if state.dim() != 2 or state.shape[1] != self.state_dim + self.num_mode:
             raise ValueError(f"state must be [B, {self.state_dim + self.num_mode}], got {tuple(state.shape)}")
         B, T, A = state.shape[0], self.diffusion_iter, self.action_dim
-        packed, shape, prec = self._packed(precision)
+        packed, shape, prec = self._packed(precision, need=1)
         dev = packed.device
         state = state.to(device=dev, dtype=torch.float32).contiguous()
         if noise is None:
@@ -226,7 +233,7 @@ class DiffusionPolicy(nn.Module):
         Returns ``out_host`` ([B, A] fp32, pinned; valid once the call returns)."""
         precision = precision or self.precision
         B, A, T = state_host.shape[0], self.action_dim, self.diffusion_iter
-        packed, shape, prec = self._packed(precision)
+        packed, shape, prec = self._packed(precision, need=1)
         dev = packed.device
         if out_host is None:
             out_host = torch.empty((B, A), dtype=torch.float32).pin_memory()
@@ -267,7 +274,7 @@ class DiffusionPolicy(nn.Module):
         return out_host
 
     def _loss_and_grads(self, state, action, noise, timesteps, inv_count=None, precision=None):
-        packed, shape, prec = self._packed(precision or self.train_precision)
+        packed, shape, prec = self._packed(precision or self.train_precision, need=2)
         dev = packed.device
         B = action.shape[0]
         state = state.detach().to(device=dev, dtype=torch.float32).contiguous()

@@ -63,6 +63,12 @@ const char* ddp_last_error(void);
 size_t ddp_actor_packed_bytes(const ddp_actor_shape* shape, int precision);
 int ddp_actor_pack(const ddp_actor_shape* shape, const float* const params[12], void* packed,
                    int precision, void* stream);
+/* The same, restricted to what one consumer reads (a training loop re-packs after every optimizer step and never
+ * samples in between): parts = DDP_PACK_SAMPLE (ddp_actor_sample*), DDP_PACK_TRAIN (ddp_actor_loss_fwd_bwd) or both.
+ * A buffer packed for a precision serves calls of that precision only. */
+enum ddp_pack_parts { DDP_PACK_SAMPLE = 1, DDP_PACK_TRAIN = 2 };
+int ddp_actor_pack_parts(const ddp_actor_shape* shape, const float* const params[12], void* packed,
+                         int precision, int parts, void* stream);
 
 /* Replaces DiffusionPolicy.forward / get_actions(sample=True, add_noise=False)
  * (ddiffpg/models/diffusion_mlp.py:184-185,219-251): the whole T-step reverse chain in one launch.
@@ -106,6 +112,13 @@ int ddp_clip_adamw_step(float* params_flat, float* grads_flat, float* exp_avg, f
                         size_t n, int step, float lr, float beta1, float beta2, float eps,
                         float weight_decay, float max_norm, float* norm_out, float* scratch,
                         void* stream);
+
+/* The same step with the 1-based step count kept in DEVICE memory: *step_counter is incremented by the call and the
+ * bias corrections are derived from it on the device, so the launch sequence carries no per-step host value and
+ * a whole training step can be captured once into a CUDA graph.  scratch: 3 floats. */
+int ddp_clip_adamw_step_dev(float* params_flat, float* grads_flat, float* exp_avg, float* exp_avg_sq, size_t n,
+                            int* step_counter, float lr, float beta1, float beta2, float eps, float weight_decay,
+                            float max_norm, float* norm_out, float* scratch, void* stream);
 
 /* ----------------------------------------------------------------------------------------------
  * Critics.  params[16*n_modes]: per mode the tensors of DistributionalDoubleQ.state_dict()

@@ -556,3 +556,29 @@ def test_replay_gather_large_roundtrip():
     assert torch.equal(o["target"], new) and torch.equal(gids, grp) and seg_off[-1] == n
     assert torch.equal(o["obs"], buf.buf_obs[perm]) and torch.equal(o["done"], buf.buf_done[perm].float())
     assert torch.equal(o["reward"], buf.buf_reward[perm]) and torch.equal(o["next_obs"], buf.buf_next_obs[perm])
+
+
+def test_fused_trainer_graph_replay_matches_eager():
+    """The CUDA-graph form of the training step (captured on the second call, replayed afterwards) walks the same
+    trajectory as the eager launch sequence and as the oracle's AdamW steps, with fresh inputs every step."""
+    from ddiffpg_b200 import FusedActorTrainer
+    T, B = 5, 96
+    p = port.init_actor_params(47)
+    gen = torch.Generator().manual_seed(9)
+    batches = [(torch.randn(B, 34, generator=gen), torch.rand(B, 8, generator=gen) * 2 - 1,
+                torch.randn(B, 8, generator=gen), torch.randint(0, T, (B,), generator=gen)) for _ in range(5)]
+    pol_g, pol_e = make_policy(p, T), make_policy(p, T)
+    tr_g, tr_e = FusedActorTrainer(pol_g, graph=True), FusedActorTrainer(pol_e)
+    st, cur = None, p
+    for s, a, n, t in batches:
+        lg, ng = tr_g.step(_dev(s), _dev(a), noise=_dev(n), timesteps=_dev(t))
+        le, ne = tr_e.step(_dev(s), _dev(a), noise=_dev(n), timesteps=_dev(t))
+        l_ref, n_ref, cur, st = port.adamw_train_step(cur, s, a, n, t, T, opt_state=st)
+        assert abs(lg.item() - le.item()) <= 1e-6 * max(1.0, abs(le.item()))
+        assert abs(ng.item() - ne.item()) <= 1e-5 * ne.item()
+        assert abs(lg.item() - l_ref.item()) < 1e-5 * max(1, l_ref.item()) and abs(ng.item() / n_ref.item() - 1) < 1e-4
+    assert tr_g.step_count == 5 and int(tr_g._step_dev.item()) == 5
+    _assert_params_after_adam(pol_g, cur, steps=5, lr=3e-4)
+    # the sampler sees the weights the replayed graph wrote
+    s6, n6 = torch.randn(7, 34, generator=gen), torch.randn(T, 7, 8, generator=gen)
+    assert_close(pol_g.get_actions(_dev(s6), noise=_dev(n6)), pol_e.get_actions(_dev(s6), noise=_dev(n6)), 1e-4, 1e-4, "post-train")
