@@ -338,10 +338,14 @@ int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, co
     const bool chain = use_chain(L);
     float neg_inv[kMaxModes];
     for (int m = 0; m < L.n_modes; ++m) neg_inv[m] = -seg.inv_cnt[m];
-    // DDP_Q_FUSED_ADAM=1: all iterations in ONE cooperative launch (grid barrier on the clip norm, Adam applied by the
-    // CTA that owns the rows).  Measured equal to one launch per iteration + the Adam kernel (4.41 vs 4.33 ms: the
-    // stream already hides the launches, a pass is 344 k cycles of tile work either way), so it stays opt-in.
-    const bool fused = getenv("DDP_Q_FUSED_ADAM") && atoi(getenv("DDP_Q_FUSED_ADAM")) != 0;
+    // All iterations in ONE cooperative launch (grid barrier on the clip norm, Adam applied by the CTA that owns the
+    // rows): 8 % faster while the batch is at most ~half a wave of tiles (1.12 vs 1.22 ms at 256..4096 states: the
+    // per-tile latency chain dominates and the launches in between are exposed), equal or slower beyond (4.41 vs
+    // 4.33 ms at 65 536: the stream hides the launches).  DDP_Q_FUSED_ADAM=0/1 forces either form.
+    long tiles = 0;
+    for (int m = 0; m < L.n_modes; ++m) tiles += (seg_off[m + 1] - seg_off[m] + 127) / 128;
+    const char* fe = getenv("DDP_Q_FUSED_ADAM");
+    const bool fused = fe ? atoi(fe) != 0 : tiles <= 64;
     if (chain && fused && iters >= 1 && iters <= 32) {
         QChainAscent asc{iters, action, w.m1, w.m2, gnorm_out, w.grid_bar, lr, b1, b2, eps, max_norm, lim};
         int rc = q_chain_pass(L, packed, seg_off, neg_inv, w.xin, w.g, w.gsq, nullptr, nullptr, nullptr, B,
