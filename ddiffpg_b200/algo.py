@@ -297,21 +297,23 @@ class HotPathMixin:
     kernels while keeping the reference's signatures; reads the same cfg keys
     (cfg.diffusion.action_lr / update_times, cfg.algo.max_grad_norm)."""
 
-    def get_actions(self, obs, sample=True):
+    # ``noise`` / ``expl_noise`` (keyword-only, not in the reference) inject the Gaussian draws for reproducible runs
+    def get_actions(self, obs, sample=True, *, noise=None, expl_noise=None):
         if self.cfg.algo.obs_norm:
             obs = self.obs_rms.normalize(obs)
         n = self.cfg.algo.noise
         return get_actions(self.actor, obs, sample=sample, noise_type=n.type, std_min=n.get("std_min", 0.0),
-                           std_max=n.get("std_max", 0.0), std=self.get_noise_std() if n.type == "fixed" else None)
+                           std_max=n.get("std_max", 0.0), std=self.get_noise_std() if n.type == "fixed" else None,
+                           noise=noise, expl_noise=expl_noise)
 
-    def get_tgt_policy_actions(self, obs, sample=True):
+    def get_tgt_policy_actions(self, obs, sample=True, *, noise=None, expl_noise=None):
         n = self.cfg.algo.noise
         return get_tgt_policy_actions(self.actor_target, obs, sample=sample, tgt_pol_std=n.tgt_pol_std,
-                                      tgt_pol_noise_bound=n.tgt_pol_noise_bound)
+                                      tgt_pol_noise_bound=n.tgt_pol_noise_bound, noise=noise, expl_noise=expl_noise)
 
     def update_critic(self, critic, critic_target, critic_optimizer, obs, action, reward, next_obs,
-                      embedded_next_obs, done):
-        next_actions = self.get_tgt_policy_actions(embedded_next_obs)
+                      embedded_next_obs, done, *, noise=None, expl_noise=None):
+        next_actions = self.get_tgt_policy_actions(embedded_next_obs, noise=noise, expl_noise=expl_noise)
         return update_critic(critic, critic_target, critic_optimizer, obs, action, reward, next_obs, next_actions,
                              done, gamma_n=self.cfg.algo.gamma ** self.cfg.algo.nstep,
                              max_grad_norm=self.cfg.algo.max_grad_norm)

@@ -582,3 +582,65 @@ def test_fused_trainer_graph_replay_matches_eager():
     # the sampler sees the weights the replayed graph wrote
     s6, n6 = torch.randn(7, 34, generator=gen), torch.randn(T, 7, 8, generator=gen)
     assert_close(pol_g.get_actions(_dev(s6), noise=_dev(n6)), pol_e.get_actions(_dev(s6), noise=_dev(n6)), 1e-4, 1e-4, "post-train")
+
+
+# ------------------------------------------------------------------------------------------ agent-level mixin
+class _Cfg(dict):
+    """Attribute + .get access, like the reference's OmegaConf nodes."""
+    __getattr__ = dict.__getitem__
+
+
+def _agent(actor, actor_target, lr=3e-4):
+    from ddiffpg_b200 import HotPathMixin
+    cfg = _Cfg(algo=_Cfg(obs_norm=False, gamma=0.99, nstep=3, max_grad_norm=1.0, num_atoms=51,
+                         noise=_Cfg(type="mixed", std_min=0.05, std_max=0.6, tgt_pol_std=0.8, tgt_pol_noise_bound=0.2)),
+               diffusion=_Cfg(action_lr=0.03, update_times=20))
+
+    class Agent(HotPathMixin):
+        pass
+    a = Agent()
+    a.cfg, a.actor, a.actor_target = cfg, actor, actor_target
+    a.actor_optimizer = torch.optim.AdamW(actor.parameters(), lr)
+    return a
+
+
+def test_hot_path_mixin_reads_the_reference_cfg_and_matches_the_oracle():
+    """One inner iteration of AgentDDiffPG.update_net (ddiffpg.py:231-281) through the mixin's methods, every
+    random draw injected: exploration actions, critic update (target-policy actions -> projection -> BCE -> AdamW),
+    action ascent and actor update, each against the oracle's composition of the same reference steps."""
+    T, B = 5, 160
+    gen = torch.Generator().manual_seed(101)
+    pa, pc, pt = port.init_actor_params(60), port.init_critic_params(61, scale=1.2), port.init_critic_params(62, scale=1.2)
+    agent = _agent(make_policy(pa, T), make_policy(pa, T))
+    critic, critic_t = make_critic(pc), make_critic(pt)
+    copt = torch.optim.AdamW(critic.parameters(), 5e-4)
+    obs, nobs = torch.randn(B, 29, generator=gen), torch.randn(B, 29, generator=gen)
+    emb = torch.randn(5, generator=gen)
+    state, nstate = torch.cat([obs, emb.expand(B, 5)], 1), torch.cat([nobs, emb.expand(B, 5)], 1)
+    act = torch.rand(B, 8, generator=gen) * 2 - 1
+    reward, done = torch.rand(B, 1, generator=gen), (torch.rand(B, 1, generator=gen) < 0.2).float()
+    noise, z = torch.randn(T, B, 8, generator=gen), torch.randn(B, 8, generator=gen)
+    # exploration actions: sampler + add_mixed_normal_noise(std_min, std_max) from the cfg
+    a_expl = agent.get_actions(_dev(state), noise=_dev(noise), expl_noise=_dev(z))
+    assert_close(a_expl, port.add_noise_to_actions(port.actor_sample(pa, state, noise, T), z, 0.05, 0.6), 1e-4, 3e-5, "get_actions")
+    # critic update with gamma ** nstep and the target-policy smoothing of the cfg
+    _, c_loss, c_norm = agent.update_critic(critic, critic_t, copt, _dev(obs), _dev(act), _dev(reward), _dev(nobs),
+                                            _dev(nstate), _dev(done), noise=_dev(noise), expl_noise=_dev(z))
+    nact = port.add_noise_to_actions(port.actor_sample(pa, nstate, noise, T), z, 0.8, 0.8, noise_bounds=(-0.2, 0.2))
+    tq = port.critic_target_dist(pt, nobs, nact, reward, done, 0.99 ** 3).clamp_max(1.0)
+    l_ref, g_ref = port.critic_loss_and_grads(pc, tq, obs, act)
+    n_ref = torch.sqrt(sum((g ** 2).sum() for g in g_ref.values())).item()
+    assert abs(c_loss - l_ref.item()) <= 2e-5 * max(1.0, l_ref.item()) and abs(c_norm - n_ref) <= 2e-4 * n_ref
+    # action ascent on the updated critic (action_lr / update_times / max_grad_norm from the cfg), then the actor step
+    pc_new = {k: v.detach().cpu() for k, v in critic.state_dict().items()}
+    work = _dev(act).clone()
+    mean_abs, new_action = agent.update_target_action(_dev(obs), work, critic)
+    m_ref, a_ref, _, gaps = port.q_action_ascent(pc_new, obs, act.clone(), iters=20, return_trace=True)
+    assert_ascent_close(new_action, a_ref, gaps, 20, 0.03, "update_target_action")
+    assert abs(mean_abs - m_ref) <= 1e-4 and new_action.data_ptr() != work.data_ptr()
+    assert all(p.requires_grad for p in critic.parameters())
+    ts, n2 = torch.randint(0, T, (B,), generator=gen), torch.randn(B, 8, generator=gen)
+    loss = agent.actor.get_loss(_dev(state), new_action, noise=_dev(n2), timesteps=_dev(ts))
+    gnorm = agent.optimizer_update(agent.actor_optimizer, loss)
+    l2, _, _, _ = port.adamw_train_step(pa, state, new_action.cpu(), n2, ts, T)
+    assert abs(loss.item() - l2.item()) <= 1e-5 * max(1.0, l2.item()) and gnorm.item() > 0
