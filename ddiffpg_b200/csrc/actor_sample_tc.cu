@@ -8,7 +8,10 @@
 //
 // Per CTA (one per SM, persistent over 128-row tiles), per denoising step:
 //   layer 0 (K = [x|state] = 42 -> 48): warp-level mma.sync in the 8 epilogue warps, register
-//            accumulators; + time table, Mish, bf16 -> 64-column A chunks in SWIZZLE_128B shared memory
+//            accumulators; + time table, Mish, bf16 -> 64-column A chunks in SWIZZLE_128B shared memory.
+//            Only x_t changes between the steps of a tile: the contribution of state[8:] (k16 steps 1 and 2)
+//            is computed once per tile, parked as fp16 in an L2-resident scratch in the owning lane's fragment
+//            order, and each step adds one k16 step ([x_t | state[0:8]]) on top of it
 //   layer 1 (K = h1): tcgen05.mma, A = those chunks as they appear (K-outer), B = W1 tiles streamed by
 //            TMA from L2 through a 4-stage ring, D = the full [128 x h2] fp32 accumulator in TMEM
 //   layer 2 (K = h2): A = Mish(acc1) chunks drained from TMEM by the epilogue warps, D = [128 x h3]
@@ -60,6 +63,7 @@ struct TcArgs {
     const float *tb0, *b1, *b2, *b3, *cst;
     const float *state, *noise;
     float* out;
+    uint4* pscr;               // per-CTA scratch of the state partial sums: [h1/64][8 warps][4][32 lanes] x 16 B
     long B;
     int S, A, T, h1, h2, h3;
     int nparts1, part1;        // layer-1 output split into nparts1 parts of part1 (<= 256) columns
@@ -113,15 +117,14 @@ struct EpiCtx {
 
 // [x (8) | state (S) | 0 ...] of the owned row into the layer-0 input tile, in the operand format F16/bf16
 template <bool F16>
-__device__ __forceinline__ void write_in0_row(const TcArgs& a, const EpiCtx& e, bool with_state) {
+__device__ __forceinline__ void write_in0_row(const TcArgs& a, const EpiCtx& e, int nstate) {
     uint16_t* rp = reinterpret_cast<uint16_t*>(e.smem + SM::in0) + e.my_row * kIn0Stride;
     uint4 xv;
     xv.x = pack2<F16>(e.xr[0], e.xr[1]); xv.y = pack2<F16>(e.xr[2], e.xr[3]);
     xv.z = pack2<F16>(e.xr[4], e.xr[5]); xv.w = pack2<F16>(e.xr[6], e.xr[7]);
     *reinterpret_cast<uint4*>(rp) = xv;
-    if (with_state)
-        for (int i = 0; i < kK0 - 8; ++i)
-            rp[8 + i] = cvt16<F16>((e.valid && i < a.S) ? a.state[e.row * a.S + i] : 0.f);
+    for (int i = 0; i < nstate; ++i)
+        rp[8 + i] = cvt16<F16>((e.valid && i < a.S) ? a.state[e.row * a.S + i] : 0.f);
 }
 
 // 16 accumulator columns (already in registers) of this thread's row -> +bias, Mish, 16-bit -> two
@@ -205,6 +208,58 @@ __device__ __forceinline__ void drain_acc(EpiCtx& e, int nchunks, const float* b
     }
 }
 
+// Scratch slot of this lane for chunk c: 4 x 16 B, [c][warp][j][lane] so that every access is one coalesced 512 B row
+__device__ __forceinline__ uint4* pscr_slot(const TcArgs& a, const EpiCtx& e, int c) {
+    return a.pscr + ((size_t)blockIdx.x * e.NC1 + c) * (kEpiWarps * 4 * 32) + (e.q + 4 * e.ch) * (4 * 32) + e.lane;
+}
+
+// Tile prologue: P = W0[:, state[8:]] . state[8:] for the 32 rows x kColsPerWarp features this warp owns in every
+// chunk (k16 steps 1 and 2 of the layer-0 contraction; operands in the first step's format), kept as fp16 in the
+// lane's own fragment order.  Written and read back by the same thread: no synchronisation is involved.
+static_assert(kEpiWarps == 8 && kNT == 4, "the state-partial fragment order is laid out for 8 warps x 32 columns");
+template <bool F16>
+__device__ __forceinline__ void state_partial(const TcArgs& a, const EpiCtx& e) {
+    const uint32_t in0_lane = smem_u32(e.smem + SM::in0) +
+        (uint32_t)(((e.q * 32 + (e.lane & 7) + ((e.lane >> 3) & 1) * 8) * kIn0Stride + (e.lane >> 4) * 8) * 2);
+    const uint2* wf = F16 ? a.w0frag_h : a.w0frag;
+    uint32_t af[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+            ldmatrix_x4(af[mt][ks], in0_lane + (uint32_t)((mt * 16 * kIn0Stride + (ks + 1) * 16) * 2));
+    uint2 bfr[kNT][2], nxt[kNT][2];
+    auto load_b = [&](int c, uint2 (&f)[kNT][2]) {
+        const uint2* bf = wf + ((size_t)(c * 8 + e.ch * kNT) * 3) * 32 + e.lane;
+#pragma unroll
+        for (int nt = 0; nt < kNT; ++nt)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) f[nt][ks] = __ldg(bf + (nt * 3 + ks + 1) * 32);
+    };
+    load_b(0, bfr);
+#pragma unroll 2
+    for (int c = 0; c < e.NC1; ++c) {
+        load_b(min(c + 1, e.NC1 - 1), nxt);       // next chunk's fragments in flight during this chunk's HMMAs
+        uint4* dst = pscr_slot(a, e, c);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            uint32_t h[kNT][2];
+#pragma unroll
+            for (int nt = 0; nt < kNT; ++nt) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) mma_m16n8k16<F16>(acc, af[mt][ks], bfr[nt][ks].x, bfr[nt][ks].y);
+                h[nt][0] = pack_f16x2(acc[0], acc[1]);
+                h[nt][1] = pack_f16x2(acc[2], acc[3]);
+            }
+            __stcg(dst + (mt * 2 + 0) * 32, make_uint4(h[0][0], h[0][1], h[1][0], h[1][1]));
+            __stcg(dst + (mt * 2 + 1) * 32, make_uint4(h[2][0], h[2][1], h[3][0], h[3][1]));
+        }
+#pragma unroll
+        for (int nt = 0; nt < kNT; ++nt) { bfr[nt][0] = nxt[nt][0]; bfr[nt][1] = nxt[nt][1]; }
+    }
+}
+
 // One denoising step of the epilogue warps (operand format of THIS step = F16 ? fp16 : bf16).
 template <bool F16>
 __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
@@ -212,30 +267,33 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
     const bool prof = a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long tk0 = prof ? clock64() : 0, tk1;
 #define DDP_TICK(slot) do { if (prof) { tk1 = clock64(); a.dbg[slot] += tk1 - tk0; tk0 = tk1; } } while (0)
-    // layer-0 A fragments are re-read from the input tile with ldmatrix for every chunk (6 per chunk) instead
-    // of living in 24 registers for the whole step
+    // ---- layer 0: one 64-feature chunk at a time, straight into the A ring.  accumulator = state partial of the
+    // tile (scratch, fp16) + time-table row + one k16 step over [x_t | state[0:8]]
     const uint32_t in0_lane = smem_u32(e.smem + SM::in0) +
         (uint32_t)(((e.q * 32 + (e.lane & 7) + ((e.lane >> 3) & 1) * 8) * kIn0Stride + (e.lane >> 4) * 8) * 2);
-
-    // ---- layer 0: one 64-feature chunk at a time, straight into the A ring
+    uint32_t afx[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) ldmatrix_x4(afx[mt], in0_lane + (uint32_t)((mt * 16 * kIn0Stride) * 2));
     const float* tb = a.tb0 + (size_t)t * a.h1;
     const uint2* wf = F16 ? a.w0frag_h : a.w0frag;
-    uint2 bfr[kNT][3];
+    uint2 bfr[kNT];
     float2 bias[kNT];
+    uint4 pp[4];
     // packed fragment order: [chunk][32-feature half][n8 tile 0..3][k16 step][lane]; this warp's first
     // feature inside the chunk is ch * kColsPerWarp
-    auto load_frags = [&](int c, uint2 (&f)[kNT][3], float2 (&b)[kNT]) {
+    auto load_frags = [&](int c) {
         const int n8 = e.ch * kNT;                              // first n8 tile (0..7) of this warp in the chunk
         const uint2* bf = wf + ((size_t)(c * 8 + n8) * 3) * 32 + e.lane;
 #pragma unroll
-        for (int nt = 0; nt < kNT; ++nt)
-#pragma unroll
-            for (int ks = 0; ks < 3; ++ks) f[nt][ks] = __ldg(bf + (nt * 3 + ks) * 32);
+        for (int nt = 0; nt < kNT; ++nt) bfr[nt] = __ldg(bf + (nt * 3) * 32);
 #pragma unroll
         for (int nt = 0; nt < kNT; ++nt)
-            b[nt] = __ldg(reinterpret_cast<const float2*>(tb + c * 64 + e.ch * kColsPerWarp + nt * 8 + 2 * e.t4));
+            bias[nt] = __ldg(reinterpret_cast<const float2*>(tb + c * 64 + e.ch * kColsPerWarp + nt * 8 + 2 * e.t4));
+        const uint4* ps = pscr_slot(a, e, c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pp[j] = __ldcg(ps + j * 32);
     };
-    load_frags(0, bfr, bias);
+    load_frags(0);
     int pending0 = -1;
     for (int c = 0; c < e.NC1; ++c) {
         float acc[2][kNT][4];
@@ -243,24 +301,23 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
         for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
             for (int nt = 0; nt < kNT; ++nt) {
-                acc[mt][nt][0] = bias[nt].x; acc[mt][nt][1] = bias[nt].y;
-                acc[mt][nt][2] = bias[nt].x; acc[mt][nt][3] = bias[nt].y;
+                const uint4 pv = pp[mt * 2 + (nt >> 1)];
+                const uint32_t h0 = (nt & 1) ? pv.z : pv.x, h1 = (nt & 1) ? pv.w : pv.y;
+                const float2 p01 = __half22float2(*reinterpret_cast<const __half2*>(&h0));
+                const float2 p23 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+                acc[mt][nt][0] = p01.x + bias[nt].x; acc[mt][nt][1] = p01.y + bias[nt].y;
+                acc[mt][nt][2] = p23.x + bias[nt].x; acc[mt][nt][3] = p23.y + bias[nt].y;
             }
-#pragma unroll
-            for (int ks = 0; ks < 3; ++ks) {
-                uint32_t af[4];
-                ldmatrix_x4(af, in0_lane + (uint32_t)((mt * 16 * kIn0Stride + ks * 16) * 2));
 #pragma unroll
 #ifndef DDP_EXP_NO_HMMA
-                for (int nt = 0; nt < kNT; ++nt) mma_m16n8k16<F16>(acc[mt][nt], af, bfr[nt][ks].x, bfr[nt][ks].y);
+            for (int nt = 0; nt < kNT; ++nt) mma_m16n8k16<F16>(acc[mt][nt], afx[mt], bfr[nt].x, bfr[nt].y);
 #else
-                for (int nt = 0; nt < kNT; ++nt) { acc[mt][nt][0] += __uint_as_float(af[0] ^ bfr[nt][ks].x) * 1e-30f; acc[mt][nt][3] += __uint_as_float(af[3] ^ bfr[nt][ks].y) * 1e-30f; }
+            for (int nt = 0; nt < kNT; ++nt) { acc[mt][nt][0] += __uint_as_float(afx[mt][0] ^ bfr[nt].x) * 1e-30f; acc[mt][nt][3] += __uint_as_float(afx[mt][3] ^ bfr[nt].y) * 1e-30f; }
 #endif
-            }
         }
         // the fragment registers are dead after the HMMAs: refill them for the next chunk now, so the
         // loads are in flight during the Mish / store phase
-        if (c + 1 < e.NC1) load_frags(c + 1, bfr, bias);
+        if (c + 1 < e.NC1) load_frags(c + 1);
         mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
         uint8_t* slot = e.smem + SM::aring + e.as.idx * kChunkBytes;
 #pragma unroll
@@ -335,7 +392,7 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
         }
         if (t > 0) {
             // the next step runs in bf16; after an fp16 step the state columns are re-written as bf16 too
-            write_in0_row<false>(a, e, F16);
+            write_in0_row<false>(a, e, F16 ? 8 : 0);
         } else if (e.valid) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -497,9 +554,10 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
             if (e.ch == 0) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) e.xr[i] = (e.valid && i < a.A) ? a.noise[e.row * a.A + i] : 0.f;
-                if (a.first_f16) write_in0_row<true>(a, e, true); else write_in0_row<false>(a, e, true);
+                if (a.first_f16) write_in0_row<true>(a, e, kK0 - 8); else write_in0_row<false>(a, e, kK0 - 8);
             }
             epi_bar_sync();
+            if (a.first_f16) state_partial<true>(a, e); else state_partial<false>(a, e);
             for (int j = 0; j < a.T; ++j) {
                 if (a.first_f16 && j == 0) epi_step<true>(a, e, j); else epi_step<false>(a, e, j);
             }
@@ -594,11 +652,26 @@ int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, 
     return DDP_OK;
 }
 
-size_t actor_sample_tc_workspace(const ActorLayout&, long) { return 0; }
+static int tc_sm_count() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return 0;
+    return sms;
+}
+
+// state partial sums: one [h1/64][8 warps][4][32 lanes] x 16 B block per resident CTA (256 KB at h1 = 1024)
+size_t actor_sample_tc_workspace(const ActorLayout& L, long B) {
+    const long tiles = (B + kRows - 1) / kRows;
+    const long sms = tc_sm_count();
+    const long ctas = tiles < sms ? tiles : sms;
+    return (size_t)ctas * (L.h1 / 64) * kEpiWarps * 4 * 32 * sizeof(uint4);
+}
 
 int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state, const float* noise, float* out,
-                    long B, const ExplNoise& expl, void*, size_t, cudaStream_t st) {
+                    long B, const ExplNoise& expl, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (!tc_shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 actor path does not support this shape");
+    if (!ws || ((uintptr_t)ws & 15) || ws_bytes < actor_sample_tc_workspace(L, B))
+        DDP_FAIL(DDP_ERR_ARG, "ddp_actor_sample (DDP_BF16): workspace missing, misaligned or smaller than ddp_actor_sample_workspace_bytes");
     const uint8_t* base = (const uint8_t*)packed;
     const float* pk = (const float*)packed;
     TcArgs a;
@@ -613,6 +686,7 @@ int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state
     a.first_f16 = pure_bf16 ? 0 : 1;
     a.tb0 = pk + L.tb0; a.b1 = pk + L.b1; a.b2 = pk + L.b2; a.b3 = pk + L.b3; a.cst = pk + L.cst;
     a.state = state; a.noise = noise; a.out = out; a.B = B;
+    a.pscr = (uint4*)ws;
     a.S = L.S; a.A = L.A; a.T = L.T; a.h1 = L.h1; a.h2 = L.h2; a.h3 = L.h3;
     a.nparts1 = L.h2 > 256 ? L.h2 / 256 : 1;
     a.part1 = L.h2 / a.nparts1;
@@ -625,9 +699,8 @@ int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state
         make_tmap_bf16_sw128(&m1h, base + L.tc_w1h, L.h2, L.h1, a.part1, true) != 0 ||
         make_tmap_bf16_sw128(&m2h, base + L.tc_w2h, L.h3, L.h2, L.h3, true) != 0)
         DDP_FAIL(DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the actor weight tiles");
-    int dev = 0, sms = 0;
-    DDP_CUDA_CHECK(cudaGetDevice(&dev));
-    DDP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = tc_sm_count();
+    if (sms <= 0) DDP_FAIL(DDP_ERR_CUDA, "cannot query the SM count");
     const size_t smem = SM::total + 1024;         // slack for the 1024-byte alignment of the base
     DDP_CUDA_CHECK(cudaFuncSetAttribute(actor_sample_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;

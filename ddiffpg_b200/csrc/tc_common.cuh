@@ -178,14 +178,14 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t smem_addr
 
 // legacy warp-level tensor-core MMA for the K=48 first layer (register accumulators, no TMEM needed)
 __device__ __forceinline__ void mma_m16n8k16_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 __device__ __forceinline__ void mma_m16n8k16_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -225,20 +225,24 @@ __device__ __forceinline__ void ex2_pair_f16(float t0, float t1, float& e0, floa
 #ifndef DDP_MISH_RCPG
 #define DDP_MISH_RCPG 2
 #endif
+// Instruction count per element (RCPG = 2): FFMA, FMNMX, EX2, FADD, FFMA, 1/2 FMUL, 1/2 RCP, FMUL, FFMA.  The exponent is
+// shifted by -1/2 so that v = (e^x + 1)/sqrt(2) and q = -(v^2 + 1/2) = -((e^x+1)^2 + 1)/2 come out of one FADD and one
+// FFMA; then mish(x) = x + x/q needs no separate -2x product.
 template <int N, bool HALF_EX2 = false, int RCPG = DDP_MISH_RCPG>
 __device__ __forceinline__ void mish_fast_n(float (&x)[N]) {
     float s[N];
-    constexpr float kCap = (HALF_EX2 || RCPG > 1) ? 15.87f : 28.853900817779268f;
+    constexpr float kCap = (HALF_EX2 || RCPG > 1) ? 15.37f : 28.353900817779268f;
+    constexpr float kL2e = 1.4426950408889634f, kRh = 0.70710678118654752f;
     if (HALF_EX2) {
 #pragma unroll
         for (int i = 0; i < N; i += 2)
-            ex2_pair_f16(fminf(x[i] * 1.4426950408889634f, kCap), fminf(x[i + 1] * 1.4426950408889634f, kCap), s[i], s[i + 1]);
+            ex2_pair_f16(fminf(fmaf(x[i], kL2e, -0.5f), kCap), fminf(fmaf(x[i + 1], kL2e, -0.5f), kCap), s[i], s[i + 1]);
     } else {
 #pragma unroll
-        for (int i = 0; i < N; ++i) s[i] = ex2_approx(fminf(x[i] * 1.4426950408889634f, kCap));
+        for (int i = 0; i < N; ++i) s[i] = ex2_approx(fminf(fmaf(x[i], kL2e, -0.5f), kCap));
     }
 #pragma unroll
-    for (int i = 0; i < N; ++i) { const float u = s[i] + 1.f; s[i] = fmaf(u, u, 1.f); }
+    for (int i = 0; i < N; ++i) { const float v = s[i] + kRh; s[i] = fmaf(v, -v, -0.5f); }
     if (RCPG == 4) {
 #pragma unroll
         for (int i = 0; i < N; i += 4) {
@@ -260,7 +264,7 @@ __device__ __forceinline__ void mish_fast_n(float (&x)[N]) {
         for (int i = 0; i < N; ++i) s[i] = rcp_approx(s[i]);
     }
 #pragma unroll
-    for (int i = 0; i < N; ++i) x[i] = fmaf(-2.f * x[i], s[i], x[i]);
+    for (int i = 0; i < N; ++i) x[i] = fmaf(x[i], s[i], x[i]);
 }
 
 // ------------------------------------------------------------------------------------ host: tensor maps

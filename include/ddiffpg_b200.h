@@ -73,7 +73,10 @@ int ddp_actor_pack_parts(const ddp_actor_shape* shape, const float* const params
 /* Replaces DiffusionPolicy.forward / get_actions(sample=True, add_noise=False)
  * (ddiffpg/models/diffusion_mlp.py:184-185,219-251): the whole T-step reverse chain in one launch.
  * state [B,S]; noise [T,B,A] with noise[0] = x_T (the draw at :222) and noise[j] = the Gaussian the
- * scheduler adds at t = T-j (j >= 1); action_out [B,A] in [-1,1]. */
+ * scheduler adds at t = T-j (j >= 1); action_out [B,A] in [-1,1].
+ * DDP_BF16 needs a 16-byte aligned device workspace of ddp_actor_sample_workspace_bytes() (per-CTA scratch for the
+ * state part of the first layer, 256 KB per SM at width 1024; queried with the target device current); DDP_FP32
+ * needs none (0 bytes, ws may be NULL). */
 size_t ddp_actor_sample_workspace_bytes(const ddp_actor_shape* shape, long B, int precision);
 int ddp_actor_sample(const ddp_actor_shape* shape, const void* packed, const float* state,
                      const float* noise, float* action_out, long B, int precision,

@@ -224,9 +224,11 @@ def test_q_ascent_bf16_mode_segments():
         _check_ascent(ps[i], obs[sl], work.cpu()[sl], a_ref, _ridge_free(gaps, 3e-2), f"mode {i}")
 
 
-def test_get_actions_host_matches_chunked_device_calls():
-    """Host-resident batches: chunked H2D / sampler / D2H pipeline == per-chunk device calls with the same RNG."""
-    B, T = 1000, 5
+@pytest.mark.parametrize("B", [1000, 30000])
+def test_get_actions_host_matches_chunked_device_calls(B):
+    """Host-resident batches: chunked H2D / sampler / D2H pipeline == per-chunk device calls with the same RNG.
+    Below 8192 rows per range the call does not chunk (B = 1000: one range), B = 30000 runs three ranges."""
+    T = 5
     gen = torch.Generator().manual_seed(21)
     p = port.init_actor_params(86)
     pol = make_policy(p, T, precision="bf16")
@@ -234,12 +236,14 @@ def test_get_actions_host_matches_chunked_device_calls():
     torch.manual_seed(123)
     out_h = pol.get_actions_host(state_h, chunks=3)
     torch.manual_seed(123)
-    rows = ((B + 2) // 3 + 127) // 128 * 128
+    chunks = max(1, min(3, B // 8192))
+    rows = ((B + chunks - 1) // chunks + 127) // 128 * 128
     ref = []
     for lo in range(0, B, rows):
         hi = min(B, lo + rows)
         noise = torch.randn((T, hi - lo, 8), device="cuda")
         ref.append(pol.get_actions(state_h[lo:hi].cuda(), noise=noise).cpu())
+    assert len(ref) == chunks
     assert out_h.is_pinned() and torch.equal(out_h, torch.cat(ref))
     assert pol.get_actions_host(torch.zeros(0, 34).pin_memory()).shape == (0, 8)
 
