@@ -237,6 +237,10 @@ __device__ __forceinline__ void mish_fast_n(float (&x)[N]) {
 #pragma unroll
         for (int i = 0; i < N; i += 2)
             ex2_pair_f16(fminf(fmaf(x[i], kL2e, -0.5f), kCap), fminf(fmaf(x[i + 1], kL2e, -0.5f), kCap), s[i], s[i + 1]);
+    } else if (RCPG == 1) {
+        // no cap needed: e^x = inf -> q = -inf -> 1/q = -0 -> mish = x
+#pragma unroll
+        for (int i = 0; i < N; ++i) s[i] = ex2_approx(fmaf(x[i], kL2e, -0.5f));
     } else {
 #pragma unroll
         for (int i = 0; i < N; ++i) s[i] = ex2_approx(fminf(fmaf(x[i], kL2e, -0.5f), kCap));
