@@ -312,8 +312,17 @@ __global__ void rows_linear_t_kernel(const float* __restrict__ g, int ldg, int N
     const int i = blockIdx.x * 32 + lane, t = blockIdx.y;
     const float* gr = g + (size_t)t * ldg;
     float acc = 0.f;
-    if (i < M)
-        for (int n = warp; n < N; n += 8) acc = fmaf(gr[n], W[(size_t)n * ldw + i], acc);
+    if (i < M) {
+        // eight independent loads in flight per thread: the loop is a latency chain of L2 reads otherwise
+        float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int n = warp;
+        for (; n + 56 < N; n += 64) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a8[u] = fmaf(gr[n + 8 * u], __ldg(W + (size_t)(n + 8 * u) * ldw + i), a8[u]);
+        }
+        for (; n < N; n += 8) a8[0] = fmaf(gr[n], __ldg(W + (size_t)n * ldw + i), a8[0]);
+        acc = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
+    }
     part[warp][lane] = acc;
     __syncthreads();
     if (warp == 0 && i < M) {

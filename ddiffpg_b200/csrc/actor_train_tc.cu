@@ -46,11 +46,18 @@ TrainTcWs carve(const ActorLayout& L, long B, uint8_t* base) {
     return w;
 }
 
+// For T <= 8 the time branch rides on the layer-0 GEMM itself: columns 48+2t / 49+2t of the input row hold the one-hot
+// of the row's timestep and the same columns of the packed W0 hold the [T, h1] time table split into a bf16 "hi" and
+// a bf16 "lo" part (hi + lo reproduces the fp32 entry to 2^-17), so the forward needs no per-row table lookup and the
+// layer-0 weight-gradient GEMM delivers G[t] = sum of dZ0 rows with timestep t in its "hi" columns.
+constexpr int kTCol0 = 48;
+__host__ __device__ inline bool time_cols(int T, int S) { return T <= 8 && S + 8 <= kTCol0; }
+
 // xin[r] = [noisy action (A, padded to 8) | state (S) | 0 ...] (64 columns), onehot[r][t_r] = 1
 __global__ void train_tc_prep_kernel(const float* __restrict__ state, const float* __restrict__ action,
                                      const float* __restrict__ noise, const int64_t* __restrict__ ts,
                                      const float* __restrict__ cst, int S, int A, int T, int Tp, long B,
-                                     bf16* __restrict__ xin, bf16* __restrict__ onehot) {
+                                     bf16* __restrict__ xin, bf16* __restrict__ onehot, int tcols) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long row = idx >> 6;
     const int c = (int)(idx & 63);
@@ -65,9 +72,11 @@ __global__ void train_tc_prep_kernel(const float* __restrict__ state, const floa
         }
     } else if (c - 8 < S) {
         v = state[row * S + c - 8];
+    } else if (tcols && c >= kTCol0) {
+        v = ((c - kTCol0) >> 1) == t ? 1.f : 0.f;         // one-hot of the timestep, twice (hi / lo table columns)
     }
     xin[row * 64 + c] = __float2bfloat16(v);
-    if (c < Tp) onehot[row * Tp + c] = __float2bfloat16(c == t ? 1.f : 0.f);
+    if (!tcols && c < Tp) onehot[row * Tp + c] = __float2bfloat16(c == t ? 1.f : 0.f);
 }
 
 // eps_hat [B][16] fp32 -> loss partial sum (mse_loss, :320) and d loss / d eps_hat as zero-padded bf16 [B][64]
@@ -143,7 +152,7 @@ __global__ void pack_train_tc_kernel(const float* __restrict__ W0, const float* 
                                      const float* __restrict__ W2, const float* __restrict__ W3, int D, int S, int A,
                                      int h1, int h2, int h3, bf16* __restrict__ w0, bf16* __restrict__ w3,
                                      bf16* __restrict__ w3t, bf16* __restrict__ w2t, bf16* __restrict__ w1t,
-                                     int* __restrict__ colmap) {
+                                     int* __restrict__ colmap, const float* __restrict__ tb0, int T, int tcols) {
     const size_t n0 = (size_t)h1 * 64, n3 = (size_t)16 * h3, n3t = (size_t)h3 * 64, n2t = (size_t)h2 * h3,
                  n1t = (size_t)h1 * h2;
     const int ld0 = D + S + A;
@@ -155,6 +164,11 @@ __global__ void pack_train_tc_kernel(const float* __restrict__ W0, const float* 
             float v = 0.f;
             if (k < 8) { if (k < A) v = W0[(size_t)f * ld0 + D + S + k]; }
             else if (k - 8 < S) v = W0[(size_t)f * ld0 + D + k - 8];
+            else if (tcols && k >= kTCol0 && ((k - kTCol0) >> 1) < T) {
+                const float tv = tb0[(size_t)((k - kTCol0) >> 1) * h1 + f];
+                const float hi = __bfloat162float(__float2bfloat16(tv));
+                v = (k & 1) ? tv - hi : hi;
+            }
             w0[j] = __float2bfloat16(v);
             continue;
         }
@@ -168,7 +182,9 @@ __global__ void pack_train_tc_kernel(const float* __restrict__ W0, const float* 
         if (j < n1t) { const int r = (int)(j / h2), c = (int)(j % h2); w1t[j] = __float2bfloat16(W1[(size_t)c * h1 + r]); continue; }
         j -= n1t;
         const int k = (int)j;
-        colmap[k] = k < 8 ? (k < A ? D + S + k : -1) : (k - 8 < S ? D + k - 8 : -1);
+        int cm = k < 8 ? (k < A ? D + S + k : -1) : (k - 8 < S ? D + k - 8 : -1);
+        if (tcols && k >= kTCol0 && !(k & 1) && ((k - kTCol0) >> 1) < T) cm = tcg::kDwCol2 + ((k - kTCol0) >> 1);
+        colmap[k] = cm;
     }
 }
 
@@ -181,7 +197,8 @@ int pack_actor_train_tc(const ActorLayout& L, const float* const p[12], void* pa
     uint8_t* b = (uint8_t*)packed;
     pack_train_tc_kernel<<<592, 256, 0, st>>>(p[4], p[6], p[8], p[10], L.D, L.S, L.A, L.h1, L.h2, L.h3,
                                                (bf16*)(b + L.tr_w0), (bf16*)(b + L.tr_w3), (bf16*)(b + L.tr_w3t),
-                                               (bf16*)(b + L.tr_w2t), (bf16*)(b + L.tr_w1t), (int*)(b + L.tr_colmap));
+                                               (bf16*)(b + L.tr_w2t), (bf16*)(b + L.tr_w1t), (int*)(b + L.tr_colmap),
+                                               (const float*)packed + L.tb0, L.T, time_cols(L.T, L.S) ? 1 : 0);
     DDP_LAUNCH_CHECK("pack_train_tc_kernel");
     return DDP_OK;
 }
@@ -203,7 +220,8 @@ int actor_train_tc(const ActorLayout& L, const void* packed, const float* const 
     DDP_CUDA_CHECK(cudaMemsetAsync(grads, 0, go.off[12] * sizeof(float), st));
     DDP_CUDA_CHECK(cudaMemsetAsync(w.GT, 0, (size_t)L.h1 * Tp * sizeof(float), st));
     const unsigned eb = (unsigned)((B * 64 + 255) / 256);
-    train_tc_prep_kernel<<<eb, 256, 0, st>>>(state, action, noise, t, pk + L.cst, L.S, L.A, L.T, Tp, B, w.xin, w.onehot);
+    const bool tcols = time_cols(L.T, L.S);
+    train_tc_prep_kernel<<<eb, 256, 0, st>>>(state, action, noise, t, pk + L.cst, L.S, L.A, L.T, Tp, B, w.xin, w.onehot, tcols ? 1 : 0);
 
     auto row = [&](const bf16* A, int lda, const bf16* W, int ldw, int N, int K, int epi, const float* bias,
                    const bf16* aux, bf16* out_a, bf16* out_d, float* out_f, int outf_ld, int n_valid) {
@@ -218,7 +236,7 @@ int actor_train_tc(const ActorLayout& L, const void* packed, const float* const 
     // ---- forward
     {
         RowGemm g = row(w.xin, 64, (const bf16*)(pb + L.tr_w0), 64, L.h1, 64, EPI_MISH_FWD, nullptr, nullptr, w.a0, w.d0, nullptr, 0, 0);
-        g.tbl = pk + L.tb0; g.trow = t; g.tbl_ld = L.h1; g.tbl_rows = L.T;      // time table (includes b0), per row
+        if (!tcols) { g.tbl = pk + L.tb0; g.trow = t; g.tbl_ld = L.h1; g.tbl_rows = L.T; }   // time table (includes b0), per row
         if ((rc = launch_row_gemm(g, st)) != DDP_OK) return rc;
     }
     if ((rc = launch_row_gemm(row(w.a0, L.h1, (const bf16*)(pb + L.tc_w1), L.h1, L.h2, L.h1, EPI_MISH_FWD, pk + L.b1, nullptr, w.a1, w.d1, nullptr, 0, 0), st)) != DDP_OK) return rc;
@@ -230,16 +248,19 @@ int actor_train_tc(const ActorLayout& L, const void* packed, const float* const 
     if ((rc = launch_row_gemm(row(w.d2, L.h3, (const bf16*)(pb + L.tr_w2t), L.h3, L.h2, L.h3, EPI_MUL_D, nullptr, w.d1, w.d1, nullptr, nullptr, 0, 0), st)) != DDP_OK) return rc;
     if ((rc = launch_row_gemm(row(w.d1, L.h2, (const bf16*)(pb + L.tr_w1t), L.h2, L.h1, L.h2, EPI_MUL_D, nullptr, w.d0, w.d0, nullptr, nullptr, 0, 0), st)) != DDP_OK) return rc;
     // ---- weight gradients
-    auto dw = [&](const bf16* dz, int ldz, int N, const bf16* X, int ldx, int K, float* C, int ldc, const int* colmap) {
+    auto dw = [&](const bf16* dz, int ldz, int N, const bf16* X, int ldx, int K, float* C, int ldc, const int* colmap,
+                  float* C2 = nullptr, int ldc2 = 0) {
         DwGemm g{};
         g.dZ = dz; g.ldz = ldz; g.N = N; g.X = X; g.ldx = ldx; g.K = K; g.R = B; g.C = C; g.ldc = ldc; g.colmap = colmap;
+        g.C2 = C2; g.ldc2 = ldc2;
         return launch_dw_gemm(g, st);
     };
     if ((rc = dw(w.deps, 64, L.A, w.a2, L.h3, L.h3, grads + go.off[10], L.h3, nullptr)) != DDP_OK) return rc;
     if ((rc = dw(w.d2, L.h3, L.h3, w.a1, L.h2, L.h2, grads + go.off[8], L.h2, nullptr)) != DDP_OK) return rc;
     if ((rc = dw(w.d1, L.h2, L.h2, w.a0, L.h1, L.h1, grads + go.off[6], L.h1, nullptr)) != DDP_OK) return rc;
-    if ((rc = dw(w.d0, L.h1, L.h1, w.xin, 64, 64, grads + go.off[4], ld0, (const int*)(pb + L.tr_colmap))) != DDP_OK) return rc;
-    if ((rc = dw(w.d0, L.h1, L.h1, w.onehot, Tp, L.T, w.GT, Tp, nullptr)) != DDP_OK) return rc;       // G^T[n][t]
+    // G^T[n][t]: from the one-hot columns of xin in the same launch (T <= 8), else from a separate one-hot operand
+    if ((rc = dw(w.d0, L.h1, L.h1, w.xin, 64, 64, grads + go.off[4], ld0, (const int*)(pb + L.tr_colmap), w.GT, Tp)) != DDP_OK) return rc;
+    if (!tcols && (rc = dw(w.d0, L.h1, L.h1, w.onehot, Tp, L.T, w.GT, Tp, nullptr)) != DDP_OK) return rc;
     const unsigned rb = (unsigned)((B + 255) / 256);
     colsum_bf16_kernel<<<rb, 256, 0, st>>>(w.deps, 64, L.A, B, grads + go.off[11]);
     colsum_bf16_kernel<<<rb, 256, 0, st>>>(w.d2, L.h3, L.h3, B, grads + go.off[9]);

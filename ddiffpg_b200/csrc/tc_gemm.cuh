@@ -48,7 +48,9 @@ struct DwGemm {
     long R;
     float* C; int ldc;                        // output rows n, columns colmap[k] (or k)
     const int* colmap;                        // device array [K] (-1 = drop) or NULL
+    float* C2; int ldc2;                      // optional second output: colmap[k] >= kDwCol2 goes to C2[n][colmap[k] - kDwCol2]
 };
+constexpr int kDwCol2 = 1 << 20;
 int launch_dw_gemm(const DwGemm& g, cudaStream_t st);
 
 }  // namespace tcg
