@@ -48,8 +48,6 @@ constexpr int kColsPerWarp = 64 / (kEpiWarps / 4);   // columns of a 64-column c
 constexpr int kNT = kColsPerWarp / 8;        // mma.sync n8 tiles per warp in layer 0
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kEpiThreads + 64;  // + TMA warp + MMA warp
-constexpr int kRegsEpilogue = 224;          // setmaxnreg budgets (per thread) after the role split
-constexpr int kRegsProducer = 64;
 constexpr int kIn0Stride = 56;              // bf16 per row of the layer-0 input tile (112 B: conflict-free)
 constexpr int kK0 = 48;                     // layer-0 contraction: x(8) | state(<=34) | zero pad
 constexpr int kTmemCols = 512;

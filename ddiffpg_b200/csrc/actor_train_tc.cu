@@ -106,39 +106,6 @@ __global__ void train_tc_loss_kernel(const float* __restrict__ eps, const float*
     }
 }
 
-// db[n] += sum_r dZ[r][n]  (bias gradients), bf16 input, fp32 atomics.  A block covers 256 rows; each thread owns
-// 8 consecutive columns (one 16-byte load per row) of one row strip, strips are reduced through shared memory.
-__global__ void colsum_bf16_kernel(const bf16* __restrict__ dz, int ld, int N, long R, float* __restrict__ db) {
-    __shared__ float part[256][9];
-    const int groups = (N + 7) >> 3;                       // 8-column groups
-    const int strips = 256 / groups > 0 ? 256 / groups : 1;  // row strips handled concurrently by the block
-    const int grp = threadIdx.x % groups, strip = threadIdx.x / groups;
-    const long r0 = (long)blockIdx.x * 256, r1 = r0 + 256 < R ? r0 + 256 : R;
-    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (strip < strips && groups <= 256) {
-        for (long r = r0 + strip; r < r1; r += strips) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(dz + r * ld + grp * 8));
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                s[2 * i] += __uint_as_float(w[i] << 16);
-                s[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) part[threadIdx.x][i] = s[i];
-    __syncthreads();
-    if (threadIdx.x < groups) {
-        for (int i = 0; i < 8; ++i) {
-            float t = 0.f;
-            for (int st = 0; st < strips; ++st) t += part[st * groups + threadIdx.x][i];
-            const int c = threadIdx.x * 8 + i;
-            if (c < N && t != 0.f) atomicAdd(db + c, t);
-        }
-    }
-}
-
 __global__ void transpose_small_kernel(const float* __restrict__ src, int rows, int cols, int ld, float* __restrict__ dst) {
     // dst[c][r] = src[r][c]  (src: [rows][ld], dst: [cols][rows])
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -249,22 +216,19 @@ int actor_train_tc(const ActorLayout& L, const void* packed, const float* const 
     if ((rc = launch_row_gemm(row(w.d1, L.h2, (const bf16*)(pb + L.tr_w1t), L.h2, L.h1, L.h2, EPI_MUL_D, nullptr, w.d0, w.d0, nullptr, nullptr, 0, 0), st)) != DDP_OK) return rc;
     // ---- weight gradients
     auto dw = [&](const bf16* dz, int ldz, int N, const bf16* X, int ldx, int K, float* C, int ldc, const int* colmap,
-                  float* C2 = nullptr, int ldc2 = 0) {
+                  float* C2 = nullptr, int ldc2 = 0, float* colsum = nullptr) {
         DwGemm g{};
         g.dZ = dz; g.ldz = ldz; g.N = N; g.X = X; g.ldx = ldx; g.K = K; g.R = B; g.C = C; g.ldc = ldc; g.colmap = colmap;
-        g.C2 = C2; g.ldc2 = ldc2;
+        g.C2 = C2; g.ldc2 = ldc2; g.colsum = colsum;
         return launch_dw_gemm(g, st);
     };
-    if ((rc = dw(w.deps, 64, L.A, w.a2, L.h3, L.h3, grads + go.off[10], L.h3, nullptr)) != DDP_OK) return rc;
-    if ((rc = dw(w.d2, L.h3, L.h3, w.a1, L.h2, L.h2, grads + go.off[8], L.h2, nullptr)) != DDP_OK) return rc;
-    if ((rc = dw(w.d1, L.h2, L.h2, w.a0, L.h1, L.h1, grads + go.off[6], L.h1, nullptr)) != DDP_OK) return rc;
+    // bias gradients (column sums of dZ) come out of the same launches
+    if ((rc = dw(w.deps, 64, L.A, w.a2, L.h3, L.h3, grads + go.off[10], L.h3, nullptr, nullptr, 0, grads + go.off[11])) != DDP_OK) return rc;
+    if ((rc = dw(w.d2, L.h3, L.h3, w.a1, L.h2, L.h2, grads + go.off[8], L.h2, nullptr, nullptr, 0, grads + go.off[9])) != DDP_OK) return rc;
+    if ((rc = dw(w.d1, L.h2, L.h2, w.a0, L.h1, L.h1, grads + go.off[6], L.h1, nullptr, nullptr, 0, grads + go.off[7])) != DDP_OK) return rc;
     // G^T[n][t]: from the one-hot columns of xin in the same launch (T <= 8), else from a separate one-hot operand
     if ((rc = dw(w.d0, L.h1, L.h1, w.xin, 64, 64, grads + go.off[4], ld0, (const int*)(pb + L.tr_colmap), w.GT, Tp)) != DDP_OK) return rc;
     if (!tcols && (rc = dw(w.d0, L.h1, L.h1, w.onehot, Tp, L.T, w.GT, Tp, nullptr)) != DDP_OK) return rc;
-    const unsigned rb = (unsigned)((B + 255) / 256);
-    colsum_bf16_kernel<<<rb, 256, 0, st>>>(w.deps, 64, L.A, B, grads + go.off[11]);
-    colsum_bf16_kernel<<<rb, 256, 0, st>>>(w.d2, L.h3, L.h3, B, grads + go.off[9]);
-    colsum_bf16_kernel<<<rb, 256, 0, st>>>(w.d1, L.h2, L.h2, B, grads + go.off[7]);
     // ---- time branch (fp32, T rows): b0's gradient comes out of it as the column sums of G
     transpose_small_kernel<<<(L.h1 * L.T + 255) / 256, 256, 0, st>>>(w.GT, L.h1, L.T, Tp, w.G);
     time_branch_backward(L, pk, p, w.G, w.dtemb, w.dhmid, grads, st);

@@ -26,7 +26,8 @@ constexpr int kRowEpiWarps = DDP_ROW_EPI_WARPS;    // 8 or 16: warps of a lane q
 constexpr int kThreads = 64 + 32 * kRowEpiWarps;   // warp 0 TMA, warp 1 MMA, then the epilogue warps (row GEMM)
 constexpr int kDwThreads = 192;             // dW GEMM: warps 2-5 epilogue
 constexpr uint32_t kOffBars = kStages * kStageBytes;
-constexpr uint32_t kSmemBytes = kOffBars + 8 * (2 * kStages + 4) + 16 + 1024;
+constexpr uint32_t kOffOnes = kOffBars + 256;                  // dW GEMM: [64 reduction rows][64] bf16 ones (8 KB)
+constexpr uint32_t kSmemBytes = kOffOnes + 8192 + 1024;
 // row GEMM: one stage less, the space is the per-warp staging that turns the row-per-lane epilogue into
 // coalesced global accesses (two [32 rows][128 B] buffers per epilogue warp)
 constexpr int kRowStages = 3;
@@ -345,7 +346,14 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant_
         mbar_init(bar_done, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    // bias gradient: only the CTAs of the first X-column tile carry it
+    const bool do_colsum = g.colsum != nullptr && k0 == 0;
+    if (do_colsum) {
+        uint4* ones = reinterpret_cast<uint4*>(smem + kOffOnes);
+        for (int i = threadIdx.x; i < 8192 / 16; i += kDwThreads) ones[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        fence_proxy_async();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -374,6 +382,7 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant_
         if (lane == 0) {
             // both operands MN-major: bits 15 / 16 of the instruction descriptor
             const uint32_t idesc = make_idesc_16(128, k.BN, false) | (1u << 15) | (1u << 16);
+            const uint32_t idesc1 = make_idesc_16(128, 16, false) | (1u << 15) | (1u << 16);
             int st = 0; uint32_t ph = 0;
             for (int c = 0; c < chunks; ++c) {
                 mbar_wait(bar_full(st), ph);
@@ -383,6 +392,12 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant_
                 for (int q = 0; q < 4; ++q)       // 16 reduction rows per instruction = 2 KB
                     umma_bf16(tmem_base, make_smem_desc_mn_sw128(a0 + q * 2048, 8192),
                               make_smem_desc_mn_sw128(b0 + q * 2048, 8192), idesc, (c | q) != 0);
+                if (do_colsum) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)   // D2[n][0..15] += sum over these 16 rows of dZ[r][n] * 1
+                        umma_bf16(tmem_base + 256, make_smem_desc_mn_sw128(a0 + q * 2048, 8192),
+                                  make_smem_desc_mn_sw128(base + kOffOnes + q * 2048, 8192), idesc1, (c | q) != 0);
+                }
                 umma_commit(bar_empty(st));
                 if (++st == kStages) { st = 0; ph ^= 1; }
             }
@@ -394,6 +409,12 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant_
         mbar_wait(bar_done, 0);
         tc_fence_after();
         const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (do_colsum) {
+            uint32_t v[16];
+            tmem_ld16(tb + 256, v);
+            tmem_ld_wait();
+            if (n < g.N) atomicAdd(g.colsum + n, __uint_as_float(v[0]));
+        }
         for (int p = 0; p < (k.BN >> 4); ++p) {
             uint32_t v[16];
             tmem_ld16(tb + p * 16, v);
@@ -411,7 +432,7 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace

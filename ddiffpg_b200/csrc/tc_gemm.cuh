@@ -49,6 +49,8 @@ struct DwGemm {
     float* C; int ldc;                        // output rows n, columns colmap[k] (or k)
     const int* colmap;                        // device array [K] (-1 = drop) or NULL
     float* C2; int ldc2;                      // optional second output: colmap[k] >= kDwCol2 goes to C2[n][colmap[k] - kDwCol2]
+    float* colsum;                            // optional: colsum[n] += sum_r dZ[r][n] (bias gradient), from one extra
+                                              // N = 16 MMA per reduction step against a shared-memory tile of ones
 };
 constexpr int kDwCol2 = 1 << 20;
 int launch_dw_gemm(const DwGemm& g, cudaStream_t st);
