@@ -79,33 +79,6 @@ __global__ void train_tc_prep_kernel(const float* __restrict__ state, const floa
     if (!tcols && c < Tp) onehot[row * Tp + c] = __float2bfloat16(c == t ? 1.f : 0.f);
 }
 
-// eps_hat [B][16] fp32 -> loss partial sum (mse_loss, :320) and d loss / d eps_hat as zero-padded bf16 [B][64]
-__global__ void train_tc_loss_kernel(const float* __restrict__ eps, const float* __restrict__ noise, int A, long B,
-                                     float inv_count, float* __restrict__ loss_out, bf16* __restrict__ deps) {
-    __shared__ float red[8];
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long row = idx >> 6;
-    const int c = (int)(idx & 63);
-    float sq = 0.f;
-    if (row < B) {
-        float d = 0.f;
-        if (c < A) {
-            const float diff = eps[row * 16 + c] - noise[row * A + c];
-            sq = diff * diff;
-            d = 2.f * diff * inv_count;
-        }
-        deps[row * 64 + c] = __float2bfloat16(d);
-    }
-    sq = warp_sum(sq);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int i = 0; i < 8; ++i) s += red[i];
-        if (s != 0.f) atomicAdd(loss_out, s * inv_count);
-    }
-}
-
 __global__ void transpose_small_kernel(const float* __restrict__ src, int rows, int cols, int ld, float* __restrict__ dst) {
     // dst[c][r] = src[r][c]  (src: [rows][ld], dst: [cols][rows])
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,8 +181,11 @@ int actor_train_tc(const ActorLayout& L, const void* packed, const float* const 
     }
     if ((rc = launch_row_gemm(row(w.a0, L.h1, (const bf16*)(pb + L.tc_w1), L.h1, L.h2, L.h1, EPI_MISH_FWD, pk + L.b1, nullptr, w.a1, w.d1, nullptr, 0, 0), st)) != DDP_OK) return rc;
     if ((rc = launch_row_gemm(row(w.a1, L.h2, (const bf16*)(pb + L.tc_w2), L.h2, L.h3, L.h2, EPI_MISH_FWD, pk + L.b2, nullptr, w.a2, w.d2, nullptr, 0, 0), st)) != DDP_OK) return rc;
-    if ((rc = launch_row_gemm(row(w.a2, L.h3, (const bf16*)(pb + L.tr_w3), L.h3, 16, L.h3, EPI_LINEAR_F32, pk + L.b3, nullptr, nullptr, nullptr, w.eps, 16, L.A), st)) != DDP_OK) return rc;
-    train_tc_loss_kernel<<<eb, 256, 0, st>>>(w.eps, noise, L.A, B, inv_count, loss_out, w.deps);
+    {   // head + mse_loss (:320) + d loss / d eps_hat in the epilogue of the last GEMM
+        RowGemm g = row(w.a2, L.h3, (const bf16*)(pb + L.tr_w3), L.h3, 16, L.h3, EPI_MSE_HEAD, pk + L.b3, nullptr, w.deps, nullptr, nullptr, 0, L.A);
+        g.out_ld = 64; g.target = noise; g.target_ld = L.A; g.scale = inv_count; g.loss = loss_out;
+        if ((rc = launch_row_gemm(g, st)) != DDP_OK) return rc;
+    }
     // ---- backward: dZ chain (dZ_l overwrites the stored derivative d_l in place)
     if ((rc = launch_row_gemm(row(w.deps, 64, (const bf16*)(pb + L.tr_w3t), 64, L.h3, 64, EPI_MUL_D, nullptr, w.d2, w.d2, nullptr, nullptr, 0, 0), st)) != DDP_OK) return rc;
     if ((rc = launch_row_gemm(row(w.d2, L.h3, (const bf16*)(pb + L.tr_w2t), L.h3, L.h2, L.h3, EPI_MUL_D, nullptr, w.d1, w.d1, nullptr, nullptr, 0, 0), st)) != DDP_OK) return rc;

@@ -239,6 +239,27 @@ row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         for (int i = 0; i < 16; ++i)
                             if (c0 + i < g.n_valid) g.out_f[row * g.outf_ld + c0 + i] = z[i];
                     }
+                } else if (g.epi == EPI_MSE_HEAD) {
+                    // one 16-column piece per tile: squared error of the row, its gradient as a zero-padded 64-column
+                    // bf16 row (the A operand of the first backward GEMM), one loss atomic per warp
+                    float sq = 0.f, d[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float e = 0.f;
+                        if (valid && c0 + i < g.n_valid) e = z[i] - __ldg(g.target + row * g.target_ld + c0 + i);
+                        sq = fmaf(e, e, sq);
+                        d[i] = 2.f * g.scale * e;
+                    }
+                    if (valid && c0 == 0) {
+                        uint4* o = reinterpret_cast<uint4*>(g.out_a + row * g.out_ld);
+                        o[0] = make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
+                        o[1] = make_uint4(pack_bf16x2(d[8], d[9]), pack_bf16x2(d[10], d[11]), pack_bf16x2(d[12], d[13]), pack_bf16x2(d[14], d[15]));
+#pragma unroll
+                        for (int i = 2; i < 8; ++i) o[i] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    if (lane == 0 && sq != 0.f) atomicAdd(g.loss, sq * g.scale);
                 } else if (valid && c0 < g.N) {
                     // backward epilogues: the row-per-lane accesses go straight to global memory (staging them was
                     // measured slower: 41 / 72 / 147 us against 35 / 62 / 129 us for the three backward layers)
@@ -483,7 +504,9 @@ int launch_dw_gemm(const DwGemm& g, cudaStream_t st) {
     k.tiles_k = (g.K + k.BN - 1) / k.BN;
     const long tiles = (long)k.tiles_n * k.tiles_k;
     const long chunks = (g.R + 63) / 64;
-    long splits = (2 * 148 + tiles - 1) / tiles;          // about two waves of CTAs
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long splits = 2L * sms / tiles;                       // at most two full waves of CTAs (never a third, partial one)
     if (splits > chunks) splits = chunks;
     if (splits < 1) splits = 1;
     const long cps = (chunks + splits - 1) / splits;

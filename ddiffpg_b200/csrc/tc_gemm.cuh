@@ -17,7 +17,9 @@ enum RowEpi {
     EPI_ELU_FWD = 1,     // out_a = elu(acc + bias)                                                  (bf16)
     EPI_LINEAR_F32 = 2,  // out_f[r][c] = acc + bias, c < n_valid                                    (fp32)
     EPI_MUL_D = 3,       // out_a = acc * aux[r][c]                      (aux = stored mish', bf16)  (bf16)
-    EPI_MUL_ELU_D = 4    // out_a = acc * (aux > 0 ? 1 : aux + 1)        (aux = stored ELU activation) (bf16)
+    EPI_MUL_ELU_D = 4,   // out_a = acc * (aux > 0 ? 1 : aux + 1)        (aux = stored ELU activation) (bf16)
+    EPI_MSE_HEAD = 5     // head of the denoiser: e = acc + bias - target[r][c] (c < n_valid): *loss += scale * sum e^2,
+                         // out_a[r][0..63] = 2 * scale * e, zero padded  (mse_loss forward + d loss / d eps_hat; N = 16)
 };
 
 // Rows are split into `n_groups` contiguous segments; group g uses weight matrix g (and bias block g).
@@ -37,6 +39,7 @@ struct RowGemm {
     const __nv_bfloat16* aux; int aux_ld;
     __nv_bfloat16* out_a; __nv_bfloat16* out_d; int out_ld;
     float* out_f; int outf_ld; int n_valid;
+    const float* target; int target_ld; float scale; float* loss;      // EPI_MSE_HEAD
     RowGroups groups;
 };
 int launch_row_gemm(const RowGemm& g, cudaStream_t st);
