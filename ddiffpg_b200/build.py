@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libddiffpg_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
-SOURCES = ["abi.cu", "actor_pack.cu", "actor_sample_fma.cu", "actor_sample_tc.cu", "actor_train_fma.cu", "actor_train_tc.cu", "q_fma.cu", "q_chain_tc.cu", "q_tc.cu", "replay_gather.cu", "tc_gemm.cu"]
+SOURCES = ["abi.cu", "actor_pack.cu", "actor_sample_fma.cu", "actor_sample_tc.cu", "actor_train_fma.cu", "actor_train_tc.cu", "actor_train_chain_tc.cu", "q_fma.cu", "q_chain_tc.cu", "q_tc.cu", "replay_gather.cu", "tc_gemm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "--expt-extended-lambda", "-Xcompiler", "-fPIC,-ffp-contract=off",
               "-Xptxas", "-v"]

@@ -15,7 +15,7 @@ void set_error(const char* fmt, ...) {
 
 // implemented in the kernel translation units
 int pack_actor_fp32(const ActorLayout& L, const float* const p[12], float* out, bool fma_operands, cudaStream_t st);
-int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, bool sampler, cudaStream_t st);
+int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, bool sampler, bool train, cudaStream_t st);
 int actor_sample_fma(const ActorLayout& L, const float* pk, const float* state, const float* noise, float* out,
                      long B, const ExplNoise& expl, cudaStream_t st);
 int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state, const float* noise, float* out,
@@ -96,7 +96,7 @@ int ddp_actor_pack_parts(const ddp_actor_shape* s, const float* const params[12]
     rc = pack_actor_fp32(L, params, (float*)packed, precision == DDP_FP32, st);
     if (rc != DDP_OK) return rc;
     if (precision == DDP_BF16) {
-        rc = pack_actor_tc(L, params, packed, (parts & DDP_PACK_SAMPLE) != 0, st);
+        rc = pack_actor_tc(L, params, packed, (parts & DDP_PACK_SAMPLE) != 0, (parts & DDP_PACK_TRAIN) != 0, st);
         if (rc != DDP_OK) return rc;
         if (parts & DDP_PACK_TRAIN) return pack_actor_train_tc(L, params, packed, st);
     }

@@ -627,7 +627,7 @@ static bool tc_shape_ok(const ActorLayout& L) {
            (L.h2 <= 256 || L.h2 % 256 == 0);
 }
 
-int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, bool sampler, cudaStream_t st) {
+int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, bool sampler, bool train, cudaStream_t st) {
     if (!tc_shape_ok(L))
         DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 actor path needs A<=8, S<=40, widths multiple of 64 with h2<=512, h3<=256");
     uint8_t* base = (uint8_t*)packed;
@@ -645,6 +645,10 @@ int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, 
         f32_to_16_kernel<true><<<blocks(n2), 256, 0, st>>>(p[8], (uint16_t*)(base + L.tc_w2h), n2);
         w3_image_pack_kernel<false><<<blocks(n3), 256, 0, st>>>(p[10], L.A, L.h3, (uint16_t*)(base + L.tc_w3));
         w3_image_pack_kernel<true><<<blocks(n3), 256, 0, st>>>(p[10], L.A, L.h3, (uint16_t*)(base + L.tc_w3h));
+    } else if (train) {
+        // the fused training forward (csrc/actor_train_chain_tc.cu) shares the sampler's bf16 layer-0 fragments and head image
+        w0_frag_pack_kernel<false><<<blocks(n0), 256, 0, st>>>(p[4], ld0, L.D, L.S, L.A, L.h1, (uint2*)(base + L.tc_w0));
+        w3_image_pack_kernel<false><<<blocks(n3), 256, 0, st>>>(p[10], L.A, L.h3, (uint16_t*)(base + L.tc_w3));
     }
     DDP_LAUNCH_CHECK("actor tensor-core pack kernels");
     return DDP_OK;

@@ -8,6 +8,7 @@
 // uses the packed fp32 [T, h1] table in the forward (added per row in the epilogue of layer 0) and, in the
 // backward, G[t] = sum of dZ0 rows with timestep t obtained as dZ0^T . onehot(t) by the same dW GEMM, followed
 // by the fp32 T-row products shared with the fp32 path.
+#include <stdlib.h>
 #include "actor_layout.cuh"
 #include "tc_gemm.cuh"
 
@@ -15,6 +16,10 @@ namespace ddp {
 
 void time_branch_backward(const ActorLayout& L, const float* pk, const float* const p[12], const float* G,
                           float* dtemb, float* dhmid, float* g, cudaStream_t st);
+bool actor_train_chain_shape_ok(const ActorLayout& L);
+int actor_train_chain_fwd(const ActorLayout& L, const void* packed, const void* xin, const int64_t* t, const float* noise,
+                          float inv_count, float* loss_out, void* a0, void* d0, void* a1, void* d1, void* a2, void* d2,
+                          void* deps, long B, cudaStream_t st);
 
 namespace {
 
@@ -173,18 +178,25 @@ int actor_train_tc(const ActorLayout& L, const void* packed, const float* const 
         return g;
     };
     int rc;
-    // ---- forward
-    {
-        RowGemm g = row(w.xin, 64, (const bf16*)(pb + L.tr_w0), 64, L.h1, 64, EPI_MISH_FWD, nullptr, nullptr, w.a0, w.d0, nullptr, 0, 0);
-        if (!tcols) { g.tbl = pk + L.tb0; g.trow = t; g.tbl_ld = L.h1; g.tbl_rows = L.T; }   // time table (includes b0), per row
-        if ((rc = launch_row_gemm(g, st)) != DDP_OK) return rc;
-    }
-    if ((rc = launch_row_gemm(row(w.a0, L.h1, (const bf16*)(pb + L.tc_w1), L.h1, L.h2, L.h1, EPI_MISH_FWD, pk + L.b1, nullptr, w.a1, w.d1, nullptr, 0, 0), st)) != DDP_OK) return rc;
-    if ((rc = launch_row_gemm(row(w.a1, L.h2, (const bf16*)(pb + L.tc_w2), L.h2, L.h3, L.h2, EPI_MISH_FWD, pk + L.b2, nullptr, w.a2, w.d2, nullptr, 0, 0), st)) != DDP_OK) return rc;
-    {   // head + mse_loss (:320) + d loss / d eps_hat in the epilogue of the last GEMM
-        RowGemm g = row(w.a2, L.h3, (const bf16*)(pb + L.tr_w3), L.h3, 16, L.h3, EPI_MSE_HEAD, pk + L.b3, nullptr, w.deps, nullptr, nullptr, 0, L.A);
-        g.out_ld = 64; g.target = noise; g.target_ld = L.A; g.scale = inv_count; g.loss = loss_out;
-        if ((rc = launch_row_gemm(g, st)) != DDP_OK) return rc;
+    // ---- forward: one fused launch (all four layers on chip, activations / derivatives leave by TMA store) when the
+    // shape fits the sampler's tile plan, else one row GEMM per layer.  DDP_TRAIN_NO_CHAIN=1 forces the latter.
+    static const bool no_chain = getenv("DDP_TRAIN_NO_CHAIN") && atoi(getenv("DDP_TRAIN_NO_CHAIN")) != 0;
+    if (!no_chain && actor_train_chain_shape_ok(L)) {
+        if ((rc = actor_train_chain_fwd(L, packed, w.xin, t, noise, inv_count, loss_out, w.a0, w.d0, w.a1, w.d1, w.a2, w.d2,
+                                        w.deps, B, st)) != DDP_OK) return rc;
+    } else {
+        {
+            RowGemm g = row(w.xin, 64, (const bf16*)(pb + L.tr_w0), 64, L.h1, 64, EPI_MISH_FWD, nullptr, nullptr, w.a0, w.d0, nullptr, 0, 0);
+            if (!tcols) { g.tbl = pk + L.tb0; g.trow = t; g.tbl_ld = L.h1; g.tbl_rows = L.T; }   // time table (includes b0), per row
+            if ((rc = launch_row_gemm(g, st)) != DDP_OK) return rc;
+        }
+        if ((rc = launch_row_gemm(row(w.a0, L.h1, (const bf16*)(pb + L.tc_w1), L.h1, L.h2, L.h1, EPI_MISH_FWD, pk + L.b1, nullptr, w.a1, w.d1, nullptr, 0, 0), st)) != DDP_OK) return rc;
+        if ((rc = launch_row_gemm(row(w.a1, L.h2, (const bf16*)(pb + L.tc_w2), L.h2, L.h3, L.h2, EPI_MISH_FWD, pk + L.b2, nullptr, w.a2, w.d2, nullptr, 0, 0), st)) != DDP_OK) return rc;
+        {   // head + mse_loss (:320) + d loss / d eps_hat in the epilogue of the last GEMM
+            RowGemm g = row(w.a2, L.h3, (const bf16*)(pb + L.tr_w3), L.h3, 16, L.h3, EPI_MSE_HEAD, pk + L.b3, nullptr, w.deps, nullptr, nullptr, 0, L.A);
+            g.out_ld = 64; g.target = noise; g.target_ld = L.A; g.scale = inv_count; g.loss = loss_out;
+            if ((rc = launch_row_gemm(g, st)) != DDP_OK) return rc;
+        }
     }
     // ---- backward: dZ chain (dZ_l overwrites the stored derivative d_l in place)
     if ((rc = launch_row_gemm(row(w.deps, 64, (const bf16*)(pb + L.tr_w3t), 64, L.h3, 64, EPI_MUL_D, nullptr, w.d2, w.d2, nullptr, nullptr, 0, 0), st)) != DDP_OK) return rc;
