@@ -436,18 +436,31 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant_
             tmem_ld_wait();
             if (n < g.N) atomicAdd(g.colsum + n, __uint_as_float(v[0]));
         }
-        for (int p = 0; p < (k.BN >> 4); ++p) {
-            uint32_t v[16];
-            tmem_ld16(tb + p * 16, v);
+        // The accumulator arrives one output row (n) per lane; the atomics want one output row per INSTRUCTION (32 lanes
+        // on 32 consecutive k): each 32 x 32 block goes through a swizzled shared-memory transpose (the pipeline stages
+        // are idle by now), so a RED touches one 128-byte line instead of 32.
+        uint8_t* tr = smem + (warp - 2) * 4096;                      // [32 rows][128 B], 16-byte chunks XOR-swizzled by row
+        for (int p = 0; p < (k.BN >> 4); p += 2) {
+            uint32_t v[32];
+            tmem_ld16(tb + p * 16, reinterpret_cast<uint32_t(&)[16]>(v[0]));
+            tmem_ld16(tb + p * 16 + 16, reinterpret_cast<uint32_t(&)[16]>(v[16]));
             tmem_ld_wait();
-            if (n >= g.N) continue;
+            __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int kk = k0 + p * 16 + i;
-                if (kk >= g.K) break;
-                const int col = g.colmap ? g.colmap[kk] : kk;
-                if (col >= kDwCol2) atomicAdd(g.C2 + (size_t)n * g.ldc2 + (col - kDwCol2), __uint_as_float(v[i]));
-                else if (col >= 0) atomicAdd(g.C + (size_t)n * g.ldc + col, __uint_as_float(v[i]));
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(tr + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            const int kk = k0 + p * 16 + lane;
+            int col = -1;
+            if (kk < g.K) col = g.colmap ? g.colmap[kk] : kk;
+            float* dst = col >= kDwCol2 ? g.C2 + (col - kDwCol2) : g.C + col;
+            const size_t ld = col >= kDwCol2 ? (size_t)g.ldc2 : (size_t)g.ldc;
+            const int nrows = g.N - (n0 + q * 32) < 32 ? g.N - (n0 + q * 32) : 32;
+            if (col >= 0) {
+                for (int r = 0; r < nrows; ++r) {
+                    const float x = *reinterpret_cast<const float*>(tr + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                    atomicAdd(dst + (size_t)(n0 + q * 32 + r) * ld, x);
+                }
             }
         }
     }
