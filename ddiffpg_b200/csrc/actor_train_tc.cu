@@ -180,7 +180,8 @@ int actor_train_tc(const ActorLayout& L, const void* packed, const float* const 
     int rc;
     // ---- forward: one fused launch (all four layers on chip, activations / derivatives leave by TMA store) when the
     // shape fits the sampler's tile plan, else one row GEMM per layer.  DDP_TRAIN_NO_CHAIN=1 forces the latter.
-    static const bool no_chain = getenv("DDP_TRAIN_NO_CHAIN") && atoi(getenv("DDP_TRAIN_NO_CHAIN")) != 0;
+    const char* nc_env = getenv("DDP_TRAIN_NO_CHAIN");      // read per call: the tests switch between the two forwards
+    const bool no_chain = nc_env && atoi(nc_env) != 0;
     if (!no_chain && actor_train_chain_shape_ok(L)) {
         if ((rc = actor_train_chain_fwd(L, packed, w.xin, t, noise, inv_count, loss_out, w.a0, w.d0, w.a1, w.d1, w.a2, w.d2,
                                         w.deps, B, st)) != DDP_OK) return rc;

@@ -76,7 +76,8 @@ struct QcArgs {
     float* gsq;                      // [n_modes] += sum g^2 over the segment       (may be NULL)
     float* qmin;                     // [B]                                          (may be NULL)
     float* p_out[2];                 // [B, atoms] softmax of each net               (may be NULL)
-    uint16_t* dscr;                  // ELU' scratch: [grid][2 nets][(h1+h2+h3)/16][128 rows][16] bf16
+    uint16_t* dscr;                  // ELU' scratch: [grid][2 nets][(h1+h2+h3)/16][2 halves][128 rows][8] bf16 (a warp's
+                                     // 16-byte accesses are 512 contiguous bytes)
     long seg_off[kMaxModes + 1];
     int tile_off[kMaxModes + 1];
     float scale[kMaxModes];
@@ -194,7 +195,7 @@ __device__ __forceinline__ void emit_fwd(const QEpi& e, uint8_t* slot, const uin
     w0.x = pack_bf16x2(d[0], d[1]); w0.y = pack_bf16x2(d[2], d[3]); w0.z = pack_bf16x2(d[4], d[5]); w0.w = pack_bf16x2(d[6], d[7]);
     w1.x = pack_bf16x2(d[8], d[9]); w1.y = pack_bf16x2(d[10], d[11]); w1.z = pack_bf16x2(d[12], d[13]); w1.w = pack_bf16x2(d[14], d[15]);
     __stcg(reinterpret_cast<uint4*>(dptr), w0);
-    __stcg(reinterpret_cast<uint4*>(dptr) + 1, w1);
+    __stcg(reinterpret_cast<uint4*>(dptr) + kRows, w1);
 }
 
 // backward: 16 accumulator columns * ELU' -> A chunk (bf16)
@@ -216,14 +217,14 @@ template <bool FWD>
 __device__ __forceinline__ void q_drain(QEpi& e, int col, int nchunks, const float* bias, int g0, int signal_after) {
     const uint32_t tbase = e.tmem_base + ((uint32_t)(e.q * 32) << 16) + col + e.ch * kColsPerWarp;
     // scratch group of this warp's first 16 columns inside chunk 0 (4 groups per chunk)
-    uint16_t* dbase = e.dscr + ((size_t)(g0 + e.ch * (kColsPerWarp / 16)) * kRows + e.my_row) * 16;
+    uint16_t* dbase = e.dscr + (size_t)(g0 + e.ch * (kColsPerWarp / 16)) * kRows * 16 + e.my_row * 8;
     uint32_t va[16], vb[16];
     uint4 d0{}, d1{}, d2{}, d3{};
     tmem_ld16(tbase, va);
     if (!FWD) {
         const uint4* dp = reinterpret_cast<const uint4*>(dbase);
-        d0 = __ldcg(dp); d1 = __ldcg(dp + 1);
-        if (kColsPerWarp == 32) { d2 = __ldcg(dp + kRows * 2); d3 = __ldcg(dp + kRows * 2 + 1); }
+        d0 = __ldcg(dp); d1 = __ldcg(dp + kRows);
+        if (kColsPerWarp == 32) { d2 = __ldcg(dp + kRows * 2); d3 = __ldcg(dp + kRows * 3); }
     }
 #ifdef DDP_QC_FINE_TIMING
     long long* fine = (e.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? e.dbg + (FWD ? 16 : 24) : nullptr;
@@ -262,8 +263,8 @@ __device__ __forceinline__ void q_drain(QEpi& e, int col, int nchunks, const flo
                     emit_bwd(e, slot, vb, e.ch * 32 + 16, d2, d3);
                     if (c + 1 < nchunks) {
                         const uint4* dp = reinterpret_cast<const uint4*>(dptr + (size_t)4 * kRows * 16);
-                        d0 = __ldcg(dp); d1 = __ldcg(dp + 1);
-                        d2 = __ldcg(dp + kRows * 2); d3 = __ldcg(dp + kRows * 2 + 1);
+                        d0 = __ldcg(dp); d1 = __ldcg(dp + kRows);
+                        d2 = __ldcg(dp + kRows * 2); d3 = __ldcg(dp + kRows * 3);
                     }
                 }
                 QC_FINE(4);
@@ -274,7 +275,7 @@ __device__ __forceinline__ void q_drain(QEpi& e, int col, int nchunks, const flo
                 uint4 e0 = d0, e1 = d1;
                 if (!FWD && c + 1 < nchunks) {
                     const uint4* dp = reinterpret_cast<const uint4*>(dptr + (size_t)4 * kRows * 16);
-                    d0 = __ldcg(dp); d1 = __ldcg(dp + 1);
+                    d0 = __ldcg(dp); d1 = __ldcg(dp + kRows);
                 }
                 mbar_wait(qb_a_empty(e.bars, rs.idx), rs.phase ^ 1);
                 uint8_t* slot = e.smem + SMQ::aring + rs.idx * kChunkBytes;

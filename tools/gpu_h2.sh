@@ -1,6 +1,8 @@
 #!/bin/bash
+# H2 critic chain + the round's new tests, then the ascent / train bench lines
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_tc_gpu.py -m gpu -q --timeout 120 -k "q_" > gpurun_out/pytest_h2.log 2>&1
-echo "pytest exit $?" >> gpurun_out/pytest_h2.log
-grep -E "^E  .*(Error|assert)|passed|failed|^FAILED" gpurun_out/pytest_h2.log | head -20
-for prec in fp32 bf16; do timeout 300 python bench.py --workload ascent --precision $prec --batch 65536 --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_ascent_$prec.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$prec', d['value'], d['ms_per_step'], d['roofline']['frac'])"; tail -2 gpurun_out/bench_ascent_$prec.err; done
+timeout 600 python -m pytest tests -m gpu -q --timeout 200 -k "q_ or ascent or layerwise or requires_its_workspace or critic" > gpurun_out/pytest_h2.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_h2.log; tail -3 gpurun_out/pytest_h2.log
+for wl in ascent train; do
+timeout 300 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tee gpurun_out/bench_${wl}_bf16.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$wl', round(d['ms_per_step'],4), 'ms', round(d['value']/1e6,1), 'M/s frac', round(d['roofline']['frac'],4))"
+done
+timeout 100 python tools/qc_timing.py 2>&1 | head -13
