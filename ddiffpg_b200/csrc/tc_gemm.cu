@@ -260,26 +260,69 @@ row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
                     if (lane == 0 && sq != 0.f) atomicAdd(g.loss, sq * g.scale);
-                } else if (valid && c0 < g.N) {
-                    // backward epilogues: the row-per-lane accesses go straight to global memory (staging them was
-                    // measured slower: 41 / 72 / 147 us against 35 / 62 / 129 us for the three backward layers)
-                    float a[16];
-                    load_bf16x16(g.aux + row * g.aux_ld + c0, a);
-                    if (g.epi == EPI_MUL_D) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) z[i] *= a[i];
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) z[i] *= a[i] > 0.f ? 1.f : a[i] + 1.f;
-                    }
-                    store_bf16x16(g.out_a + row * g.out_ld + c0, z);
                 }
+            };
+            // backward epilogues: the row-per-lane accesses go straight to global memory (staging them was measured
+            // slower), but every aux operand of the warp's pieces is requested BEFORE the accumulator is waited for:
+            // one exposed memory latency per tile instead of one per 16-column piece
+            auto process_bwd = [&](const uint32_t (&cur)[16], int p, const uint4& a0, const uint4& a1) {
+                const int c0 = n0 + p * 16;
+                if (!valid || c0 >= g.N) return;
+                const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                float z[16];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xffff0000u);
+                    if (g.epi == EPI_MUL_D) {
+                        z[2 * i] = __uint_as_float(cur[2 * i]) * lo;
+                        z[2 * i + 1] = __uint_as_float(cur[2 * i + 1]) * hi;
+                    } else {
+                        z[2 * i] = __uint_as_float(cur[2 * i]) * (lo > 0.f ? 1.f : lo + 1.f);
+                        z[2 * i + 1] = __uint_as_float(cur[2 * i + 1]) * (hi > 0.f ? 1.f : hi + 1.f);
+                    }
+                }
+                store_bf16x16(g.out_a + row * g.out_ld + c0, z);
             };
             // the warps of a lane quarter split the 16-column pieces of the tile
             constexpr int kSplit = kRowEpiWarps / 4;
             const int part = (warp - 2) >> 2;
             const int p_begin = (pieces * part + kSplit - 1) / kSplit, p_end = (pieces * (part + 1) + kSplit - 1) / kSplit;
             uint32_t va[16], vb[16];
+            const bool needs_aux = g.epi == EPI_MUL_D || g.epi == EPI_MUL_ELU_D;
+            static_assert(256 / 16 / (kRowEpiWarps / 4) <= 8, "a warp owns at most 8 pieces of a tile");
+            if (needs_aux) {
+                uint4 axq[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c0 = n0 + (p_begin + j) * 16;
+                    axq[2 * j] = axq[2 * j + 1] = make_uint4(0u, 0u, 0u, 0u);
+                    if (p_begin + j < p_end && valid && c0 < g.N) {
+                        const uint4* ap = reinterpret_cast<const uint4*>(g.aux + row * g.aux_ld + c0);
+                        axq[2 * j] = ap[0]; axq[2 * j + 1] = ap[1];
+                    }
+                }
+                mbar_wait(bar_acc_full(buf), (it >> 1) & 1);
+                tc_fence_after();
+                if (p_begin < p_end) tmem_ld16(tb + p_begin * 16, va);
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    const int p = p_begin + j;
+                    if (p < p_end) {
+                        tmem_ld_wait();
+                        if (p + 1 < p_end) tmem_ld16(tb + (p + 1) * 16, vb);
+                        process_bwd(va, p, axq[2 * j], axq[2 * j + 1]);
+                        if (p + 1 < p_end) {
+                            tmem_ld_wait();
+                            if (p + 2 < p_end) tmem_ld16(tb + (p + 2) * 16, va);
+                            process_bwd(vb, p + 1, axq[2 * j + 2], axq[2 * j + 3]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_empty(buf));
+                continue;
+            }
             mbar_wait(bar_acc_full(buf), (it >> 1) & 1);
             tc_fence_after();
             if (p_begin < p_end) tmem_ld16(tb + p_begin * 16, va);
