@@ -98,13 +98,19 @@ __device__ __forceinline__ void mish_fd_n(float (&x)[N], float (&d)[N]) {
     float e[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) e[i] = ex2_approx(fminf(x[i] * kLog2e, 28.853900817779268f));
+    // one MUFU.RCP per two elements: 1/p0, 1/p1 = r p1, r p0 with r = rcp(p0 p1) (p <= e^40 + ..., the product stays
+    // far below 2^128); the XU pipe (ex2, rcp and the two bf16 packs per element) is what this epilogue saturates
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const float s = e[i] + 1.f;
-        const float r = rcp_approx(fmaf(s, s, 1.f));
-        const float w = fmaf(-2.f, r, 1.f);
-        d[i] = fmaf(4.f * x[i], (e[i] * s) * (r * r), w);
-        x[i] *= w;
+    for (int i = 0; i < N; i += 2) {
+        const float s0 = e[i] + 1.f, s1 = e[i + 1] + 1.f;
+        const float p0 = fmaf(s0, s0, 1.f), p1 = fmaf(s1, s1, 1.f);
+        const float r = rcp_approx(p0 * p1);
+        const float r0 = r * p1, r1 = r * p0;
+        const float w0 = fmaf(-2.f, r0, 1.f), w1 = fmaf(-2.f, r1, 1.f);
+        d[i] = fmaf(4.f * x[i], (e[i] * s0) * (r0 * r0), w0);
+        d[i + 1] = fmaf(4.f * x[i + 1], (e[i + 1] * s1) * (r1 * r1), w1);
+        x[i] *= w0;
+        x[i + 1] *= w1;
     }
 }
 
