@@ -253,7 +253,9 @@ def run_cuda(args):
         ts = torch.randint(0, T, (B,), generator=gen).to(dev)
         loss_h = torch.empty(2).pin_memory()
         step = lambda: trainer.step(st, ac, noise=nz, timesteps=ts)
-        launches_per_step = 14 + 2 + 12          # pack + fwd/bwd/dW kernels + clip/AdamW
+        # own kernels per step (profiles/r01/launches_train_bf16_v3.txt): re-pack 12, prep 1, fused forward 1, backward
+        # row GEMMs 3, dW GEMMs 4, time branch 6, norm / clip / AdamW 3, + 2 of the fp32 transposes
+        launches_per_step = 32
 
         def e2e_step():
             s = st_h.to(dev, non_blocking=True)

@@ -76,7 +76,8 @@ int ddp_actor_pack_parts(const ddp_actor_shape* shape, const float* const params
  * scheduler adds at t = T-j (j >= 1); action_out [B,A] in [-1,1].
  * DDP_BF16 needs a 16-byte aligned device workspace of ddp_actor_sample_workspace_bytes() (per-CTA scratch for the
  * state part of the first layer, 256 KB per SM at width 1024; queried with the target device current); DDP_FP32
- * needs none (0 bytes, ws may be NULL). */
+ * needs none (0 bytes, ws may be NULL).  Like every workspace of this API it belongs to one call at a time: launches
+ * that may overlap (different streams) need their own. */
 size_t ddp_actor_sample_workspace_bytes(const ddp_actor_shape* shape, long B, int precision);
 int ddp_actor_sample(const ddp_actor_shape* shape, const void* packed, const float* state,
                      const float* noise, float* action_out, long B, int precision,
