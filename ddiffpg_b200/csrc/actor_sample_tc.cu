@@ -31,8 +31,11 @@ namespace {
 constexpr int kRows = 128;                  // rows per tile == UMMA M
 constexpr int kChunkBytes = kRows * 128;    // one A chunk: 128 rows x 64 bf16
 constexpr int kStageBytes = 256 * 128;      // one weight stage: up to 256 rows x 64 bf16
-constexpr int kStages = 4;
-constexpr int kASlots = 4;
+#ifndef DDP_TC_STAGES
+#define DDP_TC_STAGES 4
+#endif
+constexpr int kStages = DDP_TC_STAGES;       // 32 KB weight stages; stages + A slots / 2 = 6 fills shared memory
+constexpr int kASlots = 2 * (6 - kStages);   // 16 KB A chunks
 #ifndef DDP_TC_HALF_EX2
 #define DDP_TC_HALF_EX2 0   // 1: packed-fp16 ex2 in the bf16 steps (one MUFU op per two elements)
 #endif
@@ -781,6 +784,90 @@ extern "C" int ddp_debug_tc_gemm(const void* A, const void* Bm, float* C, int N,
     DDP_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_gemm_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(m, (const __nv_bfloat16*)A, C, N, K);
     DDP_LAUNCH_CHECK("tc_gemm_selftest_kernel");
+    return DDP_OK;
+}
+
+// Layout probe (development aid for the 64-row tile plan): one tcgen05.mma with M = 64 (A: 64 rows x 64 bf16, manual
+// SWIZZLE_128B; B: [N][64] by TMA), then ALL 128 TMEM lanes x N columns are dumped with 32x32b loads, so the host can
+// see which (lane, column) each accumulator element D[r][n] landed in.  raw: [128][N] fp32.
+namespace ddp {
+namespace {
+__global__ void __launch_bounds__(128, 1)
+tc_m64_probe_kernel(const __grid_constant__ CUtensorMap map_b, const __nv_bfloat16* __restrict__ A, float* __restrict__ raw, int N) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t rawa = smem_u32(smem_raw);
+    const uint32_t base = (rawa + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - rawa);
+    const uint32_t a_off = 0, b_off = kChunkBytes, bar_off = kChunkBytes + kStageBytes, tp_off = bar_off + 16;
+    const uint32_t bar_full = base + bar_off, bar_done = base + bar_off + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(bar_full, 1); mbar_init(bar_done, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(base + tp_off, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + tp_off);
+    // poison the accumulator region first so that untouched lanes are recognisable
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t v[16];
+        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(-1.f);
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                     ::"r"(tmem_base + ((uint32_t)(warp * 32) << 16) + c0), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
+                       "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    if (threadIdx.x < 64) {
+        const uint4* src = reinterpret_cast<const uint4*>(A + (size_t)threadIdx.x * 64);
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(smem + a_off + sw128_offset(threadIdx.x, j * 8)) = src[j];
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tc_fence_after();
+        mbar_expect_tx(bar_full, (uint32_t)N * 128u);
+        tma_load_2d(base + b_off, &map_b, bar_full, 0, 0);
+        mbar_wait(bar_full, 0);
+        tc_fence_after();
+        const uint32_t idesc = make_idesc_bf16(64, N);
+        const uint64_t ad = make_smem_desc_sw128(base + a_off), bd = make_smem_desc_sw128(base + b_off);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, k != 0);
+        umma_commit(bar_done);
+        mbar_wait(bar_done, 0);
+    }
+    __syncthreads();
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 16; ++i) raw[(size_t)(warp * 32 + lane) * N + c0 + i] = __uint_as_float(v[i]);
+    }
+    // second dump: the first 8 columns of each lane quarter through the 16-lane shape (16x256b.x1: 4 registers per
+    // thread), appended as frag[warp][thread][4] after the raw block
+    {
+        uint32_t f[4];
+        asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(f[0]), "=r"(f[1]), "=r"(f[2]), "=r"(f[3]) : "r"(tmem_base + ((uint32_t)(warp * 32) << 16)));
+        tmem_ld_wait();
+        for (int i = 0; i < 4; ++i) raw[(size_t)128 * N + (warp * 32 + lane) * 4 + i] = __uint_as_float(f[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+}  // namespace
+}  // namespace ddp
+
+extern "C" int ddp_debug_tc_m64_probe(const void* A, const void* Bm, float* raw, int N, void* stream) {
+    using namespace ddp;
+    if (N % 16 || N < 16 || N > 256) DDP_FAIL(DDP_ERR_SHAPE, "m64 probe: N in [16,256] step 16");
+    CUtensorMap m;
+    if (tc::make_tmap_bf16_sw128(&m, Bm, N, 64, N) != 0) DDP_FAIL(DDP_ERR_CUDA, "m64 probe: tensor map encode failed");
+    const size_t smem = kChunkBytes + kStageBytes + 64 + 1024;
+    DDP_CUDA_CHECK(cudaFuncSetAttribute(tc_m64_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_m64_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(m, (const __nv_bfloat16*)A, raw, N);
+    DDP_LAUNCH_CHECK("tc_m64_probe_kernel");
     return DDP_OK;
 }
 
