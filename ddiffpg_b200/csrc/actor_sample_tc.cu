@@ -68,7 +68,8 @@ struct TcArgs {
     long B;
     int S, A, T, h1, h2, h3;
     int nparts1, part1;        // layer-1 output split into nparts1 parts of part1 (<= 256) columns
-    int num_tiles;
+    int num_tiles;             // tiles of this launch (128 rows each, or 64 in the M = 64 kernel)
+    long row0;                 // first row of this launch
     ExplNoise expl;            // optional exploration / target-policy noise epilogue
     long long* dbg;            // optional per-phase cycle counters of CTA 0 (development aid), else NULL
 };
@@ -113,12 +114,14 @@ struct EpiCtx {
     Ring as;
     long row;
     bool valid;
+    bool owner;                         // this thread owns a row of the tile (64-row tiles: lanes 0..15 only)
     float xr[8];                        // x_t of the owned row (ch == 0 threads), fp32
 };
 
 // [x (8) | state (S) | 0 ...] of the owned row into the layer-0 input tile, in the operand format F16/bf16
 template <bool F16>
 __device__ __forceinline__ void write_in0_row(const TcArgs& a, const EpiCtx& e, int nstate) {
+    if (!e.owner) return;
     uint16_t* rp = reinterpret_cast<uint16_t*>(e.smem + SM::in0) + e.my_row * kIn0Stride;
     uint4 xv;
     xv.x = pack2<F16>(e.xr[0], e.xr[1]); xv.y = pack2<F16>(e.xr[2], e.xr[3]);
@@ -209,6 +212,61 @@ __device__ __forceinline__ void drain_acc(EpiCtx& e, int nchunks, const float* b
     }
 }
 
+// 64-row tiles (tcgen05.mma M = 64): D[r][n] sits in lane (r % 16) + 32 (r / 16), column n (tools/m64_probe.py), i.e.
+// each lane quarter holds 16 rows.  tcgen05.ld.16x256b hands them to the warp as mma.m16n8 C fragments -- thread t:
+// rows t/4 and t/4 + 8 of the quarter, columns 2 (t % 4), +1 of every 8-column block -- so all 32 lanes work and the
+// warp's share of a chunk (16 rows x 32 columns) is half of what it is in a 128-row tile.
+__device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
+template <bool F16>
+__device__ __forceinline__ void drain_acc_m64(EpiCtx& e, int nchunks, const float* bias, int lo_chunks) {
+    const uint32_t tbase = e.tmem_base + ((uint32_t)(e.q * 32) << 16) + e.ch * kColsPerWarp;
+    uint32_t va[kNT][4], vb[kNT][4];
+    auto fetch = [&](int c, uint32_t (&v)[kNT][4]) {
+#pragma unroll
+        for (int nt = 0; nt < kNT; ++nt) tmem_ld_16x256b(tbase + c * 64 + nt * 8, v[nt]);
+    };
+    auto chunk = [&](int c, const uint32_t (&v)[kNT][4]) {
+        float x[kNT * 4];
+#pragma unroll
+        for (int nt = 0; nt < kNT; ++nt) {
+            const float2 b = *reinterpret_cast<const float2*>(bias + c * 64 + e.ch * kColsPerWarp + nt * 8 + 2 * e.t4);
+            x[nt * 4 + 0] = __uint_as_float(v[nt][0]) + b.x; x[nt * 4 + 1] = __uint_as_float(v[nt][1]) + b.y;
+            x[nt * 4 + 2] = __uint_as_float(v[nt][2]) + b.x; x[nt * 4 + 3] = __uint_as_float(v[nt][3]) + b.y;
+        }
+        mish_fast_n<kNT * 4, !F16 && DDP_TC_HALF_EX2>(x);
+        mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
+        uint8_t* slot = e.smem + SM::aring + e.as.idx * kChunkBytes;
+#pragma unroll
+        for (int nt = 0; nt < kNT; ++nt) {
+            const int r0 = e.q * 16 + e.g, col = e.ch * kColsPerWarp + nt * 8 + 2 * e.t4;
+            *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0, col)) = pack2<F16>(x[nt * 4 + 0], x[nt * 4 + 1]);
+            *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0 + 8, col)) = pack2<F16>(x[nt * 4 + 2], x[nt * 4 + 3]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (e.lane == 0) {
+            mbar_arrive(bar_a_full(e.bars, e.as.idx));
+            if (c == lo_chunks) mbar_arrive(bar_lo_free(e.bars));
+        }
+        e.as.advance(kASlots);
+    };
+    fetch(0, va);
+    for (int c = 0; c < nchunks; c += 2) {
+        tmem_ld_wait();
+        if (c + 1 < nchunks) fetch(c + 1, vb);
+        chunk(c, va);
+        if (c + 1 < nchunks) {
+            tmem_ld_wait();
+            if (c + 2 < nchunks) fetch(c + 2, va);
+            chunk(c + 1, vb);
+        }
+    }
+}
+
 // Scratch slot of this lane for chunk c: 4 x 16 B, [c][warp][j][lane] so that every access is one coalesced 512 B row
 __device__ __forceinline__ uint4* pscr_slot(const TcArgs& a, const EpiCtx& e, int c) {
     return a.pscr + ((size_t)blockIdx.x * e.NC1 + c) * (kEpiWarps * 4 * 32) + (e.q + 4 * e.ch) * (4 * 32) + e.lane;
@@ -218,14 +276,20 @@ __device__ __forceinline__ uint4* pscr_slot(const TcArgs& a, const EpiCtx& e, in
 // chunk (k16 steps 1 and 2 of the layer-0 contraction; operands in the first step's format), kept as fp16 in the
 // lane's own fragment order.  Written and read back by the same thread: no synchronisation is involved.
 static_assert(kEpiWarps == 8 && kNT == 4, "the state-partial fragment order is laid out for 8 warps x 32 columns");
-template <bool F16>
+// ldmatrix lane address of the m16 tile(s) this warp contracts: rows q*32 + mt*16 (128-row tile) or q*16 (64-row tile)
+template <bool HM>
+__device__ __forceinline__ uint32_t in0_lane_addr(const EpiCtx& e) {
+    const int r = (HM ? e.q * 16 : e.q * 32) + (e.lane & 7) + ((e.lane >> 3) & 1) * 8;
+    return smem_u32(e.smem + SM::in0) + (uint32_t)((r * kIn0Stride + (e.lane >> 4) * 8) * 2);
+}
+template <bool F16, bool HM>
 __device__ __forceinline__ void state_partial(const TcArgs& a, const EpiCtx& e) {
-    const uint32_t in0_lane = smem_u32(e.smem + SM::in0) +
-        (uint32_t)(((e.q * 32 + (e.lane & 7) + ((e.lane >> 3) & 1) * 8) * kIn0Stride + (e.lane >> 4) * 8) * 2);
+    constexpr int MT = HM ? 1 : 2;
+    const uint32_t in0_lane = in0_lane_addr<HM>(e);
     const uint2* wf = F16 ? a.w0frag_h : a.w0frag;
-    uint32_t af[2][2][4];
+    uint32_t af[MT][2][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
             ldmatrix_x4(af[mt][ks], in0_lane + (uint32_t)((mt * 16 * kIn0Stride + (ks + 1) * 16) * 2));
@@ -243,7 +307,7 @@ __device__ __forceinline__ void state_partial(const TcArgs& a, const EpiCtx& e) 
         load_b(min(c + 1, e.NC1 - 1), nxt);       // next chunk's fragments in flight during this chunk's HMMAs
         uint4* dst = pscr_slot(a, e, c);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
             uint32_t h[kNT][2];
 #pragma unroll
             for (int nt = 0; nt < kNT; ++nt) {
@@ -262,24 +326,24 @@ __device__ __forceinline__ void state_partial(const TcArgs& a, const EpiCtx& e) 
 }
 
 // One denoising step of the epilogue warps (operand format of THIS step = F16 ? fp16 : bf16).
-template <bool F16>
+template <bool F16, bool HM>
 __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
+    constexpr int MT = HM ? 1 : 2;
     const int t = a.T - 1 - j;
     const bool prof = a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long tk0 = prof ? clock64() : 0, tk1;
 #define DDP_TICK(slot) do { if (prof) { tk1 = clock64(); a.dbg[slot] += tk1 - tk0; tk0 = tk1; } } while (0)
     // ---- layer 0: one 64-feature chunk at a time, straight into the A ring.  accumulator = state partial of the
     // tile (scratch, fp16) + time-table row + one k16 step over [x_t | state[0:8]]
-    const uint32_t in0_lane = smem_u32(e.smem + SM::in0) +
-        (uint32_t)(((e.q * 32 + (e.lane & 7) + ((e.lane >> 3) & 1) * 8) * kIn0Stride + (e.lane >> 4) * 8) * 2);
-    uint32_t afx[2][4];
+    const uint32_t in0_lane = in0_lane_addr<HM>(e);
+    uint32_t afx[MT][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) ldmatrix_x4(afx[mt], in0_lane + (uint32_t)((mt * 16 * kIn0Stride) * 2));
+    for (int mt = 0; mt < MT; ++mt) ldmatrix_x4(afx[mt], in0_lane + (uint32_t)((mt * 16 * kIn0Stride) * 2));
     const float* tb = a.tb0 + (size_t)t * a.h1;
     const uint2* wf = F16 ? a.w0frag_h : a.w0frag;
     uint2 bfr[kNT];
     float2 bias[kNT];
-    uint4 pp[4];
+    uint4 pp[2 * MT];
     // packed fragment order: [chunk][32-feature half][n8 tile 0..3][k16 step][lane]; this warp's first
     // feature inside the chunk is ch * kColsPerWarp
     auto load_frags = [&](int c) {
@@ -292,14 +356,14 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
             bias[nt] = __ldg(reinterpret_cast<const float2*>(tb + c * 64 + e.ch * kColsPerWarp + nt * 8 + 2 * e.t4));
         const uint4* ps = pscr_slot(a, e, c);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pp[j] = __ldcg(ps + j * 32);
+        for (int j = 0; j < 2 * MT; ++j) pp[j] = __ldcg(ps + j * 32);
     };
     load_frags(0);
     int pending0 = -1;
     for (int c = 0; c < e.NC1; ++c) {
-        float acc[2][kNT][4];
+        float acc[MT][kNT][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
             for (int nt = 0; nt < kNT; ++nt) {
                 const uint4 pv = pp[mt * 2 + (nt >> 1)];
@@ -322,13 +386,13 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
         mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
         uint8_t* slot = e.smem + SM::aring + e.as.idx * kChunkBytes;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
 #ifndef DDP_EXP_NO_L0_MISH
             mish_fast_n<kNT * 4, !F16 && DDP_TC_HALF_EX2>(reinterpret_cast<float(&)[kNT * 4]>(acc[mt]));
 #endif
 #pragma unroll
             for (int nt = 0; nt < kNT; ++nt) {
-                const int r0 = e.q * 32 + mt * 16 + e.g, col = e.ch * kColsPerWarp + nt * 8 + 2 * e.t4;
+                const int r0 = (HM ? e.q * 16 : e.q * 32 + mt * 16) + e.g, col = e.ch * kColsPerWarp + nt * 8 + 2 * e.t4;
                 *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0, col)) = pack2<F16>(acc[mt][nt][0], acc[mt][nt][1]);
                 *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0 + 8, col)) = pack2<F16>(acc[mt][nt][2], acc[mt][nt][3]);
             }
@@ -354,13 +418,15 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
     mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
     tc_fence_after();
     DDP_TICK(1);       // wait for the last layer-1 MMA
-    drain_acc<F16>(e, e.NC2, sb1, e.NC3 - 1);          // lo_free: TMEM cols [0, h3) are drained
+    if constexpr (HM) drain_acc_m64<F16>(e, e.NC2, sb1, e.NC3 - 1);
+    else drain_acc<F16>(e, e.NC2, sb1, e.NC3 - 1);     // lo_free: TMEM cols [0, h3) are drained
     DDP_TICK(2);       // drain acc1
     // ---- layer-2 epilogue: acc2 (TMEM cols [0,h3)) -> +b2, Mish -> A chunks of layer 3
     mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
     tc_fence_after();
     DDP_TICK(3);       // wait for the last layer-2 MMA
-    drain_acc<F16>(e, e.NC3, sb2, -1);
+    if constexpr (HM) drain_acc_m64<F16>(e, e.NC3, sb2, -1);
+    else drain_acc<F16>(e, e.NC3, sb2, -1);
     DDP_TICK(4);       // drain acc2
 
     // ---- head + scheduler step: eps_hat from acc3, x_t in registers (fp32)
@@ -406,6 +472,9 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
 #undef DDP_TICK
 }
 
+// HM = false: 128-row tiles.  HM = true: 64-row tiles (tcgen05.mma M = 64) for small batches -- a separate instantiation,
+// so neither pays for the other's registers or code size (one kernel with both paths inlined ran 20 % slower).
+template <bool HM>
 __global__ void __launch_bounds__(kThreads, 1)
 actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
                        const __grid_constant__ CUtensorMap map_w1h, const __grid_constant__ CUtensorMap map_w2h,
@@ -443,7 +512,6 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + SM::tmem_ptr);
-
     if (warp == kEpiWarps) {
         // ============================================================== TMA producer (one lane)
         if (lane == 0) {
@@ -482,9 +550,10 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
                 for (int j = 0; j < a.T; ++j) {
                     const bool f16 = a.first_f16 && j == 0;
-                    const uint32_t idesc1 = make_idesc_16(kRows, a.part1, f16);
-                    const uint32_t idesc2 = make_idesc_16(kRows, a.h3, f16);
-                    const uint32_t idesc3 = make_idesc_16(kRows, 16, f16);
+                    constexpr int M = HM ? 64 : kRows;
+                    const uint32_t idesc1 = make_idesc_16(M, a.part1, f16);
+                    const uint32_t idesc2 = make_idesc_16(M, a.h3, f16);
+                    const uint32_t idesc3 = make_idesc_16(M, 16, f16);
                     const uint32_t w3base = base + (f16 ? SM::w3_f16 : SM::w3);
                     // ---- layer 1: acc1[128 x h2] (TMEM cols [0, h2)) += h0 chunk . W1 chunk^T
                     for (int c = 0; c < NC1; ++c) {
@@ -545,12 +614,19 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
         EpiCtx e;
         e.smem = smem; e.bars = bars; e.tmem_base = tmem_base;
         e.q = warp & 3; e.ch = warp >> 2; e.g = lane >> 2; e.t4 = lane & 3; e.lane = lane;
-        e.my_row = e.q * 32 + lane;
         e.NC1 = NC1; e.NC2 = NC2; e.NC3 = NC3;
         e.acc_phase = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-            e.row = (long)tile * kRows + e.my_row;
-            e.valid = e.row < a.B;
+            if (!HM) {
+                e.my_row = e.q * 32 + lane;
+                e.owner = true;
+                e.row = a.row0 + (long)tile * kRows + e.my_row;
+            } else {
+                e.my_row = e.q * 16 + (lane & 15);
+                e.owner = lane < 16;
+                e.row = a.row0 + (long)tile * 64 + e.my_row;
+            }
+            e.valid = e.owner && e.row < a.B;
             // ---- tile prologue: x_T -> registers; [x | state | 0] -> in0 in the first step's operand format
             if (e.ch == 0) {
 #pragma unroll
@@ -558,9 +634,9 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
                 if (a.first_f16) write_in0_row<true>(a, e, kK0 - 8); else write_in0_row<false>(a, e, kK0 - 8);
             }
             epi_bar_sync();
-            if (a.first_f16) state_partial<true>(a, e); else state_partial<false>(a, e);
+            if (a.first_f16) state_partial<true, HM>(a, e); else state_partial<false, HM>(a, e);
             for (int j = 0; j < a.T; ++j) {
-                if (a.first_f16 && j == 0) epi_step<true>(a, e, j); else epi_step<false>(a, e, j);
+                if (a.first_f16 && j == 0) epi_step<true, HM>(a, e, j); else epi_step<false, HM>(a, e, j);
             }
         }
     }
@@ -664,12 +740,29 @@ static int tc_sm_count() {
     return sms;
 }
 
+// Tiles of a launch.  Batches of at most half a wave of 128-row tiles run on 64-row tiles instead (tcgen05.mma M = 64, its
+// own kernel instantiation): twice the SMs and 0.135 instead of 0.17 ms per call at 256 ... 9 472 states.  For the partial
+// LAST wave of a large batch the same idea was built and measured -- 136 64-row tiles behind the 444 128-row tiles of a
+// 65 536-state launch, also with a programmatic dependent launch so that they fill SMs as the first kernel's CTAs retire --
+// and gains nothing (0.5954 vs 0.5953 ms): a 64-row tile-step costs 0.89 of a 128-row one, because the weight stream
+// (1.25 MB per tile-step from L2), the MMA issue time (M = 64 runs at the M = 128 rate) and the per-chunk hand-over do not
+// shrink with the rows.  DDP_TC_NO_HALF_TILES=1 switches the 64-row tiles off.
+struct TilePlan { int num_full, num_half, grid_full, grid_half; };
+static TilePlan tile_plan(long B, int sms) {
+    static const bool no_half = getenv("DDP_TC_NO_HALF_TILES") && atoi(getenv("DDP_TC_NO_HALF_TILES")) != 0;
+    const long tiles = (B + kRows - 1) / kRows;
+    TilePlan p;
+    p.num_full = (int)tiles; p.num_half = 0;
+    if (sms > 0 && !no_half && 2 * tiles <= sms) { p.num_full = 0; p.num_half = (int)((B + 63) / 64); }
+    p.grid_full = p.num_full < sms ? p.num_full : sms;
+    p.grid_half = p.num_half < sms ? p.num_half : sms;
+    return p;
+}
+
 // state partial sums: one [h1/64][8 warps][4][32 lanes] x 16 B block per resident CTA (256 KB at h1 = 1024)
 size_t actor_sample_tc_workspace(const ActorLayout& L, long B) {
-    const long tiles = (B + kRows - 1) / kRows;
-    const long sms = tc_sm_count();
-    const long ctas = tiles < sms ? tiles : sms;
-    return (size_t)ctas * (L.h1 / 64) * kEpiWarps * 4 * 32 * sizeof(uint4);
+    const TilePlan p = tile_plan(B, tc_sm_count());
+    return (size_t)(p.grid_full + p.grid_half) * (L.h1 / 64) * kEpiWarps * 4 * 32 * sizeof(uint4);
 }
 
 int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state, const float* noise, float* out,
@@ -691,11 +784,10 @@ int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state
     a.first_f16 = pure_bf16 ? 0 : 1;
     a.tb0 = pk + L.tb0; a.b1 = pk + L.b1; a.b2 = pk + L.b2; a.b3 = pk + L.b3; a.cst = pk + L.cst;
     a.state = state; a.noise = noise; a.out = out; a.B = B;
-    a.pscr = (uint4*)ws;
     a.S = L.S; a.A = L.A; a.T = L.T; a.h1 = L.h1; a.h2 = L.h2; a.h3 = L.h3;
     a.nparts1 = L.h2 > 256 ? L.h2 / 256 : 1;
     a.part1 = L.h2 / a.nparts1;
-    a.num_tiles = (int)((B + kRows - 1) / kRows);
+    const TilePlan plan = tile_plan(B, tc_sm_count());
     a.dbg = g_tc_dbg;
     a.expl = expl;
     CUtensorMap m1, m2, m1h, m2h;
@@ -707,9 +799,17 @@ int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state
     const int sms = tc_sm_count();
     if (sms <= 0) DDP_FAIL(DDP_ERR_CUDA, "cannot query the SM count");
     const size_t smem = SM::total + 1024;         // slack for the 1024-byte alignment of the base
-    DDP_CUDA_CHECK(cudaFuncSetAttribute(actor_sample_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    actor_sample_tc_kernel<<<grid, kThreads, smem, st>>>(m1, m2, m1h, m2h, a);
+    const size_t per_cta = (size_t)(L.h1 / 64) * kEpiWarps * 4 * 32;      // uint4 of state-partial scratch per CTA
+    if (plan.num_full > 0) {
+        a.num_tiles = plan.num_full; a.row0 = 0; a.pscr = (uint4*)ws;
+        DDP_CUDA_CHECK(cudaFuncSetAttribute(actor_sample_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        actor_sample_tc_kernel<false><<<plan.grid_full, kThreads, smem, st>>>(m1, m2, m1h, m2h, a);
+    }
+    if (plan.num_half > 0) {
+        a.num_tiles = plan.num_half; a.row0 = (long)plan.num_full * kRows; a.pscr = (uint4*)ws + (size_t)plan.grid_full * per_cta;
+        DDP_CUDA_CHECK(cudaFuncSetAttribute(actor_sample_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        actor_sample_tc_kernel<true><<<plan.grid_half, kThreads, smem, st>>>(m1, m2, m1h, m2h, a);
+    }
     DDP_LAUNCH_CHECK("actor_sample_tc_kernel");
     return DDP_OK;
 }
