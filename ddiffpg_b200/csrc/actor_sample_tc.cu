@@ -39,15 +39,12 @@ constexpr int kASlots = 2 * (6 - kStages);   // 16 KB A chunks
 #ifndef DDP_TC_HALF_EX2
 #define DDP_TC_HALF_EX2 0   // 1: packed-fp16 ex2 in the bf16 steps (one MUFU op per two elements)
 #endif
-#ifndef DDP_TC_EPI_WARPS
-#define DDP_TC_EPI_WARPS 8
-#endif
 #ifndef DDP_TC_PAIR_PUBLISH
 #define DDP_TC_PAIR_PUBLISH 0   // 1: two chunks per proxy fence (measured slower here: it delays the layer-1 MMAs)
 #endif
 constexpr bool kPairPublish = DDP_TC_PAIR_PUBLISH != 0;
-constexpr int kEpiWarps = DDP_TC_EPI_WARPS;  // 8 or 16 (2 or 4 per SM sub-partition)
-constexpr int kColsPerWarp = 64 / (kEpiWarps / 4);   // columns of a 64-column chunk owned by one warp (32 or 16)
+constexpr int kEpiWarps = 8;                 // two per SM sub-partition (16 spill under the 96-register cap: 1.28 ms)
+constexpr int kColsPerWarp = 32;             // columns of a 64-column chunk owned by one warp
 constexpr int kNT = kColsPerWarp / 8;        // mma.sync n8 tiles per warp in layer 0
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kEpiThreads + 64;  // + TMA warp + MMA warp
@@ -142,12 +139,7 @@ __device__ __forceinline__ void emit_half(const EpiCtx& e, uint8_t* slot, const 
         x[i4 * 4 + 0] = __uint_as_float(v[i4 * 4 + 0]) + b.x; x[i4 * 4 + 1] = __uint_as_float(v[i4 * 4 + 1]) + b.y;
         x[i4 * 4 + 2] = __uint_as_float(v[i4 * 4 + 2]) + b.z; x[i4 * 4 + 3] = __uint_as_float(v[i4 * 4 + 3]) + b.w;
     }
-#if DDP_TC_EPI_WARPS >= 16
-    mish_fast_n<8>(reinterpret_cast<float(&)[8]>(x[0]));
-    mish_fast_n<8>(reinterpret_cast<float(&)[8]>(x[8]));
-#else
     mish_fast_n<16, !F16 && DDP_TC_HALF_EX2>(x);
-#endif
 #pragma unroll
     for (int i8 = 0; i8 < 2; ++i8) {
         uint4 w;
@@ -158,7 +150,7 @@ __device__ __forceinline__ void emit_half(const EpiCtx& e, uint8_t* slot, const 
 }
 
 // Drain `nchunks` 64-column chunks of the accumulator at TMEM column 0 into the A ring.  This warp owns
-// kColsPerWarp columns of each chunk, moved as 16-column TMEM loads: while one piece goes through Mish the
+// 32 columns of each chunk, moved as 16-column TMEM loads: while one piece goes through Mish the
 // next load is in flight (two 16-register buffers).  After chunk `signal_after` the thread arrives on
 // lo_free (-1: never).
 template <bool F16>
@@ -169,28 +161,14 @@ __device__ __forceinline__ void drain_acc(EpiCtx& e, int nchunks, const float* b
     tmem_ld16(tbase, va);
     for (int c = 0; c < nchunks; ++c) {
         const float* bb = bias + c * 64 + e.ch * kColsPerWarp;
-        if (kColsPerWarp == 32) {
-            tmem_ld_wait();
-            tmem_ld16(tbase + c * 64 + 16, vb);
-            mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
-            uint8_t* slot = e.smem + SM::aring + e.as.idx * kChunkBytes;
-            emit_half<F16>(e, slot, va, bb, e.ch * 32);
-            tmem_ld_wait();
-            if (c + 1 < nchunks) tmem_ld16(tbase + (c + 1) * 64, va);
-            emit_half<F16>(e, slot, vb, bb + 16, e.ch * 32 + 16);
-        } else {
-            // 16 columns per warp: alternate the two buffers chunk by chunk
-            tmem_ld_wait();
-            mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
-            uint8_t* slot = e.smem + SM::aring + e.as.idx * kChunkBytes;
-            if ((c & 1) == 0) {
-                if (c + 1 < nchunks) tmem_ld16(tbase + (c + 1) * 64, vb);
-                emit_half<F16>(e, slot, va, bb, e.ch * 16);
-            } else {
-                if (c + 1 < nchunks) tmem_ld16(tbase + (c + 1) * 64, va);
-                emit_half<F16>(e, slot, vb, bb, e.ch * 16);
-            }
-        }
+        tmem_ld_wait();
+        tmem_ld16(tbase + c * 64 + 16, vb);
+        mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
+        uint8_t* slot = e.smem + SM::aring + e.as.idx * kChunkBytes;
+        emit_half<F16>(e, slot, va, bb, e.ch * 32);
+        tmem_ld_wait();
+        if (c + 1 < nchunks) tmem_ld16(tbase + (c + 1) * 64, va);
+        emit_half<F16>(e, slot, vb, bb + 16, e.ch * 32 + 16);
         // every lane publishes its own writes to the async proxy, then one lane arrives for the warp
         // (32 lanes arriving on one mbarrier word serialise in the shared-memory pipe).  Two chunks share one
         // publication: the proxy fence is the expensive part of handing a chunk over.
