@@ -89,6 +89,28 @@ class _ActorLossFn(torch.autograd.Function):
         return (None, None, None, None, None, *outs)
 
 
+def host_batch_ranges(B, chunks, sms):
+    """Row ranges of a host-resident batch for the copy / compute pipeline of ``get_actions_host``.  Below ~8k rows per
+    range the copies are microseconds and extra launches cost more than they hide: one range.  Otherwise ranges are whole
+    waves of the sampler (``sms`` tiles of 128 rows), at most ``chunks`` of them, with the partial wave FIRST: the first
+    launch then waits for the smallest upload, and no range ends in a second partial wave."""
+    chunks = max(1, min(chunks, B // 8192))
+    if chunks == 1:
+        return [(0, B)] if B > 0 else []
+    wave = sms * 128
+    n_waves, rem = divmod(B, wave)
+    if n_waves == 0:
+        return [(0, B)]
+    ranges = [(0, rem)] if rem else []
+    groups = max(1, min(n_waves, chunks - len(ranges)))
+    lo = rem
+    for g in range(groups):
+        w = n_waves // groups + (1 if g < n_waves % groups else 0)
+        ranges.append((lo, lo + w * wave))
+        lo += w * wave
+    return ranges
+
+
 class DiffusionPolicy(nn.Module):
     """Drop-in for ``ddiffpg.models.diffusion_mlp.DiffusionPolicy`` (:148-321).
 
@@ -228,7 +250,8 @@ class DiffusionPolicy(nn.Module):
     def get_actions_host(self, state_host, out_host=None, chunks=4, precision=None):
         """``actor(obs)`` for a batch that lives in (pinned) HOST memory, the situation of the reference's env
         wrappers (wrappers/d4rl_wrapper.py:21-45 copy observations up and actions down around every call).
-        The batch is cut into ``chunks`` row ranges; the H2D copy of range i+1 and the D2H copy of range i-1
+        The batch is cut into at most ``chunks`` row ranges (``host_batch_ranges``: whole sampler waves, the partial
+        wave first); the H2D copy of range i+1 and the D2H copy of range i-1
         overlap the sampler launch of range i on two side streams, so PCIe time hides behind the kernel.
         Returns ``out_host`` ([B, A] fp32, pinned; valid once the call returns)."""
         precision = precision or self.precision
@@ -239,20 +262,17 @@ class DiffusionPolicy(nn.Module):
             out_host = torch.empty((B, A), dtype=torch.float32).pin_memory()
         if B == 0:
             return out_host
-        # below ~8k rows per range the copies are microseconds and the extra launches cost more than they hide
-        chunks = max(1, min(chunks, B // 8192))
+        ranges = host_batch_ranges(B, chunks, torch.cuda.get_device_properties(dev).multi_processor_count)
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream()
             if "h2d" not in self._ws:
                 self._ws["h2d"], self._ws["d2h"] = torch.cuda.Stream(), torch.cuda.Stream()
             h2d, d2h = self._ws["h2d"], self._ws["d2h"]
             h2d.wait_stream(main)
-            rows = ((B + chunks - 1) // chunks + 127) // 128 * 128
             st_dev = torch.empty((B, state_host.shape[1]), device=dev, dtype=torch.float32)
             out_dev = torch.empty((B, A), device=dev, dtype=torch.float32)
             done = []
-            for lo in range(0, B, rows):
-                hi = min(B, lo + rows)
+            for lo, hi in ranges:
                 with torch.cuda.stream(h2d):
                     st_dev[lo:hi].copy_(state_host[lo:hi], non_blocking=True)
                     ev = torch.cuda.Event()

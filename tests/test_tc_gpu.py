@@ -278,7 +278,8 @@ def test_q_ascent_bf16_mode_segments():
 @pytest.mark.parametrize("B", [1000, 30000])
 def test_get_actions_host_matches_chunked_device_calls(B):
     """Host-resident batches: chunked H2D / sampler / D2H pipeline == per-chunk device calls with the same RNG.
-    Below 8192 rows per range the call does not chunk (B = 1000: one range), B = 30000 runs three ranges."""
+    Below 8192 rows per range the call does not chunk (B = 1000: one range); B = 30000 on 148 SMs runs the partial wave
+    (11 056 rows) first and one whole wave behind it."""
     T = 5
     gen = torch.Generator().manual_seed(21)
     p = port.init_actor_params(86)
@@ -287,14 +288,13 @@ def test_get_actions_host_matches_chunked_device_calls(B):
     torch.manual_seed(123)
     out_h = pol.get_actions_host(state_h, chunks=3)
     torch.manual_seed(123)
-    chunks = max(1, min(3, B // 8192))
-    rows = ((B + chunks - 1) // chunks + 127) // 128 * 128
+    from ddiffpg_b200.models import host_batch_ranges
+    ranges = host_batch_ranges(B, 3, torch.cuda.get_device_properties(0).multi_processor_count)
     ref = []
-    for lo in range(0, B, rows):
-        hi = min(B, lo + rows)
+    for lo, hi in ranges:
         noise = torch.randn((T, hi - lo, 8), device="cuda")
         ref.append(pol.get_actions(state_h[lo:hi].cuda(), noise=noise).cpu())
-    assert len(ref) == chunks
+    assert len(ranges) == (1 if B < 16384 else 2) and ranges[0][0] == 0 and ranges[-1][1] == B
     assert out_h.is_pinned() and torch.equal(out_h, torch.cat(ref))
     assert pol.get_actions_host(torch.zeros(0, 34).pin_memory()).shape == (0, 8)
 
