@@ -797,7 +797,7 @@ int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state
 // ---------------------------------------------------------------------------------------- self-test
 // C[128][N] = A[128][K] . B[N][K]^T with the SAME building blocks as the sampler (manual SWIZZLE_128B
 // A chunks, TMA-loaded B tiles, tcgen05.mma into TMEM, 32x32b TMEM loads).  One CTA; used by
-// tests/test_tc_blocks_gpu.py to pin descriptors and layouts independently of the fused kernel.
+// tests/test_tc_gpu.py (test_tcgen05_blocks_selftest_gemm) to pin descriptors and layouts independently of the fused kernel.
 namespace ddp {
 namespace {
 __global__ void __launch_bounds__(128, 1)
