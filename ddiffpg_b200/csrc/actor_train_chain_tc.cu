@@ -364,8 +364,10 @@ actor_train_chain_kernel(const __grid_constant__ FcMaps maps, const FcArgs a) {
                     for (int ks = 0; ks < 3; ++ks) f[nt][ks] = __ldg(bf + (nt * 3 + ks) * 32);
             };
             load_frags(0, bfr);
-            for (int c = 0; c < NC1; ++c) {
-                float acc[2][kNT][4];
+            // accumulators start from the time-table rows of the four rows a thread holds; the loads for chunk c + 1 are
+            // issued into the (dead) accumulator registers as soon as chunk c has been stored, not at the top of c + 1
+            float acc[2][kNT][4];
+            auto acc_init = [&](int c) {
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -374,6 +376,9 @@ actor_train_chain_kernel(const __grid_constant__ FcMaps maps, const FcArgs a) {
                         const float2 hi = __ldg(reinterpret_cast<const float2*>(tbr[mt][1] + c * 64 + nt * 8));
                         acc[mt][nt][0] = lo.x; acc[mt][nt][1] = lo.y; acc[mt][nt][2] = hi.x; acc[mt][nt][3] = hi.y;
                     }
+            };
+            acc_init(0);
+            for (int c = 0; c < NC1; ++c) {
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -400,6 +405,7 @@ actor_train_chain_kernel(const __grid_constant__ FcMaps maps, const FcArgs a) {
                         *reinterpret_cast<uint32_t*>(dslot + o1) = pack_bf16x2(d[nt * 4 + 2], d[nt * 4 + 3]);
                     }
                 }
+                if (c + 1 < NC1) acc_init(c + 1);
                 e.publish(false);
             }
             // ---- layer-1 / layer-2 epilogues
