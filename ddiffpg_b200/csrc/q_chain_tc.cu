@@ -150,16 +150,6 @@ struct QEpi {
         ++acc_cnt;
         tc_fence_after();
     }
-    __device__ __forceinline__ void publish_chunk(bool signal_lo) {
-        fence_proxy_async();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(qb_a_full(bars, as.idx));
-            if (signal_lo) mbar_arrive(qb_lo_free(bars));
-        }
-        as.advance(kASlots);
-    }
 };
 
 __device__ __forceinline__ void store_chunk16(uint8_t* slot, int row, int col0, const float (&x)[16]) {

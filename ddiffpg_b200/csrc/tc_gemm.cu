@@ -73,16 +73,6 @@ __device__ __forceinline__ void store_bf16x16(__nv_bfloat16* p, const float (&v)
     reinterpret_cast<uint4*>(p)[0] = a;
     reinterpret_cast<uint4*>(p)[1] = b;
 }
-__device__ __forceinline__ void load_bf16x16(const __nv_bfloat16* p, float (&v)[16]) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
-    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        v[2 * i] = __uint_as_float(w[i] << 16);
-        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-    }
-}
-
 // ------------------------------------------------------------------------------------------ row GEMM
 __global__ void __launch_bounds__(kThreads, 1)
 row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ WMaps maps_w, const RowKernelArgs k) {
