@@ -19,7 +19,6 @@
 //   layer 3 (K = h3): B = W3 resident in shared memory, D = [128 x 16]
 //   scheduler step on x_t: fp32 registers of the thread that owns the row; x_t never leaves the SM.
 // Activations only ever exist as 16 KB chunks in a 4-slot ring; weights never leave L2/SMEM.
-#include <stdlib.h>
 #include "actor_layout.cuh"
 #include "tc_common.cuh"
 
@@ -36,9 +35,10 @@ constexpr int kStageBytes = 256 * 128;      // one weight stage: up to 256 rows 
 #endif
 constexpr int kStages = DDP_TC_STAGES;       // 32 KB weight stages; stages + A slots / 2 = 6 fills shared memory
 constexpr int kASlots = 2 * (6 - kStages);   // 16 KB A chunks
-#ifndef DDP_TC_HALF_EX2
-#define DDP_TC_HALF_EX2 0   // 1: packed-fp16 ex2 in the bf16 steps (one MUFU op per two elements)
-#endif
+#ifndef DDP_TC_H2
+#define DDP_TC_H2 1   // 1: fp16 operands in every step and, after the first step, the packed-fp16 Mish in the TMEM drains;
+#endif                // 0: round-1 plan (fp16 first step, bf16 operands after it, fp32 Mish everywhere)
+constexpr bool kH2 = DDP_TC_H2 != 0;
 #ifndef DDP_TC_PAIR_PUBLISH
 #define DDP_TC_PAIR_PUBLISH 0   // 1: two chunks per proxy fence (measured slower here: it delays the layer-1 MMAs)
 #endif
@@ -78,6 +78,8 @@ struct SM {
     static constexpr uint32_t aring = wring + kStages * kStageBytes;       // kASlots x 16 KB A chunks
     static constexpr uint32_t w3 = aring + kASlots * kChunkBytes;          // W3 tiles: bf16 image, fp16 image
     static constexpr uint32_t w3_f16 = w3 + 4 * 2048;
+    static constexpr uint32_t b1h = w3;                                    // kH2: fp16 copies of b1 / b2 take the place of the
+    static constexpr uint32_t b2h = w3 + 512 * 2;                          //      bf16 W3 image (every step runs on fp16 operands)
     static constexpr uint32_t in0 = w3 + 2 * 4 * 2048;                     // layer-0 input tile [128][56] 16-bit
     static constexpr uint32_t b1 = in0 + kRows * kIn0Stride * 2;           // fp32 biases
     static constexpr uint32_t b2 = b1 + 512 * 4;
@@ -130,8 +132,22 @@ __device__ __forceinline__ void write_in0_row(const TcArgs& a, const EpiCtx& e, 
 
 // 16 accumulator columns (already in registers) of this thread's row -> +bias, Mish, 16-bit -> two
 // 16-byte pieces of the A chunk slot (columns col0 .. col0+15 of the 64-column chunk)
-template <bool F16>
-__device__ __forceinline__ void emit_half(const EpiCtx& e, uint8_t* slot, const uint32_t (&v)[16], const float* bb, int col0) {
+template <bool F16, bool H2>
+__device__ __forceinline__ void emit_half(const EpiCtx& e, uint8_t* slot, const uint32_t (&v)[16], const float* bb,
+                                          const __half* bh, int col0) {
+    if constexpr (H2) {
+        // packed-fp16 path: round the accumulator pair to fp16, add the fp16 bias pair, Mish in HFMA2 arithmetic
+        const uint4 b0 = *reinterpret_cast<const uint4*>(bh), b1 = *reinterpret_cast<const uint4*>(bh + 8);
+        const uint32_t bp[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const __half2 x = __hadd2(u32_as_h2(pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]))), u32_as_h2(bp[i]));
+            w[i] = mish_h2(h2_as_u32(x));
+        }
+        *reinterpret_cast<uint4*>(slot + sw128_offset(e.my_row, col0)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(slot + sw128_offset(e.my_row, col0 + 8)) = make_uint4(w[4], w[5], w[6], w[7]);
+    } else {
     float x[16];
 #pragma unroll
     for (int i4 = 0; i4 < 4; ++i4) {
@@ -139,7 +155,7 @@ __device__ __forceinline__ void emit_half(const EpiCtx& e, uint8_t* slot, const 
         x[i4 * 4 + 0] = __uint_as_float(v[i4 * 4 + 0]) + b.x; x[i4 * 4 + 1] = __uint_as_float(v[i4 * 4 + 1]) + b.y;
         x[i4 * 4 + 2] = __uint_as_float(v[i4 * 4 + 2]) + b.z; x[i4 * 4 + 3] = __uint_as_float(v[i4 * 4 + 3]) + b.w;
     }
-    mish_fast_n<16, !F16 && DDP_TC_HALF_EX2>(x);
+    mish_fast_n<16>(x);
 #pragma unroll
     for (int i8 = 0; i8 < 2; ++i8) {
         uint4 w;
@@ -147,28 +163,30 @@ __device__ __forceinline__ void emit_half(const EpiCtx& e, uint8_t* slot, const 
         w.z = pack2<F16>(x[i8 * 8 + 4], x[i8 * 8 + 5]); w.w = pack2<F16>(x[i8 * 8 + 6], x[i8 * 8 + 7]);
         *reinterpret_cast<uint4*>(slot + sw128_offset(e.my_row, col0 + i8 * 8)) = w;
     }
+    }
 }
 
 // Drain `nchunks` 64-column chunks of the accumulator at TMEM column 0 into the A ring.  This warp owns
 // 32 columns of each chunk, moved as 16-column TMEM loads: while one piece goes through Mish the
 // next load is in flight (two 16-register buffers).  After chunk `signal_after` the thread arrives on
 // lo_free (-1: never).
-template <bool F16>
-__device__ __forceinline__ void drain_acc(EpiCtx& e, int nchunks, const float* bias, int signal_after) {
+template <bool F16, bool H2>
+__device__ __forceinline__ void drain_acc(EpiCtx& e, int nchunks, const float* bias, const __half* biash, int signal_after) {
     const uint32_t tbase = e.tmem_base + ((uint32_t)(e.q * 32) << 16) + e.ch * kColsPerWarp;
     uint32_t va[16], vb[16];
     int pending = -1;                  // ring slot written but not yet published
     tmem_ld16(tbase, va);
     for (int c = 0; c < nchunks; ++c) {
         const float* bb = bias + c * 64 + e.ch * kColsPerWarp;
+        const __half* bh = biash + c * 64 + e.ch * kColsPerWarp;
         tmem_ld_wait();
         tmem_ld16(tbase + c * 64 + 16, vb);
         mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
         uint8_t* slot = e.smem + SM::aring + e.as.idx * kChunkBytes;
-        emit_half<F16>(e, slot, va, bb, e.ch * 32);
+        emit_half<F16, H2>(e, slot, va, bb, bh, e.ch * 32);
         tmem_ld_wait();
         if (c + 1 < nchunks) tmem_ld16(tbase + (c + 1) * 64, va);
-        emit_half<F16>(e, slot, vb, bb + 16, e.ch * 32 + 16);
+        emit_half<F16, H2>(e, slot, vb, bb + 16, bh + 16, e.ch * 32 + 16);
         // every lane publishes its own writes to the async proxy, then one lane arrives for the warp
         // (32 lanes arriving on one mbarrier word serialise in the shared-memory pipe).  Two chunks share one
         // publication: the proxy fence is the expensive part of handing a chunk over.
@@ -198,8 +216,8 @@ __device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, uint32_t (&v)[4]
     asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
 }
-template <bool F16>
-__device__ __forceinline__ void drain_acc_m64(EpiCtx& e, int nchunks, const float* bias, int lo_chunks) {
+template <bool F16, bool H2>
+__device__ __forceinline__ void drain_acc_m64(EpiCtx& e, int nchunks, const float* bias, const __half* biash, int lo_chunks) {
     const uint32_t tbase = e.tmem_base + ((uint32_t)(e.q * 32) << 16) + e.ch * kColsPerWarp;
     uint32_t va[kNT][4], vb[kNT][4];
     auto fetch = [&](int c, uint32_t (&v)[kNT][4]) {
@@ -207,21 +225,33 @@ __device__ __forceinline__ void drain_acc_m64(EpiCtx& e, int nchunks, const floa
         for (int nt = 0; nt < kNT; ++nt) tmem_ld_16x256b(tbase + c * 64 + nt * 8, v[nt]);
     };
     auto chunk = [&](int c, const uint32_t (&v)[kNT][4]) {
-        float x[kNT * 4];
+        uint32_t w[kNT][2];
+        if constexpr (H2) {
 #pragma unroll
-        for (int nt = 0; nt < kNT; ++nt) {
-            const float2 b = *reinterpret_cast<const float2*>(bias + c * 64 + e.ch * kColsPerWarp + nt * 8 + 2 * e.t4);
-            x[nt * 4 + 0] = __uint_as_float(v[nt][0]) + b.x; x[nt * 4 + 1] = __uint_as_float(v[nt][1]) + b.y;
-            x[nt * 4 + 2] = __uint_as_float(v[nt][2]) + b.x; x[nt * 4 + 3] = __uint_as_float(v[nt][3]) + b.y;
+            for (int nt = 0; nt < kNT; ++nt) {
+                const __half2 b = *reinterpret_cast<const __half2*>(biash + c * 64 + e.ch * kColsPerWarp + nt * 8 + 2 * e.t4);
+                w[nt][0] = mish_h2(h2_as_u32(__hadd2(u32_as_h2(pack_f16x2(__uint_as_float(v[nt][0]), __uint_as_float(v[nt][1]))), b)));
+                w[nt][1] = mish_h2(h2_as_u32(__hadd2(u32_as_h2(pack_f16x2(__uint_as_float(v[nt][2]), __uint_as_float(v[nt][3]))), b)));
+            }
+        } else {
+            float x[kNT * 4];
+#pragma unroll
+            for (int nt = 0; nt < kNT; ++nt) {
+                const float2 b = *reinterpret_cast<const float2*>(bias + c * 64 + e.ch * kColsPerWarp + nt * 8 + 2 * e.t4);
+                x[nt * 4 + 0] = __uint_as_float(v[nt][0]) + b.x; x[nt * 4 + 1] = __uint_as_float(v[nt][1]) + b.y;
+                x[nt * 4 + 2] = __uint_as_float(v[nt][2]) + b.x; x[nt * 4 + 3] = __uint_as_float(v[nt][3]) + b.y;
+            }
+            mish_fast_n<kNT * 4>(x);
+#pragma unroll
+            for (int nt = 0; nt < kNT; ++nt) { w[nt][0] = pack2<F16>(x[nt * 4 + 0], x[nt * 4 + 1]); w[nt][1] = pack2<F16>(x[nt * 4 + 2], x[nt * 4 + 3]); }
         }
-        mish_fast_n<kNT * 4, !F16 && DDP_TC_HALF_EX2>(x);
         mbar_wait(bar_a_empty(e.bars, e.as.idx), e.as.phase ^ 1);
         uint8_t* slot = e.smem + SM::aring + e.as.idx * kChunkBytes;
 #pragma unroll
         for (int nt = 0; nt < kNT; ++nt) {
             const int r0 = e.q * 16 + e.g, col = e.ch * kColsPerWarp + nt * 8 + 2 * e.t4;
-            *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0, col)) = pack2<F16>(x[nt * 4 + 0], x[nt * 4 + 1]);
-            *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0 + 8, col)) = pack2<F16>(x[nt * 4 + 2], x[nt * 4 + 3]);
+            *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0, col)) = w[nt][0];
+            *reinterpret_cast<uint32_t*>(slot + sw128_offset(r0 + 8, col)) = w[nt][1];
         }
         fence_proxy_async();
         tc_fence_before();
@@ -303,8 +333,9 @@ __device__ __forceinline__ void state_partial(const TcArgs& a, const EpiCtx& e) 
     }
 }
 
-// One denoising step of the epilogue warps (operand format of THIS step = F16 ? fp16 : bf16).
-template <bool F16, bool HM>
+// One denoising step of the epilogue warps (operand format of THIS step = F16 ? fp16 : bf16; H2: the TMEM drains run
+// the packed-fp16 Mish -- every step but the first, whose eps_hat error is amplified by 1/sqrt(abar_{T-1})).
+template <bool F16, bool HM, bool H2 = false>
 __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
     constexpr int MT = HM ? 1 : 2;
     const int t = a.T - 1 - j;
@@ -366,7 +397,7 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
 #ifndef DDP_EXP_NO_L0_MISH
-            mish_fast_n<kNT * 4, !F16 && DDP_TC_HALF_EX2>(reinterpret_cast<float(&)[kNT * 4]>(acc[mt]));
+            mish_fast_n<kNT * 4>(reinterpret_cast<float(&)[kNT * 4]>(acc[mt]));
 #endif
 #pragma unroll
             for (int nt = 0; nt < kNT; ++nt) {
@@ -393,18 +424,20 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
     // ---- layer-1 epilogue: acc1 (TMEM cols [0,h2)) -> +b1, Mish -> A chunks of layer 2
     const float* sb1 = reinterpret_cast<const float*>(e.smem + SM::b1);
     const float* sb2 = reinterpret_cast<const float*>(e.smem + SM::b2);
+    const __half* sb1h = reinterpret_cast<const __half*>(e.smem + SM::b1h);
+    const __half* sb2h = reinterpret_cast<const __half*>(e.smem + SM::b2h);
     mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
     tc_fence_after();
     DDP_TICK(1);       // wait for the last layer-1 MMA
-    if constexpr (HM) drain_acc_m64<F16>(e, e.NC2, sb1, e.NC3 - 1);
-    else drain_acc<F16>(e, e.NC2, sb1, e.NC3 - 1);     // lo_free: TMEM cols [0, h3) are drained
+    if constexpr (HM) drain_acc_m64<F16, H2>(e, e.NC2, sb1, sb1h, e.NC3 - 1);
+    else drain_acc<F16, H2>(e, e.NC2, sb1, sb1h, e.NC3 - 1);     // lo_free: TMEM cols [0, h3) are drained
     DDP_TICK(2);       // drain acc1
     // ---- layer-2 epilogue: acc2 (TMEM cols [0,h3)) -> +b2, Mish -> A chunks of layer 3
     mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
     tc_fence_after();
     DDP_TICK(3);       // wait for the last layer-2 MMA
-    if constexpr (HM) drain_acc_m64<F16>(e, e.NC3, sb2, -1);
-    else drain_acc<F16>(e, e.NC3, sb2, -1);
+    if constexpr (HM) drain_acc_m64<F16, H2>(e, e.NC3, sb2, sb2h, -1);
+    else drain_acc<F16, H2>(e, e.NC3, sb2, sb2h, -1);
     DDP_TICK(4);       // drain acc2
 
     // ---- head + scheduler step: eps_hat from acc3, x_t in registers (fp32)
@@ -436,8 +469,10 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
             e.xr[i] = i < a.A ? xn : 0.f;
         }
         if (t > 0) {
-            // the next step runs in bf16; after an fp16 step the state columns are re-written as bf16 too
-            write_in0_row<false>(a, e, F16 ? 8 : 0);
+            // kH2: every step runs on fp16 operands.  Round-1 plan: the next step runs in bf16; after the fp16 step the
+            // state columns are re-written as bf16 too
+            if constexpr (kH2) write_in0_row<true>(a, e, 0);
+            else write_in0_row<false>(a, e, F16 ? 8 : 0);
         } else if (e.valid) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -479,11 +514,16 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
     {
         const int n16 = NC3 * 2048 / 16;
         uint4* dst = reinterpret_cast<uint4*>(smem + SM::w3);
-        for (int i = threadIdx.x; i < n16; i += kThreads) { dst[i] = a.w3img[i]; dst[(SM::w3_f16 - SM::w3) / 16 + i] = a.w3img_h[i]; }
+        for (int i = threadIdx.x; i < n16; i += kThreads) {
+            if (!kH2) dst[i] = a.w3img[i];
+            dst[(SM::w3_f16 - SM::w3) / 16 + i] = a.w3img_h[i];
+        }
         float* sb1 = reinterpret_cast<float*>(smem + SM::b1);
         float* sb2 = reinterpret_cast<float*>(smem + SM::b2);
-        for (int i = threadIdx.x; i < a.h2; i += kThreads) sb1[i] = a.b1[i];
-        for (int i = threadIdx.x; i < a.h3; i += kThreads) sb2[i] = a.b2[i];
+        __half* sb1h = reinterpret_cast<__half*>(smem + SM::b1h);
+        __half* sb2h = reinterpret_cast<__half*>(smem + SM::b2h);
+        for (int i = threadIdx.x; i < a.h2; i += kThreads) { sb1[i] = a.b1[i]; if (kH2) sb1h[i] = __float2half_rn(a.b1[i]); }
+        for (int i = threadIdx.x; i < a.h3; i += kThreads) { sb2[i] = a.b2[i]; if (kH2) sb2h[i] = __float2half_rn(a.b2[i]); }
         fence_proxy_async();
     }
     tc_fence_before();
@@ -500,7 +540,7 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
             Ring ws;
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
                 for (int j = 0; j < a.T; ++j) {
-                    const bool f16 = a.first_f16 && j == 0;
+                    const bool f16 = kH2 || (a.first_f16 && j == 0);
                     const CUtensorMap* m1 = f16 ? &map_w1h : &map_w1;
                     const CUtensorMap* m2 = f16 ? &map_w2h : &map_w2;
                     for (int c = 0; c < NC1; ++c)
@@ -527,7 +567,7 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
             uint32_t lo_phase = 0;
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
                 for (int j = 0; j < a.T; ++j) {
-                    const bool f16 = a.first_f16 && j == 0;
+                    const bool f16 = kH2 || (a.first_f16 && j == 0);
                     constexpr int M = HM ? 64 : kRows;
                     const uint32_t idesc1 = make_idesc_16(M, a.part1, f16);
                     const uint32_t idesc2 = make_idesc_16(M, a.h3, f16);
@@ -609,12 +649,18 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
             if (e.ch == 0) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) e.xr[i] = (e.valid && i < a.A) ? a.noise[e.row * a.A + i] : 0.f;
-                if (a.first_f16) write_in0_row<true>(a, e, kK0 - 8); else write_in0_row<false>(a, e, kK0 - 8);
+                if (kH2 || a.first_f16) write_in0_row<true>(a, e, kK0 - 8); else write_in0_row<false>(a, e, kK0 - 8);
             }
             epi_bar_sync();
-            if (a.first_f16) state_partial<true, HM>(a, e); else state_partial<false, HM>(a, e);
-            for (int j = 0; j < a.T; ++j) {
-                if (a.first_f16 && j == 0) epi_step<true, HM>(a, e, j); else epi_step<false, HM>(a, e, j);
+            if constexpr (kH2) {
+                state_partial<true, HM>(a, e);
+                epi_step<true, HM, false>(a, e, 0);
+                for (int j = 1; j < a.T; ++j) epi_step<true, HM, true>(a, e, j);
+            } else {
+                if (a.first_f16) state_partial<true, HM>(a, e); else state_partial<false, HM>(a, e);
+                for (int j = 0; j < a.T; ++j) {
+                    if (a.first_f16 && j == 0) epi_step<true, HM>(a, e, j); else epi_step<false, HM>(a, e, j);
+                }
             }
         }
     }
@@ -724,10 +770,10 @@ static int tc_sm_count() {
 // 65 536-state launch, also with a programmatic dependent launch so that they fill SMs as the first kernel's CTAs retire --
 // and gains nothing (0.5954 vs 0.5953 ms): a 64-row tile-step costs 0.89 of a 128-row one, because the weight stream
 // (1.25 MB per tile-step from L2), the MMA issue time (M = 64 runs at the M = 128 rate) and the per-chunk hand-over do not
-// shrink with the rows.  DDP_TC_NO_HALF_TILES=1 switches the 64-row tiles off.
+// shrink with the rows.
 struct TilePlan { int num_full, num_half, grid_full, grid_half; };
 static TilePlan tile_plan(long B, int sms) {
-    static const bool no_half = getenv("DDP_TC_NO_HALF_TILES") && atoi(getenv("DDP_TC_NO_HALF_TILES")) != 0;
+    constexpr bool no_half = false;
     const long tiles = (B + kRows - 1) / kRows;
     TilePlan p;
     p.num_full = (int)tiles; p.num_half = 0;
@@ -757,9 +803,8 @@ int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state
     a.w3img_h = (const uint4*)(base + L.tc_w3h);
     // The first reverse step divides by sqrt(abar_{T-1}) (1e2..2e3): bf16 operand rounding of eps_hat would
     // surface as ~1e-2 action errors, so that one step uses fp16 operands (same tensor rate, 3 more mantissa
-    // bits).  DDP_TC_PURE_BF16=1 keeps every step in bf16 (for measurements).
-    static const bool pure_bf16 = getenv("DDP_TC_PURE_BF16") && atoi(getenv("DDP_TC_PURE_BF16")) != 0;
-    a.first_f16 = pure_bf16 ? 0 : 1;
+    // bits).  With DDP_TC_H2 (default) every step runs on fp16 operands and this flag is moot.
+    a.first_f16 = 1;
     a.tb0 = pk + L.tb0; a.b1 = pk + L.b1; a.b2 = pk + L.b2; a.b3 = pk + L.b3; a.cst = pk + L.cst;
     a.state = state; a.noise = noise; a.out = out; a.B = B;
     a.S = L.S; a.A = L.A; a.T = L.T; a.h1 = L.h1; a.h2 = L.h2; a.h3 = L.h3;

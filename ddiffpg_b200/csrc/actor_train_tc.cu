@@ -81,7 +81,8 @@ __global__ void train_tc_prep_kernel(const float* __restrict__ state, const floa
         v = ((c - kTCol0) >> 1) == t ? 1.f : 0.f;         // one-hot of the timestep, twice (hi / lo table columns)
     }
     xin[row * 64 + c] = __float2bfloat16(v);
-    if (!tcols && c < Tp) onehot[row * Tp + c] = __float2bfloat16(c == t ? 1.f : 0.f);
+    if (!tcols)                                           // 64 threads per row cover all Tp columns (T up to kMaxT)
+        for (int cc = c; cc < Tp; cc += 64) onehot[row * Tp + cc] = __float2bfloat16(cc == t ? 1.f : 0.f);
 }
 
 __global__ void transpose_small_kernel(const float* __restrict__ src, int rows, int cols, int ld, float* __restrict__ dst) {

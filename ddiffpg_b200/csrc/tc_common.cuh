@@ -155,10 +155,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     // saturate to the finite fp16 range: an overflow must not become inf -> NaN inside the accumulators
-    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
-    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
+    // (one F2FP.SATFINITE.F16.F32.PACK_AB; .x = lo in the low 16 bits)
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
 }
 template <bool F16> __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
@@ -174,6 +174,13 @@ template <bool F16> __device__ __forceinline__ uint16_t cvt16(float v) {
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t smem_addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr));
+}
+
+// four 8x8 b16 matrices from the mma.sync C-fragment layout (register j = this thread's pair of matrix j: row lane / 4,
+// columns 2 (lane % 4), +1) to shared memory; lane l supplies the 16-byte row address of row l % 8 of matrix l / 8
+__device__ __forceinline__ void stmatrix_x4(uint32_t smem_addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};"
+                 ::"r"(smem_addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
 
 // legacy warp-level tensor-core MMA for the K=48 first layer (register accumulators, no TMEM needed)
@@ -269,6 +276,40 @@ __device__ __forceinline__ void mish_fast_n(float (&x)[N]) {
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = fmaf(x[i], s[i], x[i]);
+}
+
+// Mish of two values in packed fp16 arithmetic: x (f16x2) in, mish(x) (f16x2) out -- the operand format of the next
+// layer's MMA, so no conversion follows.  13 instructions per PAIR (the fp32 sequence above costs 19 per pair) and half
+// the MUFU work (ex2.approx.f16x2 is two MUFU.EX2.F16; there is no reciprocal on the XU pipe at all):
+//   t = min(x log2e - 1/2, 7)                     HFMA2, HMNMX2      (cap: p below stays < 2^15)
+//   v = 2^t + 1/sqrt2 = (e^x + 1)/sqrt2           2 MUFU, PRMT, HADD2
+//   p = v^2 + 1/2 = ((e^x + 1)^2 + 1)/2 >= 1      HFMA2
+//   r ~ 1/p: r0 = bits(0x77b7) - bits(p) (7 % seed), e = 1 - p r0, r = r0 + r0 (e + e^2)   IADD, 3 HFMA2 (7.4e-4 rel.)
+//   mish = x - x r                                HFMA2
+// Relative error ~2^-10 for x >= 0, absolute ~|x| 2^-11 for x << 0 (1 - r cancels there; mish itself -> 0): the same
+// size as rounding the activation to a 16-bit operand.  Used by the denoising steps after the first one.
+__device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t mish_h2(uint32_t xb) {
+    const __half2 x = u32_as_h2(xb);
+    const __half2 kL2E = __float2half2_rn(1.4426950408889634f), kMH = __float2half2_rn(-0.5f), kCap = __float2half2_rn(7.0f);
+    const __half2 kRh = __float2half2_rn(0.70710678118654752f), kHalf = __float2half2_rn(0.5f), kOne = __float2half2_rn(1.f);
+    const __half2 t = __hmin2(__hfma2(x, kL2E, kMH), kCap);
+    uint32_t ub;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(ub) : "r"(h2_as_u32(t)));
+    const __half2 v = __hadd2(u32_as_h2(ub), kRh);
+    const __half2 p = __hfma2(v, v, kHalf);
+    const __half2 r0 = u32_as_h2(0x77b777b7u - h2_as_u32(p));
+    const __half2 e = __hfma2(__hneg2(p), r0, kOne);
+    const __half2 f = __hfma2(e, e, e);
+    const __half2 r = __hfma2(r0, f, r0);
+    return h2_as_u32(__hfma2(__hneg2(x), r, x));
+}
+
+// legacy warp-level MMA with fp16 accumulators: D (2 x f16x2) = A . B + C; c[0] = (row g, cols 2t, 2t+1), c[1] = row g + 8
+__device__ __forceinline__ void mma_m16n8k16_f16acc(uint32_t (&c)[2], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f16.f16.f16.f16 {%0, %1}, {%2, %3, %4, %5}, {%6, %7}, {%0, %1};"
+        : "+r"(c[0]), "+r"(c[1]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 // ------------------------------------------------------------------------------------ host: tensor maps

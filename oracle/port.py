@@ -243,7 +243,7 @@ def critic_loss_and_grads(p, target_q, obs, action):
 
 
 def q_action_ascent(p, obs, action, iters=20, lr=0.03, eps=1e-5, max_norm=1.0,
-                    betas=(0.9, 0.999), v_min=0.0, v_max=5.0, return_trace=False):
+                    betas=(0.9, 0.999), v_min=0.0, v_max=5.0, return_trace=False, return_grads=False):
     """AgentDDiffPG.update_target_action, ddiffpg.py:358-373 (+ optimizer_update, ac_base.py:83-92).
 
     Uses the real torch.optim.Adam and clip_grad_norm_ like the reference.  Returns
@@ -251,13 +251,15 @@ def q_action_ascent(p, obs, action, iters=20, lr=0.03, eps=1e-5, max_norm=1.0,
     and the per-iteration, per-row gap Q1-Q2 [iters, B].  The ascent climbs min(Q1, Q2), so rows drift
     onto the ridge Q1 == Q2 where the arg-min (hence the gradient) flips on the last float bit; the
     parity tests use the gap to treat such rows with the bound the non-smooth objective allows.
+    ``return_grads`` appends the per-iteration pre-clip gradients [iters, B, A] (what Adam consumes before
+    the clip coefficient), so a test can tell elements with a well-defined step sign from near-zero ones.
     """
     pp = {k: v.detach() for k, v in p.items()}
     action = action.detach().clone()
     lim = 1 - 1e-5
     action.clamp_(-lim, lim)
     opt = torch.optim.Adam([action], lr=lr, eps=eps, betas=betas)
-    norms, gaps = [], []
+    norms, gaps, grads = [], [], []
     for _ in range(iters):
         action.requires_grad_(True)
         if return_trace:
@@ -268,13 +270,19 @@ def q_action_ascent(p, obs, action, iters=20, lr=0.03, eps=1e-5, max_norm=1.0,
         loss = -q_min(pp, obs, action, v_min, v_max).mean()
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        if return_grads:
+            grads.append(action.grad.detach().clone())
         norms.append(torch.nn.utils.clip_grad_norm_([action], max_norm=max_norm).detach().clone())
         opt.step()
         action.requires_grad_(False)
         action.clamp_(-lim, lim)
     out = action.detach().clone()
     res = (torch.abs(out).mean().item(), out)
-    return res + (torch.stack(norms), torch.stack(gaps)) if return_trace else res
+    if return_trace:
+        res = res + (torch.stack(norms), torch.stack(gaps))
+    if return_grads:
+        res = res + (torch.stack(grads),)
+    return res
 
 
 # ------------------------------------------------------------------------------------------ N4: RND / NovelD

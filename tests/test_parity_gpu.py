@@ -204,7 +204,7 @@ def test_train_loss_and_grads_match_reference_fixture(name):
         assert abs(gk.norm().item() - float(g[f"gnorm_{i}"])) <= 1e-4 * float(g[f"gnorm_{i}"]) + 1e-9
 
 
-@pytest.mark.parametrize("B,T", [(1, 5), (37, 5), (700, 5), (2000, 20)])
+@pytest.mark.parametrize("B,T", [(1, 5), (37, 5), (700, 5), (2000, 20), (1500, 100)])
 def test_train_grads_vs_oracle(B, T):
     gen = torch.Generator().manual_seed(300 + B)
     p = port.init_actor_params(71)

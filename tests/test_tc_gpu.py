@@ -75,6 +75,27 @@ def test_sampler_bf16_width_sweep(h):
     assert (out - ref).abs().max().item() <= BF16_ATOL
 
 
+@pytest.mark.parametrize("h", [1024, 512, 256])
+@pytest.mark.parametrize("T", [5, 20, 100])
+def test_sampler_bf16_config_sweep_full_batch_slice(T, h):
+    """BASELINE configs[4]: every (T, width) of the sweep on the tensor path, as a 4,096-row slice of a 65,536-row
+    launch against the fp32 oracle at the bf16 bound.  T = 100 is the hardest case: the first reverse step divides by
+    sqrt(abar_99) (x2029).  Measured worst case over the nine configs: 1.04e-3 (tools/parity_probe.py)."""
+    B, n = 65536, 4096
+    gen = torch.Generator().manual_seed(1000 + h + T)
+    p = port.init_actor_params(83, h=h)
+    state = torch.randn(B, 34, generator=gen)
+    noise = torch.randn(T, B, 8, generator=gen)
+    pol = make_policy(p, T, precision="bf16", hidden=(h, h // 2, h // 4))
+    out = pol.get_actions(_dev(state), noise=_dev(noise))
+    assert torch.isfinite(out).all() and out.abs().max().item() <= 1.0
+    sl = slice(30000, 30000 + n)
+    ref = port.actor_sample(p, state[sl], noise[:, sl], T)
+    err = (out[sl].cpu() - ref).abs()
+    assert err.max().item() <= BF16_ATOL, f"T={T} h={h}: max abs err {err.max().item():.3e}"
+    assert err.mean().item() <= 5e-4, f"T={T} h={h}: mean abs err {err.mean().item():.3e}"
+
+
 def test_sampler_bf16_large_batch_properties():
     """BASELINE size (65,536 rows): size-independent checks -- range, determinism, row independence, and a
     4,096-row slice against the oracle."""
@@ -119,10 +140,14 @@ def test_sampler_bf16_requires_its_workspace():
 
 
 # ------------------------------------------------------------------------------------------ H3 tensor path
-@pytest.mark.parametrize("B,T", [(64, 5), (700, 5), (4096, 5), (1000, 20)])
+BF16_GRAD_REL = 1e-2        # relative L2, flat gradient AND every one of the 12 tensors (measured <= 5.5e-3)
+
+
+@pytest.mark.parametrize("B,T", [(64, 5), (700, 5), (4096, 5), (1000, 20), (4096, 100)])
 def test_train_bf16_grads_vs_oracle(B, T):
     """tcgen05 GEMM path of the training step: loss and all 12 gradients against the fp32 oracle at the bf16
-    bound (relative L2 error of the flat gradient <= 2e-2, of every weight matrix <= 3e-2)."""
+    bound: loss 1e-4 relative, relative L2 error of the flat gradient and of every tensor <= 1e-2.  T = 100 exercises
+    the separate one-hot operand of the time branch beyond one 64-column box."""
     gen = torch.Generator().manual_seed(900 + B)
     p = port.init_actor_params(84)
     state = torch.randn(B, 34, generator=gen)
@@ -134,15 +159,15 @@ def test_train_bf16_grads_vs_oracle(B, T):
     pol.train_precision = "bf16"
     loss = pol.get_loss(_dev(state), _dev(action), noise=_dev(noise), timesteps=_dev(ts))
     loss.backward()
-    assert abs(loss.item() - l_ref.item()) <= 2e-3 * l_ref.item()
+    assert abs(loss.item() - l_ref.item()) <= 1e-4 * l_ref.item()
     got = torch.cat([q.grad.reshape(-1) for _, q in pol.named_parameters()]).cpu()
     ref = torch.cat([g_ref[k].reshape(-1) for k in port.ACTOR_KEYS])
     rel = ((got - ref).norm() / ref.norm()).item()
-    assert rel <= 2e-2, f"flat gradient relative L2 error {rel:.3e}"
+    assert rel <= BF16_GRAD_REL, f"flat gradient relative L2 error {rel:.3e}"
     for k, q in pol.named_parameters():
         r = g_ref[k]
         e = ((q.grad.cpu() - r).norm() / r.norm().clamp_min(1e-12)).item()
-        assert e <= 3e-2, f"{k}: relative L2 error {e:.3e}"
+        assert e <= BF16_GRAD_REL, f"{k}: relative L2 error {e:.3e}"
 
 
 @pytest.mark.parametrize("B,T", [(700, 5), (1000, 20)])
@@ -164,10 +189,10 @@ def test_train_bf16_layerwise_forward_matches_fused_forward(B, T, monkeypatch):
         pol.train_precision = "bf16"
         loss = pol.get_loss(_dev(state), _dev(action), noise=_dev(noise), timesteps=_dev(ts))
         loss.backward()
-        assert abs(loss.item() - l_ref.item()) <= 2e-3 * l_ref.item(), f"no_chain={no_chain}"
+        assert abs(loss.item() - l_ref.item()) <= 1e-4 * l_ref.item(), f"no_chain={no_chain}"
         got = torch.cat([q.grad.reshape(-1) for _, q in pol.named_parameters()]).cpu()
         rel = ((got - ref).norm() / ref.norm()).item()
-        assert rel <= 2e-2, f"no_chain={no_chain}: flat gradient relative L2 error {rel:.3e}"
+        assert rel <= BF16_GRAD_REL, f"no_chain={no_chain}: flat gradient relative L2 error {rel:.3e}"
         flats.append(got)
     # the two forwards round differently (fp16-free bf16 chain vs GEMM epilogues) but agree far inside the oracle bound
     assert ((flats[0] - flats[1]).norm() / ref.norm()).item() <= 1e-2
@@ -187,8 +212,8 @@ def test_fused_trainer_bf16_tracks_fp32():
     for _ in range(3):
         loss, gnorm = tr.step(_dev(args[0]), _dev(args[1]), noise=_dev(args[2]), timesteps=_dev(args[3]))
         l_ref, n_ref, cur, st = port.adamw_train_step(cur, *args, T, opt_state=st)
-        assert abs(loss.item() - l_ref.item()) <= 3e-3 * l_ref.item()
-        assert abs(gnorm.item() / n_ref.item() - 1) <= 2e-2
+        assert abs(loss.item() - l_ref.item()) <= 1e-3 * l_ref.item()
+        assert abs(gnorm.item() / n_ref.item() - 1) <= 1e-2
 
 
 # ------------------------------------------------------------------------------------------ H2 tensor path
@@ -196,12 +221,26 @@ def _ridge_free(gaps, thr):
     return gaps.abs().min(0).values > thr
 
 
-def _check_ascent(p, obs, got, a_ref, ok, what=""):
-    """bf16 gradients through Adam: Adam normalises every element's step to ~lr, so an element whose true
-    gradient is below the bf16 error of the gradient (a few % of the typical magnitude) can take steps of the
-    wrong sign -- elementwise 1e-2 cannot hold for those.  The bound is therefore statistical and functional:
-    mean |error| <= 5e-3, 97 % of the elements within 2e-2, and the objective reached (mean min(Q1,Q2) of the
-    final actions, evaluated by the fp32 oracle) within 2e-3 of what the reference reaches."""
+G_REL_THR = 0.25        # an element is "well-conditioned" if its reference |g| never drops below this x rms(g)
+MIN_KEPT = 0.30         # ... and at least this fraction of all elements must be (measured 0.39 - 0.67)
+
+
+def _check_ascent(p, obs, got, a_ref, ok, what="", grads=None):
+    """bf16 gradients through Adam.  The north-star bound, stated the way it can hold: **elementwise
+    |a - a_ref| <= 1e-2 on every element whose reference gradient stays above G_REL_THR x rms(g) in all 20
+    iterations, on rows clear of the Q1 == Q2 ridge** (`ok`); the excluded fraction is asserted (MIN_KEPT).
+    Adam normalises every element's step to ~lr (eps 1e-5 only matters once |g| ~ 1e-5), so an element whose true
+    gradient is below the bf16 error of the gradient can legitimately step with the other sign -- for those, and
+    for the batch as a whole, the bound is statistical and functional: mean |error| <= 5e-3, 97 % of the elements
+    within 2e-2, and the objective reached (mean min(Q1,Q2) of the final actions, evaluated by the fp32 oracle)
+    within 2e-3 of what the reference reaches."""
+    if grads is not None:
+        rms = grads.pow(2).mean().sqrt()
+        well = ok[:, None] & (grads.abs().min(0).values > G_REL_THR * rms)
+        kept = well.float().mean().item()
+        assert kept >= MIN_KEPT, (what, f"only {kept:.1%} of the elements are well-conditioned")
+        worst = (got - a_ref)[well].abs().max().item()
+        assert worst <= BF16_ATOL, (what, f"elementwise bound: {worst:.3e} on {kept:.1%} of the elements")
     err = (got - a_ref)[ok].abs()
     assert err.mean().item() <= 5e-3, (what, err.mean().item())
     assert (err <= 2e-2).float().mean().item() >= 0.97, (what, (err <= 2e-2).float().mean().item())
@@ -236,7 +275,7 @@ def test_q_bf16_forward_and_gradient_vs_oracle(B):
     assert ok.float().mean().item() > 0.5 and rel <= 3e-2, f"relative L2 error of dQ/da {rel:.3e}"
 
 
-@pytest.mark.parametrize("B", [64, 2000])
+@pytest.mark.parametrize("B", [64, 2000, 16384])
 def test_q_ascent_bf16_vs_oracle(B):
     """20 Adam iterations on the tensor path against the fp32 oracle, on rows that stay clear of the Q1 == Q2
     ridge by more than the bf16 error of Q (elsewhere the arg-min may legitimately differ)."""
@@ -245,12 +284,13 @@ def test_q_ascent_bf16_vs_oracle(B):
     gen = torch.Generator().manual_seed(800 + B)
     p = port.init_critic_params(92, scale=2.0)
     obs, act = torch.randn(B, 29, generator=gen), torch.rand(B, 8, generator=gen) * 2 - 1
-    m_ref, a_ref, _, gaps = port.q_action_ascent(p, obs, act.clone(), iters=20, return_trace=True)
+    m_ref, a_ref, _, gaps, grads = port.q_action_ascent(p, obs, act.clone(), iters=20, return_trace=True,
+                                                        return_grads=True)
     work = _dev(act).clone()
     mean_abs = q_action_ascent_segments([make_critic(p)], _dev(obs), work, [0, B], iters=20, precision="bf16")
-    ok = _ridge_free(gaps, 3e-2)
+    ok = _ridge_free(gaps, 1e-2)
     assert ok.float().mean().item() > 0.3
-    _check_ascent(p, obs, work.cpu(), a_ref, ok, f"B={B}")
+    _check_ascent(p, obs, work.cpu(), a_ref, ok, f"B={B}", grads=grads)
     assert abs(mean_abs[0].item() - m_ref) <= 2e-2
 
 

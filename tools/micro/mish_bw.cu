@@ -4,7 +4,11 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include "../../ddiffpg_b200/csrc/tc_common.cuh"
+using ddp::tc::mish_h2;
+using ddp::tc::pack_f16x2;
 
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcpa(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -56,13 +60,23 @@ __global__ void __launch_bounds__(512, 1) k(const float* in, uint32_t* out, int 
 #pragma unroll
             for (int i = 0; i < 16; ++i) y[i] = fmaf(y[i], s[i], y[i]);
         }
+        if (V == 6) {                                 // packed-fp16 Mish from fp32 accumulators (drain path): F2FP + HADD2 bias + mish_h2
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                const __half2 xb = __hadd2(ddp::tc::u32_as_h2(pack_f16x2(y[i], y[i + 1])), ddp::tc::u32_as_h2(0x2e662e66u));
+                acc ^= mish_h2(ddp::tc::h2_as_u32(xb));
+            }
+        } else if (V == 7) {                          // packed-fp16 Mish on packed inputs (layer-0 path, fp16 accumulators)
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) acc ^= mish_h2(__float_as_uint(y[i]) ^ (__float_as_uint(y[i + 1]) >> 16));
+        }
         if (V == 0 || V == 1 || V == 4 || V == 5) {
 #pragma unroll
             for (int i = 0; i < 16; i += 2) acc ^= packbf(y[i], y[i + 1]);
         } else if (V == 2) {
 #pragma unroll
             for (int i = 0; i < 16; i += 2) acc ^= packint(y[i], y[i + 1]);
-        } else {
+        } else if (V == 3) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc ^= __float_as_uint(y[i]);
         }
@@ -91,6 +105,8 @@ int main() {
     cudaMemset(in, 0, 512 * 16 * 4);
     for (int threads : {256, 512}) {
         run<0>("mish + F2FP pack", in, out, clk, threads);
+        run<6>("packed-fp16 mish (F2FP in, bias)", in, out, clk, threads);
+        run<7>("packed-fp16 mish (packed in)", in, out, clk, threads);
         run<5>("mish, rcp per element + F2FP pack", in, out, clk, threads);
         run<2>("mish + integer round/pack", in, out, clk, threads);
         run<3>("mish, no pack", in, out, clk, threads);

@@ -10,7 +10,7 @@ B, T = int(sys.argv[1]) if len(sys.argv) > 1 else 65536, 5
 pol = make_policy(port.init_actor_params(1), T, precision="bf16")
 s = torch.randn(B, 34, device='cuda'); n = torch.randn(T, B, 8, device='cuda')
 for _ in range(3): pol.get_actions(s, noise=n)
-buf = torch.zeros(8, dtype=torch.int64, device='cuda')
+buf = torch.zeros(16, dtype=torch.int64, device='cuda')
 L.ddp_debug_tc_timing(buf.data_ptr())
 pol.get_actions(s, noise=n); torch.cuda.synchronize()
 L.ddp_debug_tc_timing(None)
