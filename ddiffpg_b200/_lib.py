@@ -47,6 +47,9 @@ PROTOTYPES = {
     "ddp_actor_loss_fwd_bwd": (c_int, [POINTER(ActorShape), c_void_p, POINTER(c_void_p), c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_long, c_int, c_void_p,
                                        c_size_t, c_void_p]),
+    "ddp_actor_loss_fwd_bwd_ev": (c_int, [POINTER(ActorShape), c_void_p, POINTER(c_void_p), c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_long, c_int, c_void_p,
+                                          c_size_t, c_void_p, POINTER(c_void_p)]),
     "ddp_clip_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_float, c_float,
                                     c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "ddp_clip_adamw_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_float, c_float,

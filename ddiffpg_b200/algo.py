@@ -181,19 +181,26 @@ def soft_update(target_net, current_net, tau):
 
 
 class FusedActorTrainer:
-    """Whole ``update_actor`` on the device: loss + 12 gradients (one C-ABI call), optional data-parallel
-    gradient all-reduce, then clip + AdamW on a flat parameter vector (``ddp_clip_adamw_step``).
+    """Whole ``update_actor`` on the device: loss + 12 gradients (one C-ABI call), the data-parallel gradient
+    all-reduce, then clip + AdamW on a flat parameter vector (``ddp_clip_adamw_step``).
 
     The module's parameters are re-pointed at slices of one flat fp32 buffer (state_dict keys, shapes and
-    values unchanged), so the flat gradient of ``ddp_actor_loss_fwd_bwd`` lines up with it and a single
-    NCCL all-reduce covers the whole model.  Hyper-parameters default to the reference's
-    ``torch.optim.AdamW(actor.parameters(), actor_lr)`` (ac_base.py:52) and ``max_grad_norm`` 1.0."""
+    values unchanged), so the flat gradient of ``ddp_actor_loss_fwd_bwd`` lines up with it.  Hyper-parameters default
+    to the reference's ``torch.optim.AdamW(actor.parameters(), actor_lr)`` (ac_base.py:52) and ``max_grad_norm`` 1.0.
+
+    Data parallel (``torch.distributed`` initialised, or ``process_group`` given; ``process_group=False`` switches
+    the collective off): the backward hands the gradient over in four groups, last layer first
+    (``ddp_actor_loss_fwd_bwd_ev``); each group is summed over the ranks on a side stream as soon as it is final, so
+    only the reduction of the last group (time_mlp + net.mlp.0) is not hidden behind the rest of the backward.  The
+    loss rides in the same buffer (one float behind the gradient): there is no separate collective for it."""
+
+    GROUPS = 4
 
     def __init__(self, actor, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0,
                  process_group=None, precision=None, graph=False):
         self.actor = actor
-        # graph=True: the whole step (re-pack, forward/backward, all-reduce, clip + AdamW: ~50 launches) is captured
-        # once per batch shape into a CUDA graph and replayed; the Adam step count lives on the device
+        # graph=True: the whole step (re-pack, forward/backward, all-reduce, clip + AdamW) is captured once per batch
+        # shape into a CUDA graph and replayed; the Adam step count lives on the device
         self.use_graph = graph
         self._graphs = {}
         self.precision = precision          # None: actor.train_precision ("fp32" | "bf16")
@@ -204,18 +211,43 @@ class FusedActorTrainer:
         dev = params[0].device
         n = sum(p.numel() for p in params)
         self.flat = torch.empty(n, device=dev, dtype=torch.float32)
-        off = 0
+        off, self._offsets = 0, [0]
         for p in params:
             self.flat[off:off + p.numel()].copy_(p.detach().reshape(-1))
             p.data = self.flat[off:off + p.numel()].view(p.shape)
             off += p.numel()
+            self._offsets.append(off)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = 0
         self._norm = torch.zeros(1, device=dev)
-        self._scratch = torch.zeros(4, device=dev)
+        self._scratch = torch.zeros(640, device=dev)          # DDP_ADAMW_SCRATCH_FLOATS
         self._step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._side = None                   # stream of the overlapped all-reduce, events of the gradient groups
+        self._events = None
         actor.mark_dirty()
+
+    # ------------------------------------------------------------------ plumbing
+    def world_size(self):
+        if self.group is False:
+            return 1
+        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return torch.distributed.get_world_size(self.group)
+        return 1
+
+    def launches_per_step(self):
+        """Own kernels of one step on the tensor path: re-pack 12, prep 1, fused forward 1, backward row GEMMs 3,
+        dW GEMMs 4, time branch 6 (+ 2 fp32 transposes), norm / clip / AdamW 3."""
+        return 32
+
+    def close(self):
+        """Release the captured CUDA graphs (and with them the collectives they hold).  Call before
+        ``torch.distributed.destroy_process_group()``: tearing NCCL down under a live graph that captured an
+        all-reduce blocks."""
+        dev = self.flat.device
+        torch.cuda.synchronize(dev)
+        self._graphs.clear()
+        torch.cuda.synchronize(dev)
 
     def _check_flat(self):
         off = 0
@@ -225,6 +257,12 @@ class FusedActorTrainer:
                                    "(e.g. .to() or load into new storage); build a new trainer")
             off += p.numel()
 
+    def _group_slices(self, n):
+        """Element ranges of the four gradient groups in the flat [n + 1] buffer (state_dict order: time_mlp.1/.3,
+        mlp.0, mlp.2, mlp.4, mlp.6, then the loss): group 0 = mlp.6 + loss, 1 = mlp.4, 2 = mlp.2, 3 = the rest."""
+        o = self._offsets
+        return [(o[10], n + 1), (o[8], o[10]), (o[6], o[8]), (0, o[6])]
+
     def step(self, state, action, noise=None, timesteps=None, global_batch=None):
         """One training step; returns (loss, pre-clip grad norm) as 0-dim device tensors (no host sync).
         ``global_batch``: rows over all data-parallel ranks (defaults to local rows x world size)."""
@@ -232,37 +270,82 @@ class FusedActorTrainer:
         actor = self.actor
         dev = self.flat.device
         B = action.shape[0]
-        world = 1
-        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            world = torch.distributed.get_world_size(self.group)
         if global_batch is None:
-            global_batch = B * world
+            global_batch = B * self.world_size()
         if noise is None:
             noise = torch.randn(action.shape, device=dev, dtype=torch.float32)
         if timesteps is None:
             timesteps = torch.randint(0, actor.diffusion_iter, (B,), device=dev)
         if self.use_graph:
             return self._step_graph(state, action, noise, timesteps, global_batch)
-        loss, norm = self._step_body(state, action, noise, timesteps, global_batch)
-        return loss, norm.clone()
+        bufs = self._buffers(B, None)
+        loss, norm = self._step_body(state, action, noise, timesteps, global_batch, bufs)
+        return loss.clone(), norm.clone()
 
-    def _step_body(self, state, action, noise, timesteps, global_batch):
+    def _buffers(self, B, owner):
+        """Gradient (+ loss) buffer and kernel workspace of a step.  A captured graph keeps raw pointers into them, so
+        every graph owns its own pair (``owner`` = its entry); eager steps share one that only ever grows."""
         actor = self.actor
         dev = self.flat.device
-        loss, grads = actor._loss_and_grads(state, action, noise, timesteps,
-                                            inv_count=1.0 / (global_batch * actor.action_dim),
-                                            precision=self.precision)
-        # the one exchange step of the path: sum the flat gradient (and the loss) over NVLink
-        ddist.allreduce_sum_(grads, loss, group=self.group)
-        self.step_count += 1
+        prec = _lib.PRECISIONS[self.precision or actor.train_precision]
+        n = self.flat.numel()
         with torch.cuda.device(dev):
+            ws_bytes = lib().ddp_actor_train_workspace_bytes(actor._shape(), B, prec)
+        holder = owner if owner is not None else self.__dict__.setdefault("_eager", {})
+        if holder.get("ws") is None or holder["ws"].numel() < ws_bytes:
+            holder["ws"] = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=dev)
+        if holder.get("gbuf") is None:
+            holder["gbuf"] = torch.zeros(n + 4, device=dev, dtype=torch.float32)      # [gradient | loss | pad]
+        return holder
+
+    def _step_body(self, state, action, noise, timesteps, global_batch, bufs):
+        actor = self.actor
+        dev = self.flat.device
+        n = self.flat.numel()
+        precision = self.precision or actor.train_precision
+        packed, shape, prec = actor._packed(precision, need=2)
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        state, action, noise = f32(state), f32(action), f32(noise)
+        timesteps = timesteps.detach().to(device=dev, dtype=torch.int64).contiguous()
+        B = action.shape[0]
+        gbuf, ws = bufs["gbuf"], bufs["ws"]
+        grads, loss = gbuf[:n], gbuf[n:n + 1]
+        loss.zero_()
+        world = self.world_size()
+        params = actor._params()
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream()
+            ev_arr = None
+            if world > 1:
+                if self._side is None:
+                    self._side = torch.cuda.Stream()
+                    self._events = [torch.cuda.Event() for _ in range(self.GROUPS)]
+                    for ev in self._events:          # torch creates the CUDA event lazily: force the handles into being
+                        ev.record(main)
+                ev_arr = (_lib.c_void_p * self.GROUPS)(*[ev.cuda_event for ev in self._events])
+            check(lib().ddp_actor_loss_fwd_bwd_ev(shape, ptr(packed), _lib.ptr_array([p.detach() for p in params]),
+                                                  ptr(state), ptr(action), ptr(noise), ptr(timesteps),
+                                                  1.0 / (global_batch * actor.action_dim), ptr(loss), ptr(grads), B,
+                                                  prec, ptr(ws), ws.numel(), stream_ptr(), ev_arr),
+                  "ddp_actor_loss_fwd_bwd_ev")
+            if world > 1:
+                # the one exchange step of the path: each gradient group is summed over NVLink on the side stream as soon
+                # as the backward has finished it; the main stream joins before the clip
+                side = self._side
+                group = None if self.group in (None, False) else self.group
+                with torch.cuda.stream(side):
+                    for (lo, hi), ev in zip(self._group_slices(n), self._events):
+                        side.wait_event(ev)
+                        torch.distributed.all_reduce(gbuf[lo:hi], group=group)
+                main.wait_stream(side)
+            self.step_count += 1
             check(lib().ddp_clip_adamw_step_dev(ptr(self.flat), ptr(grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                                                self.flat.numel(), ptr(self._step_dev), self.lr, self.betas[0],
+                                                n, ptr(self._step_dev), self.lr, self.betas[0],
                                                 self.betas[1], self.eps, self.weight_decay, self.max_grad_norm,
                                                 ptr(self._norm), ptr(self._scratch), stream_ptr()),
                   "ddp_clip_adamw_step_dev")
         actor.mark_dirty()
-        return loss, self._norm[0]
+        return loss[0], self._norm[0]
 
     def _step_graph(self, state, action, noise, timesteps, global_batch):
         dev = self.flat.device
@@ -275,7 +358,8 @@ class FusedActorTrainer:
             ent = {"state": f32(state).clone(), "action": f32(action).clone(), "noise": f32(noise).clone(),
                    "ts": timesteps.detach().to(device=dev, dtype=torch.int64).clone(), "graph": None}
             self._graphs[key] = ent
-            loss, norm = self._step_body(ent["state"], ent["action"], ent["noise"], ent["ts"], global_batch)
+            self._buffers(action.shape[0], ent)
+            loss, norm = self._step_body(ent["state"], ent["action"], ent["noise"], ent["ts"], global_batch, ent)
             return loss.clone(), norm.clone()
         ent["state"].copy_(state); ent["action"].copy_(action); ent["noise"].copy_(noise); ent["ts"].copy_(timesteps)
         if ent["graph"] is None:
@@ -283,7 +367,8 @@ class FusedActorTrainer:
             g = torch.cuda.CUDAGraph()
             count = self.step_count
             with torch.cuda.graph(g):
-                ent["loss"], ent["norm"] = self._step_body(ent["state"], ent["action"], ent["noise"], ent["ts"], global_batch)
+                ent["loss"], ent["norm"] = self._step_body(ent["state"], ent["action"], ent["noise"], ent["ts"],
+                                                           global_batch, ent)
             self.step_count = count                  # capturing records, it does not execute
             ent["graph"] = g
         ent["graph"].replay()

@@ -29,7 +29,7 @@ int pack_actor_train_tc(const ActorLayout& L, const float* const p[12], void* pa
 size_t actor_train_tc_workspace(const ActorLayout& L, long B);
 int actor_train_tc(const ActorLayout& L, const void* packed, const float* const p[12], const float* state,
                    const float* action, const float* noise, const int64_t* t, float inv_count, float* loss_out,
-                   float* grads, long B, void* ws, size_t ws_bytes, cudaStream_t st);
+                   float* grads, long B, void* ws, size_t ws_bytes, cudaStream_t st, const cudaEvent_t* group_ev);
 int clip_adamw(float* p, float* g, float* m, float* v, size_t n, int step, float lr, float b1, float b2, float eps,
                float wd, float max_norm, float* norm_out, float* scratch, cudaStream_t st);
 int clip_adamw_dev(float* p, float* g, float* m, float* v, size_t n, int* step_dev, float lr, float b1, float b2,
@@ -148,10 +148,10 @@ size_t ddp_actor_train_workspace_bytes(const ddp_actor_shape* s, long B, int pre
     return actor_train_workspace(make_actor_layout(*s, precision), B);
 }
 
-int ddp_actor_loss_fwd_bwd(const ddp_actor_shape* s, const void* packed, const float* const params[12],
-                           const float* state, const float* action, const float* noise, const int64_t* t,
-                           float inv_count, float* loss_out, float* grads_flat, long B, int precision, void* ws,
-                           size_t ws_bytes, void* stream) {
+int ddp_actor_loss_fwd_bwd_ev(const ddp_actor_shape* s, const void* packed, const float* const params[12],
+                              const float* state, const float* action, const float* noise, const int64_t* t,
+                              float inv_count, float* loss_out, float* grads_flat, long B, int precision, void* ws,
+                              size_t ws_bytes, void* stream, void* const* group_events) {
     int rc = check_actor_shape(s);
     if (rc != DDP_OK) return rc;
     if (B <= 0) DDP_FAIL(DDP_ERR_SHAPE, "ddp_actor_loss_fwd_bwd: batch must be positive");
@@ -160,12 +160,27 @@ int ddp_actor_loss_fwd_bwd(const ddp_actor_shape* s, const void* packed, const f
     if (precision != DDP_FP32 && precision != DDP_BF16) DDP_FAIL(DDP_ERR_ARG, "unknown precision %d", precision);
     ActorLayout L = make_actor_layout(*s, precision);
     if (!aligned16(ws) || !aligned16(grads_flat)) DDP_FAIL(DDP_ERR_ARG, "workspace/grads must be 16-byte aligned");
+    cudaEvent_t ev[DDP_ACTOR_GRAD_GROUPS] = {};
+    if (group_events)
+        for (int g = 0; g < DDP_ACTOR_GRAD_GROUPS; ++g) ev[g] = (cudaEvent_t)group_events[g];
     if (precision == DDP_BF16)
         return actor_train_tc(L, packed, params, state, action, noise, t, inv_count, loss_out, grads_flat, B, ws,
-                              ws_bytes, (cudaStream_t)stream);
+                              ws_bytes, (cudaStream_t)stream, ev);
     if (ws_bytes < actor_train_workspace(L, B)) DDP_FAIL(DDP_ERR_ARG, "ddp_actor_loss_fwd_bwd: workspace too small");
-    return actor_train_fma(L, (const float*)packed, params, state, action, noise, t, inv_count, loss_out, grads_flat,
-                           B, ws, ws_bytes, (cudaStream_t)stream);
+    rc = actor_train_fma(L, (const float*)packed, params, state, action, noise, t, inv_count, loss_out, grads_flat,
+                         B, ws, ws_bytes, (cudaStream_t)stream);
+    // the fp32 path finishes all groups together: every event marks the end of the call
+    for (int g = 0; rc == DDP_OK && g < DDP_ACTOR_GRAD_GROUPS; ++g)
+        if (ev[g]) DDP_CUDA_CHECK(cudaEventRecord(ev[g], (cudaStream_t)stream));
+    return rc;
+}
+
+int ddp_actor_loss_fwd_bwd(const ddp_actor_shape* s, const void* packed, const float* const params[12],
+                           const float* state, const float* action, const float* noise, const int64_t* t,
+                           float inv_count, float* loss_out, float* grads_flat, long B, int precision, void* ws,
+                           size_t ws_bytes, void* stream) {
+    return ddp_actor_loss_fwd_bwd_ev(s, packed, params, state, action, noise, t, inv_count, loss_out, grads_flat, B,
+                                     precision, ws, ws_bytes, stream, nullptr);
 }
 
 int ddp_clip_adamw_step(float* params_flat, float* grads_flat, float* exp_avg, float* exp_avg_sq, size_t n, int step,

@@ -407,7 +407,12 @@ int actor_train_fma(const ActorLayout& L, const float* pk, const float* const p[
 }
 
 // -------------------------------------------------------------------------------- clip + AdamW
-__global__ void sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+// ||g||^2 in a FIXED summation order: every block leaves its partial sum in partials[blockIdx.x] (no atomics), and
+// every consumer adds the partials up in the same order (block_total).  Data-parallel replicas that hold the same
+// reduced gradient therefore compute bit-identical norms, clip coefficients and parameters.
+constexpr int kNormBlocks = 592;           // partial sums; scratch holds kScratchPartials + kNormBlocks floats
+constexpr int kScratchPartials = 8;
+__global__ void sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ partials) {
     __shared__ float red[8];
     float s = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -418,18 +423,35 @@ __global__ void sumsq_kernel(const float* __restrict__ g, size_t n, float* __res
     if (threadIdx.x == 0) {
         float t = 0.f;
         for (int i = 0; i < 8; ++i) t += red[i];
-        atomicAdd(out, t);
+        partials[blockIdx.x] = t;
     }
+}
+// sum of `count` partials, identical in every thread of every block (256 threads)
+__device__ __forceinline__ float block_total(const float* __restrict__ partials, int count) {
+    __shared__ float red[8];
+    __shared__ float total;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < count; i += 256) s += partials[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        total = t;
+    }
+    __syncthreads();
+    return total;
 }
 
 // torch.optim.AdamW single-tensor semantics: p *= 1 - lr*wd; m.lerp_(g, 1-b1); v = b2*v + (1-b2) g^2;
 // p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps), after clip_grad_norm_ scaled g in place.
 __global__ void clip_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                                  float* __restrict__ v, size_t n, const float* __restrict__ sumsq, float decay,
+                                  float* __restrict__ v, size_t n, const float* __restrict__ partials, int n_partials, float decay,
                                   float step_size, float bc2_sqrt, float b1, float b2, float eps, float max_norm,
                                   float* __restrict__ norm_out, const float* __restrict__ dev_scalars) {
     if (dev_scalars) { step_size = dev_scalars[0]; bc2_sqrt = dev_scalars[1]; }     // step count kept on the device
-    const float norm = sqrtf(*sumsq);
+    const float norm = sqrtf(block_total(partials, n_partials));
     const float coef = fminf(max_norm / (norm + 1e-6f), 1.0f);
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *norm_out = norm;
@@ -445,18 +467,18 @@ __global__ void clip_adamw_kernel(float* __restrict__ p, float* __restrict__ g, 
 
 int clip_adamw(float* p, float* g, float* m, float* v, size_t n, int step, float lr, float b1, float b2, float eps,
                float wd, float max_norm, float* norm_out, float* scratch, cudaStream_t st) {
-    DDP_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(float), st));
     unsigned gb = (unsigned)((n + 255) / 256);
-    sumsq_kernel<<<gb < 592 ? gb : 592, 256, 0, st>>>(g, n, scratch);
+    const int nb = gb < (unsigned)kNormBlocks ? (int)gb : kNormBlocks;
+    sumsq_kernel<<<nb, 256, 0, st>>>(g, n, scratch + kScratchPartials);
     const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
-    clip_adamw_kernel<<<gb, 256, 0, st>>>(p, g, m, v, n, scratch, (float)(1.0 - (double)lr * wd), (float)(lr / bc1),
+    clip_adamw_kernel<<<gb, 256, 0, st>>>(p, g, m, v, n, scratch + kScratchPartials, nb, (float)(1.0 - (double)lr * wd), (float)(lr / bc1),
                                          (float)sqrt(bc2), b1, b2, eps, max_norm, norm_out, nullptr);
     DDP_LAUNCH_CHECK("clip_adamw kernels");
     return DDP_OK;
 }
 
 // The same step with the step count on the device (incremented by the call), so that the launch sequence carries
-// no per-step host value and can be captured once into a CUDA graph.  scratch: 3 floats.
+// no per-step host value and can be captured once into a CUDA graph.  scratch: DDP_ADAMW_SCRATCH_FLOATS.
 __global__ void adam_scalars_kernel(int* __restrict__ step_dev, float lr, float b1, float b2, float* __restrict__ out) {
     const int step = *step_dev + 1;
     *step_dev = step;
@@ -467,11 +489,11 @@ __global__ void adam_scalars_kernel(int* __restrict__ step_dev, float lr, float 
 
 int clip_adamw_dev(float* p, float* g, float* m, float* v, size_t n, int* step_dev, float lr, float b1, float b2,
                    float eps, float wd, float max_norm, float* norm_out, float* scratch, cudaStream_t st) {
-    DDP_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(float), st));
     unsigned gb = (unsigned)((n + 255) / 256);
-    sumsq_kernel<<<gb < 592 ? gb : 592, 256, 0, st>>>(g, n, scratch);
+    const int nb = gb < (unsigned)kNormBlocks ? (int)gb : kNormBlocks;
+    sumsq_kernel<<<nb, 256, 0, st>>>(g, n, scratch + kScratchPartials);
     adam_scalars_kernel<<<1, 1, 0, st>>>(step_dev, lr, b1, b2, scratch + 1);
-    clip_adamw_kernel<<<gb, 256, 0, st>>>(p, g, m, v, n, scratch, (float)(1.0 - (double)lr * wd), 0.f, 1.f, b1, b2, eps,
+    clip_adamw_kernel<<<gb, 256, 0, st>>>(p, g, m, v, n, scratch + kScratchPartials, nb, (float)(1.0 - (double)lr * wd), 0.f, 1.f, b1, b2, eps,
                                          max_norm, norm_out, scratch + 1);
     DDP_LAUNCH_CHECK("clip_adamw (device step) kernels");
     return DDP_OK;

@@ -8,11 +8,12 @@
 // uses the packed fp32 [T, h1] table in the forward (added per row in the epilogue of layer 0) and, in the
 // backward, G[t] = sum of dZ0 rows with timestep t obtained as dZ0^T . onehot(t) by the same dW GEMM, followed
 // by the fp32 T-row products shared with the fp32 path.
-#include <stdlib.h>
 #include "actor_layout.cuh"
 #include "tc_gemm.cuh"
 
 namespace ddp {
+
+static bool g_train_no_chain = false;      // set by ddp_debug_train_no_chain (development aid, not in the public header)
 
 void time_branch_backward(const ActorLayout& L, const float* pk, const float* const p[12], const float* G,
                           float* dtemb, float* dhmid, float* g, cudaStream_t st);
@@ -153,7 +154,7 @@ size_t actor_train_tc_workspace(const ActorLayout& L, long B) { return carve(L, 
 
 int actor_train_tc(const ActorLayout& L, const void* packed, const float* const p[12], const float* state,
                    const float* action, const float* noise, const int64_t* t, float inv_count, float* loss_out,
-                   float* grads, long B, void* ws, size_t ws_bytes, cudaStream_t st) {
+                   float* grads, long B, void* ws, size_t ws_bytes, cudaStream_t st, const cudaEvent_t* group_ev) {
     using namespace tcg;
     if (!shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 training path needs A<=8, S<=56, widths multiple of 64");
     if (ws_bytes < carve(L, B, nullptr).total) DDP_FAIL(DDP_ERR_ARG, "training workspace too small");
@@ -180,10 +181,9 @@ int actor_train_tc(const ActorLayout& L, const void* packed, const float* const 
     };
     int rc;
     // ---- forward: one fused launch (all four layers on chip, activations / derivatives leave by TMA store) when the
-    // shape fits the sampler's tile plan, else one row GEMM per layer.  DDP_TRAIN_NO_CHAIN=1 forces the latter.
-    const char* nc_env = getenv("DDP_TRAIN_NO_CHAIN");      // read per call: the tests switch between the two forwards
-    const bool no_chain = nc_env && atoi(nc_env) != 0;
-    if (!no_chain && actor_train_chain_shape_ok(L)) {
+    // shape fits the sampler's tile plan, else one row GEMM per layer (g_train_no_chain: debug switch for A/B runs and
+    // for the test that pins the two forwards against each other).
+    if (!g_train_no_chain && actor_train_chain_shape_ok(L)) {
         if ((rc = actor_train_chain_fwd(L, packed, w.xin, t, noise, inv_count, loss_out, w.a0, w.d0, w.a1, w.d1, w.a2, w.d2,
                                         w.deps, B, st)) != DDP_OK) return rc;
     } else {
@@ -200,11 +200,9 @@ int actor_train_tc(const ActorLayout& L, const void* packed, const float* const 
             if ((rc = launch_row_gemm(g, st)) != DDP_OK) return rc;
         }
     }
-    // ---- backward: dZ chain (dZ_l overwrites the stored derivative d_l in place)
-    if ((rc = launch_row_gemm(row(w.deps, 64, (const bf16*)(pb + L.tr_w3t), 64, L.h3, 64, EPI_MUL_D, nullptr, w.d2, w.d2, nullptr, nullptr, 0, 0), st)) != DDP_OK) return rc;
-    if ((rc = launch_row_gemm(row(w.d2, L.h3, (const bf16*)(pb + L.tr_w2t), L.h3, L.h2, L.h3, EPI_MUL_D, nullptr, w.d1, w.d1, nullptr, nullptr, 0, 0), st)) != DDP_OK) return rc;
-    if ((rc = launch_row_gemm(row(w.d1, L.h2, (const bf16*)(pb + L.tr_w1t), L.h2, L.h1, L.h2, EPI_MUL_D, nullptr, w.d0, w.d0, nullptr, nullptr, 0, 0), st)) != DDP_OK) return rc;
-    // ---- weight gradients
+    // ---- backward, last layer first: the dZ chain (dZ_l overwrites the stored derivative d_l in place) interleaved
+    // with the weight gradients, so that every gradient group is final -- and its all-reduce can start (group_ev) --
+    // while the earlier layers are still being differentiated
     auto dw = [&](const bf16* dz, int ldz, int N, const bf16* X, int ldx, int K, float* C, int ldc, const int* colmap,
                   float* C2 = nullptr, int ldc2 = 0, float* colsum = nullptr) {
         DwGemm g{};
@@ -212,10 +210,20 @@ int actor_train_tc(const ActorLayout& L, const void* packed, const float* const 
         g.C2 = C2; g.ldc2 = ldc2; g.colsum = colsum;
         return launch_dw_gemm(g, st);
     };
-    // bias gradients (column sums of dZ) come out of the same launches
+    auto mark = [&](int g) -> int {
+        if (group_ev && group_ev[g]) DDP_CUDA_CHECK(cudaEventRecord(group_ev[g], st));
+        return DDP_OK;
+    };
+    // bias gradients (column sums of dZ) come out of the same launches as the weight gradients
     if ((rc = dw(w.deps, 64, L.A, w.a2, L.h3, L.h3, grads + go.off[10], L.h3, nullptr, nullptr, 0, grads + go.off[11])) != DDP_OK) return rc;
+    if ((rc = mark(0)) != DDP_OK) return rc;
+    if ((rc = launch_row_gemm(row(w.deps, 64, (const bf16*)(pb + L.tr_w3t), 64, L.h3, 64, EPI_MUL_D, nullptr, w.d2, w.d2, nullptr, nullptr, 0, 0), st)) != DDP_OK) return rc;
     if ((rc = dw(w.d2, L.h3, L.h3, w.a1, L.h2, L.h2, grads + go.off[8], L.h2, nullptr, nullptr, 0, grads + go.off[9])) != DDP_OK) return rc;
+    if ((rc = mark(1)) != DDP_OK) return rc;
+    if ((rc = launch_row_gemm(row(w.d2, L.h3, (const bf16*)(pb + L.tr_w2t), L.h3, L.h2, L.h3, EPI_MUL_D, nullptr, w.d1, w.d1, nullptr, nullptr, 0, 0), st)) != DDP_OK) return rc;
     if ((rc = dw(w.d1, L.h2, L.h2, w.a0, L.h1, L.h1, grads + go.off[6], L.h1, nullptr, nullptr, 0, grads + go.off[7])) != DDP_OK) return rc;
+    if ((rc = mark(2)) != DDP_OK) return rc;
+    if ((rc = launch_row_gemm(row(w.d1, L.h2, (const bf16*)(pb + L.tr_w1t), L.h2, L.h1, L.h2, EPI_MUL_D, nullptr, w.d0, w.d0, nullptr, nullptr, 0, 0), st)) != DDP_OK) return rc;
     // G^T[n][t]: from the one-hot columns of xin in the same launch (T <= 8), else from a separate one-hot operand
     if ((rc = dw(w.d0, L.h1, L.h1, w.xin, 64, 64, grads + go.off[4], ld0, (const int*)(pb + L.tr_colmap), w.GT, Tp)) != DDP_OK) return rc;
     if (!tcols && (rc = dw(w.d0, L.h1, L.h1, w.onehot, Tp, L.T, w.GT, Tp, nullptr)) != DDP_OK) return rc;
@@ -223,7 +231,11 @@ int actor_train_tc(const ActorLayout& L, const void* packed, const float* const 
     transpose_small_kernel<<<(L.h1 * L.T + 255) / 256, 256, 0, st>>>(w.GT, L.h1, L.T, Tp, w.G);
     time_branch_backward(L, pk, p, w.G, w.dtemb, w.dhmid, grads, st);
     DDP_LAUNCH_CHECK("actor_train_tc kernels");
-    return DDP_OK;
+    return mark(3);
 }
 
 }  // namespace ddp
+
+// Debug entry point (not part of the public header): 1 = run the forward of the tensor-core training path as one row
+// GEMM per layer instead of the fused on-chip chain (A/B measurements, tests/test_tc_gpu.py).  Process-wide.
+extern "C" void ddp_debug_train_no_chain(int on) { ddp::g_train_no_chain = on != 0; }

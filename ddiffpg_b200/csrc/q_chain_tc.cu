@@ -22,7 +22,6 @@
 // Weight tiles stream from L2 through a 3-stage TMA ring; all K+1 critics live in the same tensor maps (row
 // offset = mode * N), a tile never straddles a mode segment.
 #include <math.h>
-#include <stdlib.h>
 #include <type_traits>
 #include "q_layout.cuh"
 #include "tc_common.cuh"
@@ -798,8 +797,6 @@ int q_chain_pass(const QLayout& L, const void* packed, const int64_t* seg_off, c
     const size_t smem = SMQ::total + 1024;
     DDP_CUDA_CHECK(cudaFuncSetAttribute(q_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    static const int grid_cap = getenv("DDP_QC_GRID") ? atoi(getenv("DDP_QC_GRID")) : 0;      // experiments only
-    if (grid_cap > 0 && grid_cap < grid) grid = grid_cap;
     if (asc) {
         // the grid barrier needs every CTA resident at once: cooperative launch, one CTA per SM
         void* kargs[2] = {(void*)&maps, (void*)&a};

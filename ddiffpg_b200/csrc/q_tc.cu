@@ -9,7 +9,6 @@
 // Per ascent iteration: 2 nets x 4 forward GEMMs, one softmax/selection kernel, 2 nets x 4 backward GEMMs (ELU
 // derivative fused in the epilogue, from the stored activation), one gradient/norm kernel, one Adam kernel.
 #include <math.h>
-#include <stdlib.h>
 #include "q_layout.cuh"
 #include "tc_gemm.cuh"
 
@@ -34,11 +33,12 @@ namespace {
 
 using bf16 = __nv_bfloat16;
 
-// DDP_Q_NO_CHAIN=1 selects the layer-by-layer GEMM path even where the fused kernel applies (A/B measurements)
-bool use_chain(const QLayout& L) {
-    const char* e = getenv("DDP_Q_NO_CHAIN");          // read per call: tests flip it
-    return !(e && atoi(e) != 0) && q_chain_shape_ok(L);
-}
+// Debug switches (ddp_debug_q_variant, not in the public header): the three schedules of the same bf16 arithmetic that
+// tests/test_tc_gpu.py pins against each other.  Defaults: fused chain where the shape fits; all iterations in one
+// cooperative launch while the batch is at most ~half a wave of tiles.
+int g_q_no_chain = 0;        // 1: layer-by-layer GEMM path even where the fused kernel applies
+int g_q_fused_adam = -1;     // -1: by batch size, 0 / 1: force the per-iteration / the single-launch form
+bool use_chain(const QLayout& L) { return !g_q_no_chain && q_chain_shape_ok(L); }
 
 struct QSeg {
     long off[kMaxModes + 1];
@@ -341,11 +341,10 @@ int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, co
     // All iterations in ONE cooperative launch (grid barrier on the clip norm, Adam applied by the CTA that owns the
     // rows): 8 % faster while the batch is at most ~half a wave of tiles (1.12 vs 1.22 ms at 256..4096 states: the
     // per-tile latency chain dominates and the launches in between are exposed), equal or slower beyond (4.41 vs
-    // 4.33 ms at 65 536: the stream hides the launches).  DDP_Q_FUSED_ADAM=0/1 forces either form.
+    // 4.33 ms at 65 536: the stream hides the launches).
     long tiles = 0;
     for (int m = 0; m < L.n_modes; ++m) tiles += (seg_off[m + 1] - seg_off[m] + 127) / 128;
-    const char* fe = getenv("DDP_Q_FUSED_ADAM");
-    const bool fused = fe ? atoi(fe) != 0 : tiles <= 64;
+    const bool fused = g_q_fused_adam >= 0 ? g_q_fused_adam != 0 : tiles <= 64;
     if (chain && fused && iters >= 1 && iters <= 32) {
         QChainAscent asc{iters, action, w.m1, w.m2, gnorm_out, w.grid_bar, lr, b1, b2, eps, max_norm, lim};
         int rc = q_chain_pass(L, packed, seg_off, neg_inv, w.xin, w.g, w.gsq, nullptr, nullptr, nullptr, B,
@@ -376,3 +375,10 @@ int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, co
 }
 
 }  // namespace ddp
+
+// Debug entry point (not part of the public header): choose the schedule of the tensor-core critic path explicitly
+// (no_chain: 0 / 1; fused_adam: -1 = by batch size, 0, 1).  Process-wide; used by tests and A/B measurements only.
+extern "C" void ddp_debug_q_variant(int no_chain, int fused_adam) {
+    ddp::g_q_no_chain = no_chain;
+    ddp::g_q_fused_adam = fused_adam;
+}

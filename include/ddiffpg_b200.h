@@ -107,11 +107,27 @@ int ddp_actor_loss_fwd_bwd(const ddp_actor_shape* shape, const void* packed,
                            const float* noise, const int64_t* t, float inv_count, float* loss_out,
                            float* grads_flat, long B, int precision, void* ws, size_t ws_bytes,
                            void* stream);
+/* The same call with completion events for the data-parallel exchange step (the sum all-reduce of the
+ * flat gradient is the only collective of the path).  The backward produces the gradient in four groups, last layer
+ * first; group_events[g] (a cudaEvent_t, or NULL to skip) is recorded on `stream` as soon as group g is final, so the
+ * caller can start reducing it on another stream while the rest of the backward still runs:
+ *   g = 0: net.mlp.6.{weight,bias} (and loss_out)   1: net.mlp.4.*   2: net.mlp.2.*
+ *   g = 3: net.time_mlp.* and net.mlp.0.* (recorded at the end of the call).
+ * group_events == NULL is ddp_actor_loss_fwd_bwd. */
+enum { DDP_ACTOR_GRAD_GROUPS = 4 };
+int ddp_actor_loss_fwd_bwd_ev(const ddp_actor_shape* shape, const void* packed,
+                              const float* const params[12], const float* state, const float* action,
+                              const float* noise, const int64_t* t, float inv_count, float* loss_out,
+                              float* grads_flat, long B, int precision, void* ws, size_t ws_bytes,
+                              void* stream, void* const* group_events);
 
 /* Tail of ActorCriticBase.optimizer_update (ddiffpg/algo/ac_base.py:86-91) for a flat parameter
  * vector: g_norm = ||g||_2, g *= min(1, max_norm/(g_norm+1e-6)), AdamW step (torch.optim.AdamW
  * semantics, decoupled weight decay, bias-corrected).  norm_out[0] receives the pre-clip norm.
- * step is the 1-based step count after this update.  scratch: 1 float, zeroed by the call. */
+ * step is the 1-based step count after this update.  scratch: DDP_ADAMW_SCRATCH_FLOATS floats (per-block partial
+ * sums of ||g||^2, added up in a fixed order: the norm, hence the clip coefficient and the parameters, are
+ * bit-identical on data-parallel replicas that hold the same reduced gradient; no atomics). */
+enum { DDP_ADAMW_SCRATCH_FLOATS = 640 };
 int ddp_clip_adamw_step(float* params_flat, float* grads_flat, float* exp_avg, float* exp_avg_sq,
                         size_t n, int step, float lr, float beta1, float beta2, float eps,
                         float weight_decay, float max_norm, float* norm_out, float* scratch,
@@ -119,7 +135,7 @@ int ddp_clip_adamw_step(float* params_flat, float* grads_flat, float* exp_avg, f
 
 /* The same step with the 1-based step count kept in DEVICE memory: *step_counter is incremented by the call and the
  * bias corrections are derived from it on the device, so the launch sequence carries no per-step host value and
- * a whole training step can be captured once into a CUDA graph.  scratch: 3 floats. */
+ * a whole training step can be captured once into a CUDA graph.  scratch: DDP_ADAMW_SCRATCH_FLOATS floats. */
 int ddp_clip_adamw_step_dev(float* params_flat, float* grads_flat, float* exp_avg, float* exp_avg_sq, size_t n,
                             int* step_counter, float lr, float beta1, float beta2, float eps, float weight_decay,
                             float max_norm, float* norm_out, float* scratch, void* stream);

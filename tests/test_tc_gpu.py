@@ -171,9 +171,12 @@ def test_train_bf16_grads_vs_oracle(B, T):
 
 
 @pytest.mark.parametrize("B,T", [(700, 5), (1000, 20)])
-def test_train_bf16_layerwise_forward_matches_fused_forward(B, T, monkeypatch):
-    """DDP_TRAIN_NO_CHAIN=1 runs the forward as one row GEMM per layer (time table folded into the layer-0 GEMM for
-    T <= 8, loss in the head epilogue) instead of the fused on-chip chain: same loss and gradients at the bf16 bound."""
+def test_train_bf16_layerwise_forward_matches_fused_forward(B, T):
+    """ddp_debug_train_no_chain(1) runs the forward as one row GEMM per layer (time table folded into the layer-0 GEMM
+    for T <= 8, loss in the head epilogue) instead of the fused on-chip chain: same loss and gradients at the bf16 bound."""
+    from ddiffpg_b200 import _lib
+    dbg = _lib.lib().ddp_debug_train_no_chain
+    dbg.argtypes, dbg.restype = [ctypes.c_int], None
     gen = torch.Generator().manual_seed(1900 + B)
     p = port.init_actor_params(87)
     state = torch.randn(B, 34, generator=gen)
@@ -183,12 +186,16 @@ def test_train_bf16_layerwise_forward_matches_fused_forward(B, T, monkeypatch):
     l_ref, g_ref = port.actor_loss_and_grads(p, state, action, noise, ts, T)
     ref = torch.cat([g_ref[k].reshape(-1) for k in port.ACTOR_KEYS])
     flats = []
-    for no_chain in ("0", "1"):
-        monkeypatch.setenv("DDP_TRAIN_NO_CHAIN", no_chain)
-        pol = make_policy(p, T)
-        pol.train_precision = "bf16"
-        loss = pol.get_loss(_dev(state), _dev(action), noise=_dev(noise), timesteps=_dev(ts))
-        loss.backward()
+    for no_chain in (0, 1):
+        dbg(no_chain)
+        try:
+            pol = make_policy(p, T)
+            pol.train_precision = "bf16"
+            loss = pol.get_loss(_dev(state), _dev(action), noise=_dev(noise), timesteps=_dev(ts))
+            loss.backward()
+            torch.cuda.synchronize()
+        finally:
+            dbg(0)
         assert abs(loss.item() - l_ref.item()) <= 1e-4 * l_ref.item(), f"no_chain={no_chain}"
         got = torch.cat([q.grad.reshape(-1) for _, q in pol.named_parameters()]).cpu()
         rel = ((got - ref).norm() / ref.norm()).item()
@@ -339,22 +346,19 @@ def test_get_actions_host_matches_chunked_device_calls(B):
     assert pol.get_actions_host(torch.zeros(0, 34).pin_memory()).shape == (0, 8)
 
 
-def _ascent_with_env(env, critics, obs, act, off, **kw):
-    import os
-    from ddiffpg_b200 import q_action_ascent_segments
-    old = {k: os.environ.get(k) for k in env}
-    os.environ.update(env)
+def _ascent_variant(no_chain, fused_adam, critics, obs, act, off, **kw):
+    """One ascent under an explicitly chosen schedule (ddp_debug_q_variant; the default is restored afterwards)."""
+    from ddiffpg_b200 import _lib, q_action_ascent_segments
+    dbg = _lib.lib().ddp_debug_q_variant
+    dbg.argtypes, dbg.restype = [ctypes.c_int, ctypes.c_int], None
+    dbg(no_chain, fused_adam)
     try:
         work = act.clone()
         mean_abs, norms = q_action_ascent_segments(critics, obs, work, off, iters=20, precision="bf16", return_norms=True, **kw)
         torch.cuda.synchronize()
         return work, mean_abs, norms
     finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
+        dbg(0, -1)
 
 
 def test_q_chain_variants_agree():
@@ -371,9 +375,9 @@ def test_q_chain_variants_agree():
     for s in sizes:
         off.append(off[-1] + s)
     obs, act = _dev(torch.randn(B, 29, generator=gen)), _dev(torch.rand(B, 8, generator=gen) * 2 - 1)
-    a_chain, m_chain, n_chain = _ascent_with_env({"DDP_Q_NO_CHAIN": "0", "DDP_Q_FUSED_ADAM": "0"}, critics, obs, act, off)
-    a_fused, m_fused, n_fused = _ascent_with_env({"DDP_Q_NO_CHAIN": "0", "DDP_Q_FUSED_ADAM": "1"}, critics, obs, act, off)
-    a_gemm, m_gemm, n_gemm = _ascent_with_env({"DDP_Q_NO_CHAIN": "1", "DDP_Q_FUSED_ADAM": "0"}, critics, obs, act, off)
+    a_chain, m_chain, n_chain = _ascent_variant(0, 0, critics, obs, act, off)
+    a_fused, m_fused, n_fused = _ascent_variant(0, 1, critics, obs, act, off)
+    a_gemm, m_gemm, n_gemm = _ascent_variant(1, 0, critics, obs, act, off)
     live = [i for i, s in enumerate(sizes) if s]
     assert torch.allclose(n_chain[live], n_fused[live], rtol=1e-4, atol=1e-7)
     assert torch.allclose(n_chain[live][:, 0], n_gemm[live][:, 0], rtol=2e-2)      # same gradient, different bf16 rounding points
