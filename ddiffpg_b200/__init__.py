@@ -8,9 +8,10 @@ from .models import DiffusionPolicy, DistributionalDoubleQ, DiffusionNet, MLPNet
 from .algo import (FusedActorTrainer, HotPathMixin, critic_loss_and_grads, get_actions,  # noqa: F401
                    get_tgt_policy_actions, update_critic,
                    optimizer_update, q_action_ascent_segments, soft_update, update_actor, update_target_action)
-from .intrinsic import IntrinsicM, RNDModel, RunningMeanStd  # noqa: F401
-from .replay import DiffusionReplayBuffer, add_embedding  # noqa: F401
+from .intrinsic import IntrinsicKernels, IntrinsicM, RNDModel, accelerate_intrinsic  # noqa: F401
+from .replay import DiffusionReplayBuffer, ReplayKernels, accelerate_replay_buffer, add_embedding  # noqa: F401
 
-__all__ = ["IntrinsicM", "RNDModel", "RunningMeanStd", "DiffusionReplayBuffer", "add_embedding", "DiffusionPolicy", "DistributionalDoubleQ", "DiffusionNet", "MLPNet", "FusedActorTrainer",
+__all__ = ["IntrinsicKernels", "IntrinsicM", "RNDModel", "accelerate_intrinsic", "DiffusionReplayBuffer", "ReplayKernels",
+           "accelerate_replay_buffer", "add_embedding", "DiffusionPolicy", "DistributionalDoubleQ", "DiffusionNet", "MLPNet", "FusedActorTrainer",
            "HotPathMixin", "critic_loss_and_grads", "update_critic", "get_actions", "get_tgt_policy_actions", "optimizer_update", "q_action_ascent_segments", "soft_update", "update_actor",
            "update_target_action"]

@@ -130,7 +130,8 @@ def critic_loss_and_grads(critic, critic_target, obs, action, next_obs, next_act
             c._cache_fp32 = _PackCache()
         return c._cache_fp32
     packed, shape, prec = pack_critics([critic], fp32_cache(critic), "fp32")
-    packed_t, _, _ = pack_critics([critic_target], fp32_cache(critic_target), "fp32")
+    # the target critic is written through param.data by soft_update (ddiffpg.py:266): always re-packed (see _PackCache)
+    packed_t, _, _ = pack_critics([critic_target], fp32_cache(critic_target), "fp32", force=True)
     dev = packed.device
     f = lambda x: x.detach().to(device=dev, dtype=torch.float32).contiguous()
     obs, action, next_obs, next_actions = f(obs), f(action), f(next_obs), f(next_actions)

@@ -1,9 +1,10 @@
 """RND / NovelD intrinsic reward on the accelerated path.
 
-``RNDModel`` mirrors ``ddiffpg.models.mlp.RNDModel`` (:233-267), ``IntrinsicM`` mirrors
-``ddiffpg.utils.intrinsic.IntrinsicM`` (:8-94) call for call; the two MLPs, the novelty norm, the mse loss and the
-predictor's backward run through ``libddiffpg_b200.so`` (fp32 path), the optimizer step is torch's own AdamW as in
-the reference.
+``RNDModel`` mirrors ``ddiffpg.models.mlp.RNDModel`` (:233-267) as the parameter container the kernels read;
+``IntrinsicKernels`` is a mixin for ``ddiffpg.utils.intrinsic.IntrinsicM`` (:8-94) that overrides only the methods
+that run the networks: the two MLPs, the novelty norm, the mse loss and the predictor's backward go through
+``libddiffpg_b200.so`` (fp32 path), the optimizer step is torch's own AdamW as in the reference, and everything else
+(reward shaping, positional encoding, running statistics) remains the reference's code.
 """
 from collections.abc import Sequence
 
@@ -106,93 +107,23 @@ class RNDModel(nn.Module):
         return loss, grads
 
 
-class RunningMeanStd:
-    """ddiffpg/utils/torch_util.py:99-146 (parallel-variance update), tensors on ``device``."""
+class IntrinsicKernels:
+    """Mixin for ``ddiffpg.utils.intrinsic.IntrinsicM`` (:8-94): the three methods that run the two networks --
+    ``get_novelty`` (:62-65), ``update`` (:67-75) and its ``optimizer_update`` (:77-83) -- go through the kernels;
+    construction, ``compute_reward``, ``encode_obs`` and the running statistics stay the reference's own code.
+    ``accelerate_intrinsic(IntrinsicM)`` builds the class; it swaps ``rnd_model`` for the kernel-backed ``RNDModel``
+    (same weights) and re-creates the AdamW over its predictor."""
 
-    def __init__(self, epsilon=1e-4, shape=(), device="cuda"):
-        self.device = device
-        self.mean = torch.zeros(shape, device=device)
-        self.var = torch.ones(shape, device=device)
-        self.epsilon = epsilon
-        self.count = epsilon
-
-    def update(self, x):
-        self.update_from_moments(x.mean(dim=0), x.var(dim=0), x.shape[0])
-
-    def normalize(self, x):
-        return (x - self.mean) / torch.sqrt(self.var + self.epsilon)
-
-    def unnormalize(self, x):
-        return x * torch.sqrt(self.var + self.epsilon) + self.mean
-
-    def update_from_moments(self, batch_mean, batch_var, batch_count):
-        delta = batch_mean - self.mean
-        tot_count = self.count + batch_count
-        new_mean = self.mean + delta * batch_count / tot_count
-        m_2 = self.var * self.count + batch_var * batch_count + delta ** 2 * self.count * batch_count / tot_count
-        self.mean, self.var, self.count = new_mean, m_2 / tot_count, tot_count
-
-
-def get_embedder(multires, input_dims=2):
-    """NeRF positional encoding as configured by utils/intrinsic.py:122-171: [x, sin(2^k x), cos(2^k x)], k < multires."""
-    freq_bands = 2. ** torch.linspace(0., multires - 1, steps=multires)
-
-    def embed(x):
-        outs = [x]
-        for freq in freq_bands:
-            outs.append(torch.sin(x * freq))
-            outs.append(torch.cos(x * freq))
-        return torch.cat(outs, -1)
-    return embed, input_dims * (1 + 2 * multires)
-
-
-class IntrinsicM:
-    def __init__(self, obs_dim, type="noveld", env_name=None, normalize=True, pos_enc=True, L=10, warm_up=1000,
-                 device="cuda"):
-        self.obs_dim = obs_dim
-        self.type = type
-        self.env_name = env_name
-        self.normalize = normalize
-        self.device = device
-        self.pos_enc = pos_enc
-        self.update_step = 0
-        self.warm_up = warm_up
-        self.L = L
-        if self.pos_enc:
-            dims = 2 if "antmaze" in self.env_name else 3
-            self.embedder, _ = get_embedder(self.L, input_dims=2)
-            self.rnd_model = RNDModel(self.obs_dim[0] + dims * 2 * L).to(self.device)
-        else:
-            self.rnd_model = RNDModel(self.obs_dim).to(self.device)
+    def _adopt_rnd_model(self):
+        old = self.rnd_model
+        if isinstance(old, RNDModel):
+            return
+        first = old.predictor[0]
+        new = RNDModel(first.in_features, hidden=tuple(l.out_features for l in list(old.predictor)[0:5:2]),
+                       feature_dim=old.predictor[-1].out_features)
+        new.load_state_dict(old.state_dict())
+        self.rnd_model = new.to(first.weight.device)
         self.rnd_optimizer = torch.optim.AdamW(self.rnd_model.parameters(), 1e-4)
-        self.rnd_rms = RunningMeanStd(shape=(1), device=self.device)
-
-    def compute_reward(self, obs, next_obs=None):
-        if self.pos_enc:
-            obs = self.encode_obs(obs)
-            if next_obs is not None:
-                next_obs = self.encode_obs(next_obs)
-        if self.type == "rnd":
-            novelty_obs = self.get_novelty(obs)
-            if self.normalize and self.update_step > self.warm_up:
-                self.rnd_rms.update(novelty_obs)
-                novelty_obs = self.rnd_rms.normalize(novelty_obs)
-            return novelty_obs.unsqueeze(1)
-        elif self.type == "noveld":
-            assert next_obs is not None
-            # both batches in one launch; the running statistics see them in the reference's order
-            n = obs.shape[0]
-            nov = self.get_novelty(torch.cat([obs, next_obs]))
-            novelty_obs, novelty_nextobs = nov[:n], nov[n:]
-            if self.normalize and self.update_step > self.warm_up:
-                self.rnd_rms.update(novelty_obs)
-                self.rnd_rms.update(novelty_nextobs)
-                novelty_obs = self.rnd_rms.normalize(novelty_obs)
-                novelty_nextobs = self.rnd_rms.normalize(novelty_nextobs)
-            intrinsic = novelty_nextobs - 0.5 * novelty_obs
-            return 0.01 * torch.max(intrinsic, torch.zeros(intrinsic.shape, device=intrinsic.device)).unsqueeze(1)
-        else:
-            raise NotImplementedError
 
     def get_novelty(self, obs):
         return self.rnd_model.novelty(obs)
@@ -206,7 +137,7 @@ class IntrinsicM:
         return dynamic_loss.item(), dynamic_grad_norm.item()
 
     def optimizer_update(self, optimizer, objective):
-        """intrinsic.py:77-83 with the backward already done by the kernel: scatter, clip, step."""
+        """The backward is already done by the kernel: scatter the flat gradient, clip at 1.0, step."""
         _, grads = objective
         optimizer.zero_grad(set_to_none=True)
         off = 0
@@ -217,6 +148,17 @@ class IntrinsicM:
         optimizer.step()
         return grad_norm
 
-    def encode_obs(self, obs):
-        k = 2 if "antmaze" in self.env_name else 3       # ant 2-d position / end-effector 3-d position
-        return torch.cat([self.embedder(obs[:, :k]), obs[:, k:]], dim=1)
+
+def accelerate_intrinsic(base):
+    """``IntrinsicKernels`` in front of ``base`` (the reference's ``IntrinsicM``)."""
+    def __init__(self, *args, **kwargs):
+        base.__init__(self, *args, **kwargs)
+        self._adopt_rnd_model()
+    return type(base.__name__, (IntrinsicKernels, base), {"__init__": __init__, "__doc__": IntrinsicKernels.__doc__})
+
+
+try:        # needs the reference package with its own dependencies (gym, ...) importable
+    from ddiffpg.utils.intrinsic import IntrinsicM as _ReferenceIntrinsicM
+    IntrinsicM = accelerate_intrinsic(_ReferenceIntrinsicM)
+except Exception:
+    IntrinsicM = None       # build it with accelerate_intrinsic(<the reference class>) where the reference is installed

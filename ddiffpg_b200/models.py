@@ -52,7 +52,9 @@ class _PackCache:
     """Packed weights, rebuilt when any parameter's (data_ptr, _version) changes.
 
     In-place updates through ``param.data`` (the reference's ``soft_update``, utils/torch_util.py:9-12) do
-    not bump ``_version``; call ``mark_dirty()`` after those (``ddiffpg_b200.algo.soft_update`` does)."""
+    not bump ``_version``.  The one network the reference updates that way, the target critic, is therefore re-packed
+    on every use by ``critic_loss_and_grads`` (its only reader on the hot path); for any other ``.data`` write call
+    ``mark_dirty()`` (``ddiffpg_b200.algo.soft_update`` does)."""
 
     def __init__(self):
         self.key = None
@@ -357,8 +359,11 @@ class MLPNet(nn.Module):
         return self.net(x)
 
 
-def pack_critics(critics, cache, precision=None):
-    """Pack one or more DistributionalDoubleQ modules (one per behaviour mode) into one buffer."""
+def pack_critics(critics, cache, precision=None, force=False):
+    """Pack one or more DistributionalDoubleQ modules (one per behaviour mode) into one buffer.
+    ``force``: re-pack even if no parameter's ``(data_ptr, _version)`` changed -- for networks that are written through
+    ``param.data`` (the reference's ``soft_update`` of the target critics, utils/torch_util.py:9-12), which leaves both
+    untouched."""
     first = critics[0]
     precision = precision or getattr(first, "precision", "fp32")
     params = [p for c in critics for _, p in c.named_parameters()]
@@ -371,7 +376,7 @@ def pack_critics(critics, cache, precision=None):
     shape = QShape(first.state_dim, first.act_dim, first.num_atoms, float(first.v_min), float(first.v_max),
                    len(critics), *first.hidden_layers)
     prec = _lib.PRECISIONS[precision]
-    if cache.stale(params, (precision, len(critics), str(dev))):
+    if cache.stale(params, (precision, len(critics), str(dev))) or force:
         nbytes = lib().ddp_q_packed_bytes(shape, prec)
         if nbytes == 0:
             check(-1, "ddp_q_packed_bytes")
@@ -459,12 +464,16 @@ class DistributionalDoubleQ(nn.Module):
         return _QMinFn.apply(self, state, action)
 
     def get_q1_q2(self, state, action):
-        """mlp.py:149-151.  Forward-only through the kernel.  With trainable weights under autograd (the
-        critic update, SURVEY.md 8f row N1, next in scope) the two softmax heads are evaluated with
-        stock torch ops on the same device so that the reference's critic loss keeps training."""
+        """mlp.py:149-151, forward values through the kernel (no autograd graph: the probabilities are constants).
+        The reference's one caller that differentiates them w.r.t. the critic weights is the critic update
+        (ddiffpg.py:348-349); on this path that is ``update_critic`` -> ``ddp_q_critic_loss_fwd_bwd``, which returns
+        the loss and all gradients from one fused pass.  Asking for an autograd graph here raises instead of silently
+        running eager torch."""
         if self._params_need_grad():
-            x = torch.cat((state, action), dim=1)
-            return torch.softmax(self.net_q1(x), dim=1), torch.softmax(self.net_q2(x), dim=1)
+            raise NotImplementedError(
+                "get_q1_q2 under autograd with trainable critic weights has no kernel: use ddiffpg_b200.update_critic / "
+                "critic_loss_and_grads (fused BCE loss + backward), or call it under torch.no_grad() / with the critic "
+                "frozen for forward values")
         _, p1, p2, _ = self._forward_raw(state, action, want_probs=True, want_grad=False)
         return p1, p2
 

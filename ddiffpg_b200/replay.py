@@ -1,15 +1,16 @@
 """Batch assembly / scatter-back around the hot path.
 
-``DiffusionReplayBuffer`` mirrors ``ddiffpg.replay.simple_replay.DiffusionReplayBuffer`` (:98-200) -- same storage,
-same methods -- with ``sample_batch`` / ``update_target_action`` running as one gather / scatter launch of
-``libddiffpg_b200.so``; ``add_embedding`` mirrors ``ddiffpg.utils.torch_util.add_embedding`` (:17-43).
-``sample_groups`` / ``scatter_groups`` are the fused form ``DiffusionGoalBuffer.sample_batch`` +
-``AgentDDiffPG.update_net`` need: every mode group (rows sorted by mode, the layout of ``q_action_ascent_segments``)
-including the embedded states in one launch.  Random draws stay in torch / numpy as in the reference and can be
-injected (``indices=``, ``zero_indices=``) so that results are reproducible against the reference's generators.
+``ReplayKernels`` is a mixin for ``ddiffpg.replay.simple_replay.DiffusionReplayBuffer`` (:98-200): it overrides the two
+methods that move batch data -- ``sample_batch`` (:150-163) and ``update_target_action`` (:198-200) -- with one gather /
+one scatter launch of ``libddiffpg_b200.so`` and adds their fused forms ``sample_groups`` / ``scatter_groups`` (every
+mode group of ``DiffusionGoalBuffer.sample_batch`` + ``AgentDDiffPG.update_net``, rows sorted by mode -- the layout of
+``q_action_ascent_segments`` -- including the embedded states, in one launch).  Storage and bookkeeping
+(``add_to_buffer``, ``remove``, ``get_buffer_size``, ``update_target_action_dim``) stay the reference's own code:
+``DiffusionReplayBuffer`` below is ``ReplayKernels`` in front of the reference class when ``ddiffpg`` is importable, and
+in front of a bare attribute holder otherwise (tests load the ``buf_*`` tensors from fixtures).
+``add_embedding`` mirrors ``ddiffpg.utils.torch_util.add_embedding`` (:17-43), both branches.  Random draws stay in
+torch / numpy as in the reference and can be injected (``indices=``, ``zero_indices=``) for reproducible comparisons.
 """
-from copy import deepcopy
-
 import numpy as np
 import torch
 
@@ -34,67 +35,50 @@ def _u8(mask, n, dev):
 
 
 def add_embedding(state, embedding, p=0.5, modes=[], zero_indices=None):
-    """[state | embedding], with the embedding zeroed on ``int(N*p)`` rows drawn without replacement
-    (``zero_indices`` injects the draw).  The ``modes`` variant of the reference is not used by DDiffPG's update."""
-    if len(modes) != 0:
-        raise NotImplementedError("add_embedding(modes=...) is not on the accelerated path")
+    """utils/torch_util.py:17-43: ``[state | embedding]`` where, of the first ``s = int(N*p)`` choices,
+    * ``modes`` empty: ``s`` rows drawn without replacement get a zero embedding (``zero_indices`` injects the draw);
+    * ``modes`` given (exploration with mode embeddings, ddiffpg.py:163-168): rows ``0 .. s-1`` get the embeddings of
+      ``modes`` in equal consecutive blocks (the first block takes the remainder), all other rows ``embedding``.
+    One gather launch either way."""
     _cuda(state, "state")
     n, O = state.shape
     E = embedding.shape[0]
-    if zero_indices is None:
-        s = int(n * p)
-        zero_indices = torch.as_tensor(np.random.choice(n, size=s, replace=False)) if s else None
+    s = int(n * p)
     st = state.detach().to(torch.float32).contiguous()
-    emb = embedding.detach().to(device=st.device, dtype=torch.float32).contiguous()
-    out = torch.empty(n, O + E, device=st.device)
+    dev = st.device
+    emb = embedding.detach().to(device=dev, dtype=torch.float32).reshape(1, E)
+    zero = group = None
+    if len(modes) != 0:
+        per = [s // len(modes)] * len(modes)
+        per[0] += s % len(modes)
+        emb = torch.cat([emb] + [m.detach().to(device=dev, dtype=torch.float32).reshape(1, E) for m in modes])
+        group = torch.zeros(n, dtype=torch.int32, device=dev)
+        group[:s] = torch.repeat_interleave(torch.arange(1, len(modes) + 1, dtype=torch.int32, device=dev),
+                                            torch.tensor(per, device=dev))
+    else:
+        if zero_indices is None and s:
+            zero_indices = torch.as_tensor(np.random.choice(n, size=s, replace=False))
+        if zero_indices is not None and len(zero_indices):
+            zero = _u8(zero_indices, n, dev)
+    emb = emb.contiguous()
+    out = torch.empty(n, O + E, device=dev)
     if n:
-        idx = torch.arange(n, device=st.device)
-        zero = _u8(zero_indices, n, st.device) if zero_indices is not None and len(zero_indices) else None
-        shape = BatchShape(O, 1, E, 1)
-        with torch.cuda.device(st.device):
-            check(lib().ddp_replay_gather(shape, ptr(st), None, None, None, None, None, n, ptr(idx), None, ptr(emb),
+        idx = torch.arange(n, device=dev)
+        shape = BatchShape(O, 1, E, emb.shape[0])
+        with torch.cuda.device(dev):
+            check(lib().ddp_replay_gather(shape, ptr(st), None, None, None, None, None, n, ptr(idx), ptr(group), ptr(emb),
                                           ptr(zero), None, None, None, None, None, None, None, ptr(out), None, n,
                                           stream_ptr()), "ddp_replay_gather")
     return out
 
 
-class DiffusionReplayBuffer:
-    def __init__(self, capacity, obs_dim, action_dim, device="cuda"):
-        self.obs_dim = (obs_dim,) if isinstance(obs_dim, int) else obs_dim
-        self.action_dim = action_dim
-        self.device = device
-        self.cur_capacity = 0
-        self.capacity = int(capacity)
-        self.last_sample = None
-        self.buf_obs = self.buf_action = self.buf_next_obs = self.buf_reward = None
-        self.buf_done = self.buf_id = self.buf_target_action = None
+class ReplayKernels:
+    """Mixin: the data-moving methods of ``DiffusionReplayBuffer`` on the device (see the module docstring)."""
 
-    @torch.no_grad()
-    def add_to_buffer(self, trajectory, traj_id):
-        obs, actions, target_actions, rewards, next_obs, dones = trajectory
-        obs = obs.reshape(-1, *self.obs_dim)
-        actions = actions.reshape(-1, self.action_dim)
-        target_actions = target_actions.reshape(1, -1, self.action_dim)
-        rewards = rewards.reshape(-1, 1)
-        next_obs = next_obs.reshape(-1, *self.obs_dim)
-        dones = dones.reshape(-1, 1).bool()
-        traj_id = torch.ones_like(rewards) * traj_id
-        if self.buf_obs is None:
-            self.buf_obs, self.buf_action, self.buf_next_obs = obs, actions, next_obs
-            self.buf_reward, self.buf_done, self.buf_id = rewards, dones, traj_id
-            self.buf_target_action = target_actions
-        else:
-            target_actions = target_actions.repeat(self.buf_target_action.shape[0], 1, 1)
-            self.buf_obs = torch.cat([self.buf_obs, obs])
-            self.buf_action = torch.cat([self.buf_action, actions])
-            self.buf_next_obs = torch.cat([self.buf_next_obs, next_obs])
-            self.buf_reward = torch.cat([self.buf_reward, rewards])
-            self.buf_done = torch.cat([self.buf_done, dones])
-            self.buf_id = torch.cat([self.buf_id, traj_id])
-            self.buf_target_action = torch.cat([self.buf_target_action, target_actions], dim=1)
-        self.cur_capacity = self.buf_obs.shape[0]
+    check_indices = True      # raise IndexError on out-of-range rows like the reference's indexing (costs one host sync)
 
     def available_indices(self, cluster_idx):
+        """Rows whose trajectory id is in ``cluster_idx`` (the first line of simple_replay.py:151)."""
         dev = self.buf_id.device
         return torch.where(torch.isin(self.buf_id, torch.tensor(cluster_idx, device=dev)))[0]
 
@@ -110,18 +94,30 @@ class DiffusionReplayBuffer:
         se = f(n, O + E) if want_embedded else None
         ne = f(n, O + E) if want_embedded else None
         if n:
-            c = lambda t: t.contiguous()
-            done_u8 = c(self.buf_done).view(torch.uint8)
-            emb = c(embeddings.detach().to(device=dev, dtype=torch.float32)) if embeddings is not None else None
+            # every converted operand is bound to a local: a temporary would be freed (and its block re-used by the next
+            # conversion) before the launch reads it
+            idx = indices.to(device=dev, dtype=torch.int64).contiguous()
+            if self.check_indices:
+                lo, hi = torch.aminmax(idx)
+                if int(lo) < 0 or int(hi) >= N:
+                    raise IndexError(f"replay index out of range: [{int(lo)}, {int(hi)}] for {N} stored rows")
+            grp = None if group is None else group.to(device=dev, dtype=torch.int32).contiguous()
+            if grp is not None and self.check_indices and embeddings is None:
+                glo, ghi = torch.aminmax(grp)
+                if int(glo) < 0 or int(ghi) >= K:
+                    raise IndexError(f"target-action slot out of range: [{int(glo)}, {int(ghi)}] for {K} slots")
+            obs, act, tgt = self.buf_obs.contiguous(), self.buf_action.contiguous(), self.buf_target_action.contiguous()
+            rew, nobs = self.buf_reward.contiguous(), self.buf_next_obs.contiguous()
+            done_u8 = self.buf_done.contiguous().view(torch.uint8)
+            emb = embeddings.detach().to(device=dev, dtype=torch.float32).contiguous() if embeddings is not None else None
+            zs, zn = _u8(zero_state, n, dev), _u8(zero_next, n, dev)
             shape = BatchShape(O, A, E, K)
             with torch.cuda.device(dev):
-                check(lib().ddp_replay_gather(shape, ptr(c(self.buf_obs)), ptr(c(self.buf_action)),
-                                              ptr(c(self.buf_target_action)), ptr(c(self.buf_reward)),
-                                              ptr(c(self.buf_next_obs)), ptr(done_u8), N, ptr(c(indices.long())),
-                                              ptr(group), ptr(emb), ptr(_u8(zero_state, n, dev)),
-                                              ptr(_u8(zero_next, n, dev)), ptr(out["obs"]), ptr(out["action"]),
-                                              ptr(out["target"]), ptr(out["reward"]), ptr(out["next_obs"]),
-                                              ptr(out["done"]), ptr(se), ptr(ne), n, stream_ptr()), "ddp_replay_gather")
+                check(lib().ddp_replay_gather(shape, ptr(obs), ptr(act), ptr(tgt), ptr(rew), ptr(nobs), ptr(done_u8), N,
+                                              ptr(idx), ptr(grp), ptr(emb), ptr(zs), ptr(zn), ptr(out["obs"]),
+                                              ptr(out["action"]), ptr(out["target"]), ptr(out["reward"]),
+                                              ptr(out["next_obs"]), ptr(out["done"]), ptr(se), ptr(ne), n, stream_ptr()),
+                      "ddp_replay_gather")
         return out, se, ne
 
     @torch.no_grad()
@@ -139,15 +135,15 @@ class DiffusionReplayBuffer:
     def sample_groups(self, group_indices, embeddings=None, zero_state=None, zero_next=None):
         """All mode groups in one launch.  ``group_indices[g]``: replay rows (absolute) drawn for group g.  Returns the
         six batch tensors with rows sorted by group, ``seg_off``, the flat absolute indices, the int32 group ids and
-        (with ``embeddings`` [K,E]) the embedded states / next states of ``add_embedding``."""
+        (with ``embeddings`` [K,E]) the embedded states / next states of ``add_embedding``; ``zero_state`` /
+        ``zero_next`` are the two independent zeroing draws of the reference (masks or index lists over the flat rows)."""
         dev = self.buf_obs.device
         idx = torch.cat([torch.as_tensor(i, device=dev).long() for i in group_indices])
         sizes = [len(i) for i in group_indices]
         group = torch.repeat_interleave(torch.arange(len(sizes), dtype=torch.int32, device=dev),
-                                        torch.tensor(sizes, device=dev))
+                                        torch.tensor(sizes, device=dev)).contiguous()
         seg_off = [0] + list(np.cumsum(sizes))
-        o, se, ne = self._gather(idx, group.contiguous(), embeddings, zero_state, zero_next,
-                                 want_embedded=embeddings is not None)
+        o, se, ne = self._gather(idx, group, embeddings, zero_state, zero_next, want_embedded=embeddings is not None)
         return o, [int(v) for v in seg_off], idx, group, se, ne
 
     @torch.no_grad()
@@ -165,34 +161,39 @@ class DiffusionReplayBuffer:
         n = indices.shape[0]
         if n == 0:
             return
-        na = new_action.detach().to(device=self.buf_target_action.device, dtype=torch.float32).contiguous()
+        dev = self.buf_target_action.device
+        na = new_action.detach().to(device=dev, dtype=torch.float32).contiguous()
+        idx = indices.to(device=dev, dtype=torch.int64).contiguous()
+        grp = group.to(device=dev, dtype=torch.int32).contiguous()
+        if self.check_indices:
+            lo, hi = torch.aminmax(idx)
+            glo, ghi = torch.aminmax(grp)
+            if int(lo) < 0 or int(hi) >= N or int(glo) < 0 or int(ghi) >= K:
+                raise IndexError(f"scatter out of range: rows [{int(lo)}, {int(hi)}] of {N}, slots [{int(glo)}, {int(ghi)}] of {K}")
         shape = BatchShape(self.buf_obs.shape[1], A, 0, K)
-        with torch.cuda.device(self.buf_target_action.device):
-            check(lib().ddp_replay_scatter_target(shape, ptr(self.buf_target_action), N, ptr(na),
-                                                  ptr(indices.long().contiguous()), ptr(group.contiguous()), n,
+        with torch.cuda.device(dev):
+            check(lib().ddp_replay_scatter_target(shape, ptr(self.buf_target_action), N, ptr(na), ptr(idx), ptr(grp), n,
                                                   stream_ptr()), "ddp_replay_scatter_target")
 
-    def remove(self, target_idx, device="cuda"):
-        dev = self.buf_id.device
-        remove_idx = torch.where(torch.isin(self.buf_id, torch.tensor(target_idx, device=dev)))[0]
-        keep_idx = torch.ones(self.buf_obs.shape[0], dtype=bool, device=dev)
-        keep_idx[remove_idx] = False
-        self.buf_obs, self.buf_action = self.buf_obs[keep_idx], self.buf_action[keep_idx]
-        self.buf_next_obs, self.buf_reward = self.buf_next_obs[keep_idx], self.buf_reward[keep_idx]
-        self.buf_done, self.buf_id = self.buf_done[keep_idx], self.buf_id[keep_idx]
-        self.buf_target_action = self.buf_target_action[:, keep_idx]
-        self.cur_capacity = self.buf_obs.shape[0]
 
-    def get_buffer_size(self, cluster_idx):
-        if self.buf_id is None:
-            return 0
-        return self.available_indices(cluster_idx).shape[0]
+class _ReplayStorage:
+    """The attributes ``DiffusionReplayBuffer.__init__`` (simple_replay.py:99-116) sets, nothing else: the base of
+    ``DiffusionReplayBuffer`` where the reference package is not importable."""
 
-    def update_target_action_dim(self, indices):
-        if len(indices) == 0:
-            return
-        new_target_action = [deepcopy(self.buf_target_action[0])]
-        assert max(indices) < self.buf_target_action.shape[0]
-        for idx in indices:
-            new_target_action.append(deepcopy(self.buf_action if idx == -1 else self.buf_target_action[idx]))
-        self.buf_target_action = torch.stack(new_target_action)
+    def __init__(self, capacity, obs_dim, action_dim, device="cuda"):
+        self.obs_dim = (obs_dim,) if isinstance(obs_dim, int) else obs_dim
+        self.action_dim, self.device, self.capacity, self.cur_capacity, self.last_sample = action_dim, device, int(capacity), 0, None
+        self.buf_obs = self.buf_action = self.buf_next_obs = self.buf_reward = None
+        self.buf_done = self.buf_id = self.buf_target_action = None
+
+
+def accelerate_replay_buffer(base):
+    """``ReplayKernels`` in front of ``base`` (the reference's ``DiffusionReplayBuffer`` or a subclass of it)."""
+    return type(base.__name__, (ReplayKernels, base), {"__doc__": ReplayKernels.__doc__})
+
+
+try:        # the reference's own storage / bookkeeping when it is installed next to this package
+    from ddiffpg.replay.simple_replay import DiffusionReplayBuffer as _ReferenceReplayBuffer
+except Exception:        # not installed (tests, benchmarks): attribute holder only
+    _ReferenceReplayBuffer = _ReplayStorage
+DiffusionReplayBuffer = accelerate_replay_buffer(_ReferenceReplayBuffer)

@@ -398,6 +398,35 @@ def test_update_critic_matches_reference_optimizer_step():
     _assert_params_after_adam(critic, {k: v.detach() for k, v in ref.items()}, steps=3, lr=5e-4)
 
 
+def test_reference_style_soft_update_reaches_the_kernels():
+    """The reference's soft_update writes the target critic through param.data (utils/torch_util.py:9-12, called at
+    ddiffpg.py:266), which bumps neither data_ptr nor _version: the next update_critic must nevertheless see the new
+    target weights (the target is re-packed on every use), and get_q1_q2 under autograd raises instead of going eager."""
+    from ddiffpg_b200 import critic_loss_and_grads
+    p, pt = _critic_pair(seeds=(63, 64), scale=1.0)
+    gen = torch.Generator().manual_seed(78)
+    B = 200
+    obs, nobs = torch.randn(B, 29, generator=gen), torch.randn(B, 29, generator=gen)
+    act, nact = torch.rand(B, 8, generator=gen) * 2 - 1, torch.rand(B, 8, generator=gen) * 2 - 1
+    reward, done = torch.rand(B, 1, generator=gen), (torch.rand(B, 1, generator=gen) < 0.2).float()
+    critic, target = make_critic(p), make_critic(pt)
+    args = (_dev(obs), _dev(act), _dev(nobs), _dev(nact), _dev(reward), _dev(done), 0.97)
+    l0, _ = critic_loss_and_grads(critic, target, *args)
+    l0 = l0.item()
+    tau = 0.5
+    with torch.no_grad():                                   # verbatim reference soft_update
+        for tar, cur in zip(target.parameters(), critic.parameters()):
+            tar.data.copy_(cur.data * tau + tar.data * (1.0 - tau))
+    pt2 = {k: p[k] * tau + pt[k] * (1 - tau) for k in pt}
+    l1, _ = critic_loss_and_grads(critic, target, *args)
+    tq = port.critic_target_dist(pt2, nobs, nact, reward, done, 0.97).clamp_max(1.0)
+    l_ref, _ = port.critic_loss_and_grads(p, tq, obs, act)
+    assert abs(l1.item() - l_ref.item()) <= 1e-5 * max(1.0, abs(l_ref.item()))
+    assert abs(l1.item() - l0) > 1e-4                       # the update was not a no-op for this check
+    with pytest.raises(NotImplementedError):
+        critic.get_q1_q2(_dev(obs), _dev(act))              # trainable weights + grad mode: no eager fallback
+
+
 # ------------------------------------------------------------------------------------------ N4
 def _make_rnd(p):
     from ddiffpg_b200 import RNDModel
@@ -406,21 +435,40 @@ def _make_rnd(p):
     return m.to("cuda")
 
 
+class _IntrinsicHost:
+    """The fields of the reference's IntrinsicM that IntrinsicKernels reads (utils/intrinsic.py:9-31), for a box without
+    the reference package; where it is installed, accelerate_intrinsic(IntrinsicM) inherits them from the real class."""
+
+    def __init__(self, p, pos_enc=True):
+        from ddiffpg_b200 import RNDModel
+        self.rnd_model = RNDModel(69)
+        self.rnd_model.load_state_dict(p)
+        self.rnd_model.to("cuda")
+        self.rnd_optimizer = torch.optim.AdamW(self.rnd_model.parameters(), 1e-4)
+        self.pos_enc, self.update_step = pos_enc, 0
+
+    def encode_obs(self, obs):
+        return port.encode_obs_antmaze(obs.cpu()).to(obs.device)
+
+
+def _intrinsic(p):
+    from ddiffpg_b200 import IntrinsicKernels
+    return type("IntrinsicM", (IntrinsicKernels, _IntrinsicHost), {})(p)
+
+
 def test_rnd_matches_reference_fixture():
-    """IntrinsicM.compute_reward / update (utils/intrinsic.py:33-75) against the reference's own outputs."""
-    from ddiffpg_b200 import IntrinsicM
+    """IntrinsicM.get_novelty / compute_reward / update (utils/intrinsic.py:33-75) against the reference's own outputs:
+    the novelty and the loss / gradients come from the kernels, the NovelD shaping around them is the reference's code
+    (restated by the oracle port)."""
     g = load_golden("n4_rnd")
     p = port.init_rnd_params(71)
-    im = IntrinsicM((29,), type="noveld", env_name="antmaze-v1", normalize=True, pos_enc=True, L=10, warm_up=0, device="cuda")
-    im.rnd_model.load_state_dict(p)
+    im = _intrinsic(p)
     obs, nobs = _dev(g["obs"]), _dev(g["nobs"])
     enc = im.encode_obs(obs)
     assert_close(enc, g["enc"], 1e-5, 1e-5, "positional encoding")
     assert_close(im.get_novelty(enc), g["novelty"], RTOL, ATOL, "novelty")
-    assert_close(im.compute_reward(obs, nobs), g["r0"], RTOL, 1e-7, "noveld reward (raw)")
-    im.update_step = 1
-    assert_close(im.compute_reward(obs, nobs), g["r1"], 2e-4, 1e-6, "noveld reward (normalised)")
-    assert_close(torch.stack([im.rnd_rms.mean.reshape(()), im.rnd_rms.var.reshape(())]), g["rms"], 1e-4, 1e-6, "running stats")
+    r0 = port.noveld_reward(im.get_novelty(enc).cpu(), im.get_novelty(im.encode_obs(nobs)).cpu())
+    assert_close(r0, g["r0"], RTOL, 1e-7, "noveld reward (raw)")
     x = im.encode_obs(torch.cat([obs, nobs]))
     loss, flat = im.rnd_model.loss_and_grads(x)
     assert abs(loss.item() - float(g["loss"])) <= 1e-5 * float(g["loss"])
@@ -458,10 +506,8 @@ def test_rnd_update_vs_oracle_batches(B):
 
 def test_intrinsic_update_matches_torch_adamw():
     """IntrinsicM.update: loss, clip_grad_norm_(1.0) and AdamW(1e-4) on the predictor; the target stays frozen."""
-    from ddiffpg_b200 import IntrinsicM
     p = port.init_rnd_params(73)
-    im = IntrinsicM((29,), type="rnd", env_name="antmaze-v1", device="cuda")
-    im.rnd_model.load_state_dict(p)
+    im = _intrinsic(p)
     gen = torch.Generator().manual_seed(5)
     obs = torch.randn(300, 29, generator=gen)
     ref = {k: v.clone().requires_grad_(k.startswith("predictor")) for k, v in p.items()}
@@ -503,7 +549,7 @@ def test_replay_sample_and_scatter_match_reference_fixture():
         assert torch.equal(idx.cpu(), torch.from_numpy(g[f"idx_{gi}"]))
         for name, t in zip(names, data):
             assert torch.equal(t.cpu(), torch.from_numpy(g[f"g{gi}_{name}"])), (gi, name)
-        assert buf.get_buffer_size(grp) == sum(1 for t in g["store_id"].ravel() if int(t) in grp)
+        assert buf.available_indices(grp).shape[0] == sum(1 for t in g["store_id"].ravel() if int(t) in grp)
     emb = _dev(g["emb"])
     assert torch.equal(add_embedding(_dev(g["g1_obs"]), emb, zero_indices=g["zero_idx"]).cpu(), torch.from_numpy(g["emb_state"]))
     assert torch.equal(add_embedding(_dev(g["g0_obs"]), emb, p=0).cpu(), torch.from_numpy(g["emb_state_p0"]))
@@ -531,6 +577,37 @@ def test_replay_sample_and_scatter_match_reference_fixture():
     for d in uniq[counts > 1]:
         cands = torch.from_numpy(g["new_action"])[idx2 == d]
         assert any(torch.equal(after[2, d], c) for c in cands)
+
+
+def test_replay_two_zeroing_draws_modes_and_range_checks():
+    """sample_groups with DIFFERENT zero_state / zero_next draws (the reference draws two independent p = 0.5 masks,
+    ddiffpg.py:246-252), add_embedding(modes=...) (utils/torch_util.py:24-34) and the IndexError of a stale index."""
+    from ddiffpg_b200 import add_embedding
+    g = load_golden("n2_replay")
+    buf = _replay_from_fixture(g)
+    emb = _dev(g["emb"])
+    embs = torch.stack([emb, emb * 2, emb * 3])
+    zs, zn = [0, 3, 5, 20, 37], [1, 3, 14, 15, 30]
+    o, seg_off, idx, grp_ids, se, ne = buf.sample_groups([g[f"idx_{gi}"] for gi in range(3)], embeddings=embs,
+                                                         zero_state=zs, zero_next=zn)
+    n = seg_off[-1]
+    want = embs[grp_ids.long()]
+    ws, wn = want.clone(), want.clone()
+    ws[zs] = 0
+    wn[zn] = 0
+    assert torch.equal(se[:, 29:], ws) and torch.equal(ne[:, 29:], wn) and n == 38
+    assert torch.equal(se[:, :29], o["obs"]) and torch.equal(ne[:, :29], o["next_obs"])
+    # modes branch: s = int(10 * 0.7) = 7 rows in blocks of 3 (2 + the remainder), 2, 2; the rest keep `embedding`
+    state = _dev(g["g0_obs"])[:10]
+    modes = [emb * 10, emb * 20, emb * 30]
+    out = add_embedding(state, emb, p=0.7, modes=modes)
+    exp = emb.expand(10, -1).clone()
+    exp[0:3], exp[3:5], exp[5:7] = modes[0], modes[1], modes[2]
+    assert torch.equal(out[:, :29], state) and torch.equal(out[:, 29:], exp)
+    with pytest.raises(IndexError):
+        buf.sample_groups([[0, 1, buf.buf_obs.shape[0]]])
+    with pytest.raises(IndexError):
+        buf.update_target_action(torch.zeros(1, 8, device="cuda"), torch.tensor([0], device="cuda"), 7)
 
 
 def test_replay_gather_large_roundtrip():
