@@ -67,6 +67,10 @@ struct TcArgs {
     int nparts1, part1;        // layer-1 output split into nparts1 parts of part1 (<= 256) columns
     int num_tiles;             // tiles of this launch (128 rows each, or 64 in the M = 64 kernel)
     long row0;                 // first row of this launch
+    int split_steps;           // 1: the T steps of a tile may be shared by two neighbouring CTAs (see Job)
+    uint4* pshare;             // [grid] state-partial blocks of the tiles shared by two CTAs (written by the head's CTA)
+    float* handoff;            // [grid][128][8] fp32: x_t of the tile a CTA leaves unfinished, for its right neighbour
+    int* handoff_flag;         // [grid] zeroed before the launch; 1 once handoff[b] is complete
     ExplNoise expl;            // optional exploration / target-policy noise epilogue
     long long* dbg;            // optional per-phase cycle counters of CTA 0 (development aid), else NULL
 };
@@ -104,6 +108,41 @@ struct Ring {
     __device__ __forceinline__ void advance(int n) { if (++idx == n) { idx = 0; phase ^= 1; } }
 };
 
+// Work assignment.  The unit of work is one denoising step of one tile.  Without `split_steps` CTA b owns whole tiles
+// b, b + grid, ...  With it (large batches whose tile count is not a multiple of the grid: 512 tiles on 148 SMs are
+// 3.46 waves that cost 4) the num_tiles * T units are dealt out in contiguous, balanced ranges of the tile-major order,
+// so a CTA's range may begin and / or end inside a tile.  Such a tile is shared with the neighbouring CTA through
+// x_t (128 x 8 floats in global memory, one release / acquire flag): the CTA runs the unfinished HEAD of its last tile
+// FIRST, then its whole tiles, and the TAIL of its first tile LAST -- by then the left neighbour, which started with
+// exactly that head, has long published it, so nobody ever waits.  The second CTA recomputes the per-tile state partial
+// of layer 0 (~0.1 step).  The host only enables this when every range spans at least two tiles (no piece is both).
+struct Job { int tile, j0, j1; bool head, tail; };      // steps j0..j1; head: ends before T-1 (publishes x_t); tail: starts after 0
+struct Schedule {
+    int b, grid, num_tiles, T, split;
+    int f, js, l, je, full0, full1, njobs;
+    __device__ __forceinline__ Schedule(const TcArgs& a) {
+        b = blockIdx.x; grid = gridDim.x; num_tiles = a.num_tiles; T = a.T; split = a.split_steps;
+        if (split) {
+            const long units = (long)num_tiles * T, base = units / grid, rem = units % grid;
+            const long lo = b * base + (b < rem ? b : rem), hi = lo + base + (b < rem ? 1 : 0);
+            f = (int)(lo / T); js = (int)(lo % T); l = (int)((hi - 1) / T); je = (int)((hi - 1) % T);
+            full0 = js > 0 ? f + 1 : f;
+            full1 = je < T - 1 ? l - 1 : l;                 // inclusive
+            njobs = (je < T - 1 ? 1 : 0) + (full1 - full0 + 1) + (js > 0 ? 1 : 0);
+        } else {
+            njobs = b < num_tiles ? (num_tiles - b + grid - 1) / grid : 0;
+        }
+    }
+    __device__ __forceinline__ Job job(int i) const {
+        if (!split) return Job{b + i * grid, 0, T - 1, false, false};
+        const int has_head = je < T - 1 ? 1 : 0;
+        if (has_head && i == 0) return Job{l, 0, je, true, false};
+        const int k = i - has_head, nfull = full1 - full0 + 1;
+        if (k < nfull) return Job{full0 + k, 0, T - 1, false, false};
+        return Job{f, js, T - 1, false, true};
+    }
+};
+
 // Per-thread state of an epilogue / layer-0 warp.
 struct EpiCtx {
     uint8_t* smem;
@@ -111,11 +150,39 @@ struct EpiCtx {
     int q, ch, g, t4, lane, my_row;     // TMEM lane quarter, column group of the chunk, mma.sync coords, owned row
     int NC1, NC2, NC3;
     Ring as;
+    uint4* pscr_base;                   // state-partial block of the current job (private, or shared with the neighbour)
     long row;
     bool valid;
     bool owner;                         // this thread owns a row of the tile (64-row tiles: lanes 0..15 only)
     float xr[8];                        // x_t of the owned row (ch == 0 threads), fp32
 };
+
+// Tile prologue form of write_in0_row: the whole [x (8) | state (S <= 40) | 0] row.  All loads of the row are issued
+// before the first conversion (8-byte loads when S is even): the row costs one memory round trip, not one per element
+// (the plain loop below, with its run-time trip count, measured 4.5 k clk per tile).
+template <bool F16>
+__device__ __forceinline__ void write_in0_row_full(const TcArgs& a, const EpiCtx& e) {
+    if (!e.owner) return;
+    constexpr int NS = kK0 - 8;
+    float sv[NS];
+    const float* sp = a.state + e.row * a.S;
+    if ((a.S & 1) == 0) {
+#pragma unroll
+        for (int i = 0; i < NS; i += 2) {
+            const float2 v = (e.valid && i + 1 < a.S) ? __ldg(reinterpret_cast<const float2*>(sp + i)) : make_float2(0.f, 0.f);
+            sv[i] = v.x; sv[i + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) sv[i] = (e.valid && i < a.S) ? __ldg(sp + i) : 0.f;
+    }
+    uint4* rp = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.smem + SM::in0) + e.my_row * kIn0Stride);
+    rp[0] = make_uint4(pack2<F16>(e.xr[0], e.xr[1]), pack2<F16>(e.xr[2], e.xr[3]), pack2<F16>(e.xr[4], e.xr[5]), pack2<F16>(e.xr[6], e.xr[7]));
+#pragma unroll
+    for (int g = 0; g < NS / 8; ++g)
+        rp[1 + g] = make_uint4(pack2<F16>(sv[8 * g], sv[8 * g + 1]), pack2<F16>(sv[8 * g + 2], sv[8 * g + 3]),
+                               pack2<F16>(sv[8 * g + 4], sv[8 * g + 5]), pack2<F16>(sv[8 * g + 6], sv[8 * g + 7]));
+}
 
 // [x (8) | state (S) | 0 ...] of the owned row into the layer-0 input tile, in the operand format F16/bf16
 template <bool F16>
@@ -275,9 +342,11 @@ __device__ __forceinline__ void drain_acc_m64(EpiCtx& e, int nchunks, const floa
     }
 }
 
-// Scratch slot of this lane for chunk c: 4 x 16 B, [c][warp][j][lane] so that every access is one coalesced 512 B row
+// Scratch slot of this lane for chunk c: 4 x 16 B, [c][warp][j][lane] so that every access is one coalesced 512 B row.
+// The layout depends on (warp, lane) only, so the block a CTA writes for the head of a shared tile serves the same
+// threads of the neighbouring CTA that finishes the tile.
 __device__ __forceinline__ uint4* pscr_slot(const TcArgs& a, const EpiCtx& e, int c) {
-    return a.pscr + ((size_t)blockIdx.x * e.NC1 + c) * (kEpiWarps * 4 * 32) + (e.q + 4 * e.ch) * (4 * 32) + e.lane;
+    return e.pscr_base + (size_t)c * (kEpiWarps * 4 * 32) + (e.q + 4 * e.ch) * (4 * 32) + e.lane;
 }
 
 // Tile prologue: P = W0[:, state[8:]] . state[8:] for the 32 rows x kColsPerWarp features this warp owns in every
@@ -333,41 +402,57 @@ __device__ __forceinline__ void state_partial(const TcArgs& a, const EpiCtx& e) 
     }
 }
 
+// Layer-0 operands of one chunk that do not depend on x_t: W0 fragments of the [x_t | state[0:8]] k16 step, the
+// time-table pair of each n8 tile and the parked state partial.  Chunk 0 of a step is fetched BEFORE the previous step's
+// head (nothing in it depends on the new x_t), so its L2 latency hides behind the layer-3 MMA wait and the scheduler math.
+struct L0Frags {
+    uint2 bfr[kNT];
+    float2 bias[kNT];
+    uint4 pp[4];
+};
+template <bool F16, bool HM>
+__device__ __forceinline__ void load_l0_frags(const TcArgs& a, const EpiCtx& e, int t, int c, L0Frags& fr) {
+    constexpr int MT = HM ? 1 : 2;
+    // packed fragment order: [chunk][32-feature half][n8 tile 0..3][k16 step][lane]; this warp's first feature inside
+    // the chunk is ch * kColsPerWarp
+    const float* tb = a.tb0 + (size_t)t * a.h1;
+    const uint2* wf = F16 ? a.w0frag_h : a.w0frag;
+    const int n8 = e.ch * kNT;                              // first n8 tile (0..7) of this warp in the chunk
+    const uint2* bf = wf + ((size_t)(c * 8 + n8) * 3) * 32 + e.lane;
+#pragma unroll
+    for (int nt = 0; nt < kNT; ++nt) fr.bfr[nt] = __ldg(bf + (nt * 3) * 32);
+#pragma unroll
+    for (int nt = 0; nt < kNT; ++nt)
+        fr.bias[nt] = __ldg(reinterpret_cast<const float2*>(tb + c * 64 + e.ch * kColsPerWarp + nt * 8 + 2 * e.t4));
+    const uint4* ps = pscr_slot(a, e, c);
+#pragma unroll
+    for (int j = 0; j < 2 * MT; ++j) fr.pp[j] = __ldcg(ps + j * 32);
+}
+
 // One denoising step of the epilogue warps (operand format of THIS step = F16 ? fp16 : bf16; H2: the TMEM drains run
 // the packed-fp16 Mish -- every step but the first, whose eps_hat error is amplified by 1/sqrt(abar_{T-1})).
-template <bool F16, bool HM, bool H2 = false>
-__device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
+// `fr` arrives holding chunk 0 of this step and leaves holding chunk 0 of the next one (`has_next`).
+template <bool F16, bool HM, bool H2 = false, bool H2_ACC2 = H2>
+__device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j, L0Frags& fr, bool has_next) {
     constexpr int MT = HM ? 1 : 2;
     const int t = a.T - 1 - j;
+#ifdef DDP_TC_PROFILE      // per-phase cycle counters of CTA 0 (tools/tc_timing.py builds this variant): registers the product does not pay for
     const bool prof = a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long tk0 = prof ? clock64() : 0, tk1;
 #define DDP_TICK(slot) do { if (prof) { tk1 = clock64(); a.dbg[slot] += tk1 - tk0; tk0 = tk1; } } while (0)
+#else
+#define DDP_TICK(slot) do { } while (0)
+#endif
     // ---- layer 0: one 64-feature chunk at a time, straight into the A ring.  accumulator = state partial of the
     // tile (scratch, fp16) + time-table row + one k16 step over [x_t | state[0:8]]
     const uint32_t in0_lane = in0_lane_addr<HM>(e);
     uint32_t afx[MT][4];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) ldmatrix_x4(afx[mt], in0_lane + (uint32_t)((mt * 16 * kIn0Stride) * 2));
-    const float* tb = a.tb0 + (size_t)t * a.h1;
-    const uint2* wf = F16 ? a.w0frag_h : a.w0frag;
-    uint2 bfr[kNT];
-    float2 bias[kNT];
-    uint4 pp[2 * MT];
-    // packed fragment order: [chunk][32-feature half][n8 tile 0..3][k16 step][lane]; this warp's first
-    // feature inside the chunk is ch * kColsPerWarp
-    auto load_frags = [&](int c) {
-        const int n8 = e.ch * kNT;                              // first n8 tile (0..7) of this warp in the chunk
-        const uint2* bf = wf + ((size_t)(c * 8 + n8) * 3) * 32 + e.lane;
-#pragma unroll
-        for (int nt = 0; nt < kNT; ++nt) bfr[nt] = __ldg(bf + (nt * 3) * 32);
-#pragma unroll
-        for (int nt = 0; nt < kNT; ++nt)
-            bias[nt] = __ldg(reinterpret_cast<const float2*>(tb + c * 64 + e.ch * kColsPerWarp + nt * 8 + 2 * e.t4));
-        const uint4* ps = pscr_slot(a, e, c);
-#pragma unroll
-        for (int j = 0; j < 2 * MT; ++j) pp[j] = __ldcg(ps + j * 32);
-    };
-    load_frags(0);
+    uint2 (&bfr)[kNT] = fr.bfr;
+    float2 (&bias)[kNT] = fr.bias;
+    uint4 (&pp)[4] = fr.pp;
+    auto load_frags = [&](int c) { load_l0_frags<F16, HM>(a, e, t, c, fr); };
     int pending0 = -1;
     for (int c = 0; c < e.NC1; ++c) {
         float acc[MT][kNT][4];
@@ -436,23 +521,26 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, EpiCtx& e, int j) {
     mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
     tc_fence_after();
     DDP_TICK(3);       // wait for the last layer-2 MMA
-    if constexpr (HM) drain_acc_m64<F16, H2>(e, e.NC3, sb2, sb2h, -1);
-    else drain_acc<F16, H2>(e, e.NC3, sb2, sb2h, -1);
+    if constexpr (HM) drain_acc_m64<F16, H2_ACC2>(e, e.NC3, sb2, sb2h, -1);
+    else drain_acc<F16, H2_ACC2>(e, e.NC3, sb2, sb2h, -1);
     DDP_TICK(4);       // drain acc2
 
-    // ---- head + scheduler step: eps_hat from acc3, x_t in registers (fp32)
-    mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
-    tc_fence_after();
-    DDP_TICK(5);       // wait for layer 3
+    // ---- head + scheduler step: eps_hat from acc3, x_t in registers (fp32).  Everything the head and the next step's
+    // first chunk need from global memory is requested before the wait for the layer-3 MMA: the step noise and head bias
+    // of the owned row, and chunk 0 of the next step's layer-0 operands (kernel-format next step: F16 again under kH2)
+    float zr[8], b3r[8];
     if (e.ch == 0) {
-        // step noise and head bias of the owned row (loaded here: keeping them live across the drains costs
-        // 16 registers for ~500 cycles of exposed latency per step)
-        float zr[8], b3r[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             zr[i] = (e.valid && t > 0 && i < a.A) ? __ldg(a.noise + ((size_t)(j + 1) * a.B + e.row) * a.A + i) : 0.f;
             b3r[i] = i < a.A ? __ldg(a.b3 + i) : 0.f;
         }
+    }
+    if (has_next) load_l0_frags<kH2 ? true : false, HM>(a, e, t - 1, 0, fr);
+    mbar_wait(bar_acc_full(e.bars), e.acc_phase); e.acc_phase ^= 1;
+    tc_fence_after();
+    DDP_TICK(5);       // wait for layer 3
+    if (e.ch == 0) {
         uint32_t ev[8];
         tmem_ld8(e.tmem_base + ((uint32_t)(e.q * 32) << 16) + a.h3, ev);
         tmem_ld_wait();
@@ -538,8 +626,10 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
             tma_prefetch_desc(&map_w1h);
             tma_prefetch_desc(&map_w2h);
             Ring ws;
-            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-                for (int j = 0; j < a.T; ++j) {
+            const Schedule sch(a);
+            for (int ji = 0; ji < sch.njobs; ++ji) {
+                const Job jb = sch.job(ji);
+                for (int j = jb.j0; j <= jb.j1; ++j) {
                     const bool f16 = kH2 || (a.first_f16 && j == 0);
                     const CUtensorMap* m1 = f16 ? &map_w1h : &map_w1;
                     const CUtensorMap* m2 = f16 ? &map_w2h : &map_w2;
@@ -565,8 +655,10 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
         if (lane == 0) {
             Ring ws, as;
             uint32_t lo_phase = 0;
-            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-                for (int j = 0; j < a.T; ++j) {
+            const Schedule sch(a);
+            for (int ji = 0; ji < sch.njobs; ++ji) {
+                const Job jb = sch.job(ji);
+                for (int j = jb.j0; j <= jb.j1; ++j) {
                     const bool f16 = kH2 || (a.first_f16 && j == 0);
                     constexpr int M = HM ? 64 : kRows;
                     const uint32_t idesc1 = make_idesc_16(M, a.part1, f16);
@@ -634,7 +726,15 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
         e.q = warp & 3; e.ch = warp >> 2; e.g = lane >> 2; e.t4 = lane & 3; e.lane = lane;
         e.NC1 = NC1; e.NC2 = NC2; e.NC3 = NC3;
         e.acc_phase = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const Schedule sch(a);
+#ifdef DDP_TC_PROFILE
+        const bool prof = a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+        long long pc0 = 0, pt0 = 0;
+        if (prof) { pc0 = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(pt0)); }
+#endif
+        for (int ji = 0; ji < sch.njobs; ++ji) {
+            const Job jb = sch.job(ji);
+            const int tile = jb.tile;
             if (!HM) {
                 e.my_row = e.q * 32 + lane;
                 e.owner = true;
@@ -645,24 +745,91 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
                 e.row = a.row0 + (long)tile * 64 + e.my_row;
             }
             e.valid = e.owner && e.row < a.B;
+            {
+                const size_t per_cta = (size_t)e.NC1 * kEpiWarps * 4 * 32;
+                e.pscr_base = jb.head ? a.pshare + (size_t)blockIdx.x * per_cta
+                            : jb.tail ? a.pshare + (size_t)(blockIdx.x - 1) * per_cta
+                                      : a.pscr + (size_t)blockIdx.x * per_cta;
+            }
+#ifdef DDP_TC_PROFILE
+            long long pq0 = prof ? clock64() : 0;
+#endif
             // ---- tile prologue: x_T -> registers; [x | state | 0] -> in0 in the first step's operand format
+            if (jb.tail) {
+                // the left neighbour ran steps 0 .. j0-1 of this tile first thing: its x_t has been waiting for a while
+                if (threadIdx.x == 0) {
+                    const int* flag = a.handoff_flag + (blockIdx.x - 1);
+                    int v, spins = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                        if (!v && ++spins > (1 << 26)) asm volatile("trap;");       // a protocol bug must not hang the box
+                    } while (!v);
+                }
+                epi_bar_sync();
+            }
             if (e.ch == 0) {
+                const float* hx = a.handoff + ((size_t)(blockIdx.x - 1) * kRows + e.my_row) * 8;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) e.xr[i] = (e.valid && i < a.A) ? a.noise[e.row * a.A + i] : 0.f;
-                if (kH2 || a.first_f16) write_in0_row<true>(a, e, kK0 - 8); else write_in0_row<false>(a, e, kK0 - 8);
+                for (int i = 0; i < 8; ++i) {
+                    if (jb.tail) e.xr[i] = e.owner ? __ldcg(hx + i) : 0.f;
+                    else e.xr[i] = (e.valid && i < a.A) ? a.noise[e.row * a.A + i] : 0.f;
+                }
+                if (kH2 || a.first_f16) write_in0_row_full<true>(a, e); else write_in0_row_full<false>(a, e);
             }
             epi_bar_sync();
+#ifdef DDP_TC_PROFILE
+            if (prof) { const long long q = clock64(); a.dbg[8] += q - pq0; pq0 = q; }      // x_T / state -> in0, barrier
+#endif
+            L0Frags fr;
             if constexpr (kH2) {
-                state_partial<true, HM>(a, e);
-                epi_step<true, HM, false>(a, e, 0);
-                for (int j = 1; j < a.T; ++j) epi_step<true, HM, true>(a, e, j);
+                if (!jb.tail) state_partial<true, HM>(a, e);       // a tail re-uses the block its left neighbour parked
+#ifdef DDP_TC_PROFILE
+                if (prof) { const long long q = clock64(); a.dbg[9] += q - pq0; a.dbg[10] += 1; }   // state partial; jobs
+#endif
+                load_l0_frags<true, HM>(a, e, a.T - 1 - jb.j0, 0, fr);
+                for (int j = jb.j0; j <= jb.j1; ++j) {
+                    const bool nx = j < jb.j1;
+#if defined(DDP_TC_H2_FIRST) && DDP_TC_H2_FIRST == 2
+                    if (j == 0) epi_step<true, HM, true, false>(a, e, j, fr, nx); else epi_step<true, HM, true>(a, e, j, fr, nx);
+#elif defined(DDP_TC_H2_FIRST)
+                    epi_step<true, HM, true>(a, e, j, fr, nx);
+#else
+                    if (j == 0) epi_step<true, HM, false>(a, e, j, fr, nx); else epi_step<true, HM, true>(a, e, j, fr, nx);
+#endif
+                }
             } else {
-                if (a.first_f16) state_partial<true, HM>(a, e); else state_partial<false, HM>(a, e);
-                for (int j = 0; j < a.T; ++j) {
-                    if (a.first_f16 && j == 0) epi_step<true, HM>(a, e, j); else epi_step<false, HM>(a, e, j);
+                // round-1 plan: the operand format changes after the first step, so does the fragment set: no carry-over
+                if (!jb.tail) { if (a.first_f16) state_partial<true, HM>(a, e); else state_partial<false, HM>(a, e); }
+                for (int j = jb.j0; j <= jb.j1; ++j) {
+                    if (a.first_f16 && j == 0) { load_l0_frags<true, HM>(a, e, a.T - 1 - j, 0, fr); epi_step<true, HM>(a, e, j, fr, false); }
+                    else { load_l0_frags<false, HM>(a, e, a.T - 1 - j, 0, fr); epi_step<false, HM>(a, e, j, fr, false); }
+                }
+            }
+            if (jb.head) {
+                // leave x_t (after step j1) for the right neighbour, which finishes this tile at the end of its range
+                if (e.ch == 0 && e.owner) {
+                    float* hx = a.handoff + ((size_t)blockIdx.x * kRows + e.my_row) * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) __stcg(hx + i, e.xr[i]);
+                }
+                __threadfence();         // every thread: its part of the shared state-partial block travels with x_t
+                epi_bar_sync();
+                if (threadIdx.x == 0) {
+                    int one = 1;
+                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.handoff_flag + blockIdx.x), "r"(one) : "memory");
                 }
             }
         }
+#ifdef DDP_TC_PROFILE
+        if (prof) {     // slots 12..14: cycles and nanoseconds of CTA 0's whole job list, number of tile-steps it ran
+            long long pt1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(pt1));
+            a.dbg[12] += clock64() - pc0; a.dbg[13] += pt1 - pt0;
+            long long units = 0;
+            for (int ji = 0; ji < sch.njobs; ++ji) { const Job jb = sch.job(ji); units += jb.j1 - jb.j0 + 1; }
+            a.dbg[14] += units;
+        }
+#endif
     }
 
     // ------------------------------------------------------------------ teardown
@@ -784,9 +951,19 @@ static TilePlan tile_plan(long B, int sms) {
 }
 
 // state partial sums: one [h1/64][8 warps][4][32 lanes] x 16 B block per resident CTA (256 KB at h1 = 1024)
+// + per CTA of the 128-row launch, for a tile shared with the right neighbour (split_steps): a second state-partial
+// block, the x_t hand-off slot and its flag
+constexpr size_t kHandoffBytes = (size_t)kRows * 8 * sizeof(float);
+static size_t pscr_cta_bytes(const ActorLayout& L) { return (size_t)(L.h1 / 64) * kEpiWarps * 4 * 32 * sizeof(uint4); }
+static size_t pscr_bytes(const ActorLayout& L, const TilePlan& p) { return (size_t)(p.grid_full + p.grid_half) * pscr_cta_bytes(L); }
+// tile-steps are dealt out in balanced contiguous ranges when whole tiles would leave a partial last wave and every
+// range still spans two tiles or more (see Schedule)
+static bool split_steps(const ActorLayout& L, const TilePlan& p) {
+    return p.num_full > p.grid_full && p.num_full % p.grid_full != 0 && ((long)p.num_full * L.T) / p.grid_full >= 2L * L.T;
+}
 size_t actor_sample_tc_workspace(const ActorLayout& L, long B) {
     const TilePlan p = tile_plan(B, tc_sm_count());
-    return (size_t)(p.grid_full + p.grid_half) * (L.h1 / 64) * kEpiWarps * 4 * 32 * sizeof(uint4);
+    return pscr_bytes(L, p) + (split_steps(L, p) ? (size_t)p.grid_full * (pscr_cta_bytes(L) + kHandoffBytes + 64) : 0);
 }
 
 int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state, const float* noise, float* out,
@@ -823,7 +1000,12 @@ int actor_sample_tc(const ActorLayout& L, const void* packed, const float* state
     if (sms <= 0) DDP_FAIL(DDP_ERR_CUDA, "cannot query the SM count");
     const size_t smem = SM::total + 1024;         // slack for the 1024-byte alignment of the base
     const size_t per_cta = (size_t)(L.h1 / 64) * kEpiWarps * 4 * 32;      // uint4 of state-partial scratch per CTA
+    a.split_steps = split_steps(L, plan) ? 1 : 0;
+    a.pshare = (uint4*)((uint8_t*)ws + pscr_bytes(L, plan));
+    a.handoff = (float*)((uint8_t*)a.pshare + (size_t)plan.grid_full * pscr_cta_bytes(L));
+    a.handoff_flag = (int*)((uint8_t*)a.handoff + (size_t)plan.grid_full * kHandoffBytes);
     if (plan.num_full > 0) {
+        if (a.split_steps) DDP_CUDA_CHECK(cudaMemsetAsync(a.handoff_flag, 0, (size_t)plan.grid_full * sizeof(int), st));
         a.num_tiles = plan.num_full; a.row0 = 0; a.pscr = (uint4*)ws;
         DDP_CUDA_CHECK(cudaFuncSetAttribute(actor_sample_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         actor_sample_tc_kernel<false><<<plan.grid_full, kThreads, smem, st>>>(m1, m2, m1h, m2h, a);

@@ -93,13 +93,18 @@ class _ActorLossFn(torch.autograd.Function):
 
 def host_batch_ranges(B, chunks, sms):
     """Row ranges of a host-resident batch for the copy / compute pipeline of ``get_actions_host``.  Below ~8k rows per
-    range the copies are microseconds and extra launches cost more than they hide: one range.  Otherwise ranges are whole
-    waves of the sampler (``sms`` tiles of 128 rows), at most ``chunks`` of them, with the partial wave FIRST: the first
-    launch then waits for the smallest upload, and no range ends in a second partial wave."""
+    range the copies are microseconds and extra launches cost more than they hide: one range.  Up to three waves of the
+    sampler (``sms`` tiles of 128 rows) ranges are whole waves, at most ``chunks`` of them, with the partial wave FIRST:
+    the first launch then waits for the smallest upload, and no range ends in a second partial wave.  Beyond: one wave,
+    then the rest."""
     chunks = max(1, min(chunks, B // 8192))
     if chunks == 1:
         return [(0, B)] if B > 0 else []
     wave = sms * 128
+    if B >= 3 * wave:
+        # large batches: one wave first (its upload is the only exposed one), everything else in a second launch -- the
+        # sampler deals tile-steps out evenly once a launch holds two waves or more, so nothing is lost to a partial wave
+        return [(0, wave), (wave, B)]
     n_waves, rem = divmod(B, wave)
     if n_waves == 0:
         return [(0, B)]
@@ -271,17 +276,24 @@ class DiffusionPolicy(nn.Module):
                 self._ws["h2d"], self._ws["d2h"] = torch.cuda.Stream(), torch.cuda.Stream()
             h2d, d2h = self._ws["h2d"], self._ws["d2h"]
             h2d.wait_stream(main)
-            st_dev = torch.empty((B, state_host.shape[1]), device=dev, dtype=torch.float32)
-            out_dev = torch.empty((B, A), device=dev, dtype=torch.float32)
-            done = []
-            for lo, hi in ranges:
+            stage = self._ws.get("host_stage")
+            if stage is None or stage[0] != (B, state_host.shape[1], T, str(dev)):
+                # staging buffers persist across calls of the same shape (no allocator traffic in the steady state)
+                stage = ((B, state_host.shape[1], T, str(dev)),
+                         torch.empty((B, state_host.shape[1]), device=dev, dtype=torch.float32),
+                         torch.empty((B, A), device=dev, dtype=torch.float32),
+                         [torch.empty((T, hi - lo, A), device=dev, dtype=torch.float32) for lo, hi in ranges])
+                self._ws["host_stage"] = stage
+            _, st_dev, out_dev, noise_bufs = stage
+            main.wait_stream(d2h)              # the previous call's downloads have left out_dev
+            for ri, (lo, hi) in enumerate(ranges):
                 with torch.cuda.stream(h2d):
                     st_dev[lo:hi].copy_(state_host[lo:hi], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(h2d)
                 main.wait_event(ev)
                 n = hi - lo
-                noise = torch.randn((T, n, A), device=dev, dtype=torch.float32)
+                noise = noise_bufs[ri].normal_()
                 ws_bytes = lib().ddp_actor_sample_workspace_bytes(shape, n, prec)
                 ws = self._workspace("sample", ws_bytes, dev) if ws_bytes else None
                 check(lib().ddp_actor_sample(shape, ptr(packed), ptr(st_dev[lo:hi]), ptr(noise), ptr(out_dev[lo:hi]), n,
@@ -291,7 +303,6 @@ class DiffusionPolicy(nn.Module):
                 with torch.cuda.stream(d2h):
                     d2h.wait_event(ev2)
                     out_host[lo:hi].copy_(out_dev[lo:hi], non_blocking=True)
-                done.append(noise)          # keep the buffers alive until the streams have drained
             main.wait_stream(d2h)
             d2h.synchronize()
         return out_host

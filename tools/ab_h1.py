@@ -39,12 +39,11 @@ for B in (65536, 75776):
         pol.get_actions(s, noise=z)
         torch.cuda.synchronize()
         L.ddp_debug_tc_timing(None)
-        tiles = (B + 127) // 128
-        my = len(range(0, tiles, min(tiles, 148)))
-        v = [x / (my * T) for x in buf.tolist()[:7]]
+        raw = buf.tolist()
+        units = max(raw[14], 1)
+        v = [x / units for x in raw[:7]]
         line += f" tile-step {sum(v):6.0f} clk (L0 {v[0]:5.0f} w1 {v[1]:4.0f} d1 {v[2]:5.0f} w2 {v[3]:4.0f} d2 {v[4]:4.0f} w3 {v[5]:4.0f} hd {v[6]:4.0f}) |"
-        u = [x / (my * T * (h // 64)) for x in buf.tolist()[8:12]]
-        line += f" L0 chunk: compute {u[0]:4.0f} slot-wait {u[1]:4.0f} stores {u[2]:4.0f} fence+arrive {u[3]:4.0f} |"
+        line += f" CTA0: {units} units, {raw[12]} clk in {raw[13] / 1e3:.1f} us = {raw[12] / max(raw[13], 1) * 1e3:.0f} MHz, outside steps {(raw[12] - sum(raw[:7])) / max(raw[12], 1):.1%}; {raw[10]} jobs: load+in0 {raw[8] / max(raw[10], 1):.0f} clk, state partial {raw[9] / max(raw[10], 1):.0f} clk per job |"
     meds = []
     for _ in range(3):
         ts = []

@@ -15,7 +15,7 @@ L.ddp_debug_tc_timing(buf.data_ptr())
 pol.get_actions(s, noise=n); torch.cuda.synchronize()
 L.ddp_debug_tc_timing(None)
 names = ["L0+Mish (16 chunks)", "wait acc1", "drain acc1 (8)", "wait acc2", "drain acc2 (4)", "wait acc3", "head+step+bar"]
-tiles = (B + 127) // 128; my = len(range(0, tiles, min(tiles, 148)))
+raw = buf.tolist(); units = max(raw[14], 1)
 tot = int(buf[:7].sum())
-print(f"B={B}: CTA0 ran {my} tiles x {T} steps; total {tot} clk; per tile-step {tot/(my*T):.0f} clk")
-for nm, v in zip(names, buf.tolist()): print(f"  {nm:22s} {v/(my*T):9.0f} clk/tile-step  {100*v/tot:5.1f}%")
+print(f"B={B}: CTA0 ran {units} tile-steps; {tot} clk inside steps; per tile-step {tot/units:.0f} clk; whole job list {raw[12]} clk in {raw[13]/1e3:.1f} us ({raw[12]/max(raw[13],1)*1e3:.0f} MHz)")
+for nm, v in zip(names, raw): print(f"  {nm:22s} {v/units:9.0f} clk/tile-step  {100*v/tot:5.1f}%")
