@@ -65,19 +65,23 @@ def test_gradient_allreduce_equals_full_batch_gloo(tmp_path):
 
 
 def test_host_batch_ranges_cover_the_batch_in_whole_waves():
-    """Ranges of get_actions_host: contiguous cover of [0, B), one range below 8k rows per range, otherwise the partial wave
-    first and whole waves (sms x 128 rows) behind it, never more than `chunks` ranges."""
+    """Ranges of get_actions_host: contiguous cover of [0, B), one range below 8k rows per range; below three sampler
+    waves (sms x 128 rows) the partial wave first and whole waves behind it, never more than `chunks` ranges; from three
+    waves on exactly one wave (the only exposed upload) followed by the rest in one launch."""
     from ddiffpg_b200.models import host_batch_ranges
     sms = 148
     wave = sms * 128
-    for B in (0, 1, 1000, 16383, 16384, 18944, 20000, 30000, 37888, 65536, 75776, 1 << 20):
+    for B in (0, 1, 1000, 16383, 16384, 18944, 20000, 30000, 37888, 56831, 56832, 65536, 75776, 1 << 20):
         for chunks in (1, 2, 3, 4, 8):
             r = host_batch_ranges(B, chunks, sms)
             assert len(r) <= max(chunks, 1)
             assert sum(hi - lo for lo, hi in r) == B
             assert all(r[i][1] == r[i + 1][0] for i in range(len(r) - 1)) and (not r or (r[0][0] == 0 and r[-1][1] == B))
-            if len(r) > 1:
+            if len(r) > 1 and B >= 3 * wave:
+                assert r == [(0, wave), (wave, B)]
+            elif len(r) > 1:
                 assert all((hi - lo) % wave == 0 for lo, hi in r[1:])      # everything behind the first range: whole waves
                 first = r[0][1] - r[0][0]
                 assert first < wave or first % wave == 0                      # the partial wave, if any, comes first
-    assert host_batch_ranges(65536, 4, sms) == [(0, 8704), (8704, 27648), (27648, 46592), (46592, 65536)]
+    assert host_batch_ranges(65536, 4, sms) == [(0, wave), (wave, 65536)]
+    assert host_batch_ranges(50000, 4, sms) == [(0, 50000 - 2 * wave), (50000 - 2 * wave, 50000 - wave), (50000 - wave, 50000)]
