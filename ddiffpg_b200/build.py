@@ -47,6 +47,18 @@ def build_variant(out, defines):
     return out
 
 
+def build_variant_of(src, out, defines):
+    """A/B build that recompiles ONE source with extra -D flags and links it against the objects of the main build."""
+    build(verbose=False)
+    objdir = os.path.join(HERE, "build")
+    obj = os.path.join(objdir, "variant_" + os.path.basename(out) + "_" + src.replace(".cu", ".o"))
+    subprocess.run([nvcc_path(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj],
+                   check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    objs = [obj if s == src else os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
+    subprocess.run([nvcc_path(), "-shared", "-cudart", "static", "-o", out, *objs], check=True)
+    return out
+
+
 def build(force=False, verbose=True):
     """Compile every .cu under csrc/ into one shared library.  Skips when sources are unchanged."""
     dig = _digest()
