@@ -27,9 +27,10 @@ sys.path.insert(0, ROOT)
 
 S, A, O = 34, 8, 29
 L2_FLUSH_BYTES = 256 << 20
-CPU_SAMPLE_ROWS = {"sample": 4096, "ascent": 2048, "train": 4096}     # rows per step of the CPU arms (bounded samples)
+CPU_SAMPLE_ROWS = {"sample": 4096, "ascent": 2048, "train": 4096, "critic": 4096}     # rows per step of the CPU arms (bounded samples)
 SECONDARY_ROWS = 131072                                                 # configs[2] / [3]: 1 M rows over 8 GPUs
-UNITS = {"sample": "actions/s", "ascent": "states/s", "train": "rows/s"}
+UNITS = {"sample": "actions/s", "ascent": "states/s", "train": "rows/s", "critic": "rows/s"}
+Q_HID, Q_ATOMS = (512, 256, 128), 51           # DistributionalDoubleQ defaults (reference mlp.py:131-141)
 
 _REAL_STDOUT = None
 
@@ -56,6 +57,11 @@ def algorithmic_flops(workload, T, h):
         return 2.0 * (T * (0.625 * h * h + 10 * h) + 34 * h)              # per action (6 725 632 at T=5, h=1024)
     if workload == "ascent":
         return 20 * 1395712.0 + 59392.0                                    # per state, 20 iterations
+    if workload == "critic":
+        # per row, two nets each: forward of the target critic and of the critic, dX through layers 4..2, dW of all four
+        h1, h2, h3 = Q_HID
+        fwd = (O + A) * h1 + h1 * h2 + h2 * h3 + h3 * Q_ATOMS
+        return 2.0 * 2 * (fwd + fwd + (fwd - (O + A) * h1) + fwd)          # 2 953 216
     return 2.0 * (2 * (42 * h + 0.625 * h * h + 2 * h) + (0.625 * h * h + 2 * h))   # train: fwd + dW + dX (4 116 480)
 
 
@@ -126,13 +132,16 @@ class ClockSampler:
 
 def metric_name(workload):
     return {"sample": "denoised actions/sec (T-step chain)", "ascent": "Q-ascent states/sec (20 Adam iterations)",
-            "train": "denoiser train rows/sec (eps-loss fwd+bwd)"}[workload]
+            "train": "denoiser train rows/sec (eps-loss fwd+bwd)",
+            "critic": "critic update rows/sec (C51 target + BCE fwd+bwd)"}[workload]
 
 
 def workload_config(args, workload, rows):
     cfg = {"workload": {"sample": "antmaze-v1 actor shapes, fused T-step sampler (BASELINE configs[1])",
                         "ascent": "mode-conditioned double-Q action ascent (BASELINE configs[2])",
-                        "train": "denoiser eps-loss fwd+bwd + gradient all-reduce + clip/AdamW (BASELINE configs[3])"}[workload],
+                        "train": "denoiser eps-loss fwd+bwd + gradient all-reduce + clip/AdamW (BASELINE configs[3])",
+                        "critic": "critic update of one mode: target heads, C51 projection, BCE, backward, gradient "
+                                  "all-reduce, clip + AdamW (SURVEY 8f row N1)"}[workload],
            "rows_per_gpu": rows, "S": S, "A": A, "T": args.T, "trunk": [args.width, args.width // 2, args.width // 4],
            "precision_path": args.precision, "l2": "flushed between timed steps (256 MiB write, untimed)",
            "cpu_arm_rows_per_step": CPU_SAMPLE_ROWS[workload]}
@@ -153,6 +162,15 @@ def cpu_fn(workload, p, T, rows, seed=0):
     if workload == "ascent":
         co, ca = torch.randn(rows, O, generator=g), torch.rand(rows, A, generator=g) * 2 - 1
         return lambda: port.q_action_ascent(p, co, ca.clone(), iters=20)
+    if workload == "critic":
+        co, cn = torch.randn(rows, O, generator=g), torch.randn(rows, O, generator=g)
+        ca, cb = torch.rand(rows, A, generator=g) * 2 - 1, torch.rand(rows, A, generator=g) * 2 - 1
+        cr, cd = torch.rand(rows, 1, generator=g), (torch.rand(rows, 1, generator=g) < 0.2).float()
+
+        def critic_step():
+            tq = port.critic_target_dist(p, cn, cb, cr, cd, 0.97).clamp_max(1.0)
+            return port.critic_loss_and_grads(p, tq, co, ca)
+        return critic_step
     c1, c2 = torch.randn(rows, S, generator=g), torch.rand(rows, A, generator=g) * 2 - 1
     c3, c4 = torch.randn(rows, A, generator=g), torch.randint(0, T, (rows,), generator=g)
     return lambda: port.adamw_train_step(p, c1, c2, c3, c4, T)
@@ -160,7 +178,7 @@ def cpu_fn(workload, p, T, rows, seed=0):
 
 def cpu_params(workload, h):
     from oracle import port
-    return port.init_critic_params(0) if workload == "ascent" else port.init_actor_params(0, h=h)
+    return port.init_critic_params(0) if workload in ("ascent", "critic") else port.init_actor_params(0, h=h)
 
 
 def cpu_baseline(workload, p, T, budget_s, with_configs0):
@@ -365,7 +383,43 @@ def setup_train(cx, rows):
             "d2h": 8, "params": params, "trainer": trainer, "pol": pol, "inputs": (st, ac, nz, ts), "keep": (st_h, ac_h)}
 
 
-SETUP = {"sample": setup_sample, "ascent": setup_ascent, "train": setup_train}
+def setup_critic(cx, rows):
+    """N1: update_critic for one mode's critic -- fused target / loss / backward (ddp_q_critic_loss_fwd_bwd), the flat
+    gradient averaged over the ranks (one all-reduce, as in H3), then torch's own clip_grad_norm_ + AdamW step."""
+    torch, args, dev = cx.torch, cx.args, cx.dev
+    from ddiffpg_b200 import DistributionalDoubleQ, update_critic
+    torch.manual_seed(0)
+    critic = DistributionalDoubleQ(O, A, v_min=0, v_max=5, num_atoms=Q_ATOMS, device="cuda").to(dev)
+    params = {k: v.clone().cpu() for k, v in critic.state_dict().items()}
+    torch.manual_seed(1)
+    target = DistributionalDoubleQ(O, A, v_min=0, v_max=5, num_atoms=Q_ATOMS, device="cuda").to(dev).requires_grad_(False)
+    critic.train_precision = args.precision
+    opt = torch.optim.AdamW(critic.parameters(), lr=5e-4)
+    host = [torch.randn(rows, O, generator=cx.gen), torch.rand(rows, A, generator=cx.gen) * 2 - 1,
+            torch.rand(rows, 1, generator=cx.gen), torch.randn(rows, O, generator=cx.gen),
+            torch.rand(rows, A, generator=cx.gen) * 2 - 1, (torch.rand(rows, 1, generator=cx.gen) < 0.2).float()]
+    host = [t.pin_memory() for t in host]
+    devt = [t.to(dev) for t in host]
+    loss_h = torch.empty(2).pin_memory()
+    group = cx.dist.group.WORLD if cx.world > 1 else None
+
+    def step():
+        update_critic(critic, target, opt, *devt, gamma_n=0.97, max_grad_norm=1.0, process_group=group, sync=False)
+
+    def e2e_step():
+        up = [t.to(dev, non_blocking=True) for t in host]
+        _, loss, gn = update_critic(critic, target, opt, *up, gamma_n=0.97, max_grad_norm=1.0, process_group=group,
+                                    sync=False)
+        loss_h[0:1].copy_(loss.reshape(1), non_blocking=True)
+        loss_h[1:2].copy_(gn.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    # launches of this repo's kernels per update at the tensor path: target chain + projection + prep/colmap + 8 forward
+    # GEMMs + BCE + 2 x (4 dW + 3 dX) + 2 packs of 2 nets; the optimizer tail is torch's
+    return {"step": step, "e2e": e2e_step, "launches": 30 if args.precision == "bf16" else 14,
+            "h2d": sum(t.numel() for t in host) * 4, "d2h": 8, "params": params, "keep": (critic, target, opt, devt)}
+
+
+SETUP = {"sample": setup_sample, "ascent": setup_ascent, "train": setup_train, "critic": setup_critic}
 
 
 def train_collective_report(cx, leg, rows, steps):
@@ -487,7 +541,8 @@ def run_leg(cx, workload, rows, steps, want_cpu, with_configs0, cpu_budget_s):
                 "frac": achieved / peaks["bf16_tflops"], "traffic": None,
                 "peak_source": f"{peaks['source']} bf16 burst (MEASURED_PEAKS.json)",
                 "algorithmic_flops_per_unit": flops_unit,
-                "hbm_bytes_per_unit": {"sample": 4 * (S + T * A + A), "ascent": 180, "train": 208}[workload]}
+                "hbm_bytes_per_unit": {"sample": 4 * (S + T * A + A), "ascent": 180, "train": 208,
+                                       "critic": 4 * (2 * (O + A) + 2)}[workload]}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         with open(prof) as f:
@@ -517,7 +572,7 @@ def run_cuda(args):
     main = run_leg(cx, args.workload, args.batch, steps, want_cpu, True, 10.0)
     secondary = {}
     if args.workload == "sample" and not args.no_secondary:
-        for wl in ("ascent", "train"):
+        for wl in ("ascent", "train", "critic"):
             secondary[wl] = run_leg(cx, wl, args.secondary_batch, max(3, min(steps, 10)), want_cpu, False, 4.0)
     if cx.rank == 0:
         line = {"metric": main["metric"], "value": main["value"], "unit": main["unit"], "n_gpus": cx.world, "steps": steps,
@@ -551,7 +606,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default="sample", choices=["sample", "ascent", "train"])
+    ap.add_argument("--workload", default="sample", choices=["sample", "ascent", "train", "critic"])
     ap.add_argument("--precision", default=None, choices=["fp32", "bf16"],
                     help="default: bf16 tensor-core paths (fp32 = warp-FMA parity paths)")
     ap.add_argument("--batch", type=int, default=65536, help="rows per GPU of the primary workload")

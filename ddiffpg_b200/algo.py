@@ -120,18 +120,23 @@ def update_actor(actor, actor_optimizer, obs, target_action, max_grad_norm=1.0, 
     return actor_loss.item(), grad_norm.item()
 
 
-def critic_loss_and_grads(critic, critic_target, obs, action, next_obs, next_actions, reward, done, gamma_n):
+def critic_loss_and_grads(critic, critic_target, obs, action, next_obs, next_actions, reward, done, gamma_n,
+                          precision=None):
     """Loss and flat gradient (state_dict order) of the reference's critic objective (ddiffpg.py:325-349) for one
-    critic: target = min of the two C51-projected target heads, loss = BCE(Q1, target) + BCE(Q2, target)."""
-    def fp32_cache(c):      # the update runs on the fp32 path; keep its pack apart from a bf16 inference pack
-        if getattr(c, "precision", "fp32") == "fp32":
+    critic: target = min of the two C51-projected target heads, loss = BCE(Q1, target) + BCE(Q2, target).
+    ``precision``: "fp32" (FMA kernels, 1e-4 parity) or "bf16" (tcgen05 GEMMs, 1e-2 parity); default
+    ``critic.train_precision``."""
+    precision = precision or getattr(critic, "train_precision", "fp32")
+    def cache_for(c):       # keep the update's pack apart from an inference pack of another precision
+        if getattr(c, "precision", "fp32") == precision:
             return c._cache
-        if not hasattr(c, "_cache_fp32"):
-            c._cache_fp32 = _PackCache()
-        return c._cache_fp32
-    packed, shape, prec = pack_critics([critic], fp32_cache(critic), "fp32")
+        name = "_cache_" + precision
+        if not hasattr(c, name):
+            setattr(c, name, _PackCache())
+        return getattr(c, name)
+    packed, shape, prec = pack_critics([critic], cache_for(critic), precision)
     # the target critic is written through param.data by soft_update (ddiffpg.py:266): always re-packed (see _PackCache)
-    packed_t, _, _ = pack_critics([critic_target], fp32_cache(critic_target), "fp32", force=True)
+    packed_t, _, _ = pack_critics([critic_target], cache_for(critic_target), precision, force=True)
     dev = packed.device
     f = lambda x: x.detach().to(device=dev, dtype=torch.float32).contiguous()
     obs, action, next_obs, next_actions = f(obs), f(action), f(next_obs), f(next_actions)
@@ -153,12 +158,23 @@ def critic_loss_and_grads(critic, critic_target, obs, action, next_obs, next_act
 
 
 def update_critic(critic, critic_target, critic_optimizer, obs, action, reward, next_obs, next_actions, done,
-                  gamma_n=0.99, max_grad_norm=1.0):
+                  gamma_n=0.99, max_grad_norm=1.0, process_group=None, sync=True):
     """``AgentDDiffPG.update_critic`` (ddiffpg.py:322-351) with ``next_actions`` already sampled
     (``get_tgt_policy_actions``): fused target/loss/backward, then the reference's own clip + optimizer step on
-    the ``.grad`` fields.  Returns ``(critic, loss float, pre-clip grad norm float)``."""
+    the ``.grad`` fields.  Returns ``(critic, loss float, pre-clip grad norm float)``.
+
+    ``process_group``: data-parallel replicas, every rank holding an equal share of one batch -- the flat gradient and
+    the loss are averaged over the ranks (one all-reduce, the critic's counterpart of H3's exchange step) before the
+    identical clip + step on every replica.  ``sync=False`` returns the loss and norm as 0-dim device tensors instead
+    of floats (no host synchronisation inside the call)."""
     loss, grads = critic_loss_and_grads(critic, critic_target, obs, action, next_obs, next_actions, reward, done,
                                         gamma_n)
+    _, world = ddist.world_info(process_group) if process_group is not None else (0, 1)
+    if world > 1:
+        flat = torch.cat([grads, loss.reshape(1)])            # the loss rides in the gradient buffer: one collective
+        ddist.allreduce_sum_(flat, group=process_group)
+        flat.div_(world)
+        grads, loss = flat[:-1], flat[-1]
     critic_optimizer.zero_grad(set_to_none=True)
     off = 0
     for p in critic.parameters():
@@ -169,6 +185,8 @@ def update_critic(critic, critic_target, critic_optimizer, obs, action, reward, 
     else:
         grad_norm = None
     critic_optimizer.step()
+    if not sync:
+        return critic, loss, grad_norm
     return critic, loss.item(), (grad_norm.item() if grad_norm is not None else None)
 
 

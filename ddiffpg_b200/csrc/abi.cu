@@ -56,6 +56,11 @@ int q_critic_train_fma(const QLayout& L, const float* pk, const float* pk_target
                        const float* next_obs, const float* next_act, const float* reward, const float* done, float gamma,
                        float* loss_out, float* grads, long B, void* ws, size_t ws_bytes, cudaStream_t st);
 
+size_t q_critic_train_tc_workspace(const QLayout& L, long B);
+int q_critic_train_tc(const QLayout& L, const void* packed, const void* packed_target, const float* obs, const float* act,
+                      const float* next_obs, const float* next_act, const float* reward, const float* done, float gamma,
+                      float* loss_out, float* grads, long B, void* ws, size_t ws_bytes, cudaStream_t st);
+
 size_t rnd_grad_count(const QLayout& L);
 size_t rnd_train_workspace(const QLayout& L, long B);
 int rnd_novelty_fma(const QLayout& L, const float* pk, const float* x, float* novelty, float* pred, float* target,
@@ -287,7 +292,8 @@ size_t ddp_q_grad_count(const ddp_q_shape* s) {
 }
 
 size_t ddp_q_critic_train_workspace_bytes(const ddp_q_shape* s, long B, int precision) {
-    if (check_q_shape(s) != DDP_OK || B <= 0 || precision != DDP_FP32) return 0;
+    if (check_q_shape(s) != DDP_OK || B <= 0 || (precision != DDP_FP32 && precision != DDP_BF16)) return 0;
+    if (precision == DDP_BF16) return q_critic_train_tc_workspace(make_q_layout(*s, precision), B);
     return q_critic_train_workspace(make_q_layout(*s, precision), B);
 }
 
@@ -302,8 +308,11 @@ int ddp_q_critic_loss_fwd_bwd(const ddp_q_shape* s, const void* packed, const vo
     if (!packed || !packed_target || !obs || !action || !next_obs || !next_action || !reward || !done || !loss_out ||
         !grads_flat || !ws)
         DDP_FAIL(DDP_ERR_ARG, "ddp_q_critic_loss_fwd_bwd: NULL argument");
-    if (precision != DDP_FP32) DDP_FAIL(DDP_ERR_UNSUPPORTED, "critic update: only DDP_FP32 is implemented");
+    if (precision != DDP_FP32 && precision != DDP_BF16) DDP_FAIL(DDP_ERR_ARG, "critic update: unknown precision %d", precision);
     if (!aligned16(ws) || !aligned16(grads_flat)) DDP_FAIL(DDP_ERR_ARG, "workspace/grads must be 16-byte aligned");
+    if (precision == DDP_BF16)      // both packs must have been made with DDP_BF16 (they carry the 16-bit operand section)
+        return q_critic_train_tc(make_q_layout(*s, precision), packed, packed_target, obs, action, next_obs, next_action,
+                                 reward, done, gamma_n, loss_out, grads_flat, B, ws, ws_bytes, (cudaStream_t)stream);
     return q_critic_train_fma(make_q_layout(*s, precision), (const float*)packed, (const float*)packed_target, obs,
                               action, next_obs, next_action, reward, done, gamma_n, loss_out, grads_flat, B, ws,
                               ws_bytes, (cudaStream_t)stream);

@@ -579,6 +579,13 @@ __global__ void c51_projection_min_kernel(const float* __restrict__ p1, const fl
     }
 }
 
+void launch_c51_projection_min(const float* p1, const float* p2, const float* reward, const float* done, float gamma,
+                               float v_min, float v_max, int atoms, const float* z, long B, float* target,
+                               cudaStream_t st) {
+    c51_projection_min_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(p1, p2, reward, done, gamma, v_min, v_max, atoms, z,
+                                                                        B, target);
+}
+
 struct QTrainWs {
     float *p1t, *p2t, *target;
     QTrainBufs b;

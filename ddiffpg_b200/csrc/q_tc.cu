@@ -374,6 +374,171 @@ int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, co
     return DDP_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// N1, bf16 tensor-core path: critic update (AgentDDiffPG.update_critic, ddiffpg/algo/ddiffpg.py:322-351).
+//   target  critic_target.get_q1_q2(next_obs, next_actions) by the fused chain kernel (forward half), then the fp32 C51
+//           projection of both heads and their minimum (ddiffpg/utils/distl_util.py:4-20, ddiffpg.py:340-346);
+//   forward one grouped row GEMM per Linear, ELU fused, activations kept in bf16, logits fp32;
+//   loss    softmax + F.binary_cross_entropy (+ d loss / d logits) in fp32, one warp per row;
+//   backward per net, last layer first: dW_l = dZ_l^T . a_(l-1) (MN-major dW GEMM, bias gradient from its ones-MMA),
+//           then dZ_(l-1) = (dZ_l . W_l) * elu'(a_(l-1)) written over a_(l-1) -- every activation is read by its weight
+//           gradient before the backward GEMM overwrites it.
+void launch_c51_projection_min(const float* p1, const float* p2, const float* reward, const float* done, float gamma,
+                               float v_min, float v_max, int atoms, const float* z, long B, float* target,
+                               cudaStream_t st);                              // csrc/q_fma.cu
+
+namespace {
+
+struct QTrainTcWs {
+    void* fwd_ws; size_t fwd_bytes;
+    bf16 *xin, *a1[2], *a2[2], *a3[2], *dl[2];
+    float *logits[2], *p1t, *p2t, *target;
+    int* colmap;
+    size_t total;
+};
+
+QTrainTcWs carve_train(const QLayout& L, long B, uint8_t* base) {
+    QTrainTcWs w{};
+    size_t o = 0;
+    auto take = [&](size_t bytes) { uint8_t* r = base ? base + o : nullptr; o += (bytes + 255) / 256 * 256; return r; };
+    w.fwd_bytes = carve(L, B, 0, nullptr).total;
+    w.fwd_ws = take(w.fwd_bytes);
+    w.xin = (bf16*)take((size_t)B * 64 * 2);
+    for (int j = 0; j < 2; ++j) {
+        w.a1[j] = (bf16*)take((size_t)B * L.h1 * 2);
+        w.a2[j] = (bf16*)take((size_t)B * L.h2 * 2);
+        w.a3[j] = (bf16*)take((size_t)B * L.h3 * 2);
+        w.dl[j] = (bf16*)take((size_t)B * 64 * 2);
+        w.logits[j] = (float*)take((size_t)B * 64 * 4);
+    }
+    w.p1t = (float*)take((size_t)B * L.atoms * 4);
+    w.p2t = (float*)take((size_t)B * L.atoms * 4);
+    w.target = (float*)take((size_t)B * L.atoms * 4);
+    w.colmap = (int*)take(64 * 4);
+    w.total = o;
+    return w;
+}
+
+__global__ void q_tc_colmap_kernel(int in1, int* __restrict__ colmap) {
+    if (threadIdx.x < 64) colmap[threadIdx.x] = (int)threadIdx.x < in1 ? (int)threadIdx.x : -1;
+}
+
+// One warp per row, both nets: p = softmax(logits); loss += BCE(p, target) (logs clamped at -100 like
+// F.binary_cross_entropy); dl = d loss / d logits = p (g - <p, g>), g = inv_count (p - t) / max(p (1 - p), 1e-12).
+__global__ void q_tc_bce_kernel(const float* __restrict__ lg1, const float* __restrict__ lg2,
+                                const float* __restrict__ target, int atoms, long B, float inv_count,
+                                bf16* __restrict__ dl1, bf16* __restrict__ dl2, float* __restrict__ loss_out) {
+    __shared__ float red[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + warp;
+    float lsum = 0.f;
+    if (row < B) {
+        const int c0 = lane, c1 = lane + 32;
+        const bool v0 = c0 < atoms, v1 = c1 < atoms;
+        const float t0 = v0 ? target[row * atoms + c0] : 0.f, t1 = v1 ? target[row * atoms + c1] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float* lg = (j == 0 ? lg1 : lg2) + row * 64;
+            const float l0 = v0 ? lg[c0] : -INFINITY, l1 = v1 ? lg[c1] : -INFINITY;
+            const float mx = warp_max(fmaxf(l0, l1));
+            const float e0 = v0 ? expf(l0 - mx) : 0.f, e1 = v1 ? expf(l1 - mx) : 0.f;
+            const float sum = warp_sum(e0 + e1);
+            const float p0 = e0 / sum, p1 = e1 / sum;
+            float g0 = 0.f, g1 = 0.f;
+            if (v0) {
+                lsum -= t0 * fmaxf(logf(p0), -100.f) + (1.f - t0) * fmaxf(log1pf(-p0), -100.f);
+                g0 = inv_count * (p0 - t0) / fmaxf((1.f - p0) * p0, 1e-12f);
+            }
+            if (v1) {
+                lsum -= t1 * fmaxf(logf(p1), -100.f) + (1.f - t1) * fmaxf(log1pf(-p1), -100.f);
+                g1 = inv_count * (p1 - t1) / fmaxf((1.f - p1) * p1, 1e-12f);
+            }
+            const float dot = warp_sum(p0 * g0 + p1 * g1);
+            bf16* dl = (j == 0 ? dl1 : dl2) + row * 64;
+            dl[c0] = __float2bfloat16(v0 ? p0 * (g0 - dot) : 0.f);
+            dl[c1] = __float2bfloat16(v1 ? p1 * (g1 - dot) : 0.f);
+        }
+    }
+    lsum = warp_sum(lsum);
+    if (lane == 0) red[warp] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        if (t != 0.f) atomicAdd(loss_out, t * inv_count);
+    }
+}
+
+}  // namespace
+
+size_t q_critic_train_tc_workspace(const QLayout& L, long B) { return carve_train(L, B, nullptr).total; }
+
+int q_critic_train_tc(const QLayout& L, const void* packed, const void* packed_target, const float* obs, const float* act,
+                      const float* next_obs, const float* next_act, const float* reward, const float* done, float gamma,
+                      float* loss_out, float* grads, long B, void* ws, size_t ws_bytes, cudaStream_t st) {
+    using namespace tcg;
+    if (!shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 critic update does not support this shape");
+    if (ws_bytes < carve_train(L, B, nullptr).total) DDP_FAIL(DDP_ERR_ARG, "critic update (tensor path): workspace too small");
+    QTrainTcWs w = carve_train(L, B, (uint8_t*)ws);
+    const uint8_t* pb = (const uint8_t*)packed;
+    const float* pk = (const float*)packed;
+    const int64_t seg_off[2] = {0, B};
+    int rc = q_forward_tc(L, packed_target, seg_off, next_obs, next_act, nullptr, w.p1t, w.p2t, nullptr, B, w.fwd_ws,
+                          w.fwd_bytes, st);
+    if (rc != DDP_OK) return rc;
+    launch_c51_projection_min(w.p1t, w.p2t, reward, done, gamma, L.v_min, L.v_max, L.atoms,
+                              (const float*)packed_target + L.z, B, w.target, st);
+    const size_t in1 = (size_t)L.O + L.A;
+    const size_t per_net = (size_t)L.h1 * in1 + L.h1 + (size_t)L.h2 * L.h1 + L.h2 + (size_t)L.h3 * L.h2 + L.h3 +
+                           (size_t)L.atoms * L.h3 + L.atoms;
+    DDP_CUDA_CHECK(cudaMemsetAsync(grads, 0, 2 * per_net * sizeof(float), st));
+    const unsigned eb = (unsigned)((B * 64 + 255) / 256);
+    q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, const_cast<float*>(act), L.O, L.A, B, 0.f, w.xin);
+    q_tc_colmap_kernel<<<1, 64, 0, st>>>((int)in1, w.colmap);
+    auto row = [&](const bf16* A, int lda, size_t w_off, int ldw, int N, int K, int epi, const float* bias, const bf16* aux,
+                   bf16* out_a, float* out_f, int outf_ld, int n_valid) {
+        RowGemm g{};
+        g.A = A; g.lda = lda; g.W = (const bf16*)(pb + w_off); g.ldw = ldw; g.w_stride = 0;
+        g.M = B; g.N = N; g.K = K; g.epi = epi; g.bias = bias; g.bias_stride = 0;
+        g.aux = aux; g.aux_ld = N; g.out_a = out_a; g.out_ld = N; g.out_f = out_f; g.outf_ld = outf_ld; g.n_valid = n_valid;
+        g.groups.n_groups = 1; g.groups.off[0] = 0; g.groups.off[1] = B;
+        return launch_row_gemm(g, st);
+    };
+    for (int j = 0; j < 2; ++j) {
+        const QNetLayout& n = L.net[j];
+        if ((rc = row(w.xin, 64, L.tc_fwd[j][0], 64, L.h1, 64, EPI_ELU_FWD, pk + n.b1, nullptr, w.a1[j], nullptr, 0, 0)) != DDP_OK) return rc;
+        if ((rc = row(w.a1[j], L.h1, L.tc_fwd[j][1], L.h1, L.h2, L.h1, EPI_ELU_FWD, pk + n.b2, nullptr, w.a2[j], nullptr, 0, 0)) != DDP_OK) return rc;
+        if ((rc = row(w.a2[j], L.h2, L.tc_fwd[j][2], L.h2, L.h3, L.h2, EPI_ELU_FWD, pk + n.b3, nullptr, w.a3[j], nullptr, 0, 0)) != DDP_OK) return rc;
+        if ((rc = row(w.a3[j], L.h3, L.tc_fwd[j][3], L.h3, 64, L.h3, EPI_LINEAR_F32, pk + n.b4, nullptr, nullptr, w.logits[j], 64, L.atoms)) != DDP_OK) return rc;
+    }
+    q_tc_bce_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(w.logits[0], w.logits[1], w.target, L.atoms, B,
+                                                              1.0f / ((float)B * (float)L.atoms), w.dl[0], w.dl[1], loss_out);
+    auto dw = [&](const bf16* dz, int ldz, int N, const bf16* X, int ldx, int K, float* C, int ldc, const int* colmap,
+                  float* colsum) {
+        DwGemm g{};
+        g.dZ = dz; g.ldz = ldz; g.N = N; g.X = X; g.ldx = ldx; g.K = K; g.R = B; g.C = C; g.ldc = ldc; g.colmap = colmap;
+        g.colsum = colsum;
+        return launch_dw_gemm(g, st);
+    };
+    for (int j = 0; j < 2; ++j) {
+        // flat gradient of one net, state_dict order: W1, b1, W2, b2, W3, b3, W4, b4
+        float* g1 = grads + (size_t)j * per_net;
+        float* g2 = g1 + (size_t)L.h1 * in1 + L.h1;
+        float* g3 = g2 + (size_t)L.h2 * L.h1 + L.h2;
+        float* g4 = g3 + (size_t)L.h3 * L.h2 + L.h3;
+        if ((rc = dw(w.dl[j], 64, L.atoms, w.a3[j], L.h3, L.h3, g4, L.h3, nullptr, g4 + (size_t)L.atoms * L.h3)) != DDP_OK) return rc;
+        if ((rc = row(w.dl[j], 64, L.tc_bwd[j][0], 64, L.h3, 64, EPI_MUL_ELU_D, nullptr, w.a3[j], w.a3[j], nullptr, 0, 0)) != DDP_OK) return rc;
+        if ((rc = dw(w.a3[j], L.h3, L.h3, w.a2[j], L.h2, L.h2, g3, L.h2, nullptr, g3 + (size_t)L.h3 * L.h2)) != DDP_OK) return rc;
+        if ((rc = row(w.a3[j], L.h3, L.tc_bwd[j][1], L.h3, L.h2, L.h3, EPI_MUL_ELU_D, nullptr, w.a2[j], w.a2[j], nullptr, 0, 0)) != DDP_OK) return rc;
+        if ((rc = dw(w.a2[j], L.h2, L.h2, w.a1[j], L.h1, L.h1, g2, L.h1, nullptr, g2 + (size_t)L.h2 * L.h1)) != DDP_OK) return rc;
+        if ((rc = row(w.a2[j], L.h2, L.tc_bwd[j][2], L.h2, L.h1, L.h2, EPI_MUL_ELU_D, nullptr, w.a1[j], w.a1[j], nullptr, 0, 0)) != DDP_OK) return rc;
+        if ((rc = dw(w.a1[j], L.h1, L.h1, w.xin, 64, 64, g1, (int)in1, w.colmap, g1 + (size_t)L.h1 * in1)) != DDP_OK) return rc;
+    }
+    DDP_LAUNCH_CHECK("critic update (tensor path) kernels");
+    return DDP_OK;
+}
+
 }  // namespace ddp
 
 // Debug entry point (not part of the public header): choose the schedule of the tensor-core critic path explicitly

@@ -424,6 +424,7 @@ class DistributionalDoubleQ(nn.Module):
                  precision="fp32"):
         super().__init__()
         self.precision = precision      # "fp32" FMA path | "bf16" tcgen05 GEMM path (large batches)
+        self.train_precision = "fp32"   # precision of update_critic's loss/backward ("bf16": tcgen05 GEMMs)
         if isinstance(state_dim, Sequence):
             state_dim = state_dim[0]
         self.device = device
@@ -438,8 +439,9 @@ class DistributionalDoubleQ(nn.Module):
 
     def mark_dirty(self):
         self._cache.dirty = True
-        if hasattr(self, "_cache_fp32"):
-            self._cache_fp32.dirty = True
+        for name in ("_cache_fp32", "_cache_bf16"):
+            if hasattr(self, name):
+                getattr(self, name).dirty = True
 
     def _forward_raw(self, obs, action, want_probs, want_grad):
         packed, shape, prec = pack_critics([self], self._cache)

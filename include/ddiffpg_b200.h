@@ -180,7 +180,10 @@ int ddp_q_action_ascent(const ddp_q_shape* shape, const void* packed, const int6
  *   loss    = BCE(current_Q1, target) + BCE(current_Q2, target)   (F.binary_cross_entropy, mean over B*atoms);
  *   grads   = d loss / d params of `packed`, flat in DistributionalDoubleQ.state_dict() order (overwritten).
  * reward, done: [B] fp32.  loss_out[0] += loss (zero it first).  The optimizer step (clip_grad_norm_ + AdamW,
- * ac_base.py:86-91) stays with the caller: ddp_clip_adamw_step on a flat vector, or torch's own. */
+ * ac_base.py:86-91) stays with the caller: ddp_clip_adamw_step on a flat vector, or torch's own.
+ * precision: DDP_FP32 (FMA tile kernel + fp32 dW GEMMs, 1e-4) or DDP_BF16 (target heads by the fused tcgen05 chain,
+ * forward / dX / dW by the tcgen05 row and dW GEMMs, softmax + BCE + projection in fp32; 1e-2) -- `packed` and
+ * `packed_target` must both have been packed with the same precision. */
 size_t ddp_q_grad_count(const ddp_q_shape* shape);
 size_t ddp_q_critic_train_workspace_bytes(const ddp_q_shape* shape, long B, int precision);
 int ddp_q_critic_loss_fwd_bwd(const ddp_q_shape* shape, const void* packed, const void* packed_target,

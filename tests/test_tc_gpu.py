@@ -483,3 +483,84 @@ def test_million_row_sampler_equals_chunked_calls():
     for i in range(4):
         sl = slice(i * q, (i + 1) * q)
         assert torch.equal(out[sl], pol.get_actions(state[sl].contiguous(), noise=noise[:, sl].contiguous()))
+
+
+# ------------------------------------------------------------------------------------------ N1 tensor path
+def _critic_named(flat, params):
+    out, off = {}, 0
+    for k in port.CRITIC_KEYS:
+        n = params[k].numel()
+        out[k] = flat[off:off + n].view(params[k].shape).cpu()
+        off += n
+    assert off == flat.numel()
+    return out
+
+
+def _rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-12)).item()
+
+
+def test_critic_update_bf16_reference_fixture():
+    """update_critic's loss and 16 gradients (ddiffpg.py:322-349) on the tcgen05 path against the reference's autograd
+    fixture: loss within 2e-3 relative, every gradient tensor within 1e-2 relative L2 (the stated bf16 bound)."""
+    from ddiffpg_b200 import critic_loss_and_grads
+    from tests.util import make_critic
+    g = load_golden("n1_critic")
+    p, pt = port.init_critic_params(41, scale=1.5), port.init_critic_params(42, scale=1.5)
+    loss, flat = critic_loss_and_grads(make_critic(p), make_critic(pt), _dev(g["obs"]), _dev(g["act"]), _dev(g["nobs"]),
+                                       _dev(g["nact"]), _dev(g["reward"]), _dev(g["done"]), float(g["gamma"]),
+                                       precision="bf16")
+    assert abs(loss.item() - float(g["loss"])) <= 2e-3 * max(1.0, abs(float(g["loss"])))
+    named = _critic_named(flat, p)
+    for i, k in enumerate(port.CRITIC_KEYS):
+        ref = torch.from_numpy(g[f"g_{i}"])
+        got = named[k] if named[k].numel() <= 8192 else named[k].flatten()[::97]
+        assert _rel_l2(got.reshape(ref.shape), ref) <= BF16_ATOL, (k, _rel_l2(got.reshape(ref.shape), ref))
+        assert abs(float(named[k].norm()) - float(g[f"gnorm_{i}"])) <= BF16_ATOL * float(g[f"gnorm_{i}"]) + 1e-8, k
+
+
+@pytest.mark.parametrize("B", [1, 7, 129, 3000])
+def test_critic_update_bf16_vs_oracle_batches(B):
+    from ddiffpg_b200 import critic_loss_and_grads
+    from tests.util import make_critic
+    p, pt = port.init_critic_params(51, scale=1.2), port.init_critic_params(52, scale=1.2)
+    gen = torch.Generator().manual_seed(600 + B)
+    obs, nobs = torch.randn(B, 29, generator=gen), torch.randn(B, 29, generator=gen)
+    act, nact = torch.rand(B, 8, generator=gen) * 2 - 1, torch.rand(B, 8, generator=gen) * 2 - 1
+    reward = torch.rand(B, 1, generator=gen) * 3.0
+    reward[::5] = 0.0
+    done = (torch.rand(B, 1, generator=gen) < 0.25).float()
+    tq = port.critic_target_dist(pt, nobs, nact, reward, done, 0.97)
+    keep = tq.max(1).values <= 1.0          # as in the fp32 test: rows on which F.binary_cross_entropy itself raises
+    obs, nobs, act, nact, reward, done, tq = (x[keep] for x in (obs, nobs, act, nact, reward, done, tq))
+    l_ref, g_ref = port.critic_loss_and_grads(p, tq, obs, act)
+    loss, flat = critic_loss_and_grads(make_critic(p), make_critic(pt), _dev(obs), _dev(act), _dev(nobs), _dev(nact),
+                                       _dev(reward), _dev(done), 0.97, precision="bf16")
+    assert abs(loss.item() - l_ref.item()) <= 2e-3 * max(1.0, abs(l_ref.item()))
+    named = _critic_named(flat, p)
+    flat_ref = torch.cat([g_ref[k].flatten() for k in port.CRITIC_KEYS])
+    assert _rel_l2(flat.cpu(), flat_ref) <= BF16_ATOL, _rel_l2(flat.cpu(), flat_ref)
+    for k in port.CRITIC_KEYS:
+        assert _rel_l2(named[k], g_ref[k]) <= (BF16_ATOL if B >= 100 else 2 * BF16_ATOL), (k, _rel_l2(named[k], g_ref[k]))
+
+
+def test_critic_update_bf16_large_batch_is_mean_of_halves():
+    """BASELINE-sized property (no oracle at this size): with mean-reduced BCE the gradient of a 262 144-row batch is the
+    mean of the gradients of its two halves, and so is the loss."""
+    from ddiffpg_b200 import critic_loss_and_grads
+    from tests.util import make_critic
+    p, pt = port.init_critic_params(71, scale=1.0), port.init_critic_params(72, scale=1.0)
+    critic, target = make_critic(p), make_critic(pt)
+    B = 262144
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    obs, nobs = torch.randn(B, 29, device="cuda", generator=gen), torch.randn(B, 29, device="cuda", generator=gen)
+    act = torch.rand(B, 8, device="cuda", generator=gen) * 2 - 1
+    nact = torch.rand(B, 8, device="cuda", generator=gen) * 2 - 1
+    reward, done = torch.rand(B, device="cuda", generator=gen), (torch.rand(B, device="cuda", generator=gen) < 0.2).float()
+    run = lambda s: critic_loss_and_grads(critic, target, obs[s], act[s], nobs[s], nact[s], reward[s], done[s], 0.97,
+                                          precision="bf16")
+    l_all, g_all = run(slice(0, B))
+    l_a, g_a = run(slice(0, B // 2))
+    l_b, g_b = run(slice(B // 2, B))
+    assert abs(l_all.item() - 0.5 * (l_a.item() + l_b.item())) <= 1e-5 * abs(l_all.item())
+    assert _rel_l2(g_all, 0.5 * (g_a + g_b)) <= 1e-4
