@@ -9,9 +9,11 @@ from .algo import (FusedActorTrainer, HotPathMixin, critic_loss_and_grads, get_a
                    get_tgt_policy_actions, update_critic,
                    optimizer_update, q_action_ascent_segments, soft_update, update_actor, update_target_action)
 from .intrinsic import IntrinsicKernels, IntrinsicM, RNDModel, accelerate_intrinsic  # noqa: F401
-from .replay import DiffusionReplayBuffer, ReplayKernels, accelerate_replay_buffer, add_embedding  # noqa: F401
+from .replay import (DiffusionGoalBuffer, DiffusionReplayBuffer, GoalBufferKernels, ReplayKernels,  # noqa: F401
+                     accelerate_goal_buffer, accelerate_replay_buffer, add_embedding)
 
-__all__ = ["IntrinsicKernels", "IntrinsicM", "RNDModel", "accelerate_intrinsic", "DiffusionReplayBuffer", "ReplayKernels",
+__all__ = ["IntrinsicKernels", "IntrinsicM", "RNDModel", "accelerate_intrinsic", "DiffusionReplayBuffer", "ReplayKernels", "DiffusionGoalBuffer",
+           "GoalBufferKernels", "accelerate_goal_buffer",
            "accelerate_replay_buffer", "add_embedding", "DiffusionPolicy", "DistributionalDoubleQ", "DiffusionNet", "MLPNet", "FusedActorTrainer",
            "HotPathMixin", "critic_loss_and_grads", "update_critic", "get_actions", "get_tgt_policy_actions", "optimizer_update", "q_action_ascent_segments", "soft_update", "update_actor",
            "update_target_action"]

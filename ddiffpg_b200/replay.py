@@ -8,6 +8,8 @@ mode group of ``DiffusionGoalBuffer.sample_batch`` + ``AgentDDiffPG.update_net``
 (``add_to_buffer``, ``remove``, ``get_buffer_size``, ``update_target_action_dim``) stay the reference's own code:
 ``DiffusionReplayBuffer`` below is ``ReplayKernels`` in front of the reference class when ``ddiffpg`` is importable, and
 in front of a bare attribute holder otherwise (tests load the ``buf_*`` tensors from fixtures).
+``GoalBufferKernels`` does the same for ``ddiffpg.replay.diffusion_replay.DiffusionGoalBuffer.sample_batch`` /
+``add_temp_data`` (:250-332).
 ``add_embedding`` mirrors ``ddiffpg.utils.torch_util.add_embedding`` (:17-43), both branches.  Random draws stay in
 torch / numpy as in the reference and can be injected (``indices=``, ``zero_indices=``) for reproducible comparisons.
 """
@@ -78,9 +80,27 @@ class ReplayKernels:
     check_indices = True      # raise IndexError on out-of-range rows like the reference's indexing (costs one host sync)
 
     def available_indices(self, cluster_idx):
-        """Rows whose trajectory id is in ``cluster_idx`` (the first line of simple_replay.py:151)."""
+        """Rows whose trajectory id is in ``cluster_idx`` (the first line of simple_replay.py:151), ascending like
+        ``torch.where(torch.isin(...))``: one table look-up per stored row (trajectory ids are small non-negative
+        integers, diffusion_replay.py:84-118) instead of isin's sort / broadcast compare."""
         dev = self.buf_id.device
-        return torch.where(torch.isin(self.buf_id, torch.tensor(cluster_idx, device=dev)))[0]
+        ids = torch.as_tensor(cluster_idx, device=dev).long().reshape(-1)
+        if ids.numel() == 0:
+            return torch.empty(0, dtype=torch.int64, device=dev)
+        rows = self.buf_id.reshape(-1)
+        if rows.is_floating_point() and not bool((rows == rows.round()).all()):
+            return torch.where(torch.isin(self.buf_id, ids.to(self.buf_id.dtype)))[0]       # not ids at all: as written
+        rows = rows.long()
+        lo, hi = int(min(rows.min().item(), ids.min().item())), int(max(rows.max().item(), ids.max().item()))
+        if hi - lo > 4 * rows.numel() + 65536:                                              # sparse id space: as written
+            return torch.where(torch.isin(self.buf_id, ids.to(self.buf_id.dtype)))[0]
+        lut = torch.zeros(hi - lo + 1, dtype=torch.bool, device=dev)
+        lut[ids - lo] = True
+        return torch.where(lut[rows - lo])[0]
+
+    def get_buffer_size(self, cluster_idx):
+        """simple_replay.py:183-186."""
+        return 0 if self.buf_id is None else int(self.available_indices(cluster_idx).shape[0])
 
     def _gather(self, indices, group, embeddings=None, zero_state=None, zero_next=None, want_embedded=False):
         _cuda(self.buf_obs, "the replay storage")
@@ -176,6 +196,95 @@ class ReplayKernels:
                                                   stream_ptr()), "ddp_replay_scatter_target")
 
 
+class GoalBufferKernels:
+    """Mixin for ``ddiffpg.replay.diffusion_replay.DiffusionGoalBuffer``: ``sample_batch`` (:250-283) and
+    ``add_temp_data`` (:285-332) with the replay rows of ALL mode groups gathered by one launch (``sample_groups``); the
+    group split, the temp-buffer share of group 0 and the order of the random draws are the reference's.  Clustering,
+    trajectory bookkeeping and the Q scheduler stay the reference's own code."""
+
+    def _group_plan(self, batch_size):
+        groups = [self.success_id + list(self.unsuccess_id)]
+        for i in range(len(self.clusters)):
+            groups.append(self.clusters[i] + self.unsuccess_clusters[i])
+        sizes = [batch_size // len(groups)] * len(groups)
+        sizes[0] += batch_size % len(groups)
+        assert len(self.Qs) == len(groups) and len(self.Qs) == len(self.embeddings)
+        if self.replay_buffer.buf_target_action is not None:
+            assert len(self.Qs) == self.replay_buffer.buf_target_action.shape[0]
+        return groups, sizes
+
+    def _draw(self, batch_size, cluster_idx, if_add_temp):
+        """The index draws of one ``add_temp_data`` call, in the reference's order (replay rows, then temp rows)."""
+        temp_size = self.temp_state.shape[0]
+        b_temp = 0
+        if if_add_temp:
+            buffer_size = self.replay_buffer.get_buffer_size(cluster_idx)
+            b_temp = int((temp_size / (temp_size + buffer_size)) * batch_size)
+        b_sample = batch_size - b_temp
+        rows = temp_rows = None
+        if b_sample != 0:
+            avail = self.replay_buffer.available_indices(cluster_idx)
+            rows = avail[torch.randint(avail.shape[0], size=(b_sample,), device=avail.device)]
+        if b_temp != 0:
+            temp_rows = torch.randint(temp_size, size=(b_temp,), device=self.device)
+        return rows, temp_rows
+
+    def _with_temp(self, parts, temp_rows, device):
+        if temp_rows is not None:
+            t = temp_rows.to(self.temp_state.device)
+            temp = (self.temp_state[t], self.temp_action[t], self.temp_action[t], self.temp_reward[t],
+                    self.temp_next_state[t], self.temp_done[t].float())
+            dev = parts[0].device if parts is not None else torch.device(device)
+            temp = tuple(x.to(device=dev, dtype=torch.float32) for x in temp)
+            parts = temp if parts is None else tuple(torch.cat([a, b]) for a, b in zip(parts, temp))
+        return tuple(x.to(device) for x in parts)
+
+    @torch.no_grad()
+    def sample_batch(self, batch_size, device=None):
+        device = self.device if device is None else device
+        groups, sizes = self._group_plan(batch_size)
+        draws = [self._draw(sizes[i], groups[i], i == 0) for i in range(len(groups))]
+        live = [i for i, (rows, _) in enumerate(draws) if rows is not None]
+        data_list, parts = [], {}
+        if live:
+            rb = self.replay_buffer
+            idx = torch.cat([draws[i][0] for i in live])
+            slot = torch.repeat_interleave(torch.tensor(live, dtype=torch.int32, device=idx.device),
+                                           torch.tensor([draws[i][0].shape[0] for i in live], device=idx.device))
+            o, _, _ = rb._gather(idx, slot)
+            off = 0
+            for i in live:
+                n = draws[i][0].shape[0]
+                parts[i] = tuple(o[k][off:off + n] for k in ("obs", "action", "target", "reward", "next_obs", "done"))
+                off += n
+        for i in range(len(groups)):
+            rows, temp_rows = draws[i]
+            data_list.append({"Q": self.Qs[i], "batch": self._with_temp(parts.get(i), temp_rows, device),
+                              "indices": rows, "embedding": self.embeddings[i]})
+        return data_list
+
+    def add_temp_data(self, batch_size, cluster_idx, target_idx, if_add_temp=True, device=None):
+        device = self.device if device is None else device
+        rows, temp_rows = self._draw(batch_size, cluster_idx, if_add_temp)
+        parts = None
+        if rows is not None:
+            slot = torch.full((rows.shape[0],), int(target_idx), dtype=torch.int32, device=rows.device)
+            o, _, _ = self.replay_buffer._gather(rows, slot)
+            parts = tuple(o[k] for k in ("obs", "action", "target", "reward", "next_obs", "done"))
+        return self._with_temp(parts, temp_rows, device), rows
+
+
+def accelerate_goal_buffer(base):
+    """``GoalBufferKernels`` in front of ``base`` (the reference's ``DiffusionGoalBuffer``); the inner replay buffer the
+    reference constructs (diffusion_replay.py:45-48) is switched to the accelerated class in place."""
+    def __init__(self, *args, **kwargs):
+        base.__init__(self, *args, **kwargs)
+        rb = self.replay_buffer
+        if not isinstance(rb, ReplayKernels):
+            rb.__class__ = accelerate_replay_buffer(type(rb))
+    return type(base.__name__, (GoalBufferKernels, base), {"__init__": __init__, "__doc__": GoalBufferKernels.__doc__})
+
+
 class _ReplayStorage:
     """The attributes ``DiffusionReplayBuffer.__init__`` (simple_replay.py:99-116) sets, nothing else: the base of
     ``DiffusionReplayBuffer`` where the reference package is not importable."""
@@ -197,3 +306,8 @@ try:        # the reference's own storage / bookkeeping when it is installed nex
 except Exception:        # not installed (tests, benchmarks): attribute holder only
     _ReferenceReplayBuffer = _ReplayStorage
 DiffusionReplayBuffer = accelerate_replay_buffer(_ReferenceReplayBuffer)
+try:        # needs the reference's clustering dependencies (dtaidistance, scipy) as well
+    from ddiffpg.replay.diffusion_replay import DiffusionGoalBuffer as _ReferenceGoalBuffer
+    DiffusionGoalBuffer = accelerate_goal_buffer(_ReferenceGoalBuffer)
+except Exception:
+    DiffusionGoalBuffer = None

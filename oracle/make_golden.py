@@ -335,10 +335,85 @@ def replay_fixture():
     print("n2_replay: port == reference")
 
 
+def goal_buffer_fixture():
+    """N2, the caller side: the reference's own DiffusionGoalBuffer.sample_batch / add_temp_data
+    (ddiffpg/replay/diffusion_replay.py:250-332) on a small replay + temp buffer, with its torch.randint draws recorded.
+    The module is loaded by path; its clustering dependency (dtaidistance) and the Q scheduler (pulls gym through
+    ddiffpg.models) are absent here and not on this path: both are stubbed, and the buffer object is built without
+    its constructor (which only sets the attributes assigned below)."""
+    import sys
+    import types
+    sys.path.insert(0, ref_loader.REF_ROOT)
+    stub = types.ModuleType("dtaidistance"); stub.dtw_ndim = None
+    sys.modules.setdefault("dtaidistance", stub)
+    qs = types.ModuleType("ddiffpg.utils.Q_scheduler"); qs.Q_scheduler = object
+    sys.modules.setdefault("ddiffpg.utils.Q_scheduler", qs)
+    from ddiffpg.replay.diffusion_replay import DiffusionGoalBuffer
+    from ddiffpg.replay.simple_replay import DiffusionReplayBuffer
+    g = torch.Generator().manual_seed(7100)
+    rb = DiffusionReplayBuffer(10000, 29, 8, device="cpu")
+    lens = [17, 30, 9, 22, 40, 13]
+    for tid, n in enumerate(lens):
+        tr = (torch.randn(n, 29, generator=g), torch.rand(n, 8, generator=g) * 2 - 1, torch.rand(n, 8, generator=g) * 2 - 1,
+              torch.rand(n, generator=g), torch.randn(n, 29, generator=g), torch.rand(n, generator=g) < 0.2)
+        rb.add_to_buffer(tr, tid)
+    rb.update_target_action_dim([-1, 0])                          # explore + 2 modes
+    rb.buf_target_action[1] += 0.25; rb.buf_target_action[2] -= 0.25
+    # add_temp_data calls replay_buffer.sample_batch with its default device='cuda' (no GPU here): same method, device="cpu"
+    import functools
+    rb.sample_batch = functools.partial(DiffusionReplayBuffer.sample_batch, rb, device="cpu")
+    gb = object.__new__(DiffusionGoalBuffer)
+    gb.device, gb.replay_buffer = "cpu", rb
+    gb.success_id, gb.unsuccess_id = [0, 1, 3, 4], [2, 5]
+    gb.clusters, gb.unsuccess_clusters = [[0, 3], [1, 4]], [[2], [5]]
+    gb.Qs, gb.embeddings = ["Q0", "Q1", "Q2"], [torch.zeros(5), torch.ones(5), -torch.ones(5)]
+    nt = 23
+    gb.temp_state, gb.temp_action = torch.randn(nt, 29, generator=g), torch.rand(nt, 8, generator=g) * 2 - 1
+    gb.temp_reward, gb.temp_next_state = torch.rand(nt, 1, generator=g), torch.randn(nt, 29, generator=g)
+    gb.temp_done = torch.rand(nt, 1, generator=g) < 0.3
+    batch = 50                                                    # 50 = 3 * 16 + 2: group 0 takes the remainder
+    store = dict(obs=rb.buf_obs.clone(), action=rb.buf_action.clone(), target_action=rb.buf_target_action.clone(),
+                 reward=rb.buf_reward.clone(), next_obs=rb.buf_next_obs.clone(), done=rb.buf_done.clone(), id=rb.buf_id.clone())
+    temp = dict(state=gb.temp_state, action=gb.temp_action, reward=gb.temp_reward, next_state=gb.temp_next_state, done=gb.temp_done)
+    plan = port.goal_buffer_plan(batch, gb.success_id, gb.unsuccess_id, gb.clusters, gb.unsuccess_clusters, nt, rb.buf_id)
+    recorded, real_randint = [], torch.randint
+
+    def recording_randint(high, size=None, device=None, **kw):   # the reference draws on `device`; record what it drew
+        t = real_randint(high, size, generator=g)
+        recorded.append(t)
+        return t
+    torch.randint = recording_randint
+    try:
+        data_list = gb.sample_batch(batch, device="cpu")
+    finally:
+        torch.randint = real_randint
+    save = {f"store_{k}": v.numpy() for k, v in store.items()}
+    save.update({f"temp_{k}": v.numpy() for k, v in temp.items()})
+    it = iter(recorded)
+    for i, ((grp, b_sample, b_temp), d) in enumerate(zip(plan, data_list)):
+        draw = next(it) if b_sample else None
+        tdraw = next(it) if b_temp else None
+        assert (draw is None or draw.shape[0] == b_sample) and (tdraw is None or tdraw.shape[0] == b_temp)
+        pd, rows = port.goal_buffer_group(store, temp, grp, i, draw, tdraw)
+        assert all(torch.equal(a.float(), b) for a, b in zip(d["batch"], pd)), i
+        assert (rows is None and d["indices"] is None) or torch.equal(rows, d["indices"])
+        assert d["Q"] == gb.Qs[i] and torch.equal(d["embedding"], gb.embeddings[i])
+        save[f"draw_{i}"] = draw.numpy() if draw is not None else np.zeros(0, np.int64)
+        save[f"tdraw_{i}"] = tdraw.numpy() if tdraw is not None else np.zeros(0, np.int64)
+        save[f"idx_{i}"] = d["indices"].numpy() if d["indices"] is not None else np.zeros(0, np.int64)
+        for name, t in zip(("obs", "action", "target", "reward", "next_obs", "done"), d["batch"]):
+            save[f"g{i}_{name}"] = t.float().numpy()
+    assert next(it, None) is None
+    save.update(batch=batch, success_id=np.array(gb.success_id), unsuccess_id=np.array(gb.unsuccess_id),
+                clusters=np.array(gb.clusters), unsuccess_clusters=np.array(gb.unsuccess_clusters))
+    np.savez(os.path.join(OUT, "n2_goal_buffer.npz"), **save)
+    print("n2_goal_buffer: port == reference;", [(len(p[0]), p[1], p[2]) for p in plan])
+
+
 if __name__ == "__main__":
     argv = set(__import__("sys").argv[1:])
     only = {"--noise-only": noise_fixture, "--critic-only": critic_fixture, "--rnd-only": rnd_fixture,
-            "--replay-only": replay_fixture}
+            "--replay-only": replay_fixture, "--goal-buffer-only": goal_buffer_fixture}
     if argv & set(only):
         for flag in sorted(argv & set(only)):
             only[flag]()
@@ -348,3 +423,4 @@ if __name__ == "__main__":
         critic_fixture()
         rnd_fixture()
         replay_fixture()
+        goal_buffer_fixture()

@@ -353,6 +353,34 @@ def replay_gather(bufs, indices, target_idx):
             bufs["reward"][indices], bufs["next_obs"][indices], bufs["done"][indices].float())
 
 
+def goal_buffer_plan(batch_size, success_id, unsuccess_id, clusters, unsuccess_clusters, temp_size, buf_id):
+    """The group / size split of DiffusionGoalBuffer.sample_batch (replay/diffusion_replay.py:255-266) and the
+    temp-buffer share of add_temp_data (:286-292): per group (trajectory ids, rows from the replay, rows from the
+    temp buffer)."""
+    groups = [list(success_id) + list(unsuccess_id)] + [list(c) + list(u) for c, u in zip(clusters, unsuccess_clusters)]
+    sizes = [batch_size // len(groups)] * len(groups)
+    sizes[0] += batch_size % len(groups)
+    plan = []
+    for i, (grp, b) in enumerate(zip(groups, sizes)):
+        buffer_size = int(torch.isin(buf_id, torch.tensor(grp, dtype=buf_id.dtype)).sum())
+        b_temp = int((temp_size / (temp_size + buffer_size)) * b) if i == 0 else 0
+        plan.append((grp, b - b_temp, b_temp))
+    return plan
+
+
+def goal_buffer_group(bufs, temp, grp, target_idx, draw, temp_draw):
+    """One add_temp_data call (:285-332) after its two index draws.  temp: dict state, action, reward, next_state, done."""
+    parts, rows = [], None
+    if draw is not None:
+        avail = torch.where(torch.isin(bufs["id"], torch.tensor(grp, dtype=bufs["id"].dtype)))[0]
+        rows = avail[draw]
+        parts.append(replay_gather(bufs, rows, target_idx))
+    if temp_draw is not None:
+        parts.append((temp["state"][temp_draw], temp["action"][temp_draw], temp["action"][temp_draw],
+                      temp["reward"][temp_draw], temp["next_state"][temp_draw], temp["done"][temp_draw].float()))
+    return tuple(torch.cat([p[k].float() for p in parts]) for k in range(6)), rows
+
+
 def add_embedding_port(state, embedding, zero_indices):
     """add_embedding (utils/torch_util.py:17-43) with the np.random.choice draw passed in."""
     new_embedding = embedding.unsqueeze(0).repeat(state.shape[0], 1)

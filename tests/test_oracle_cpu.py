@@ -301,6 +301,25 @@ def test_port_replay_matches_reference_fixture():
     np.testing.assert_array_equal(store["target_action"].numpy(), g["target_after"])
 
 
+def test_port_goal_buffer_matches_reference_fixture():
+    """N2, caller side: DiffusionGoalBuffer.sample_batch / add_temp_data (diffusion_replay.py:250-332) with the
+    reference's recorded draws -- group split, temp-buffer share of group 0, and the six tensors of every group."""
+    g = load_golden("n2_goal_buffer")
+    store = {k[6:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("store_")}
+    temp = {k[5:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("temp_")}
+    plan = port.goal_buffer_plan(int(g["batch"]), g["success_id"].tolist(), g["unsuccess_id"].tolist(),
+                                 g["clusters"].tolist(), g["unsuccess_clusters"].tolist(), temp["state"].shape[0], store["id"])
+    assert [(p[1], p[2]) for p in plan] == [(g[f"draw_{i}"].shape[0], g[f"tdraw_{i}"].shape[0]) for i in range(3)]
+    assert plan[0][2] > 0 and sum(p[1] + p[2] for p in plan) == int(g["batch"])
+    for i, (grp, b_sample, b_temp) in enumerate(plan):
+        draw = torch.from_numpy(g[f"draw_{i}"]) if b_sample else None
+        tdraw = torch.from_numpy(g[f"tdraw_{i}"]) if b_temp else None
+        data, rows = port.goal_buffer_group(store, temp, grp, i, draw, tdraw)
+        np.testing.assert_array_equal(rows.numpy(), g[f"idx_{i}"])
+        for name, t in zip(("obs", "action", "target", "reward", "next_obs", "done"), data):
+            np.testing.assert_array_equal(t.numpy(), g[f"g{i}_{name}"], err_msg=f"group {i} {name}")
+
+
 def test_bench_reference_arm_prints_one_json_line():
     """bench.py contract on the CPU-only arm: exactly one line on stdout, valid JSON, the keys the driver reads."""
     import json

@@ -579,6 +579,57 @@ def test_replay_sample_and_scatter_match_reference_fixture():
         assert any(torch.equal(after[2, d], c) for c in cands)
 
 
+def test_goal_buffer_sample_batch_matches_reference_fixture():
+    """DiffusionGoalBuffer.sample_batch / add_temp_data (diffusion_replay.py:250-332) through GoalBufferKernels, byte-exact
+    against the reference's own outputs with its recorded torch.randint draws replayed in the reference's order."""
+    from ddiffpg_b200 import GoalBufferKernels
+    g = load_golden("n2_goal_buffer")
+
+    class Holder(GoalBufferKernels):        # the attributes of the reference class the two methods read
+        pass
+    gb = Holder()
+    gb.device, gb.replay_buffer = "cuda", _replay_from_fixture(g)
+    gb.success_id, gb.unsuccess_id = g["success_id"].tolist(), g["unsuccess_id"].tolist()
+    gb.clusters, gb.unsuccess_clusters = g["clusters"].tolist(), g["unsuccess_clusters"].tolist()
+    gb.Qs, gb.embeddings = ["Q0", "Q1", "Q2"], [torch.zeros(5), torch.ones(5), -torch.ones(5)]
+    gb.temp_state, gb.temp_action = _dev(g["temp_state"]), _dev(g["temp_action"])
+    gb.temp_reward, gb.temp_next_state, gb.temp_done = _dev(g["temp_reward"]), _dev(g["temp_next_state"]), _dev(g["temp_done"])
+    draws = []
+    for i in range(3):
+        draws += [g[f"draw_{i}"]] if g[f"draw_{i}"].shape[0] else []
+        draws += [g[f"tdraw_{i}"]] if g[f"tdraw_{i}"].shape[0] else []
+    it = iter(draws)
+    real = torch.randint
+
+    def replay(high, size=None, device=None, **kw):
+        d = next(it)
+        assert tuple(size) == d.shape and int(d.max()) < high
+        return torch.from_numpy(d).to(device)
+    torch.randint = replay
+    try:
+        data_list = gb.sample_batch(int(g["batch"]))
+        assert next(it, None) is None
+        it = iter(draws[:2])
+        single, rows0 = gb.add_temp_data(g["draw_0"].shape[0] + g["tdraw_0"].shape[0], gb.success_id + gb.unsuccess_id, 0)
+    finally:
+        torch.randint = real
+    names = ("obs", "action", "target", "reward", "next_obs", "done")
+    for i, d in enumerate(data_list):
+        assert d["Q"] == gb.Qs[i] and torch.equal(d["embedding"], gb.embeddings[i])
+        assert torch.equal(d["indices"].cpu(), torch.from_numpy(g[f"idx_{i}"]))
+        for name, t in zip(names, d["batch"]):
+            assert t.is_cuda and t.dtype == torch.float32
+            assert torch.equal(t.cpu(), torch.from_numpy(g[f"g{i}_{name}"])), (i, name)
+    assert torch.equal(rows0.cpu(), torch.from_numpy(g["idx_0"]))
+    for name, t in zip(names, single):
+        assert torch.equal(t.cpu(), torch.from_numpy(g[f"g0_{name}"])), name
+    # available_indices (table look-up) == torch.where(torch.isin(...)) of simple_replay.py:151, any id subset
+    rb = gb.replay_buffer
+    for ids in ([0], [5, 2], [1, 3, 4], list(range(6)), [9]):
+        ref = torch.where(torch.isin(rb.buf_id, torch.tensor(ids, device="cuda").to(rb.buf_id.dtype)))[0]
+        assert torch.equal(rb.available_indices(ids), ref) and rb.get_buffer_size(ids) == ref.shape[0]
+
+
 def test_replay_two_zeroing_draws_modes_and_range_checks():
     """sample_groups with DIFFERENT zero_state / zero_next draws (the reference draws two independent p = 0.5 masks,
     ddiffpg.py:246-252), add_embedding(modes=...) (utils/torch_util.py:24-34) and the IndexError of a stale index."""
