@@ -49,26 +49,22 @@ constexpr int kStageBytes = 256 * 128;
 #endif
 constexpr int kStages = DDP_QC_STAGES;
 constexpr int kASlots = 4;
-// Epilogue warps: kGroups groups of 8 warps (4 TMEM lane quarters x 2 column halves of a 64-column chunk).  The groups
-// drain alternate chunks of an accumulator, so two chunks are in flight per SM sub-partition: one group's TMEM wait /
-// proxy fence / barrier hand-over hides behind the other group's arithmetic.
 #ifndef DDP_QC_EPI_WARPS
 #define DDP_QC_EPI_WARPS 8
 #endif
+#ifndef DDP_QC_PAIR_PUBLISH
+#define DDP_QC_PAIR_PUBLISH 0   // 1: two chunks per proxy fence (measured slower: the hand-off latency matters more)
+#endif
+constexpr bool kPairPublish = DDP_QC_PAIR_PUBLISH != 0;
 constexpr int kEpiWarps = DDP_QC_EPI_WARPS;      // 8 or 16: 2 or 4 warps per SM sub-partition
-constexpr int kGroups = kEpiWarps / 8;
-static_assert(kGroups == 1 || kGroups == 2, "8 or 16 epilogue warps");
-constexpr int kSubs = kEpiWarps / 4;               // warps per TMEM lane quarter (they split the 64 logit columns)
-constexpr int kColsPerWarp = 32;                   // columns of a chunk owned by one warp
+constexpr int kColsPerWarp = 64 / (kEpiWarps / 4);  // columns of a chunk owned by one warp (32 or 16)
 constexpr int kEpiThreads = kEpiWarps * 32;
-// 16 epilogue warps: the two service warps sit in a warpgroup of their own (two idle warps), which hands registers to
-// the epilogue warpgroups (setmaxnreg): 640 threads start at 96 registers, service 32, epilogue 112
-constexpr int kThreads = kEpiThreads + (kGroups == 2 ? 128 : 64);
+constexpr int kThreads = kEpiThreads + 64;
 constexpr int kTmemCols = 512;
 #ifndef DDP_QC_ABLATE
 #define DDP_QC_ABLATE 0     // timing experiments only (results are wrong when set): 1 no proxy fence, 2 no ELU' scratch
 #endif                      // traffic, 4 no MUFU, 8 no TMEM loads in the drains, 16 no drain arithmetic
-constexpr int kAblate = DDP_QC_ABLATE;
+constexpr int kAblate = DDP_QC_ABLATE;     // measurements: profiles/r02/ablation_qchain.txt
 constexpr int kBiasPerNet = 512 + 256 + 256 + 64;     // b1 | b2 | b3 | b4 slots (floats)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kMaxIters = 32;               // iterations one cooperative launch can carry
@@ -111,8 +107,7 @@ struct SMQ {
     static constexpr uint32_t dl = aring + kASlots * kChunkBytes;
     static constexpr uint32_t a0 = dl + 2 * kChunkBytes;                   // [obs | act | 0] chunk of the tile
     static constexpr uint32_t bias = a0 + kChunkBytes;
-    static constexpr uint32_t red = bias + 2 * kBiasPerNet * 4;           // [3][kSubs][128] floats: softmax partials
-    static constexpr uint32_t bars = red + 3 * 4 * kRows * 4;
+    static constexpr uint32_t bars = bias + 2 * kBiasPerNet * 4;
     static constexpr uint32_t tmem_ptr = bars + 8 * 24;
     static constexpr uint32_t total = tmem_ptr + 8;
 };
@@ -149,8 +144,8 @@ __device__ __forceinline__ bool q_gated(const QcArgs& a, int p) { return p * a.p
 struct QEpi {
     uint8_t* smem;
     uint32_t bars, tmem_base, acc_cnt;
-    uint32_t seq;                   // chunks handed to the A ring so far (all groups count every chunk)
-    int q, ch, grp, sub, lane, my_row;
+    int q, ch, lane, my_row;
+    QRing as;
     uint16_t* dscr;                 // this CTA's scratch block
     long long* dbg;
     __device__ __forceinline__ void wait_acc() {
@@ -180,13 +175,14 @@ __device__ __forceinline__ void emit_fwd(const QEpi& e, uint8_t* slot, const uin
         x[i4 * 4 + 0] = __uint_as_float(v[i4 * 4 + 0]) + b.x; x[i4 * 4 + 1] = __uint_as_float(v[i4 * 4 + 1]) + b.y;
         x[i4 * 4 + 2] = __uint_as_float(v[i4 * 4 + 2]) + b.z; x[i4 * 4 + 3] = __uint_as_float(v[i4 * 4 + 3]) + b.w;
     }
-    // ELU without compare/select (those run on the half-rate ALU pipe, which bounded this drain): with t = min(x, 0),
-    // e = exp(t) is the derivative (exactly 1 for x >= 0) and elu(x) = (x - t) + (e - 1) -- exact in both branches
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d[i] = (kAblate & 4) ? x[i] * kLog2e : ex2_approx(x[i] * kLog2e);
+    // (a compare/select-free form -- t = min(x, 0), e = exp t, elu = (x - t) + (e - 1) -- measured 1.3 % slower)
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const float t = fminf(x[i], 0.f);
-        d[i] = (kAblate & 4) ? t * kLog2e : ex2_approx(t * kLog2e);
-        x[i] = (x[i] - t) + (d[i] - 1.f);
+        const bool neg = x[i] < 0.f;
+        x[i] = neg ? d[i] - 1.f : x[i];
+        d[i] = neg ? d[i] : 1.f;
     }
     store_chunk16(slot, e.my_row, col0, x);
     uint4 w0, w1;
@@ -210,31 +206,27 @@ __device__ __forceinline__ void emit_bwd(const QEpi& e, uint8_t* slot, const uin
     store_chunk16(slot, e.my_row, col0, x);
 }
 
-// Drain `nchunks` 64-column chunks of the accumulator at TMEM column `col` into the A ring.  Chunk c of the call is
-// the ring's chunk number e.seq + c; group g takes the chunks whose ring number is g modulo kGroups.  A warp owns 32
-// columns of its chunks (two 16-column TMEM loads, the second in flight while the first is processed).
+// Drain `nchunks` 64-column chunks of the accumulator at TMEM column `col` into the A ring.  This warp owns 32
+// columns of each chunk (two 16-column TMEM loads, the second in flight while the first is processed).
 // FWD: +bias, ELU, derivative to scratch group `g0 + ...`; else: times the derivative read back from there.
-// signal_after >= 0: lo_free is signalled once this warp has read everything it reads of chunks 0..signal_after.
 template <bool FWD>
 __device__ __forceinline__ void q_drain(QEpi& e, int col, int nchunks, const float* bias, int g0, int signal_after) {
     const uint32_t tbase = e.tmem_base + ((uint32_t)(e.q * 32) << 16) + col + e.ch * kColsPerWarp;
     // scratch group of this warp's first 16 columns inside chunk 0 (4 groups per chunk)
     uint16_t* dbase = e.dscr + (size_t)(g0 + e.ch * (kColsPerWarp / 16)) * kRows * 16 + e.my_row * 8;
-    const int c_first = (int)((e.grp - e.seq) & (kGroups - 1));
     uint32_t va[16], vb[16];
     uint4 d0{}, d1{}, d2{}, d3{};
     if (kAblate & 8) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { va[i] = e.seq * 7u + i * e.lane; vb[i] = e.seq * 5u + i * e.lane; }
-    }
-    if (c_first < nchunks) {
-        if (!(kAblate & 8)) tmem_ld16(tbase + c_first * 64, va);
-        if (!FWD && !(kAblate & 2)) {
-            const uint4* dp = reinterpret_cast<const uint4*>(dbase + (size_t)c_first * 4 * kRows * 16);
-            d0 = __ldcg(dp); d1 = __ldcg(dp + kRows); d2 = __ldcg(dp + kRows * 2); d3 = __ldcg(dp + kRows * 3);
+        for (int i = 0; i < 16; ++i) { va[i] = (uint32_t)(col * 7 + i * e.lane); vb[i] = (uint32_t)(col * 5 + i * e.lane); }
+    } else tmem_ld16(tbase, va);
+    if (!FWD) {
+        const uint4* dp = reinterpret_cast<const uint4*>(dbase);
+        if (!(kAblate & 2)) {
+            d0 = __ldcg(dp); d1 = __ldcg(dp + kRows);
+            if (kColsPerWarp == 32) { d2 = __ldcg(dp + kRows * 2); d3 = __ldcg(dp + kRows * 3); }
         }
     }
-    if (signal_after >= 0 && c_first > signal_after && e.lane == 0) mbar_arrive(qb_lo_free(e.bars));   // nothing to read there
 #ifdef DDP_QC_FINE_TIMING
     long long* fine = (e.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? e.dbg + (FWD ? 16 : 24) : nullptr;
     long long f0 = fine ? clock64() : 0, f1;
@@ -244,50 +236,79 @@ __device__ __forceinline__ void q_drain(QEpi& e, int col, int nchunks, const flo
 #define QC_FINE(slot) do { } while (0)
 #define QC_FINE_COUNT() do { } while (0)
 #endif
-    for (int c = c_first; c < nchunks; c += kGroups) {
-        const uint32_t n = e.seq + (uint32_t)c;
-        const int slot_i = (int)(n % kASlots);
-        const uint32_t ph = (n / kASlots) & 1u;
-        const int cn = c + kGroups;
-        uint16_t* dptr = dbase + (size_t)c * 4 * kRows * 16;
-        if (!(kAblate & 8)) { tmem_ld_wait(); tmem_ld16(tbase + c * 64 + 16, vb); }
-        QC_FINE(0);
-        mbar_wait(qb_a_empty(e.bars, slot_i), ph ^ 1);
-        QC_FINE(1);
-        uint8_t* slot = e.smem + SMQ::aring + slot_i * kChunkBytes;
-        if (kAblate & 16) { }
-        else if (FWD) emit_fwd(e, slot, va, bias + c * 64 + e.ch * 32, e.ch * 32, dptr);
-        else emit_bwd(e, slot, va, e.ch * 32, d0, d1);
-        QC_FINE(2);
-        if (!(kAblate & 8)) { tmem_ld_wait(); if (cn < nchunks) tmem_ld16(tbase + cn * 64, va); }
-        QC_FINE(3);
-        if (kAblate & 16) { }
-        else if (FWD) emit_fwd(e, slot, vb, bias + c * 64 + e.ch * 32 + 16, e.ch * 32 + 16, dptr + kRows * 16);
-        else {
-            emit_bwd(e, slot, vb, e.ch * 32 + 16, d2, d3);
-            if (cn < nchunks && !(kAblate & 2)) {
-                const uint4* dp = reinterpret_cast<const uint4*>(dbase + (size_t)cn * 4 * kRows * 16);
-                d0 = __ldcg(dp); d1 = __ldcg(dp + kRows);
-                d2 = __ldcg(dp + kRows * 2); d3 = __ldcg(dp + kRows * 3);
+    for (int c0 = 0; c0 < nchunks; c0 += kPairPublish ? 2 : 1) {
+        // two chunks per publication: the generic->async proxy fence is the expensive part of handing a chunk over
+        const int n2 = (!kPairPublish || nchunks - c0 < 2) ? 1 : 2;
+        QRing rs = e.as;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u >= n2) break;
+            const int c = c0 + u;
+            uint16_t* dptr = dbase + (size_t)c * 4 * kRows * 16;
+            if (kColsPerWarp == 32) {
+                if (!(kAblate & 8)) { tmem_ld_wait(); tmem_ld16(tbase + c * 64 + 16, vb); }
+                QC_FINE(0);
+                mbar_wait(qb_a_empty(e.bars, rs.idx), rs.phase ^ 1);
+                QC_FINE(1);
+                uint8_t* slot = e.smem + SMQ::aring + rs.idx * kChunkBytes;
+                rs.advance(kASlots);
+                if (kAblate & 16) { }
+                else if (FWD) emit_fwd(e, slot, va, bias + c * 64 + e.ch * 32, e.ch * 32, dptr);
+                else emit_bwd(e, slot, va, e.ch * 32, d0, d1);
+                QC_FINE(2);
+                if (!(kAblate & 8)) { tmem_ld_wait(); if (c + 1 < nchunks) tmem_ld16(tbase + (c + 1) * 64, va); }
+                QC_FINE(3);
+                if (kAblate & 16) { }
+                else if (FWD) emit_fwd(e, slot, vb, bias + c * 64 + e.ch * 32 + 16, e.ch * 32 + 16, dptr + kRows * 16);
+                else {
+                    emit_bwd(e, slot, vb, e.ch * 32 + 16, d2, d3);
+                    if (c + 1 < nchunks) {
+                        const uint4* dp = reinterpret_cast<const uint4*>(dptr + (size_t)4 * kRows * 16);
+                        if (!(kAblate & 2)) {
+                            d0 = __ldcg(dp); d1 = __ldcg(dp + kRows);
+                            d2 = __ldcg(dp + kRows * 2); d3 = __ldcg(dp + kRows * 3);
+                        }
+                    }
+                }
+                QC_FINE(4);
+            } else {
+                // 16 columns per warp: the two register buffers alternate chunk by chunk (u is compile-time)
+                tmem_ld_wait();
+                if (c + 1 < nchunks) { if (u == 0) tmem_ld16(tbase + (c + 1) * 64, vb); else tmem_ld16(tbase + (c + 1) * 64, va); }
+                uint4 e0 = d0, e1 = d1;
+                if (!FWD && c + 1 < nchunks) {
+                    const uint4* dp = reinterpret_cast<const uint4*>(dptr + (size_t)4 * kRows * 16);
+                    d0 = __ldcg(dp); d1 = __ldcg(dp + kRows);
+                }
+                mbar_wait(qb_a_empty(e.bars, rs.idx), rs.phase ^ 1);
+                uint8_t* slot = e.smem + SMQ::aring + rs.idx * kChunkBytes;
+                rs.advance(kASlots);
+                if (FWD) emit_fwd(e, slot, u == 0 ? va : vb, bias + c * 64 + e.ch * 16, e.ch * 16, dptr);
+                else emit_bwd(e, slot, u == 0 ? va : vb, e.ch * 16, e0, e1);
             }
+            QC_FINE_COUNT();
         }
-        QC_FINE(4);
-        QC_FINE_COUNT();
         if (!(kAblate & 1)) fence_proxy_async();
         tc_fence_before();
         __syncwarp();
         if (e.lane == 0) {
-            mbar_arrive(qb_a_full(e.bars, slot_i));
-            if (c <= signal_after && cn > signal_after) mbar_arrive(qb_lo_free(e.bars));
+            mbar_arrive(qb_a_full(e.bars, e.as.idx));
+            if (n2 == 2) mbar_arrive(qb_a_full(e.bars, e.as.idx + 1 == kASlots ? 0 : e.as.idx + 1));
+            if (signal_after >= c0 && signal_after < c0 + n2) mbar_arrive(qb_lo_free(e.bars));
         }
+        e.as = rs;
         QC_FINE(5);
     }
-    e.seq += (uint32_t)nchunks;
 #undef QC_FINE
 #undef QC_FINE_COUNT
 }
 
+#if DDP_QC_EPI_WARPS >= 16
+// 18 warps: ptxas would round the block up to 640 threads and cap at 96 registers
+__global__ void __maxnreg__(96)
+#else
 __global__ void __launch_bounds__(kThreads, 1)
+#endif
 q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -300,11 +321,11 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(qb_w_full(bars, i), 1); mbar_init(qb_w_empty(bars, i), 1); }
-        for (int i = 0; i < kASlots; ++i) { mbar_init(qb_a_full(bars, i), 8); mbar_init(qb_a_empty(bars, i), 1); }
+        for (int i = 0; i < kASlots; ++i) { mbar_init(qb_a_full(bars, i), kEpiWarps); mbar_init(qb_a_empty(bars, i), 1); }
         mbar_init(qb_acc_full(bars, 0), 1);
         mbar_init(qb_acc_full(bars, 1), 1);
         mbar_init(qb_lo_free(bars), kEpiWarps);
-        mbar_init(qb_dl_full(bars), kEpiWarps);
+        mbar_init(qb_dl_full(bars), 4);
         mbar_init(qb_a0_full(bars), 1);
         mbar_init(qb_a0_free(bars), 1);
         mbar_init(qb_acc_free(bars), kEpiWarps);
@@ -317,8 +338,6 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + SMQ::tmem_ptr);
 
-    if (warp >= kEpiWarps) {
-    if (kGroups == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == kEpiWarps) {
         // ============================================================== TMA producer (one lane)
         if (lane == 0) {
@@ -461,14 +480,11 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                 }
             }
         }
-    }
     } else {
         // ============================================================== epilogue warps
-        if (kGroups == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         QEpi e;
-        e.smem = smem; e.bars = bars; e.tmem_base = tmem_base; e.acc_cnt = 0; e.seq = 0;
-        e.q = warp & 3; e.ch = (warp >> 2) & 1; e.grp = warp >> 3; e.sub = warp >> 2; e.lane = lane; e.my_row = e.q * 32 + lane;
-        float* red = reinterpret_cast<float*>(smem + SMQ::red);            // [3][4][128]
+        e.smem = smem; e.bars = bars; e.tmem_base = tmem_base; e.acc_cnt = 0;
+        e.q = warp & 3; e.ch = warp >> 2; e.lane = lane; e.my_row = e.q * 32 + lane;
         e.dbg = a.dbg;
         const int G = (a.h1 + a.h2 + a.h3) >> 4;              // 16-column scratch groups per net
         const int g1 = 0, g2 = a.h1 >> 4, g3 = (a.h1 + a.h2) >> 4;
@@ -513,23 +529,24 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                 e.wait_acc();
                 q_drain<true>(e, a.h2, NC3, sb + 768, g3, -1);      // F3 -> a3
                 QC_TICK(4);
-                {
-                    // logits -> softmax, expectation, d Q / d logits (unmasked): the kSubs warps of a TMEM lane quarter
-                    // split the 64 columns of a row; the row's max / sum / first moment go through shared memory
-                    constexpr int W = 64 / kSubs;                  // columns per warp (16 or 32)
+                if (e.ch == 0) {
+                    // logits -> softmax, expectation, d Q / d logits (unmasked) for this thread's row
                     e.wait_acc();
                     // columns >= atoms carry a bias of -inf (see the bias load): their exponentials are exact zeros
-                    float l[W];
-#pragma unroll
-                    for (int h = 0; h < W / 16; ++h) {
-                        uint32_t v[16];
-                        tmem_ld16(tmem_base + ((uint32_t)(e.q * 32) << 16) + e.sub * W + h * 16, v);
+                    float l[64];
+                    {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(e.q * 32) << 16), v0);
+                        tmem_ld32(tmem_base + ((uint32_t)(e.q * 32) << 16) + 32, v1);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i4 = 0; i4 < 4; ++i4) {
-                            const float4 b = *reinterpret_cast<const float4*>(sb + 1024 + e.sub * W + h * 16 + i4 * 4);
-                            l[h * 16 + i4 * 4 + 0] = __uint_as_float(v[i4 * 4 + 0]) + b.x; l[h * 16 + i4 * 4 + 1] = __uint_as_float(v[i4 * 4 + 1]) + b.y;
-                            l[h * 16 + i4 * 4 + 2] = __uint_as_float(v[i4 * 4 + 2]) + b.z; l[h * 16 + i4 * 4 + 3] = __uint_as_float(v[i4 * 4 + 3]) + b.w;
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(sb + 1024 + i4 * 4);
+                            const float4 b1 = *reinterpret_cast<const float4*>(sb + 1056 + i4 * 4);
+                            l[i4 * 4 + 0] = __uint_as_float(v0[i4 * 4 + 0]) + b0.x; l[i4 * 4 + 1] = __uint_as_float(v0[i4 * 4 + 1]) + b0.y;
+                            l[i4 * 4 + 2] = __uint_as_float(v0[i4 * 4 + 2]) + b0.z; l[i4 * 4 + 3] = __uint_as_float(v0[i4 * 4 + 3]) + b0.w;
+                            l[32 + i4 * 4 + 0] = __uint_as_float(v1[i4 * 4 + 0]) + b1.x; l[32 + i4 * 4 + 1] = __uint_as_float(v1[i4 * 4 + 1]) + b1.y;
+                            l[32 + i4 * 4 + 2] = __uint_as_float(v1[i4 * 4 + 2]) + b1.z; l[32 + i4 * 4 + 3] = __uint_as_float(v1[i4 * 4 + 3]) + b1.w;
                         }
                     }
                     // the accumulator columns are free again: the MMA warp may start the next net's first layer
@@ -538,54 +555,46 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                     if ((j == 0 || !backward) && lane == 0) mbar_arrive(qb_acc_free(bars));
                     float mx4[4] = {l[0], l[1], l[2], l[3]};
 #pragma unroll
-                    for (int i = 4; i < W; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], l[i]);
-                    red[e.sub * kRows + e.my_row] = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-                    q_epi_bar_sync();
-                    float mxl = red[e.my_row];
-#pragma unroll
-                    for (int s2 = 1; s2 < kSubs; ++s2) mxl = fmaxf(mxl, red[s2 * kRows + e.my_row]);
-                    mxl *= kLog2e;
+                    for (int i = 4; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], l[i]);
+                    const float mxl = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * kLog2e;
                     float sum4[4] = {0.f, 0.f, 0.f, 0.f}, qz4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int i = 0; i < W; ++i) {
+                    for (int i = 0; i < 64; ++i) {
                         const float ex = ex2_approx(fmaf(l[i], kLog2e, -mxl));
                         l[i] = ex;
                         sum4[i & 3] += ex;
-                        qz4[i & 3] = fmaf(ex, (float)(e.sub * W + i), qz4[i & 3]);
+                        qz4[i & 3] = fmaf(ex, (float)i, qz4[i & 3]);
                     }
-                    red[(4 + e.sub) * kRows + e.my_row] = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-                    red[(8 + e.sub) * kRows + e.my_row] = (qz4[0] + qz4[1]) + (qz4[2] + qz4[3]);
-                    q_epi_bar_sync();
-                    float ssum = red[4 * kRows + e.my_row], sqz = red[8 * kRows + e.my_row];
-#pragma unroll
-                    for (int s2 = 1; s2 < kSubs; ++s2) { ssum += red[(4 + s2) * kRows + e.my_row]; sqz += red[(8 + s2) * kRows + e.my_row]; }
-                    const float inv = 1.f / ssum;
-                    const float Qi = sqz * inv;                                          // expectation of the atom index
+                    const float inv = 1.f / ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+                    const float Qi = ((qz4[0] + qz4[1]) + (qz4[2] + qz4[3])) * inv;      // expectation of the atom index
                     qv[j] = fmaf(a.dz, Qi, a.v_min);
                     float* pout = a.p_out[j];
                     if (pout && valid) {
 #pragma unroll
-                        for (int i = 0; i < W; ++i)
-                            if (e.sub * W + i < a.atoms) pout[row * a.atoms + e.sub * W + i] = l[i] * inv;
+                        for (int at = 0; at < 64; ++at)
+                            if (at < a.atoms) pout[row * a.atoms + at] = l[at] * inv;
                     }
                     uint8_t* dl = smem + SMQ::dl + j * kChunkBytes;
                     const float sdz = a.dz * inv;                                       // p (z - Q) = ex * inv * dz * (i - Qi)
 #pragma unroll
-                    for (int i8 = 0; i8 < W / 8; ++i8) {
+                    for (int i8 = 0; i8 < 8; ++i8) {
                         float d[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) d[i] = l[i8 * 8 + i] * (sdz * ((float)(e.sub * W + i8 * 8 + i) - Qi));
+                        for (int i = 0; i < 8; ++i) d[i] = l[i8 * 8 + i] * (sdz * ((float)(i8 * 8 + i) - Qi));
                         uint4 w;
                         w.x = pack_bf16x2(d[0], d[1]); w.y = pack_bf16x2(d[2], d[3]);
                         w.z = pack_bf16x2(d[4], d[5]); w.w = pack_bf16x2(d[6], d[7]);
-                        *reinterpret_cast<uint4*>(dl + sw128_offset(e.my_row, e.sub * W + i8 * 8)) = w;
+                        *reinterpret_cast<uint4*>(dl + sw128_offset(e.my_row, i8 * 8)) = w;
                     }
+                    tc_fence_before();
+                } else {
+                    ++e.acc_cnt;                   // the logits stage is read by the ch == 0 warps only
+                    if ((j == 0 || !backward) && lane == 0) mbar_arrive(qb_acc_free(bars));
                 }
                 QC_TICK(5);
             }
-            {
-                constexpr int W = 64 / kSubs;
-                if (e.sub == 0 && a.qmin && valid) a.qmin[row] = fminf(qv[0], qv[1]);
+            if (e.ch == 0) {
+                if (a.qmin && valid) a.qmin[row] = fminf(qv[0], qv[1]);
                 if (backward) {
                     // torch.min backward: the smaller head takes the gradient, exact ties split it evenly
                     const float w0 = qv[0] == qv[1] ? 0.5f : (qv[0] < qv[1] ? 1.f : 0.f);
@@ -594,8 +603,8 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                         const float w = j == 0 ? w0 : 1.f - w0;
                         if (w == 1.f) continue;
                         uint8_t* dl = smem + SMQ::dl + j * kChunkBytes;
-                        for (int i8 = 0; i8 < W / 8; ++i8) {
-                            uint4* ptr = reinterpret_cast<uint4*>(dl + sw128_offset(e.my_row, e.sub * W + i8 * 8));
+                        for (int i8 = 0; i8 < 8; ++i8) {
+                            uint4* ptr = reinterpret_cast<uint4*>(dl + sw128_offset(e.my_row, i8 * 8));
                             uint4 v = make_uint4(0, 0, 0, 0);
                             if (w != 0.f) {
                                 v = *ptr;
@@ -626,7 +635,7 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                 e.wait_acc();
                 q_drain<false>(e, 0, NC1, nullptr, g1, 0);             // B2 -> dz1
                 QC_TICK(8);
-                if (e.sub == 0) {
+                if (e.ch == 0) {
                     e.wait_acc();
                     uint32_t v[16];
                     tmem_ld16(tmem_base + ((uint32_t)(e.q * 32) << 16), v);
@@ -642,7 +651,7 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                 }
                 QC_TICK(9);
             }
-            if (e.sub == 0) {
+            if (e.ch == 0) {
                 const float sc = a.scale[m];
                 float ss = 0.f;
                 if (valid) {

@@ -286,14 +286,21 @@ class DiffusionPolicy(nn.Module):
                 self._ws["host_stage"] = stage
             _, st_dev, out_dev, noise_bufs = stage
             main.wait_stream(d2h)              # the previous call's downloads have left out_dev
-            for ri, (lo, hi) in enumerate(ranges):
-                with torch.cuda.stream(h2d):
+            # every upload is queued first (they run back to back on the copy engine), and all noise is drawn while the
+            # first one is in flight: nothing but the first range's upload sits in front of the first launch
+            uploaded = []
+            with torch.cuda.stream(h2d):
+                for lo, hi in ranges:
                     st_dev[lo:hi].copy_(state_host[lo:hi], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(h2d)
-                main.wait_event(ev)
+                    uploaded.append(ev)
+            for buf in noise_bufs:
+                buf.normal_()
+            for ri, (lo, hi) in enumerate(ranges):
+                main.wait_event(uploaded[ri])
                 n = hi - lo
-                noise = noise_bufs[ri].normal_()
+                noise = noise_bufs[ri]
                 ws_bytes = lib().ddp_actor_sample_workspace_bytes(shape, n, prec)
                 ws = self._workspace("sample", ws_bytes, dev) if ws_bytes else None
                 check(lib().ddp_actor_sample(shape, ptr(packed), ptr(st_dev[lo:hi]), ptr(noise), ptr(out_dev[lo:hi]), n,
