@@ -34,7 +34,7 @@ int clip_adamw(float* p, float* g, float* m, float* v, size_t n, int step, float
                float wd, float max_norm, float* norm_out, float* scratch, cudaStream_t st);
 int clip_adamw_dev(float* p, float* g, float* m, float* v, size_t n, int* step_dev, float lr, float b1, float b2,
                    float eps, float wd, float max_norm, float* norm_out, float* scratch, cudaStream_t st);
-int pack_q_fp32(const QLayout& L, const float* const p[], float* out, cudaStream_t st);
+int pack_q_fp32(const QLayout& L, const float* const p[], float* out, cudaStream_t st, bool bias_only);
 int q_forward_fma(const QLayout& L, const float* pk, const int64_t* seg_off, const float* obs, const float* act,
                   float* qmin, float* p1, float* p2, float* dq_da, long B, cudaStream_t st);
 size_t q_ascent_workspace(const QLayout& L, long B, int iters);
@@ -222,7 +222,7 @@ int ddp_q_pack(const ddp_q_shape* s, const float* const params[], void* packed, 
         if (!params[i]) DDP_FAIL(DDP_ERR_ARG, "ddp_q_pack: params[%d] is NULL", i);
     if (precision != DDP_FP32 && precision != DDP_BF16) DDP_FAIL(DDP_ERR_ARG, "unknown precision %d", precision);
     QLayout L = make_q_layout(*s, precision);
-    rc = pack_q_fp32(L, params, (float*)packed, (cudaStream_t)stream);
+    rc = pack_q_fp32(L, params, (float*)packed, (cudaStream_t)stream, precision == DDP_BF16);
     if (rc != DDP_OK || precision == DDP_FP32) return rc;
     return pack_q_tc(L, params, packed, (cudaStream_t)stream);
 }
@@ -345,7 +345,7 @@ int ddp_rnd_pack(const ddp_rnd_shape* s, const float* const params[16], void* pa
     if (!params || !packed) DDP_FAIL(DDP_ERR_ARG, "ddp_rnd_pack: NULL argument");
     for (int i = 0; i < 16; ++i)
         if (!params[i]) DDP_FAIL(DDP_ERR_ARG, "ddp_rnd_pack: params[%d] is NULL", i);
-    return pack_q_fp32(L, params, (float*)packed, (cudaStream_t)stream);
+    return pack_q_fp32(L, params, (float*)packed, (cudaStream_t)stream, false);
 }
 
 int ddp_rnd_novelty(const ddp_rnd_shape* s, const void* packed, const float* x, float* novelty_out, float* pred_out,

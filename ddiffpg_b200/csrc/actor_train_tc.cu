@@ -64,26 +64,36 @@ __global__ void train_tc_prep_kernel(const float* __restrict__ state, const floa
                                      const float* __restrict__ noise, const int64_t* __restrict__ ts,
                                      const float* __restrict__ cst, int S, int A, int T, int Tp, long B,
                                      bf16* __restrict__ xin, bf16* __restrict__ onehot, int tcols) {
+    // one thread = 8 consecutive columns of a row = one 16-byte store
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long row = idx >> 6;
-    const int c = (int)(idx & 63);
+    const long row = idx >> 3;
+    const int c0 = (int)(idx & 7) * 8;
     if (row >= B) return;
     int t = (int)ts[row];
     t = t < 0 ? 0 : (t >= T ? T - 1 : t);
-    float v = 0.f;
-    if (c < 8) {
-        if (c < A) {
-            const float* cs = cst + t * kCstStride;       // scheduler.add_noise (diffusion_mlp.py:309-310)
-            v = __fadd_rn(__fmul_rn(cs[CST_ADD_A], action[row * A + c]), __fmul_rn(cs[CST_ADD_B], noise[row * A + c]));
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        float x = 0.f;
+        if (c < 8) {
+            if (c < A) {
+                const float* cs = cst + t * kCstStride;       // scheduler.add_noise (diffusion_mlp.py:309-310)
+                x = __fadd_rn(__fmul_rn(cs[CST_ADD_A], action[row * A + c]), __fmul_rn(cs[CST_ADD_B], noise[row * A + c]));
+            }
+        } else if (c - 8 < S) {
+            x = state[row * S + c - 8];
+        } else if (tcols && c >= kTCol0) {
+            x = ((c - kTCol0) >> 1) == t ? 1.f : 0.f;         // one-hot of the timestep, twice (hi / lo table columns)
         }
-    } else if (c - 8 < S) {
-        v = state[row * S + c - 8];
-    } else if (tcols && c >= kTCol0) {
-        v = ((c - kTCol0) >> 1) == t ? 1.f : 0.f;         // one-hot of the timestep, twice (hi / lo table columns)
+        v[i] = x;
     }
-    xin[row * 64 + c] = __float2bfloat16(v);
-    if (!tcols)                                           // 64 threads per row cover all Tp columns (T up to kMaxT)
-        for (int cc = c; cc < Tp; cc += 64) onehot[row * Tp + cc] = __float2bfloat16(cc == t ? 1.f : 0.f);
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(xin + row * 64 + c0) = *reinterpret_cast<const uint4*>(h);
+    if (!tcols)                                               // 8 threads per row cover all Tp columns (T up to kMaxT)
+        for (int cc = (int)(idx & 7); cc < Tp; cc += 8) onehot[row * Tp + cc] = __float2bfloat16(cc == t ? 1.f : 0.f);
 }
 
 __global__ void transpose_small_kernel(const float* __restrict__ src, int rows, int cols, int ld, float* __restrict__ dst) {
@@ -166,7 +176,7 @@ int actor_train_tc(const ActorLayout& L, const void* packed, const float* const 
     const int Tp = (L.T + 7) / 8 * 8, D = L.D, ld0 = D + L.S + L.A;
     DDP_CUDA_CHECK(cudaMemsetAsync(grads, 0, go.off[12] * sizeof(float), st));
     DDP_CUDA_CHECK(cudaMemsetAsync(w.GT, 0, (size_t)L.h1 * Tp * sizeof(float), st));
-    const unsigned eb = (unsigned)((B * 64 + 255) / 256);
+    const unsigned eb = (unsigned)((B * 8 + 255) / 256);
     const bool tcols = time_cols(L.T, L.S);
     train_tc_prep_kernel<<<eb, 256, 0, st>>>(state, action, noise, t, pk + L.cst, L.S, L.A, L.T, Tp, B, w.xin, w.onehot, tcols ? 1 : 0);
 

@@ -71,9 +71,37 @@ __global__ void submatrix_pack_kernel(const float* __restrict__ src, int ld, int
     out[i] = c < cols ? src[(size_t)r * ld + off + c] : 0.f;
 }
 
-int pack_q_fp32(const QLayout& L, const float* const p[], float* out, cudaStream_t st) {
+// the fp32 operands the tensor-core path reads: the eight bias vectors of one critic and the support atoms, one launch
+struct QBiasPack { const float* src[8]; size_t dst[8]; int n[8], np[8]; };
+__global__ void q_bias_pack_kernel(QBiasPack bp, float* __restrict__ base, size_t z_off, int atoms, int atomsP,
+                                   float v_min, float v_max) {
+    const int v = blockIdx.x;
+    if (v < 8) {
+        for (int i = threadIdx.x; i < bp.np[v]; i += blockDim.x) base[bp.dst[v] + i] = i < bp.n[v] ? bp.src[v][i] : 0.f;
+    } else {
+        const float step = (v_max - v_min) / (float)(atoms - 1);       // torch.linspace, as q_support_kernel
+        for (int i = threadIdx.x; i < atomsP; i += blockDim.x)
+            base[z_off + i] = i < atoms ? ((i < atoms / 2) ? v_min + step * (float)i : v_max - step * (float)(atoms - i - 1)) : 0.f;
+    }
+}
+
+// bias_only: the DDP_BF16 pack -- every matrix the tensor path multiplies lives in the 16-bit section (pack_q_tc), the
+// fp32 section only supplies biases and atoms (1 launch per critic instead of 25)
+int pack_q_fp32(const QLayout& L, const float* const p[], float* out, cudaStream_t st, bool bias_only) {
     auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
     const int in1 = L.O + L.A;
+    for (int m = 0; m < L.n_modes && bias_only; ++m) {
+        QBiasPack bp;
+        for (int j = 0; j < 2; ++j) {
+            const float* const* q = p + 16 * m + 8 * j;
+            const QNetLayout& n = L.net[j];
+            const size_t dst[4] = {n.b1, n.b2, n.b3, n.b4};
+            const int cnt[4] = {L.h1, L.h2, L.h3, L.atoms}, cntp[4] = {L.h1, L.h2, L.h3, L.atomsP};
+            for (int i = 0; i < 4; ++i) { bp.src[4 * j + i] = q[2 * i + 1]; bp.dst[4 * j + i] = dst[i]; bp.n[4 * j + i] = cnt[i]; bp.np[4 * j + i] = cntp[i]; }
+        }
+        q_bias_pack_kernel<<<9, 256, 0, st>>>(bp, out + (size_t)m * L.mode_stride, L.z, L.atoms, L.atomsP, L.v_min, L.v_max);
+    }
+    if (bias_only) { DDP_LAUNCH_CHECK("critic bias pack kernel"); return DDP_OK; }
     for (int m = 0; m < L.n_modes; ++m) {
         float* base = out + (size_t)m * L.mode_stride;
         for (int j = 0; j < 2; ++j) {
@@ -548,16 +576,21 @@ void launch_dw(const float* dz, int ldz, int N, const float* x, int ldx, int K, 
                cudaStream_t st);      // fp32 dW = dZ^T . X with bias column sums (actor_train_fma.cu)
 
 // Categorical projection of r + (1 - done) * gamma * z onto the support (ddiffpg/utils/distl_util.py:4-20) for
-// both target heads, then their element-wise minimum (ddiffpg.py:346).  One warp per row.
+// both target heads, then their element-wise minimum (ddiffpg.py:346).  One warp per row.  The scatter-add
+// (index_add_ in the reference) accumulates in 2^-30 fixed point with integer shared-memory atomics: fp32 atomicAdd on
+// shared memory is a compare-and-swap loop that spins under the address conflicts this scatter is full of (a `done` row
+// sends all atoms to the same two bins), the integer add is native -- and the sums become order-independent.  A bin
+// holds at most the total mass 1 (+ rounding), the quantisation error per bin is below atoms * 2^-31 = 2.4e-8.
 __global__ void c51_projection_min_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                                           const float* __restrict__ reward, const float* __restrict__ done,
                                           float gamma, float v_min, float v_max, int atoms, const float* __restrict__ z,
                                           long B, float* __restrict__ target) {
-    __shared__ float bins[8][2][64];
+    __shared__ int bins[8][2][64];
+    constexpr float kScale = 1073741824.f, kInv = 1.f / 1073741824.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * 8 + warp;
-    bins[warp][0][lane] = 0.f; bins[warp][0][lane + 32] = 0.f;
-    bins[warp][1][lane] = 0.f; bins[warp][1][lane + 32] = 0.f;
+    bins[warp][0][lane] = 0; bins[warp][0][lane + 32] = 0;
+    bins[warp][1][lane] = 0; bins[warp][1][lane + 32] = 0;
     __syncwarp();
     if (row < B) {
         const float delta_z = (float)(((double)v_max - (double)v_min) / (double)(atoms - 1));
@@ -571,11 +604,12 @@ __global__ void c51_projection_min_kernel(const float* __restrict__ p1, const fl
             if (lo < atoms - 1 && lo == up) up += 1;
             const float wl = __fsub_rn((float)up, b), wu = __fsub_rn(b, (float)lo);
             const float a1 = p1[row * atoms + j], a2 = p2[row * atoms + j];
-            atomicAdd(&bins[warp][0][lo], a1 * wl); atomicAdd(&bins[warp][0][up], a1 * wu);
-            atomicAdd(&bins[warp][1][lo], a2 * wl); atomicAdd(&bins[warp][1][up], a2 * wu);
+            atomicAdd(&bins[warp][0][lo], __float2int_rn(a1 * wl * kScale)); atomicAdd(&bins[warp][0][up], __float2int_rn(a1 * wu * kScale));
+            atomicAdd(&bins[warp][1][lo], __float2int_rn(a2 * wl * kScale)); atomicAdd(&bins[warp][1][up], __float2int_rn(a2 * wu * kScale));
         }
         __syncwarp();
-        for (int j = lane; j < atoms; j += 32) target[row * atoms + j] = fminf(bins[warp][0][j], bins[warp][1][j]);
+        for (int j = lane; j < atoms; j += 32)
+            target[row * atoms + j] = (float)min(bins[warp][0][j], bins[warp][1][j]) * kInv;
     }
 }
 

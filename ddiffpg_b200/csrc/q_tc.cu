@@ -85,17 +85,29 @@ QTcWs carve(const QLayout& L, long B, int iters, uint8_t* base) {
 // place first (the pre-loop clamp of update_target_action, ddiffpg.py:361)
 __global__ void q_tc_prep_kernel(const float* __restrict__ obs, float* __restrict__ act, int O, int A, long B,
                                  float clamp_lim, bf16* __restrict__ xin) {
+    // one thread = 8 consecutive columns of a row = one 16-byte store
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long row = idx >> 6;
-    const int c = (int)(idx & 63);
+    const long row = idx >> 3;
+    const int c0 = (int)(idx & 7) * 8;
     if (row >= B) return;
-    float v = 0.f;
-    if (c < O) v = obs[row * O + c];
-    else if (c < O + A) {
-        v = act[row * A + c - O];
-        if (clamp_lim > 0.f) { v = fminf(fmaxf(v, -clamp_lim), clamp_lim); act[row * A + c - O] = v; }
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        float x = 0.f;
+        if (c < O) x = obs[row * O + c];
+        else if (c < O + A) {
+            x = act[row * A + c - O];
+            if (clamp_lim > 0.f) { x = fminf(fmaxf(x, -clamp_lim), clamp_lim); act[row * A + c - O] = x; }
+        }
+        v[i] = x;
     }
-    if (xin) xin[row * 64 + c] = __float2bfloat16(v);
+    if (xin) {
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(xin + row * 64 + c0) = *reinterpret_cast<const uint4*>(h);
+    }
 }
 
 // One warp per row: softmax over atoms of both nets, expectations, min / selection, d min(Q1,Q2) / d logits.
@@ -180,14 +192,29 @@ __global__ void q_tc_adam_kernel(QSeg seg, int O, int A, float* __restrict__ act
 }
 
 __global__ void q_tc_abs_kernel(QSeg seg, int A, const float* __restrict__ act, long n_elems, float* __restrict__ abs_sum) {
+    // per-thread partial sums per mode run, one shared atomic per WARP where the warp sits inside one mode (fp32 shared
+    // atomics are compare-and-swap loops: one per element on the same address was 61 us per call)
     __shared__ float bins[kMaxModes];
     if (threadIdx.x < kMaxModes) bins[threadIdx.x] = 0.f;
     __syncthreads();
+    float local = 0.f;
+    int cur = -1;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += (long)gridDim.x * blockDim.x) {
         const long row = i / A;
-        int mode = 0;
+        int mode = cur < 0 ? 0 : cur;
         while (mode + 1 < seg.n_modes && row >= seg.off[mode + 1]) ++mode;
-        atomicAdd(&bins[mode], fabsf(act[i]));
+        if (mode != cur) {
+            if (cur >= 0 && local != 0.f) atomicAdd(&bins[cur], local);
+            cur = mode; local = 0.f;
+        }
+        local += fabsf(act[i]);
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, cur);
+    if (peers == 0xffffffffu) {
+        local = warp_sum(local);
+        if ((threadIdx.x & 31) == 0 && cur >= 0 && local != 0.f) atomicAdd(&bins[cur], local);
+    } else if (cur >= 0 && local != 0.f) {
+        atomicAdd(&bins[cur], local);
     }
     __syncthreads();
     if (threadIdx.x < seg.n_modes && bins[threadIdx.x] != 0.f) atomicAdd(abs_sum + threadIdx.x, bins[threadIdx.x]);
@@ -309,7 +336,7 @@ int q_forward_tc(const QLayout& L, const void* packed, const int64_t* seg_off, c
     if (!ws || ws_bytes < carve(L, B, 0, nullptr).total) DDP_FAIL(DDP_ERR_ARG, "critic tensor path: workspace too small");
     QTcWs w = carve(L, B, 0, (uint8_t*)ws);
     QSeg seg = make_seg(L, seg_off, nullptr);
-    const unsigned eb = (unsigned)((B * 64 + 255) / 256);
+    const unsigned eb = (unsigned)((B * 8 + 255) / 256);
     q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, const_cast<float*>(act), L.O, L.A, B, 0.f, w.xin);
     if (use_chain(L))
         return q_chain_pass(L, packed, seg_off, nullptr, w.xin, dq_da, nullptr, qmin, p1, p2, B, w.chain_scratch,
@@ -332,7 +359,7 @@ int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, co
     QTcWs w = carve(L, B, iters, (uint8_t*)ws);
     QSeg seg = make_seg(L, seg_off, seg_cnt);
     const long n = B * L.A;
-    const unsigned eb = (unsigned)((B * 64 + 255) / 256), nb = (unsigned)((n + 255) / 256);
+    const unsigned eb = (unsigned)((B * 8 + 255) / 256), nb = (unsigned)((n + 255) / 256);
     DDP_CUDA_CHECK(cudaMemsetAsync(w.m1, 0, w.adam_bytes, st));          // fresh Adam state, zeroed reductions
     q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, action, L.O, L.A, B, lim, w.xin);
     const bool chain = use_chain(L);
@@ -493,7 +520,7 @@ int q_critic_train_tc(const QLayout& L, const void* packed, const void* packed_t
     const size_t per_net = (size_t)L.h1 * in1 + L.h1 + (size_t)L.h2 * L.h1 + L.h2 + (size_t)L.h3 * L.h2 + L.h3 +
                            (size_t)L.atoms * L.h3 + L.atoms;
     DDP_CUDA_CHECK(cudaMemsetAsync(grads, 0, 2 * per_net * sizeof(float), st));
-    const unsigned eb = (unsigned)((B * 64 + 255) / 256);
+    const unsigned eb = (unsigned)((B * 8 + 255) / 256);
     q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, const_cast<float*>(act), L.O, L.A, B, 0.f, w.xin);
     q_tc_colmap_kernel<<<1, 64, 0, st>>>((int)in1, w.colmap);
     auto row = [&](const bf16* A, int lda, size_t w_off, int ldw, int N, int K, int epi, const float* bias, const bf16* aux,
