@@ -361,7 +361,7 @@ def setup_train(cx, rows):
     pol = DiffusionPolicy(S, A, T, device="cuda", hidden=(h, h // 2, h // 4))
     params = {k: v.clone() for k, v in pol.state_dict().items()}
     pol.to(dev)
-    trainer = FusedActorTrainer(pol, precision=args.precision, graph=not args.no_graph)
+    trainer = FusedActorTrainer(pol, precision=args.precision, graph=not args.no_graph, buckets=args.train_buckets)
     st_h = torch.randn(rows, S, generator=cx.gen).pin_memory()
     ac_h = (torch.rand(rows, A, generator=cx.gen) * 2 - 1).pin_memory()
     st, ac = st_h.to(dev), ac_h.to(dev)
@@ -617,6 +617,8 @@ def main():
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--modes", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-buckets", type=int, default=None, choices=[1, 2, 4],
+                    help="train workload under torchrun: gradient all-reduces per step (default: by world size)")
     ap.add_argument("--no-graph", action="store_true", help="train workload: eager launches instead of the CUDA graph")
     args = ap.parse_args()
     quiet_stdout()

@@ -216,8 +216,14 @@ class FusedActorTrainer:
     GROUPS = 4
 
     def __init__(self, actor, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0,
-                 process_group=None, precision=None, graph=False):
+                 process_group=None, precision=None, graph=False, buckets=None):
         self.actor = actor
+        # collectives per step: 4 = every gradient group as soon as it is final, 2 = groups 0-2 together (behind the
+        # layer-1 weight gradient) + the last group, 1 = one all-reduce behind the backward; None: by world size (see
+        # _bucket_plan)
+        if buckets not in (None, 1, 2, 4):
+            raise ValueError("buckets must be None, 1, 2 or 4")
+        self.buckets = buckets
         # graph=True: the whole step (re-pack, forward/backward, all-reduce, clip + AdamW) is captured once per batch
         # shape into a CUDA graph and replayed; the Adam step count lives on the device
         self.use_graph = graph
@@ -281,6 +287,21 @@ class FusedActorTrainer:
         mlp.0, mlp.2, mlp.4, mlp.6, then the loss): group 0 = mlp.6 + loss, 1 = mlp.4, 2 = mlp.2, 3 = the rest."""
         o = self._offsets
         return [(o[10], n + 1), (o[8], o[10]), (o[6], o[8]), (0, o[6])]
+
+    def _bucket_plan(self, n):
+        """[(event index to wait for, lo, hi)] of the all-reduces of one step.  The flat buffer is in state_dict order,
+        so groups 0-2 (mlp.6 + loss, mlp.4, mlp.2) are one contiguous range and so is the whole buffer."""
+        sl = self._group_slices(n)
+        buckets = self.buckets
+        if buckets is None:
+            # measured at 8 ranks, 131 072 rows per rank (profiles/r02/bench_train_n8_b{4,2,1}.json): 4 buckets 1.219 ms,
+            # 2 buckets 1.269 ms, 1 bucket 1.226 ms per step -- per-group reduction stays the default at every world size
+            buckets = 4
+        if buckets == 4:
+            return [(g, lo, hi) for g, (lo, hi) in enumerate(sl)]
+        if buckets == 2:
+            return [(2, sl[2][0], sl[0][1]), (3, sl[3][0], sl[3][1])]
+        return [(3, 0, n + 1)]
 
     def step(self, state, action, noise=None, timesteps=None, global_batch=None):
         """One training step; returns (loss, pre-clip grad norm) as 0-dim device tensors (no host sync).
@@ -353,8 +374,8 @@ class FusedActorTrainer:
                 side = self._side
                 group = None if self.group in (None, False) else self.group
                 with torch.cuda.stream(side):
-                    for (lo, hi), ev in zip(self._group_slices(n), self._events):
-                        side.wait_event(ev)
+                    for g, lo, hi in self._bucket_plan(n):
+                        side.wait_event(self._events[g])
                         torch.distributed.all_reduce(gbuf[lo:hi], group=group)
                 main.wait_stream(side)
             self.step_count += 1

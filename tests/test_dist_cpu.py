@@ -85,3 +85,31 @@ def test_host_batch_ranges_cover_the_batch_in_whole_waves():
                 assert first < wave or first % wave == 0                      # the partial wave, if any, comes first
     assert host_batch_ranges(65536, 4, sms) == [(0, wave), (wave, 65536)]
     assert host_batch_ranges(50000, 4, sms) == [(0, 50000 - 2 * wave), (50000 - 2 * wave, 50000 - wave), (50000 - wave, 50000)]
+
+
+def test_trainer_bucket_plan_covers_the_gradient_buffer():
+    """FusedActorTrainer._bucket_plan: every plan covers [0, n + 1) (gradient + the loss slot) exactly once, each bucket
+    waits for the event of the LAST group it contains, and the default is one collective per gradient group."""
+    from ddiffpg_b200.algo import FusedActorTrainer
+
+    class Stub:
+        _offsets = [0, 10, 14, 30, 34, 100, 110, 200, 208, 240, 244, 250, 252]
+        _group_slices = FusedActorTrainer._group_slices
+        _bucket_plan = FusedActorTrainer._bucket_plan
+
+        def __init__(self, buckets, world):
+            self.buckets, self._world = buckets, world
+
+        def world_size(self):
+            return self._world
+    n = 252
+    for buckets, world, want in ((4, 2, 4), (2, 2, 2), (1, 2, 1), (None, 2, 4), (None, 8, 4), (None, 1, 4)):
+        plan = Stub(buckets, world)._bucket_plan(n)
+        assert len(plan) == want
+        cover = sorted((lo, hi) for _, lo, hi in plan)
+        assert cover[0][0] == 0 and cover[-1][1] == n + 1 and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+        assert [g for g, _, _ in plan] == sorted(g for g, _, _ in plan) and plan[-1][0] == 3
+        groups = Stub(4, 2)._group_slices(n)
+        for g, lo, hi in plan:          # the bucket's event is the one of the last-finished group inside it
+            inside = [k for k, (a, b) in enumerate(groups) if a >= lo and b <= hi]
+            assert g == max(inside)
