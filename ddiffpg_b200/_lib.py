@@ -75,6 +75,13 @@ PROTOTYPES = {
     "ddp_rnd_train_workspace_bytes": (c_size_t, [POINTER(RndShape), c_long]),
     "ddp_rnd_loss_fwd_bwd": (c_int, [POINTER(RndShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long,
                                      c_void_p, c_size_t, c_void_p]),
+    "ddp_rnd_packed_bytes_p": (c_size_t, [POINTER(RndShape), c_int]),
+    "ddp_rnd_pack_p": (c_int, [POINTER(RndShape), POINTER(c_void_p), c_void_p, c_int, c_void_p]),
+    "ddp_rnd_workspace_bytes_p": (c_size_t, [POINTER(RndShape), c_long, c_int]),
+    "ddp_rnd_novelty_p": (c_int, [POINTER(RndShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int,
+                                  c_void_p, c_size_t, c_void_p]),
+    "ddp_rnd_loss_fwd_bwd_p": (c_int, [POINTER(RndShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int,
+                                       c_void_p, c_size_t, c_void_p]),
     "ddp_replay_gather": (c_int, [POINTER(BatchShape)] + [c_void_p] * 6 + [c_long] + [c_void_p] * 13 + [c_long, c_void_p]),
     "ddp_replay_scatter_target": (c_int, [POINTER(BatchShape), c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_long,
                                           c_void_p]),

@@ -68,6 +68,12 @@ int rnd_novelty_fma(const QLayout& L, const float* pk, const float* x, float* no
 int rnd_train_fma(const QLayout& L, const float* pk, const float* x, float* loss_out, float* grads, float* novelty,
                   long B, void* ws, size_t ws_bytes, cudaStream_t st);
 
+size_t rnd_tc_workspace(const QLayout& L, long B);
+int rnd_novelty_tc(const QLayout& L, const void* packed, const float* x, float* novelty, float* pred, float* target,
+                   long B, void* ws, size_t ws_bytes, cudaStream_t st);
+int rnd_train_tc(const QLayout& L, const void* packed, const float* x, float* loss_out, float* grads, float* novelty,
+                 long B, void* ws, size_t ws_bytes, cudaStream_t st);
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace ddp
@@ -319,43 +325,66 @@ int ddp_q_critic_loss_fwd_bwd(const ddp_q_shape* s, const void* packed, const vo
 }
 
 // RNDModel as a two-net pack: O = D, no action columns, atoms = F, net 0 = predictor, net 1 = target
-static int rnd_layout(const ddp_rnd_shape* s, QLayout* L) {
+static int rnd_layout(const ddp_rnd_shape* s, QLayout* L, int precision = DDP_FP32) {
     if (!s) DDP_FAIL(DDP_ERR_ARG, "RND shape is NULL");
+    if (precision != DDP_FP32 && precision != DDP_BF16) DDP_FAIL(DDP_ERR_ARG, "unknown precision %d", precision);
     if (s->D <= 0 || s->D > 512 || s->F < 4 || s->F > 256 || s->F % 4)
         DDP_FAIL(DDP_ERR_SHAPE, "RND shape: need 0<D<=512 and F a multiple of 4 in [4,256] (got D=%d F=%d)", s->D, s->F);
     if (s->hid1 <= 0 || s->hid2 <= 0 || s->hid3 <= 0 || s->hid1 % 4 || s->hid2 % 4 || s->hid3 % 4 || s->hid1 > 1024 ||
         s->hid2 > 1024 || s->hid3 > 1024)
         DDP_FAIL(DDP_ERR_SHAPE, "RND shape: hidden widths must be multiples of 4 in (0,1024]");
+    if (precision == DDP_BF16 && (s->D > 256 || s->hid1 % 64 || s->hid2 % 64 || s->hid3 % 64))
+        DDP_FAIL(DDP_ERR_UNSUPPORTED, "RND tensor path: need D<=256 and hidden widths multiples of 64");
     ddp_q_shape q{};
     q.O = s->D; q.A = 0; q.atoms = s->F; q.v_min = 0.f; q.v_max = 1.f; q.n_modes = 1;
     q.hid1 = s->hid1; q.hid2 = s->hid2; q.hid3 = s->hid3;
-    *L = make_q_layout(q, DDP_FP32);
+    *L = make_q_layout(q, precision);
     return DDP_OK;
 }
 
-size_t ddp_rnd_packed_bytes(const ddp_rnd_shape* s) {
+size_t ddp_rnd_packed_bytes_p(const ddp_rnd_shape* s, int precision) {
     QLayout L;
-    return rnd_layout(s, &L) == DDP_OK ? L.total_bytes : 0;
+    return rnd_layout(s, &L, precision) == DDP_OK ? L.total_bytes : 0;
 }
+size_t ddp_rnd_packed_bytes(const ddp_rnd_shape* s) { return ddp_rnd_packed_bytes_p(s, DDP_FP32); }
 
-int ddp_rnd_pack(const ddp_rnd_shape* s, const float* const params[16], void* packed, void* stream) {
+int ddp_rnd_pack_p(const ddp_rnd_shape* s, const float* const params[16], void* packed, int precision, void* stream) {
     QLayout L;
-    int rc = rnd_layout(s, &L);
+    int rc = rnd_layout(s, &L, precision);
     if (rc != DDP_OK) return rc;
     if (!params || !packed) DDP_FAIL(DDP_ERR_ARG, "ddp_rnd_pack: NULL argument");
     for (int i = 0; i < 16; ++i)
         if (!params[i]) DDP_FAIL(DDP_ERR_ARG, "ddp_rnd_pack: params[%d] is NULL", i);
-    return pack_q_fp32(L, params, (float*)packed, (cudaStream_t)stream, false);
+    rc = pack_q_fp32(L, params, (float*)packed, (cudaStream_t)stream, precision == DDP_BF16);
+    if (rc != DDP_OK || precision == DDP_FP32) return rc;
+    return pack_q_tc(L, params, packed, (cudaStream_t)stream);
+}
+int ddp_rnd_pack(const ddp_rnd_shape* s, const float* const params[16], void* packed, void* stream) {
+    return ddp_rnd_pack_p(s, params, packed, DDP_FP32, stream);
 }
 
-int ddp_rnd_novelty(const ddp_rnd_shape* s, const void* packed, const float* x, float* novelty_out, float* pred_out,
-                    float* target_out, long B, void* stream) {
+size_t ddp_rnd_workspace_bytes_p(const ddp_rnd_shape* s, long B, int precision) {
     QLayout L;
-    int rc = rnd_layout(s, &L);
+    if (rnd_layout(s, &L, precision) != DDP_OK || B <= 0) return 0;
+    return precision == DDP_BF16 ? rnd_tc_workspace(L, B) : rnd_train_workspace(L, B);
+}
+
+int ddp_rnd_novelty_p(const ddp_rnd_shape* s, const void* packed, const float* x, float* novelty_out, float* pred_out,
+                      float* target_out, long B, int precision, void* ws, size_t ws_bytes, void* stream) {
+    QLayout L;
+    int rc = rnd_layout(s, &L, precision);
     if (rc != DDP_OK) return rc;
     if (B <= 0) DDP_FAIL(DDP_ERR_SHAPE, "ddp_rnd_novelty: batch must be positive");
     if (!packed || !x) DDP_FAIL(DDP_ERR_ARG, "ddp_rnd_novelty: NULL argument");
+    if (precision == DDP_BF16) {
+        if (!ws || !aligned16(ws)) DDP_FAIL(DDP_ERR_ARG, "ddp_rnd_novelty: the tensor path needs a 16-byte aligned workspace");
+        return rnd_novelty_tc(L, packed, x, novelty_out, pred_out, target_out, B, ws, ws_bytes, (cudaStream_t)stream);
+    }
     return rnd_novelty_fma(L, (const float*)packed, x, novelty_out, pred_out, target_out, B, (cudaStream_t)stream);
+}
+int ddp_rnd_novelty(const ddp_rnd_shape* s, const void* packed, const float* x, float* novelty_out, float* pred_out,
+                    float* target_out, long B, void* stream) {
+    return ddp_rnd_novelty_p(s, packed, x, novelty_out, pred_out, target_out, B, DDP_FP32, nullptr, 0, stream);
 }
 
 size_t ddp_rnd_grad_count(const ddp_rnd_shape* s) {
@@ -363,22 +392,24 @@ size_t ddp_rnd_grad_count(const ddp_rnd_shape* s) {
     return rnd_layout(s, &L) == DDP_OK ? rnd_grad_count(L) : 0;
 }
 
-size_t ddp_rnd_train_workspace_bytes(const ddp_rnd_shape* s, long B) {
-    QLayout L;
-    if (rnd_layout(s, &L) != DDP_OK || B <= 0) return 0;
-    return rnd_train_workspace(L, B);
-}
+size_t ddp_rnd_train_workspace_bytes(const ddp_rnd_shape* s, long B) { return ddp_rnd_workspace_bytes_p(s, B, DDP_FP32); }
 
-int ddp_rnd_loss_fwd_bwd(const ddp_rnd_shape* s, const void* packed, const float* x, float* loss_out, float* grads_flat,
-                         float* novelty_out, long B, void* ws, size_t ws_bytes, void* stream) {
+int ddp_rnd_loss_fwd_bwd_p(const ddp_rnd_shape* s, const void* packed, const float* x, float* loss_out, float* grads_flat,
+                           float* novelty_out, long B, int precision, void* ws, size_t ws_bytes, void* stream) {
     QLayout L;
-    int rc = rnd_layout(s, &L);
+    int rc = rnd_layout(s, &L, precision);
     if (rc != DDP_OK) return rc;
     if (B <= 0) DDP_FAIL(DDP_ERR_SHAPE, "ddp_rnd_loss_fwd_bwd: batch must be positive");
     if (!packed || !x || !loss_out || !grads_flat || !ws) DDP_FAIL(DDP_ERR_ARG, "ddp_rnd_loss_fwd_bwd: NULL argument");
     if (!aligned16(ws) || !aligned16(grads_flat)) DDP_FAIL(DDP_ERR_ARG, "workspace/grads must be 16-byte aligned");
+    if (precision == DDP_BF16)
+        return rnd_train_tc(L, packed, x, loss_out, grads_flat, novelty_out, B, ws, ws_bytes, (cudaStream_t)stream);
     return rnd_train_fma(L, (const float*)packed, x, loss_out, grads_flat, novelty_out, B, ws, ws_bytes,
                          (cudaStream_t)stream);
+}
+int ddp_rnd_loss_fwd_bwd(const ddp_rnd_shape* s, const void* packed, const float* x, float* loss_out, float* grads_flat,
+                         float* novelty_out, long B, void* ws, size_t ws_bytes, void* stream) {
+    return ddp_rnd_loss_fwd_bwd_p(s, packed, x, loss_out, grads_flat, novelty_out, B, DDP_FP32, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -727,7 +727,7 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
 static long long* g_qc_dbg = nullptr;
 
 bool q_chain_shape_ok(const QLayout& L) {
-    return L.O + L.A <= 64 && L.A <= 16 && L.atoms <= 64 && L.h1 % 64 == 0 && L.h2 % 64 == 0 && L.h3 % 64 == 0 &&
+    return L.K1c == 64 && L.AtP == 64 && L.A <= 16 && L.A >= 1 && L.h1 % 64 == 0 && L.h2 % 64 == 0 && L.h3 % 64 == 0 &&
            L.h1 <= 512 && L.h2 <= 256 && L.h3 <= 256 && L.h2 + L.h3 <= kTmemCols && L.h2 <= L.h1 && L.h2 >= 64 &&
            (L.h1 <= 256 || L.h1 % 256 == 0);
 }

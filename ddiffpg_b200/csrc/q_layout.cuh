@@ -18,6 +18,7 @@ struct QLayout {
     int O, A, atoms, n_modes, h1, h2, h3;
     float v_min, v_max;
     int K1p, A4, atomsP;
+    int K1c, AtP;                // tensor path: input width and head width padded to whole 64-column chunks
     QNetLayout net[2];           // offsets in floats inside one mode's block
     size_t z;                    // [atomsP] support atoms (shared by both nets)
     size_t mode_stride;          // floats per mode
@@ -33,6 +34,7 @@ inline QLayout make_q_layout(const ddp_q_shape& s, int precision) {
     L.O = s.O; L.A = s.A; L.atoms = s.atoms; L.n_modes = s.n_modes; L.h1 = s.hid1; L.h2 = s.hid2; L.h3 = s.hid3;
     L.v_min = s.v_min; L.v_max = s.v_max;
     L.K1p = pad4(s.O + s.A); L.A4 = pad4(s.A); L.atomsP = pad4(s.atoms);
+    L.K1c = (s.O + s.A + 63) / 64 * 64; L.AtP = (s.atoms + 63) / 64 * 64;
     size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o += (n + 63) / 64 * 64; return r; };
     for (int j = 0; j < 2; ++j) {
@@ -47,10 +49,11 @@ inline QLayout make_q_layout(const ddp_q_shape& s, int precision) {
     L.mode_stride = o;
     size_t bytes = align_up(o * sizeof(float) * (size_t)s.n_modes, 1024);
     if (precision == DDP_BF16) {
-        // forward: W1 [h1][64] (K = [obs|act|0]), W2 [h2][h1], W3 [h3][h2], W4 [64][h3] (rows >= atoms zero)
-        // backward (dX = dY.W): W4^T [h3][64], W3^T [h2][h3], W2^T [h1][h2], W1[:, O:O+A]^T [16][h1]
-        const size_t fe[4] = {(size_t)L.h1 * 64, (size_t)L.h2 * L.h1, (size_t)L.h3 * L.h2, (size_t)64 * L.h3};
-        const size_t be[4] = {(size_t)L.h3 * 64, (size_t)L.h2 * L.h3, (size_t)L.h1 * L.h2, (size_t)16 * L.h1};
+        // forward: W1 [h1][K1c] (K = [obs|act|0]), W2 [h2][h1], W3 [h3][h2], W4 [AtP][h3] (rows >= atoms zero)
+        // backward (dX = dY.W): W4^T [h3][AtP], W3^T [h2][h3], W2^T [h1][h2], W1[:, O:O+A]^T [16][h1]
+        // (K1c = AtP = 64 for the critics; the RND nets have 69 inputs and 128 features)
+        const size_t fe[4] = {(size_t)L.h1 * L.K1c, (size_t)L.h2 * L.h1, (size_t)L.h3 * L.h2, (size_t)L.AtP * L.h3};
+        const size_t be[4] = {(size_t)L.h3 * L.AtP, (size_t)L.h2 * L.h3, (size_t)L.h1 * L.h2, (size_t)16 * L.h1};
         for (int i = 0; i < 4; ++i) { L.tc_fwd_elems[i] = fe[i]; L.tc_bwd_elems[i] = be[i]; }
         for (int j = 0; j < 2; ++j) {
             for (int i = 0; i < 4; ++i) { L.tc_fwd[j][i] = bytes; bytes += align_up(fe[i] * 2 * s.n_modes, 1024); }

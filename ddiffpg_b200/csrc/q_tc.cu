@@ -60,7 +60,7 @@ QTcWs carve(const QLayout& L, long B, int iters, uint8_t* base) {
     auto take = [&](size_t bytes) { uint8_t* r = base ? base + o : nullptr; o += (bytes + 255) / 256 * 256; return r; };
     const bool chain = use_chain(L);
     if (chain) w.chain_scratch = take(q_chain_workspace(L));
-    w.xin = (bf16*)take((size_t)B * 64 * 2);
+    w.xin = (bf16*)take((size_t)B * L.K1c * 2);
     for (int j = 0; j < 2 && !chain; ++j) {
         w.a1[j] = (bf16*)take((size_t)B * L.h1 * 2);
         w.a2[j] = (bf16*)take((size_t)B * L.h2 * 2);
@@ -84,11 +84,12 @@ QTcWs carve(const QLayout& L, long B, int iters, uint8_t* base) {
 // xin[r] = [obs (O) | action (A) | 0 ...] as bf16, 64 columns; `clamp_lim` > 0 also clamps the fp32 action in
 // place first (the pre-loop clamp of update_target_action, ddiffpg.py:361)
 __global__ void q_tc_prep_kernel(const float* __restrict__ obs, float* __restrict__ act, int O, int A, long B,
-                                 float clamp_lim, bf16* __restrict__ xin) {
-    // one thread = 8 consecutive columns of a row = one 16-byte store
+                                 float clamp_lim, bf16* __restrict__ xin, int K1c) {
+    // one thread = 8 consecutive columns of a row = one 16-byte store; K1c (a multiple of 64) columns per row
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long row = idx >> 3;
-    const int c0 = (int)(idx & 7) * 8;
+    const int per_row = K1c >> 3;
+    const long row = idx / per_row;
+    const int c0 = (int)(idx - row * per_row) * 8;
     if (row >= B) return;
     float v[8];
 #pragma unroll
@@ -106,7 +107,7 @@ __global__ void q_tc_prep_kernel(const float* __restrict__ obs, float* __restric
         __nv_bfloat162 h[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        *reinterpret_cast<uint4*>(xin + row * 64 + c0) = *reinterpret_cast<const uint4*>(h);
+        *reinterpret_cast<uint4*>(xin + row * K1c + c0) = *reinterpret_cast<const uint4*>(h);
     }
 }
 
@@ -230,15 +231,15 @@ __global__ void q_tc_finish_kernel(QSeg seg, int A, const float* __restrict__ ab
 
 // bf16 operands, all modes back to back per (net, layer)
 __global__ void q_tc_pack_kernel(const float* __restrict__ W1, const float* __restrict__ W2, const float* __restrict__ W3,
-                                 const float* __restrict__ W4, int O, int A, int atoms, int h1, int h2, int h3,
-                                 bf16* f1, bf16* f2, bf16* f3, bf16* f4, bf16* b4, bf16* b3, bf16* b2, bf16* b1) {
+                                 const float* __restrict__ W4, int O, int A, int atoms, int h1, int h2, int h3, int K1c,
+                                 int AtP, bf16* f1, bf16* f2, bf16* f3, bf16* f4, bf16* b4, bf16* b3, bf16* b2, bf16* b1) {
     const int in1 = O + A;
-    const size_t n1 = (size_t)h1 * 64, n2 = (size_t)h2 * h1, n3 = (size_t)h3 * h2, n4 = (size_t)64 * h3,
-                 m4 = (size_t)h3 * 64, m3 = (size_t)h2 * h3, m2 = (size_t)h1 * h2, m1 = (size_t)16 * h1;
+    const size_t n1 = (size_t)h1 * K1c, n2 = (size_t)h2 * h1, n3 = (size_t)h3 * h2, n4 = (size_t)AtP * h3,
+                 m4 = (size_t)h3 * AtP, m3 = (size_t)h2 * h3, m2 = (size_t)h1 * h2, m1 = (size_t)16 * h1;
     const size_t total = n1 + n2 + n3 + n4 + m4 + m3 + m2 + m1;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t j = i;
-        if (j < n1) { const int r = (int)(j / 64), c = (int)(j % 64); f1[j] = __float2bfloat16(c < in1 ? W1[(size_t)r * in1 + c] : 0.f); continue; }
+        if (j < n1) { const int r = (int)(j / K1c), c = (int)(j % K1c); f1[j] = __float2bfloat16(c < in1 ? W1[(size_t)r * in1 + c] : 0.f); continue; }
         j -= n1;
         if (j < n2) { f2[j] = __float2bfloat16(W2[j]); continue; }
         j -= n2;
@@ -246,7 +247,7 @@ __global__ void q_tc_pack_kernel(const float* __restrict__ W1, const float* __re
         j -= n3;
         if (j < n4) { const int r = (int)(j / h3); f4[j] = __float2bfloat16(r < atoms ? W4[j] : 0.f); continue; }
         j -= n4;
-        if (j < m4) { const int r = (int)(j / 64), c = (int)(j % 64); b4[j] = __float2bfloat16(c < atoms ? W4[(size_t)c * h3 + r] : 0.f); continue; }
+        if (j < m4) { const int r = (int)(j / AtP), c = (int)(j % AtP); b4[j] = __float2bfloat16(c < atoms ? W4[(size_t)c * h3 + r] : 0.f); continue; }
         j -= m4;
         if (j < m3) { const int r = (int)(j / h3), c = (int)(j % h3); b3[j] = __float2bfloat16(W3[(size_t)c * h2 + r]); continue; }
         j -= m3;
@@ -256,9 +257,12 @@ __global__ void q_tc_pack_kernel(const float* __restrict__ W1, const float* __re
     }
 }
 
-bool shape_ok(const QLayout& L) {
-    return L.O + L.A <= 64 && L.A <= 16 && L.atoms <= 64 && L.h1 % 64 == 0 && L.h2 % 64 == 0 && L.h3 % 64 == 0;
+// what the 16-bit pack and the grouped GEMMs need (RND included: 69 inputs -> K1c = 128, 128 features -> AtP = 128)
+bool pack_shape_ok(const QLayout& L) {
+    return L.K1c <= 256 && L.A <= 16 && L.AtP <= 256 && L.h1 % 64 == 0 && L.h2 % 64 == 0 && L.h3 % 64 == 0;
 }
+// the critic kernels around them (softmax / BCE: one warp per row over 64 logit columns, 64-column input rows)
+bool shape_ok(const QLayout& L) { return pack_shape_ok(L) && L.K1c == 64 && L.AtP == 64; }
 
 QSeg make_seg(const QLayout& L, const int64_t* seg_off, const int64_t* seg_cnt) {
     QSeg s{};
@@ -311,7 +315,7 @@ int q_tc_pass(const QLayout& L, const uint8_t* pb, const QTcWs& w, const QSeg& s
 }  // namespace
 
 int pack_q_tc(const QLayout& L, const float* const p[], void* packed, cudaStream_t st) {
-    if (!shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 critic path needs O+A<=64, A<=16, atoms<=64, widths multiple of 64");
+    if (!pack_shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 critic path needs O+A<=256, A<=16, atoms<=256, widths multiple of 64");
     uint8_t* b = (uint8_t*)packed;
     for (int m = 0; m < L.n_modes; ++m)
         for (int j = 0; j < 2; ++j) {
@@ -321,8 +325,8 @@ int pack_q_tc(const QLayout& L, const float* const p[], void* packed, cudaStream
                 f[i] = (bf16*)(b + L.tc_fwd[j][i]) + (size_t)m * L.tc_fwd_elems[i];
                 r[i] = (bf16*)(b + L.tc_bwd[j][i]) + (size_t)m * L.tc_bwd_elems[i];
             }
-            q_tc_pack_kernel<<<296, 256, 0, st>>>(q[0], q[2], q[4], q[6], L.O, L.A, L.atoms, L.h1, L.h2, L.h3, f[0], f[1],
-                                                  f[2], f[3], r[0], r[1], r[2], r[3]);
+            q_tc_pack_kernel<<<296, 256, 0, st>>>(q[0], q[2], q[4], q[6], L.O, L.A, L.atoms, L.h1, L.h2, L.h3, L.K1c, L.AtP,
+                                                  f[0], f[1], f[2], f[3], r[0], r[1], r[2], r[3]);
         }
     DDP_LAUNCH_CHECK("q_tc_pack_kernel");
     return DDP_OK;
@@ -337,7 +341,7 @@ int q_forward_tc(const QLayout& L, const void* packed, const int64_t* seg_off, c
     QTcWs w = carve(L, B, 0, (uint8_t*)ws);
     QSeg seg = make_seg(L, seg_off, nullptr);
     const unsigned eb = (unsigned)((B * 8 + 255) / 256);
-    q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, const_cast<float*>(act), L.O, L.A, B, 0.f, w.xin);
+    q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, const_cast<float*>(act), L.O, L.A, B, 0.f, w.xin, L.K1c);
     if (use_chain(L))
         return q_chain_pass(L, packed, seg_off, nullptr, w.xin, dq_da, nullptr, qmin, p1, p2, B, w.chain_scratch,
                             q_chain_workspace(L), st, nullptr);
@@ -361,7 +365,7 @@ int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, co
     const long n = B * L.A;
     const unsigned eb = (unsigned)((B * 8 + 255) / 256), nb = (unsigned)((n + 255) / 256);
     DDP_CUDA_CHECK(cudaMemsetAsync(w.m1, 0, w.adam_bytes, st));          // fresh Adam state, zeroed reductions
-    q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, action, L.O, L.A, B, lim, w.xin);
+    q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, action, L.O, L.A, B, lim, w.xin, L.K1c);
     const bool chain = use_chain(L);
     float neg_inv[kMaxModes];
     for (int m = 0; m < L.n_modes; ++m) neg_inv[m] = -seg.inv_cnt[m];
@@ -521,7 +525,7 @@ int q_critic_train_tc(const QLayout& L, const void* packed, const void* packed_t
                            (size_t)L.atoms * L.h3 + L.atoms;
     DDP_CUDA_CHECK(cudaMemsetAsync(grads, 0, 2 * per_net * sizeof(float), st));
     const unsigned eb = (unsigned)((B * 8 + 255) / 256);
-    q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, const_cast<float*>(act), L.O, L.A, B, 0.f, w.xin);
+    q_tc_prep_kernel<<<eb, 256, 0, st>>>(obs, const_cast<float*>(act), L.O, L.A, B, 0.f, w.xin, L.K1c);
     q_tc_colmap_kernel<<<1, 64, 0, st>>>((int)in1, w.colmap);
     auto row = [&](const bf16* A, int lda, size_t w_off, int ldw, int N, int K, int epi, const float* bias, const bf16* aux,
                    bf16* out_a, float* out_f, int outf_ld, int n_valid) {
@@ -563,6 +567,162 @@ int q_critic_train_tc(const QLayout& L, const void* packed, const void* packed_t
         if ((rc = dw(w.a1[j], L.h1, L.h1, w.xin, 64, 64, g1, (int)in1, w.colmap, g1 + (size_t)L.h1 * in1)) != DDP_OK) return rc;
     }
     DDP_LAUNCH_CHECK("critic update (tensor path) kernels");
+    return DDP_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// N4, bf16 tensor-core path: RND / NovelD (ddiffpg/utils/intrinsic.py:62-75, ddiffpg/models/mlp.py:233-267) at the
+// update-batch sizes (4 096 rows, NovelD 8 192).  L is the two-net pack of rnd_layout (net 0 = predictor, net 1 =
+// target, O = input width, A = 0, atoms = feature width F).  Forward: four row GEMMs per net (ELU fused, features fp32);
+// novelty / mse / d loss / d pred in fp32, one warp per row; the predictor's backward as in the critic update above
+// (dW by the MN-major GEMM with its ones-MMA bias gradient, dZ written over the activation it no longer needs).
+namespace {
+
+struct RndTcWs {
+    bf16 *xin, *a1[2], *a2[2], *a3[2], *dl;
+    float *feat[2];
+    int* colmap;
+    size_t total;
+};
+
+RndTcWs carve_rnd(const QLayout& L, long B, uint8_t* base) {
+    RndTcWs w{};
+    size_t o = 0;
+    auto take = [&](size_t bytes) { uint8_t* r = base ? base + o : nullptr; o += (bytes + 255) / 256 * 256; return r; };
+    w.xin = (bf16*)take((size_t)B * L.K1c * 2);
+    for (int j = 0; j < 2; ++j) {
+        w.a1[j] = (bf16*)take((size_t)B * L.h1 * 2);
+        w.a2[j] = (bf16*)take((size_t)B * L.h2 * 2);
+        w.a3[j] = (bf16*)take((size_t)B * L.h3 * 2);
+        w.feat[j] = (float*)take((size_t)B * L.AtP * 4);
+    }
+    w.dl = (bf16*)take((size_t)B * L.AtP * 2);
+    w.colmap = (int*)take((size_t)L.K1c * 4);
+    w.total = o;
+    return w;
+}
+
+__global__ void rnd_tc_colmap_kernel(int in1, int K1c, int* __restrict__ colmap) {
+    for (int k = threadIdx.x; k < K1c; k += blockDim.x) colmap[k] = k < in1 ? k : -1;
+}
+
+// One warp per row: novelty = ||pred - target||_2 (IntrinsicM.get_novelty), optional copies of both feature rows, and for
+// the update: loss += inv_count * sum d^2, dl = 2 inv_count d (bf16, zero padded to AtP columns)
+__global__ void rnd_tc_mse_kernel(const float* __restrict__ fp, const float* __restrict__ ft, int F, int AtP, long B,
+                                  float inv_count, float* __restrict__ novelty, float* __restrict__ pred_out,
+                                  float* __restrict__ target_out, bf16* __restrict__ dl, float* __restrict__ loss_out) {
+    __shared__ float red[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + warp;
+    float ss = 0.f;
+    if (row < B) {
+        for (int c = lane; c < AtP; c += 32) {
+            const float a = c < F ? fp[row * AtP + c] : 0.f, b = c < F ? ft[row * AtP + c] : 0.f;
+            const float d = a - b;
+            ss = fmaf(d, d, ss);
+            if (c < F && pred_out) pred_out[row * F + c] = a;
+            if (c < F && target_out) target_out[row * F + c] = b;
+            if (dl) dl[row * AtP + c] = __float2bfloat16(2.f * inv_count * d);
+        }
+    }
+    ss = warp_sum(ss);
+    if (row < B && lane == 0 && novelty) novelty[row] = sqrtf(ss);
+    if (!loss_out) return;
+    if (lane == 0) red[warp] = row < B ? ss : 0.f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        if (t != 0.f) atomicAdd(loss_out, t * inv_count);
+    }
+}
+
+// forward of `nets` nets (1: predictor only is never needed; 2: predictor + target) into w.feat
+int rnd_tc_forward(const QLayout& L, const uint8_t* pb, const RndTcWs& w, const float* x, long B, cudaStream_t st) {
+    using namespace tcg;
+    const float* pk = (const float*)pb;
+    const long per_row = L.K1c >> 3;
+    q_tc_prep_kernel<<<(unsigned)((B * per_row + 255) / 256), 256, 0, st>>>(x, nullptr, L.O, 0, B, 0.f, w.xin, L.K1c);
+    auto row = [&](const bf16* A, int lda, size_t w_off, int ldw, int N, int K, int epi, const float* bias, bf16* out_a,
+                   float* out_f, int outf_ld, int n_valid) {
+        RowGemm g{};
+        g.A = A; g.lda = lda; g.W = (const bf16*)(pb + w_off); g.ldw = ldw; g.M = B; g.N = N; g.K = K; g.epi = epi;
+        g.bias = bias; g.aux_ld = N; g.out_a = out_a; g.out_ld = N; g.out_f = out_f; g.outf_ld = outf_ld; g.n_valid = n_valid;
+        g.groups.n_groups = 1; g.groups.off[0] = 0; g.groups.off[1] = B;
+        return launch_row_gemm(g, st);
+    };
+    int rc;
+    for (int j = 0; j < 2; ++j) {
+        const QNetLayout& n = L.net[j];
+        if ((rc = row(w.xin, L.K1c, L.tc_fwd[j][0], L.K1c, L.h1, L.K1c, EPI_ELU_FWD, pk + n.b1, w.a1[j], nullptr, 0, 0)) != DDP_OK) return rc;
+        if ((rc = row(w.a1[j], L.h1, L.tc_fwd[j][1], L.h1, L.h2, L.h1, EPI_ELU_FWD, pk + n.b2, w.a2[j], nullptr, 0, 0)) != DDP_OK) return rc;
+        if ((rc = row(w.a2[j], L.h2, L.tc_fwd[j][2], L.h2, L.h3, L.h2, EPI_ELU_FWD, pk + n.b3, w.a3[j], nullptr, 0, 0)) != DDP_OK) return rc;
+        if ((rc = row(w.a3[j], L.h3, L.tc_fwd[j][3], L.h3, L.AtP, L.h3, EPI_LINEAR_F32, pk + n.b4, nullptr, w.feat[j], L.AtP, L.atoms)) != DDP_OK) return rc;
+    }
+    return DDP_OK;
+}
+
+}  // namespace
+
+size_t rnd_tc_workspace(const QLayout& L, long B) { return carve_rnd(L, B, nullptr).total; }
+
+int rnd_novelty_tc(const QLayout& L, const void* packed, const float* x, float* novelty, float* pred, float* target,
+                   long B, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!pack_shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 RND path does not support this shape");
+    if (!ws || ws_bytes < carve_rnd(L, B, nullptr).total) DDP_FAIL(DDP_ERR_ARG, "RND (tensor path): workspace too small");
+    RndTcWs w = carve_rnd(L, B, (uint8_t*)ws);
+    int rc = rnd_tc_forward(L, (const uint8_t*)packed, w, x, B, st);
+    if (rc != DDP_OK) return rc;
+    rnd_tc_mse_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(w.feat[0], w.feat[1], L.atoms, L.AtP, B, 0.f, novelty, pred,
+                                                                target, nullptr, nullptr);
+    DDP_LAUNCH_CHECK("RND novelty (tensor path) kernels");
+    return DDP_OK;
+}
+
+int rnd_train_tc(const QLayout& L, const void* packed, const float* x, float* loss_out, float* grads, float* novelty,
+                 long B, void* ws, size_t ws_bytes, cudaStream_t st) {
+    using namespace tcg;
+    if (!pack_shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 RND path does not support this shape");
+    if (!ws || ws_bytes < carve_rnd(L, B, nullptr).total) DDP_FAIL(DDP_ERR_ARG, "RND (tensor path): workspace too small");
+    RndTcWs w = carve_rnd(L, B, (uint8_t*)ws);
+    const uint8_t* pb = (const uint8_t*)packed;
+    int rc = rnd_tc_forward(L, pb, w, x, B, st);
+    if (rc != DDP_OK) return rc;
+    const size_t in1 = (size_t)L.O;
+    const size_t n_grad = (size_t)L.h1 * in1 + L.h1 + (size_t)L.h2 * L.h1 + L.h2 + (size_t)L.h3 * L.h2 + L.h3 +
+                          (size_t)L.atoms * L.h3 + L.atoms;
+    DDP_CUDA_CHECK(cudaMemsetAsync(grads, 0, n_grad * sizeof(float), st));
+    rnd_tc_colmap_kernel<<<1, 256, 0, st>>>((int)in1, L.K1c, w.colmap);
+    rnd_tc_mse_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(w.feat[0], w.feat[1], L.atoms, L.AtP, B,
+                                                                1.0f / ((float)B * (float)L.atoms), novelty, nullptr,
+                                                                nullptr, w.dl, loss_out);
+    auto row = [&](const bf16* A, int lda, size_t w_off, int ldw, int N, int K, bf16* aux_inout) {
+        RowGemm g{};
+        g.A = A; g.lda = lda; g.W = (const bf16*)(pb + w_off); g.ldw = ldw; g.M = B; g.N = N; g.K = K; g.epi = EPI_MUL_ELU_D;
+        g.aux = aux_inout; g.aux_ld = N; g.out_a = aux_inout; g.out_ld = N;
+        g.groups.n_groups = 1; g.groups.off[0] = 0; g.groups.off[1] = B;
+        return launch_row_gemm(g, st);
+    };
+    auto dw = [&](const bf16* dz, int ldz, int N, const bf16* X, int ldx, int K, float* C, int ldc, const int* colmap,
+                  float* colsum) {
+        DwGemm g{};
+        g.dZ = dz; g.ldz = ldz; g.N = N; g.X = X; g.ldx = ldx; g.K = K; g.R = B; g.C = C; g.ldc = ldc; g.colmap = colmap;
+        g.colsum = colsum;
+        return launch_dw_gemm(g, st);
+    };
+    float* g1 = grads;                                   // predictor only, state_dict order: W1, b1, ..., W4, b4
+    float* g2 = g1 + (size_t)L.h1 * in1 + L.h1;
+    float* g3 = g2 + (size_t)L.h2 * L.h1 + L.h2;
+    float* g4 = g3 + (size_t)L.h3 * L.h2 + L.h3;
+    if ((rc = dw(w.dl, L.AtP, L.atoms, w.a3[0], L.h3, L.h3, g4, L.h3, nullptr, g4 + (size_t)L.atoms * L.h3)) != DDP_OK) return rc;
+    if ((rc = row(w.dl, L.AtP, L.tc_bwd[0][0], L.AtP, L.h3, L.AtP, w.a3[0])) != DDP_OK) return rc;
+    if ((rc = dw(w.a3[0], L.h3, L.h3, w.a2[0], L.h2, L.h2, g3, L.h2, nullptr, g3 + (size_t)L.h3 * L.h2)) != DDP_OK) return rc;
+    if ((rc = row(w.a3[0], L.h3, L.tc_bwd[0][1], L.h3, L.h2, L.h3, w.a2[0])) != DDP_OK) return rc;
+    if ((rc = dw(w.a2[0], L.h2, L.h2, w.a1[0], L.h1, L.h1, g2, L.h1, nullptr, g2 + (size_t)L.h2 * L.h1)) != DDP_OK) return rc;
+    if ((rc = row(w.a2[0], L.h2, L.tc_bwd[0][2], L.h2, L.h1, L.h2, w.a1[0])) != DDP_OK) return rc;
+    if ((rc = dw(w.a1[0], L.h1, L.h1, w.xin, L.K1c, L.K1c, g1, (int)in1, w.colmap, g1 + (size_t)L.h1 * in1)) != DDP_OK) return rc;
+    DDP_LAUNCH_CHECK("RND update (tensor path) kernels");
     return DDP_OK;
 }
 

@@ -3,7 +3,8 @@
 ``RNDModel`` mirrors ``ddiffpg.models.mlp.RNDModel`` (:233-267) as the parameter container the kernels read;
 ``IntrinsicKernels`` is a mixin for ``ddiffpg.utils.intrinsic.IntrinsicM`` (:8-94) that overrides only the methods
 that run the networks: the two MLPs, the novelty norm, the mse loss and the predictor's backward go through
-``libddiffpg_b200.so`` (fp32 path), the optimizer step is torch's own AdamW as in the reference, and everything else
+``libddiffpg_b200.so`` (``RNDModel.precision``: "fp32" FMA tile kernel, or "bf16" tcgen05 GEMMs for the update-batch
+sizes), the optimizer step is torch's own AdamW as in the reference, and everything else
 (reward shaping, positional encoding, running statistics) remains the reference's code.
 """
 from collections.abc import Sequence
@@ -19,8 +20,9 @@ from .models import _PackCache
 
 
 class RNDModel(nn.Module):
-    def __init__(self, state_dim, hidden=(512, 256, 128), feature_dim=128):
+    def __init__(self, state_dim, hidden=(512, 256, 128), feature_dim=128, precision="fp32"):
         super().__init__()
+        self.precision = precision      # "fp32" | "bf16" (tensor path: D <= 256, hidden widths multiples of 64)
         if isinstance(state_dim, Sequence):
             state_dim = state_dim[0]
         self.state_dim, self.hidden, self.feature_dim = int(state_dim), tuple(hidden), int(feature_dim)
@@ -49,17 +51,24 @@ class RNDModel(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("ddiffpg_b200.RNDModel runs on CUDA only (no CPU fallback)")
         shape = RndShape(self.state_dim, self.feature_dim, *self.hidden)
-        if self._cache.stale(params, ("rnd", str(dev))):
-            nbytes = lib().ddp_rnd_packed_bytes(shape)
+        prec = _lib.PRECISIONS[self.precision]
+        if self._cache.stale(params, ("rnd", self.precision, str(dev))):
+            nbytes = lib().ddp_rnd_packed_bytes_p(shape, prec)
             if nbytes == 0:
-                check(-1, "ddp_rnd_packed_bytes")
+                check(-1, "ddp_rnd_packed_bytes_p")
             if self._cache.buf is None or self._cache.buf.numel() != nbytes or self._cache.buf.device != dev:
                 self._cache.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             with torch.cuda.device(dev):
-                check(lib().ddp_rnd_pack(shape, ptr_array([p.detach() for p in params]), ptr(self._cache.buf),
-                                         stream_ptr()), "ddp_rnd_pack")
+                check(lib().ddp_rnd_pack_p(shape, ptr_array([p.detach() for p in params]), ptr(self._cache.buf), prec,
+                                           stream_ptr()), "ddp_rnd_pack_p")
             self._cache.dirty = False
-        return self._cache.buf, shape
+        return self._cache.buf, shape, prec
+
+    def _workspace(self, shape, B, prec, dev):
+        ws_bytes = lib().ddp_rnd_workspace_bytes_p(shape, B, prec)
+        if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
+            self._ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=dev)
+        return self._ws, ws_bytes
 
     def _x(self, state, dev):
         x = state.detach().to(device=dev, dtype=torch.float32).contiguous()
@@ -70,7 +79,7 @@ class RNDModel(nn.Module):
     @torch.no_grad()
     def features(self, state, want_features=True):
         """(novelty [B], predict_feature [B,F], target_feature [B,F]) from one launch."""
-        packed, shape = self._packed()
+        packed, shape, prec = self._packed()
         x = self._x(state, packed.device)
         B = x.shape[0]
         nov = torch.empty(B, device=x.device)
@@ -78,8 +87,9 @@ class RNDModel(nn.Module):
         tf = torch.empty(B, self.feature_dim, device=x.device) if want_features else None
         if B:
             with torch.cuda.device(x.device):
-                check(lib().ddp_rnd_novelty(shape, ptr(packed), ptr(x), ptr(nov), ptr(pf), ptr(tf), B, stream_ptr()),
-                      "ddp_rnd_novelty")
+                ws, ws_bytes = self._workspace(shape, B, prec, x.device)
+                check(lib().ddp_rnd_novelty_p(shape, ptr(packed), ptr(x), ptr(nov), ptr(pf), ptr(tf), B, prec, ptr(ws),
+                                              ws_bytes, stream_ptr()), "ddp_rnd_novelty_p")
         return nov, pf, tf
 
     def forward(self, state):
@@ -92,18 +102,16 @@ class RNDModel(nn.Module):
 
     def loss_and_grads(self, state):
         """mse_loss(predictor(x), target(x)) and its flat gradient w.r.t. the predictor parameters."""
-        packed, shape = self._packed()
+        packed, shape, prec = self._packed()
         x = self._x(state, packed.device)
         B = x.shape[0]
         n = lib().ddp_rnd_grad_count(shape)
         grads = torch.empty(n, device=x.device)
         loss = torch.zeros((), device=x.device)
         with torch.cuda.device(x.device):
-            ws_bytes = lib().ddp_rnd_train_workspace_bytes(shape, B)
-            if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != x.device:
-                self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-            check(lib().ddp_rnd_loss_fwd_bwd(shape, ptr(packed), ptr(x), ptr(loss), ptr(grads), None, B, ptr(self._ws),
-                                             ws_bytes, stream_ptr()), "ddp_rnd_loss_fwd_bwd")
+            ws, ws_bytes = self._workspace(shape, B, prec, x.device)
+            check(lib().ddp_rnd_loss_fwd_bwd_p(shape, ptr(packed), ptr(x), ptr(loss), ptr(grads), None, B, prec, ptr(ws),
+                                               ws_bytes, stream_ptr()), "ddp_rnd_loss_fwd_bwd_p")
         return loss, grads
 
 

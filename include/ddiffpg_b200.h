@@ -215,6 +215,20 @@ size_t ddp_rnd_train_workspace_bytes(const ddp_rnd_shape* shape, long B);
 int ddp_rnd_loss_fwd_bwd(const ddp_rnd_shape* shape, const void* packed, const float* x, float* loss_out,
                          float* grads_flat, float* novelty_out, long B, void* ws, size_t ws_bytes, void* stream);
 
+/* The same three calls with a precision argument (the forms above are DDP_FP32).  DDP_BF16: tcgen05 row / dW GEMMs
+ * with fp32 accumulation, novelty / mse / gradients of the loss in fp32 (1e-2); for the update-batch sizes the reference
+ * calls IntrinsicM.compute_reward / update with (ddiffpg/algo/ddiffpg.py:225,296-299: 4 096 rows, NovelD 8 192).
+ * Needs D <= 256 and hidden widths multiples of 64.  `packed` must come from ddp_rnd_pack_p with the same precision;
+ * ws: ddp_rnd_workspace_bytes_p (novelty needs it on the tensor path only; may be NULL with DDP_FP32). */
+size_t ddp_rnd_packed_bytes_p(const ddp_rnd_shape* shape, int precision);
+int ddp_rnd_pack_p(const ddp_rnd_shape* shape, const float* const params[16], void* packed, int precision, void* stream);
+size_t ddp_rnd_workspace_bytes_p(const ddp_rnd_shape* shape, long B, int precision);
+int ddp_rnd_novelty_p(const ddp_rnd_shape* shape, const void* packed, const float* x, float* novelty_out,
+                      float* pred_out, float* target_out, long B, int precision, void* ws, size_t ws_bytes, void* stream);
+int ddp_rnd_loss_fwd_bwd_p(const ddp_rnd_shape* shape, const void* packed, const float* x, float* loss_out,
+                           float* grads_flat, float* novelty_out, long B, int precision, void* ws, size_t ws_bytes,
+                           void* stream);
+
 /* ----------------------------------------------------------------------------------------------
  * Batch assembly / scatter-back around the hot path, all mode groups in one launch.
  * Replay storage as in DiffusionReplayBuffer (ddiffpg/replay/simple_replay.py:98-200): buf_obs / buf_next_obs [N,O],

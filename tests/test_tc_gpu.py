@@ -564,3 +564,76 @@ def test_critic_update_bf16_large_batch_is_mean_of_halves():
     l_b, g_b = run(slice(B // 2, B))
     assert abs(l_all.item() - 0.5 * (l_a.item() + l_b.item())) <= 1e-5 * abs(l_all.item())
     assert _rel_l2(g_all, 0.5 * (g_a + g_b)) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------ N4 tensor path
+def _rnd_bf16(p):
+    from ddiffpg_b200 import RNDModel
+    m = RNDModel(69, precision="bf16")
+    m.load_state_dict(p)
+    return m.to("cuda")
+
+
+def test_rnd_bf16_reference_fixture():
+    """IntrinsicM.get_novelty / update (utils/intrinsic.py:62-75) on the tcgen05 path against the reference's own outputs
+    (fixture n4_rnd): novelty and features within 1e-2 of their scale, loss 2e-3 relative, every predictor gradient tensor
+    1e-2 relative L2."""
+    g = load_golden("n4_rnd")
+    p = port.init_rnd_params(71)
+    m = _rnd_bf16(p)
+    enc = _dev(g["enc"])
+    nov = m.novelty(enc).cpu()
+    ref = torch.from_numpy(g["novelty"])
+    assert (nov - ref).abs().max().item() <= BF16_ATOL * ref.abs().max().item()
+    x = port.encode_obs_antmaze(torch.cat([torch.from_numpy(g["obs"]), torch.from_numpy(g["nobs"])]))
+    loss, flat = m.loss_and_grads(_dev(x))
+    assert abs(loss.item() - float(g["loss"])) <= 2e-3 * float(g["loss"])
+    off = 0
+    for i, (k, q) in enumerate(m.predictor.named_parameters()):
+        got = flat[off:off + q.numel()].view(q.shape).cpu()
+        off += q.numel()
+        ref = torch.from_numpy(g[f"g_{i}"])
+        sub = got if got.numel() <= 8192 else got.flatten()[::97]
+        assert _rel_l2(sub.reshape(ref.shape), ref) <= BF16_ATOL, (k, _rel_l2(sub.reshape(ref.shape), ref))
+        assert abs(float(got.norm()) - float(g[f"gnorm_{i}"])) <= BF16_ATOL * float(g[f"gnorm_{i}"]) + 1e-9, k
+    assert off == flat.numel()
+    pf, tf = m(_dev(x))
+    rp, rt = port.rnd_forward(p, x)
+    for got, want in ((pf, rp), (tf, rt)):
+        assert (got.cpu() - want).abs().max().item() <= BF16_ATOL * want.abs().max().item()
+
+
+@pytest.mark.parametrize("B", [1, 9, 130, 4096])
+def test_rnd_bf16_vs_oracle_batches(B):
+    p = port.init_rnd_params(72, scale=1.3)
+    gen = torch.Generator().manual_seed(900 + B)
+    x = torch.randn(B, 69, generator=gen)
+    m = _rnd_bf16(p)
+    nov, ref = m.novelty(_dev(x)).cpu(), port.rnd_novelty(p, x)
+    assert (nov - ref).abs().max().item() <= BF16_ATOL * ref.abs().max().item()
+    loss, flat = m.loss_and_grads(_dev(x))
+    l_ref, g_ref = port.rnd_loss_and_grads(p, x)
+    assert abs(loss.item() - l_ref.item()) <= 2e-3 * l_ref.item()
+    off = 0
+    for k in (k for k in port.RND_KEYS if k.startswith("predictor")):
+        n = p[k].numel()
+        e = _rel_l2(flat[off:off + n].view(p[k].shape).cpu(), g_ref[k])
+        assert e <= (BF16_ATOL if B >= 100 else 2 * BF16_ATOL), (k, e)
+        off += n
+    assert off == flat.numel()
+
+
+def test_rnd_bf16_large_batch_matches_fp32_path():
+    """262 144 rows (no oracle at this size): the tensor path against this repo's own fp32 FMA path -- novelty within
+    1e-2 of its scale, loss 2e-3, flat gradient 1e-2 relative L2."""
+    from ddiffpg_b200 import RNDModel
+    p = port.init_rnd_params(73)
+    m16, m32 = _rnd_bf16(p), RNDModel(69)
+    m32.load_state_dict(p)
+    m32 = m32.to("cuda")
+    x = torch.randn(262144, 69, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    n16, n32 = m16.novelty(x), m32.novelty(x)
+    assert (n16 - n32).abs().max().item() <= BF16_ATOL * n32.abs().max().item()
+    (l16, g16), (l32, g32) = m16.loss_and_grads(x), m32.loss_and_grads(x)
+    assert abs(l16.item() - l32.item()) <= 2e-3 * l32.item()
+    assert _rel_l2(g16, g32) <= BF16_ATOL
