@@ -34,6 +34,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     return ok != 0;
 }
+// non-blocking probe (no suspend hint): has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 // Bounded spin: a protocol bug must surface as a trap (reported by the next CUDA call), not as a hang
 // of the GPU box.  ~2^28 polls is seconds; a healthy wait is microseconds.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {

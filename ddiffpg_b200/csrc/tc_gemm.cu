@@ -32,18 +32,26 @@ constexpr uint32_t kSmemBytes = kOffOnes + 8192 + 1024;
 // coalesced global accesses (two [32 rows][128 B] buffers per epilogue warp)
 constexpr int kRowStages = 3;
 constexpr uint32_t kRowOffBars = kRowStages * kStageBytes;
-constexpr uint32_t kRowOffStage = kRowOffBars + 256;
+constexpr uint32_t kRowOffStage = (kRowOffBars + 256 + 1023) / 1024 * 1024;      // 1024-aligned: also holds TMA boxes
 constexpr uint32_t kStageWarpBytes = 2 * 4096;
 constexpr uint32_t kRowSmemBytes = kRowOffStage + kRowEpiWarps * kStageWarpBytes + 1024;
 static_assert(kRowSmemBytes <= 227 * 1024, "row GEMM shared memory");
+// Backward epilogues with ONE row group (H3, N1, N4): the aux operand (stored derivative / activation) of a tile arrives
+// by TMA into the staging area and the masked gradient leaves from the same bytes by TMA store -- two [128 x 128] bf16
+// halves of the 256-column tile (four 16 KB SWIZZLE_128B boxes), so the load of the next tile's half overlaps the
+// epilogue of the other half.  No thread issues a row-per-lane global access any more.
+constexpr uint32_t kAuxHalfBytes = 2 * 128 * 128;
+static_assert(2 * kAuxHalfBytes <= kRowEpiWarps * kStageWarpBytes, "aux halves live in the forward staging area");
 
 struct WMaps { CUtensorMap m[kMaxGroups]; };
+struct AuxMaps { CUtensorMap in, out; };
 
 struct RowKernelArgs {
     RowGemm g;
     long tile0[kMaxGroups + 1];    // first m-tile of each group
     int n_tiles_n, BN;
     long total_tiles;
+    int tma_aux;                   // 1: backward epilogue through the TMA-staged aux tile (see kAuxHalfBytes)
 };
 
 // 16-bit (bf16) row-major matrix [rows][cols valid] with leading dimension ld; box = [box_rows][64 columns],
@@ -75,7 +83,8 @@ __device__ __forceinline__ void store_bf16x16(__nv_bfloat16* p, const float (&v)
 }
 // ------------------------------------------------------------------------------------------ row GEMM
 __global__ void __launch_bounds__(kThreads, 1)
-row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ WMaps maps_w, const RowKernelArgs k) {
+row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ WMaps maps_w,
+                const __grid_constant__ AuxMaps maps_x, const RowKernelArgs k) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -87,13 +96,17 @@ row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     auto bar_acc_full = [&](int i) { return bars + 8 * (2 * kStages + i); };
     auto bar_acc_empty = [&](int i) { return bars + 8 * (2 * kStages + 2 + i); };
     const uint32_t tmem_slot = bars + 8 * (2 * kStages + 4);
+    auto bar_aux_full = [&](int i) { return bars + 8 * (2 * kStages + 5 + i); };
+    auto bar_aux_empty = [&](int i) { return bars + 8 * (2 * kStages + 7 + i); };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const RowGemm& g = k.g;
     const int kchunks = (g.K + 63) >> 6;
+    const int halves = (k.BN + 127) >> 7;          // 128-column halves of a tile (TMA-staged backward epilogue)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full(i), 1); mbar_init(bar_acc_empty(i), kRowEpiWarps); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_aux_full(i), 1); mbar_init(bar_aux_empty(i), 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -115,17 +128,37 @@ row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (warp == 0) {
         if (lane == 0) {
             tma_prefetch_desc(&map_a);
-            int st = 0; uint32_t ph = 0;
-            for (long tile = blockIdx.x; tile < k.total_tiles; tile += gridDim.x) {
+            if (k.tma_aux) { tma_prefetch_desc(&maps_x.in); tma_prefetch_desc(&maps_x.out); }
+            int st = 0; uint32_t ph = 0, it = 0;
+            for (long tile = blockIdx.x; tile < k.total_tiles; tile += gridDim.x, ++it) {
                 int grp, n0; long row0, row_end;
                 decode(tile, grp, row0, row_end, n0);
+                // aux halves of this tile: requested as soon as the epilogue has shipped the previous tile's half out of
+                // the buffer -- polled between the operand stages, so that neither stream waits for the other
+                int aux_next = k.tma_aux ? 0 : halves;
+                auto aux_load = [&](bool block) {
+                    while (aux_next < halves) {
+                        const int h = aux_next;
+                        if (block) mbar_wait(bar_aux_empty(h), (it & 1) ^ 1);
+                        else if (!mbar_test_wait(bar_aux_empty(h), (it & 1) ^ 1)) return;
+                        const int c0 = n0 + h * 128;
+                        const int boxes = (g.N - c0 + 63) / 64 < 2 ? (g.N - c0 + 63) / 64 : 2;
+                        mbar_expect_tx(bar_aux_full(h), (uint32_t)boxes * 128u * 128u);
+                        for (int b = 0; b < boxes; ++b)
+                            tma_load_2d(base + kRowOffStage + h * kAuxHalfBytes + b * 16384, &maps_x.in, bar_aux_full(h),
+                                        c0 + b * 64, (int)row0);
+                        ++aux_next;
+                    }
+                };
                 for (int c = 0; c < kchunks; ++c) {
+                    aux_load(false);
                     mbar_wait(bar_empty(st), ph ^ 1);
                     mbar_expect_tx(bar_full(st), (uint32_t)(kStageA + k.BN * 128));
                     tma_load_2d(base + st * kStageBytes, &map_a, bar_full(st), c * 64, (int)row0);
                     tma_load_2d(base + st * kStageBytes + kStageA, &maps_w.m[grp], bar_full(st), c * 64, n0);
                     if (++st == kStages) { st = 0; ph ^= 1; }
                 }
+                aux_load(true);
             }
         }
     } else if (warp == 1) {
@@ -280,6 +313,62 @@ row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             uint32_t va[16], vb[16];
             const bool needs_aux = g.epi == EPI_MUL_D || g.epi == EPI_MUL_ELU_D;
             static_assert(256 / 16 / (kRowEpiWarps / 4) <= 8, "a warp owns at most 8 pieces of a tile");
+            if (needs_aux && k.tma_aux) {
+                // thread = one row; the warps of a lane quarter split the 16-column pieces of each 128-column half
+                const int r = q * 32 + lane;
+                mbar_wait(bar_acc_full(buf), (it >> 1) & 1);
+                tc_fence_after();
+                for (int h = 0; h < halves; ++h) {
+                    const int hp = (k.BN - h * 128 < 128 ? k.BN - h * 128 : 128) >> 4;      // pieces of this half
+                    const int pb = (hp * part + kSplit - 1) / kSplit, pe = (hp * (part + 1) + kSplit - 1) / kSplit;
+                    uint8_t* stg = smem + kRowOffStage + h * kAuxHalfBytes;
+                    if (pb < pe) tmem_ld16(tb + (h * 8 + pb) * 16, va);
+                    mbar_wait(bar_aux_full(h), it & 1);
+                    for (int p = pb; p < pe; ++p) {
+                        tmem_ld_wait();
+                        uint32_t cur[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) cur[i] = va[i];
+                        if (p + 1 < pe) tmem_ld16(tb + (h * 8 + p + 1) * 16, va);
+                        uint8_t* bx = stg + (p >> 2) * 16384;
+                        uint4* s0 = reinterpret_cast<uint4*>(bx + sw128_offset(r, (p & 3) * 16));
+                        uint4* s1 = reinterpret_cast<uint4*>(bx + sw128_offset(r, (p & 3) * 16 + 8));
+                        const uint4 a0 = *s0, a1 = *s1;
+                        const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                        float z[16];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xffff0000u);
+                            if (g.epi == EPI_MUL_D) {
+                                z[2 * i] = __uint_as_float(cur[2 * i]) * lo;
+                                z[2 * i + 1] = __uint_as_float(cur[2 * i + 1]) * hi;
+                            } else {
+                                z[2 * i] = __uint_as_float(cur[2 * i]) * (lo > 0.f ? 1.f : lo + 1.f);
+                                z[2 * i + 1] = __uint_as_float(cur[2 * i + 1]) * (hi > 0.f ? 1.f : hi + 1.f);
+                            }
+                        }
+                        *s0 = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]), pack_bf16x2(z[6], z[7]));
+                        *s1 = make_uint4(pack_bf16x2(z[8], z[9]), pack_bf16x2(z[10], z[11]), pack_bf16x2(z[12], z[13]), pack_bf16x2(z[14], z[15]));
+                    }
+                    if (h == halves - 1) {
+                        // every TMEM read of this tile is done: the MMA warp may start the tile after next in this buffer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_acc_empty(buf));
+                    }
+                    fence_proxy_async();                                   // generic-proxy stores -> visible to the TMA store
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * kRowEpiWarps) : "memory");
+                    if (threadIdx.x == 64) {
+                        const int c0 = n0 + h * 128;
+                        for (int b = 0; b < 2 && c0 + b * 64 < g.N; ++b)
+                            tma_store_2d(&maps_x.out, base + kRowOffStage + h * kAuxHalfBytes + b * 16384, c0 + b * 64, (int)row0);
+                        tma_store_commit();
+                        tma_store_wait_read();                             // the buffer may be refilled
+                        mbar_arrive(bar_aux_empty(h));
+                    }
+                }
+                continue;
+            }
             if (needs_aux) {
                 uint4 axq[16];
 #pragma unroll
@@ -350,6 +439,7 @@ row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (lane == 0) mbar_arrive(bar_acc_empty(buf));
         }
     }
+    if (threadIdx.x == 64 && k.tma_aux) tma_store_wait_all();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
@@ -504,6 +594,8 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant_
 
 }  // namespace
 
+static bool g_row_no_tma_aux = false;       // ddp_debug_row_gemm_direct_aux: A/B switch for the backward epilogue (tests, measurements)
+
 int launch_row_gemm(const RowGemm& g, cudaStream_t st) {
     if (g.M <= 0) return DDP_OK;
     if (g.N <= 0 || g.K <= 0 || g.lda % 8 || g.ldw % 8) DDP_FAIL(DDP_ERR_SHAPE, "row gemm: bad shape (N=%d K=%d lda=%d ldw=%d)", g.N, g.K, g.lda, g.ldw);
@@ -529,12 +621,24 @@ int launch_row_gemm(const RowGemm& g, cudaStream_t st) {
         if (make_tmap(&mw.m[i], g.W + (size_t)i * g.w_stride, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, (uint32_t)k.BN) != 0)
             DDP_FAIL(DDP_ERR_CUDA, "row gemm: tensor map (W) failed");
     for (int i = g.groups.n_groups; i < kMaxGroups; ++i) mw.m[i] = mw.m[0];
+    // backward epilogues of a single row group go through the TMA-staged aux tile (a box written past the end of a group
+    // would land in the next group's rows; the tensor map only clips at M)
+    AuxMaps mx;
+    mx.in = ma; mx.out = ma;
+    const bool needs_aux = g.epi == EPI_MUL_D || g.epi == EPI_MUL_ELU_D;
+    k.tma_aux = (needs_aux && !g_row_no_tma_aux && g.groups.n_groups == 1 && g.N % 64 == 0 && g.aux_ld % 8 == 0 &&
+                 g.out_ld % 8 == 0 && ((uintptr_t)g.aux & 15) == 0 && ((uintptr_t)g.out_a & 15) == 0) ? 1 : 0;
+    if (k.tma_aux) {
+        if (make_tmap(&mx.in, g.aux, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.aux_ld, 128) != 0 ||
+            make_tmap(&mx.out, g.out_a, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.out_ld, 128) != 0)
+            DDP_FAIL(DDP_ERR_CUDA, "row gemm: tensor map (aux) failed");
+    }
     int dev = 0, sms = 0;
     DDP_CUDA_CHECK(cudaGetDevice(&dev));
     DDP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     DDP_CUDA_CHECK(cudaFuncSetAttribute(row_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowSmemBytes));
     const long grid = k.total_tiles < sms ? k.total_tiles : sms;
-    row_gemm_kernel<<<(unsigned)grid, kThreads, kRowSmemBytes, st>>>(ma, mw, k);
+    row_gemm_kernel<<<(unsigned)grid, kThreads, kRowSmemBytes, st>>>(ma, mw, mx, k);
     DDP_LAUNCH_CHECK("row_gemm_kernel");
     return DDP_OK;
 }
@@ -570,6 +674,10 @@ int launch_dw_gemm(const DwGemm& g, cudaStream_t st) {
 
 }  // namespace tcg
 }  // namespace ddp
+
+// Debug entry point (not part of the public header): 1 = backward epilogues with direct row-per-lane global accesses
+// instead of the TMA-staged aux tile.  Process-wide; A/B measurements and tests only.
+extern "C" void ddp_debug_row_gemm_direct_aux(int on) { ddp::tcg::g_row_no_tma_aux = on != 0; }
 
 // Debug entry points (not part of the public header) used by tests/test_tc_gemm_gpu.py
 extern "C" int ddp_debug_row_gemm(const void* A, int lda, const void* W, int ldw, long M, int N, int K, int epi,

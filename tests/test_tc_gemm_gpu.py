@@ -27,13 +27,13 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def row_gemm(A, W, epi, bias=None, aux=None, groups=None, tbl=None, trow=None):
+def row_gemm(A, W, epi, bias=None, aux=None, groups=None, tbl=None, trow=None, in_place=False):
     L, _lib = _load()
     M, K = A.shape
     ng = 1 if groups is None else len(groups) - 1
     N = W.shape[-2]
     off = (c_long * (ng + 1))(*([0, M] if groups is None else groups))
-    out_a = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    out_a = aux if in_place else torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
     out_d = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
     out_f = torch.zeros(M, N, device="cuda")
     rc = L.ddp_debug_row_gemm(_ptr(A), A.stride(0), _ptr(W), W.stride(-2), M, N, K, epi, _ptr(bias), _ptr(aux), _ptr(out_a),
@@ -97,6 +97,33 @@ def test_row_gemm_elu_forward_and_backward_masks():
     m2, _, _ = row_gemm(A, W, 4, aux=act)
     dz = torch.where(act.float() > 0, torch.ones_like(z), act.float() + 1)
     _close(m2, (A.float() @ W.float().t()) * dz, 1e-2, 2e-2, "mul_elu_d")
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 64, 64), (127, 128, 64), (129, 256, 128), (400, 512, 256), (1000, 1024, 512),
+                                   (20000, 256, 64), (70001, 512, 512)])
+@pytest.mark.parametrize("epi", [3, 4])
+def test_row_gemm_backward_epilogue_tma_equals_direct(M, N, K, epi):
+    """The backward maskings through the TMA-staged aux tile (one row group: aux in by TMA, gradient out by TMA store,
+    in place) against the direct row-per-lane epilogue: same arithmetic, so bit-identical -- ragged last tiles (rows
+    past M are clipped by the tensor map), one to four 256-column tiles, 64- / 128-column halves; and against torch."""
+    L, _ = _load()
+    dbg = L.ddp_debug_row_gemm_direct_aux
+    dbg.argtypes, dbg.restype = [c_int], None
+    gen = torch.Generator().manual_seed(M + N + K + epi)
+    A, W = _mk((M, K), gen), _mk((N, K), gen, K ** -0.5)
+    aux = _mk((M, N), gen) if epi == 3 else F.elu(_mk((M, N), gen).float()).to(torch.bfloat16)
+    guard = torch.full((64, N), 3.0, dtype=torch.bfloat16, device="cuda")      # rows behind the matrix must stay untouched
+    buf = torch.cat([aux, guard])
+    tma, _, _ = row_gemm(A, W, epi, aux=buf[:M].clone() if False else buf[:M], in_place=True)
+    assert torch.equal(buf[M:], guard)
+    dbg(1)
+    try:
+        direct, _, _ = row_gemm(A, W, epi, aux=aux.clone(), in_place=True)
+    finally:
+        dbg(0)
+    assert torch.equal(tma, direct)
+    d = aux.float() if epi == 3 else torch.where(aux.float() > 0, torch.ones_like(aux, dtype=torch.float32), aux.float() + 1)
+    _close(tma, (A.float() @ W.float().t()) * d, 1e-2, 2e-2 * K ** 0.5 / 8, "masked gradient")
 
 
 def test_row_gemm_groups_use_their_own_weights():
