@@ -166,39 +166,9 @@ __device__ __forceinline__ void store_chunk16(uint8_t* slot, int row, int col0, 
     }
 }
 
-#ifndef DDP_QC_H2FWD
-#define DDP_QC_H2FWD 0
-#endif
-constexpr bool kH2Fwd = DDP_QC_H2FWD != 0;
-
-// forward in packed fp16 (kH2Fwd): 16 accumulator columns -> fp16 pairs, + bias, ELU and its derivative e = exp(min(x, 0))
-// in HADD2 / HMNMX2 / HMUL2 + ex2.f16x2: the activation pairs are the next layer's fp16 MMA operand as they are and the
-// derivative pairs go to the scratch as they are -- no conversion, no select (78 instead of 136 instructions per piece)
-__device__ __forceinline__ void emit_fwd_h2(const QEpi& e, uint8_t* slot, const uint32_t (&v)[16], const __half2* bb,
-                                            int col0, uint16_t* dptr) {
-    const __half2 kZero = __float2half2_rn(0.f), kOne = __float2half2_rn(1.f), kL2E = __float2half2_rn(kLog2e);
-    uint32_t a[8], d[8];
-    const uint4 b0 = *reinterpret_cast<const uint4*>(bb), b1 = *reinterpret_cast<const uint4*>(bb + 4);
-    const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const __half2 x = __hadd2(__floats2half2_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), u32_as_h2(bw[i]));
-        const __half2 t = __hmin2(x, kZero);
-        uint32_t eb;
-        asm("ex2.approx.f16x2 %0, %1;" : "=r"(eb) : "r"(h2_as_u32(__hmul2(t, kL2E))));
-        d[i] = eb;
-        a[i] = h2_as_u32(__hadd2(__hmax2(x, kZero), __hsub2(u32_as_h2(eb), kOne)));
-    }
-    *reinterpret_cast<uint4*>(slot + sw128_offset(e.my_row, col0)) = make_uint4(a[0], a[1], a[2], a[3]);
-    *reinterpret_cast<uint4*>(slot + sw128_offset(e.my_row, col0 + 8)) = make_uint4(a[4], a[5], a[6], a[7]);
-    __stcg(reinterpret_cast<uint4*>(dptr), make_uint4(d[0], d[1], d[2], d[3]));
-    __stcg(reinterpret_cast<uint4*>(dptr) + kRows, make_uint4(d[4], d[5], d[6], d[7]));
-}
-
 // forward: 16 accumulator columns -> +bias, ELU -> A chunk (bf16); ELU' -> scratch (bf16)
 __device__ __forceinline__ void emit_fwd(const QEpi& e, uint8_t* slot, const uint32_t (&v)[16], const float* bb,
                                          int col0, uint16_t* dptr) {
-    if (kH2Fwd) { emit_fwd_h2(e, slot, v, reinterpret_cast<const __half2*>(bb), col0, dptr); return; }
     float x[16], d[16];
 #pragma unroll
     for (int i4 = 0; i4 < 4; ++i4) {
@@ -231,14 +201,8 @@ __device__ __forceinline__ void emit_bwd(const QEpi& e, uint8_t* slot, const uin
     const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        if (kH2Fwd) {
-            const float2 f = __half22float2(u32_as_h2(dw[i]));
-            x[2 * i] = __uint_as_float(v[2 * i]) * f.x;
-            x[2 * i + 1] = __uint_as_float(v[2 * i + 1]) * f.y;
-        } else {
-            x[2 * i] = __uint_as_float(v[2 * i]) * __uint_as_float(dw[i] << 16);
-            x[2 * i + 1] = __uint_as_float(v[2 * i + 1]) * __uint_as_float(dw[i] & 0xffff0000u);
-        }
+        x[2 * i] = __uint_as_float(v[2 * i]) * __uint_as_float(dw[i] << 16);
+        x[2 * i + 1] = __uint_as_float(v[2 * i + 1]) * __uint_as_float(dw[i] & 0xffff0000u);
     }
     store_chunk16(slot, e.my_row, col0, x);
 }
