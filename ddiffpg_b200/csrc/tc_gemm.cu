@@ -52,6 +52,7 @@ struct RowKernelArgs {
     int n_tiles_n, BN;
     long total_tiles;
     int tma_aux;                   // 1: backward epilogue through the TMA-staged aux tile (see kAuxHalfBytes)
+    int tma_fwd;                   // 1: ELU forward epilogue written as SWIZZLE_128B boxes and shipped by TMA store
 };
 
 // 16-bit (bf16) row-major matrix [rows][cols valid] with leading dimension ld; box = [box_rows][64 columns],
@@ -129,6 +130,7 @@ row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (lane == 0) {
             tma_prefetch_desc(&map_a);
             if (k.tma_aux) { tma_prefetch_desc(&maps_x.in); tma_prefetch_desc(&maps_x.out); }
+            if (k.tma_fwd) tma_prefetch_desc(&maps_x.out);
             int st = 0; uint32_t ph = 0, it = 0;
             for (long tile = blockIdx.x; tile < k.total_tiles; tile += gridDim.x, ++it) {
                 int grp, n0; long row0, row_end;
@@ -185,7 +187,7 @@ row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     } else {
         // ------------------------------------------------------------ epilogue: thread = one row of the tile
         const int q = warp & 3;
-        uint32_t it = 0;
+        uint32_t it = 0, hb = 0;
         for (long tile = blockIdx.x; tile < k.total_tiles; tile += gridDim.x, ++it) {
             int grp, n0; long row0, row_end;
             decode(tile, grp, row0, row_end, n0);
@@ -258,9 +260,16 @@ row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     put(stg_a, z);
                 } else if (g.epi == EPI_LINEAR_F32) {
                     if (valid && c0 < g.N) {
+                        float* o = g.out_f + row * g.outf_ld + c0;
+                        if (c0 + 16 <= g.n_valid && (g.outf_ld & 3) == 0 && ((uintptr_t)g.out_f & 15) == 0) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (c0 + i < g.n_valid) g.out_f[row * g.outf_ld + c0 + i] = z[i];
+                            for (int i4 = 0; i4 < 4; ++i4)
+                                reinterpret_cast<float4*>(o)[i4] = make_float4(z[4 * i4], z[4 * i4 + 1], z[4 * i4 + 2], z[4 * i4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < g.n_valid) o[i] = z[i];
+                        }
                     }
                 } else if (g.epi == EPI_MSE_HEAD) {
                     // one 16-column piece per tile: squared error of the row, its gradient as a zero-padded 64-column
@@ -402,6 +411,58 @@ row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 if (lane == 0) mbar_arrive(bar_acc_empty(buf));
                 continue;
             }
+            if (k.tma_fwd) {
+                // ELU forward of a single row group: the thread that owns a row writes its packed pieces straight into
+                // the box layout of a [128 x 128] half (two buffers, alternating), one thread ships the half by TMA
+                // store -- no copy-out loop, no row-per-lane global store.  Buffer b is free again once the store
+                // thread has passed its wait_group.read and everybody has met at the next named barrier.
+                const int r = q * 32 + lane;
+                mbar_wait(bar_acc_full(buf), (it >> 1) & 1);
+                tc_fence_after();
+                for (int h = 0; h < halves; ++h, ++hb) {
+                    const int hp = (k.BN - h * 128 < 128 ? k.BN - h * 128 : 128) >> 4;
+                    const int pb = (hp * part + kSplit - 1) / kSplit, pe = (hp * (part + 1) + kSplit - 1) / kSplit;
+                    uint8_t* stg = smem + kRowOffStage + (hb & 1) * kAuxHalfBytes;
+                    if (pb < pe) tmem_ld16(tb + (h * 8 + pb) * 16, va);
+                    for (int p = pb; p < pe; ++p) {
+                        tmem_ld_wait();
+                        float z[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) z[i] = __uint_as_float(va[i]);
+                        if (p + 1 < pe) tmem_ld16(tb + (h * 8 + p + 1) * 16, va);
+                        const int c0 = n0 + (h * 8 + p) * 16;
+                        if (bias && c0 < g.N) {
+#pragma unroll
+                            for (int i4 = 0; i4 < 4; ++i4) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + i4);
+                                z[4 * i4] += b.x; z[4 * i4 + 1] += b.y; z[4 * i4 + 2] += b.z; z[4 * i4 + 3] += b.w;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) z[i] = z[i] > 0.f ? z[i] : ex2_approx(z[i] * 1.4426950408889634f) - 1.f;
+                        uint8_t* bx = stg + (p >> 2) * 16384;
+                        *reinterpret_cast<uint4*>(bx + sw128_offset(r, (p & 3) * 16)) =
+                            make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]), pack_bf16x2(z[6], z[7]));
+                        *reinterpret_cast<uint4*>(bx + sw128_offset(r, (p & 3) * 16 + 8)) =
+                            make_uint4(pack_bf16x2(z[8], z[9]), pack_bf16x2(z[10], z[11]), pack_bf16x2(z[12], z[13]), pack_bf16x2(z[14], z[15]));
+                    }
+                    if (h == halves - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_acc_empty(buf));
+                    }
+                    fence_proxy_async();
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * kRowEpiWarps) : "memory");
+                    if (threadIdx.x == 64) {
+                        const int c0 = n0 + h * 128;
+                        for (int b = 0; b < 2 && c0 + b * 64 < g.N; ++b)
+                            tma_store_2d(&maps_x.out, base + kRowOffStage + (hb & 1) * kAuxHalfBytes + b * 16384, c0 + b * 64, (int)row0);
+                        tma_store_commit();
+                        tma_store_wait_read();
+                    }
+                }
+                continue;
+            }
             mbar_wait(bar_acc_full(buf), (it >> 1) & 1);
             tc_fence_after();
             if (p_begin < p_end) tmem_ld16(tb + p_begin * 16, va);
@@ -439,7 +500,7 @@ row_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (lane == 0) mbar_arrive(bar_acc_empty(buf));
         }
     }
-    if (threadIdx.x == 64 && k.tma_aux) tma_store_wait_all();
+    if (threadIdx.x == 64 && (k.tma_aux || k.tma_fwd)) tma_store_wait_all();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
@@ -628,6 +689,10 @@ int launch_row_gemm(const RowGemm& g, cudaStream_t st) {
     const bool needs_aux = g.epi == EPI_MUL_D || g.epi == EPI_MUL_ELU_D;
     k.tma_aux = (needs_aux && !g_row_no_tma_aux && g.groups.n_groups == 1 && g.N % 64 == 0 && g.aux_ld % 8 == 0 &&
                  g.out_ld % 8 == 0 && ((uintptr_t)g.aux & 15) == 0 && ((uintptr_t)g.out_a & 15) == 0) ? 1 : 0;
+    k.tma_fwd = (g.epi == EPI_ELU_FWD && !g_row_no_tma_aux && g.groups.n_groups == 1 && g.N % 64 == 0 && g.out_ld % 8 == 0 &&
+                 ((uintptr_t)g.out_a & 15) == 0 && !g.tbl) ? 1 : 0;
+    if (k.tma_fwd && make_tmap(&mx.out, g.out_a, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.out_ld, 128) != 0)
+        DDP_FAIL(DDP_ERR_CUDA, "row gemm: tensor map (out) failed");
     if (k.tma_aux) {
         if (make_tmap(&mx.in, g.aux, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.aux_ld, 128) != 0 ||
             make_tmap(&mx.out, g.out_a, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.out_ld, 128) != 0)
@@ -694,6 +759,18 @@ extern "C" int ddp_debug_row_gemm(const void* A, int lda, const void* W, int ldw
     g.out_f = out_f; g.outf_ld = N; g.n_valid = N;
     g.groups.n_groups = n_groups;
     for (int i = 0; i <= n_groups; ++i) g.groups.off[i] = group_off[i];
+    return launch_row_gemm(g, (cudaStream_t)stream);
+}
+
+// EPI_LINEAR_F32 with an explicit output leading dimension and valid-column count
+extern "C" int ddp_debug_row_gemm_nvalid(const void* A, int lda, const void* W, int ldw, long M, int N, int K,
+                                         const float* bias, float* out_f, int outf_ld, int n_valid, void* stream) {
+    using namespace ddp::tcg;
+    RowGemm g{};
+    g.A = (const __nv_bfloat16*)A; g.lda = lda; g.W = (const __nv_bfloat16*)W; g.ldw = ldw;
+    g.M = M; g.N = N; g.K = K; g.epi = EPI_LINEAR_F32; g.bias = bias;
+    g.out_f = out_f; g.outf_ld = outf_ld; g.n_valid = n_valid;
+    g.groups.n_groups = 1; g.groups.off[0] = 0; g.groups.off[1] = M;
     return launch_row_gemm(g, (cudaStream_t)stream);
 }
 

@@ -18,6 +18,8 @@ def _load():
     L.ddp_debug_row_gemm.argtypes = [c_void, c_int, c_void, c_int, c_long, c_int, c_int, c_int, c_void, c_void, c_void,
                                      c_void, c_void, c_int, ctypes.POINTER(c_long), c_size, c_size, c_void, c_void,
                                      c_int, c_int, c_void]
+    L.ddp_debug_row_gemm_nvalid.restype = c_int
+    L.ddp_debug_row_gemm_nvalid.argtypes = [c_void, c_int, c_void, c_int, c_long, c_int, c_int, c_void, c_void, c_int, c_int, c_void]
     L.ddp_debug_dw_gemm.restype = c_int
     L.ddp_debug_dw_gemm.argtypes = [c_void, c_int, c_int, c_void, c_int, c_int, c_long, c_void, c_int, c_void, c_void]
     return L, _lib
@@ -124,6 +126,47 @@ def test_row_gemm_backward_epilogue_tma_equals_direct(M, N, K, epi):
     assert torch.equal(tma, direct)
     d = aux.float() if epi == 3 else torch.where(aux.float() > 0, torch.ones_like(aux, dtype=torch.float32), aux.float() + 1)
     _close(tma, (A.float() @ W.float().t()) * d, 1e-2, 2e-2 * K ** 0.5 / 8, "masked gradient")
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 64, 64), (127, 128, 64), (129, 256, 128), (400, 512, 64), (1000, 1024, 256), (70001, 512, 64)])
+def test_row_gemm_elu_forward_tma_store_equals_staged(M, N, K):
+    """EPI_ELU_FWD of a single row group written as SWIZZLE_128B boxes and shipped by TMA store, against the per-warp
+    staged epilogue (bit-identical: same arithmetic) and against torch; rows behind the matrix stay untouched."""
+    L, _lib = _load()
+    dbg = L.ddp_debug_row_gemm_direct_aux
+    dbg.argtypes, dbg.restype = [c_int], None
+    gen = torch.Generator().manual_seed(3 * M + N + K)
+    A, W = _mk((M, K), gen), _mk((N, K), gen, K ** -0.5)
+    bias = torch.randn(N, generator=gen).cuda()
+    buf = torch.full((M + 64, N), 3.0, dtype=torch.bfloat16, device="cuda")
+    tma, _, _ = row_gemm(A, W, 1, bias=bias, aux=buf[:M], in_place=True)
+    assert torch.equal(buf[M:], torch.full((64, N), 3.0, dtype=torch.bfloat16, device="cuda"))
+    dbg(1)
+    try:
+        staged, _, _ = row_gemm(A, W, 1, bias=bias)
+    finally:
+        dbg(0)
+    assert torch.equal(tma, staged)
+    _close(tma, F.elu(A.float() @ W.float().t() + bias), 1e-2, 1e-2, "elu")
+
+
+@pytest.mark.parametrize("M,N,nv", [(300, 64, 51), (1000, 128, 128), (77, 16, 8)])
+def test_row_gemm_linear_partial_columns(M, N, nv):
+    """EPI_LINEAR_F32 with fewer valid columns than the tile (the 51 atoms of the critic head): whole 16-column pieces
+    go out as float4 stores, the ragged piece element by element; columns >= n_valid stay untouched."""
+    L, _lib = _load()
+    gen = torch.Generator().manual_seed(M + N + nv)
+    K = 128
+    A, W = _mk((M, K), gen), _mk((N, K), gen, K ** -0.5)
+    bias = torch.randn(N, generator=gen).cuda()
+    out_f = torch.full((M, N), -7.0, device="cuda")
+    off = (c_long * 2)(0, M)
+    rc = L.ddp_debug_row_gemm_nvalid(_ptr(A), K, _ptr(W), K, M, N, K, _ptr(bias), _ptr(out_f), N, nv, _lib.stream_ptr())
+    _lib.check(rc, "ddp_debug_row_gemm_nvalid")
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias
+    _close(out_f[:, :nv], ref[:, :nv], 1e-3, 1e-3, "linear")
+    assert (out_f[:, nv:] == -7.0).all()
 
 
 def test_row_gemm_groups_use_their_own_weights():

@@ -29,9 +29,13 @@ B = 150
 critic_loss_and_grads(c, ct, torch.randn(B, 29, generator=gen).to(dev), torch.rand(B, 8, generator=gen).to(dev),
                       torch.randn(B, 29, generator=gen).to(dev), torch.rand(B, 8, generator=gen).to(dev),
                       torch.rand(B, 1, generator=gen).to(dev), torch.zeros(B, 1).to(dev), 0.99)
-rnd = RNDModel(69).to(dev)
-x = torch.randn(70, 69, generator=gen).to(dev)
-rnd.novelty(x); rnd.loss_and_grads(x); rnd(x)
+critic_loss_and_grads(c, ct, torch.randn(B, 29, generator=gen).to(dev), torch.rand(B, 8, generator=gen).to(dev),
+                      torch.randn(B, 29, generator=gen).to(dev), torch.rand(B, 8, generator=gen).to(dev),
+                      torch.rand(B, 1, generator=gen).to(dev), torch.zeros(B, 1).to(dev), 0.99, precision="bf16")
+for prec in ("fp32", "bf16"):
+    rnd = RNDModel(69, precision=prec).to(dev)
+    x = torch.randn(70, 69, generator=gen).to(dev)
+    rnd.novelty(x); rnd.loss_and_grads(x); rnd(x)
 buf = DiffusionReplayBuffer(1000, 29, 8, device=dev)
 for tid in range(3):
     n = 20 + tid
