@@ -472,18 +472,20 @@ __global__ void q_tc_bce_kernel(const float* __restrict__ lg1, const float* __re
         for (int j = 0; j < 2; ++j) {
             const float* lg = (j == 0 ? lg1 : lg2) + row * 64;
             const float l0 = v0 ? lg[c0] : -INFINITY, l1 = v1 ? lg[c1] : -INFINITY;
+            // hardware exp2 / log2 / reciprocal (2^-22 relative): far inside the 1e-2 bound of this path, and the
+            // kernel is bound by exactly these functions (6 transcendentals + 2 divisions per lane and net)
             const float mx = warp_max(fmaxf(l0, l1));
-            const float e0 = v0 ? expf(l0 - mx) : 0.f, e1 = v1 ? expf(l1 - mx) : 0.f;
-            const float sum = warp_sum(e0 + e1);
-            const float p0 = e0 / sum, p1 = e1 / sum;
+            const float e0 = v0 ? __expf(l0 - mx) : 0.f, e1 = v1 ? __expf(l1 - mx) : 0.f;
+            const float inv = __frcp_rn(warp_sum(e0 + e1));
+            const float p0 = e0 * inv, p1 = e1 * inv;
             float g0 = 0.f, g1 = 0.f;
             if (v0) {
-                lsum -= t0 * fmaxf(logf(p0), -100.f) + (1.f - t0) * fmaxf(log1pf(-p0), -100.f);
-                g0 = inv_count * (p0 - t0) / fmaxf((1.f - p0) * p0, 1e-12f);
+                lsum -= t0 * fmaxf(__logf(p0), -100.f) + (1.f - t0) * fmaxf(__logf(1.f - p0), -100.f);
+                g0 = __fdividef(inv_count * (p0 - t0), fmaxf((1.f - p0) * p0, 1e-12f));
             }
             if (v1) {
-                lsum -= t1 * fmaxf(logf(p1), -100.f) + (1.f - t1) * fmaxf(log1pf(-p1), -100.f);
-                g1 = inv_count * (p1 - t1) / fmaxf((1.f - p1) * p1, 1e-12f);
+                lsum -= t1 * fmaxf(__logf(p1), -100.f) + (1.f - t1) * fmaxf(__logf(1.f - p1), -100.f);
+                g1 = __fdividef(inv_count * (p1 - t1), fmaxf((1.f - p1) * p1, 1e-12f));
             }
             const float dot = warp_sum(p0 * g0 + p1 * g1);
             bf16* dl = (j == 0 ? dl1 : dl2) + row * 64;
