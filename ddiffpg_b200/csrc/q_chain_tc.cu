@@ -319,6 +319,14 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NC1 = a.h1 >> 6, NC2 = a.h2 >> 6, NC3 = a.h3 >> 6;
     const bool backward = a.g_out != nullptr;
+    // B2 in two halves (h1 = 2 x 256 column parts): the part above h2 is complete as soon as the last dz2 chunk has been
+    // multiplied, so its chunks are drained while the part that overlaps the B3 accumulator is still being multiplied.
+    // The action-gradient accumulator (Ba) then lives in drained columns of the upper part, clear of the next net's B4
+    // accumulator [h2, h2 + h3).
+    const bool split_b2 = a.nparts1 == 2 && (NC1 & 1) == 0 && a.h2 + a.h3 + 16 <= a.h1 && a.h2 + a.h3 >= a.part1 &&
+                          ((a.h2 + a.h3) & 63) == 0;
+    const int ba_col = split_b2 ? a.h2 + a.h3 : 0;                    // TMEM column of the Ba accumulator
+    const int ba_gate = split_b2 ? (ba_col - a.part1) >> 6 : 0;       // upper-part chunk whose drain frees those columns
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(qb_w_full(bars, i), 1); mbar_init(qb_w_empty(bars, i), 1); }
@@ -394,7 +402,10 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                     for (int c = 0; c < NC2; ++c)
                         for (int p = 0; p < a.nparts1; ++p)
                             if (q_gated(a, p)) load(&maps.bwd[j][2], c * 64, m * a.h1 + p * a.part1, a.part1);
-                    for (int c = 0; c < NC1; ++c) load(&maps.bwd[j][3], c * 64, m * 16, 16);
+                    for (int c = 0; c < NC1; ++c) {
+                        const int cc = split_b2 ? (c + NC1 / 2) % NC1 : c;      // upper-part chunks are drained first
+                        load(&maps.bwd[j][3], cc * 64, m * 16, 16);
+                    }
                 }
             }
             }
@@ -473,6 +484,7 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                             for (int p = 0; p < a.nparts1; ++p)
                                 if (!q_gated(a, p)) mma_w(p * a.part1, ad[c], id_p1, c == 0);
                         }
+                        if (split_b2) acc_done();   // the upper part is complete: its drain starts now
                         lo_wait();                  // the B3 accumulator is fully drained
                         for (int c = 0; c < NC2; ++c) {
                             for (int p = 0; p < a.nparts1; ++p)
@@ -481,8 +493,8 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                         }
                         acc_done();
                     }
-                    lo_wait();                      // columns [0, 64) of the B2 accumulator are drained
-                    stage(NC1, 0, id_16);           // Ba
+                    lo_wait();                      // the columns the Ba accumulator takes are drained
+                    stage(NC1, ba_col, id_16);      // Ba
                 }
             }
         }
@@ -639,12 +651,17 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                 q_drain<false>(e, 0, NC2, nullptr, g2, NC2 - 1);       // B3 -> dz2 (then the low columns are free)
                 QC_TICK(7);
                 e.wait_acc();
+                if (split_b2) {
+                    q_drain<false>(e, a.part1, NC1 / 2, nullptr, g1 + (NC1 / 2) * 4, ba_gate);   // upper part -> dz1 chunks NC1/2..
+                    e.wait_acc();
+                    q_drain<false>(e, 0, NC1 / 2, nullptr, g1, -1);                              // lower part
+                } else
                 q_drain<false>(e, 0, NC1, nullptr, g1, 0);             // B2 -> dz1
                 QC_TICK(8);
                 if (e.ch == 0) {
                     e.wait_acc();
                     uint32_t v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(e.q * 32) << 16), v);
+                    tmem_ld16(tmem_base + ((uint32_t)(e.q * 32) << 16) + ba_col, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; ++i) da[i] += __uint_as_float(v[i]);
