@@ -413,9 +413,10 @@ def setup_critic(cx, rows):
         loss_h[0:1].copy_(loss.reshape(1), non_blocking=True)
         loss_h[1:2].copy_(gn.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
-    # launches of this repo's kernels per update at the tensor path: target chain + projection + prep/colmap + 8 forward
-    # GEMMs + BCE + 2 x (4 dW + 3 dX) + 2 packs of 2 nets; the optimizer tail is torch's
-    return {"step": step, "e2e": e2e_step, "launches": 30 if args.precision == "bf16" else 14,
+    # launches of this repo's kernels per update.  Tensor path: 2 packs x (biases + 2 nets) = 6, target pass (prep, chain,
+    # projection) = 3, prep + column map = 2, 8 forward GEMMs, BCE, 2 x (4 dW + 3 dX) = 14: 34.  FMA path: 2 packs x 25,
+    # target tile kernel + projection, tile kernel, 8 dW: 61.  The optimizer tail is torch's.
+    return {"step": step, "e2e": e2e_step, "launches": 34 if args.precision == "bf16" else 61,
             "h2d": sum(t.numel() for t in host) * 4, "d2h": 8, "params": params, "keep": (critic, target, opt, devt)}
 
 
