@@ -1,8 +1,9 @@
 """Worker of tests/test_dist_gpu.py: one rank of a data-parallel FusedActorTrainer run (launched by torchrun, NCCL).
 Checks, on the real kernels: (1) all-reduced shard gradients == gradient of the gathered batch, (2) the sharded
 trainer walks the trajectory of a single-process trainer on the full batch, (3) replicas stay bit-identical,
-(4) CUDA-graph replay with the captured, overlapped all-reduce == eager steps, (5) the process group tears down with the
-trainer closed.  Exit code 0 = all checks passed on this rank."""
+(4) CUDA-graph replay with the captured, overlapped all-reduce == eager steps, (5) the critic update's data-parallel form
+(update_critic(process_group=...)) == the single-process update on the gathered batch, replicas identical, (6) the process
+group tears down with the trainer closed.  Exit code 0 = all checks passed on this rank."""
 import os
 import sys
 
@@ -12,7 +13,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import port                                   # noqa: E402
-from ddiffpg_b200 import DiffusionPolicy, FusedActorTrainer   # noqa: E402
+from ddiffpg_b200 import DiffusionPolicy, DistributionalDoubleQ, FusedActorTrainer, update_critic   # noqa: E402
 from ddiffpg_b200 import dist as ddist                    # noqa: E402
 
 
@@ -81,9 +82,34 @@ def main():
             assert d.max().item() <= 1e-6, (precision, d.max().item())
         else:
             assert d.max().item() <= 4 * 3e-4 * 1.05 and (d > 1e-4).float().mean().item() <= 1e-3, (precision, d.max().item())
+    # (5) N1: sharded update_critic == update on the full batch (three steps of torch's AdamW on both), replicas identical
+    def critic(params):
+        c = DistributionalDoubleQ(29, 8, v_min=0, v_max=5, num_atoms=51, device="cuda")
+        c.load_state_dict(params)
+        return c.to(dev)
+    gc = torch.Generator().manual_seed(99)
+    cb = [torch.randn(B, 29, generator=gc), torch.rand(B, 8, generator=gc) * 2 - 1, torch.rand(B, 1, generator=gc),
+          torch.randn(B, 29, generator=gc), torch.rand(B, 8, generator=gc) * 2 - 1, (torch.rand(B, 1, generator=gc) < 0.2).float()]
+    cb = [x.to(dev) for x in cb]
+    cmine = [x[lo:hi].contiguous() for x in cb]
+    pc, pt = port.init_critic_params(5), port.init_critic_params(6)
+    for precision, tol in (("fp32", 1e-5), ("bf16", 5e-3)):
+        sh, ref, tgt = critic(pc), critic(pc), critic(pt).requires_grad_(False)
+        sh.train_precision = ref.train_precision = precision
+        o_sh, o_ref = torch.optim.AdamW(sh.parameters(), lr=5e-4), torch.optim.AdamW(ref.parameters(), lr=5e-4)
+        for it in range(3):
+            _, l_sh, n_sh = update_critic(sh, tgt, o_sh, *cmine, gamma_n=0.97, process_group=dist.group.WORLD)
+            _, l_ref, n_ref = update_critic(ref, tgt, o_ref, *cb, gamma_n=0.97)
+            assert abs(l_sh - l_ref) <= 10 * tol * abs(l_ref), (precision, it, l_sh, l_ref)
+            assert abs(n_sh / n_ref - 1) <= 10 * tol, (precision, it, n_sh, n_ref)
+        flat = torch.cat([q.detach().reshape(-1) for q in sh.parameters()]).double()
+        mine_sum = torch.stack([flat.sum(), flat.abs().sum()])
+        allc = [torch.zeros_like(mine_sum) for _ in range(world)]
+        dist.all_gather(allc, mine_sum)
+        assert all(torch.equal(allc[0], c) for c in allc), f"critic {precision}: replicas diverged"
     torch.cuda.synchronize()
     dist.barrier()
-    dist.destroy_process_group()                          # (5)
+    dist.destroy_process_group()                          # (6)
     print(f"rank {rank}: ok", flush=True)
 
 
