@@ -141,7 +141,7 @@ def workload_config(args, workload, rows):
                         "ascent": "mode-conditioned double-Q action ascent (BASELINE configs[2])",
                         "train": "denoiser eps-loss fwd+bwd + gradient all-reduce + clip/AdamW (BASELINE configs[3])",
                         "critic": "critic update of one mode: target heads, C51 projection, BCE, backward, gradient "
-                                  "all-reduce, clip + AdamW (SURVEY 8f row N1)"}[workload],
+                                  "all-reduce, clip + AdamW on the flat vector, one CUDA graph (SURVEY 8f row N1)"}[workload],
            "rows_per_gpu": rows, "S": S, "A": A, "T": args.T, "trunk": [args.width, args.width // 2, args.width // 4],
            "precision_path": args.precision, "l2": "flushed between timed steps (256 MiB write, untimed)",
            "cpu_arm_rows_per_step": CPU_SAMPLE_ROWS[workload]}
@@ -384,17 +384,18 @@ def setup_train(cx, rows):
 
 
 def setup_critic(cx, rows):
-    """N1: update_critic for one mode's critic -- fused target / loss / backward (ddp_q_critic_loss_fwd_bwd), the flat
-    gradient averaged over the ranks (one all-reduce, as in H3), then torch's own clip_grad_norm_ + AdamW step."""
+    """N1: update_critic for one mode's critic as FusedCriticTrainer runs it -- fused target / loss / backward
+    (ddp_q_critic_loss_fwd_bwd), the flat gradient averaged over the ranks (one all-reduce), clip + AdamW on the flat
+    parameter vector (ddp_clip_adamw_step_dev), the whole update replayed as one CUDA graph.  `--no-graph`: the same with
+    eager launches; `--torch-tail`: update_critic with torch's own clip_grad_norm_ + AdamW instead."""
     torch, args, dev = cx.torch, cx.args, cx.dev
-    from ddiffpg_b200 import DistributionalDoubleQ, update_critic
+    from ddiffpg_b200 import DistributionalDoubleQ, FusedCriticTrainer, update_critic
     torch.manual_seed(0)
     critic = DistributionalDoubleQ(O, A, v_min=0, v_max=5, num_atoms=Q_ATOMS, device="cuda").to(dev)
     params = {k: v.clone().cpu() for k, v in critic.state_dict().items()}
     torch.manual_seed(1)
     target = DistributionalDoubleQ(O, A, v_min=0, v_max=5, num_atoms=Q_ATOMS, device="cuda").to(dev).requires_grad_(False)
     critic.train_precision = args.precision
-    opt = torch.optim.AdamW(critic.parameters(), lr=5e-4)
     host = [torch.randn(rows, O, generator=cx.gen), torch.rand(rows, A, generator=cx.gen) * 2 - 1,
             torch.rand(rows, 1, generator=cx.gen), torch.randn(rows, O, generator=cx.gen),
             torch.rand(rows, A, generator=cx.gen) * 2 - 1, (torch.rand(rows, 1, generator=cx.gen) < 0.2).float()]
@@ -402,22 +403,34 @@ def setup_critic(cx, rows):
     devt = [t.to(dev) for t in host]
     loss_h = torch.empty(2).pin_memory()
     group = cx.dist.group.WORLD if cx.world > 1 else None
+    trainer = None
+    if args.torch_tail:
+        opt = torch.optim.AdamW(critic.parameters(), lr=5e-4)
+        run = lambda batch: update_critic(critic, target, opt, *batch, gamma_n=0.97, max_grad_norm=1.0, process_group=group,
+                                          sync=False)[1:]
+    else:
+        trainer = FusedCriticTrainer(critic, target, lr=5e-4, process_group=group if group is not None else False,
+                                     graph=not args.no_graph)
+        run = lambda batch: trainer.step(*batch, gamma_n=0.97)
 
     def step():
-        update_critic(critic, target, opt, *devt, gamma_n=0.97, max_grad_norm=1.0, process_group=group, sync=False)
+        run(devt)
 
     def e2e_step():
         up = [t.to(dev, non_blocking=True) for t in host]
-        _, loss, gn = update_critic(critic, target, opt, *up, gamma_n=0.97, max_grad_norm=1.0, process_group=group,
-                                    sync=False)
+        loss, gn = run(up)
         loss_h[0:1].copy_(loss.reshape(1), non_blocking=True)
         loss_h[1:2].copy_(gn.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
     # launches of this repo's kernels per update.  Tensor path: 2 packs x (biases + 2 nets) = 6, target pass (prep, chain,
-    # projection) = 3, prep + column map = 2, 8 forward GEMMs, BCE, 2 x (4 dW + 3 dX) = 14: 34.  FMA path: 2 packs x 25,
-    # target tile kernel + projection, tile kernel, 8 dW: 61.  The optimizer tail is torch's.
-    return {"step": step, "e2e": e2e_step, "launches": 34 if args.precision == "bf16" else 61,
-            "h2d": sum(t.numel() for t in host) * 4, "d2h": 8, "params": params, "keep": (critic, target, opt, devt)}
+    # projection) = 3, prep + column map = 2, 8 forward GEMMs, BCE, 2 x (4 dW + 3 dX) = 14: 34 (+ norm, scalars, clip/AdamW
+    # = 37 with the fused tail).  FMA path: 2 packs x 25, target tile kernel + projection, tile kernel, 8 dW: 61 (64).
+    base = 34 if args.precision == "bf16" else 61
+    leg = {"step": step, "e2e": e2e_step, "launches": base if args.torch_tail else base + 3,
+           "h2d": sum(t.numel() for t in host) * 4, "d2h": 8, "params": params, "keep": (critic, target, devt)}
+    if trainer is not None:
+        leg["trainer"] = trainer
+    return leg
 
 
 SETUP = {"sample": setup_sample, "ascent": setup_ascent, "train": setup_train, "critic": setup_critic}
@@ -620,6 +633,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-buckets", type=int, default=None, choices=[1, 2, 4],
                     help="train workload under torchrun: gradient all-reduces per step (default: by world size)")
+    ap.add_argument("--torch-tail", action="store_true",
+                    help="critic workload: update_critic with torch's own clip_grad_norm_ + AdamW instead of FusedCriticTrainer")
     ap.add_argument("--no-graph", action="store_true", help="train workload: eager launches instead of the CUDA graph")
     args = ap.parse_args()
     quiet_stdout()

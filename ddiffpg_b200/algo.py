@@ -120,23 +120,23 @@ def update_actor(actor, actor_optimizer, obs, target_action, max_grad_norm=1.0, 
     return actor_loss.item(), grad_norm.item()
 
 
-def critic_loss_and_grads(critic, critic_target, obs, action, next_obs, next_actions, reward, done, gamma_n,
-                          precision=None):
-    """Loss and flat gradient (state_dict order) of the reference's critic objective (ddiffpg.py:325-349) for one
-    critic: target = min of the two C51-projected target heads, loss = BCE(Q1, target) + BCE(Q2, target).
-    ``precision``: "fp32" (FMA kernels, 1e-4 parity) or "bf16" (tcgen05 GEMMs, 1e-2 parity); default
-    ``critic.train_precision``."""
-    precision = precision or getattr(critic, "train_precision", "fp32")
-    def cache_for(c):       # keep the update's pack apart from an inference pack of another precision
-        if getattr(c, "precision", "fp32") == precision:
-            return c._cache
-        name = "_cache_" + precision
-        if not hasattr(c, name):
-            setattr(c, name, _PackCache())
-        return getattr(c, name)
-    packed, shape, prec = pack_critics([critic], cache_for(critic), precision)
+def _critic_pack_cache(c, precision):
+    """Pack cache of `c` for `precision`: the update's pack is kept apart from an inference pack of another precision."""
+    if getattr(c, "precision", "fp32") == precision:
+        return c._cache
+    name = "_cache_" + precision
+    if not hasattr(c, name):
+        setattr(c, name, _PackCache())
+    return getattr(c, name)
+
+
+def _critic_loss_into(critic, critic_target, obs, action, next_obs, next_actions, reward, done, gamma_n, precision, loss,
+                      grads, ws_holder):
+    """The C-ABI call behind ``critic_loss_and_grads``: ``loss`` (1 float, zeroed here) and ``grads`` (flat) are written
+    in place; ``ws_holder`` is a dict that keeps the kernel workspace alive (a captured graph holds pointers into it)."""
+    packed, shape, prec = pack_critics([critic], _critic_pack_cache(critic, precision), precision)
     # the target critic is written through param.data by soft_update (ddiffpg.py:266): always re-packed (see _PackCache)
-    packed_t, _, _ = pack_critics([critic_target], cache_for(critic_target), precision, force=True)
+    packed_t, _, _ = pack_critics([critic_target], _critic_pack_cache(critic_target, precision), precision, force=True)
     dev = packed.device
     f = lambda x: x.detach().to(device=dev, dtype=torch.float32).contiguous()
     obs, action, next_obs, next_actions = f(obs), f(action), f(next_obs), f(next_actions)
@@ -144,17 +144,37 @@ def critic_loss_and_grads(critic, critic_target, obs, action, next_obs, next_act
     B = obs.shape[0]
     if reward.numel() != B or done.numel() != B:
         raise ValueError("reward and done must have one entry per row")
-    n = lib().ddp_q_grad_count(shape)
-    grads = torch.empty(n, device=dev, dtype=torch.float32)
-    loss = torch.zeros((), device=dev, dtype=torch.float32)
+    if grads.numel() != lib().ddp_q_grad_count(shape):
+        raise ValueError("gradient buffer does not match the critic")
+    loss.zero_()
     with torch.cuda.device(dev):
         ws_bytes = lib().ddp_q_critic_train_workspace_bytes(shape, B, prec)
-        ws = _workspace("q_train", ws_bytes, dev)
+        if ws_holder.get("ws") is None or ws_holder["ws"].numel() < ws_bytes or ws_holder["ws"].device != dev:
+            ws_holder["ws"] = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=dev)
+        ws = ws_holder["ws"]
         check(lib().ddp_q_critic_loss_fwd_bwd(shape, ptr(packed), ptr(packed_t), ptr(obs), ptr(action), ptr(next_obs),
                                               ptr(next_actions), ptr(reward), ptr(done), float(gamma_n), ptr(loss),
                                               ptr(grads), B, prec, ptr(ws), ws_bytes, stream_ptr()),
               "ddp_q_critic_loss_fwd_bwd")
-    return loss, grads
+
+
+_CRITIC_WS = {}
+
+
+def critic_loss_and_grads(critic, critic_target, obs, action, next_obs, next_actions, reward, done, gamma_n,
+                          precision=None):
+    """Loss and flat gradient (state_dict order) of the reference's critic objective (ddiffpg.py:325-349) for one
+    critic: target = min of the two C51-projected target heads, loss = BCE(Q1, target) + BCE(Q2, target).
+    ``precision``: "fp32" (FMA kernels, 1e-4 parity) or "bf16" (tcgen05 GEMMs, 1e-2 parity); default
+    ``critic.train_precision``."""
+    precision = precision or getattr(critic, "train_precision", "fp32")
+    dev = next(critic.parameters()).device
+    n = sum(p.numel() for p in critic.parameters())
+    grads = torch.empty(n, device=dev, dtype=torch.float32)
+    loss = torch.zeros(1, device=dev, dtype=torch.float32)
+    _critic_loss_into(critic, critic_target, obs, action, next_obs, next_actions, reward, done, gamma_n, precision, loss,
+                      grads, _CRITIC_WS.setdefault(str(dev), {}))
+    return loss[0], grads
 
 
 def update_critic(critic, critic_target, critic_optimizer, obs, action, reward, next_obs, next_actions, done,
@@ -414,6 +434,104 @@ class FusedActorTrainer:
         ent["graph"].replay()
         self.step_count += 1
         self.actor.mark_dirty()
+        return ent["loss"].clone(), ent["norm"].clone()
+
+
+class FusedCriticTrainer:
+    """Whole ``update_critic`` for one critic on the device: fused target / loss / backward (one C-ABI call), the
+    data-parallel gradient average, then clip + AdamW on a flat parameter vector (``ddp_clip_adamw_step_dev``) instead
+    of ``clip_grad_norm_`` + ``torch.optim.AdamW.step`` (ddiffpg.py:322-351, ac_base.py:83-92; hyper-parameters default
+    to the reference's ``AdamW(critic.parameters(), critic_lr)`` and ``max_grad_norm`` 1.0).  The critic's parameters
+    are re-pointed at slices of one flat fp32 buffer (state_dict keys, shapes and values unchanged).  ``graph=True``
+    captures the whole update once per batch shape into a CUDA graph -- the launch-bound regime of the reference's
+    4 096-row updates."""
+
+    def __init__(self, critic, critic_target, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0,
+                 process_group=None, precision=None, graph=False):
+        self.critic, self.target = critic, critic_target
+        self.precision = precision or getattr(critic, "train_precision", "fp32")
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.max_grad_norm = float("inf") if max_grad_norm is None else max_grad_norm
+        self.group, self.use_graph, self._graphs = process_group, graph, {}
+        params = list(critic.parameters())
+        dev = params[0].device
+        n = sum(p.numel() for p in params)
+        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        off = 0
+        for p in params:
+            self.flat[off:off + p.numel()].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        self._norm = torch.zeros(1, device=dev)
+        self._scratch = torch.zeros(640, device=dev)          # DDP_ADAMW_SCRATCH_FLOATS
+        self._step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.step_count = 0
+        critic.mark_dirty()
+
+    def world_size(self):
+        if self.group is False:
+            return 1
+        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return torch.distributed.get_world_size(self.group)
+        return 1
+
+    def close(self):
+        """Release the captured graphs (they hold the collective) before ``destroy_process_group()``."""
+        torch.cuda.synchronize(self.flat.device)
+        self._graphs.clear()
+        torch.cuda.synchronize(self.flat.device)
+
+    def _body(self, batch, gamma_n, holder):
+        n = self.flat.numel()
+        dev = self.flat.device
+        if holder.get("gbuf") is None:
+            holder["gbuf"] = torch.zeros(n + 4, device=dev, dtype=torch.float32)        # [gradient | loss | pad]
+        gbuf = holder["gbuf"]
+        self.critic.mark_dirty()          # the flat vector is written by raw pointer: the weight pack is redone every step
+        obs, action, reward, next_obs, next_actions, done = batch
+        _critic_loss_into(self.critic, self.target, obs, action, next_obs, next_actions, reward, done, gamma_n,
+                          self.precision, gbuf[n:n + 1], gbuf[:n], holder)
+        world = self.world_size()
+        if world > 1:
+            torch.distributed.all_reduce(gbuf[:n + 1], group=None if self.group in (None, False) else self.group)
+            gbuf[:n + 1].mul_(1.0 / world)
+        self.step_count += 1
+        with torch.cuda.device(dev):
+            check(lib().ddp_clip_adamw_step_dev(ptr(self.flat), ptr(gbuf), ptr(self.exp_avg), ptr(self.exp_avg_sq), n,
+                                                ptr(self._step_dev), self.lr, self.betas[0], self.betas[1], self.eps,
+                                                self.weight_decay, self.max_grad_norm, ptr(self._norm),
+                                                ptr(self._scratch), stream_ptr()), "ddp_clip_adamw_step_dev")
+        self.critic.mark_dirty()
+        return gbuf[n], self._norm[0]
+
+    def step(self, obs, action, reward, next_obs, next_actions, done, gamma_n=0.99):
+        """One update (argument order of ``update_critic``); returns (loss, pre-clip grad norm) as 0-dim device tensors."""
+        batch = (obs, action, reward, next_obs, next_actions, done)
+        if not self.use_graph:
+            loss, norm = self._body(batch, gamma_n, self.__dict__.setdefault("_eager", {}))
+            return loss.clone(), norm.clone()
+        dev = self.flat.device
+        key = (tuple(tuple(t.shape) for t in batch), float(gamma_n))
+        ent = self._graphs.get(key)
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32)
+        if ent is None:       # first step of this shape runs eagerly (sizes workspaces); the graph's static inputs are made here
+            ent = {"batch": tuple(f32(t).clone() for t in batch), "graph": None}
+            self._graphs[key] = ent
+            loss, norm = self._body(ent["batch"], gamma_n, ent)
+            return loss.clone(), norm.clone()
+        for dst, src in zip(ent["batch"], batch):
+            dst.copy_(src)
+        if ent["graph"] is None:
+            g = torch.cuda.CUDAGraph()
+            count = self.step_count
+            with torch.cuda.graph(g):
+                ent["loss"], ent["norm"] = self._body(ent["batch"], gamma_n, ent)
+            self.step_count = count
+            ent["graph"] = g
+        ent["graph"].replay()
+        self.step_count += 1
+        self.critic.mark_dirty()
         return ent["loss"].clone(), ent["norm"].clone()
 
 
