@@ -13,7 +13,8 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import port                                   # noqa: E402
-from ddiffpg_b200 import DiffusionPolicy, DistributionalDoubleQ, FusedActorTrainer, update_critic   # noqa: E402
+from ddiffpg_b200 import (DiffusionPolicy, DistributionalDoubleQ, FusedActorTrainer, FusedCriticTrainer,   # noqa: E402
+                          update_critic)
 from ddiffpg_b200 import dist as ddist                    # noqa: E402
 
 
@@ -107,6 +108,20 @@ def main():
         allc = [torch.zeros_like(mine_sum) for _ in range(world)]
         dist.all_gather(allc, mine_sum)
         assert all(torch.equal(allc[0], c) for c in allc), f"critic {precision}: replicas diverged"
+        # the fused form (flat-vector clip + AdamW, graph-captured all-reduce): sharded == gathered batch, replicas identical
+        ftr = FusedCriticTrainer(critic(pc), tgt, lr=5e-4, precision=precision, graph=True)
+        fref = FusedCriticTrainer(critic(pc), tgt, lr=5e-4, precision=precision, graph=False, process_group=False)
+        for it in range(4):
+            l_f, n_f = ftr.step(*cmine, gamma_n=0.97)
+            l_r, n_r = fref.step(*cb, gamma_n=0.97)
+            assert abs(l_f.item() - l_r.item()) <= 10 * tol * abs(l_r.item()), (precision, it, l_f.item(), l_r.item())
+            assert abs(n_f.item() / n_r.item() - 1) <= 10 * tol, (precision, it, n_f.item(), n_r.item())
+        mine_sum = torch.stack([ftr.flat.double().sum(), ftr.flat.double().abs().sum()])
+        allc = [torch.zeros_like(mine_sum) for _ in range(world)]
+        dist.all_gather(allc, mine_sum)
+        assert all(torch.equal(allc[0], c) for c in allc), f"fused critic {precision}: replicas diverged"
+        ftr.close()
+        fref.close()
     torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()                          # (6)
