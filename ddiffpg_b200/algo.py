@@ -437,23 +437,19 @@ class FusedActorTrainer:
         return ent["loss"].clone(), ent["norm"].clone()
 
 
-class FusedCriticTrainer:
-    """Whole ``update_critic`` for one critic on the device: fused target / loss / backward (one C-ABI call), the
-    data-parallel gradient average, then clip + AdamW on a flat parameter vector (``ddp_clip_adamw_step_dev``) instead
-    of ``clip_grad_norm_`` + ``torch.optim.AdamW.step`` (ddiffpg.py:322-351, ac_base.py:83-92; hyper-parameters default
-    to the reference's ``AdamW(critic.parameters(), critic_lr)`` and ``max_grad_norm`` 1.0).  The critic's parameters
-    are re-pointed at slices of one flat fp32 buffer (state_dict keys, shapes and values unchanged).  ``graph=True``
-    captures the whole update once per batch shape into a CUDA graph -- the launch-bound regime of the reference's
-    4 096-row updates."""
+class _FlatTrainer:
+    """Shared machinery of the fused trainers of the callers' networks (critic, RND predictor): the parameters re-pointed
+    at slices of one flat fp32 buffer (state_dict keys, shapes and values unchanged), a loss / flat-gradient call that
+    writes into a persistent ``[gradient | loss]`` buffer, the data-parallel average (one all-reduce, the loss in the same
+    buffer), clip + AdamW on the flat vector (``ddp_clip_adamw_step_dev``: the step count lives on the device), and the
+    whole update replayed as one CUDA graph per batch shape (``graph=True``).  Subclasses provide ``_loss_into`` and
+    ``_dirty``."""
 
-    def __init__(self, critic, critic_target, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0,
-                 process_group=None, precision=None, graph=False):
-        self.critic, self.target = critic, critic_target
-        self.precision = precision or getattr(critic, "train_precision", "fp32")
+    def __init__(self, params, lr, betas, eps, weight_decay, max_grad_norm, process_group, graph):
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.max_grad_norm = float("inf") if max_grad_norm is None else max_grad_norm
         self.group, self.use_graph, self._graphs = process_group, graph, {}
-        params = list(critic.parameters())
+        params = list(params)
         dev = params[0].device
         n = sum(p.numel() for p in params)
         self.flat = torch.empty(n, device=dev, dtype=torch.float32)
@@ -467,7 +463,7 @@ class FusedCriticTrainer:
         self._scratch = torch.zeros(640, device=dev)          # DDP_ADAMW_SCRATCH_FLOATS
         self._step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         self.step_count = 0
-        critic.mark_dirty()
+        self._dirty()
 
     def world_size(self):
         if self.group is False:
@@ -482,16 +478,14 @@ class FusedCriticTrainer:
         self._graphs.clear()
         torch.cuda.synchronize(self.flat.device)
 
-    def _body(self, batch, gamma_n, holder):
+    def _body(self, batch, extra, holder):
         n = self.flat.numel()
         dev = self.flat.device
         if holder.get("gbuf") is None:
             holder["gbuf"] = torch.zeros(n + 4, device=dev, dtype=torch.float32)        # [gradient | loss | pad]
         gbuf = holder["gbuf"]
-        self.critic.mark_dirty()          # the flat vector is written by raw pointer: the weight pack is redone every step
-        obs, action, reward, next_obs, next_actions, done = batch
-        _critic_loss_into(self.critic, self.target, obs, action, next_obs, next_actions, reward, done, gamma_n,
-                          self.precision, gbuf[n:n + 1], gbuf[:n], holder)
+        self._dirty()                     # the flat vector is written by raw pointer: the weight pack is redone every step
+        self._loss_into(batch, extra, gbuf[n:n + 1], gbuf[:n], holder)
         world = self.world_size()
         if world > 1:
             torch.distributed.all_reduce(gbuf[:n + 1], group=None if self.group in (None, False) else self.group)
@@ -502,23 +496,22 @@ class FusedCriticTrainer:
                                                 ptr(self._step_dev), self.lr, self.betas[0], self.betas[1], self.eps,
                                                 self.weight_decay, self.max_grad_norm, ptr(self._norm),
                                                 ptr(self._scratch), stream_ptr()), "ddp_clip_adamw_step_dev")
-        self.critic.mark_dirty()
+        self._dirty()
         return gbuf[n], self._norm[0]
 
-    def step(self, obs, action, reward, next_obs, next_actions, done, gamma_n=0.99):
-        """One update (argument order of ``update_critic``); returns (loss, pre-clip grad norm) as 0-dim device tensors."""
-        batch = (obs, action, reward, next_obs, next_actions, done)
+    def _run(self, batch, extra):
+        """(loss, pre-clip grad norm) as 0-dim device tensors; ``extra``: hashable call constants (part of the graph key)."""
         if not self.use_graph:
-            loss, norm = self._body(batch, gamma_n, self.__dict__.setdefault("_eager", {}))
+            loss, norm = self._body(batch, extra, self.__dict__.setdefault("_eager", {}))
             return loss.clone(), norm.clone()
         dev = self.flat.device
-        key = (tuple(tuple(t.shape) for t in batch), float(gamma_n))
+        key = (tuple(tuple(t.shape) for t in batch), extra)
         ent = self._graphs.get(key)
         f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32)
         if ent is None:       # first step of this shape runs eagerly (sizes workspaces); the graph's static inputs are made here
             ent = {"batch": tuple(f32(t).clone() for t in batch), "graph": None}
             self._graphs[key] = ent
-            loss, norm = self._body(ent["batch"], gamma_n, ent)
+            loss, norm = self._body(ent["batch"], extra, ent)
             return loss.clone(), norm.clone()
         for dst, src in zip(ent["batch"], batch):
             dst.copy_(src)
@@ -526,13 +519,59 @@ class FusedCriticTrainer:
             g = torch.cuda.CUDAGraph()
             count = self.step_count
             with torch.cuda.graph(g):
-                ent["loss"], ent["norm"] = self._body(ent["batch"], gamma_n, ent)
+                ent["loss"], ent["norm"] = self._body(ent["batch"], extra, ent)
             self.step_count = count
             ent["graph"] = g
         ent["graph"].replay()
         self.step_count += 1
-        self.critic.mark_dirty()
+        self._dirty()
         return ent["loss"].clone(), ent["norm"].clone()
+
+
+class FusedCriticTrainer(_FlatTrainer):
+    """Whole ``update_critic`` for one critic on the device: fused target / loss / backward (one C-ABI call), the
+    data-parallel gradient average, then clip + AdamW on a flat parameter vector instead of ``clip_grad_norm_`` +
+    ``torch.optim.AdamW.step`` (ddiffpg.py:322-351, ac_base.py:83-92; hyper-parameters default to the reference's
+    ``AdamW(critic.parameters(), critic_lr)`` and ``max_grad_norm`` 1.0).  ``graph=True`` captures the whole update once per
+    batch shape into a CUDA graph -- the launch-bound regime of the reference's 4 096-row updates."""
+
+    def __init__(self, critic, critic_target, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0,
+                 process_group=None, precision=None, graph=False):
+        self.critic, self.target = critic, critic_target
+        self.precision = precision or getattr(critic, "train_precision", "fp32")
+        super().__init__(critic.parameters(), lr, betas, eps, weight_decay, max_grad_norm, process_group, graph)
+
+    def _dirty(self):
+        self.critic.mark_dirty()
+
+    def _loss_into(self, batch, gamma_n, loss, grads, holder):
+        obs, action, reward, next_obs, next_actions, done = batch
+        _critic_loss_into(self.critic, self.target, obs, action, next_obs, next_actions, reward, done, gamma_n,
+                          self.precision, loss, grads, holder)
+
+    def step(self, obs, action, reward, next_obs, next_actions, done, gamma_n=0.99):
+        """One update (argument order of ``update_critic``); returns (loss, pre-clip grad norm) as 0-dim device tensors."""
+        return self._run((obs, action, reward, next_obs, next_actions, done), float(gamma_n))
+
+
+class FusedRNDTrainer(_FlatTrainer):
+    """``IntrinsicM.update`` (utils/intrinsic.py:67-83) on the device: mse loss + predictor backward (one C-ABI call),
+    clip at 1.0 + AdamW(lr 1e-4) on the flat predictor vector, optionally one CUDA graph per batch shape."""
+
+    def __init__(self, rnd_model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0,
+                 process_group=False, graph=False):
+        self.model = rnd_model
+        super().__init__(rnd_model.predictor.parameters(), lr, betas, eps, weight_decay, max_grad_norm, process_group, graph)
+
+    def _dirty(self):
+        self.model.mark_dirty()
+
+    def _loss_into(self, batch, extra, loss, grads, holder):
+        self.model.loss_and_grads_into(batch[0], loss, grads)
+
+    def step(self, x):
+        """One predictor update on the (already encoded) states ``x``; returns (loss, pre-clip grad norm)."""
+        return self._run((x,), None)
 
 
 class HotPathMixin:

@@ -100,19 +100,28 @@ class RNDModel(nn.Module):
     def novelty(self, state):
         return self.features(state, want_features=False)[0]
 
-    def loss_and_grads(self, state):
-        """mse_loss(predictor(x), target(x)) and its flat gradient w.r.t. the predictor parameters."""
+    def loss_and_grads_into(self, state, loss, grads):
+        """mse_loss(predictor(x), target(x)) into ``loss`` (1 float, zeroed here) and its flat gradient w.r.t. the predictor
+        parameters into ``grads``, both written in place (persistent buffers of a fused trainer / captured graph)."""
         packed, shape, prec = self._packed()
         x = self._x(state, packed.device)
         B = x.shape[0]
-        n = lib().ddp_rnd_grad_count(shape)
-        grads = torch.empty(n, device=x.device)
-        loss = torch.zeros((), device=x.device)
+        if grads.numel() != lib().ddp_rnd_grad_count(shape):
+            raise ValueError("gradient buffer does not match the predictor")
+        loss.zero_()
         with torch.cuda.device(x.device):
             ws, ws_bytes = self._workspace(shape, B, prec, x.device)
             check(lib().ddp_rnd_loss_fwd_bwd_p(shape, ptr(packed), ptr(x), ptr(loss), ptr(grads), None, B, prec, ptr(ws),
                                                ws_bytes, stream_ptr()), "ddp_rnd_loss_fwd_bwd_p")
-        return loss, grads
+
+    def loss_and_grads(self, state):
+        """mse_loss(predictor(x), target(x)) and its flat gradient w.r.t. the predictor parameters."""
+        dev = next(self.parameters()).device
+        n = sum(p.numel() for p in self.predictor.parameters())
+        grads = torch.empty(n, device=dev)
+        loss = torch.zeros(1, device=dev)
+        self.loss_and_grads_into(state, loss, grads)
+        return loss[0], grads
 
 
 class IntrinsicKernels:
@@ -136,9 +145,20 @@ class IntrinsicKernels:
     def get_novelty(self, obs):
         return self.rnd_model.novelty(obs)
 
+    def enable_fused_update(self, graph=True):
+        """Route ``update`` through ``FusedRNDTrainer`` (flat-vector clip + AdamW on the device, one CUDA graph per batch
+        shape) instead of ``rnd_optimizer``; same hyper-parameters (AdamW 1e-4, clip 1.0)."""
+        from .algo import FusedRNDTrainer
+        self.rnd_trainer = FusedRNDTrainer(self.rnd_model, lr=1e-4, graph=graph)
+        return self.rnd_trainer
+
     def update(self, obs):
         if self.pos_enc:
             obs = self.encode_obs(obs)
+        if getattr(self, "rnd_trainer", None) is not None:
+            dynamic_loss, dynamic_grad_norm = self.rnd_trainer.step(obs)
+            self.update_step += 1
+            return dynamic_loss.item(), dynamic_grad_norm.item()
         dynamic_loss, grads = self.rnd_model.loss_and_grads(obs)
         dynamic_grad_norm = self.optimizer_update(self.rnd_optimizer, (dynamic_loss, grads))
         self.update_step += 1

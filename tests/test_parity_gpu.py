@@ -523,6 +523,37 @@ def test_rnd_matches_reference_fixture():
     assert_close(tf, rt, RTOL, ATOL, "target features")
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_rnd_trainer_matches_reference_optimizer_step(graph):
+    """IntrinsicM.update through FusedRNDTrainer (enable_fused_update): the predictor walks the trajectory of the
+    reference's tail -- clip_grad_norm_(1.0) + torch AdamW(1e-4) on the oracle's gradients -- eager and as a CUDA graph."""
+    p = port.init_rnd_params(74)
+    im = _intrinsic(p)
+    im.enable_fused_update(graph=graph)
+    gen = torch.Generator().manual_seed(31)
+    obs = torch.randn(500, 29, generator=gen)
+    keys = [k for k in port.RND_KEYS if k.startswith("predictor")]
+    ref = {k: v.clone().requires_grad_(k in keys) for k, v in p.items()}
+    ropt = torch.optim.AdamW([ref[k] for k in keys], lr=1e-4)
+    steps = 4
+    for _ in range(steps):
+        loss, gnorm = im.update(_dev(obs))
+        x = port.encode_obs_antmaze(obs)
+        l_ref, g_ref = port.rnd_loss_and_grads({k: v.detach() for k, v in ref.items()}, x)
+        for k in keys:
+            ref[k].grad = g_ref[k].clone()
+        n_ref = torch.nn.utils.clip_grad_norm_([ref[k] for k in keys], 1.0)
+        ropt.step()
+        assert abs(loss - l_ref.item()) <= 2e-5 * max(1.0, abs(l_ref.item()))
+        assert abs(gnorm - n_ref.item()) <= 1e-4 * n_ref.item()
+    for k in keys:
+        d = (dict(im.rnd_model.named_parameters())[k].detach().cpu().double() - ref[k].detach().double()).abs()
+        assert d.max().item() <= steps * 1e-4 * 0.1, (k, d.max().item())
+        assert d.mean().item() < 2e-7, (k, d.mean().item())
+    assert im.update_step == steps
+    im.rnd_trainer.close()
+
+
 @pytest.mark.parametrize("B", [1, 9, 600, 5000])
 def test_rnd_update_vs_oracle_batches(B):
     p = port.init_rnd_params(72, scale=1.3)
