@@ -655,7 +655,7 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant_
 
 }  // namespace
 
-static bool g_row_no_tma_aux = false;       // ddp_debug_row_gemm_direct_aux: A/B switch for the backward epilogue (tests, measurements)
+static bool g_row_no_tma_aux = false;       // ddp_debug_row_gemm_direct_aux: A/B switch for the TMA-staged epilogues (tests, measurements)
 
 int launch_row_gemm(const RowGemm& g, cudaStream_t st) {
     if (g.M <= 0) return DDP_OK;
@@ -740,8 +740,9 @@ int launch_dw_gemm(const DwGemm& g, cudaStream_t st) {
 }  // namespace tcg
 }  // namespace ddp
 
-// Debug entry point (not part of the public header): 1 = backward epilogues with direct row-per-lane global accesses
-// instead of the TMA-staged aux tile.  Process-wide; A/B measurements and tests only.
+// Debug entry point (not part of the public header): 1 = the round-1 epilogues (backward: direct row-per-lane global
+// accesses; ELU forward: per-warp staging + copy-out loop) instead of the TMA-staged ones.  Process-wide; A/B
+// measurements and tests only.
 extern "C" void ddp_debug_row_gemm_direct_aux(int on) { ddp::tcg::g_row_no_tma_aux = on != 0; }
 
 // Debug entry points (not part of the public header) used by tests/test_tc_gemm_gpu.py
