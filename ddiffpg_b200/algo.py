@@ -281,9 +281,10 @@ class FusedActorTrainer:
         return 1
 
     def launches_per_step(self):
-        """Own kernels of one step on the tensor path: re-pack 12, prep 1, fused forward 1, backward row GEMMs 3,
-        dW GEMMs 4, time branch 6 (+ 2 fp32 transposes), norm / clip / AdamW 3."""
-        return 32
+        """Own kernels of one step on the tensor path: re-pack 6 (small jobs, the three T-row layers of the time branch,
+        16-bit operands, training operands), prep 1, fused forward 1, backward row GEMMs 3, dW GEMMs 4, time branch 6
+        (transpose, three T-row weight gradients, two T-row products), norm / scalars / clip + AdamW 3."""
+        return 24
 
     def close(self):
         """Release the captured CUDA graphs (and with them the collectives they hold).  Call before

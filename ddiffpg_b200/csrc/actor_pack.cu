@@ -53,21 +53,27 @@ void fill_schedule(int T, ScheduleTable& tab) {
     }
 }
 
-__global__ void schedule_store_kernel(ScheduleTable tab, int T, float* __restrict__ dst) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < T * kCstStride) dst[i] = tab.v[i / kCstStride][i % kCstStride];
-}
-
-// pe[t][i] = sin(t*f_i) (i < D/2), cos(t*f_{i-D/2}) otherwise, f_i = exp(i * -(ln 1e4/(D/2-1))).
-__global__ void posemb_kernel(int T, int D, float* __restrict__ pe) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= T * D) return;
-    int t = idx / D, i = idx % D, half = D / 2;
-    float c = -(float)(log(10000.0) / (half - 1));
-    int j = i < half ? i : i - half;
-    float f = expf(__fmul_rn((float)j, c));
-    float a = __fmul_rn((float)t, f);
-    pe[idx] = i < half ? sinf(a) : cosf(a);
+// the five small jobs of a pack in one launch: blockIdx.y = b1 | b2 | b3 (zero padded to np3) | scheduler constants | posemb
+__global__ void actor_small_pack_kernel(ScheduleTable tab, int T, int D, const float* __restrict__ b1, int n1,
+                                        float* __restrict__ d1, const float* __restrict__ b2, int n2, float* __restrict__ d2,
+                                        const float* __restrict__ b3, int n3, int np3, float* __restrict__ d3,
+                                        float* __restrict__ cst, float* __restrict__ pe) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    switch (blockIdx.y) {
+    case 0: if (i < n1) d1[i] = b1[i]; break;
+    case 1: if (i < n2) d2[i] = b2[i]; break;
+    case 2: if (i < np3) d3[i] = i < n3 ? b3[i] : 0.f; break;
+    case 3: if (i < T * kCstStride) cst[i] = tab.v[i / kCstStride][i % kCstStride]; break;
+    default:
+        if (i < T * D) {
+            const int t = i / D, k = i % D, half = D / 2;
+            const float c = -(float)(log(10000.0) / (half - 1));
+            const int j = k < half ? k : k - half;
+            const float f = expf(__fmul_rn((float)j, c));
+            const float a = __fmul_rn((float)t, f);
+            pe[i] = k < half ? sinf(a) : cosf(a);
+        }
+    }
 }
 
 // y[t][n] = b[n] + sum_k W[n*ldw + koff + k] * x[t*ldx + k]; optional Mish; one warp per (t, n).
@@ -102,14 +108,18 @@ int pack_actor_fp32(const ActorLayout& L, const float* const p[12], float* out, 
         transpose_pack_kernel<<<blocks((size_t)L.h3 * L.A4), 256, 0, st>>>(p[10], L.h3, 0, L.h3, L.h3, A, L.A4, out + L.wt3);
         copy_pad_kernel<<<blocks((size_t)L.A4 * L.h3), 256, 0, st>>>(p[10], A * L.h3, L.A4 * L.h3, out + L.w3b);
     }
-    copy_pad_kernel<<<blocks(L.h2), 256, 0, st>>>(p[7], L.h2, L.h2, out + L.b1);
-    copy_pad_kernel<<<blocks(L.h3), 256, 0, st>>>(p[9], L.h3, L.h3, out + L.b2);
-    copy_pad_kernel<<<blocks(L.A4), 256, 0, st>>>(p[11], A, L.A4, out + L.b3);
+    // biases, scheduler constants and positional embedding: one launch (block y = job)
     ScheduleTable tab;
     fill_schedule(T, tab);
-    schedule_store_kernel<<<blocks((size_t)T * kCstStride), 256, 0, st>>>(tab, T, out + L.cst);
+    {
+        size_t most = (size_t)T * D;
+        if ((size_t)L.h2 > most) most = L.h2;
+        if ((size_t)T * kCstStride > most) most = (size_t)T * kCstStride;
+        dim3 grid(blocks(most), 5);
+        actor_small_pack_kernel<<<grid, 256, 0, st>>>(tab, T, D, p[7], L.h2, out + L.b1, p[9], L.h3, out + L.b2, p[11], A, L.A4,
+                                                     out + L.b3, out + L.cst, out + L.pe);
+    }
     // time path on the T distinct timesteps
-    posemb_kernel<<<blocks((size_t)T * D), 256, 0, st>>>(T, D, out + L.pe);
     dim3 g1(blocks((size_t)4 * D * 32), T), g2(blocks((size_t)D * 32), T), g3(blocks((size_t)L.h1 * 32), T);
     rows_linear_kernel<<<g1, 256, 0, st>>>(p[0], D, 0, p[1], out + L.pe, D, D, 4 * D, 1, out + L.zmid, out + L.hmid, 4 * D);
     rows_linear_kernel<<<g2, 256, 0, st>>>(p[2], 4 * D, 0, p[3], out + L.hmid, 4 * D, 4 * D, D, 0, nullptr, out + L.temb, D);

@@ -842,22 +842,13 @@ actor_sample_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
 }
 
 // ---------------------------------------------------------------------------------------- packing
-template <bool F16>
-__global__ void f32_to_16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = cvt16<F16>(src[i]);
-}
-
 // Layer-0 B fragments in mma.sync m16n8k16 order.  K order is [x (A<=8, padded to 8) | state (S) | 0 ...].
 // Entry [(c*2+ch)*12 + nt*3 + ks][lane] = {b0, b1}: feature f = c*64 + ch*32 + nt*8 + lane/4,
 // b0 = (k, k+1) with k = ks*16 + 2*(lane%4), b1 = (k+8, k+9).
 template <bool F16>
-__global__ void w0_frag_pack_kernel(const float* __restrict__ W0, int ld0, int D, int S, int A, int h1,
-                                    uint2* __restrict__ out) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int total = (h1 / 32) * 12 * 32;
-    if (idx >= total) return;
-    const int lane = idx & 31, e = idx >> 5;
+__device__ __forceinline__ void w0_frag_pack(size_t idx, const float* __restrict__ W0, int ld0, int D, int S, int A,
+                                             uint2* __restrict__ out) {
+    const int lane = (int)(idx & 31), e = (int)(idx >> 5);
     const int ks = e % 3, nt = (e / 3) % 4, cc = e / 12;           // cc = c*2 + ch
     const int f = cc * 32 + nt * 8 + (lane >> 2);
     auto wk = [&](int k) -> float {                                 // weight of kernel-order input k
@@ -874,13 +865,38 @@ __global__ void w0_frag_pack_kernel(const float* __restrict__ W0, int ld0, int D
 
 // Layer-3 B tiles: [h3/64][16 rows][64] bf16 written as the SWIZZLE_128B shared-memory image.
 template <bool F16>
-__global__ void w3_image_pack_kernel(const float* __restrict__ W3, int A, int h3, uint16_t* __restrict__ out) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int total = (h3 / 64) * 16 * 64;
-    if (idx >= total) return;
-    const int col = idx & 63, r = (idx >> 6) & 15, c = idx >> 10;
+__device__ __forceinline__ void w3_image_pack(size_t idx, const float* __restrict__ W3, int A, int h3, uint16_t* __restrict__ out) {
+    const int col = (int)(idx & 63), r = (int)((idx >> 6) & 15), c = (int)(idx >> 10);
     const float v = r < A ? W3[(size_t)r * h3 + c * 64 + col] : 0.f;
     out[(size_t)c * 1024 + sw128_offset(r, col) / 2] = cvt16<F16>(v);
+}
+
+// Every 16-bit operand of the tensor paths in ONE launch (it used to be four to eight: the pack runs inside every training
+// step, where at the reference's 4 096-row batch a launch costs as much as the work).  Index space: W1 | W2 | layer-0
+// fragments | head image, in bf16; with `sampler` the same four again in fp16.
+struct TcPackJob {
+    const float *W0, *W1, *W2, *W3;
+    uint16_t *w1, *w2, *w3, *w1h, *w2h, *w3h;
+    uint2 *w0, *w0h;
+    size_t n0, n1, n2, n3;
+    int ld0, D, S, A, h3, sampler;
+};
+__global__ void actor_tc_pack_kernel(TcPackJob j) {
+    const size_t per = j.n1 + j.n2 + j.n0 + j.n3;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per * (j.sampler ? 2 : 1)) return;
+    const bool h = i >= per;
+    if (h) i -= per;
+    if (i < j.n1) { if (h) j.w1h[i] = cvt16<true>(j.W1[i]); else j.w1[i] = cvt16<false>(j.W1[i]); return; }
+    i -= j.n1;
+    if (i < j.n2) { if (h) j.w2h[i] = cvt16<true>(j.W2[i]); else j.w2[i] = cvt16<false>(j.W2[i]); return; }
+    i -= j.n2;
+    if (i < j.n0) {
+        if (h) w0_frag_pack<true>(i, j.W0, j.ld0, j.D, j.S, j.A, j.w0h); else w0_frag_pack<false>(i, j.W0, j.ld0, j.D, j.S, j.A, j.w0);
+        return;
+    }
+    i -= j.n0;
+    if (h) w3_image_pack<true>(i, j.W3, j.A, j.h3, j.w3h); else w3_image_pack<false>(i, j.W3, j.A, j.h3, j.w3);
 }
 
 struct TcPacked {      // byte offsets inside the packed buffer (see ActorLayout::tc_*)
@@ -905,21 +921,18 @@ int pack_actor_tc(const ActorLayout& L, const float* const p[12], void* packed, 
     const int ld0 = L.D + L.S + L.A;
     const size_t n0 = (size_t)(L.h1 / 32) * 12 * 32, n1 = (size_t)L.h2 * L.h1, n2 = (size_t)L.h3 * L.h2,
                  n3 = (size_t)(L.h3 / 64) * 1024;
-    // bf16 W1 / W2: read by the sampler and by the training GEMMs; everything else is the sampler's own
-    f32_to_16_kernel<false><<<blocks(n1), 256, 0, st>>>(p[6], (uint16_t*)(base + L.tc_w1), n1);
-    f32_to_16_kernel<false><<<blocks(n2), 256, 0, st>>>(p[8], (uint16_t*)(base + L.tc_w2), n2);
-    if (sampler) {
-        w0_frag_pack_kernel<false><<<blocks(n0), 256, 0, st>>>(p[4], ld0, L.D, L.S, L.A, L.h1, (uint2*)(base + L.tc_w0));
-        w0_frag_pack_kernel<true><<<blocks(n0), 256, 0, st>>>(p[4], ld0, L.D, L.S, L.A, L.h1, (uint2*)(base + L.tc_w0h));
-        f32_to_16_kernel<true><<<blocks(n1), 256, 0, st>>>(p[6], (uint16_t*)(base + L.tc_w1h), n1);
-        f32_to_16_kernel<true><<<blocks(n2), 256, 0, st>>>(p[8], (uint16_t*)(base + L.tc_w2h), n2);
-        w3_image_pack_kernel<false><<<blocks(n3), 256, 0, st>>>(p[10], L.A, L.h3, (uint16_t*)(base + L.tc_w3));
-        w3_image_pack_kernel<true><<<blocks(n3), 256, 0, st>>>(p[10], L.A, L.h3, (uint16_t*)(base + L.tc_w3h));
-    } else if (train) {
-        // the fused training forward (csrc/actor_train_chain_tc.cu) shares the sampler's bf16 layer-0 fragments and head image
-        w0_frag_pack_kernel<false><<<blocks(n0), 256, 0, st>>>(p[4], ld0, L.D, L.S, L.A, L.h1, (uint2*)(base + L.tc_w0));
-        w3_image_pack_kernel<false><<<blocks(n3), 256, 0, st>>>(p[10], L.A, L.h3, (uint16_t*)(base + L.tc_w3));
-    }
+    // bf16 W1 / W2 are read by the sampler and by the training GEMMs, the bf16 layer-0 fragments and head image by the
+    // sampler and by the fused training forward (csrc/actor_train_chain_tc.cu); the fp16 copies are the sampler's own
+    (void)train;
+    TcPackJob j{};
+    j.W0 = p[4]; j.W1 = p[6]; j.W2 = p[8]; j.W3 = p[10];
+    j.w0 = (uint2*)(base + L.tc_w0); j.w0h = (uint2*)(base + L.tc_w0h);
+    j.w1 = (uint16_t*)(base + L.tc_w1); j.w1h = (uint16_t*)(base + L.tc_w1h);
+    j.w2 = (uint16_t*)(base + L.tc_w2); j.w2h = (uint16_t*)(base + L.tc_w2h);
+    j.w3 = (uint16_t*)(base + L.tc_w3); j.w3h = (uint16_t*)(base + L.tc_w3h);
+    j.n0 = n0; j.n1 = n1; j.n2 = n2; j.n3 = n3;
+    j.ld0 = ld0; j.D = L.D; j.S = L.S; j.A = L.A; j.h3 = L.h3; j.sampler = sampler ? 1 : 0;
+    actor_tc_pack_kernel<<<blocks((n0 + n1 + n2 + n3) * (sampler ? 2 : 1)), 256, 0, st>>>(j);
     DDP_LAUNCH_CHECK("actor tensor-core pack kernels");
     return DDP_OK;
 }
