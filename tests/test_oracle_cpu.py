@@ -165,6 +165,23 @@ def test_abi_argument_errors_without_gpu(built_lib):
     qbad = _lib.QShape(29, 8, 51, 5.0, 0.0, 1, 512, 256, 128)
     assert L.ddp_q_packed_bytes(qbad, 0) == 0
     assert L.ddp_q_forward(q, None, None, None, None, None, None, None, None, 0, 0, None, 0, None) == 0
+    # round-2 entry points: the critic update and RND on both precisions (sizes only -- no compute without a GPU)
+    q1 = _lib.QShape(29, 8, 51, 0.0, 5.0, 1, 512, 256, 128)
+    assert L.ddp_q_packed_bytes(q1, 1) > L.ddp_q_packed_bytes(q1, 0)
+    w32, w16 = L.ddp_q_critic_train_workspace_bytes(q1, 4096, 0), L.ddp_q_critic_train_workspace_bytes(q1, 4096, 1)
+    assert w32 > 0 and w16 > 0 and L.ddp_q_critic_train_workspace_bytes(q1, 4096, 7) == 0
+    assert L.ddp_q_critic_loss_fwd_bwd(q, None, None, None, None, None, None, None, None, 0.99, None, None, 8, 1, None, 0,
+                                       None) == -1                  # one critic per call
+    assert L.ddp_q_critic_loss_fwd_bwd(q1, None, None, None, None, None, None, None, None, 0.99, None, None, 8, 1, None, 0,
+                                       None) == -2                  # NULL arguments
+    r = _lib.RndShape(69, 128, 512, 256, 128)
+    assert L.ddp_rnd_packed_bytes_p(r, 0) == L.ddp_rnd_packed_bytes(r) > 0
+    assert L.ddp_rnd_packed_bytes_p(r, 1) > L.ddp_rnd_packed_bytes_p(r, 0)
+    assert L.ddp_rnd_workspace_bytes_p(r, 4096, 1) > 0 and L.ddp_rnd_workspace_bytes_p(r, 4096, 0) == L.ddp_rnd_train_workspace_bytes(r, 4096)
+    assert L.ddp_rnd_packed_bytes_p(_lib.RndShape(300, 128, 512, 256, 128), 1) == 0       # tensor path: D <= 256
+    assert L.ddp_rnd_packed_bytes_p(_lib.RndShape(69, 128, 500, 256, 128), 1) == 0        # ... widths multiples of 64
+    assert L.ddp_rnd_packed_bytes_p(_lib.RndShape(69, 128, 500, 256, 128), 0) > 0         # the FMA path takes them
+    assert L.ddp_rnd_novelty_p(r, None, None, None, None, None, 4, 1, None, 0, None) == -2
 
 
 # ------------------------------------------------------------------ host mirror of the reference surface
