@@ -212,9 +212,16 @@ def update_critic(critic, critic_target, critic_optimizer, obs, action, reward, 
 
 @torch.no_grad()
 def soft_update(target_net, current_net, tau):
-    """``ddiffpg/utils/torch_util.py:9-12`` plus the cache invalidation ``.data`` writes cannot signal."""
-    for tar, cur in zip(target_net.parameters(), current_net.parameters()):
-        tar.data.copy_(cur.data * tau + tar.data * (1.0 - tau))
+    """``ddiffpg/utils/torch_util.py:9-12`` plus the cache invalidation ``.data`` writes cannot signal.  The reference's
+    per-parameter ``tar.data.copy_(cur.data * tau + tar.data * (1.0 - tau))`` (three launches per tensor, 48 per critic) is
+    issued as three multi-tensor launches over all parameters -- the same two products and one sum per element, hence the
+    same bits."""
+    tars = [p.data for p in target_net.parameters()]
+    curs = [p.data for p in current_net.parameters()]
+    if tars:
+        scaled = torch._foreach_mul(curs, tau)
+        torch._foreach_mul_(tars, 1.0 - tau)
+        torch._foreach_add_(tars, scaled)
     if hasattr(target_net, "mark_dirty"):
         target_net.mark_dirty()
 

@@ -91,7 +91,10 @@ class ReplayKernels:
         if rows.is_floating_point() and not bool((rows == rows.round()).all()):
             return torch.where(torch.isin(self.buf_id, ids.to(self.buf_id.dtype)))[0]       # not ids at all: as written
         rows = rows.long()
-        lo, hi = int(min(rows.min().item(), ids.min().item())), int(max(rows.max().item(), ids.max().item()))
+        r_lo, r_hi = torch.aminmax(rows)
+        i_lo, i_hi = torch.aminmax(ids)
+        lo, hi = torch.stack([torch.minimum(r_lo, i_lo), torch.maximum(r_hi, i_hi)]).tolist()        # one host sync
+        lo, hi = int(lo), int(hi)
         if hi - lo > 4 * rows.numel() + 65536:                                              # sparse id space: as written
             return torch.where(torch.isin(self.buf_id, ids.to(self.buf_id.dtype)))[0]
         lut = torch.zeros(hi - lo + 1, dtype=torch.bool, device=dev)

@@ -355,3 +355,17 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["vs_baseline"] is None and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+def test_soft_update_is_bit_identical_to_the_reference_expression():
+    """ddiffpg_b200.soft_update issues three multi-tensor launches instead of three per parameter; the arithmetic per
+    element is the reference's (utils/torch_util.py:9-12): cur * tau + tar * (1 - tau), two products and one sum."""
+    import torch.nn as nn
+    from ddiffpg_b200 import soft_update
+    torch.manual_seed(5)
+    cur = nn.Sequential(nn.Linear(37, 64), nn.ELU(), nn.Linear(64, 51))
+    tar = nn.Sequential(nn.Linear(37, 64), nn.ELU(), nn.Linear(64, 51))
+    want = [c.data * 0.05 + t.data * (1.0 - 0.05) for t, c in zip(tar.parameters(), cur.parameters())]
+    soft_update(tar, cur, 0.05)
+    for got, w in zip(tar.parameters(), want):
+        assert torch.equal(got.data, w)

@@ -71,6 +71,10 @@ def _enc(obs, Lp=10):        # IntrinsicM.encode_obs for AntMaze (utils/intrinsi
         outs += [torch.sin(x * 2.0 ** k), torch.cos(x * 2.0 ** k)]
     return torch.cat(outs + [obs[:, 2:]], dim=1)
 
+from ddiffpg_b200.models import _PackCache
+ascent_cache = _PackCache()
+
+
 def iteration():
     data_list = gb.sample_batch(B)
     obs = torch.cat([d["batch"][0] for d in data_list]); nobs = torch.cat([d["batch"][4] for d in data_list])
@@ -78,7 +82,7 @@ def iteration():
     nov = rnd.novelty(_enc(torch.cat([obs, nobs])))
     r_int = 0.01 * torch.clamp(nov[obs.shape[0]:] - 0.5 * nov[:obs.shape[0]], min=0).unsqueeze(1)
     rewards = reward + r_int
-    prev, states, actions = 0, [], []
+    prev, states = 0, []
     for i, d in enumerate(data_list):
         s, a, ta, _, ns, dn = d["batch"]
         n = s.shape[0]
@@ -88,14 +92,25 @@ def iteration():
         nact = get_tgt_policy_actions(actor, ens)
         d["Q"]["trainer"].step(s, a, r, ns, nact, dn, gamma_n=0.99 ** 3)
         soft_update(d["Q"]["target_Q"], d["Q"]["Q"], 0.05)
-        ta = ta.contiguous()
-        d["Q"]["Q"].requires_grad_(False)
-        q_action_ascent_segments([d["Q"]["Q"]], s, ta, [0, n], iters=20, precision=args.precision)
-        d["Q"]["Q"].requires_grad_(True)
-        if d["indices"] is not None:
-            rb.update_target_action(ta[:d["indices"].shape[0]], d["indices"], i)
-        states.append(es); actions.append(ta)
+        states.append(es)
         prev += n
+    # the ascent of group i only reads critic i: the three reference calls (one per group, after that group's critic update)
+    # are one segmented call here -- same per-group 1/B, clip norm and Adam state
+    critics = [d["Q"]["Q"] for d in data_list]
+    seg = [0]
+    for d in data_list:
+        seg.append(seg[-1] + d["batch"][0].shape[0])
+    ta_all = torch.cat([d["batch"][2] for d in data_list]).contiguous()
+    for c in critics:
+        c.requires_grad_(False)
+    q_action_ascent_segments(critics, obs, ta_all, seg, iters=20, precision=args.precision, cache=ascent_cache)
+    for c in critics:
+        c.requires_grad_(True)
+    ascent_cache.dirty = True                 # the critics change every iteration
+    actions = [ta_all]
+    for i, d in enumerate(data_list):
+        if d["indices"] is not None:
+            rb.update_target_action(ta_all[seg[i]:seg[i] + d["indices"].shape[0]], d["indices"], i)
     actor_tr.step(torch.cat(states), torch.cat(actions))
     rnd_tr.step(_enc(torch.cat([obs, nobs])))
 
