@@ -84,6 +84,20 @@ class ReplayKernels:
         ``torch.where(torch.isin(...))``: one table look-up per stored row (trajectory ids are small non-negative
         integers, diffusion_replay.py:84-118) instead of isin's sort / broadcast compare."""
         dev = self.buf_id.device
+        # the answer only changes when the storage does, and every change of the reference's storage (add_to_buffer,
+        # remove) re-allocates buf_id: cache per id set on (data_ptr, rows)
+        key = (tuple(int(i) for i in cluster_idx), self.buf_id.data_ptr(), self.buf_id.shape[0])
+        cache = self.__dict__.setdefault("_avail_cache", {})
+        hit = cache.get(key)
+        if hit is not None:
+            return hit
+        if len(cache) >= 64:
+            cache.clear()
+        out = self._available_indices(cluster_idx, dev)
+        cache[key] = out
+        return out
+
+    def _available_indices(self, cluster_idx, dev):
         ids = torch.as_tensor(cluster_idx, device=dev).long().reshape(-1)
         if ids.numel() == 0:
             return torch.empty(0, dtype=torch.int64, device=dev)

@@ -113,3 +113,24 @@ def test_trainer_bucket_plan_covers_the_gradient_buffer():
         for g, lo, hi in plan:          # the bucket's event is the one of the last-finished group inside it
             inside = [k for k, (a, b) in enumerate(groups) if a >= lo and b <= hi]
             assert g == max(inside)
+
+
+def test_available_indices_cache_follows_the_storage():
+    """ReplayKernels.available_indices (pure index logic, no kernel): equals torch.where(torch.isin(...)) of
+    simple_replay.py:151, is cached per id set while the storage is unchanged, and recomputed once buf_id is re-allocated
+    (what the reference's add_to_buffer / remove do)."""
+    import torch
+    from ddiffpg_b200.replay import ReplayKernels
+
+    class Store(ReplayKernels):
+        pass
+    s = Store()
+    s.buf_id = torch.tensor([[0.], [1.], [1.], [2.], [5.], [7.]])
+    for ids in ([1, 5], [0], [9], [7, 2, 0], []):
+        ref = torch.where(torch.isin(s.buf_id, torch.tensor(ids, dtype=s.buf_id.dtype)))[0] if ids else torch.empty(0, dtype=torch.int64)
+        assert torch.equal(s.available_indices(ids), ref)
+        assert s.get_buffer_size(ids) == ref.shape[0]
+    first = s.available_indices([1, 5])
+    assert s.available_indices([1, 5]) is first
+    s.buf_id = torch.cat([s.buf_id, torch.tensor([[5.]])])
+    assert s.available_indices([1, 5]).tolist() == [1, 2, 4, 6]
