@@ -21,6 +21,7 @@
 // Activations only ever exist as 16 KB chunks in a 4-slot ring; weights never leave L2/SMEM.
 #include "actor_layout.cuh"
 #include "tc_common.cuh"
+#include "scratch_cache.cuh"
 
 namespace ddp {
 using namespace tc;
@@ -43,6 +44,10 @@ constexpr bool kH2 = DDP_TC_H2 != 0;
 #define DDP_TC_PAIR_PUBLISH 0   // 1: two chunks per proxy fence (measured slower here: it delays the layer-1 MMAs)
 #endif
 constexpr bool kPairPublish = DDP_TC_PAIR_PUBLISH != 0;
+#ifndef DDP_TC_KEEP_PARTIAL
+#define DDP_TC_KEEP_PARTIAL 0   // 1: evict_last L2 policy on the state-partial scratch (scratch_cache.cuh)
+#endif
+constexpr bool kKeepPartial = DDP_TC_KEEP_PARTIAL != 0;
 constexpr int kEpiWarps = 8;                 // two per SM sub-partition (16 spill under the 96-register cap: 1.28 ms)
 constexpr int kColsPerWarp = 32;             // columns of a 64-column chunk owned by one warp
 constexpr int kNT = kColsPerWarp / 8;        // mma.sync n8 tiles per warp in layer 0
@@ -394,8 +399,8 @@ __device__ __forceinline__ void state_partial(const TcArgs& a, const EpiCtx& e) 
                 h[nt][0] = pack_f16x2(acc[0], acc[1]);
                 h[nt][1] = pack_f16x2(acc[2], acc[3]);
             }
-            __stcg(dst + (mt * 2 + 0) * 32, make_uint4(h[0][0], h[0][1], h[1][0], h[1][1]));
-            __stcg(dst + (mt * 2 + 1) * 32, make_uint4(h[2][0], h[2][1], h[3][0], h[3][1]));
+            scratch_st<kKeepPartial>(dst + (mt * 2 + 0) * 32, make_uint4(h[0][0], h[0][1], h[1][0], h[1][1]));
+            scratch_st<kKeepPartial>(dst + (mt * 2 + 1) * 32, make_uint4(h[2][0], h[2][1], h[3][0], h[3][1]));
         }
 #pragma unroll
         for (int nt = 0; nt < kNT; ++nt) { bfr[nt][0] = nxt[nt][0]; bfr[nt][1] = nxt[nt][1]; }
@@ -426,7 +431,7 @@ __device__ __forceinline__ void load_l0_frags(const TcArgs& a, const EpiCtx& e, 
         fr.bias[nt] = __ldg(reinterpret_cast<const float2*>(tb + c * 64 + e.ch * kColsPerWarp + nt * 8 + 2 * e.t4));
     const uint4* ps = pscr_slot(a, e, c);
 #pragma unroll
-    for (int j = 0; j < 2 * MT; ++j) fr.pp[j] = __ldcg(ps + j * 32);
+    for (int j = 0; j < 2 * MT; ++j) fr.pp[j] = scratch_ld<kKeepPartial>(ps + j * 32);
 }
 
 // One denoising step of the epilogue warps (operand format of THIS step = F16 ? fp16 : bf16; H2: the TMEM drains run

@@ -25,6 +25,7 @@
 #include <type_traits>
 #include "q_layout.cuh"
 #include "tc_common.cuh"
+#include "scratch_cache.cuh"
 
 namespace ddp {
 using namespace tc;
@@ -155,6 +156,18 @@ struct QEpi {
     }
 };
 
+// ELU' scratch accesses (scratch_cache.cuh).  DDP_QC_SCRATCH, A/B switch measured in profiles/r02/ab_scratch_policy.txt:
+// bit 0 = evict_last policy on the stores / loads (default: 185 -> 26 MB of DRAM writes per launch at no cost in time),
+// bit 1 = a line is discarded from L2 once the backward has consumed it (10 MB with both, but 1.4 % slower: off).
+#ifndef DDP_QC_SCRATCH
+#define DDP_QC_SCRATCH 1
+#endif
+__device__ __forceinline__ void dscr_st(uint4* p, const uint4 w) { scratch_st<(DDP_QC_SCRATCH & 1) != 0>(p, w); }
+__device__ __forceinline__ uint4 dscr_ld(const uint4* p) { return scratch_ld<(DDP_QC_SCRATCH & 1) != 0>(p); }
+__device__ __forceinline__ void dscr_discard(const uint4* p, int lane, uint32_t loaded) {
+    if ((DDP_QC_SCRATCH & 2) && (lane & 7) == 0) scratch_discard(p, loaded);      // 8 rows x 16 bytes = one line
+}
+
 __device__ __forceinline__ void store_chunk16(uint8_t* slot, int row, int col0, const float (&x)[16]) {
 #pragma unroll
     for (int i8 = 0; i8 < 2; ++i8) {
@@ -190,13 +203,14 @@ __device__ __forceinline__ void emit_fwd(const QEpi& e, uint8_t* slot, const uin
     w0.x = pack_bf16x2(d[0], d[1]); w0.y = pack_bf16x2(d[2], d[3]); w0.z = pack_bf16x2(d[4], d[5]); w0.w = pack_bf16x2(d[6], d[7]);
     w1.x = pack_bf16x2(d[8], d[9]); w1.y = pack_bf16x2(d[10], d[11]); w1.z = pack_bf16x2(d[12], d[13]); w1.w = pack_bf16x2(d[14], d[15]);
     if (!(kAblate & 2)) {
-        __stcg(reinterpret_cast<uint4*>(dptr), w0);
-        __stcg(reinterpret_cast<uint4*>(dptr) + kRows, w1);
+        dscr_st(reinterpret_cast<uint4*>(dptr), w0);
+        dscr_st(reinterpret_cast<uint4*>(dptr) + kRows, w1);
     }
 }
 
 // backward: 16 accumulator columns * ELU' -> A chunk (bf16)
-__device__ __forceinline__ void emit_bwd(const QEpi& e, uint8_t* slot, const uint32_t (&v)[16], int col0, uint4 d0, uint4 d1) {
+__device__ __forceinline__ void emit_bwd(const QEpi& e, uint8_t* slot, const uint32_t (&v)[16], int col0, uint4 d0, uint4 d1,
+                                         const uint4* dp) {
     float x[16];
     const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
@@ -205,6 +219,8 @@ __device__ __forceinline__ void emit_bwd(const QEpi& e, uint8_t* slot, const uin
         x[2 * i + 1] = __uint_as_float(v[2 * i + 1]) * __uint_as_float(dw[i] & 0xffff0000u);
     }
     store_chunk16(slot, e.my_row, col0, x);
+    dscr_discard(dp, e.lane, d0.x);
+    dscr_discard(dp + kRows, e.lane, d1.x);
 }
 
 // Drain `nchunks` 64-column chunks of the accumulator at TMEM column `col` into the A ring.  This warp owns 32
@@ -224,8 +240,8 @@ __device__ __forceinline__ void q_drain(QEpi& e, int col, int nchunks, const flo
     if (!FWD) {
         const uint4* dp = reinterpret_cast<const uint4*>(dbase);
         if (!(kAblate & 2)) {
-            d0 = __ldcg(dp); d1 = __ldcg(dp + kRows);
-            if (kColsPerWarp == 32) { d2 = __ldcg(dp + kRows * 2); d3 = __ldcg(dp + kRows * 3); }
+            d0 = dscr_ld(dp); d1 = dscr_ld(dp + kRows);
+            if (kColsPerWarp == 32) { d2 = dscr_ld(dp + kRows * 2); d3 = dscr_ld(dp + kRows * 3); }
         }
     }
 #ifdef DDP_QC_FINE_TIMING
@@ -255,19 +271,19 @@ __device__ __forceinline__ void q_drain(QEpi& e, int col, int nchunks, const flo
                 rs.advance(kASlots);
                 if (kAblate & 16) { }
                 else if (FWD) emit_fwd(e, slot, va, bias + c * 64 + e.ch * 32, e.ch * 32, dptr);
-                else emit_bwd(e, slot, va, e.ch * 32, d0, d1);
+                else emit_bwd(e, slot, va, e.ch * 32, d0, d1, reinterpret_cast<const uint4*>(dptr));
                 QC_FINE(2);
                 if (!(kAblate & 8)) { tmem_ld_wait(); if (c + 1 < nchunks) tmem_ld16(tbase + (c + 1) * 64, va); }
                 QC_FINE(3);
                 if (kAblate & 16) { }
                 else if (FWD) emit_fwd(e, slot, vb, bias + c * 64 + e.ch * 32 + 16, e.ch * 32 + 16, dptr + kRows * 16);
                 else {
-                    emit_bwd(e, slot, vb, e.ch * 32 + 16, d2, d3);
+                    emit_bwd(e, slot, vb, e.ch * 32 + 16, d2, d3, reinterpret_cast<const uint4*>(dptr) + kRows * 2);
                     if (c + 1 < nchunks) {
                         const uint4* dp = reinterpret_cast<const uint4*>(dptr + (size_t)4 * kRows * 16);
                         if (!(kAblate & 2)) {
-                            d0 = __ldcg(dp); d1 = __ldcg(dp + kRows);
-                            d2 = __ldcg(dp + kRows * 2); d3 = __ldcg(dp + kRows * 3);
+                            d0 = dscr_ld(dp); d1 = dscr_ld(dp + kRows);
+                            d2 = dscr_ld(dp + kRows * 2); d3 = dscr_ld(dp + kRows * 3);
                         }
                     }
                 }
@@ -279,13 +295,13 @@ __device__ __forceinline__ void q_drain(QEpi& e, int col, int nchunks, const flo
                 uint4 e0 = d0, e1 = d1;
                 if (!FWD && c + 1 < nchunks) {
                     const uint4* dp = reinterpret_cast<const uint4*>(dptr + (size_t)4 * kRows * 16);
-                    d0 = __ldcg(dp); d1 = __ldcg(dp + kRows);
+                    d0 = dscr_ld(dp); d1 = dscr_ld(dp + kRows);
                 }
                 mbar_wait(qb_a_empty(e.bars, rs.idx), rs.phase ^ 1);
                 uint8_t* slot = e.smem + SMQ::aring + rs.idx * kChunkBytes;
                 rs.advance(kASlots);
                 if (FWD) emit_fwd(e, slot, u == 0 ? va : vb, bias + c * 64 + e.ch * 16, e.ch * 16, dptr);
-                else emit_bwd(e, slot, u == 0 ? va : vb, e.ch * 16, e0, e1);
+                else emit_bwd(e, slot, u == 0 ? va : vb, e.ch * 16, e0, e1, reinterpret_cast<const uint4*>(dptr));
             }
             QC_FINE_COUNT();
         }
@@ -779,6 +795,7 @@ int q_chain_pass(const QLayout& L, const void* packed, const int64_t* seg_off, c
                  size_t scratch_bytes, cudaStream_t st, const QChainAscent* asc) {
     if (!q_chain_shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "fused critic kernel does not support this shape");
     if (!scratch || scratch_bytes < q_chain_workspace(L)) DDP_FAIL(DDP_ERR_ARG, "fused critic kernel: scratch too small");
+    if ((DDP_QC_SCRATCH & 2) && ((uintptr_t)scratch & 127)) DDP_FAIL(DDP_ERR_ARG, "fused critic kernel: scratch must be 128-byte aligned");
     const uint8_t* pb = (const uint8_t*)packed;
     QcArgs a{};
     a.pk = (const float*)packed;
