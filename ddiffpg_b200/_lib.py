@@ -63,6 +63,10 @@ PROTOTYPES = {
     "ddp_q_action_ascent": (c_int, [POINTER(QShape), c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p,
                                     c_void_p, c_int, c_float, c_float, c_float, c_float, c_float, c_float, c_void_p,
                                     c_void_p, c_long, c_int, c_void_p, c_size_t, c_void_p]),
+    "ddp_q_action_ascent_sharded": (c_int, [POINTER(QShape), c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p,
+                                            c_void_p, c_int, c_float, c_float, c_float, c_float, c_float, c_float,
+                                            c_void_p, c_void_p, c_long, c_int, c_void_p, c_size_t, c_void_p, c_void_p,
+                                            c_void_p]),
     "ddp_q_grad_count": (c_size_t, [POINTER(QShape)]),
     "ddp_q_critic_train_workspace_bytes": (c_size_t, [POINTER(QShape), c_long, c_int]),
     "ddp_q_critic_loss_fwd_bwd": (c_int, [POINTER(QShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -86,6 +90,9 @@ PROTOTYPES = {
     "ddp_replay_scatter_target": (c_int, [POINTER(BatchShape), c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_long,
                                           c_void_p]),
 }
+
+# ddp_gsq_reduce_fn (include/ddiffpg_b200.h): int (*)(float* gsq_dev, int n_modes, void* stream, void* user)
+GSQ_REDUCE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_int, c_void_p, c_void_p)
 
 _lib = None
 

@@ -29,13 +29,20 @@ def _workspace(name, nbytes, dev):
 
 def q_action_ascent_segments(critics, obs, action, seg_off, iters=20, lr=0.03, eps=1e-5, max_norm=1.0,
                              betas=(0.9, 0.999), lim=1 - 1e-5, mean_counts=None, cache=None, return_norms=False,
-                             precision=None):
+                             precision=None, process_group=None, gsq_reduce=None):
     """Run the reference's action-ascent loop for several mode segments in one launch sequence.
 
     ``obs`` [B, O] / ``action`` [B, A] hold the rows of all modes, sorted by mode; ``seg_off`` (len
     n_modes+1) delimits them; ``critics[m]`` is the critic of mode m.  ``action`` is updated IN PLACE like
     the reference (ddiffpg.py:361-369).  Each segment is one reference call: its own 1/B_m in ``-Q.mean()``
     (or ``mean_counts[m]`` when the segment is a shard of a larger batch) and its own clip norm.
+
+    Row-sharded batches: by default every rank runs the reference on its own rows (shard-local semantics,
+    no collective).  With ``process_group`` (and ``mean_counts`` = the global rows per mode) the per-mode sum of g^2 is
+    all-reduced between the gradient pass and the Adam step of every iteration (K floats, ``ddp_q_action_ascent_sharded``),
+    so the clip norm is the one of the whole mode batch and the ranks take exactly the steps a single process would take
+    on the gathered batch; the returned mean|a| and norms are then global as well.  ``gsq_reduce(t)`` replaces the
+    all-reduce by any in-place reduction of the [n_modes] device tensor (tests, other transports).
     Returns (mean|a| per segment [n_modes] tensor, optional pre-clip norms [n_modes, iters])."""
     if max_norm is None:
         max_norm = float("inf")
@@ -53,7 +60,11 @@ def q_action_ascent_segments(critics, obs, action, seg_off, iters=20, lr=0.03, e
     counts = [seg_off[m + 1] - seg_off[m] for m in range(n_modes)] if mean_counts is None else list(mean_counts)
     mean_abs = torch.zeros(n_modes, device=dev)
     norms = torch.zeros(n_modes, iters, device=dev) if return_norms else None
-    if B:
+    if process_group is not None and gsq_reduce is None and ddist.world_info(process_group)[1] > 1:
+        if mean_counts is None:
+            raise ValueError("process_group needs mean_counts (the global rows per mode) for the 1/B factor")
+        gsq_reduce = lambda t: torch.distributed.all_reduce(t, group=process_group)          # noqa: E731
+    if B and gsq_reduce is None:
         with torch.cuda.device(dev):
             ws_bytes = lib().ddp_q_ascent_workspace_bytes(shape, B, iters)
             ws = _workspace("q_ascent", ws_bytes, dev)
@@ -61,6 +72,40 @@ def q_action_ascent_segments(critics, obs, action, seg_off, iters=20, lr=0.03, e
                                             ptr(obs), ptr(action), iters, lr, betas[0], betas[1], eps, max_norm,
                                             lim, ptr(mean_abs), ptr(norms), B, prec, ptr(ws), ws_bytes,
                                             stream_ptr()), "ddp_q_action_ascent")
+    elif B:
+        with torch.cuda.device(dev):
+            ws_bytes = lib().ddp_q_ascent_workspace_bytes(shape, B, iters)
+            ws = _workspace("q_ascent", ws_bytes, dev)
+            failure = []
+
+            def _reduce(gsq_dev, n, _stream, _user):
+                # the vector lives inside the workspace: hand it to torch as a view (the call runs on torch's current
+                # stream, so the reduction is ordered between the gradient pass and the Adam step)
+                try:
+                    off = int(gsq_dev) - ws.data_ptr()
+                    gsq_reduce(ws[off:off + 4 * n].view(torch.float32))
+                    return 0
+                except BaseException as exc:        # never unwind through the C frames
+                    failure.append(exc)
+                    return 1
+
+            cb = _lib.GSQ_REDUCE_FN(_reduce)
+            rc = lib().ddp_q_action_ascent_sharded(shape, ptr(packed), _lib.i64_array(seg_off), _lib.i64_array(counts),
+                                                   ptr(obs), ptr(action), iters, lr, betas[0], betas[1], eps, max_norm,
+                                                   lim, ptr(mean_abs), ptr(norms), B, prec, ptr(ws), ws_bytes,
+                                                   stream_ptr(), cb, None)
+            if failure:
+                raise failure[0]
+            check(rc, "ddp_q_action_ascent_sharded")
+    elif gsq_reduce is not None:
+        # a rank without rows still takes part in the exchange step of every iteration
+        for _ in range(iters):
+            gsq_reduce(torch.zeros(n_modes, device=dev))
+    if process_group is not None and ddist.world_info(process_group)[1] > 1:
+        local = torch.tensor([seg_off[m + 1] - seg_off[m] for m in range(n_modes)], dtype=torch.float32, device=dev)
+        tot = torch.stack([mean_abs * local, local])
+        torch.distributed.all_reduce(tot, group=process_group)
+        mean_abs = tot[0] / tot[1].clamp_min(1.0)
     return (mean_abs, norms) if return_norms else mean_abs
 
 

@@ -40,7 +40,8 @@ int q_forward_fma(const QLayout& L, const float* pk, const int64_t* seg_off, con
 size_t q_ascent_workspace(const QLayout& L, long B, int iters);
 int q_ascent_fma(const QLayout& L, const float* pk, const int64_t* seg_off, const int64_t* seg_cnt, const float* obs,
                  float* action, int iters, float lr, float b1, float b2, float eps, float max_norm, float lim,
-                 float* mean_abs, float* gnorm_out, long B, void* ws, size_t ws_bytes, cudaStream_t st);
+                 float* mean_abs, float* gnorm_out, long B, void* ws, size_t ws_bytes, cudaStream_t st,
+                 ddp_gsq_reduce_fn reduce, void* reduce_user);
 
 int pack_q_tc(const QLayout& L, const float* const p[], void* packed, cudaStream_t st);
 size_t q_tc_workspace(const QLayout& L, long B, int iters);
@@ -48,7 +49,8 @@ int q_forward_tc(const QLayout& L, const void* packed, const int64_t* seg_off, c
                  float* qmin, float* p1, float* p2, float* dq_da, long B, void* ws, size_t ws_bytes, cudaStream_t st);
 int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, const int64_t* seg_cnt, const float* obs,
                 float* action, int iters, float lr, float b1, float b2, float eps, float max_norm, float lim,
-                float* mean_abs, float* gnorm_out, long B, void* ws, size_t ws_bytes, cudaStream_t st);
+                float* mean_abs, float* gnorm_out, long B, void* ws, size_t ws_bytes, cudaStream_t st,
+                ddp_gsq_reduce_fn reduce, void* reduce_user);
 
 size_t q_critic_train_workspace(const QLayout& L, long B);
 size_t q_grad_count(const QLayout& L);
@@ -271,10 +273,11 @@ size_t ddp_q_ascent_workspace_bytes(const ddp_q_shape* s, long B, int iters) {
     return a > b ? a : b;
 }
 
-int ddp_q_action_ascent(const ddp_q_shape* s, const void* packed, const int64_t* seg_off,
-                        const int64_t* seg_mean_count, const float* obs, float* action_inout, int iters, float lr,
-                        float beta1, float beta2, float eps, float max_norm, float lim, float* mean_abs_out,
-                        float* gnorm_out, long B, int precision, void* ws, size_t ws_bytes, void* stream) {
+int ddp_q_action_ascent_sharded(const ddp_q_shape* s, const void* packed, const int64_t* seg_off,
+                                const int64_t* seg_mean_count, const float* obs, float* action_inout, int iters, float lr,
+                                float beta1, float beta2, float eps, float max_norm, float lim, float* mean_abs_out,
+                                float* gnorm_out, long B, int precision, void* ws, size_t ws_bytes, void* stream,
+                                ddp_gsq_reduce_fn reduce, void* reduce_user) {
     int rc = check_q_shape(s);
     if (rc != DDP_OK) return rc;
     if (B <= 0 || iters <= 0) DDP_FAIL(DDP_ERR_SHAPE, "ddp_q_action_ascent: B and iters must be positive");
@@ -286,10 +289,20 @@ int ddp_q_action_ascent(const ddp_q_shape* s, const void* packed, const int64_t*
     QLayout L = make_q_layout(*s, precision);
     if (precision == DDP_BF16)
         return q_ascent_tc(L, packed, seg_off, seg_mean_count, obs, action_inout, iters, lr, beta1, beta2, eps, max_norm,
-                           lim, mean_abs_out, gnorm_out, B, ws, ws_bytes, (cudaStream_t)stream);
+                           lim, mean_abs_out, gnorm_out, B, ws, ws_bytes, (cudaStream_t)stream, reduce, reduce_user);
     if (ws_bytes < q_ascent_workspace(L, B, iters)) DDP_FAIL(DDP_ERR_ARG, "ddp_q_action_ascent: workspace too small");
     return q_ascent_fma(L, (const float*)packed, seg_off, seg_mean_count, obs, action_inout, iters, lr, beta1, beta2,
-                        eps, max_norm, lim, mean_abs_out, gnorm_out, B, ws, ws_bytes, (cudaStream_t)stream);
+                        eps, max_norm, lim, mean_abs_out, gnorm_out, B, ws, ws_bytes, (cudaStream_t)stream, reduce,
+                        reduce_user);
+}
+
+int ddp_q_action_ascent(const ddp_q_shape* s, const void* packed, const int64_t* seg_off,
+                        const int64_t* seg_mean_count, const float* obs, float* action_inout, int iters, float lr,
+                        float beta1, float beta2, float eps, float max_norm, float lim, float* mean_abs_out,
+                        float* gnorm_out, long B, int precision, void* ws, size_t ws_bytes, void* stream) {
+    return ddp_q_action_ascent_sharded(s, packed, seg_off, seg_mean_count, obs, action_inout, iters, lr, beta1, beta2, eps,
+                                       max_norm, lim, mean_abs_out, gnorm_out, B, precision, ws, ws_bytes, stream, nullptr,
+                                       nullptr);
 }
 
 size_t ddp_q_grad_count(const ddp_q_shape* s) {

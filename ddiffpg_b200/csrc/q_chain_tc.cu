@@ -179,7 +179,9 @@ __device__ __forceinline__ void store_chunk16(uint8_t* slot, int row, int col0, 
     }
 }
 
-// forward: 16 accumulator columns -> +bias, ELU -> A chunk (bf16); ELU' -> scratch (bf16)
+// forward: 16 accumulator columns -> +bias, ELU -> A chunk (bf16); ELU' -> scratch (bf16) unless the launch has no
+// backward half (KEEP_D = false: ddp_q_forward, the target heads of the critic update)
+template <bool KEEP_D>
 __device__ __forceinline__ void emit_fwd(const QEpi& e, uint8_t* slot, const uint32_t (&v)[16], const float* bb,
                                          int col0, uint16_t* dptr) {
     float x[16], d[16];
@@ -199,6 +201,7 @@ __device__ __forceinline__ void emit_fwd(const QEpi& e, uint8_t* slot, const uin
         d[i] = neg ? d[i] : 1.f;
     }
     store_chunk16(slot, e.my_row, col0, x);
+    if (!KEEP_D) return;
     uint4 w0, w1;
     w0.x = pack_bf16x2(d[0], d[1]); w0.y = pack_bf16x2(d[2], d[3]); w0.z = pack_bf16x2(d[4], d[5]); w0.w = pack_bf16x2(d[6], d[7]);
     w1.x = pack_bf16x2(d[8], d[9]); w1.y = pack_bf16x2(d[10], d[11]); w1.z = pack_bf16x2(d[12], d[13]); w1.w = pack_bf16x2(d[14], d[15]);
@@ -226,7 +229,7 @@ __device__ __forceinline__ void emit_bwd(const QEpi& e, uint8_t* slot, const uin
 // Drain `nchunks` 64-column chunks of the accumulator at TMEM column `col` into the A ring.  This warp owns 32
 // columns of each chunk (two 16-column TMEM loads, the second in flight while the first is processed).
 // FWD: +bias, ELU, derivative to scratch group `g0 + ...`; else: times the derivative read back from there.
-template <bool FWD>
+template <bool FWD, bool KEEP_D = true>
 __device__ __forceinline__ void q_drain(QEpi& e, int col, int nchunks, const float* bias, int g0, int signal_after) {
     const uint32_t tbase = e.tmem_base + ((uint32_t)(e.q * 32) << 16) + col + e.ch * kColsPerWarp;
     // scratch group of this warp's first 16 columns inside chunk 0 (4 groups per chunk)
@@ -270,13 +273,13 @@ __device__ __forceinline__ void q_drain(QEpi& e, int col, int nchunks, const flo
                 uint8_t* slot = e.smem + SMQ::aring + rs.idx * kChunkBytes;
                 rs.advance(kASlots);
                 if (kAblate & 16) { }
-                else if (FWD) emit_fwd(e, slot, va, bias + c * 64 + e.ch * 32, e.ch * 32, dptr);
+                else if (FWD) emit_fwd<KEEP_D>(e, slot, va, bias + c * 64 + e.ch * 32, e.ch * 32, dptr);
                 else emit_bwd(e, slot, va, e.ch * 32, d0, d1, reinterpret_cast<const uint4*>(dptr));
                 QC_FINE(2);
                 if (!(kAblate & 8)) { tmem_ld_wait(); if (c + 1 < nchunks) tmem_ld16(tbase + (c + 1) * 64, va); }
                 QC_FINE(3);
                 if (kAblate & 16) { }
-                else if (FWD) emit_fwd(e, slot, vb, bias + c * 64 + e.ch * 32 + 16, e.ch * 32 + 16, dptr + kRows * 16);
+                else if (FWD) emit_fwd<KEEP_D>(e, slot, vb, bias + c * 64 + e.ch * 32 + 16, e.ch * 32 + 16, dptr + kRows * 16);
                 else {
                     emit_bwd(e, slot, vb, e.ch * 32 + 16, d2, d3, reinterpret_cast<const uint4*>(dptr) + kRows * 2);
                     if (c + 1 < nchunks) {
@@ -300,7 +303,7 @@ __device__ __forceinline__ void q_drain(QEpi& e, int col, int nchunks, const flo
                 mbar_wait(qb_a_empty(e.bars, rs.idx), rs.phase ^ 1);
                 uint8_t* slot = e.smem + SMQ::aring + rs.idx * kChunkBytes;
                 rs.advance(kASlots);
-                if (FWD) emit_fwd(e, slot, u == 0 ? va : vb, bias + c * 64 + e.ch * 16, e.ch * 16, dptr);
+                if (FWD) emit_fwd<KEEP_D>(e, slot, u == 0 ? va : vb, bias + c * 64 + e.ch * 16, e.ch * 16, dptr);
                 else emit_bwd(e, slot, u == 0 ? va : vb, e.ch * 16, e0, e1, reinterpret_cast<const uint4*>(dptr));
             }
             QC_FINE_COUNT();
@@ -320,6 +323,7 @@ __device__ __forceinline__ void q_drain(QEpi& e, int col, int nchunks, const flo
 #undef QC_FINE_COUNT
 }
 
+template <bool BWD>
 #if DDP_QC_EPI_WARPS >= 16
 // 18 warps: ptxas would round the block up to 640 threads and cap at 96 registers
 __global__ void __maxnreg__(96)
@@ -327,6 +331,7 @@ __global__ void __maxnreg__(96)
 __global__ void __launch_bounds__(kThreads, 1)
 #endif
 q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
+    // BWD = false: the forward half alone (g_out == NULL) -- no ELU' scratch, none of the backward stages in the image
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -334,7 +339,7 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
     const uint32_t bars = base + SMQ::bars;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NC1 = a.h1 >> 6, NC2 = a.h2 >> 6, NC3 = a.h3 >> 6;
-    const bool backward = a.g_out != nullptr;
+    const bool backward = BWD && a.g_out != nullptr;     // (runtime in the BWD image: keeps its register allocation)
     // B2 in two halves (h1 = 2 x 256 column parts): the part above h2 is complete as soon as the last dz2 chunk has been
     // multiplied, so its chunks are drained while the part that overlaps the B3 accumulator is still being multiplied.
     // The action-gradient accumulator (Ba) then lives in drained columns of the upper part, clear of the next net's B4
@@ -555,13 +560,13 @@ q_chain_tc_kernel(const __grid_constant__ QcMaps maps, const QcArgs a) {
                 QC_TICK(0);
                 e.wait_acc();
                 QC_TICK(1);
-                q_drain<true>(e, 0, NC1, sb, g1, NC2 - 1);          // F1 accumulator -> a1 chunks
+                q_drain<true, BWD>(e, 0, NC1, sb, g1, NC2 - 1);          // F1 accumulator -> a1 chunks
                 QC_TICK(2);
                 e.wait_acc();
-                q_drain<true>(e, 0, NC2, sb + 512, g2, -1);         // F2 -> a2
+                q_drain<true, BWD>(e, 0, NC2, sb + 512, g2, -1);         // F2 -> a2
                 QC_TICK(3);
                 e.wait_acc();
-                q_drain<true>(e, a.h2, NC3, sb + 768, g3, -1);      // F3 -> a3
+                q_drain<true, BWD>(e, a.h2, NC3, sb + 768, g3, -1);      // F3 -> a3
                 QC_TICK(4);
                 if (e.ch == 0) {
                     // logits -> softmax, expectation, d Q / d logits (unmasked) for this thread's row
@@ -849,16 +854,20 @@ int q_chain_pass(const QLayout& L, const void* packed, const int64_t* seg_off, c
     DDP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (sms > 160) sms = 160;
     const size_t smem = SMQ::total + 1024;
-    DDP_CUDA_CHECK(cudaFuncSetAttribute(q_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool bwd = g_out != nullptr;
+    if (asc && !bwd) DDP_FAIL(DDP_ERR_ARG, "fused ascent needs the gradient buffer");
+    DDP_CUDA_CHECK(cudaFuncSetAttribute(bwd ? q_chain_tc_kernel<true> : q_chain_tc_kernel<false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = a.num_tiles < sms ? a.num_tiles : sms;
     if (asc) {
         // the grid barrier needs every CTA resident at once: cooperative launch, one CTA per SM
         void* kargs[2] = {(void*)&maps, (void*)&a};
-        cudaError_t err = cudaLaunchCooperativeKernel((const void*)q_chain_tc_kernel, dim3(grid), dim3(kThreads), kargs, smem, st);
+        cudaError_t err = cudaLaunchCooperativeKernel((const void*)q_chain_tc_kernel<true>, dim3(grid), dim3(kThreads), kargs, smem, st);
         if (err != cudaSuccess) DDP_FAIL(DDP_ERR_CUDA, "cooperative launch of q_chain_tc_kernel failed: %s", cudaGetErrorString(err));
         return DDP_OK;
     }
-    q_chain_tc_kernel<<<grid, kThreads, smem, st>>>(maps, a);
+    if (bwd) q_chain_tc_kernel<true><<<grid, kThreads, smem, st>>>(maps, a);
+    else q_chain_tc_kernel<false><<<grid, kThreads, smem, st>>>(maps, a);
     DDP_LAUNCH_CHECK("q_chain_tc_kernel");
     return DDP_OK;
 }

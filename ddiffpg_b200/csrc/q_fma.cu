@@ -537,7 +537,8 @@ size_t q_ascent_workspace(const QLayout& L, long B, int iters) {
 
 int q_ascent_fma(const QLayout& L, const float* pk, const int64_t* seg_off, const int64_t* seg_cnt, const float* obs,
                  float* action, int iters, float lr, float b1, float b2, float eps, float max_norm, float lim,
-                 float* mean_abs, float* gnorm_out, long B, void* ws, size_t ws_bytes, cudaStream_t st) {
+                 float* mean_abs, float* gnorm_out, long B, void* ws, size_t ws_bytes, cudaStream_t st,
+                 ddp_gsq_reduce_fn reduce, void* reduce_user) {
     const size_t n = align_up((size_t)B * L.A, 64);
     float* g = (float*)ws;
     float* m1 = g + n;
@@ -558,6 +559,9 @@ int q_ascent_fma(const QLayout& L, const float* pk, const int64_t* seg_off, cons
                        : launch_q_tile<16, 1>(L, pk, seg, tiles, obs, action, nullptr, nullptr, nullptr, g,
                                              gsq + (size_t)it * kMaxModes, st);
         if (rc != DDP_OK) return rc;
+        // row-sharded batch: the clip norm is the norm over ALL ranks' rows of the mode (semantics (ii))
+        if (reduce && reduce(gsq + (size_t)it * kMaxModes, L.n_modes, (void*)st, reduce_user) != 0)
+            DDP_FAIL(DDP_ERR_ARG, "ddp_q_action_ascent_sharded: the reduce callback failed in iteration %d", it);
         const int step = it + 1;
         const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
         q_adam_kernel<<<eb, 256, 0, st>>>(seg, L.A, action, g, m1, m2, gsq + (size_t)it * kMaxModes, gnorm_out, it,

@@ -357,7 +357,8 @@ int q_forward_tc(const QLayout& L, const void* packed, const int64_t* seg_off, c
 
 int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, const int64_t* seg_cnt, const float* obs,
                 float* action, int iters, float lr, float b1, float b2, float eps, float max_norm, float lim,
-                float* mean_abs, float* gnorm_out, long B, void* ws, size_t ws_bytes, cudaStream_t st) {
+                float* mean_abs, float* gnorm_out, long B, void* ws, size_t ws_bytes, cudaStream_t st,
+                ddp_gsq_reduce_fn reduce, void* reduce_user) {
     if (!shape_ok(L)) DDP_FAIL(DDP_ERR_UNSUPPORTED, "DDP_BF16 critic path does not support this shape");
     if (ws_bytes < carve(L, B, iters, nullptr).total) DDP_FAIL(DDP_ERR_ARG, "critic tensor path: workspace too small");
     QTcWs w = carve(L, B, iters, (uint8_t*)ws);
@@ -375,7 +376,8 @@ int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, co
     // 4.33 ms at 65 536: the stream hides the launches).
     long tiles = 0;
     for (int m = 0; m < L.n_modes; ++m) tiles += (seg_off[m + 1] - seg_off[m] + 127) / 128;
-    const bool fused = g_q_fused_adam >= 0 ? g_q_fused_adam != 0 : tiles <= 64;
+    // (an exchange step between the gradient and the Adam step needs the per-iteration form)
+    const bool fused = !reduce && (g_q_fused_adam >= 0 ? g_q_fused_adam != 0 : tiles <= 64);
     if (chain && fused && iters >= 1 && iters <= 32) {
         QChainAscent asc{iters, action, w.m1, w.m2, gnorm_out, w.grid_bar, lr, b1, b2, eps, max_norm, lim};
         int rc = q_chain_pass(L, packed, seg_off, neg_inv, w.xin, w.g, w.gsq, nullptr, nullptr, nullptr, B,
@@ -394,6 +396,9 @@ int q_ascent_tc(const QLayout& L, const void* packed, const int64_t* seg_off, co
             if (rc != DDP_OK) return rc;
             q_tc_grad_kernel<<<nb, 256, 0, st>>>(seg, w.ga[0], w.ga[1], L.A, n, 1, w.g, gsq);
         }
+        // row-sharded batch: the clip norm is the norm over ALL ranks' rows of the mode (semantics (ii))
+        if (reduce && reduce(gsq, L.n_modes, (void*)st, reduce_user) != 0)
+            DDP_FAIL(DDP_ERR_ARG, "ddp_q_action_ascent_sharded: the reduce callback failed in iteration %d", it);
         const int step = it + 1;
         const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
         q_tc_adam_kernel<<<nb, 256, 0, st>>>(seg, L.O, L.A, action, w.g, w.m1, w.m2, gsq, gnorm_out, it, iters,

@@ -172,6 +172,21 @@ int ddp_q_action_ascent(const ddp_q_shape* shape, const void* packed, const int6
                         float lim, float* mean_abs_out, float* gnorm_out, long B, int precision,
                         void* ws, size_t ws_bytes, void* stream);
 
+/* The same loop on a ROW-SHARDED batch with global-batch semantics (SURVEY.md 8e, H2 semantics (ii); the reference
+ * itself is single-process): every rank holds a slice of each mode segment, passes the GLOBAL mode batch as
+ * seg_mean_count[m], and `reduce` is the one exchange step of an iteration -- called between the gradient pass and the
+ * Adam step with the device vector gsq_dev[n_modes] = sum of g^2 over THIS rank's rows of each mode; it must replace it by
+ * the sum over all ranks, in stream order on `stream` (ncclAllReduce, torch.distributed.all_reduce, ...), and return 0.
+ * The clip coefficient of ac_base.py:87-88 then comes from the norm over the whole mode batch, so the sharded ranks take
+ * exactly the steps one process would take on the gathered batch.  gnorm_out receives the global norms; mean_abs_out
+ * stays the mean over this rank's rows.  reduce == NULL is ddp_q_action_ascent (shard-local norm). */
+typedef int (*ddp_gsq_reduce_fn)(float* gsq_dev, int n_modes, void* stream, void* user);
+int ddp_q_action_ascent_sharded(const ddp_q_shape* shape, const void* packed, const int64_t* seg_off,
+                                const int64_t* seg_mean_count, const float* obs, float* action_inout,
+                                int iters, float lr, float beta1, float beta2, float eps, float max_norm,
+                                float lim, float* mean_abs_out, float* gnorm_out, long B, int precision,
+                                void* ws, size_t ws_bytes, void* stream, ddp_gsq_reduce_fn reduce, void* reduce_user);
+
 /* ----------------------------------------------------------------------------------------------
  * Critic update.  Replaces the loss/backward half of AgentDDiffPG.update_critic
  * (ddiffpg/algo/ddiffpg.py:322-351) for ONE critic (shape->n_modes must be 1):

@@ -2,8 +2,10 @@
 Checks, on the real kernels: (1) all-reduced shard gradients == gradient of the gathered batch, (2) the sharded
 trainer walks the trajectory of a single-process trainer on the full batch, (3) replicas stay bit-identical,
 (4) CUDA-graph replay with the captured, overlapped all-reduce == eager steps, (5) the critic update's data-parallel form
-(update_critic(process_group=...)) == the single-process update on the gathered batch, replicas identical, (6) the process
-group tears down with the trainer closed.  Exit code 0 = all checks passed on this rank."""
+(update_critic(process_group=...)) == the single-process update on the gathered batch, replicas identical, (6) the
+row-sharded action ascent with the per-iteration all-reduce of the clip norm (SURVEY 8e, H2 semantics (ii)) == the ascent of
+one process on the gathered, mode-sorted batch, (7) the process group tears down with the trainer closed.
+Exit code 0 = all checks passed on this rank."""
 import os
 import sys
 
@@ -14,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import port                                   # noqa: E402
 from ddiffpg_b200 import (DiffusionPolicy, DistributionalDoubleQ, FusedActorTrainer, FusedCriticTrainer,   # noqa: E402
-                          update_critic)
+                          q_action_ascent_segments, update_critic)
 from ddiffpg_b200 import dist as ddist                    # noqa: E402
 
 
@@ -122,9 +124,40 @@ def main():
         assert all(torch.equal(allc[0], c) for c in allc), f"fused critic {precision}: replicas diverged"
         ftr.close()
         fref.close()
+    # (6) H2, global-batch semantics: every rank holds a slice of each mode segment; with the K-float all-reduce of sum g^2
+    # per iteration the ranks take the steps one process takes on the gathered batch (clip active in the second pass: max_norm = 1e-4)
+    ga = torch.Generator().manual_seed(31)
+    seg_off = [0, 1000, 1000 + 1700, 1000 + 1700 + 372]     # three modes, ragged, the last shorter than a tile per rank
+    Bq = seg_off[-1]
+    q_obs, q_act = torch.randn(Bq, 29, generator=ga).to(dev), (torch.rand(Bq, 8, generator=ga) * 2 - 1).to(dev)
+    critics = [critic(port.init_critic_params(40 + m)).requires_grad_(False) for m in range(3)]
+    pairs, local_off, counts = ddist.shard_segments(seg_off, world, rank)
+    rows = torch.cat([torch.arange(a, b) for a, b in pairs]).to(dev)
+    for precision, tol in (("fp32", 2e-5), ("bf16", 2e-3)):
+        for max_norm in (1.0, 1e-4):
+            whole = q_act.clone()
+            ma_ref, n_ref = q_action_ascent_segments(critics, q_obs, whole, seg_off, iters=20, max_norm=max_norm,
+                                                     precision=precision, return_norms=True)
+            part = q_act[rows].contiguous()
+            ma_sh, n_sh = q_action_ascent_segments(critics, q_obs[rows].contiguous(), part, local_off, iters=20,
+                                                   max_norm=max_norm, precision=precision, return_norms=True,
+                                                   mean_counts=counts, process_group=dist.group.WORLD)
+            assert (n_sh / n_ref - 1).abs().max().item() <= 10 * tol, (precision, max_norm, "norms", n_sh, n_ref)
+            assert (ma_sh - ma_ref).abs().max().item() <= 10 * tol, (precision, max_norm, ma_sh, ma_ref)
+            d = (part - whole[rows]).abs()
+            if precision == "fp32":
+                assert d.max().item() <= 1e-4, (precision, max_norm, d.max().item())
+            else:       # identical arithmetic per row; only the fp32 atomics of the norm land in a different order
+                assert d.mean().item() <= 1e-4 and (d > 1e-2).float().mean().item() <= 1e-3, (precision, max_norm, d.mean().item())
+            # without the exchange step the shard-local norm differs (the clip is active at max_norm = 1e-4)
+            if max_norm < 1.0:
+                loc = q_act[rows].contiguous()
+                q_action_ascent_segments(critics, q_obs[rows].contiguous(), loc, local_off, iters=20, max_norm=max_norm,
+                                         precision=precision, mean_counts=counts)
+                assert (loc - whole[rows]).abs().max().item() > 1e-3, "the clip was not active: the test does not discriminate"
     torch.cuda.synchronize()
     dist.barrier()
-    dist.destroy_process_group()                          # (6)
+    dist.destroy_process_group()                          # (7)
     print(f"rank {rank}: ok", flush=True)
 
 

@@ -64,6 +64,50 @@ def test_gradient_allreduce_equals_full_batch_gloo(tmp_path):
         assert open(tmp_path / f"ok{r}").read() == "True"
 
 
+def _ascent_worker(rank, world, port_no, tmp):
+    """The contract of ddp_q_action_ascent_sharded (SURVEY 8e, H2 semantics (ii)) restated with torch on each rank's
+    shard: gradient of -sum(q_min) / B_global, sum g^2 all-reduced, the reference's clip coefficient and Adam step --
+    must equal the oracle port's ascent of the gathered batch (here with the clip active)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import port
+    torch.set_num_threads(2)
+    gen = torch.Generator().manual_seed(17)
+    B, iters, lr, eps, max_norm, lim = 23, 6, 0.03, 1e-5, 0.01, 1 - 1e-5
+    p = port.init_critic_params(8, scale=2.0)
+    obs, act = torch.randn(B, 29, generator=gen), torch.rand(B, 8, generator=gen) * 2 - 1
+    _, a_ref, n_ref, _ = port.q_action_ascent(p, obs, act.clone(), iters=iters, lr=lr, eps=eps, max_norm=max_norm,
+                                              return_trace=True)
+    (lo, hi), = ddist.shard_segments([0, B], world, rank)[0]
+    a = act[lo:hi].clone().clamp_(-lim, lim)
+    opt = torch.optim.Adam([a], lr=lr, eps=eps)
+    norms = []
+    for _ in range(iters):
+        a.requires_grad_(True)
+        loss = -port.q_min({k: v.detach() for k, v in p.items()}, obs[lo:hi], a, 0.0, 5.0).sum() / B      # global 1/B
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        gsq = (a.grad.double() ** 2).sum().reshape(1)
+        dist.all_reduce(gsq)                                                                        # the exchange step
+        norm = gsq.sqrt().float()
+        a.grad.mul_(torch.clamp(max_norm / (norm + 1e-6), max=1.0))                                 # clip_grad_norm_
+        norms.append(norm)
+        opt.step()
+        a.requires_grad_(False)
+        a.clamp_(-lim, lim)
+    ok = bool(torch.allclose(a, a_ref[lo:hi], atol=2e-6) and torch.allclose(torch.cat(norms), n_ref, rtol=1e-5)
+              and n_ref.min().item() > max_norm)
+    open(os.path.join(tmp, f"ok{rank}"), "w").write(str(ok))
+    dist.destroy_process_group()
+
+
+def test_sharded_ascent_with_norm_exchange_equals_gathered_batch_gloo(tmp_path):
+    world = 2
+    mp.spawn(_ascent_worker, args=(world, 29643, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"ok{r}").read() == "True"
+
+
 def test_host_batch_ranges_cover_the_batch_in_whole_waves():
     """Ranges of get_actions_host: contiguous cover of [0, B), one range below 8k rows per range; below three sampler
     waves (sms x 128 rows) the partial wave first and whole waves behind it, never more than `chunks` ranges; from three

@@ -182,6 +182,11 @@ def test_abi_argument_errors_without_gpu(built_lib):
     assert L.ddp_rnd_packed_bytes_p(_lib.RndShape(69, 128, 500, 256, 128), 1) == 0        # ... widths multiples of 64
     assert L.ddp_rnd_packed_bytes_p(_lib.RndShape(69, 128, 500, 256, 128), 0) > 0         # the FMA path takes them
     assert L.ddp_rnd_novelty_p(r, None, None, None, None, None, 4, 1, None, 0, None) == -2
+    # the row-sharded ascent (exchange-step callback): argument checks are the plain entry point's
+    common = (None, None, None, 20, 0.03, 0.9, 0.999, 1e-5, 1.0, 0.99999, None, None)
+    assert L.ddp_q_action_ascent_sharded(q, None, None, *common, 8, 0, None, 0, None, None, None) == -2
+    assert L.ddp_q_action_ascent_sharded(q, None, None, *common, 0, 0, None, 0, None, None, None) == -1
+    assert L.ddp_q_action_ascent(q, None, None, *common, 8, 0, None, 0, None) == -2
 
 
 # ------------------------------------------------------------------ host mirror of the reference surface

@@ -179,6 +179,70 @@ def test_q_ascent_mode_segments_equal_separate_calls():
     assert_close(mean_abs, means, 1e-4, 1e-5 + 0.6 * n_ridge / 5, "mean|a| per mode")
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_q_ascent_sharded_exchange_step(precision):
+    """ddp_q_action_ascent_sharded (SURVEY 8e, H2 semantics (ii)) on one GPU: (a) an identity exchange step reproduces the
+    plain call; (b) a rank that holds X of the two-rank batch [X; X] -- global count 2 B, the other rank's sum g^2 equal to
+    its own, so the exchange step doubles it -- takes exactly the steps the first half of [X; X] takes in one process
+    (clip active: max_norm = 1e-4); (c) a failing exchange step surfaces as the Python exception it raised.
+    The tensor path is pinned to its per-iteration schedule for the comparison (the single-launch form of small batches
+    differs on a few ridge rows, tests/test_tc_gpu.py::test_q_chain_variants_agree); what remains is the order of the
+    fp32 atomics in the norm."""
+    import ctypes
+    from ddiffpg_b200 import _lib, q_action_ascent_segments
+    gen = torch.Generator().manual_seed(77)
+    sizes = [300, 0, 213]
+    off = np.concatenate([[0], np.cumsum(sizes)]).tolist()
+    B = off[-1]
+    critics = [make_critic(port.init_critic_params(80 + i, scale=1.5)) for i in range(3)]
+    obs, act = _dev(torch.randn(B, 29, generator=gen)), _dev(torch.rand(B, 8, generator=gen) * 2 - 1)
+
+    def same(x, y, what):
+        d = (x - y).abs()
+        if precision == "fp32":
+            assert d.max().item() <= 2e-5, (what, d.max().item())
+        else:
+            bad = (d.max(1).values > 1e-3).float().mean().item()
+            assert bad <= 0.01 and d.mean().item() <= 2e-4, (what, bad, d.mean().item())
+
+    dbg = _lib.lib().ddp_debug_q_variant
+    dbg.argtypes, dbg.restype = [ctypes.c_int, ctypes.c_int], None
+    dbg(0, 0)
+    try:
+        for max_norm in (1.0, 1e-4):
+            plain, ident = act.clone(), act.clone()
+            m0, n0 = q_action_ascent_segments(critics, obs, plain, off, iters=20, max_norm=max_norm, precision=precision,
+                                              return_norms=True)
+            calls = []
+            m1, n1 = q_action_ascent_segments(critics, obs, ident, off, iters=20, max_norm=max_norm, precision=precision,
+                                              return_norms=True, gsq_reduce=lambda t: calls.append(tuple(t.shape)))
+            assert calls == [(3,)] * 20
+            same(ident, plain, f"identity exchange step, max_norm={max_norm}")
+            assert (n1[[0, 2]] / n0[[0, 2]] - 1).abs().max().item() <= 1e-3
+            assert_close(m1, m0, 1e-3, 1e-4, "mean|a|")
+        # (b) the two-rank batch [X; X], mode-sorted: every segment twice as long
+        obs2 = torch.cat([torch.cat([obs[off[m]:off[m + 1]]] * 2) for m in range(3)])
+        act2 = torch.cat([torch.cat([act[off[m]:off[m + 1]]] * 2) for m in range(3)])
+        off2 = [2 * o for o in off]
+        q_action_ascent_segments(critics, obs2, act2, off2, iters=20, max_norm=1e-4, precision=precision)
+        first_half = torch.cat([act2[off2[m]:off2[m] + sizes[m]] for m in range(3)])
+        shard = act.clone()
+        q_action_ascent_segments(critics, obs, shard, off, iters=20, max_norm=1e-4, precision=precision,
+                                 mean_counts=[2 * n for n in sizes], gsq_reduce=lambda t: t.mul_(2.0))
+        same(shard, first_half, "doubled exchange step vs [X; X]")
+        local = act.clone()                               # shard-local norm instead: visibly different steps
+        q_action_ascent_segments(critics, obs, local, off, iters=20, max_norm=1e-4, precision=precision,
+                                 mean_counts=[2 * n for n in sizes])
+        assert (local - first_half).abs().mean().item() > 1e-3
+    finally:
+        dbg(0, -1)
+
+    def boom(t):
+        raise KeyError("exchange step failed")
+    with pytest.raises(KeyError):
+        q_action_ascent_segments(critics, obs, act.clone(), off, iters=3, precision=precision, gsq_reduce=boom)
+
+
 # ------------------------------------------------------------------------------------------ H3
 def _flat(grads):
     return torch.cat([grads[k].reshape(-1) for k in port.ACTOR_KEYS])
