@@ -349,8 +349,15 @@ def setup_ascent(cx, rows):
         q_action_ascent_segments(critics, o, w, seg, iters=20, cache=cache, precision=args.precision)
         out_h.copy_(w, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+    def step_global():
+        # the same rows as a slice of a world x larger mode-sorted batch: global 1/B and the clip norm of the whole mode
+        # batch through the K-float exchange step of every iteration (ddp_q_action_ascent_sharded)
+        work.copy_(act0)
+        return q_action_ascent_segments(critics, obs, work, seg, iters=20, cache=cache, precision=args.precision,
+                                        mean_counts=[(seg[m + 1] - seg[m]) * cx.world for m in range(K)],
+                                        process_group=cx.dist.group.WORLD, return_norms=True)
     return {"step": step, "e2e": e2e_step, "launches": 2 + 20 * 2 + 2, "h2d": (obs_h.numel() + act_h.numel()) * 4,
-            "d2h": out_h.numel() * 4, "params": params, "keep": (critics, obs, work)}
+            "d2h": out_h.numel() * 4, "params": params, "keep": (critics, obs, work), "step_global": step_global}
 
 
 def setup_train(cx, rows):
@@ -506,6 +513,25 @@ def train_collective_report(cx, leg, rows, steps):
     return out
 
 
+def ascent_exchange_report(cx, leg, steps, ms_local_per_step):
+    """H2 under torchrun: the default is shard-local semantics (no collective, the timed line); this times the same rows
+    with global-batch semantics -- 20 all-reduces of K floats per ascent, one between every gradient pass and Adam step --
+    and checks that every rank saw the same global norms."""
+    torch, dist = cx.torch, cx.dist
+    step = leg["step_global"]
+    for _ in range(3):
+        step()
+    cx.barrier()
+    ms = cx.max_over_ranks([cx.timed(step, steps)])[0] / steps
+    _, norms = step()
+    allc = [torch.zeros_like(norms) for _ in range(cx.world)]
+    dist.all_gather(allc, norms)
+    return {"default_semantics": "shard-local (no collective)", "global_batch_ms_per_step": ms,
+            "exchange_steps_per_ascent": 20, "exchange_floats": int(norms.shape[0]),
+            "exposed_us_per_exchange": (ms - ms_local_per_step) * 1e3 / 20,
+            "global_norms_identical_on_all_ranks": all(torch.equal(allc[0], c) for c in allc)}
+
+
 def run_leg(cx, workload, rows, steps, want_cpu, with_configs0, cpu_budget_s):
     """Set one workload up, time its device-resident and end-to-end forms, and describe it as a dict."""
     torch, args = cx.torch, cx.args
@@ -542,6 +568,8 @@ def run_leg(cx, workload, rows, steps, want_cpu, with_configs0, cpu_budget_s):
     if workload == "train" and cx.world > 1:
         extra = train_collective_report(cx, leg, rows, steps)
         extra["exposed_us"] = (ms / steps - extra["local_ms_per_step"]) * 1e3
+    if workload == "ascent" and cx.world > 1:
+        extra = ascent_exchange_report(cx, leg, steps, ms / steps)
     if "trainer" in leg:
         leg["trainer"].close()            # graphs that captured the all-reduce go before the process group does
     if cx.rank != 0:
