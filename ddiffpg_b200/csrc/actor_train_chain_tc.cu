@@ -93,9 +93,33 @@ struct FRing {
 // Mish and its derivative, N values: with e = exp(x), s = e + 1, p = s^2 + 1, r = 1/p:
 //   mish(x) = x (1 - 2r),  mish'(x) = (1 - 2r) + 4 x e s r^2        (one ex2 + one rcp per element)
 // the exponent is capped at x = 20 (mish = x, mish' = 1 to fp32 there; e s r^2 stays finite)
+// DDP_FC_MISH_V2 (default): the same two functions with the exponent shifted by +1/2 (E = sqrt2 e^x, v = (e^x + 1)/sqrt2
+// and q = v^2 + 1/2 = p/2 each cost one FFMA; r = 1/q = 2/p, mish = x (1 - r), mish' = (1 - r) + x (E v) r^2):
+// 11.5 FP32 + 1.5 MUFU instructions per element instead of 13.5 + 1.5 (training step 0.986 -> 0.979 ms at 131 072 rows,
+// A B A B in one call; fp32 error of both functions unchanged, <= 2e-6 absolute).  0 keeps the first form below.
+#ifndef DDP_FC_MISH_V2
+#define DDP_FC_MISH_V2 1
+#endif
 template <int N>
 __device__ __forceinline__ void mish_fd_n(float (&x)[N], float (&d)[N]) {
     float e[N];
+    if (DDP_FC_MISH_V2) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) e[i] = ex2_approx(fminf(fmaf(x[i], kLog2e, 0.5f), 29.353900817779268f));
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            const float v0 = fmaf(e[i], 0.5f, 0.70710678118654752f), v1 = fmaf(e[i + 1], 0.5f, 0.70710678118654752f);
+            const float q0 = fmaf(v0, v0, 0.5f), q1 = fmaf(v1, v1, 0.5f);
+            const float r = rcp_approx(q0 * q1);
+            const float r0 = r * q1, r1 = r * q0;
+            const float w0 = 1.f - r0, w1 = 1.f - r1;
+            d[i] = fmaf(x[i], (e[i] * v0) * (r0 * r0), w0);
+            d[i + 1] = fmaf(x[i + 1], (e[i + 1] * v1) * (r1 * r1), w1);
+            x[i] *= w0;
+            x[i + 1] *= w1;
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) e[i] = ex2_approx(fminf(x[i] * kLog2e, 28.853900817779268f));
     // one MUFU.RCP per two elements: 1/p0, 1/p1 = r p1, r p0 with r = rcp(p0 p1) (p <= e^40 + ..., the product stays
